@@ -1,0 +1,105 @@
+"""CPU, build container only: run the UNMODIFIED reference (via oracle/ref_shim.py) and the
+NumPy oracle side by side on live RandomState streams consumed in the same order.  Skipped
+where /root/reference does not exist (the GPU box) -- tests/test_oracle_golden.py covers that."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import hamiltonian_oracle as O
+from oracle.ref_shim import load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        yield
+
+
+def data(n=150, d=20, k=6, seed=0):
+    rs = np.random.RandomState(seed)
+    X = rs.rand(n, d)
+    y = rs.randint(0, k, n)
+    return X, y, O.one_hot(y, k)
+
+
+def test_hmc_sample_softmax_live():
+    ref = load_reference()
+    X, y, Y = data()
+    rs = np.random.RandomState(1)
+    start = {"weights": rs.normal(0, .05, (20, 6)), "bias": rs.normal(0, .05, 6)}
+    s = ref.hmc(ref.softmax({"alpha": 0.1}), {k: v.copy() for k, v in start.items()},
+                path_length=1e-2, step_size=1e-3, verbose=False)
+    np.random.seed(123)
+    with quiet():
+        post, loss, _, _ = s.sample(niter=15, burnin=5, rng=np.random.RandomState(77), X_train=X, y_train=Y)
+    draws = O.StreamDraws(np.random.RandomState(77), np.random.RandomState(123))
+    opost, oloss, info = O.hmc_sample(O.SoftmaxOracle({"alpha": 0.1}), start, 1e-3, 1e-2, 15, 5, draws,
+                                      X_train=X, y_train=Y)
+    np.testing.assert_allclose(opost["weights"], post["weights"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(opost["bias"], post["bias"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(oloss, loss, rtol=1e-12)
+    assert len(np.unique(loss)) > 3  # the chain really moved
+
+
+@pytest.mark.parametrize("sampler", ["sgld", "sgd"])
+def test_minibatch_drivers_live(sampler):
+    ref = load_reference()
+    X, y, Y = data(n=210)
+    start = {"weights": np.zeros((20, 6)), "bias": np.zeros(6)}
+    if sampler == "sgld":
+        s = ref.sgld(ref.softmax({"alpha": 0.1}), {k: v.copy() for k, v in start.items()}, step_size=5e-3, verbose=False)
+        with quiet():
+            post, logp = s.sample(epochs=3, burnin=2, batch_size=50, rng=np.random.RandomState(5), X_train=X, y_train=Y)
+        draws = O.StreamDraws(np.random.RandomState(5), np.random.RandomState(0))
+        opost, ologp, _ = O.sgmcmc_sample(O.sgld_step, O.SoftmaxOracle({"alpha": 0.1}), start, 5e-3, 3, 2, 50, draws, X, Y)
+        np.testing.assert_allclose(opost["weights"], post["weights"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(ologp, logp, rtol=1e-12)
+    else:
+        s = ref.sgd(ref.softmax({"alpha": 0.1}), {k: v.copy() for k, v in start.items()}, step_size=5e-3)
+        with quiet():
+            par, loss = s.fit(epochs=4, batch_size=50, gamma=0.9, X_train=X, y_train=Y)
+        opar, oloss = O.sgd_fit(O.SoftmaxOracle({"alpha": 0.1}), start, 5e-3, 4, 50, 0.9, X, Y)
+        np.testing.assert_allclose(opar["weights"], par["weights"], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(oloss, loss, rtol=1e-12)
+
+
+@pytest.mark.parametrize("sign", ["reference"])
+def test_sghmc_step_live(sign):
+    ref = load_reference()
+    X, y, Y = data()
+    rs = np.random.RandomState(2)
+    start = {"weights": rs.normal(0, .05, (20, 6)), "bias": rs.normal(0, .05, 6)}
+    s = ref.sghmc_runnable(ref.softmax({"alpha": 0.1}), {k: v.copy() for k, v in start.items()},
+                           path_length=1e-2, step_size=1e-3, verbose=False)
+    np.random.seed(9)
+    q, p, a = s.step(start, None, np.random.RandomState(8), X_train=X, y_train=Y)
+    draws = O.StreamDraws(np.random.RandomState(8), np.random.RandomState(9))
+    r = O.sghmc_step(O.SoftmaxOracle({"alpha": 0.1}), start, ["weights", "bias"], 1e-3, 1e-2, draws, sign=sign,
+                     X_train=X, y_train=Y)
+    np.testing.assert_allclose(r["accept_prob"], a, rtol=1e-10)
+    np.testing.assert_allclose(r["q"]["weights"], q["weights"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(r["p"]["weights"], p["weights"], rtol=1e-10, atol=1e-13)
+
+
+def test_mvn_live():
+    ref = load_reference()
+    hyper = {"mu": np.zeros(2), "cov": np.array([[1, .8], [.8, 1.]])}
+    s = ref.hmc(ref.mvn_gaussian(hyper), {"x": np.zeros(2)}, path_length=1.0, step_size=0.1, verbose=False)
+    np.random.seed(4)
+    with quiet():
+        post, loss, _, _ = s.sample(niter=200, burnin=10, rng=np.random.RandomState(3))
+    draws = O.StreamDraws(np.random.RandomState(3), np.random.RandomState(4))
+    opost, oloss, _ = O.hmc_sample(O.MvnGaussianOracle(hyper), {"x": np.zeros(2)}, 0.1, 1.0, 200, 10, draws)
+    np.testing.assert_allclose(opost["x"], post["x"], rtol=1e-10, atol=1e-13)
+
+
+def test_dual_averaging_live():
+    ref = load_reference()
+    da = ref.DualAveragingStepSize(0.1)
+    st = dict(mu=np.log(10 * 0.1), target_accept=0.8, gamma=0.05, t=10.0, kappa=0.75, error_sum=0.0, log_averaged_step=0.0)
+    for a in [0.9, 0.3, 0.7, 1.0, 0.0]:
+        assert np.allclose(da.update(a), O.dual_averaging_update(st, a), rtol=1e-13)
