@@ -1,0 +1,813 @@
+// C ABI of libbhmc.so (include/bhmc.h): context, model handles and the sampler drivers.
+// The drivers restate the *control flow* of the reference samplers
+//   hmc.step / hmc.sample          hamiltonian/inference/cpu/hmc.py:39-119
+//   sghmc.step                     hamiltonian/inference/cpu/sghmc.py:19-39
+//   sgmcmc.sample + sgld.step      hamiltonian/inference/cpu/sgmcmc.py:40-89, sgld.py:31-46
+//   sgd.fit                        hamiltonian/inference/cpu/sgd.py:25-45
+// for C chains at once, enqueueing kernels on one stream with no host round-trip inside a step.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "internal.cuh"
+#include "philox.cuh"
+
+namespace bhmc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace bhmc
+
+using namespace bhmc;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+int bhmc_ctx::get_scratch(int slot, size_t bytes, void** out) {
+  if (bytes > scratch_bytes[slot]) {
+    // grow-only; free synchronises with outstanding work on the device
+    if (scratch[slot]) BHMC_CUDA_OK(cudaFree(scratch[slot]));
+    scratch[slot] = nullptr;
+    scratch_bytes[slot] = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&scratch[slot], want);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu scratch bytes failed: %s", want, cudaGetErrorString(e));
+      return BHMC_ERR_NOMEM;
+    }
+    scratch_bytes[slot] = want;
+  }
+  *out = scratch[slot];
+  return BHMC_OK;
+}
+
+int bhmc_ctx::get_pinned(size_t bytes, void** out) {
+  if (bytes > pinned_bytes) {
+    if (pinned) {
+      BHMC_CUDA_OK(cudaStreamSynchronize(stream));
+      BHMC_CUDA_OK(cudaFreeHost(pinned));
+    }
+    pinned = nullptr;
+    pinned_bytes = 0;
+    BHMC_CUDA_OK(cudaMallocHost(&pinned, bytes));
+    pinned_bytes = bytes;
+  }
+  *out = pinned;
+  return BHMC_OK;
+}
+
+void bhmc_ctx::begin_group(int g) {
+  if (!timing) return;
+  if (used[g] == pool[g].size()) {
+    if (pool[g].size() >= 4096) {
+      flush_timing();
+    } else {
+      EventPair ep;
+      cudaEventCreate(&ep.a);
+      cudaEventCreate(&ep.b);
+      pool[g].push_back(ep);
+    }
+  }
+  cudaEventRecord(pool[g][used[g]].a, stream);
+}
+
+void bhmc_ctx::end_group(int g) {
+  if (!timing) return;
+  cudaEventRecord(pool[g][used[g]].b, stream);
+  used[g]++;
+}
+
+int bhmc_ctx::flush_timing() {
+  BHMC_CUDA_OK(cudaStreamSynchronize(stream));
+  for (int g = 0; g < KG_COUNT; ++g) {
+    for (size_t i = 0; i < used[g]; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pool[g][i].a, pool[g][i].b) == cudaSuccess) {
+        ms_acc[g] += ms;
+        n_acc[g]++;
+      }
+    }
+    used[g] = 0;
+  }
+  return BHMC_OK;
+}
+
+extern "C" {
+
+int bhmc_version(void) { return 100; }
+const char* bhmc_last_error(void) { return g_err; }
+
+int bhmc_ctx_create(int device, void* cuda_stream, bhmc_ctx** out) {
+  BHMC_CHECK_ARG(out, "out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s): libbhmc has no CPU fallback", cudaGetErrorString(e));
+    return BHMC_ERR_CUDA;
+  }
+  BHMC_CHECK_ARG(device >= 0 && device < n, "device %d out of range (%d devices)", device, n);
+  BHMC_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BHMC_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libbhmc is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return BHMC_ERR_UNSUPPORTED;
+  }
+  bhmc_ctx* c = new (std::nothrow) bhmc_ctx();
+  if (!c) return BHMC_ERR_NOMEM;
+  c->device = device;
+  c->stream = (cudaStream_t)cuda_stream;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return BHMC_OK;
+}
+
+int bhmc_ctx_destroy(bhmc_ctx* ctx) {
+  if (!ctx) return BHMC_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 8; ++i) cudaFree(ctx->scratch[i]);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
+  for (int g = 0; g < KG_COUNT; ++g)
+    for (auto& ep : ctx->pool[g]) {
+      cudaEventDestroy(ep.a);
+      cudaEventDestroy(ep.b);
+    }
+  delete ctx;
+  return BHMC_OK;
+}
+
+int bhmc_ctx_sync(bhmc_ctx* ctx) {
+  BHMC_CHECK_ARG(ctx, "ctx is NULL");
+  BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return BHMC_OK;
+}
+
+int64_t bhmc_ctx_launch_count(const bhmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bhmc_ctx_timing(bhmc_ctx* ctx, int enable) {
+  BHMC_CHECK_ARG(ctx, "ctx is NULL");
+  BHMC_TRY(ctx->flush_timing());
+  ctx->timing = enable != 0;
+  for (int g = 0; g < KG_COUNT; ++g) ctx->ms_acc[g] = 0, ctx->n_acc[g] = 0;
+  return BHMC_OK;
+}
+
+int bhmc_ctx_kernel_time(bhmc_ctx* ctx, int group, double* ms, int64_t* launches) {
+  BHMC_CHECK_ARG(ctx && group >= 0 && group < KG_COUNT, "bad group");
+  BHMC_TRY(ctx->flush_timing());
+  if (ms) *ms = ctx->ms_acc[group];
+  if (launches) *launches = ctx->n_acc[group];
+  return BHMC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// models
+// ------------------------------------------------------------------------------------------------
+struct bhmc_model {
+  ModelBase* impl = nullptr;
+};
+
+namespace bhmc {
+
+struct SoftmaxModel : ModelBase {
+  SoftmaxData d;
+  float alpha = 0.f;
+  int prior = BHMC_PRIOR_CPU;
+  float* X_owned = nullptr;
+  int32_t* y_owned = nullptr;
+
+  ~SoftmaxModel() override {
+    tc_softmax_release(d);
+    cudaFree(X_owned);
+    cudaFree(y_owned);
+  }
+  int64_t default_rows() const override { return d.N; }
+
+  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) override {
+    switch (prec) {
+      case BHMC_PREC_FP32: return simt_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat);
+      case BHMC_PREC_BF16X3: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, true);
+      case BHMC_PREC_BF16: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, false);
+    }
+    set_error("unknown precision %d", prec);
+    return BHMC_ERR_ARG;
+  }
+  // NLP = -(LL + log_prior)/n  (softmax.py:74-79)
+  void energy_coeffs(int64_t nrows, double* a, double* b, double* cv) const override {
+    *a = -1.0 / (double)nrows;
+    double lp = 0.0;
+    for (int v = 0; v < n_vars; ++v) {
+      cv[v] = 0.0;
+      if (prior == BHMC_PRIOR_CPU)  // softmax.py:22-30: -(dim/2 log 2pi - dim/2 log alpha)
+        lp -= 0.5 * (double)var_len[v] * std::log(2.0 * M_PI) - 0.5 * (double)var_len[v] * std::log((double)alpha);
+      else  // models/gpu/softmax.py:29-39: -alpha/2 |theta_v|^2 / dim_v
+        cv[v] = 0.5 * (double)alpha / ((double)var_len[v] * (double)nrows);
+    }
+    *b = -lp / (double)nrows;
+  }
+};
+
+// d-dimensional Gaussian target: one thread per chain (mvn_gaussian.py:14-31)
+__global__ void k_mvn(const float* __restrict__ q, int64_t ld, int dim, const double* __restrict__ mu,
+                      const double* __restrict__ cinv, float* __restrict__ g, double* __restrict__ stat, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* x = q + (int64_t)c * ld;
+  double quad = 0.0;
+  for (int j = 0; j < dim; ++j) {
+    double s = 0.0;
+    for (int i = 0; i < dim; ++i) s += ((double)x[i] - mu[i]) * cinv[i * dim + j];  // (x-mu) Sigma^-1
+    if (g) g[(int64_t)c * ld + j] = (float)s;
+    quad += s * ((double)x[j] - mu[j]);
+  }
+  if (stat) stat[c] = quad;
+}
+
+struct MvnModel : ModelBase {
+  int dim = 0;
+  double logdet = 0.0;
+  double* dev = nullptr;  // mu | cov_inv
+  ~MvnModel() override { cudaFree(dev); }
+  int grad(const float* q, int C, int64_t ld, int64_t, int64_t, int, float* g, double* stat) override {
+    GroupTimer t(ctx, KG_FWD);
+    k_mvn<<<(C + 127) / 128, 128, 0, ctx->stream>>>(q, ld, dim, dev, dev + dim, g, stat, C);
+    ctx->launches++;
+    BHMC_CUDA_OK(cudaGetLastError());
+    return BHMC_OK;
+  }
+  // U = 0.5 (d log 2pi + log det + quad)
+  void energy_coeffs(int64_t, double* a, double* b, double* cv) const override {
+    *a = 0.5;
+    *b = 0.5 * (dim * std::log(2.0 * M_PI) + logdet);
+    cv[0] = 0.0;
+  }
+};
+
+}  // namespace bhmc
+
+extern "C" {
+
+int bhmc_softmax_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_features, int32_t n_classes, float alpha,
+                        int32_t prior_variant, bhmc_model** out) {
+  BHMC_CHECK_ARG(ctx && out, "ctx/out is NULL");
+  BHMC_CHECK_ARG(n_rows > 0 && n_features > 0 && n_classes > 0, "bad shape N=%lld D=%d K=%d", (long long)n_rows, n_features,
+                 n_classes);
+  BHMC_CHECK_ARG(n_rows < (1LL << 31) - 256, "row count %lld exceeds the 32-bit TMA coordinate range", (long long)n_rows);
+  auto* m = new (std::nothrow) SoftmaxModel();
+  if (!m) return BHMC_ERR_NOMEM;
+  m->ctx = ctx;
+  m->d.N = n_rows;
+  m->d.D = n_features;
+  m->d.K = n_classes;
+  m->alpha = alpha;
+  m->prior = prior_variant;
+  m->P = (int64_t)(n_features + 1) * n_classes;
+  m->n_vars = 2;
+  m->var_off[0] = 0;
+  m->var_len[0] = (int64_t)n_features * n_classes;
+  m->var_off[1] = m->var_len[0];
+  m->var_len[1] = n_classes;
+  bhmc_model* h = new bhmc_model();
+  h->impl = m;
+  *out = h;
+  return BHMC_OK;
+}
+
+static int softmax_of(bhmc_model* m, SoftmaxModel** out) {
+  BHMC_CHECK_ARG(m && m->impl, "model is NULL");
+  auto* s = dynamic_cast<SoftmaxModel*>(m->impl);
+  BHMC_CHECK_ARG(s, "model is not a softmax model");
+  *out = s;
+  return BHMC_OK;
+}
+
+static int bind_common(SoftmaxModel* s, int32_t mask) {
+  if (mask & ((1 << BHMC_PREC_BF16X3) | (1 << BHMC_PREC_BF16)))
+    BHMC_TRY(tc_softmax_bind(s->ctx, s->d, (mask & (1 << BHMC_PREC_BF16X3)) != 0));
+  return BHMC_OK;
+}
+
+int bhmc_softmax_bind_data(bhmc_model* m, const float* X_dev, const int32_t* labels_dev, int32_t precision_mask) {
+  SoftmaxModel* s;
+  BHMC_TRY(softmax_of(m, &s));
+  BHMC_CHECK_ARG(X_dev && labels_dev, "X/labels is NULL");
+  BHMC_CUDA_OK(cudaSetDevice(s->ctx->device));
+  s->d.X = X_dev;
+  s->d.labels = labels_dev;
+  return bind_common(s, precision_mask);
+}
+
+int bhmc_softmax_bind_data_host(bhmc_model* m, const float* X_host, const int32_t* labels_host, int32_t precision_mask) {
+  SoftmaxModel* s;
+  BHMC_TRY(softmax_of(m, &s));
+  BHMC_CHECK_ARG(X_host && labels_host, "X/labels is NULL");
+  BHMC_CUDA_OK(cudaSetDevice(s->ctx->device));
+  size_t xb = sizeof(float) * (size_t)s->d.N * s->d.D, yb = sizeof(int32_t) * (size_t)s->d.N;
+  if (!s->X_owned) BHMC_CUDA_OK(cudaMalloc(&s->X_owned, xb));
+  if (!s->y_owned) BHMC_CUDA_OK(cudaMalloc(&s->y_owned, yb));
+  BHMC_CUDA_OK(cudaMemcpyAsync(s->X_owned, X_host, xb, cudaMemcpyHostToDevice, s->ctx->stream));
+  BHMC_CUDA_OK(cudaMemcpyAsync(s->y_owned, labels_host, yb, cudaMemcpyHostToDevice, s->ctx->stream));
+  s->d.X = s->X_owned;
+  s->d.labels = s->y_owned;
+  return bind_common(s, precision_mask);
+}
+
+int bhmc_mvn_create(bhmc_ctx* ctx, int32_t dim, const double* mu_host, const double* cov_inv_host, double logdet,
+                    bhmc_model** out) {
+  BHMC_CHECK_ARG(ctx && out && mu_host && cov_inv_host, "NULL argument");
+  BHMC_CHECK_ARG(dim > 0 && dim <= 64, "dim %d out of range [1,64]", dim);
+  auto* m = new (std::nothrow) MvnModel();
+  if (!m) return BHMC_ERR_NOMEM;
+  m->ctx = ctx;
+  m->dim = dim;
+  m->logdet = logdet;
+  m->P = dim;
+  m->n_vars = 1;
+  m->var_off[0] = 0;
+  m->var_len[0] = dim;
+  BHMC_CUDA_OK(cudaMalloc(&m->dev, sizeof(double) * (dim + dim * dim)));
+  BHMC_CUDA_OK(cudaMemcpy(m->dev, mu_host, sizeof(double) * dim, cudaMemcpyHostToDevice));
+  BHMC_CUDA_OK(cudaMemcpy(m->dev + dim, cov_inv_host, sizeof(double) * dim * dim, cudaMemcpyHostToDevice));
+  bhmc_model* h = new bhmc_model();
+  h->impl = m;
+  *out = h;
+  return BHMC_OK;
+}
+
+int bhmc_model_destroy(bhmc_model* m) {
+  if (!m) return BHMC_OK;
+  if (m->impl) {
+    cudaStreamSynchronize(m->impl->ctx->stream);
+    delete m->impl;
+  }
+  delete m;
+  return BHMC_OK;
+}
+
+int64_t bhmc_model_n_params(const bhmc_model* m) { return (m && m->impl) ? m->impl->P : -1; }
+int32_t bhmc_model_n_vars(const bhmc_model* m) { return (m && m->impl) ? m->impl->n_vars : -1; }
+
+int bhmc_model_var_layout(const bhmc_model* m, int64_t* offsets, int64_t* lengths) {
+  BHMC_CHECK_ARG(m && m->impl && offsets && lengths, "NULL argument");
+  for (int v = 0; v < m->impl->n_vars; ++v) offsets[v] = m->impl->var_off[v], lengths[v] = m->impl->var_len[v];
+  return BHMC_OK;
+}
+
+static int check_state(const bhmc_model* m, const float* q, int C, int64_t ld) {
+  BHMC_CHECK_ARG(m && m->impl && q, "NULL argument");
+  BHMC_CHECK_ARG(C > 0 && C <= 65535, "n_chains %d out of range [1,65535]", C);
+  BHMC_CHECK_ARG(ld >= m->impl->P && ld % 4 == 0, "ld %lld must be >= P=%lld and a multiple of 4", (long long)ld,
+                 (long long)m->impl->P);
+  BHMC_CHECK_ARG(((uintptr_t)q & 15) == 0, "chain state must be 16-byte aligned");
+  return BHMC_OK;
+}
+
+int bhmc_model_grad(bhmc_model* m, const float* q, int32_t C, int64_t ld, int64_t row0, int64_t nrows, int32_t prec,
+                    float* g, double* loglik) {
+  BHMC_TRY(check_state(m, q, C, ld));
+  BHMC_CHECK_ARG(g && loglik, "g/loglik is NULL");
+  BHMC_CUDA_OK(cudaSetDevice(m->impl->ctx->device));
+  return m->impl->grad(q, C, ld, row0, nrows, prec, g, loglik);
+}
+
+int bhmc_model_loglik(bhmc_model* m, const float* q, int32_t C, int64_t ld, int64_t row0, int64_t nrows, int32_t prec,
+                      double* loglik) {
+  BHMC_TRY(check_state(m, q, C, ld));
+  BHMC_CHECK_ARG(loglik, "loglik is NULL");
+  BHMC_CUDA_OK(cudaSetDevice(m->impl->ctx->device));
+  return m->impl->grad(q, C, ld, row0, nrows, prec, nullptr, loglik);
+}
+
+int bhmc_model_nlp(bhmc_model* m, const float* q, int32_t C, int64_t ld, int64_t row0, int64_t nrows, int32_t prec,
+                   double* nlp) {
+  BHMC_TRY(check_state(m, q, C, ld));
+  BHMC_CHECK_ARG(nlp, "nlp is NULL");
+  ModelBase* mb = m->impl;
+  BHMC_CUDA_OK(cudaSetDevice(mb->ctx->device));
+  BHMC_TRY(mb->grad(q, C, ld, row0, nrows, prec, nullptr, nlp));
+  double a, b, cv[BHMC_MAX_VARS];
+  mb->energy_coeffs(nrows, &a, &b, cv);
+  bool need_extra = false;
+  for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
+  if (!need_extra) return launch_affine(mb->ctx, nlp, a, b, nullptr, nlp, C);
+  void* ss = nullptr;
+  BHMC_TRY(mb->ctx->get_scratch(4, sizeof(double) * C * (mb->n_vars + 1), &ss));
+  double* sumsq = (double*)ss;
+  BHMC_TRY(launch_sumsq(mb->ctx, q, ld, C, mb->n_vars, mb->var_off, mb->var_len, sumsq));
+  // fold sum_v cv*sumsq_v on the host-free path: tiny kernel via affine per variable
+  double* extra = sumsq + (size_t)C * mb->n_vars;
+  BHMC_CUDA_OK(cudaMemsetAsync(extra, 0, sizeof(double) * C, mb->ctx->stream));
+  for (int v = 0; v < mb->n_vars; ++v) {
+    // extra[c] += cv[v]*sumsq[c*n_vars+v] : strided gather done with cudaMemcpy2D into a temp then affine
+    double* tmp = nullptr;
+    void* t = nullptr;
+    BHMC_TRY(mb->ctx->get_scratch(5, sizeof(double) * C, &t));
+    tmp = (double*)t;
+    BHMC_CUDA_OK(cudaMemcpy2DAsync(tmp, sizeof(double), sumsq + v, sizeof(double) * mb->n_vars, sizeof(double), C,
+                                   cudaMemcpyDeviceToDevice, mb->ctx->stream));
+    BHMC_TRY(launch_affine(mb->ctx, tmp, cv[v], 0.0, extra, extra, C));
+  }
+  return launch_affine(mb->ctx, nlp, a, b, extra, nlp, C);
+}
+
+int bhmc_softmax_predict(bhmc_model* m, const float* q, int32_t C, int64_t ld, const float* X_dev, int64_t nrows,
+                         float* probs, int32_t* labels) {
+  SoftmaxModel* s;
+  BHMC_TRY(softmax_of(m, &s));
+  BHMC_TRY(check_state(m, q, C, ld));
+  BHMC_CHECK_ARG(X_dev && nrows > 0, "X is NULL / no rows");
+  BHMC_CUDA_OK(cudaSetDevice(s->ctx->device));
+  return simt_softmax_predict(s->ctx, s->d.D, s->d.K, q, C, ld, X_dev, nrows, probs, labels);
+}
+
+int bhmc_philox_normal(bhmc_ctx* ctx, float* out, int32_t C, int64_t P, int64_t ld, uint64_t seed, int64_t chain_id0,
+                       uint32_t slo, uint32_t shi) {
+  BHMC_CHECK_ARG(ctx && out && C > 0 && P > 0 && ld >= P, "bad argument");
+  BHMC_CUDA_OK(cudaSetDevice(ctx->device));
+  return launch_philox_normal(ctx, out, C, P, ld, seed, chain_id0, slo, shi);
+}
+
+double bhmc_philox_uniform_host(uint64_t seed, int64_t chain_id, uint32_t slo, uint32_t shi) {
+  return philox_uniform(seed, chain_id, slo, shi);
+}
+
+void bhmc_philox4x32_host(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+  U4 r = philox4x32_10(U4{counter[0], counter[1], counter[2], counter[3]}, key[0], key[1]);
+  out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// sampler
+// ------------------------------------------------------------------------------------------------
+struct bhmc_sampler {
+  bhmc_ctx* ctx = nullptr;
+  ModelBase* model = nullptr;
+  bhmc_sampler_config cfg;
+  int64_t P = 0, ld = 0;
+  float* state = nullptr;  // q | p | g | q_new | p_new  (each [C, ld])
+  float *q = nullptr, *p = nullptr, *g = nullptr, *q_new = nullptr, *p_new = nullptr;
+  double* scal = nullptr;  // stat | stat_cur | stat_new | kin0 | kin1 | extra_cur | extra_new | sumsq[C*nv] | u[C]
+  int32_t* Ldev = nullptr;
+};
+
+extern "C" {
+
+int bhmc_sampler_create(bhmc_ctx* ctx, bhmc_model* model, const bhmc_sampler_config* cfg, bhmc_sampler** out) {
+  BHMC_CHECK_ARG(ctx && model && model->impl && cfg && out, "NULL argument");
+  BHMC_CHECK_ARG(cfg->n_chains > 0 && cfg->n_chains <= 65535, "n_chains %d out of range [1,65535]", cfg->n_chains);
+  BHMC_CHECK_ARG(cfg->kind >= BHMC_KIND_HMC && cfg->kind <= BHMC_KIND_SGD, "unknown sampler kind %d", cfg->kind);
+  BHMC_CHECK_ARG(cfg->n_sweep >= 1 && cfg->n_sweep <= BHMC_MAX_VARS, "n_sweep %d out of range", cfg->n_sweep);
+  ModelBase* mb = model->impl;
+  for (int i = 0; i < cfg->n_sweep; ++i)
+    BHMC_CHECK_ARG(cfg->sweep_off[i] >= 0 && cfg->sweep_len[i] > 0 && cfg->sweep_off[i] + cfg->sweep_len[i] <= mb->P,
+                   "sweep group %d [%lld,+%lld) outside the %lld parameters", i, (long long)cfg->sweep_off[i],
+                   (long long)cfg->sweep_len[i], (long long)mb->P);
+  BHMC_CUDA_OK(cudaSetDevice(ctx->device));
+  auto* s = new (std::nothrow) bhmc_sampler();
+  if (!s) return BHMC_ERR_NOMEM;
+  s->ctx = ctx;
+  s->model = mb;
+  s->cfg = *cfg;
+  s->P = mb->P;
+  s->ld = round_up(mb->P, 4);
+  int C = cfg->n_chains;
+  size_t row = (size_t)C * s->ld;
+  cudaError_t e = cudaMalloc(&s->state, sizeof(float) * row * 5);
+  if (e != cudaSuccess) {
+    delete s;
+    set_error("cudaMalloc of chain state (%zu bytes) failed: %s", sizeof(float) * row * 5, cudaGetErrorString(e));
+    return BHMC_ERR_NOMEM;
+  }
+  BHMC_CUDA_OK(cudaMemsetAsync(s->state, 0, sizeof(float) * row * 5, ctx->stream));
+  s->q = s->state;
+  s->p = s->state + row;
+  s->g = s->state + 2 * row;
+  s->q_new = s->state + 3 * row;
+  s->p_new = s->state + 4 * row;
+  size_t nscal = (size_t)C * (8 + mb->n_vars);
+  BHMC_CUDA_OK(cudaMalloc(&s->scal, sizeof(double) * nscal));
+  BHMC_CUDA_OK(cudaMemsetAsync(s->scal, 0, sizeof(double) * nscal, ctx->stream));
+  *out = s;
+  return BHMC_OK;
+}
+
+int bhmc_sampler_destroy(bhmc_sampler* s) {
+  if (!s) return BHMC_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->state);
+  cudaFree(s->scal);
+  cudaFree(s->Ldev);
+  delete s;
+  return BHMC_OK;
+}
+
+int64_t bhmc_sampler_ld(const bhmc_sampler* s) { return s ? s->ld : -1; }
+
+int bhmc_sampler_state_ptr(bhmc_sampler* s, int32_t which, float** out) {
+  BHMC_CHECK_ARG(s && out && which >= 0 && which <= 2, "bad argument");
+  *out = which == 0 ? s->q : which == 1 ? s->p : s->g;
+  return BHMC_OK;
+}
+
+int bhmc_sampler_set_q(bhmc_sampler* s, const float* src, int32_t is_host) {
+  BHMC_CHECK_ARG(s && src, "NULL argument");
+  BHMC_CUDA_OK(cudaSetDevice(s->ctx->device));
+  BHMC_CUDA_OK(cudaMemcpy2DAsync(s->q, sizeof(float) * s->ld, src, sizeof(float) * s->P, sizeof(float) * s->P,
+                                 s->cfg.n_chains, is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                 s->ctx->stream));
+  return BHMC_OK;
+}
+
+int bhmc_sampler_get(bhmc_sampler* s, int32_t which, float* dst, int32_t is_host) {
+  BHMC_CHECK_ARG(s && dst && which >= 0 && which <= 2, "bad argument");
+  BHMC_CUDA_OK(cudaSetDevice(s->ctx->device));
+  const float* src = which == 0 ? s->q : which == 1 ? s->p : s->g;
+  BHMC_CUDA_OK(cudaMemcpy2DAsync(dst, sizeof(float) * s->P, src, sizeof(float) * s->ld, sizeof(float) * s->P,
+                                 s->cfg.n_chains, is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                 s->ctx->stream));
+  if (is_host) BHMC_CUDA_OK(cudaStreamSynchronize(s->ctx->stream));
+  return BHMC_OK;
+}
+
+// ---- HMC / SGHMC ---------------------------------------------------------------------------------
+int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
+  BHMC_CHECK_ARG(s && run, "NULL argument");
+  const bhmc_sampler_config& cfg = s->cfg;
+  BHMC_CHECK_ARG(cfg.kind == BHMC_KIND_HMC || cfg.kind == BHMC_KIND_SGHMC, "sampler kind %d cannot run hmc_run", cfg.kind);
+  BHMC_CHECK_ARG(run->n_steps >= 0 && run->step_size > 0 && run->path_length >= 0, "bad run parameters");
+  bhmc_ctx* ctx = s->ctx;
+  ModelBase* mb = s->model;
+  BHMC_CUDA_OK(cudaSetDevice(ctx->device));
+  const int C = cfg.n_chains, nsw = cfg.n_sweep;
+  const bool sghmc = cfg.kind == BHMC_KIND_SGHMC;
+  const int64_t P = s->P, ld = s->ld;
+  const int64_t nrows = run->nrows > 0 ? run->nrows : mb->default_rows();
+  const float eps = (float)run->step_size;
+  double* stat = s->scal;
+  double* stat_cur = stat + C;
+  double* stat_new = stat + 2 * C;
+  double* kin0 = stat + 3 * C;
+  double* kin1 = stat + 4 * C;
+  double* extra_cur = stat + 5 * C;
+  double* extra_new = stat + 6 * C;
+  double* u_dev = stat + 7 * C;
+  double* sumsq = stat + 8 * C;
+  double ea, eb, cv[BHMC_MAX_VARS];
+  mb->energy_coeffs(nrows, &ea, &eb, cv);
+  bool need_extra = false;
+  for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
+  if (need_extra) {
+    set_error("quadratic-prior energies (BHMC_PRIOR_GPU) are not wired into the Metropolis test yet");
+    return BHMC_ERR_UNSUPPORTED;
+  }
+  (void)extra_cur;
+  (void)extra_new;
+  (void)sumsq;
+
+  // path lengths for every step and chain: L = ceil(2 u path/eps), hmc.py:46 (host side: it sizes the launch loop)
+  const int n_steps = run->n_steps;
+  if (n_steps == 0) return BHMC_OK;
+  if (ctx->pinned_inflight) {
+    BHMC_CUDA_OK(cudaEventSynchronize(ctx->pinned_ev));
+    ctx->pinned_inflight = false;
+  }
+  void* pin = nullptr;
+  size_t l_bytes = sizeof(int32_t) * (size_t)n_steps * C, u_bytes = sizeof(double) * (size_t)n_steps * C;
+  BHMC_TRY(ctx->get_pinned(l_bytes + u_bytes + 64, &pin));
+  int32_t* Lh = (int32_t*)pin;
+  double* uacc_h = (double*)((char*)pin + ((l_bytes + 63) / 64) * 64);
+  std::vector<int> lmax(n_steps, 0);
+  run->n_grad_evals = 0;
+  run->n_grad_launched = 0;
+  for (int t = 0; t < n_steps; ++t) {
+    uint32_t step = (uint32_t)(run->step0 + t);
+    for (int c = 0; c < C; ++c) {
+      double u;
+      if (run->u_path_host)
+        u = run->u_path_host[(size_t)t * C + c];
+      else
+        u = philox_uniform(cfg.seed, cfg.shared_path ? -1 : cfg.chain_id0 + c, step, TAG_PATH);
+      double Ld = std::ceil(2.0 * u * run->path_length / run->step_size);
+      int L = Ld > 1e9 ? 1000000000 : (int)Ld;
+      Lh[(size_t)t * C + c] = L;
+      lmax[t] = std::max(lmax[t], L);
+      run->n_grad_evals += 1 + (int64_t)std::max(L - 1, 0) * nsw;
+      if (run->u_accept_host) uacc_h[(size_t)t * C + c] = run->u_accept_host[(size_t)t * C + c];
+    }
+    run->n_grad_launched += (int64_t)C * (1 + (int64_t)std::max(lmax[t] - 1, 0) * nsw);
+    BHMC_CHECK_ARG(!(sghmc && run->z_noise_dev) || std::max(lmax[t] - 1, 0) <= run->z_noise_iters,
+                   "step %d needs %d noise iterations but the tape holds %lld", t, lmax[t] - 1, (long long)run->z_noise_iters);
+  }
+  void* ldev = nullptr;
+  BHMC_TRY(ctx->get_scratch(6, l_bytes + u_bytes + 64, &ldev));
+  int32_t* Ld_all = (int32_t*)ldev;
+  double* uacc_d = (double*)((char*)ldev + ((l_bytes + 63) / 64) * 64);
+  BHMC_CUDA_OK(cudaMemcpyAsync(ldev, pin, ((l_bytes + 63) / 64) * 64 + (run->u_accept_host ? u_bytes : 0),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  if (!ctx->pinned_ev) BHMC_CUDA_OK(cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming));
+  BHMC_CUDA_OK(cudaEventRecord(ctx->pinned_ev, ctx->stream));
+  ctx->pinned_inflight = true;
+  (void)u_dev;
+
+  for (int t = 0; t < n_steps; ++t) {
+    const uint32_t step = (uint32_t)(run->step0 + t);
+    const int32_t* Lc = Ld_all + (size_t)t * C;
+    // 1. momentum ~ N(0,1), proposal := current (hmc.py:40-44)
+    BeginArgs b{};
+    b.q = s->q;
+    b.q_new = s->q_new;
+    b.p0 = s->p;
+    b.p_new = s->p_new;
+    b.ld = ld;
+    b.P = P;
+    b.C = C;
+    b.z = run->z_momentum_dev ? run->z_momentum_dev + (size_t)t * C * P : nullptr;
+    b.ld_z = P;
+    b.seed = cfg.seed;
+    b.chain_id0 = cfg.chain_id0;
+    b.stream_lo = step;
+    b.stream_hi = TAG_MOMENTUM;
+    b.kin0 = kin0;
+    BHMC_TRY(launch_hmc_begin(ctx, b));
+    // 2. gradient at the current point (hmc.py:47); its log-likelihood doubles as NLP(q)
+    BHMC_TRY(mb->grad(s->q_new, C, ld, run->row0, nrows, cfg.precision, s->g, stat));
+    BHMC_CUDA_OK(cudaMemcpyAsync(stat_cur, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
+    BHMC_CUDA_OK(cudaMemcpyAsync(stat_new, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
+    // 3. leapfrog: (L-1) Gauss-Seidel sweeps (hmc.py:49-54 / sghmc.py:28-34)
+    const int iters = std::max(lmax[t] - 1, 0);
+    UpdateArgs u{};
+    u.q = s->q_new;
+    u.p = s->p_new;
+    u.g = s->g;
+    u.ld = ld;
+    u.P = P;
+    u.C = C;
+    u.L = Lc;
+    u.eps = eps;
+    u.seed = cfg.seed;
+    u.chain_id0 = cfg.chain_id0;
+    u.stat = stat;
+    u.stat_new = stat_new;
+    if (sghmc) {
+      u.f_post = 1.0f - eps;
+      u.a_post = cfg.sghmc_descent ? eps : -eps;  // literal: p = (1-eps)p + eps*grad + r (sghmc.py:34)
+      u.n_post = 2.0f * eps;                      // N(0, std = 2 eps), sghmc.py:31
+      u.a_pre = 0.f;
+    } else {
+      u.f_post = 1.0f;
+      u.a_post = cfg.leapfrog ? 0.5f * eps : eps;  // hmc.py:54 applies a FULL eps kick
+      u.n_post = 0.f;
+      u.a_pre = 0.5f * eps;                        // hmc.py:51
+    }
+    for (int it = 0; it < iters; ++it) {
+      for (int v = 0; v < nsw; ++v) {
+        bool first = (it == 0 && v == 0);
+        int pv = v == 0 ? nsw - 1 : v - 1, pit = v == 0 ? it - 1 : it;
+        u.post_off = first ? 0 : cfg.sweep_off[pv];
+        u.post_len = first ? 0 : cfg.sweep_len[pv];
+        u.it_post = pit;
+        u.pre_off = cfg.sweep_off[v];
+        u.pre_len = cfg.sweep_len[v];
+        u.it_pre = it;
+        if (sghmc && !first) {
+          u.z = run->z_noise_dev ? run->z_noise_dev + ((size_t)t * run->z_noise_iters + pit) * C * P : nullptr;
+          u.ld_z = P;
+          u.stream_lo = step;
+          u.stream_hi = TAG_NOISE | (uint32_t)((pit * nsw + pv) & 0xffffff);
+        }
+        BHMC_TRY(launch_hmc_update(ctx, u));
+        BHMC_TRY(mb->grad(s->q_new, C, ld, run->row0, nrows, cfg.precision, s->g, stat));
+      }
+    }
+    if (iters > 0) {  // closing kick of the last variable
+      u.post_off = cfg.sweep_off[nsw - 1];
+      u.post_len = cfg.sweep_len[nsw - 1];
+      u.it_post = iters - 1;
+      u.pre_len = 0;
+      u.pre_off = 0;
+      u.it_pre = 0;
+      if (sghmc) {
+        u.z = run->z_noise_dev ? run->z_noise_dev + ((size_t)t * run->z_noise_iters + (iters - 1)) * C * P : nullptr;
+        u.ld_z = P;
+        u.stream_lo = step;
+        u.stream_hi = TAG_NOISE | (uint32_t)((((iters - 1) * nsw) + nsw - 1) & 0xffffff);
+      }
+      BHMC_TRY(launch_hmc_update(ctx, u));
+    }
+    // 4. Metropolis test (hmc.py:58-63): energies = NLP + 0.5|p|^2, momentum flipped for HMC only
+    BHMC_TRY(launch_kinetic(ctx, s->p_new, ld, P, C, kin1));
+    AcceptArgs a{};
+    a.q = s->q;
+    a.q_new = s->q_new;
+    a.p_out = s->p;
+    a.p_new = s->p_new;
+    a.ld = ld;
+    a.P = P;
+    a.C = C;
+    a.p_sign = sghmc ? 1.f : -1.f;
+    a.stat_cur = stat_cur;
+    a.stat_new = stat_new;
+    a.ea = ea;
+    a.eb = eb;
+    a.kin0 = kin0;
+    a.kin1 = kin1;
+    a.u = run->u_accept_host ? uacc_d + (size_t)t * C : nullptr;
+    a.seed = cfg.seed;
+    a.chain_id0 = cfg.chain_id0;
+    a.stream_lo = step;
+    a.stream_hi = TAG_ACCEPT;
+    a.reject_nan = cfg.reject_nan;
+    a.sample = run->samples_dev ? run->samples_dev + (size_t)t * C * P : nullptr;
+    a.loss = run->loss_dev ? run->loss_dev + (size_t)t * C : nullptr;
+    a.accept_prob = run->accept_prob_dev ? run->accept_prob_dev + (size_t)t * C : nullptr;
+    a.accepted = run->accepted_dev ? run->accepted_dev + (size_t)t * C : nullptr;
+    BHMC_TRY(launch_accept(ctx, a));
+  }
+  return BHMC_OK;
+}
+
+// ---- SGLD / SGD ------------------------------------------------------------------------------------
+int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
+  BHMC_CHECK_ARG(s && run, "NULL argument");
+  const bhmc_sampler_config& cfg = s->cfg;
+  BHMC_CHECK_ARG(cfg.kind == BHMC_KIND_SGLD || cfg.kind == BHMC_KIND_SGD, "sampler kind %d cannot run sg_run", cfg.kind);
+  bhmc_ctx* ctx = s->ctx;
+  ModelBase* mb = s->model;
+  BHMC_CUDA_OK(cudaSetDevice(ctx->device));
+  const int C = cfg.n_chains;
+  const int64_t P = s->P, ld = s->ld;
+  const int64_t n_rows = run->n_rows > 0 ? run->n_rows : mb->default_rows();
+  BHMC_CHECK_ARG(run->batch_size > 0 && run->batch_size <= n_rows, "batch_size %lld must be in [1, %lld]",
+                 (long long)run->batch_size, (long long)n_rows);
+  BHMC_CHECK_ARG(run->epochs >= 0 && run->burnin >= 0 && run->step_size > 0, "bad run parameters");
+  // sequential windows, remainder dropped (sgmcmc.py:34-38)
+  const int64_t nb = (n_rows - run->batch_size) / run->batch_size + 1;
+  const double num_batches = std::ceil((double)n_rows / (double)run->batch_size);  // sgmcmc.py:50
+  const double decay = run->step_size / num_batches;                                // sgmcmc.py:51
+  double* stat = s->scal;
+  double eps = run->step_size;
+  int64_t k = 0;  // global minibatch counter (indexes the injected tape and the Philox stream)
+  run->n_grad_evals = 0;
+  const bool sgd = cfg.kind == BHMC_KIND_SGD;
+  for (int e = 0; e < run->burnin + run->epochs; ++e) {
+    const bool sampling = e >= run->burnin;
+    for (int64_t j = 0; j < nb; ++j, ++k) {
+      const int64_t row0 = j * run->batch_size;
+      BHMC_TRY(mb->grad(s->q, C, ld, row0, run->batch_size, cfg.precision, s->g, stat));
+      run->n_grad_evals += C;
+      if (sgd) {
+        BHMC_TRY(launch_sgd_update(ctx, s->q, s->p, s->g, ld, P, C, (float)run->gamma, (float)run->step_size));
+      } else {
+        SgldArgs a{};
+        a.q = s->q;
+        a.p = s->p;
+        a.g = s->g;
+        a.ld = ld;
+        a.P = P;
+        a.C = C;
+        a.eps = (float)eps;
+        a.z = run->z_dev ? run->z_dev + (size_t)k * C * P : nullptr;
+        a.ld_z = P;
+        a.seed = cfg.seed;
+        a.chain_id0 = cfg.chain_id0;
+        a.stream_lo = (uint32_t)(run->step0 + k);
+        a.stream_hi = TAG_NOISE | (uint32_t)(((uint64_t)(run->step0 + k) >> 32) & 0xffffff);
+        BHMC_TRY(launch_sgld_update(ctx, a));
+        // step size re-assigned AFTER batch j, sampling epochs only (sgmcmc.py:72-73,88-89)
+        if (sampling) eps = run->step_size * (1.0 / (1.0 + (double)j * decay * num_batches));
+      }
+    }
+    if (sampling) {
+      const int i = e - run->burnin;
+      if (run->logp_dev) {  // NLP(q, last batch), sgmcmc.py:79 / sgd.py:42
+        const int64_t row0 = (nb - 1) * run->batch_size;
+        double a, b, cv[BHMC_MAX_VARS];
+        mb->energy_coeffs(run->batch_size, &a, &b, cv);
+        BHMC_TRY(mb->grad(s->q, C, ld, row0, run->batch_size, cfg.precision, nullptr, stat));
+        BHMC_TRY(launch_affine(ctx, stat, a, b, nullptr, run->logp_dev + (size_t)i * C, C));
+      }
+      if (run->samples_dev) BHMC_TRY(launch_copy_rows(ctx, s->q, ld, run->samples_dev + (size_t)i * C * P, P, P, C));
+    }
+  }
+  run->final_step_size = eps;
+  return BHMC_OK;
+}
+
+}  // extern "C"

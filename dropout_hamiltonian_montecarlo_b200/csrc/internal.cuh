@@ -1,0 +1,234 @@
+// Internal declarations shared by the translation units of libbhmc.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bhmc.h"
+
+namespace bhmc {
+
+void set_error(const char* fmt, ...);
+
+#define BHMC_CUDA_OK(expr)                                                                 \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ::bhmc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                         \
+      return BHMC_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+#define BHMC_CHECK_ARG(cond, ...)   \
+  do {                              \
+    if (!(cond)) {                  \
+      ::bhmc::set_error(__VA_ARGS__); \
+      return BHMC_ERR_ARG;          \
+    }                               \
+  } while (0)
+
+#define BHMC_TRY(expr)          \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != BHMC_OK) return rc__; \
+  } while (0)
+
+enum KernelGroup { KG_FWD = 0, KG_BWD = 1, KG_PREP = 2, KG_UPDATE = 3, KG_COUNT = 4 };
+
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+}  // namespace bhmc
+
+struct bhmc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // optional per-group device timing (CUDA events on the launching stream)
+  bool timing = false;
+  std::vector<bhmc::EventPair> pool[bhmc::KG_COUNT];
+  size_t used[bhmc::KG_COUNT] = {0, 0, 0, 0};
+  double ms_acc[bhmc::KG_COUNT] = {0, 0, 0, 0};
+  int64_t n_acc[bhmc::KG_COUNT] = {0, 0, 0, 0};
+  // grow-only device scratch
+  void* scratch[8] = {nullptr};
+  size_t scratch_bytes[8] = {0};
+  // pinned staging for small per-step host->device uploads
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  cudaEvent_t pinned_ev = nullptr;
+  bool pinned_inflight = false;
+
+  int get_scratch(int slot, size_t bytes, void** out);
+  int get_pinned(size_t bytes, void** out);
+  void begin_group(int group);
+  void end_group(int group);
+  int flush_timing();
+};
+
+namespace bhmc {
+
+struct GroupTimer {
+  bhmc_ctx* ctx;
+  int group;
+  GroupTimer(bhmc_ctx* c, int g) : ctx(c), group(g) { ctx->begin_group(g); }
+  ~GroupTimer() { ctx->end_group(group); }
+};
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------
+// model interface used by the sampler drivers
+// ---------------------------------------------------------------------------------------
+struct ModelBase {
+  bhmc_ctx* ctx = nullptr;
+  int64_t P = 0;
+  int n_vars = 0;
+  int64_t var_off[BHMC_MAX_VARS] = {0};
+  int64_t var_len[BHMC_MAX_VARS] = {0};
+  virtual ~ModelBase() {}
+  // g may be nullptr (log-lik only). stat[c] (double, device) receives the model's scalar.
+  virtual int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g,
+                   double* stat) = 0;
+  // potential used by the Metropolis test: U = a*stat + b (+ sum_v cv[v]*|q_v|^2)
+  virtual void energy_coeffs(int64_t nrows, double* a, double* b, double* cv) const = 0;
+  virtual int64_t default_rows() const { return 0; }
+};
+
+// ---- update.cu --------------------------------------------------------------------------
+struct UpdateArgs {
+  float* q;
+  float* p;
+  const float* g;
+  int64_t ld, P;
+  int C;
+  // post: p = f_post*p - a_post*g + n_post*z   on slice [post_off, post_off+post_len)
+  int64_t post_off, post_len;
+  int it_post;
+  float f_post, a_post, n_post;
+  // pre: p -= a_pre*g ; q += eps*p             on slice [pre_off, pre_off+pre_len)
+  int64_t pre_off, pre_len;
+  int it_pre;
+  float a_pre, eps;
+  const int32_t* L;  // per-chain path length (device); chain active for iteration it iff it < L-1
+  // noise for the post part: injected (device, [C, ld_z] rows) or Philox
+  const float* z;
+  int64_t ld_z;
+  uint64_t seed;
+  int64_t chain_id0;
+  uint32_t stream_lo, stream_hi;
+  // latch of the model scalar produced by the gradient evaluation that preceded this update
+  const double* stat;  // [C]
+  double* stat_new;    // [C] written where the chain was active for it_post
+};
+int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a);
+
+struct BeginArgs {
+  const float* q;
+  float* q_new;
+  float* p0;
+  float* p_new;
+  int64_t ld, P;
+  int C;
+  const float* z;  // injected N(0,1) [C,P] compact (ld_z) or nullptr
+  int64_t ld_z;
+  uint64_t seed;
+  int64_t chain_id0;
+  uint32_t stream_lo, stream_hi;
+  double* kin0;  // [C] zeroed by the launcher, receives 0.5*sum p^2
+};
+int launch_hmc_begin(bhmc_ctx* ctx, const BeginArgs& a);
+
+int launch_kinetic(bhmc_ctx* ctx, const float* p, int64_t ld, int64_t P, int C, double* kin);
+// per-variable sum of squares: out[c*n_vars + v]
+int launch_sumsq(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, const int64_t* off,
+                 const int64_t* len, double* out);
+
+struct AcceptArgs {
+  float* q;            // in/out: current state, overwritten by the proposal where accepted
+  const float* q_new;
+  float* p_out;        // in: p0 ; out: accepted ? sign*p_new : p0
+  const float* p_new;
+  int64_t ld, P;
+  int C;
+  float p_sign;        // -1 for HMC (hmc.py:58-59), +1 for SGHMC
+  const double* stat_cur;
+  const double* stat_new;
+  const double* extra_cur;  // optional sum_v cv*|q_v|^2 terms (may be nullptr)
+  const double* extra_new;
+  double ea, eb;       // U = ea*stat + eb + extra
+  const double* kin0;
+  const double* kin1;
+  const double* u;     // [C] injected uniforms (device) or nullptr -> Philox
+  uint64_t seed;
+  int64_t chain_id0;
+  uint32_t stream_lo, stream_hi;
+  int reject_nan;
+  float* sample;       // [C, P] compact or nullptr
+  double* loss;        // [C] or nullptr
+  double* accept_prob; // [C] or nullptr
+  int32_t* accepted;   // [C] or nullptr
+};
+int launch_accept(bhmc_ctx* ctx, const AcceptArgs& a);
+
+struct SgldArgs {
+  float* q;
+  float* p;
+  const float* g;
+  int64_t ld, P;
+  int C;
+  float eps;      // p = 2*eps*z - 0.5*eps*g ; q += p   (sgld.py:31-46)
+  const float* z; // injected or nullptr
+  int64_t ld_z;
+  uint64_t seed;
+  int64_t chain_id0;
+  uint32_t stream_lo, stream_hi;
+};
+int launch_sgld_update(bhmc_ctx* ctx, const SgldArgs& a);
+// heavy-ball: m = gamma*m - eps*g ; q += m  (sgd.py:40-41)
+int launch_sgd_update(bhmc_ctx* ctx, float* q, float* m, const float* g, int64_t ld, int64_t P, int C,
+                      float gamma, float eps);
+int launch_copy_rows(bhmc_ctx* ctx, const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t P,
+                     int C);
+int launch_philox_normal(bhmc_ctx* ctx, float* out, int C, int64_t P, int64_t ld, uint64_t seed,
+                         int64_t chain_id0, uint32_t stream_lo, uint32_t stream_hi);
+int launch_affine(bhmc_ctx* ctx, const double* in, double a, double b, const double* extra, double* out, int n);
+
+// ---- softmax_simt.cu / softmax_tc.cu -----------------------------------------------------
+struct SoftmaxData {
+  int64_t N = 0;
+  int D = 0, K = 0;
+  const float* X = nullptr;        // [N, D] fp32 (bound or owned)
+  const int32_t* labels = nullptr; // [N]
+  bool owned = false;
+  // tensor-core operand copies (built by tc_bind): bf16 hi / lo
+  int Kp = 0;                       // classes padded per chain (even)
+  int64_t Dp = 0;                   // feature stride of Xa (multiple of 8 elements)
+  int64_t Npad = 0;                 // row stride of Xt (multiple of 8 elements)
+  void* Xa_hi = nullptr;            // [N, Dp]   K-major A of the forward GEMM
+  void* Xa_lo = nullptr;
+  void* Xt_hi = nullptr;            // [Dt, Npad] K-major A of the backward GEMM (row D = ones)
+  void* Xt_lo = nullptr;
+  int64_t Dt = 0;                   // D+1 rows (ones row feeds the bias gradient)
+  bool has_lo = false;
+  bool tc_ready = false;
+};
+
+int simt_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
+                      int64_t row0, int64_t nrows, float* g, double* loglik);
+int simt_softmax_predict(bhmc_ctx* ctx, int D, int K, const float* q, int C, int64_t ld, const float* X,
+                         int64_t nrows, float* probs, int32_t* labels);
+
+int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo);
+void tc_softmax_release(SoftmaxData& d);
+int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
+                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3);
+
+}  // namespace bhmc

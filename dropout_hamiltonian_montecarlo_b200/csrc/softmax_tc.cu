@@ -1,0 +1,732 @@
+// BHMC_PREC_BF16X3 / BHMC_PREC_BF16: the two contractions of the softmax-regression gradient
+// on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by
+// TMA into 128B-swizzled shared memory), chains batched on the GEMM N dimension.
+//
+// Reference arithmetic (hamiltonian/models/cpu/softmax.py):
+//   forward  :38-43,63-72  Z = X.W + b, clip, row softmax / log-sum-exp      -> k_tc_gemm<MODE_FWD>
+//   backward :52-60        grad = X^T (P - Y) + alpha W, sum_n (P - Y) + alpha b -> k_tc_gemm<MODE_BWD> + k_tc_reduce
+//
+// Layout in HBM (all bf16 operands are "K-major": the contraction index is contiguous)
+//   Xa_{hi,lo} [N, Dp]        forward A, built once at bind time   (Dp = D rounded up to 8)
+//   Xt_{hi,lo} [D+1, Npad]    backward A = X^T plus a row of ones that yields the bias gradient
+//   Wt_{hi,lo} [C*KP, Dp]     forward B, rebuilt from the fp32 chain state before every evaluation
+//   DmT_{hi,lo}[C*KP, Mpad]   (P - Y)^T written by the forward epilogue, backward B
+//   part [S, Mt*128, Nt*BN]   fp32 split-K partials of the backward GEMM (deterministic reduce)
+// bf16x3: every fp32 value v is split v = hi + lo (two bf16); a product uses 3 MMAs
+// (hi*hi + hi*lo + lo*hi) accumulated in fp32, which restores ~fp32 accuracy.
+//
+// Kernel structure (one persistent CTA per SM, 256 threads):
+//   warp 0 : TMA producer  (cp.async.bulk.tensor -> smem ring, mbarrier expect_tx)
+//   warp 1 : MMA issuer    (one thread: tcgen05.mma, tcgen05.commit -> ring "empty" / TMEM "full")
+//   warp 2 : TMEM allocator
+//   warps 4-7 : epilogue   (tcgen05.ld -> registers -> fused math -> global)
+// Accumulators are double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "internal.cuh"
+
+namespace bhmc {
+
+static constexpr int BM = 128;        // UMMA M
+static constexpr int BK = 64;         // bf16 elements per stage row = 128 B = one swizzle span
+static constexpr int UMMA_K = 16;
+static constexpr int MAX_STAGES = 8;
+static constexpr int NTHREADS = 256;
+static constexpr int TMEM_COLS = 512;
+static constexpr int TMEM_BUF_COLS = 256;
+static constexpr float CLIP_HI = 36.04365338911715f;
+static constexpr float CLIP_LO = -708.3964185322641f;
+
+enum { MODE_FWD = 0, MODE_BWD = 1 };
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap (sticky error, process exits) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    long long now = clock64();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > 4000000000LL) {  // ~2 s
+      printf("bhmc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;           // leading byte offset: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32; // stride byte offset
+  d |= (uint64_t)1 << 46;           // descriptor version
+  d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_ld<1>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<2>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// KP consecutive columns via a greedy power-of-two decomposition (KP = 10 -> x8 + x2)
+template <int KP>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+  constexpr int N1 = KP >= 32 ? 32 : KP >= 16 ? 16 : KP >= 8 ? 8 : KP >= 4 ? 4 : KP >= 2 ? 2 : 1;
+  tmem_ld<N1>(taddr, r);
+  if constexpr (KP - N1 > 0) tmem_ld_cols<KP - N1>(taddr + N1, r + N1);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+  // work decomposition
+  int m_tiles, n_tiles, n_split;  // work items = n_split * m_tiles * n_tiles
+  int k_chunks;                   // BK-chunks of the contraction dimension (total)
+  int chunks_per_split;
+  int BN;                         // UMMA N (multiple of 16, <= 256)
+  int stages;
+  int split3;                     // 1: hi/lo operands, 3 MMAs per product
+  int a_k0, a_m0;                 // coordinate offsets of A in its tensor map (contraction, row)
+  // forward epilogue
+  int C, K, cpt;                  // chains, classes, chains per N tile (BN = cpt*KP)
+  int D;
+  int64_t ld;                     // chain row stride of q
+  const float* q;                 // bias lives at q[c*ld + D*K + k]
+  const int32_t* labels;          // already offset to the row window
+  int64_t nrows;
+  int64_t Mpad;                   // row stride of DmT
+  __nv_bfloat16* dmt_hi;
+  __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
+  double* loglik;
+  int write_dm;
+  // backward epilogue
+  float* part;                    // [n_split, m_tiles*128, n_tiles*BN]
+};
+
+template <int MODE, int KP>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_bytes = BM * BK * 2, b_bytes = p.BN * BK * 2;
+  const int stage_bytes = (p.split3 ? 2 : 1) * (a_bytes + b_bytes);
+  const int num_work = p.n_split * p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int s = w / (p.m_tiles * p.n_tiles), rem = w % (p.m_tiles * p.n_tiles);
+        int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
+        for (int k = k_begin; k < k_end; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_expect_tx(full, (uint32_t)stage_bytes);
+          uint32_t sa = smem_base + stage * stage_bytes;
+          int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM;
+          tma_load_2d(sa, &tmA_hi, full, ak, am);
+          if (p.split3) {
+            tma_load_2d(sa + a_bytes, &tmA_lo, full, ak, am);
+            tma_load_2d(sa + 2 * a_bytes, &tmB_hi, full, k * BK, nt * p.BN);
+            tma_load_2d(sa + 2 * a_bytes + b_bytes, &tmB_lo, full, k * BK, nt * p.BN);
+          } else {
+            tma_load_2d(sa + a_bytes, &tmB_hi, full, k * BK, nt * p.BN);
+          }
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        int s = w / (p.m_tiles * p.n_tiles);
+        int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
+        int buf = it & 1;
+        uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+        for (int k = k_begin; k < k_end; ++k) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tcgen05_fence_after();
+          uint32_t sa = smem_base + stage * stage_bytes;
+          uint64_t a_hi = make_smem_desc(sa);
+          uint64_t a_lo = make_smem_desc(sa + a_bytes);
+          uint64_t b_hi = make_smem_desc(sa + (p.split3 ? 2 : 1) * a_bytes);
+          uint64_t b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle span
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (k > k_begin || ks > 0) ? 1u : 0u);
+            if (p.split3) {
+              umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));  // smem slot reusable once these MMAs retire
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+        umma_commit(smem_u32(&bar_tfull[buf]));  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;             // TMEM lane quarter this warp may access
+    const int t = ew * 32 + lane;        // accumulator row handled by this thread
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      int s = w / (p.m_tiles * p.n_tiles), rem = w % (p.m_tiles * p.n_tiles);
+      int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+      int buf = it & 1;
+      uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+      if constexpr (MODE == MODE_FWD) {
+        const int64_t r = (int64_t)mt * BM + t;  // row inside the window
+        const bool valid = r < p.nrows;
+        const int y = valid ? p.labels[r] : 0;
+        for (int cc = 0; cc < p.cpt; ++cc) {
+          const int c = nt * p.cpt + cc;
+          if (c >= p.C) break;  // warp-uniform
+          uint32_t raw[KP];
+          tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
+          tmem_ld_wait();
+          const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * p.K;
+          float z[KP];
+          float m = -INFINITY, zy = 0.f;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            if (k < p.K) {
+              float v = __uint_as_float(raw[k]) + __ldg(bias + k);
+              v = fmaxf(fminf(v, CLIP_HI), CLIP_LO);
+              z[k] = v;
+              m = fmaxf(m, v);
+              if (k == y) zy = v;
+            } else {
+              z[k] = -INFINITY;
+            }
+          }
+          float ssum = 0.f;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            z[k] = (k < p.K) ? __expf(z[k] - m) : 0.f;
+            ssum += z[k];
+          }
+          float inv = 1.0f / ssum;
+          float ll = valid ? (zy - m - logf(ssum)) : 0.f;
+          if (p.write_dm) {
+            __nv_bfloat16* dh = p.dmt_hi + ((int64_t)c * KP) * p.Mpad + r;
+            __nv_bfloat16* dl = p.dmt_lo ? p.dmt_lo + ((int64_t)c * KP) * p.Mpad + r : nullptr;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+              if (k < p.K) {
+                float d = valid ? (z[k] * inv - (k == y ? 1.f : 0.f)) : 0.f;
+                __nv_bfloat16 h = __float2bfloat16_rn(d);
+                dh[(int64_t)k * p.Mpad] = h;
+                if (dl) dl[(int64_t)k * p.Mpad] = __float2bfloat16_rn(d - __bfloat162float(h));
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+          if (lane == 0) atomicAdd(p.loglik + c, (double)ll);
+        }
+      } else {
+        // backward: dump the fp32 accumulator tile to the split-K partial buffer (coalesced per row)
+        const int64_t rows = (int64_t)p.m_tiles * BM, cols = (int64_t)p.n_tiles * p.BN;
+        float* dst = p.part + ((int64_t)s * rows + (int64_t)mt * BM + t) * cols + (int64_t)nt * p.BN;
+        for (int j0 = 0; j0 < p.BN; j0 += 16) {
+          uint32_t raw[16];
+          tmem_ld<16>(tacc + (uint32_t)j0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            *reinterpret_cast<uint4*>(dst + j0 + 4 * v) = make_uint4(raw[4 * v], raw[4 * v + 1], raw[4 * v + 2], raw[4 * v + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(&bar_tempty[buf]));
+    }
+  }
+  // ---- teardown ----
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// Xa[n, d] = split(X[n, d]) with zero padding d in [D, Dp)
+__global__ void k_split_rows(const float* __restrict__ X, int64_t N, int D, int64_t Dp, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo) {
+  int64_t n = blockIdx.y;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < Dp; d += (int64_t)gridDim.x * blockDim.x) {
+    float v = d < D ? X[n * D + d] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[n * Dp + d] = h;
+    if (lo) lo[n * Dp + d] = l;
+  }
+}
+
+// Xt[d, n] = split(X[n, d]) for d < D ; Xt[D, n] = 1 ; zero padding n in [N, Npad)
+__global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D, int64_t Npad,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  int64_t n0 = (int64_t)blockIdx.x * 32;
+  int d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int64_t n = n0 + i;
+    int d = d0 + threadIdx.x;
+    float v = 0.f;
+    if (n < N) v = d < D ? X[n * D + d] : (d == D ? 1.f : 0.f);
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int d = d0 + i;
+    int64_t n = n0 + threadIdx.x;
+    if (d <= D && n < Npad) {
+      __nv_bfloat16 h, l;
+      split_bf16(tile[threadIdx.x][i], h, l);
+      hi[(int64_t)d * Npad + n] = h;
+      if (lo) lo[(int64_t)d * Npad + n] = l;
+    }
+  }
+}
+
+// Wt[(c*KP + k), d] = split(q[c, d*K + k]) (zero for k >= K or d >= D); loglik[c] = 0
+__global__ void k_tc_prep(const float* __restrict__ q, int64_t ld, int D, int K, int KP, int64_t Dp,
+                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, double* __restrict__ loglik) {
+  int c = blockIdx.y;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loglik) loglik[c] = 0.0;
+  int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= Dp) return;
+  const float* src = q + (int64_t)c * ld + d * K;
+  for (int k = 0; k < KP; ++k) {
+    float v = (k < K && d < D) ? src[k] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    int64_t o = ((int64_t)c * KP + k) * Dp + d;
+    hi[o] = h;
+    if (lo) lo[o] = l;
+  }
+}
+
+// g[c, d*K + k] = alpha*q[c, d*K + k] + sum_s part[s, d, c*KP + k]      (d <= D: row D is the bias gradient)
+__global__ void k_tc_reduce(const float* __restrict__ part, int n_split, int64_t rows, int64_t cols, int K, int KP,
+                            int64_t P, const float* __restrict__ q, float* __restrict__ g, int64_t ld, float alpha) {
+  int c = blockIdx.y;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  float v = 0.f;
+  if (i < P) {
+    int64_t d = i / K;
+    int k = (int)(i - d * K);
+    const float* src = part + d * cols + (int64_t)c * KP + k;
+    for (int s = 0; s < n_split; ++s) v += src[(int64_t)s * rows * cols];
+    v += alpha * q[(int64_t)c * ld + i];
+  }
+  g[(int64_t)c * ld + i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 matrix [outer, inner] (inner contiguous, row stride in elements), box = [box_outer, 64], 128B swizzle
+static int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                    uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    return BHMC_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu stride=%llu box=%u", (int)r, base,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_elems, box_outer);
+    return BHMC_ERR_CUDA;
+  }
+  return BHMC_OK;
+}
+
+static int pick_kp(int K) {
+  const int opts[] = {4, 8, 10, 16, 24, 40, 64};
+  for (int o : opts)
+    if (K <= o) return o;
+  return 0;
+}
+
+// chains per N tile: BN = cpt*KP must be a multiple of 16 and <= 256; minimise padded work
+static int pick_cpt(int KP, int C) {
+  int unit = 1;
+  while ((unit * KP) % 16) ++unit;
+  int best = unit;
+  double best_cost = 1e30;
+  for (int cpt = unit; cpt * KP <= 256; cpt += unit) {
+    int tiles = (C + cpt - 1) / cpt;
+    // padded columns + a small per-tile overhead that favours wide tiles
+    double cost = (double)tiles * cpt * KP * (1.0 + 24.0 / (cpt * KP));
+    if (cost < best_cost - 1e-9) best_cost = cost, best = cpt;
+  }
+  return best;
+}
+
+int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
+  tc_softmax_release(d);
+  d.Kp = pick_kp(d.K);
+  if (!d.Kp) {
+    set_error("tensor-core path supports at most 64 classes (got %d); use BHMC_PREC_FP32", d.K);
+    return BHMC_ERR_UNSUPPORTED;
+  }
+  d.Dp = round_up(d.D, 8);
+  d.Npad = round_up(d.N, 8);
+  d.Dt = d.D + 1;
+  size_t a_bytes = (size_t)d.N * d.Dp * 2, t_bytes = (size_t)d.Dt * d.Npad * 2;
+  BHMC_CUDA_OK(cudaMalloc(&d.Xa_hi, a_bytes));
+  BHMC_CUDA_OK(cudaMalloc(&d.Xt_hi, t_bytes));
+  if (want_lo) {
+    BHMC_CUDA_OK(cudaMalloc(&d.Xa_lo, a_bytes));
+    BHMC_CUDA_OK(cudaMalloc(&d.Xt_lo, t_bytes));
+  }
+  d.has_lo = want_lo;
+  {
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(d.Dp, 256), 65535), (unsigned)1);
+    // rows can exceed the 65535 limit of gridDim.y -> loop over row blocks
+    for (int64_t n0 = 0; n0 < d.N; n0 += 65535) {
+      int64_t cnt = std::min<int64_t>(65535, d.N - n0);
+      dim3 g(grid.x, (unsigned)cnt);
+      k_split_rows<<<g, 256, 0, ctx->stream>>>(d.X + n0 * d.D, cnt, d.D, d.Dp, (__nv_bfloat16*)d.Xa_hi + n0 * d.Dp,
+                                               want_lo ? (__nv_bfloat16*)d.Xa_lo + n0 * d.Dp : nullptr);
+      ctx->launches++;
+    }
+  }
+  {
+    dim3 grid((unsigned)ceil_div(d.Npad, 32), (unsigned)ceil_div(d.Dt, 32));
+    k_split_transpose<<<grid, dim3(32, 8), 0, ctx->stream>>>(d.X, d.N, d.D, d.Npad, (__nv_bfloat16*)d.Xt_hi,
+                                                             (__nv_bfloat16*)d.Xt_lo);
+    ctx->launches++;
+  }
+  BHMC_CUDA_OK(cudaGetLastError());
+  d.tc_ready = true;
+  return BHMC_OK;
+}
+
+void tc_softmax_release(SoftmaxData& d) {
+  cudaFree(d.Xa_hi);
+  cudaFree(d.Xa_lo);
+  cudaFree(d.Xt_hi);
+  cudaFree(d.Xt_lo);
+  d.Xa_hi = d.Xa_lo = d.Xt_hi = d.Xt_lo = nullptr;
+  d.tc_ready = false;
+}
+
+template <int MODE, int KP>
+static int launch_gemm(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                       const CUtensorMap& b_lo, const TcParams& p) {
+  int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + p.BN * BK * 2);
+  size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int work = p.n_split * p.m_tiles * p.n_tiles;
+  int grid = std::min(work, ctx->sm_count);
+  k_tc_gemm<MODE, KP><<<grid, NTHREADS, smem, ctx->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+template <int KP>
+static int launch_fwd_kp(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                         const CUtensorMap& b_lo, const TcParams& p) {
+  return launch_gemm<MODE_FWD, KP>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+}
+
+int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
+                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3) {
+  BHMC_CHECK_ARG(d.tc_ready, "tensor-core operands were not prepared at bind time (precision_mask)");
+  BHMC_CHECK_ARG(!split3 || d.has_lo, "bf16x3 needs the lo operand copies (precision_mask bit 1 at bind time)");
+  BHMC_CHECK_ARG(row0 >= 0 && nrows > 0 && row0 + nrows <= d.N, "row window [%lld,+%lld) outside the %lld bound rows",
+                 (long long)row0, (long long)nrows, (long long)d.N);
+  const int KP = d.Kp, K = d.K, D = d.D;
+  const int cpt = pick_cpt(KP, C);
+  const int BN = cpt * KP;
+  const int n_tiles = (int)ceil_div(C, cpt);
+  const int64_t ncols = (int64_t)C * KP;  // rows of Wt / DmT
+  const int64_t Mpad = round_up(nrows, BM);
+  const int64_t P = (int64_t)(D + 1) * K;
+  const int nmat = split3 ? 2 : 1;
+  const int stage_bytes = nmat * (BM * BK * 2 + BN * BK * 2);
+  const int stages = std::max(2, std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes)));
+
+  // scratch: slot 1 = Wt hi|lo, slot 2 = DmT hi|lo, slot 3 = split-K partials
+  void* wt = nullptr;
+  size_t wt_bytes = (size_t)ncols * d.Dp * 2;
+  BHMC_TRY(ctx->get_scratch(1, wt_bytes * 2, &wt));
+  __nv_bfloat16* wt_hi = (__nv_bfloat16*)wt;
+  __nv_bfloat16* wt_lo = (__nv_bfloat16*)((char*)wt + wt_bytes);
+
+  {
+    GroupTimer t(ctx, KG_PREP);
+    dim3 grid((unsigned)ceil_div(d.Dp, 128), C);
+    k_tc_prep<<<grid, 128, 0, ctx->stream>>>(q, ld, D, K, KP, d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
+    ctx->launches++;
+  }
+
+  void* dmt = nullptr;
+  size_t dmt_bytes = (size_t)ncols * Mpad * 2;
+  __nv_bfloat16 *dmt_hi = nullptr, *dmt_lo = nullptr;
+  if (g) {
+    BHMC_TRY(ctx->get_scratch(2, dmt_bytes * 2, &dmt));
+    dmt_hi = (__nv_bfloat16*)dmt;
+    dmt_lo = split3 ? (__nv_bfloat16*)((char*)dmt + dmt_bytes) : nullptr;
+  }
+
+  // ---- forward: Z[rows, C*KP] = Xa[rows, Dp] . Wt^T ----
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  BHMC_TRY(make_map(&a_hi, d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  BHMC_TRY(make_map(&b_hi, wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+  if (split3) {
+    BHMC_TRY(make_map(&a_lo, d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+    BHMC_TRY(make_map(&b_lo, wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+  } else {
+    a_lo = a_hi;
+    b_lo = b_hi;
+  }
+  TcParams p{};
+  p.m_tiles = (int)(Mpad / BM);
+  p.n_tiles = n_tiles;
+  p.n_split = 1;
+  p.k_chunks = (int)ceil_div(D, BK);
+  p.chunks_per_split = p.k_chunks;
+  p.BN = BN;
+  p.stages = stages;
+  p.split3 = split3 ? 1 : 0;
+  p.a_k0 = 0;
+  p.a_m0 = (int)row0;
+  p.C = C;
+  p.K = K;
+  p.cpt = cpt;
+  p.D = D;
+  p.ld = ld;
+  p.q = q;
+  p.labels = d.labels + row0;
+  p.nrows = nrows;
+  p.Mpad = Mpad;
+  p.dmt_hi = dmt_hi;
+  p.dmt_lo = dmt_lo;
+  p.loglik = loglik;
+  p.write_dm = g ? 1 : 0;
+  p.part = nullptr;
+  {
+    GroupTimer t(ctx, KG_FWD);
+    int rc;
+    switch (KP) {
+      case 4: rc = launch_fwd_kp<4>(ctx, a_hi, a_lo, b_hi, b_lo, p); break;
+      case 8: rc = launch_fwd_kp<8>(ctx, a_hi, a_lo, b_hi, b_lo, p); break;
+      case 10: rc = launch_fwd_kp<10>(ctx, a_hi, a_lo, b_hi, b_lo, p); break;
+      case 16: rc = launch_fwd_kp<16>(ctx, a_hi, a_lo, b_hi, b_lo, p); break;
+      case 24: rc = launch_fwd_kp<24>(ctx, a_hi, a_lo, b_hi, b_lo, p); break;
+      case 40: rc = launch_fwd_kp<40>(ctx, a_hi, a_lo, b_hi, b_lo, p); break;
+      case 64: rc = launch_fwd_kp<64>(ctx, a_hi, a_lo, b_hi, b_lo, p); break;
+      default: set_error("unsupported KP %d", KP); rc = BHMC_ERR_UNSUPPORTED;
+    }
+    BHMC_TRY(rc);
+  }
+  if (!g) return BHMC_OK;
+
+  // ---- backward: G[D+1, C*KP] = Xt[D+1, rows] . DmT^T, split over row slabs ----
+  TcParams b{};
+  b.m_tiles = (int)ceil_div(d.Dt, BM);
+  b.n_tiles = n_tiles;
+  b.k_chunks = (int)ceil_div(nrows, BK);
+  int tiles = b.m_tiles * b.n_tiles;
+  int want = std::max(1, ctx->sm_count / tiles);
+  want = std::min(want, std::max(1, b.k_chunks / 4));  // keep >= 4 chunks per slab
+  b.chunks_per_split = (int)ceil_div(b.k_chunks, want);
+  b.n_split = (int)ceil_div(b.k_chunks, b.chunks_per_split);
+  b.BN = BN;
+  b.stages = stages;
+  b.split3 = split3 ? 1 : 0;
+  b.a_k0 = (int)row0;
+  b.a_m0 = 0;
+  int64_t prow = (int64_t)b.m_tiles * BM, pcol = (int64_t)b.n_tiles * BN;
+  void* part = nullptr;
+  BHMC_TRY(ctx->get_scratch(3, sizeof(float) * (size_t)b.n_split * prow * pcol, &part));
+  b.part = (float*)part;
+  BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, BM));
+  BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)Mpad, (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
+  if (split3) {
+    BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, BM));
+    BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)Mpad, (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
+  } else {
+    a_lo = a_hi;
+    b_lo = b_hi;
+  }
+  {
+    GroupTimer t(ctx, KG_BWD);
+    BHMC_TRY((launch_gemm<MODE_BWD, 1>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
+    dim3 grid((unsigned)ceil_div(ld, 256), C);
+    k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, K, KP, P, q, g, ld, alpha);
+    ctx->launches++;
+  }
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+}  // namespace bhmc

@@ -1,0 +1,209 @@
+"""``hmc`` -- drop-in for reference ``hamiltonian/inference/cpu/hmc.py`` (``gpu/hmc.py`` is its
+CuPy twin), running ``n_chains`` chains batched on one B200 with no host round-trip per
+leapfrog step.
+
+Reference semantics kept (SURVEY 8(a'), all cited lines in ``inference/cpu/hmc.py``):
+  * ``step`` redraws the momentum (:41), draws L = ceil(2 u path/eps) (:46), runs L-1
+    Gauss-Seidel sweeps with the (eps/2, eps) kick pattern (:49-54), flips the momentum
+    (:58-59) and does the Metropolis test on mean-NLP + kinetic energy (:60-71).
+  * ``sample`` draws and discards one momentum (:93), runs ``burnin`` then ``niter`` steps,
+    records q and ``loss[i] = NLP(q)`` per step (:108-116).
+Random numbers: with ``rng=None`` (default) all draws come from the in-kernel Philox
+generator.  If the caller passes an ``rng`` (``RandomState``-like), draws are taken on the
+host from ``rng.normal`` / the global ``np.random.rand`` *in the reference's consumption
+order* and injected, so a chain reproduces the reference trajectory for the same seeds.
+"""
+import numpy as np
+import torch
+
+from ...._lib import KIND, PREC
+from ....runtime import SamplerHandle
+
+
+class DualAveragingStepSize:
+    """hmc.py:141-176 (host scalar logic; the reference only ever calls update() once)."""
+
+    def __init__(self, initial_step_size, target_accept=0.8, gamma=0.05, t0=10.0, kappa=0.75):
+        self.mu = np.log(10 * initial_step_size)
+        self.target_accept = target_accept
+        self.gamma = gamma
+        self.t = t0
+        self.kappa = kappa
+        self.error_sum = 0
+        self.log_averaged_step = 0
+
+    def update(self, p_accept):
+        self.error_sum += self.target_accept - p_accept
+        log_step = self.mu - self.error_sum / (np.sqrt(self.t) * self.gamma)
+        eta = self.t ** -self.kappa
+        self.log_averaged_step = eta * log_step + (1 - eta) * self.log_averaged_step
+        self.t += 1
+        return np.exp(log_step), np.exp(self.log_averaged_step)
+
+
+class _ChainSampler:
+    """Shared plumbing of hmc / sgld / sghmc / sgd: start-point handling and handle caching."""
+
+    kind = "hmc"
+
+    def __init__(self, model, start_p, path_length=1.0, step_size=0.1, verbose=True, *, n_chains=None, seed=0,
+                 sweep="reference", path_length_mode="per_chain", integrator="reference", precision=None,
+                 reject_nan=False, chain_id0=0, sign="reference"):
+        self.start = start_p
+        self.step_size = step_size
+        self.path_length = path_length
+        self.model = model
+        self.verbose = verbose
+        self.n_chains = n_chains
+        self.seed = int(seed)
+        self.sweep = sweep
+        self.path_length_mode = path_length_mode
+        self.integrator = integrator
+        self.precision = precision or getattr(model, "precision", "bf16x3")
+        self.reject_nan = reject_nan
+        self.chain_id0 = int(chain_id0)
+        self.sign = sign
+        self._sampler = None
+        self._steps_done = 0
+        self.last_run = {}
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _names(self):
+        return list(self.start.keys())
+
+    def _setup(self, **args):
+        """Bind data, flatten the start point, (re)create the device sampler.  Returns
+        (handle, shapes, squeeze, like)."""
+        model = self.model
+        h = model.handle_for(**args)
+        shapes = model.var_shapes(h)
+        names = list(model.var_names)
+        if set(self._names()) != set(names):
+            raise ValueError("start_p keys %s do not match the model variables %s" % (self._names(), names))
+        q0, squeeze, like = model.flatten(self.start, shapes)
+        C = self.n_chains or q0.shape[0]
+        if q0.shape[0] == 1 and C > 1:
+            q0 = np.repeat(q0, C, axis=0)
+        elif q0.shape[0] != C:
+            raise ValueError("start_p has %d chains but n_chains=%d" % (q0.shape[0], C))
+        squeeze = squeeze and C == 1
+        # Gauss-Seidel groups follow the *dict order* of start_p (hmc.py:50); 'joint' moves everything at once
+        layout = dict(zip(names, zip(h.var_off, h.var_len)))
+        if self.sweep == "reference":
+            groups = [layout[v] for v in self._names()]
+        elif self.sweep == "joint":
+            groups = [(0, h.P)]
+        else:
+            raise ValueError("sweep must be 'reference' or 'joint'")
+        key = (id(h), C, tuple(groups), self.precision, self.path_length_mode, self.integrator, self.sign,
+               self.reject_nan, self.seed, self.chain_id0)
+        if self._sampler is None or self._sampler[0] != key:
+            if self._sampler is not None:
+                self._sampler[1].close()
+            s = SamplerHandle(h.ctx, h, KIND[self.kind], C, seed=self.seed, chain_id0=self.chain_id0,
+                              precision=PREC[self.precision], sweep=groups,
+                              shared_path=self.path_length_mode == "shared", leapfrog=self.integrator == "leapfrog",
+                              sghmc_descent=self.sign == "descent", reject_nan=self.reject_nan)
+            self._sampler = (key, s)
+        return h, shapes, squeeze, like, q0, self._sampler[1]
+
+    def _host_draws(self, rng, n_steps, C, h, shapes, scale=1.0):
+        """Reference consumption order (hmc.py:41,46,61): per step, per chain: rng.normal per
+        variable in start_p order, then two global uniforms."""
+        names = list(self.model.var_names)
+        layout = dict(zip(names, zip(h.var_off, h.var_len)))
+        z = np.empty((n_steps, C, h.P), dtype=np.float32)
+        u1 = np.empty((n_steps, C))
+        u2 = np.empty((n_steps, C))
+        for t in range(n_steps):
+            for c in range(C):
+                for v in self._names():
+                    o, l = layout[v]
+                    z[t, c, o:o + l] = np.asarray(rng.normal(0, 1, size=shapes[v])).reshape(-1)
+                u1[t, c] = np.random.rand()
+                u2[t, c] = np.random.rand()
+        return z, u1, u2
+
+
+class hmc(_ChainSampler):
+    kind = "hmc"
+
+    def step(self, state, momentum, rng, **args):
+        """hmc.py:39-64 -> (q, p, positions, momentums, acceptprob); ``momentum`` is ignored, as in
+        the reference."""
+        saved = self.start
+        self.start = state
+        try:
+            h, shapes, squeeze, like, q0, s = self._setup(**args)
+        finally:
+            self.start = saved
+        s.set_q(q0)
+        kw = {}
+        if rng is not None:
+            z, u1, u2 = self._host_draws(rng, 1, s.C, h, shapes)
+            kw = dict(z_momentum=torch.as_tensor(z), u_path=u1, u_accept=u2)
+        out = s.hmc_run(1, self.step_size, self.path_length, step0=self._steps_done, keep_samples=False, **kw)
+        self._steps_done += 1
+        q = self.model.unflatten(s.get(0), shapes, squeeze, like)
+        p = self.model.unflatten(s.get(1), shapes, squeeze, like)
+        a = out["accept_prob"].cpu().numpy()[0]
+        a = float(a[0]) if squeeze else a
+        return q, p, [state], [None], a
+
+    def sample(self, niter=1e4, burnin=1e3, rng=None, **args):
+        """hmc.py:90-119 -> (posterior, loss, sample_positions, sample_momentums)."""
+        niter, burnin = int(niter), int(burnin)
+        h, shapes, squeeze, like, q0, s = self._setup(**args)
+        s.set_q(q0)
+        C = s.C
+        if rng is not None:  # hmc.py:93 -- one momentum drawn and discarded
+            for _ in range(C):
+                for v in self._names():
+                    rng.normal(0, 1, size=shapes[v])
+        n_grad = 0
+        accept_sum = 0.0
+        chunk = max(1, min(512, (256 << 20) // max(1, 4 * C * h.P)))  # bound injected-tape / sample memory
+
+        def run(n, keep):
+            nonlocal n_grad, accept_sum
+            outs = []
+            done = 0
+            while done < n:
+                m = min(chunk, n - done)
+                kw = {}
+                if rng is not None:
+                    z, u1, u2 = self._host_draws(rng, m, C, h, shapes)
+                    kw = dict(z_momentum=torch.as_tensor(z), u_path=u1, u_accept=u2)
+                o = s.hmc_run(m, self.step_size, self.path_length, step0=self._steps_done, keep_samples=keep, **kw)
+                self._steps_done += m
+                n_grad += o["n_grad_evals"]
+                if keep:
+                    outs.append((o["samples"].cpu().numpy(), o["loss"].cpu().numpy(), o["accept_prob"].cpu().numpy()))
+                else:
+                    accept_sum += float(o["accept_prob"].sum().item())
+                done += m
+            return outs
+
+        run(burnin, False)
+        if self.verbose and burnin > 0:
+            _, avg = DualAveragingStepSize(self.step_size).update(accept_sum / max(1, burnin * C))
+            print("adapted step size : ", avg)
+        outs = run(niter, True)
+        if outs:
+            samples = np.concatenate([o[0] for o in outs], axis=0)
+            loss = np.concatenate([o[1] for o in outs], axis=0)
+            acc = np.concatenate([o[2] for o in outs], axis=0)
+        else:
+            samples = np.zeros((0, C, h.P), np.float32)
+            loss = np.zeros((0, C))
+            acc = np.zeros((0, C))
+        posterior = self.model.unflatten(samples, shapes, squeeze, like)
+        if squeeze:
+            loss = loss[:, 0]
+        if self.verbose and niter > 0:
+            for i in range(0, niter, max(1, niter // 10)):
+                print("loss: {0:.4f}".format(float(np.mean(loss[i]))))
+        self.last_run = dict(n_grad_evals=n_grad, accept_prob=acc, n_chains=C)
+        # hmc.py:110-111 returns the pre-step position/momentum of every iteration; positions are
+        # recoverable from the samples, momenta are not kept on the device ring.
+        return posterior, loss, None, None

@@ -1,0 +1,134 @@
+"""``softmax(hyper)`` -- drop-in for reference ``hamiltonian/models/cpu/softmax.py`` (and its
+CuPy twin ``models/gpu/softmax.py``), evaluated for a *batch of chains* by libbhmc.so.
+
+Model protocol (seam 1): ``grad(par, X_train=, y_train=)``,
+``log_likelihood``, ``negative_log_posterior``, plus ``net`` / ``predict`` /
+``predict_stochastic`` / ``log_prior``.  ``par`` is the reference's dict
+``{'weights': [D,K], 'bias': [K]}``; a leading chain axis (``[C,D,K]`` / ``[C,K]``) evaluates C
+chains in one launch and returns arrays with the same leading axis.
+``y_train`` is the one-hot matrix of the reference (``utils.one_hot``) or integer labels.
+"""
+import numpy as np
+import torch
+
+from ... import _base
+from ....runtime import SoftmaxHandle, default_context
+from ...._lib import PREC, PRIOR
+
+
+class softmax(_base.ChainModel):
+    var_names = ("weights", "bias")
+
+    def __init__(self, _hyper, *, precision="bf16x3", prior="cpu", device=None):
+        super().__init__(device)
+        self.hyper = _hyper
+        self.precision = precision
+        self.prior = prior
+        self._bound = None  # (key, handle, keepalive)
+
+    # ---- data binding ------------------------------------------------------------------------
+    @staticmethod
+    def _labels_of(y, n_classes=None):
+        if isinstance(y, torch.Tensor):
+            y = y.detach().cpu().numpy()
+        y = np.asarray(y)
+        if y.ndim == 2:
+            lab = y.argmax(axis=1)
+            if not (np.all(y.max(axis=1) == 1) and np.all(np.abs(y.sum(axis=1) - 1) < 1e-6)):
+                raise ValueError("y_train must be one-hot (utils.one_hot) or integer labels")
+            return lab.astype(np.int32), y.shape[1]
+        return y.astype(np.int32), n_classes
+
+    def bind(self, X, y, n_classes=None):
+        """Bind (and cache) the data matrix: fp32 X on the device plus the bf16 operand copies the
+        tensor-core path streams.  Re-binding happens only when X / y are different objects."""
+        key = (_base.array_key(X), _base.array_key(y), self.precision)
+        if self._bound is not None and self._bound[0] == key:
+            return self._bound[1]
+        labels, k = self._labels_of(y, n_classes)
+        if k is None:
+            k = int(labels.max()) + 1
+        ctx = self.ctx
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            Xd = X.to(torch.float32).contiguous()
+        else:
+            Xd = torch.as_tensor(np.ascontiguousarray(np.asarray(X, dtype=np.float32))).to(ctx.device)
+        n, d = Xd.shape
+        h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
+        mask = 1 | (1 << PREC[self.precision])
+        h.bind(Xd, torch.as_tensor(labels).to(ctx.device), mask)
+        if self._bound is not None:
+            self._bound[1].close()
+        self._bound = (key, h, (X, y))
+        return h
+
+    def unbind(self):
+        if self._bound is not None:
+            self._bound[1].close()
+            self._bound = None
+
+    def var_shapes(self, handle):
+        return {"weights": (handle.D, handle.K), "bias": (handle.K,)}
+
+    def handle_for(self, **args):
+        return self.bind(args["X_train"], args["y_train"])
+
+    # ---- model protocol --------------------------------------------------------------------------
+    def grad(self, par, **args):
+        """softmax.py:45-61 -- gradient of the potential, summed over rows, + alpha*theta."""
+        h = self.handle_for(**args)
+        q, squeeze, like = self.flatten(par, self.var_shapes(h))
+        g, _ = h.grad(h.pack(q), 0, h.N, PREC[self.precision], True)
+        return self.unflatten(g[:, : h.P], self.var_shapes(h), squeeze, like)
+
+    def log_likelihood(self, par, **args):
+        """softmax.py:63-72."""
+        h = self.handle_for(**args)
+        q, squeeze, _ = self.flatten(par, self.var_shapes(h))
+        _, ll = h.grad(h.pack(q), 0, h.N, PREC[self.precision], False)
+        out = ll.cpu().numpy()
+        return float(out[0]) if squeeze else out
+
+    def log_prior(self, par, **args):
+        """softmax.py:22-30 (``prior='cpu'``, a constant) or models/gpu/softmax.py:29-39."""
+        k = 0.0
+        for v in par:
+            a = np.asarray(par[v].detach().cpu() if isinstance(par[v], torch.Tensor) else par[v])
+            if self.prior == "cpu":
+                k -= 0.5 * a.size * np.log(2 * np.pi) - 0.5 * a.size * np.log(self.hyper["alpha"])
+            else:
+                k -= 0.5 * self.hyper["alpha"] * np.sum(np.square(a)) / a.size
+        return k
+
+    def negative_log_posterior(self, par, **args):
+        """softmax.py:74-79: -(LL + log_prior)/N."""
+        h = self.handle_for(**args)
+        q, squeeze, _ = self.flatten(par, self.var_shapes(h))
+        out = h.nlp(h.pack(q), 0, h.N, PREC[self.precision]).cpu().numpy()
+        return float(out[0]) if squeeze else out
+
+    # ---- prediction (softmax.py:38-43,82-100) ----------------------------------------------------
+    def _predict(self, par, X, prob):
+        Xd = X if (isinstance(X, torch.Tensor) and X.is_cuda) else torch.as_tensor(
+            np.ascontiguousarray(np.asarray(X, dtype=np.float32))).to(self.ctx.device)
+        Xd = Xd.to(torch.float32).contiguous()
+        w = par["weights"]
+        d, k = tuple(w.shape[-2:])
+        h = self._bound[1] if (self._bound and self._bound[1].D == d and self._bound[1].K == k) else \
+            SoftmaxHandle(self.ctx, 1, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
+        q, squeeze, _ = self.flatten(par, {"weights": (d, k), "bias": (k,)})
+        probs, labels = h.predict(h.pack(q), Xd, want_probs=prob, want_labels=not prob)
+        out = (probs if prob else labels).cpu().numpy()
+        return out[0] if squeeze else out
+
+    def net(self, par, X):
+        return self._predict(par, X, True)
+
+    def predict(self, par, X, prob=False, batchsize=None):
+        return self._predict(par, X, prob)
+
+    def predict_stochastic(self, par, X, prob=False, p=0.5, batchsize=None):
+        """softmax.py:91-100: Bernoulli(p) input mask (host RNG, as the reference) then net()."""
+        Xn = np.asarray(X.detach().cpu() if isinstance(X, torch.Tensor) else X)
+        Z = np.random.binomial(1, p, size=Xn.shape)
+        return self._predict(par, np.multiply(Xn, Z), prob)

@@ -1,0 +1,284 @@
+"""GPU (B200): the CUDA path, called through the C ABI (ctypes) and the reference-facing Python
+classes, against the NumPy oracle and the golden vectors minted from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): trajectories within rtol 1e-4 (fp32 arithmetic vs the
+fp64 reference; atol covers entries that are ~0), accept/reject decisions identical.
+``fp32`` = CUDA-core checker path, ``bf16x3`` = tcgen05 split-precision path (parity mode),
+``bf16`` = single-pass tensor path (statistical mode, loose tolerance).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TapeRng, load_golden, replay_uniforms
+from oracle import hamiltonian_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.hmc import hmc  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sgd import sgd  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sghmc import sghmc  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sgld import sgld  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.mvn_gaussian import mvn_gaussian  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.softmax import softmax  # noqa: E402
+
+PRECS = ["fp32", "bf16x3"]
+
+
+def close(got, ref, rtol, atol_scale=1e-6, what=""):
+    ref = np.asarray(ref, dtype=np.float64)
+    got = np.asarray(got, dtype=np.float64)
+    atol = atol_scale * max(1.0, float(np.max(np.abs(ref)))) if ref.size else 0.0
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol, err_msg=what)
+
+
+# ------------------------------------------------------------------------------------------------
+# model protocol
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("case", ["small", "k10", "clip", "k38"])
+def test_softmax_model_golden(prec, case):
+    g = load_golden("softmax_model.npz")[case]
+    K = g["W"].shape[1]
+    m = softmax({"alpha": g["alpha"]}, precision=prec)
+    par = {"weights": g["W"], "bias": g["b"]}
+    Y = O.one_hot(g["y"], K)
+    got = m.grad(par, X_train=g["X"], y_train=Y)
+    rtol = {"fp32": 2e-5, "bf16x3": 1e-4, "bf16": 5e-2}[prec]
+    scale = {"fp32": 2e-6, "bf16x3": 2e-5, "bf16": 2e-2}[prec]
+    if case == "clip":  # saturated logits of magnitude ~1e2-1e3: absolute logit error scales with |z|
+        rtol, scale = rtol * 20, scale * 20
+    close(got["weights"], g["gW"], rtol, scale, "grad weights")
+    close(got["bias"], g["gb"], rtol, scale, "grad bias")
+    close(m.log_likelihood(par, X_train=g["X"], y_train=Y), g["ll"], rtol * 2, scale)
+    close(m.negative_log_posterior(par, X_train=g["X"], y_train=Y), g["nlp"], rtol * 2, scale)
+    if prec == "fp32":
+        close(m.net(par, g["X"]), g["probs"], 1e-4, 1e-6)
+        assert (m.predict(par, g["X"]) == g["probs"].argmax(1)).mean() > 0.99
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_softmax_chain_batch_and_window(prec):
+    """C chains in one launch == C independent oracle evaluations; a row window == the slice."""
+    rs = np.random.RandomState(0)
+    N, D, K, C, alpha = 700, 90, 10, 11, 0.05
+    X = rs.rand(N, D)
+    y = rs.randint(0, K, N)
+    W = rs.normal(0, .2, (C, D, K))
+    b = rs.normal(0, .2, (C, K))
+    m = softmax({"alpha": alpha}, precision=prec)
+    for (r0, r1) in [(0, N), (256, 256 + 300)]:
+        Xs, ys = X[r0:r1], y[r0:r1]
+        got = m.grad({"weights": W, "bias": b}, X_train=Xs, y_train=O.one_hot(ys, K))
+        ll = m.log_likelihood({"weights": W, "bias": b}, X_train=Xs, y_train=O.one_hot(ys, K))
+        for c in range(C):
+            ref = O.softmax_grad({"weights": W[c], "bias": b[c]}, Xs, O.one_hot(ys, K), alpha)
+            close(got["weights"][c], ref["weights"], 1e-4, 2e-5)
+            close(got["bias"][c], ref["bias"], 1e-4, 2e-5)
+            close(ll[c], O.softmax_log_likelihood({"weights": W[c], "bias": b[c]}, Xs, O.one_hot(ys, K)), 2e-6)
+
+
+def test_row_window_through_the_abi():
+    """row0/nrows of bhmc_model_grad select rows of the bound matrix without re-binding."""
+    from dropout_hamiltonian_montecarlo_b200.runtime import SoftmaxHandle, default_context
+    rs = np.random.RandomState(1)
+    N, D, K, C = 1000, 64, 10, 4
+    X = rs.rand(N, D).astype(np.float32)
+    y = rs.randint(0, K, N).astype(np.int32)
+    q = rs.normal(0, .2, (C, (D + 1) * K)).astype(np.float32)
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, N, D, K, 0.01)
+    h.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda())
+    for prec in (0, 1):
+        for (r0, n) in [(0, 1000), (130, 500), (936, 64), (999, 1)]:
+            g, ll = h.grad(h.pack(q), r0, n, prec)
+            g = g[:, :h.P].cpu().numpy()
+            for c in range(C):
+                par = {"weights": q[c, :D * K].reshape(D, K).astype(np.float64), "bias": q[c, D * K:].astype(np.float64)}
+                ref = O.softmax_grad(par, X[r0:r0 + n].astype(np.float64), O.one_hot(y[r0:r0 + n], K), 0.01)
+                close(g[c], O.flatten_par(ref, ["weights", "bias"]), 1e-4, 2e-5, "prec %d window %d+%d" % (prec, r0, n))
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler steps against the golden vectors of the unmodified reference
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("case", ["L0", "L1", "L2", "L5", "L20"])
+def test_hmc_step_golden(prec, case):
+    G = load_golden("hmc_step_softmax.npz")
+    g = G[case]
+    K = g["W0"].shape[1]
+    s = hmc(softmax({"alpha": G["alpha"]}, precision=prec), {"weights": g["W0"], "bias": g["b0"]},
+            path_length=G["path"], step_size=G["eps"], verbose=False)
+    with replay_uniforms(g["u"]) as ru:
+        q, p, _, _, a = s.step({"weights": g["W0"], "bias": g["b0"]}, None, TapeRng(g["z"]),
+                               X_train=G["X"], y_train=O.one_hot(G["y"], K))
+    assert ru.pos == 2
+    close(a, g["accept_prob"], 2e-4, 1e-6, "accept prob")
+    close(q["weights"], g["qW"], 1e-4, 1e-6, "q weights")
+    close(q["bias"], g["qb"], 1e-4, 1e-6, "q bias")
+    close(p["weights"], g["pW"], 1e-4, 2e-6, "p weights")
+    close(p["bias"], g["pb"], 1e-4, 2e-6, "p bias")
+
+
+def test_hmc_step_nan_is_accepted_like_the_reference():
+    G = load_golden("hmc_step_softmax.npz")
+    g = G["blowup"]
+    K = g["W0"].shape[1]
+    s = hmc(softmax({"alpha": g["alpha"]}, precision="fp32"), {"weights": g["W0"], "bias": g["b0"]},
+            path_length=g["path"], step_size=g["eps"], verbose=False)
+    with replay_uniforms(g["u"]):
+        q, p, _, _, a = s.step({"weights": g["W0"], "bias": g["b0"]}, None, TapeRng(g["z"]),
+                               X_train=G["X"], y_train=O.one_hot(G["y"], K))
+    assert a == 1.0 and not np.isfinite(q["weights"]).any()  # builtin-min semantics, hmc.py:70
+    s2 = hmc(softmax({"alpha": g["alpha"]}, precision="fp32"), {"weights": g["W0"], "bias": g["b0"]},
+             path_length=g["path"], step_size=g["eps"], verbose=False, reject_nan=True)
+    with replay_uniforms(g["u"]):
+        q2, _, _, _, a2 = s2.step({"weights": g["W0"], "bias": g["b0"]}, None, TapeRng(g["z"]),
+                                  X_train=G["X"], y_train=O.one_hot(G["y"], K))
+    assert a2 == 0.0 and np.allclose(q2["weights"], g["W0"], atol=1e-7)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_hmc_sample_golden(prec):
+    g = load_golden("hmc_sample_softmax.npz")
+    K = g["W0"].shape[1]
+    s = hmc(softmax({"alpha": g["alpha"]}, precision=prec), {"weights": g["W0"], "bias": g["b0"]},
+            path_length=g["path"], step_size=g["eps"], verbose=False)
+    with replay_uniforms(g["u"]) as ru:
+        post, loss, _, _ = s.sample(niter=g["niter"], burnin=g["burnin"], rng=TapeRng(g["z"]),
+                                    X_train=g["X"], y_train=O.one_hot(g["y"], K))
+    assert ru.pos == g["u"].size
+    close(post["weights"], g["postW"], 1e-4, 2e-6)
+    close(post["bias"], g["postb"], 1e-4, 2e-6)
+    close(loss, g["loss"], 1e-5)
+    # identical accept/reject decisions: the set of iterations where the state changed
+    moved_ref = np.any(np.diff(g["postW"], axis=0) != 0, axis=(1, 2))
+    moved_got = np.any(np.diff(post["weights"], axis=0) != 0, axis=(1, 2))
+    assert (moved_ref == moved_got).all() and moved_ref.any() and not moved_ref.all()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_sgld_sample_golden(prec):
+    g = load_golden("sgld_sample_softmax.npz")
+    d, K = g["postW"].shape[1:]
+    s = sgld(softmax({"alpha": g["alpha"]}, precision=prec), {"weights": np.zeros((d, K)), "bias": np.zeros(K)},
+             step_size=g["eps0"], verbose=False)
+    post, logp = s.sample(epochs=g["epochs"], burnin=g["burnin"], batch_size=g["batch_size"], rng=TapeRng(g["z"]),
+                          X_train=g["X"], y_train=O.one_hot(g["y"], K))
+    close(post["weights"], g["postW"], 1e-4, 2e-6)
+    close(post["bias"], g["postb"], 1e-4, 2e-6)
+    close(logp, g["logp"], 1e-5)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_sghmc_step_golden(prec):
+    g = load_golden("sghmc_step_softmax.npz")
+    K = g["W0"].shape[1]
+    s = sghmc(softmax({"alpha": g["alpha"]}, precision=prec), {"weights": g["W0"], "bias": g["b0"]},
+              path_length=g["path"], step_size=g["eps"], verbose=False, sign="reference")
+    with replay_uniforms(g["u"]):
+        q, p, a = s.step({"weights": g["W0"], "bias": g["b0"]}, None, TapeRng(g["z"]),
+                         X_train=g["X"], y_train=O.one_hot(g["y"], K))
+    close(a, g["accept_prob"], 2e-4, 1e-6)
+    close(q["weights"], g["qW"], 1e-4, 2e-6)
+    close(p["weights"], g["pW"], 1e-4, 2e-6)
+    close(p["bias"], g["pb"], 1e-4, 2e-6)
+
+
+def test_hmc_sample_mvn_golden():
+    g = load_golden("hmc_sample_mvn.npz")
+    s = hmc(mvn_gaussian({"mu": g["mu"], "cov": g["cov"]}), {"x": g["x0"]}, path_length=g["path"],
+            step_size=g["eps"], verbose=False)
+    with replay_uniforms(g["u"]):
+        post, loss, _, _ = s.sample(niter=g["niter"], burnin=g["burnin"], rng=TapeRng(g["z"]))
+    # 300 chained steps in fp32 vs fp64: decisions must agree; positions within rtol 1e-4 (atol for ~0 entries)
+    close(post["x"], g["post"], 1e-4, 2e-5)
+    close(loss, g["loss"], 1e-4, 1e-6)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_sgd_fit_golden(prec):
+    g = load_golden("sgd_fit_softmax.npz")
+    d, K = g["W"].shape
+    s = sgd(softmax({"alpha": g["alpha"]}, precision=prec), {"weights": np.zeros((d, K)), "bias": np.zeros(K)},
+            step_size=g["eps"])
+    par, loss = s.fit(epochs=g["epochs"], batch_size=g["batch_size"], gamma=g["gamma"], X_train=g["X"],
+                      y_train=O.one_hot(g["y"], K))
+    close(par["weights"], g["W"], 1e-4, 2e-6)
+    close(par["bias"], g["b"], 1e-4, 2e-6)
+    close(loss, g["loss"], 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# batched chains with ragged path lengths vs independent oracle chains
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECS)
+def test_hmc_ragged_chains_vs_oracle(prec):
+    rs = np.random.RandomState(5)
+    N, D, K, C, alpha, eps, path = 400, 30, 10, 6, 0.01, 5e-4, 4e-3
+    X = rs.rand(N, D)
+    y = rs.randint(0, K, N)
+    Y = O.one_hot(y, K)
+    W0 = rs.normal(0, .1, (C, D, K))
+    b0 = rs.normal(0, .1, (C, K))
+    n_steps = 3
+    from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle
+    m = softmax({"alpha": alpha}, precision=prec)
+    h = m.bind(X, Y)
+    s = SamplerHandle(h.ctx, h, 0, C, precision={"fp32": 0, "bf16x3": 1}[prec])
+    q0 = np.concatenate([W0.reshape(C, -1), b0], axis=1)
+    s.set_q(q0)
+    z = rs.normal(size=(n_steps, C, h.P))
+    u1 = rs.rand(n_steps, C)
+    u2 = rs.rand(n_steps, C)
+    out = s.hmc_run(n_steps, eps, path, z_momentum=torch.as_tensor(z, dtype=torch.float32), u_path=u1, u_accept=u2)
+    samples = out["samples"].cpu().numpy()
+    acc = out["accept_prob"].cpu().numpy()
+    n_grad = 0
+    Ls = set()
+    for c in range(C):
+        q = {"weights": W0[c], "bias": b0[c]}
+        for t in range(n_steps):
+            draws = O.TapeDraws([z[t, c, :D * K].reshape(D, K), z[t, c, D * K:]], [u1[t, c], u2[t, c]])
+            r = O.hmc_step(O.SoftmaxOracle({"alpha": alpha}), q, ["weights", "bias"], eps, path, draws, X_train=X, y_train=Y)
+            q = r["q"]
+            n_grad += r["n_grad"]
+            Ls.add(r["L"])
+            close(acc[t, c], r["accept_prob"], 5e-4, 1e-6, "accept chain %d step %d" % (c, t))
+            close(samples[t, c], O.flatten_par(q, ["weights", "bias"]), 1e-4, 2e-6, "chain %d step %d" % (c, t))
+    assert len(Ls) > 2  # the path lengths really were ragged
+    assert out["n_grad_evals"] == n_grad
+
+
+# ------------------------------------------------------------------------------------------------
+# Philox statistics and sharding invariance
+# ------------------------------------------------------------------------------------------------
+def test_philox_normals_device():
+    import ctypes as C
+    from dropout_hamiltonian_montecarlo_b200._lib import check
+    from dropout_hamiltonian_montecarlo_b200.runtime import default_context
+    ctx = default_context()
+    Cn, P = 8, 20001
+    out = ctx.zeros((Cn, P))
+    check(ctx.L.bhmc_philox_normal(ctx.handle, C.c_void_p(out.data_ptr()), Cn, P, P, 123, 0, 7, 0x7f000000))
+    a = out.cpu().numpy().astype(np.float64)
+    assert abs(a.mean()) < 0.01 and abs(a.std() - 1) < 0.01
+    assert abs(((a - a.mean()) ** 4).mean() / a.var() ** 2 - 3) < 0.1
+    assert abs(np.corrcoef(a[0, :-1], a[0, 1:])[0, 1]) < 0.03 and abs(np.corrcoef(a[0], a[1])[0, 1]) < 0.03
+    # chain c of a launch with chain_id0 = k equals chain c+k of a launch with chain_id0 = 0
+    out2 = ctx.zeros((2, P))
+    check(ctx.L.bhmc_philox_normal(ctx.handle, C.c_void_p(out2.data_ptr()), 2, P, P, 123, 5, 7, 0x7f000000))
+    assert torch.equal(out2, out[5:7])
+
+
+def test_posterior_statistics_mvn():
+    """BASELINE config 1: HMC on the 2-D Gaussian (mean 0, unit variance, rho 0.8), Philox draws, 512 chains."""
+    m = mvn_gaussian({"mu": np.zeros(2), "cov": np.array([[1.0, 0.8], [0.8, 1.0]])})
+    s = hmc(m, {"x": np.zeros(2)}, path_length=1.0, step_size=0.1, verbose=False, n_chains=512, seed=3)
+    post, loss, _, _ = s.sample(niter=400, burnin=50)
+    x = post["x"].reshape(-1, 2)
+    assert np.all(np.abs(x.mean(0)) < 0.05)
+    cov = np.cov(x.T)
+    assert np.allclose(cov, [[1, .8], [.8, 1]], atol=0.06)
+    assert 0.6 < s.last_run["accept_prob"].mean() <= 1.0
