@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: gradient evaluations / second
+(chains x leapfrog) on the MNIST-shaped softmax BNN.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+Workload at N=1 = BASELINE configs[1]: full-batch HMC, softmax regression, synthetic
+60 000 x 784, 10 classes, 64 chains (per GPU; weak scaling: chains are independent units and
+shard over ranks with no data-path collective).  A "step" is one HMC transition of every chain:
+momentum draw, L-1 Gauss-Seidel leapfrog sweeps (each sub-step one full gradient = forward +
+backward GEMM), Metropolis test, sample store.
+
+`value`  : chain-gradient evaluations applied / s, inputs resident in HBM, CUDA-event timed,
+           max over ranks.
+`e2e`    : same metric through the public API (`hmc.sample`) with HOST buffers: every step binds the
+           data from pinned host memory (H2D + operand preparation inside the timed region) and
+           reads the samples / losses back (D2H).
+`roofline`: dominant kernel (forward GEMM + fused softmax epilogue), algorithmic flops
+           2*N*D*K*C per launch / its mean duration (CUDA events on the launching stream, measured
+           live inside the timed region) against the measured sustained bf16 peak.
+`cpu_baseline`: the NumPy oracle port of the reference path (fp64, BLAS threads = host cores) on a
+           bounded sample of the same workload, same box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: N, D, K, chains per GPU, eps, path_length
+    "cfg2": dict(N=60000, D=784, K=10, C=64, eps=1e-4, path=1e-2, alpha=0.01,
+                 desc="HMC softmax 60000x784x10 full batch, 64 chains/GPU"),
+    "cfg2-small": dict(N=2048, D=784, K=10, C=16, eps=1e-4, path=2e-3, alpha=0.01,
+                       desc="HMC softmax 2048x784x10 (debug size)"),
+}
+
+
+def synth(N, D, K, seed, device=None):
+    """MNIST-shaped synthetic data: X ~ U[0,1), labels = argmax(X W* + Gumbel)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Wt = torch.randn(D, K, generator=g) * 0.1
+    if device is not None:
+        gd = torch.Generator(device=device).manual_seed(seed)
+        X = torch.rand(N, D, generator=gd, device=device, dtype=torch.float32)
+        u = torch.rand(N, K, generator=gd, device=device).clamp_(1e-12, 1 - 1e-7)
+        y = (X @ Wt.to(device) - torch.log(-torch.log(u))).argmax(1).to(torch.int32)
+        return X, y
+    X = torch.rand(N, D, generator=g, dtype=torch.float32)
+    u = torch.rand(N, K, generator=g).clamp_(1e-12, 1 - 1e-7)
+    y = (X @ Wt - torch.log(-torch.log(u))).argmax(1).to(torch.int32)
+    return X, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.8), d.get("hbm_gbs", 6552.3), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_rate(wl, seconds_target=15.0, max_steps=3):
+    """Oracle port of hmc.step (hamiltonian/inference/cpu/hmc.py:39-64 + models/cpu/softmax.py) on the
+    host cores: one chain, fp64, same data shape; bounded sample (path length pinned to L=11 per step)."""
+    from oracle import hamiltonian_oracle as O
+    import torch
+    X, y = synth(wl["N"], wl["D"], wl["K"], 0)
+    X = X.numpy().astype(np.float64)
+    Y = O.one_hot(y.numpy(), wl["K"])
+    model = O.SoftmaxOracle({"alpha": wl["alpha"]})
+    q = {"weights": np.zeros((wl["D"], wl["K"])), "bias": np.zeros(wl["K"])}
+    rs = np.random.RandomState(0)
+    L = 11
+    u_len = (L - 0.5) * wl["eps"] / (2 * wl["path"])
+    n_grad, t0 = 0, time.perf_counter()
+    steps = 0
+    while steps < max_steps and (time.perf_counter() - t0 < seconds_target or steps == 0):
+        draws = O.TapeDraws([rs.normal(size=q["weights"].shape), rs.normal(size=q["bias"].shape)], [u_len, rs.rand()])
+        r = O.hmc_step(model, q, ["weights", "bias"], wl["eps"], wl["path"], draws, X_train=X, y_train=Y)
+        q = r["q"]
+        n_grad += r["n_grad"]
+        steps += 1
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count()
+    return dict(value=n_grad / dt, unit="grad-evals/s", cores=int(threads), kind="port",
+                sample="%d HMC steps of 1 chain, L=%d (%d grad evals), fp64 NumPy oracle port of hmc.step, %s"
+                       % (steps, L, n_grad, wl["desc"]), seconds=dt)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    from oracle import hamiltonian_oracle as O
+    X, y = synth(wl["N"], wl["D"], wl["K"], 0)
+    X = X.numpy().astype(np.float64)
+    Y = O.one_hot(y.numpy(), wl["K"])
+    model = O.SoftmaxOracle({"alpha": wl["alpha"]})
+    q = {"weights": np.zeros((wl["D"], wl["K"])), "bias": np.zeros(wl["K"])}
+    rs = np.random.RandomState(0)
+    L = 6  # bounded sample: 11 gradient evaluations per step
+    u_len = (L - 0.5) * wl["eps"] / (2 * wl["path"])
+    n_grad = 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        draws = O.TapeDraws([rs.normal(size=q["weights"].shape), rs.normal(size=q["bias"].shape)], [u_len, rs.rand()])
+        r = O.hmc_step(model, q, ["weights", "bias"], wl["eps"], wl["path"], draws, X_train=X, y_train=Y)
+        q = r["q"]
+        if i >= args.warmup:
+            per_step.append(time.perf_counter() - t0)
+            n_grad += r["n_grad"]
+    total = sum(per_step)
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count()
+    val = n_grad / total
+    line = {"impl": "reference", "metric": "grad evals/sec (chains x leapfrog) on MNIST-shape softmax BNN",
+            "value": val, "unit": "grad-evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "sample": "1 chain, L=%d per step (%d grad evals/step)" % (L, 1 + (L - 1) * 2)},
+            "cpu_baseline": {"value": val, "unit": "grad-evals/s", "cores": int(threads), "kind": "port",
+                             "sample": "%d timed HMC steps of 1 chain, L=%d, fp64 NumPy oracle port "
+                                       "(the reference tree is not present on the GPU box)" % (args.steps, L)},
+            "e2e": {"value": val, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.hmc import hmc
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.softmax import softmax
+    from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle
+    from dropout_hamiltonian_montecarlo_b200._lib import PREC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    N, D, K, C = wl["N"], wl["D"], wl["K"], wl["C"]
+    prec = args.precision
+    X, y = synth(N, D, K, 0, device=dev)
+    model = softmax({"alpha": wl["alpha"]}, precision=prec)
+    h = model.bind(X, y, n_classes=K)
+    ctx = h.ctx
+    shared = args.path_mode == "shared"
+    s = SamplerHandle(ctx, h, 0, C, seed=1234, chain_id0=rank * C, precision=PREC[prec], shared_path=shared)
+    s.set_q(np.zeros((C, h.P), np.float32))
+    samples = ctx.empty((1, C, h.P))
+
+    def step(i):
+        return s.hmc_run(1, wl["eps"], wl["path"], step0=i, keep_samples=True, keep_stats=True)
+
+    for i in range(args.warmup):
+        step(i)
+    ctx.sync()
+    # L2 note: one gradient evaluation streams X (94-376 MB) + (P-Y)^T (77-245 MB) -- far larger than the
+    # 126 MB L2 -- so consecutive launches cannot be served from cache; no explicit flush is needed.
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ctx.timing(True)
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_applied = n_launched = 0
+    e0.record()
+    for i in range(args.steps):
+        o = step(args.warmup + i)
+        n_applied += o["n_grad_evals"]
+        n_launched += o["n_grad_launched"]
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    t_fwd, n_fwd = ctx.kernel_time(0)
+    t_bwd, n_bwd = ctx.kernel_time(1)
+    t_prep, _ = ctx.kernel_time(2)
+    t_upd, _ = ctx.kernel_time(3)
+    ctx.timing(False)
+    launches = ctx.launches - launches0
+    clk = clocks.stop()
+    stats = torch.tensor([ms, float(n_applied), float(n_launched)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, n_applied, n_launched = float(mx[0]), float(sm[1]), float(sm[2])
+    value = n_applied / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers (rank-local; aggregated like value) ----
+    e2e = None
+    if not args.no_e2e:
+        Xh = X.cpu().pin_memory()
+        yh = y.cpu().pin_memory()
+        api = hmc(softmax({"alpha": wl["alpha"]}, precision=prec), {"weights": np.zeros((D, K), np.float32),
+                                                                     "bias": np.zeros(K, np.float32)},
+                  path_length=wl["path"], step_size=wl["eps"], verbose=False, n_chains=C, seed=99,
+                  chain_id0=rank * C, path_length_mode=args.path_mode)
+        n_e2e = 0
+        d2h = 0
+        for i in range(1 + args.steps):  # first call = warm-up (allocations)
+            if i == 1:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+            api.model.unbind()  # every step re-binds from HOST memory: H2D + operand preparation are timed
+            post, loss, _, _ = api.sample(niter=1, burnin=0, X_train=Xh, y_train=yh)
+            if i >= 1:
+                n_e2e += api.last_run["n_grad_evals"]
+                d2h = post["weights"].size * 4 + post["bias"].size * 4 + loss.size * 8 * 2 + loss.size * 4
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = torch.tensor([dt, float(n_e2e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = st.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = st.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            dt, n_e2e = float(mx[0]), float(sm[1])
+        e2e = {"value": n_e2e / dt, "unit": "grad-evals/s", "h2d_bytes_per_step": int(N * D * 4 + N * 4),
+               "d2h_bytes_per_step": int(d2h), "api": "hmc.sample(niter=1, X_train=<pinned host>, y_train=<pinned host>)"}
+
+    if rank == 0:
+        peak_tf, peak_bw, src = peaks()
+        flops_fwd = 2.0 * N * D * K * C  # algorithmic flops of one forward launch (all chains)
+        avg_fwd = (t_fwd / max(1, n_fwd)) * 1e-3
+        avg_bwd = (t_bwd / max(1, n_bwd)) * 1e-3
+        dom = "fwd" if t_fwd >= t_bwd else "bwd"
+        avg = avg_fwd if dom == "fwd" else avg_bwd
+        achieved = flops_fwd / avg / 1e12 if avg > 0 else 0.0
+        mma_mult = 3.0 if prec == "bf16x3" else 1.0
+        cpu = None if args.no_cpu_baseline else cpu_reference_rate(wl)
+        line = {
+            "metric": "grad evals/sec (chains x leapfrog) on MNIST-shape softmax BNN",
+            "value": value, "unit": "grad-evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (bf16 hi/lo split x3 on tcgen05, fp32 accumulate)" if prec == "bf16x3" else prec,
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "N": N, "D": D, "K": K, "chains_per_gpu": C, "step_size": wl["eps"],
+                       "path_length": wl["path"], "precision": prec, "path_length_mode": args.path_mode,
+                       "sweep": "reference (Gauss-Seidel, 2 gradients per leapfrog iteration)",
+                       "l2": "inputs larger than L2 (X 94-376 MB + (P-Y)^T 77-245 MB per evaluation)",
+                       "grad_evals_launched_incl_masked": n_launched},
+            "roofline": {"bound": "tensor", "kernel": "k_tc_gemm<%s>" % dom, "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": src,
+                         "algorithmic_flops_per_launch": flops_fwd, "avg_launch_ms": avg * 1e3,
+                         "mma_flops_issued_over_algorithmic": mma_mult,
+                         "group_ms": {"fwd": t_fwd, "bwd": t_bwd, "prep": t_prep, "update": t_upd, "step_total": ms}},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--path-mode", default="per_chain", choices=["per_chain", "shared"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

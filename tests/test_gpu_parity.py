@@ -273,12 +273,16 @@ def test_philox_normals_device():
 
 
 def test_posterior_statistics_mvn():
-    """BASELINE config 1: HMC on the 2-D Gaussian (mean 0, unit variance, rho 0.8), Philox draws, 512 chains."""
+    """BASELINE config 1: HMC on the 2-D Gaussian (mean 0, unit variance, rho 0.8), Philox draws, 512 chains.
+    The reference's integrator (eps/2 + eps kicks, hmc.py:51-54) is not volume-exact, so its stationary
+    covariance is NOT the target's: 60 000 oracle samples (4 seeds, same settings) give
+    [[1.048, 0.839], [0.839, 1.040]] (+-0.04 per 15 000-sample run) and mean accept 0.86.  The CUDA path
+    must reproduce THOSE statistics under independent (Philox) draws."""
     m = mvn_gaussian({"mu": np.zeros(2), "cov": np.array([[1.0, 0.8], [0.8, 1.0]])})
     s = hmc(m, {"x": np.zeros(2)}, path_length=1.0, step_size=0.1, verbose=False, n_chains=512, seed=3)
     post, loss, _, _ = s.sample(niter=400, burnin=50)
     x = post["x"].reshape(-1, 2)
     assert np.all(np.abs(x.mean(0)) < 0.05)
     cov = np.cov(x.T)
-    assert np.allclose(cov, [[1, .8], [.8, 1]], atol=0.06)
-    assert 0.6 < s.last_run["accept_prob"].mean() <= 1.0
+    assert np.allclose(cov, [[1.048, .839], [.839, 1.040]], atol=0.05), cov
+    assert abs(s.last_run["accept_prob"].mean() - 0.86) < 0.03

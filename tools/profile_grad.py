@@ -1,0 +1,33 @@
+"""Short profiling target: a few gradient evaluations of the cfg2 workload (what ncu wraps)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from bench import WORKLOADS, synth
+from dropout_hamiltonian_montecarlo_b200._lib import PREC
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.softmax import softmax
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="cfg2")
+ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--evals", type=int, default=3)
+ap.add_argument("--chains", type=int, default=0)
+a = ap.parse_args()
+wl = WORKLOADS[a.workload]
+C = a.chains or wl["C"]
+dev = torch.device("cuda", 0)
+X, y = synth(wl["N"], wl["D"], wl["K"], 0, device=dev)
+m = softmax({"alpha": wl["alpha"]}, precision=a.precision)
+h = m.bind(X, y, n_classes=wl["K"])
+q = h.pack(np.random.RandomState(0).normal(0, 0.01, (C, h.P)).astype(np.float32))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(a.evals):
+    e0.record()
+    g, ll = h.grad(q, 0, wl["N"], PREC[a.precision])
+    e1.record()
+    torch.cuda.synchronize()
+    print("eval %d: %.3f ms  ll[0]=%.3f |g|=%.4e" % (i, e0.elapsed_time(e1), ll[0].item(), g.norm().item()))
