@@ -24,6 +24,8 @@
 // the main loop of tile i+1.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "internal.cuh"
@@ -34,7 +36,7 @@ static constexpr int BM = 128;        // UMMA M
 static constexpr int BK = 64;         // bf16 elements per stage row = 128 B = one swizzle span
 static constexpr int UMMA_K = 16;
 static constexpr int MAX_STAGES = 8;
-static constexpr int NTHREADS = 256;
+static constexpr int NON_EPI_THREADS = 128;  // warps 0-3: TMA, MMA, TMEM alloc, spare
 static constexpr int TMEM_COLS = 512;
 static constexpr int TMEM_BUF_COLS = 256;
 static constexpr float CLIP_HI = 36.04365338911715f;
@@ -179,6 +181,7 @@ struct TcParams {
   const int32_t* labels;          // already offset to the row window
   int64_t nrows;
   int64_t Mpad;                   // row stride of DmT
+  int dm_shift;                   // DmT column of window row 0 (row0 % 8: TMA needs 16 B aligned inner coordinates)
   __nv_bfloat16* dmt_hi;
   __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
   double* loglik;
@@ -187,8 +190,21 @@ struct TcParams {
   float* part;                    // [n_split, m_tiles*128, n_tiles*BN]
 };
 
-template <int MODE, int KP>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// EW = number of epilogue warps (multiple of 4).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the
+// EW/4 warps that share a lane quarter split the tile's chains (forward) / column chunks (backward).
+template <int MODE, int KP, int EW>
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -208,7 +224,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1);
-      mbar_init(smem_u32(&bar_tempty[b]), 128);
+      mbar_init(smem_u32(&bar_tempty[b]), 32 * EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -292,6 +308,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp & 3;             // TMEM lane quarter this warp may access
+    const int part = (warp - 4) >> 2;    // which share of the chains / column chunks
+    constexpr int PARTS = EW / 4;
     const int t = ew * 32 + lane;        // accumulator row handled by this thread
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
@@ -303,48 +321,60 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
       if constexpr (MODE == MODE_FWD) {
+        const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
         const int64_t r = (int64_t)mt * BM + t;  // row inside the window
         const bool valid = r < p.nrows;
-        const int y = valid ? p.labels[r] : 0;
-        for (int cc = 0; cc < p.cpt; ++cc) {
+        const int y = valid ? p.labels[r] : -1;
+        const int K = p.K;
+        for (int cc = part; cc < p.cpt; cc += PARTS) {
           const int c = nt * p.cpt + cc;
           if (c >= p.C) break;  // warp-uniform
           uint32_t raw[KP];
           tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
+          const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
+          float bv[KP];
+#pragma unroll
+          for (int k = 0; k < KP; ++k) bv[k] = (k < K) ? __ldg(bias + k) : 0.f;
           tmem_ld_wait();
-          const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * p.K;
           float z[KP];
           float m = -INFINITY, zy = 0.f;
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
-            if (k < p.K) {
-              float v = __uint_as_float(raw[k]) + __ldg(bias + k);
-              v = fmaxf(fminf(v, CLIP_HI), CLIP_LO);
-              z[k] = v;
-              m = fmaxf(m, v);
-              if (k == y) zy = v;
-            } else {
-              z[k] = -INFINITY;
-            }
+            float v = fmaxf(fminf(__uint_as_float(raw[k]) + bv[k], CLIP_HI), CLIP_LO);  // softmax.py:40-41
+            if (k >= K) v = -INFINITY;                                                   // padded classes
+            z[k] = v;
+            m = fmaxf(m, v);
+            zy = (k == y) ? v : zy;
           }
           float ssum = 0.f;
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
-            z[k] = (k < p.K) ? __expf(z[k] - m) : 0.f;
+            z[k] = ex2_approx((z[k] - m) * L2E);  // exp(z - max); exp(-inf) = 0 for padded classes
             ssum += z[k];
           }
-          float inv = 1.0f / ssum;
-          float ll = valid ? (zy - m - logf(ssum)) : 0.f;
+          const float inv = __fdividef(1.0f, ssum);
+          float ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
           if (p.write_dm) {
-            __nv_bfloat16* dh = p.dmt_hi + ((int64_t)c * KP) * p.Mpad + r;
-            __nv_bfloat16* dl = p.dmt_lo ? p.dmt_lo + ((int64_t)c * KP) * p.Mpad + r : nullptr;
+            const int64_t o = ((int64_t)c * KP) * p.Mpad + p.dm_shift + r;
+            __nv_bfloat16* dh = p.dmt_hi + o;
+            __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-              if (k < p.K) {
-                float d = valid ? (z[k] * inv - (k == y ? 1.f : 0.f)) : 0.f;
+              if (k < K) {
+                float d = valid ? fmaf(z[k], inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
                 __nv_bfloat16 h = __float2bfloat16_rn(d);
-                dh[(int64_t)k * p.Mpad] = h;
-                if (dl) dl[(int64_t)k * p.Mpad] = __float2bfloat16_rn(d - __bfloat162float(h));
+                *dh = h;
+                if (p.split3) *dl = __float2bfloat16_rn(d - __bfloat162float(h));
+              }
+              dh += p.Mpad;
+              dl += p.Mpad;
+            }
+            if (mt == 0 && t < p.dm_shift) {  // zero the alignment prefix (columns before the window)
+              __nv_bfloat16* zh = p.dmt_hi + ((int64_t)c * KP) * p.Mpad + t;
+              __nv_bfloat16* zl = p.dmt_lo + ((int64_t)c * KP) * p.Mpad + t;
+              for (int k = 0; k < K; ++k) {
+                zh[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
+                if (p.split3) zl[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
               }
             }
           }
@@ -356,7 +386,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         // backward: dump the fp32 accumulator tile to the split-K partial buffer (coalesced per row)
         const int64_t rows = (int64_t)p.m_tiles * BM, cols = (int64_t)p.n_tiles * p.BN;
         float* dst = p.part + ((int64_t)s * rows + (int64_t)mt * BM + t) * cols + (int64_t)nt * p.BN;
-        for (int j0 = 0; j0 < p.BN; j0 += 16) {
+        for (int j0 = part * 16; j0 < p.BN; j0 += 16 * PARTS) {
           uint32_t raw[16];
           tmem_ld<16>(tacc + (uint32_t)j0, raw);
           tmem_ld_wait();
@@ -573,22 +603,39 @@ void tc_softmax_release(SoftmaxData& d) {
   d.tc_ready = false;
 }
 
-template <int MODE, int KP>
-static int launch_gemm(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                       const CUtensorMap& b_lo, const TcParams& p) {
+static int epilogue_warps() {
+  static int ew = 0;
+  if (!ew) {
+    const char* e = getenv("BHMC_EPI_WARPS");
+    ew = e ? atoi(e) : 16;
+    if (ew != 8 && ew != 16) ew = 16;
+  }
+  return ew;
+}
+
+template <int MODE, int KP, int EW>
+static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                          const CUtensorMap& b_lo, const TcParams& p) {
   int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + p.BN * BK * 2);
   size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, KP, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   int work = p.n_split * p.m_tiles * p.n_tiles;
   int grid = std::min(work, ctx->sm_count);
-  k_tc_gemm<MODE, KP><<<grid, NTHREADS, smem, ctx->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  k_tc_gemm<MODE, KP, EW><<<grid, NON_EPI_THREADS + 32 * EW, smem, ctx->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
+}
+
+template <int MODE, int KP>
+static int launch_gemm(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                       const CUtensorMap& b_lo, const TcParams& p) {
+  if (epilogue_warps() == 8) return launch_gemm_ew<MODE, KP, 8>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+  return launch_gemm_ew<MODE, KP, 16>(ctx, a_hi, a_lo, b_hi, b_lo, p);
 }
 
 template <int KP>
@@ -608,7 +655,9 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const int BN = cpt * KP;
   const int n_tiles = (int)ceil_div(C, cpt);
   const int64_t ncols = (int64_t)C * KP;  // rows of Wt / DmT
-  const int64_t Mpad = round_up(nrows, BM);
+  const int64_t Mfwd = round_up(nrows, BM);          // rows covered by the forward tiles
+  const int shift = (int)(row0 % 8);                 // TMA inner coordinates must be 16 B aligned (8 bf16)
+  const int64_t Mpad = round_up(Mfwd + shift, 8);    // row stride of DmT
   const int64_t P = (int64_t)(D + 1) * K;
   const int nmat = split3 ? 2 : 1;
   const int stage_bytes = nmat * (BM * BK * 2 + BN * BK * 2);
@@ -649,7 +698,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     b_lo = b_hi;
   }
   TcParams p{};
-  p.m_tiles = (int)(Mpad / BM);
+  p.m_tiles = (int)(Mfwd / BM);
   p.n_tiles = n_tiles;
   p.n_split = 1;
   p.k_chunks = (int)ceil_div(D, BK);
@@ -668,6 +717,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.labels = d.labels + row0;
   p.nrows = nrows;
   p.Mpad = Mpad;
+  p.dm_shift = shift;
   p.dmt_hi = dmt_hi;
   p.dmt_lo = dmt_lo;
   p.loglik = loglik;
@@ -694,7 +744,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   TcParams b{};
   b.m_tiles = (int)ceil_div(d.Dt, BM);
   b.n_tiles = n_tiles;
-  b.k_chunks = (int)ceil_div(nrows, BK);
+  b.k_chunks = (int)ceil_div(nrows + shift, BK);
   int tiles = b.m_tiles * b.n_tiles;
   int want = std::max(1, ctx->sm_count / tiles);
   want = std::min(want, std::max(1, b.k_chunks / 4));  // keep >= 4 chunks per slab
@@ -703,17 +753,18 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   b.BN = BN;
   b.stages = stages;
   b.split3 = split3 ? 1 : 0;
-  b.a_k0 = (int)row0;
+  b.a_k0 = (int)(row0 - shift);
   b.a_m0 = 0;
   int64_t prow = (int64_t)b.m_tiles * BM, pcol = (int64_t)b.n_tiles * BN;
   void* part = nullptr;
   BHMC_TRY(ctx->get_scratch(3, sizeof(float) * (size_t)b.n_split * prow * pcol, &part));
   b.part = (float*)part;
   BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, BM));
-  BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)Mpad, (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
+  // inner extent = written columns only: anything beyond is zero-filled by TMA
+  BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)(Mfwd + shift), (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
   if (split3) {
     BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, BM));
-    BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)Mpad, (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
+    BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)(Mfwd + shift), (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
   } else {
     a_lo = a_hi;
     b_lo = b_hi;

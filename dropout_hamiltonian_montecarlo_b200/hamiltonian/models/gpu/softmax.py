@@ -49,14 +49,20 @@ class softmax(_base.ChainModel):
         if k is None:
             k = int(labels.max()) + 1
         ctx = self.ctx
+        mask = 1 | (1 << PREC[self.precision])
         if isinstance(X, torch.Tensor) and X.is_cuda:
             Xd = X.to(torch.float32).contiguous()
+            n, d = Xd.shape
+            h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
+            h.bind(Xd, torch.as_tensor(labels).to(ctx.device), mask)
         else:
-            Xd = torch.as_tensor(np.ascontiguousarray(np.asarray(X, dtype=np.float32))).to(ctx.device)
-        n, d = Xd.shape
-        h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
-        mask = 1 | (1 << PREC[self.precision])
-        h.bind(Xd, torch.as_tensor(labels).to(ctx.device), mask)
+            # host buffers cross the C ABI as they are (bhmc_softmax_bind_data_host does the H2D copy)
+            Xh = X if isinstance(X, torch.Tensor) else torch.as_tensor(np.asarray(X))
+            Xh = Xh.to(torch.float32).contiguous()
+            n, d = Xh.shape
+            h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
+            h.bind_host(Xh, torch.as_tensor(np.ascontiguousarray(labels)), mask)
+            ctx.sync()  # the host buffers may be released by the caller after bind returns
         if self._bound is not None:
             self._bound[1].close()
         self._bound = (key, h, (X, y))
