@@ -86,6 +86,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset in every CTA of cta_mask and signals the mbarrier at
+// the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -173,6 +196,8 @@ struct TcParams {
   int stages;
   int split3;                     // 1: hi/lo operands, 3 MMAs per product
   int a_k0, a_m0;                 // coordinate offsets of A in its tensor map (contraction, row)
+  int pair;                       // CTA pairs (cluster of 2) sharing one operand through TMA multicast:
+                                  // 0 = off, 1 = two M tiles share the B tile, 2 = two N tiles share the A tile
   // forward epilogue
   int C, K, cpt;                  // chains, classes, chains per N tile (BN = cpt*KP)
   int D;
@@ -215,12 +240,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_bytes = BM * BK * 2, b_bytes = p.BN * BK * 2;
   const int stage_bytes = (p.split3 ? 2 : 1) * (a_bytes + b_bytes);
-  const int num_work = p.n_split * p.m_tiles * p.n_tiles;
+  // work items are handed out per cluster (1 or 2 CTAs); a pair splits two adjacent M (or N) tiles
+  const int csize = p.pair ? 2 : 1;
+  const int rank = p.pair ? (int)cluster_ctarank() : 0;
+  const int m_items = p.pair == 1 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int n_items = p.pair == 2 ? (p.n_tiles + 1) / 2 : p.n_tiles;
+  const int num_work = p.n_split * m_items * n_items;
+  const int wi0 = blockIdx.x / csize, wi_step = gridDim.x / csize;
+#define BHMC_DECODE_WORK(wi)                                             \
+  const int s = (wi) / (m_items * n_items), rem = (wi) % (m_items * n_items); \
+  const int mt = (p.pair == 1) ? 2 * (rem / n_items) + rank : rem / n_items;  \
+  const int nt = (p.pair == 2) ? 2 * (rem % n_items) + rank : rem % n_items;  \
+  (void)s; (void)mt; (void)nt;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), csize);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1);
@@ -235,7 +271,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (p.pair) cluster_sync_all();  // peer barriers must be initialised before anything is multicast into them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -244,23 +281,32 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        int s = w / (p.m_tiles * p.n_tiles), rem = w % (p.m_tiles * p.n_tiles);
-        int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+      for (int w = wi0; w < num_work; w += wi_step) {
+        BHMC_DECODE_WORK(w)
         int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
+        const int nmat = p.split3 ? 2 : 1;
         for (int k = k_begin; k < k_end; ++k) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           uint32_t full = smem_u32(&bar_full[stage]);
           mbar_expect_tx(full, (uint32_t)stage_bytes);
-          uint32_t sa = smem_base + stage * stage_bytes;
-          int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM;
-          tma_load_2d(sa, &tmA_hi, full, ak, am);
-          if (p.split3) {
-            tma_load_2d(sa + a_bytes, &tmA_lo, full, ak, am);
-            tma_load_2d(sa + 2 * a_bytes, &tmB_hi, full, k * BK, nt * p.BN);
-            tma_load_2d(sa + 2 * a_bytes + b_bytes, &tmB_lo, full, k * BK, nt * p.BN);
+          uint32_t sa = smem_base + stage * stage_bytes;  // [A_hi | A_lo | B_hi | B_lo]
+          uint32_t sb = sa + nmat * a_bytes;
+          int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN;
+          if (p.pair == 2) {  // A tile shared by the pair: each CTA fetches 64 of its 128 rows for both
+            uint32_t off = (uint32_t)rank * (BM / 2) * (BK * 2);
+            tma_load_2d_mc(sa + off, &tmA_hi, full, ak, am + rank * (BM / 2), 3);
+            if (p.split3) tma_load_2d_mc(sa + a_bytes + off, &tmA_lo, full, ak, am + rank * (BM / 2), 3);
           } else {
-            tma_load_2d(sa + a_bytes, &tmB_hi, full, k * BK, nt * p.BN);
+            tma_load_2d(sa, &tmA_hi, full, ak, am);
+            if (p.split3) tma_load_2d(sa + a_bytes, &tmA_lo, full, ak, am);
+          }
+          if (p.pair == 1) {  // B tile shared by the pair: each CTA fetches BN/2 of its rows for both
+            uint32_t off = (uint32_t)rank * (p.BN / 2) * (BK * 2);
+            tma_load_2d_mc(sb + off, &tmB_hi, full, bk, bn + rank * (p.BN / 2), 3);
+            if (p.split3) tma_load_2d_mc(sb + b_bytes + off, &tmB_lo, full, bk, bn + rank * (p.BN / 2), 3);
+          } else {
+            tma_load_2d(sb, &tmB_hi, full, bk, bn);
+            if (p.split3) tma_load_2d(sb + b_bytes, &tmB_lo, full, bk, bn);
           }
           if (++stage == p.stages) stage = 0, phase ^= 1u;
         }
@@ -274,8 +320,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-        int s = w / (p.m_tiles * p.n_tiles);
+      for (int w = wi0; w < num_work; w += wi_step, ++it) {
+        BHMC_DECODE_WORK(w)
         int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
         int buf = it & 1;
         uint32_t use = (uint32_t)(it >> 1);
@@ -299,7 +345,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
               umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
             }
           }
-          umma_commit(smem_u32(&bar_empty[stage]));  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire; in pair mode the peer's producer also writes into this
+          // CTA's slot, so the release is multicast to both CTAs (empty barriers count 2 arrivals)
+          if (p.pair) umma_commit_mc(smem_u32(&bar_empty[stage]), 3);
+          else umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == p.stages) stage = 0, phase ^= 1u;
         }
         umma_commit(smem_u32(&bar_tfull[buf]));  // accumulator complete
@@ -312,15 +361,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     constexpr int PARTS = EW / 4;
     const int t = ew * 32 + lane;        // accumulator row handled by this thread
     int it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-      int s = w / (p.m_tiles * p.n_tiles), rem = w % (p.m_tiles * p.n_tiles);
-      int mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+    for (int w = wi0; w < num_work; w += wi_step, ++it) {
+      BHMC_DECODE_WORK(w)
+      const bool tile_ok = mt < p.m_tiles && nt < p.n_tiles;  // odd tile counts leave a phantom tile in the last pair
       int buf = it & 1;
       uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      if constexpr (MODE == MODE_FWD) {
+      if (!tile_ok) {
+        // nothing to store; only the barrier protocol below
+      } else if constexpr (MODE == MODE_FWD) {
         const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
         const int64_t r = (int64_t)mt * BM + t;  // row inside the window
         const bool valid = r < p.nrows;
@@ -401,7 +452,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   }
   // ---- teardown ----
   tcgen05_fence_before();
-  __syncthreads();
+  if (p.pair) cluster_sync_all();  // the peer may still multicast into this CTA's smem / barriers
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -603,6 +655,16 @@ void tc_softmax_release(SoftmaxData& d) {
   d.tc_ready = false;
 }
 
+// BHMC_PAIR=0 disables the CTA-pair multicast (debug / A-B comparison)
+static bool pairing_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BHMC_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 static int epilogue_warps() {
   static int ew = 0;
   if (!ew) {
@@ -623,9 +685,24 @@ static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
     BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, KP, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  int work = p.n_split * p.m_tiles * p.n_tiles;
-  int grid = std::min(work, ctx->sm_count);
-  k_tc_gemm<MODE, KP, EW><<<grid, NON_EPI_THREADS + 32 * EW, smem, ctx->stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+  const int m_items = p.pair == 1 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int n_items = p.pair == 2 ? (p.n_tiles + 1) / 2 : p.n_tiles;
+  const int work = p.n_split * m_items * n_items;
+  const int csize = p.pair ? 2 : 1;
+  const int grid = csize * std::min(work, ctx->sm_count / csize);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NON_EPI_THREADS + 32 * EW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, KP, EW>, a_hi, a_lo, b_hi, b_lo, p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
@@ -688,11 +765,14 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
 
   // ---- forward: Z[rows, C*KP] = Xa[rows, Dp] . Wt^T ----
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  // forward: pairs of M tiles share the W tile (each CTA fetches half of it and multicasts)
+  const int fwd_pair = (pairing_enabled() && Mfwd / BM >= 2 && (Mfwd / BM) * n_tiles >= ctx->sm_count) ? 1 : 0;
+  const uint32_t fwd_bbox = (uint32_t)(fwd_pair ? BN / 2 : BN);
   BHMC_TRY(make_map(&a_hi, d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
-  BHMC_TRY(make_map(&b_hi, wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+  BHMC_TRY(make_map(&b_hi, wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
   if (split3) {
     BHMC_TRY(make_map(&a_lo, d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
-    BHMC_TRY(make_map(&b_lo, wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+    BHMC_TRY(make_map(&b_lo, wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
   } else {
     a_lo = a_hi;
     b_lo = b_hi;
@@ -708,6 +788,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.split3 = split3 ? 1 : 0;
   p.a_k0 = 0;
   p.a_m0 = (int)row0;
+  p.pair = fwd_pair;
   p.C = C;
   p.K = K;
   p.cpt = cpt;
@@ -755,15 +836,18 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   b.split3 = split3 ? 1 : 0;
   b.a_k0 = (int)(row0 - shift);
   b.a_m0 = 0;
+  // backward: pairs of N tiles share the X^T tile
+  b.pair = (pairing_enabled() && b.n_tiles >= 2 && b.n_split * b.m_tiles * b.n_tiles >= ctx->sm_count / 2) ? 2 : 0;
+  const uint32_t bwd_abox = (uint32_t)(b.pair ? BM / 2 : BM);
   int64_t prow = (int64_t)b.m_tiles * BM, pcol = (int64_t)b.n_tiles * BN;
   void* part = nullptr;
   BHMC_TRY(ctx->get_scratch(3, sizeof(float) * (size_t)b.n_split * prow * pcol, &part));
   b.part = (float*)part;
-  BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, BM));
+  BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, bwd_abox));
   // inner extent = written columns only: anything beyond is zero-filled by TMA
   BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)(Mfwd + shift), (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
   if (split3) {
-    BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, BM));
+    BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, bwd_abox));
     BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)(Mfwd + shift), (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
   } else {
     a_lo = a_hi;
