@@ -588,16 +588,23 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     BHMC_CUDA_OK(cudaEventSynchronize(ctx->pinned_ev));
     ctx->pinned_inflight = false;
   }
+  // pinned staging: [L sorted | perm | u_accept] per step
   void* pin = nullptr;
-  size_t l_bytes = sizeof(int32_t) * (size_t)n_steps * C, u_bytes = sizeof(double) * (size_t)n_steps * C;
-  BHMC_TRY(ctx->get_pinned(l_bytes + u_bytes + 64, &pin));
+  const size_t l_bytes = ((sizeof(int32_t) * (size_t)n_steps * C + 63) / 64) * 64;
+  const size_t u_bytes = sizeof(double) * (size_t)n_steps * C;
+  BHMC_TRY(ctx->get_pinned(2 * l_bytes + u_bytes, &pin));
   int32_t* Lh = (int32_t*)pin;
-  double* uacc_h = (double*)((char*)pin + ((l_bytes + 63) / 64) * 64);
+  int32_t* perm_h = (int32_t*)((char*)pin + l_bytes);
+  double* uacc_h = (double*)((char*)pin + 2 * l_bytes);
   std::vector<int> lmax(n_steps, 0);
+  std::vector<int> Ltmp(C);
+  bool ragged = false;
   run->n_grad_evals = 0;
   run->n_grad_launched = 0;
   for (int t = 0; t < n_steps; ++t) {
     uint32_t step = (uint32_t)(run->step0 + t);
+    int32_t* Lt = Lh + (size_t)t * C;
+    int32_t* pt = perm_h + (size_t)t * C;
     for (int c = 0; c < C; ++c) {
       double u;
       if (run->u_path_host)
@@ -605,22 +612,29 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
       else
         u = philox_uniform(cfg.seed, cfg.shared_path ? -1 : cfg.chain_id0 + c, step, TAG_PATH);
       double Ld = std::ceil(2.0 * u * run->path_length / run->step_size);
-      int L = Ld > 1e9 ? 1000000000 : (int)Ld;
-      Lh[(size_t)t * C + c] = L;
-      lmax[t] = std::max(lmax[t], L);
-      run->n_grad_evals += 1 + (int64_t)std::max(L - 1, 0) * nsw;
+      Ltmp[c] = Ld > 1e9 ? 1000000000 : (int)Ld;
+      pt[c] = c;
+      run->n_grad_evals += 1 + (int64_t)std::max(Ltmp[c] - 1, 0) * nsw;
       if (run->u_accept_host) uacc_h[(size_t)t * C + c] = run->u_accept_host[(size_t)t * C + c];
     }
-    run->n_grad_launched += (int64_t)C * (1 + (int64_t)std::max(lmax[t] - 1, 0) * nsw);
+    // ragged trajectories: sort chains by path length (longest first) so that the chains still moving at
+    // leapfrog iteration `it` are always the first n_act(it) working rows -> masked chains cost nothing
+    std::stable_sort(pt, pt + C, [&](int32_t x, int32_t y) { return Ltmp[x] > Ltmp[y]; });
+    for (int r = 0; r < C; ++r) {
+      Lt[r] = Ltmp[pt[r]];
+      ragged |= pt[r] != r;
+    }
+    lmax[t] = Lt[0];
     BHMC_CHECK_ARG(!(sghmc && run->z_noise_dev) || std::max(lmax[t] - 1, 0) <= run->z_noise_iters,
                    "step %d needs %d noise iterations but the tape holds %lld", t, lmax[t] - 1, (long long)run->z_noise_iters);
   }
   void* ldev = nullptr;
-  BHMC_TRY(ctx->get_scratch(6, l_bytes + u_bytes + 64, &ldev));
+  BHMC_TRY(ctx->get_scratch(6, 2 * l_bytes + u_bytes, &ldev));
   int32_t* Ld_all = (int32_t*)ldev;
-  double* uacc_d = (double*)((char*)ldev + ((l_bytes + 63) / 64) * 64);
-  BHMC_CUDA_OK(cudaMemcpyAsync(ldev, pin, ((l_bytes + 63) / 64) * 64 + (run->u_accept_host ? u_bytes : 0),
-                               cudaMemcpyHostToDevice, ctx->stream));
+  int32_t* perm_all = (int32_t*)((char*)ldev + l_bytes);
+  double* uacc_d = (double*)((char*)ldev + 2 * l_bytes);
+  BHMC_CUDA_OK(cudaMemcpyAsync(ldev, pin, 2 * l_bytes + (run->u_accept_host ? u_bytes : 0), cudaMemcpyHostToDevice,
+                               ctx->stream));
   if (!ctx->pinned_ev) BHMC_CUDA_OK(cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming));
   BHMC_CUDA_OK(cudaEventRecord(ctx->pinned_ev, ctx->stream));
   ctx->pinned_inflight = true;
@@ -628,7 +642,15 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
 
   for (int t = 0; t < n_steps; ++t) {
     const uint32_t step = (uint32_t)(run->step0 + t);
-    const int32_t* Lc = Ld_all + (size_t)t * C;
+    const int32_t* Lc = Ld_all + (size_t)t * C;                         // sorted, row-indexed
+    const int32_t* Lhost = Lh + (size_t)t * C;
+    const int32_t* perm = ragged ? perm_all + (size_t)t * C : nullptr;  // row -> chain
+    // rows still moving at leapfrog iteration `it` (L sorted descending): it < L-1
+    auto n_act = [&](int it) {
+      int n = 0;
+      while (n < C && it < Lhost[n] - 1) ++n;
+      return n;
+    };
     // 1. momentum ~ N(0,1), proposal := current (hmc.py:40-44)
     BeginArgs b{};
     b.q = s->q;
@@ -645,9 +667,11 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     b.stream_lo = step;
     b.stream_hi = TAG_MOMENTUM;
     b.kin0 = kin0;
+    b.perm = perm;
     BHMC_TRY(launch_hmc_begin(ctx, b));
     // 2. gradient at the current point (hmc.py:47); its log-likelihood doubles as NLP(q)
     BHMC_TRY(mb->grad(s->q_new, C, ld, run->row0, nrows, cfg.precision, s->g, stat));
+    run->n_grad_launched += C;
     BHMC_CUDA_OK(cudaMemcpyAsync(stat_cur, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
     BHMC_CUDA_OK(cudaMemcpyAsync(stat_new, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
     // 3. leapfrog: (L-1) Gauss-Seidel sweeps (hmc.py:49-54 / sghmc.py:28-34)
@@ -658,13 +682,13 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     u.g = s->g;
     u.ld = ld;
     u.P = P;
-    u.C = C;
     u.L = Lc;
     u.eps = eps;
     u.seed = cfg.seed;
     u.chain_id0 = cfg.chain_id0;
     u.stat = stat;
     u.stat_new = stat_new;
+    u.perm = perm;
     if (sghmc) {
       u.f_post = 1.0f - eps;
       u.a_post = cfg.sghmc_descent ? eps : -eps;  // literal: p = (1-eps)p + eps*grad + r (sghmc.py:34)
@@ -676,7 +700,9 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
       u.n_post = 0.f;
       u.a_pre = 0.5f * eps;                        // hmc.py:51
     }
+    int rows_prev = 0;  // rows that took part in the previous sub-step (superset of the current ones)
     for (int it = 0; it < iters; ++it) {
+      const int rows = n_act(it);
       for (int v = 0; v < nsw; ++v) {
         bool first = (it == 0 && v == 0);
         int pv = v == 0 ? nsw - 1 : v - 1, pit = v == 0 ? it - 1 : it;
@@ -686,6 +712,7 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
         u.pre_off = cfg.sweep_off[v];
         u.pre_len = cfg.sweep_len[v];
         u.it_pre = it;
+        u.C = first ? rows : rows_prev;
         if (sghmc && !first) {
           u.z = run->z_noise_dev ? run->z_noise_dev + ((size_t)t * run->z_noise_iters + pit) * C * P : nullptr;
           u.ld_z = P;
@@ -693,7 +720,9 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
           u.stream_hi = TAG_NOISE | (uint32_t)((pit * nsw + pv) & 0xffffff);
         }
         BHMC_TRY(launch_hmc_update(ctx, u));
-        BHMC_TRY(mb->grad(s->q_new, C, ld, run->row0, nrows, cfg.precision, s->g, stat));
+        BHMC_TRY(mb->grad(s->q_new, rows, ld, run->row0, nrows, cfg.precision, s->g, stat));
+        run->n_grad_launched += rows;
+        rows_prev = rows;
       }
     }
     if (iters > 0) {  // closing kick of the last variable
@@ -703,6 +732,7 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
       u.pre_len = 0;
       u.pre_off = 0;
       u.it_pre = 0;
+      u.C = rows_prev;
       if (sghmc) {
         u.z = run->z_noise_dev ? run->z_noise_dev + ((size_t)t * run->z_noise_iters + (iters - 1)) * C * P : nullptr;
         u.ld_z = P;
@@ -738,6 +768,7 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     a.loss = run->loss_dev ? run->loss_dev + (size_t)t * C : nullptr;
     a.accept_prob = run->accept_prob_dev ? run->accept_prob_dev + (size_t)t * C : nullptr;
     a.accepted = run->accepted_dev ? run->accepted_dev + (size_t)t * C : nullptr;
+    a.perm = perm;
     BHMC_TRY(launch_accept(ctx, a));
   }
   return BHMC_OK;

@@ -127,6 +127,7 @@ struct UpdateArgs {
   // latch of the model scalar produced by the gradient evaluation that preceded this update
   const double* stat;  // [C]
   double* stat_new;    // [C] written where the chain was active for it_post
+  const int32_t* perm; // row -> chain for the noise stream (nullptr = identity)
 };
 int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a);
 
@@ -143,6 +144,10 @@ struct BeginArgs {
   int64_t chain_id0;
   uint32_t stream_lo, stream_hi;
   double* kin0;  // [C] zeroed by the launcher, receives 0.5*sum p^2
+  // ragged-trajectory compaction: working row r holds chain perm[r] (chains sorted by path length,
+  // longest first, so the active set is always a prefix); nullptr = identity.  q / p0 / z are chain-indexed,
+  // q_new / p_new / kin0 are row-indexed.
+  const int32_t* perm;
 };
 int launch_hmc_begin(bhmc_ctx* ctx, const BeginArgs& a);
 
@@ -175,6 +180,7 @@ struct AcceptArgs {
   double* loss;        // [C] or nullptr
   double* accept_prob; // [C] or nullptr
   int32_t* accepted;   // [C] or nullptr
+  const int32_t* perm; // row -> chain (see BeginArgs); q / p_out / u / outputs are chain-indexed
 };
 int launch_accept(bhmc_ctx* ctx, const AcceptArgs& a);
 

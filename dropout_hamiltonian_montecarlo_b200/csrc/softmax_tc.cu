@@ -607,22 +607,29 @@ static int pick_cpt(int KP, int C) {
 }
 
 int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
-  tc_softmax_release(d);
-  d.Kp = pick_kp(d.K);
-  if (!d.Kp) {
+  const int kp = pick_kp(d.K);
+  if (!kp) {
     set_error("tensor-core path supports at most 64 classes (got %d); use BHMC_PREC_FP32", d.K);
     return BHMC_ERR_UNSUPPORTED;
   }
-  d.Dp = round_up(d.D, 8);
-  d.Npad = round_up(d.N, 8);
-  d.Dt = d.D + 1;
-  size_t a_bytes = (size_t)d.N * d.Dp * 2, t_bytes = (size_t)d.Dt * d.Npad * 2;
-  BHMC_CUDA_OK(cudaMalloc(&d.Xa_hi, a_bytes));
-  BHMC_CUDA_OK(cudaMalloc(&d.Xt_hi, t_bytes));
-  if (want_lo) {
-    BHMC_CUDA_OK(cudaMalloc(&d.Xa_lo, a_bytes));
-    BHMC_CUDA_OK(cudaMalloc(&d.Xt_lo, t_bytes));
+  // re-binding the same shape (fresh host data every step) reuses the operand buffers
+  const bool reuse = d.Xa_hi && d.Kp == kp && d.Dp == round_up(d.D, 8) && d.Npad == round_up(d.N, 8) &&
+                     d.Dt == d.D + 1 && (d.has_lo || !want_lo);
+  if (!reuse) {
+    tc_softmax_release(d);
+    d.Kp = kp;
+    d.Dp = round_up(d.D, 8);
+    d.Npad = round_up(d.N, 8);
+    d.Dt = d.D + 1;
+    size_t a_bytes = (size_t)d.N * d.Dp * 2, t_bytes = (size_t)d.Dt * d.Npad * 2;
+    BHMC_CUDA_OK(cudaMalloc(&d.Xa_hi, a_bytes));
+    BHMC_CUDA_OK(cudaMalloc(&d.Xt_hi, t_bytes));
+    if (want_lo) {
+      BHMC_CUDA_OK(cudaMalloc(&d.Xa_lo, a_bytes));
+      BHMC_CUDA_OK(cudaMalloc(&d.Xt_lo, t_bytes));
+    }
   }
+  want_lo = want_lo || d.Xa_lo != nullptr;
   d.has_lo = want_lo;
   {
     dim3 grid((unsigned)std::min<int64_t>(ceil_div(d.Dp, 256), 65535), (unsigned)1);
@@ -638,7 +645,7 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
   {
     dim3 grid((unsigned)ceil_div(d.Npad, 32), (unsigned)ceil_div(d.Dt, 32));
     k_split_transpose<<<grid, dim3(32, 8), 0, ctx->stream>>>(d.X, d.N, d.D, d.Npad, (__nv_bfloat16*)d.Xt_hi,
-                                                             (__nv_bfloat16*)d.Xt_lo);
+                                                             want_lo ? (__nv_bfloat16*)d.Xt_lo : nullptr);
     ctx->launches++;
   }
   BHMC_CUDA_OK(cudaGetLastError());

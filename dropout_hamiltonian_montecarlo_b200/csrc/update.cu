@@ -52,22 +52,23 @@ __device__ __forceinline__ float4 load_z(const float* z, int64_t ld_z, int c, in
 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_hmc_begin(BeginArgs a) {
-  int c = blockIdx.y;
+  int r = blockIdx.y;                    // working row
+  int c = a.perm ? a.perm[r] : r;        // chain held by this row
   int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 4;
   double k = 0.0;
   if (i < a.P) {
-    int64_t o = (int64_t)c * a.ld + i;
+    int64_t oc = (int64_t)c * a.ld + i, orow = (int64_t)r * a.ld + i;
     float4 z = a.z ? load_z(a.z, a.ld_z, c, i, a.P)
                    : philox_normal4(a.seed, a.chain_id0 + c, (uint32_t)(i >> 2), a.stream_lo, a.stream_hi);
     if (i + 1 >= a.P) z.y = 0.f;
     if (i + 2 >= a.P) z.z = 0.f;
     if (i + 3 >= a.P) z.w = 0.f;
-    st4(a.q_new + o, ld4(a.q + o));
-    st4(a.p0 + o, z);
-    st4(a.p_new + o, z);
+    st4(a.q_new + orow, ld4(a.q + oc));
+    st4(a.p0 + oc, z);
+    st4(a.p_new + orow, z);
     k = 0.5 * ((double)z.x * z.x + (double)z.y * z.y + (double)z.z * z.z + (double)z.w * z.w);
   }
-  block_atomic_add(k, a.kin0 + c);
+  block_atomic_add(k, a.kin0 + r);
 }
 
 int launch_hmc_begin(bhmc_ctx* ctx, const BeginArgs& a) {
@@ -99,9 +100,11 @@ __global__ void __launch_bounds__(TPB) k_hmc_update(UpdateArgs a) {
   float4 g4 = ld4(a.g + o);
   float4 q4 = hit_pre ? ld4(a.q + o) : make_float4(0, 0, 0, 0);
   float4 z4 = make_float4(0, 0, 0, 0);
-  if (NOISE && hit_post)
-    z4 = a.z ? load_z(a.z, a.ld_z, c, i, a.P)
-             : philox_normal4(a.seed, a.chain_id0 + c, (uint32_t)(i >> 2), a.stream_lo, a.stream_hi);
+  if (NOISE && hit_post) {
+    int chain = a.perm ? a.perm[c] : c;  // noise streams are keyed by chain, not by working row
+    z4 = a.z ? load_z(a.z, a.ld_z, chain, i, a.P)
+             : philox_normal4(a.seed, a.chain_id0 + chain, (uint32_t)(i >> 2), a.stream_lo, a.stream_hi);
+  }
   float pe[4] = {p4.x, p4.y, p4.z, p4.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, qe[4] = {q4.x, q4.y, q4.z, q4.w};
   float ze[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
@@ -200,13 +203,14 @@ int launch_sumsq(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, c
 // Metropolis test (hmc.py:60-63,67-71) + state select + sample sink.  The decision is
 // recomputed identically by every block of a chain (a handful of double ops).
 __global__ void __launch_bounds__(TPB) k_accept(AcceptArgs a) {
-  int c = blockIdx.y;
-  double u_cur = a.ea * a.stat_cur[c] + a.eb, u_new = a.ea * a.stat_new[c] + a.eb;
+  int r = blockIdx.y;                    // working row (energies, proposal)
+  int c = a.perm ? a.perm[r] : r;        // chain (state, draws, outputs)
+  double u_cur = a.ea * a.stat_cur[r] + a.eb, u_new = a.ea * a.stat_new[r] + a.eb;
   if (a.extra_cur) {
-    u_cur += a.extra_cur[c];
-    u_new += a.extra_new[c];
+    u_cur += a.extra_cur[r];
+    u_new += a.extra_new[r];
   }
-  double e_cur = u_cur + a.kin0[c], e_new = u_new + a.kin1[c];
+  double e_cur = u_cur + a.kin0[r], e_new = u_new + a.kin1[r];
   double x = exp(e_cur - e_new);
   // Python's builtin min(1, x): returns x only when x < 1 (so NaN -> 1), hmc.py:70
   double A = (x < 1.0) ? x : 1.0;
@@ -220,15 +224,15 @@ __global__ void __launch_bounds__(TPB) k_accept(AcceptArgs a) {
   }
   int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 4;
   if (i >= a.P) return;
-  int64_t o = (int64_t)c * a.ld + i;
-  float4 qv;
+  int64_t oc = (int64_t)c * a.ld + i, orow = (int64_t)r * a.ld + i;
+  float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (acc) {
-    qv = ld4(a.q_new + o);
-    st4(a.q + o, qv);
-    float4 pv = ld4(a.p_new + o);
-    st4(a.p_out + o, make_float4(a.p_sign * pv.x, a.p_sign * pv.y, a.p_sign * pv.z, a.p_sign * pv.w));
+    qv = ld4(a.q_new + orow);
+    st4(a.q + oc, qv);
+    float4 pv = ld4(a.p_new + orow);
+    st4(a.p_out + oc, make_float4(a.p_sign * pv.x, a.p_sign * pv.y, a.p_sign * pv.z, a.p_sign * pv.w));
   } else if (a.sample) {
-    qv = ld4(a.q + o);
+    qv = ld4(a.q + oc);
   }
   if (a.sample) {
     float* s = a.sample + (int64_t)c * a.P + i;  // compact rows: scalar stores at the tail

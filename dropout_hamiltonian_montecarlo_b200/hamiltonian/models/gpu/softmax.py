@@ -19,11 +19,14 @@ from ...._lib import PREC, PRIOR
 class softmax(_base.ChainModel):
     var_names = ("weights", "bias")
 
-    def __init__(self, _hyper, *, precision="bf16x3", prior="cpu", device=None):
+    def __init__(self, _hyper, *, precision="bf16x3", prior="cpu", device=None, cache_data=True):
         super().__init__(device)
         self.hyper = _hyper
         self.precision = precision
         self.prior = prior
+        # cache_data=False: host X / y are re-uploaded on every call (into the same device buffers), for
+        # callers that mutate their arrays in place -- and for bench.py's end-to-end measurement
+        self.cache_data = cache_data
         self._bound = None  # (key, handle, keepalive)
 
     # ---- data binding ------------------------------------------------------------------------
@@ -43,7 +46,8 @@ class softmax(_base.ChainModel):
         """Bind (and cache) the data matrix: fp32 X on the device plus the bf16 operand copies the
         tensor-core path streams.  Re-binding happens only when X / y are different objects."""
         key = (_base.array_key(X), _base.array_key(y), self.precision)
-        if self._bound is not None and self._bound[0] == key:
+        host = not (isinstance(X, torch.Tensor) and X.is_cuda)
+        if self._bound is not None and self._bound[0] == key and (self.cache_data or not host):
             return self._bound[1]
         labels, k = self._labels_of(y, n_classes)
         if k is None:
@@ -60,7 +64,12 @@ class softmax(_base.ChainModel):
             Xh = X if isinstance(X, torch.Tensor) else torch.as_tensor(np.asarray(X))
             Xh = Xh.to(torch.float32).contiguous()
             n, d = Xh.shape
-            h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
+            old = self._bound[1] if self._bound is not None else None
+            if old is not None and (old.N, old.D, old.K) == (n, d, k) and self._bound[0][2] == self.precision:
+                h = old  # same shape: refresh the device copies in place (keeps the sampler state alive)
+                self._bound = None
+            else:
+                h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
             h.bind_host(Xh, torch.as_tensor(np.ascontiguousarray(labels)), mask)
             ctx.sync()  # the host buffers may be released by the caller after bind returns
         if self._bound is not None:
