@@ -66,6 +66,7 @@ _PROTOS = {
     "bhmc_softmax_bind_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "bhmc_softmax_bind_data_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "bhmc_mvn_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_void_p)]),
+    "bhmc_model_set_global_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_float]),
     "bhmc_model_destroy": (C.c_int, [C.c_void_p]),
     "bhmc_model_n_params": (C.c_int64, [C.c_void_p]),
     "bhmc_model_n_vars": (C.c_int32, [C.c_void_p]),
@@ -84,6 +85,7 @@ _PROTOS = {
     "bhmc_philox4x32_host": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "bhmc_sampler_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SamplerConfig), C.POINTER(C.c_void_p)]),
     "bhmc_sampler_destroy": (C.c_int, [C.c_void_p]),
+    "bhmc_sampler_set_grad_hook": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "bhmc_sampler_ld": (C.c_int64, [C.c_void_p]),
     "bhmc_sampler_state_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "bhmc_sampler_set_q": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
@@ -91,6 +93,8 @@ _PROTOS = {
     "bhmc_sampler_hmc_run": (C.c_int, [C.c_void_p, C.POINTER(HmcRun)]),
     "bhmc_sampler_sg_run": (C.c_int, [C.c_void_p, C.POINTER(SgRun)]),
 }
+
+GRAD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64)
 
 _lib = None
 

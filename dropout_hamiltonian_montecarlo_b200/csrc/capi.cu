@@ -196,6 +196,8 @@ struct SoftmaxModel : ModelBase {
     cudaFree(y_owned);
   }
   int64_t default_rows() const override { return d.N; }
+  int64_t global_rows = 0;
+  float alpha_energy = -1.f;  // alpha of the log-prior constant when it differs from the gradient's (row shards)
 
   int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) override {
     switch (prec) {
@@ -208,14 +210,15 @@ struct SoftmaxModel : ModelBase {
   }
   // NLP = -(LL + log_prior)/n  (softmax.py:74-79)
   void energy_coeffs(int64_t nrows, double* a, double* b, double* cv) const override {
+    if (global_rows > 0) nrows = global_rows;  // row-sharded: the all-reduced LL covers all rows
     *a = -1.0 / (double)nrows;
     double lp = 0.0;
     for (int v = 0; v < n_vars; ++v) {
       cv[v] = 0.0;
       if (prior == BHMC_PRIOR_CPU)  // softmax.py:22-30: -(dim/2 log 2pi - dim/2 log alpha)
-        lp -= 0.5 * (double)var_len[v] * std::log(2.0 * M_PI) - 0.5 * (double)var_len[v] * std::log((double)alpha);
+        lp -= 0.5 * (double)var_len[v] * std::log(2.0 * M_PI) - 0.5 * (double)var_len[v] * std::log((double)(alpha_energy > 0.f ? alpha_energy : alpha));
       else  // models/gpu/softmax.py:29-39: -alpha/2 |theta_v|^2 / dim_v
-        cv[v] = 0.5 * (double)alpha / ((double)var_len[v] * (double)nrows);
+        cv[v] = 0.5 * (double)(alpha_energy > 0.f ? alpha_energy : alpha) / ((double)var_len[v] * (double)nrows);
     }
     *b = -lp / (double)nrows;
   }
@@ -348,6 +351,16 @@ int bhmc_mvn_create(bhmc_ctx* ctx, int32_t dim, const double* mu_host, const dou
   return BHMC_OK;
 }
 
+int bhmc_model_set_global_rows(bhmc_model* m, int64_t n_global_rows, float alpha_global) {
+  SoftmaxModel* s;
+  BHMC_TRY(softmax_of(m, &s));
+  BHMC_CHECK_ARG(n_global_rows >= s->d.N, "global row count %lld is smaller than the local %lld", (long long)n_global_rows,
+                 (long long)s->d.N);
+  s->global_rows = n_global_rows;
+  s->alpha_energy = alpha_global;
+  return BHMC_OK;
+}
+
 int bhmc_model_destroy(bhmc_model* m) {
   if (!m) return BHMC_OK;
   if (m->impl) {
@@ -464,6 +477,17 @@ struct bhmc_sampler {
   float *q = nullptr, *p = nullptr, *g = nullptr, *q_new = nullptr, *p_new = nullptr;
   double* scal = nullptr;  // stat | stat_cur | stat_new | kin0 | kin1 | extra_cur | extra_new | sumsq[C*nv] | u[C]
   int32_t* Ldev = nullptr;
+  bhmc_grad_hook hook = nullptr;
+  void* hook_user = nullptr;
+  // gradient (or log-lik only when g == nullptr) of the first `rows` working rows, then the optional hook
+  int eval(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat) {
+    BHMC_TRY(model->grad(q, rows, ld, row0, nrows, cfg.precision, g, stat));
+    if (hook && hook(hook_user, g, stat, rows, ld) != 0) {
+      bhmc::set_error("gradient hook reported a failure");
+      return BHMC_ERR_STATE;
+    }
+    return BHMC_OK;
+  }
 };
 
 extern "C" {
@@ -519,6 +543,13 @@ int bhmc_sampler_destroy(bhmc_sampler* s) {
 }
 
 int64_t bhmc_sampler_ld(const bhmc_sampler* s) { return s ? s->ld : -1; }
+
+int bhmc_sampler_set_grad_hook(bhmc_sampler* s, bhmc_grad_hook hook, void* user) {
+  BHMC_CHECK_ARG(s, "sampler is NULL");
+  s->hook = hook;
+  s->hook_user = user;
+  return BHMC_OK;
+}
 
 int bhmc_sampler_state_ptr(bhmc_sampler* s, int32_t which, float** out) {
   BHMC_CHECK_ARG(s && out && which >= 0 && which <= 2, "bad argument");
@@ -670,7 +701,7 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     b.perm = perm;
     BHMC_TRY(launch_hmc_begin(ctx, b));
     // 2. gradient at the current point (hmc.py:47); its log-likelihood doubles as NLP(q)
-    BHMC_TRY(mb->grad(s->q_new, C, ld, run->row0, nrows, cfg.precision, s->g, stat));
+    BHMC_TRY(s->eval(s->q_new, C, run->row0, nrows, s->g, stat));
     run->n_grad_launched += C;
     BHMC_CUDA_OK(cudaMemcpyAsync(stat_cur, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
     BHMC_CUDA_OK(cudaMemcpyAsync(stat_new, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -720,7 +751,7 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
           u.stream_hi = TAG_NOISE | (uint32_t)((pit * nsw + pv) & 0xffffff);
         }
         BHMC_TRY(launch_hmc_update(ctx, u));
-        BHMC_TRY(mb->grad(s->q_new, rows, ld, run->row0, nrows, cfg.precision, s->g, stat));
+        BHMC_TRY(s->eval(s->q_new, rows, run->row0, nrows, s->g, stat));
         run->n_grad_launched += rows;
         rows_prev = rows;
       }
@@ -801,7 +832,7 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
     const bool sampling = e >= run->burnin;
     for (int64_t j = 0; j < nb; ++j, ++k) {
       const int64_t row0 = j * run->batch_size;
-      BHMC_TRY(mb->grad(s->q, C, ld, row0, run->batch_size, cfg.precision, s->g, stat));
+      BHMC_TRY(s->eval(s->q, C, row0, run->batch_size, s->g, stat));
       run->n_grad_evals += C;
       if (sgd) {
         BHMC_TRY(launch_sgd_update(ctx, s->q, s->p, s->g, ld, P, C, (float)run->gamma, (float)run->step_size));
@@ -831,7 +862,7 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
         const int64_t row0 = (nb - 1) * run->batch_size;
         double a, b, cv[BHMC_MAX_VARS];
         mb->energy_coeffs(run->batch_size, &a, &b, cv);
-        BHMC_TRY(mb->grad(s->q, C, ld, row0, run->batch_size, cfg.precision, nullptr, stat));
+        BHMC_TRY(s->eval(s->q, C, row0, run->batch_size, nullptr, stat));
         BHMC_TRY(launch_affine(ctx, stat, a, b, nullptr, run->logp_dev + (size_t)i * C, C));
       }
       if (run->samples_dev) BHMC_TRY(launch_copy_rows(ctx, s->q, ld, run->samples_dev + (size_t)i * C * P, P, P, C));

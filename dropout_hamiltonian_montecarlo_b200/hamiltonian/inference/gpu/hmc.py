@@ -104,6 +104,9 @@ class _ChainSampler:
                               precision=PREC[self.precision], sweep=groups,
                               shared_path=self.path_length_mode == "shared", leapfrog=self.integrator == "leapfrog",
                               sghmc_descent=self.sign == "descent", reject_nan=self.reject_nan)
+            if getattr(model, "row_sharded", False):
+                from ....parallel import RowShardHook
+                s._row_hook = RowShardHook(s, getattr(model, "group", None))  # keeps the callback alive
             self._sampler = (key, s)
         return h, shapes, squeeze, like, q0, self._sampler[1]
 

@@ -14,13 +14,20 @@ import torch
 from ... import _base
 from ....runtime import SoftmaxHandle, default_context
 from ...._lib import PREC, PRIOR
+from ...._lib import check as _lib_check
 
 
 class softmax(_base.ChainModel):
     var_names = ("weights", "bias")
 
-    def __init__(self, _hyper, *, precision="bf16x3", prior="cpu", device=None, cache_data=True):
+    def __init__(self, _hyper, *, precision="bf16x3", prior="cpu", device=None, cache_data=True,
+                 row_sharded=False, group=None):
         super().__init__(device)
+        # row_sharded=True (multi-GPU full-batch HMC, BASELINE config 5): X_train / y_train passed to this
+        # process are ITS row shard; gradients and log-likelihoods are all-reduced over ``group`` after every
+        # evaluation (NCCL), the prior term is split alpha/G per rank, energies use the global row count.
+        self.row_sharded = row_sharded
+        self.group = group
         self.hyper = _hyper
         self.precision = precision
         self.prior = prior
@@ -57,7 +64,7 @@ class softmax(_base.ChainModel):
         if isinstance(X, torch.Tensor) and X.is_cuda:
             Xd = X.to(torch.float32).contiguous()
             n, d = Xd.shape
-            h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
+            h = SoftmaxHandle(ctx, n, d, k, self._alpha_local(), PRIOR[self.prior])
             h.bind(Xd, torch.as_tensor(labels).to(ctx.device), mask)
         else:
             # host buffers cross the C ABI as they are (bhmc_softmax_bind_data_host does the H2D copy)
@@ -69,13 +76,25 @@ class softmax(_base.ChainModel):
                 h = old  # same shape: refresh the device copies in place (keeps the sampler state alive)
                 self._bound = None
             else:
-                h = SoftmaxHandle(ctx, n, d, k, float(self.hyper["alpha"]), PRIOR[self.prior])
+                h = SoftmaxHandle(ctx, n, d, k, self._alpha_local(), PRIOR[self.prior])
             h.bind_host(Xh, torch.as_tensor(np.ascontiguousarray(labels)), mask)
             ctx.sync()  # the host buffers may be released by the caller after bind returns
         if self._bound is not None:
             self._bound[1].close()
+        if self.row_sharded:
+            import torch.distributed as dist
+            tot = torch.tensor([h.N], dtype=torch.int64, device=ctx.device)
+            dist.all_reduce(tot, group=self.group)
+            _lib_check(ctx.L.bhmc_model_set_global_rows(h.handle, int(tot.item()), float(self.hyper["alpha"])))
+            h.global_rows = int(tot.item())
         self._bound = (key, h, (X, y))
         return h
+
+    def _alpha_local(self):
+        if not self.row_sharded:
+            return float(self.hyper["alpha"])
+        import torch.distributed as dist
+        return float(self.hyper["alpha"]) / dist.get_world_size(self.group)
 
     def unbind(self):
         if self._bound is not None:

@@ -88,6 +88,11 @@ int bhmc_softmax_bind_data_host(bhmc_model* m, const float* X_host, const int32_
  * cov_inv: [dim,dim] row-major (host), logdet = log det(cov). */
 int bhmc_mvn_create(bhmc_ctx* ctx, int32_t dim, const double* mu_host, const double* cov_inv_host,
                     double logdet, bhmc_model** out);
+/* row-sharded data (multi-GPU full-batch HMC): this model holds n_rows of n_global_rows; energies are
+ * normalised by the global count (softmax.py:79 divides by the size of the whole X_train) and the
+ * log-prior constant uses alpha_global (the model itself was created with alpha_global / n_ranks so that the
+ * all-reduced gradient carries the prior term exactly once) */
+int bhmc_model_set_global_rows(bhmc_model* m, int64_t n_global_rows, float alpha_global);
 int bhmc_model_destroy(bhmc_model* m);
 int64_t bhmc_model_n_params(const bhmc_model* m);
 int32_t bhmc_model_n_vars(const bhmc_model* m);
@@ -139,6 +144,12 @@ typedef struct bhmc_sampler_config {
 int bhmc_sampler_create(bhmc_ctx* ctx, bhmc_model* model, const bhmc_sampler_config* cfg,
                         bhmc_sampler** out);
 int bhmc_sampler_destroy(bhmc_sampler* s);
+/* Hook invoked (on the host, in stream order) after every gradient / log-likelihood evaluation of the
+ * drivers with the device buffers it produced: g_dev [n_rows_active, ld] (NULL for log-lik only) and
+ * stat_dev [n_rows_active].  Row-sharded runs use it to enqueue the NCCL all-reduce (sum) of both on the
+ * context stream.  Return non-zero to abort the run. */
+typedef int (*bhmc_grad_hook)(void* user, float* g_dev, double* stat_dev, int32_t n_rows_active, int64_t ld);
+int bhmc_sampler_set_grad_hook(bhmc_sampler* s, bhmc_grad_hook hook, void* user);
 int64_t bhmc_sampler_ld(const bhmc_sampler* s);
 /* device pointers of the resident chain state ([n_chains, ld] fp32): 0=q 1=p 2=grad */
 int bhmc_sampler_state_ptr(bhmc_sampler* s, int32_t which, float** out_dev);
