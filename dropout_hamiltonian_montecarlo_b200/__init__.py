@@ -24,7 +24,7 @@ def install_as_hamiltonian():
 
     root = importlib.import_module(__name__ + ".hamiltonian")
     sys.modules["hamiltonian"] = root
-    for sub in ("utils", "models", "models.gpu", "models.gpu.softmax", "models.gpu.mvn_gaussian",
+    for sub in ("utils", "models", "models.gpu", "models.gpu.softmax", "models.gpu.mvn_gaussian", "models.gpu.mlp",
                 "inference", "inference.gpu", "inference.gpu.hmc", "inference.gpu.sgmcmc",
                 "inference.gpu.sgld", "inference.gpu.sghmc", "inference.gpu.sgd"):
         sys.modules["hamiltonian." + sub] = importlib.import_module(__name__ + ".hamiltonian." + sub)

@@ -351,6 +351,30 @@ int bhmc_mvn_create(bhmc_ctx* ctx, int32_t dim, const double* mu_host, const dou
   return BHMC_OK;
 }
 
+int bhmc_mlp_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_in, int32_t n_mid, int32_t n_out, float alpha,
+                    float dropout_ratio, uint64_t seed, int64_t chain_id0, bhmc_model** out) {
+  BHMC_CHECK_ARG(ctx && out, "ctx/out is NULL");
+  BHMC_CHECK_ARG(n_rows > 0 && n_in > 0 && n_mid > 0 && n_out > 0, "bad MLP shape");
+  BHMC_CHECK_ARG(dropout_ratio >= 0.f && dropout_ratio < 1.f, "dropout ratio %f out of [0,1)", dropout_ratio);
+  ModelBase* m = mlp_model_new(ctx, n_rows, n_in, n_mid, n_out, alpha, dropout_ratio, seed, chain_id0);
+  if (!m) return BHMC_ERR_NOMEM;
+  bhmc_model* h = new bhmc_model();
+  h->impl = m;
+  *out = h;
+  return BHMC_OK;
+}
+
+int bhmc_mlp_bind_data(bhmc_model* m, const float* X, const int32_t* labels, int32_t is_host) {
+  BHMC_CHECK_ARG(m && m->impl, "model is NULL");
+  BHMC_CUDA_OK(cudaSetDevice(m->impl->ctx->device));
+  return mlp_model_bind(m->impl, X, labels, is_host);
+}
+
+int bhmc_mlp_set_masks(bhmc_model* m, const uint8_t* masks_dev) {
+  BHMC_CHECK_ARG(m && m->impl, "model is NULL");
+  return mlp_model_set_masks(m->impl, masks_dev);
+}
+
 int bhmc_model_set_global_rows(bhmc_model* m, int64_t n_global_rows, float alpha_global) {
   SoftmaxModel* s;
   BHMC_TRY(softmax_of(m, &s));
@@ -420,20 +444,8 @@ int bhmc_model_nlp(bhmc_model* m, const float* q, int32_t C, int64_t ld, int64_t
   void* ss = nullptr;
   BHMC_TRY(mb->ctx->get_scratch(4, sizeof(double) * C * (mb->n_vars + 1), &ss));
   double* sumsq = (double*)ss;
-  BHMC_TRY(launch_sumsq(mb->ctx, q, ld, C, mb->n_vars, mb->var_off, mb->var_len, sumsq));
-  // fold sum_v cv*sumsq_v on the host-free path: tiny kernel via affine per variable
   double* extra = sumsq + (size_t)C * mb->n_vars;
-  BHMC_CUDA_OK(cudaMemsetAsync(extra, 0, sizeof(double) * C, mb->ctx->stream));
-  for (int v = 0; v < mb->n_vars; ++v) {
-    // extra[c] += cv[v]*sumsq[c*n_vars+v] : strided gather done with cudaMemcpy2D into a temp then affine
-    double* tmp = nullptr;
-    void* t = nullptr;
-    BHMC_TRY(mb->ctx->get_scratch(5, sizeof(double) * C, &t));
-    tmp = (double*)t;
-    BHMC_CUDA_OK(cudaMemcpy2DAsync(tmp, sizeof(double), sumsq + v, sizeof(double) * mb->n_vars, sizeof(double), C,
-                                   cudaMemcpyDeviceToDevice, mb->ctx->stream));
-    BHMC_TRY(launch_affine(mb->ctx, tmp, cv[v], 0.0, extra, extra, C));
-  }
+  BHMC_TRY(launch_prior_energy(mb->ctx, q, ld, C, mb->n_vars, mb->var_off, mb->var_len, cv, sumsq, extra));
   return launch_affine(mb->ctx, nlp, a, b, extra, nlp, C);
 }
 
@@ -604,13 +616,6 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
   mb->energy_coeffs(nrows, &ea, &eb, cv);
   bool need_extra = false;
   for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
-  if (need_extra) {
-    set_error("quadratic-prior energies (BHMC_PRIOR_GPU) are not wired into the Metropolis test yet");
-    return BHMC_ERR_UNSUPPORTED;
-  }
-  (void)extra_cur;
-  (void)extra_new;
-  (void)sumsq;
 
   // path lengths for every step and chain: L = ceil(2 u path/eps), hmc.py:46 (host side: it sizes the launch loop)
   const int n_steps = run->n_steps;
@@ -700,6 +705,8 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     b.kin0 = kin0;
     b.perm = perm;
     BHMC_TRY(launch_hmc_begin(ctx, b));
+    if (need_extra)  // quadratic log-prior part of U(q) (row-indexed like the other energies)
+      BHMC_TRY(launch_prior_energy(ctx, s->q_new, ld, C, mb->n_vars, mb->var_off, mb->var_len, cv, sumsq, extra_cur));
     // 2. gradient at the current point (hmc.py:47); its log-likelihood doubles as NLP(q)
     BHMC_TRY(s->eval(s->q_new, C, run->row0, nrows, s->g, stat));
     run->n_grad_launched += C;
@@ -774,6 +781,8 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     }
     // 4. Metropolis test (hmc.py:58-63): energies = NLP + 0.5|p|^2, momentum flipped for HMC only
     BHMC_TRY(launch_kinetic(ctx, s->p_new, ld, P, C, kin1));
+    if (need_extra)
+      BHMC_TRY(launch_prior_energy(ctx, s->q_new, ld, C, mb->n_vars, mb->var_off, mb->var_len, cv, sumsq, extra_new));
     AcceptArgs a{};
     a.q = s->q;
     a.q_new = s->q_new;
@@ -787,6 +796,8 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     a.stat_new = stat_new;
     a.ea = ea;
     a.eb = eb;
+    a.extra_cur = need_extra ? extra_cur : nullptr;
+    a.extra_new = need_extra ? extra_new : nullptr;
     a.kin0 = kin0;
     a.kin1 = kin1;
     a.u = run->u_accept_host ? uacc_d + (size_t)t * C : nullptr;
@@ -863,7 +874,14 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
         double a, b, cv[BHMC_MAX_VARS];
         mb->energy_coeffs(run->batch_size, &a, &b, cv);
         BHMC_TRY(s->eval(s->q, C, row0, run->batch_size, nullptr, stat));
-        BHMC_TRY(launch_affine(ctx, stat, a, b, nullptr, run->logp_dev + (size_t)i * C, C));
+        bool need_extra = false;
+        for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
+        double* extra = nullptr;
+        if (need_extra) {
+          extra = s->scal + 5 * (size_t)C;
+          BHMC_TRY(launch_prior_energy(ctx, s->q, ld, C, mb->n_vars, mb->var_off, mb->var_len, cv, s->scal + 8 * (size_t)C, extra));
+        }
+        BHMC_TRY(launch_affine(ctx, stat, a, b, extra, run->logp_dev + (size_t)i * C, C));
       }
       if (run->samples_dev) BHMC_TRY(launch_copy_rows(ctx, s->q, ld, run->samples_dev + (size_t)i * C * P, P, P, C));
     }

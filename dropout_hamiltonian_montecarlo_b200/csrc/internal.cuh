@@ -156,6 +156,9 @@ int launch_kinetic(bhmc_ctx* ctx, const float* p, int64_t ld, int64_t P, int C, 
 int launch_sumsq(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, const int64_t* off,
                  const int64_t* len, double* out);
 
+int launch_prior_energy(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, const int64_t* off,
+                        const int64_t* len, const double* cv, double* sumsq_scratch, double* out);
+
 struct AcceptArgs {
   float* q;            // in/out: current state, overwritten by the proposal where accepted
   const float* q_new;
@@ -236,5 +239,11 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo);
 void tc_softmax_release(SoftmaxData& d);
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
                     int64_t row0, int64_t nrows, float* g, double* loglik, bool split3);
+
+// ---- mlp.cu -----------------------------------------------------------------------------------
+ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int n_out, float alpha, float ratio,
+                         uint64_t seed, int64_t chain_id0);
+int mlp_model_bind(ModelBase* m, const float* X, const int32_t* labels, int is_host);
+int mlp_model_set_masks(ModelBase* m, const uint8_t* masks_dev);
 
 }  // namespace bhmc

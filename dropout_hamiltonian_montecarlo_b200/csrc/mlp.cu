@@ -1,0 +1,384 @@
+// Dropout MLP (n_in -> n_mid -> n_mid -> n_out) log-posterior gradient for a batch of chains with
+// chain-private weights.  Reference: hamiltonian/models/gpu/mlp.py
+//   :19-31  MyNetwork: h = relu(dropout(l1 x)); h = relu(dropout(l2 h)); y = l3(dropout(h)), ratio 0.1,
+//           Chainer L.Linear stores W as (out, in); Chainer dropout is inverted (x * mask / (1-ratio))
+//   :47-64  grad = d(mean softmax-CE)/d theta + alpha/2 * theta
+//   :66-82  log_likelihood = the (positive) mean CE loss; NLP = loss + log_prior,
+//   :40-45  log_prior = -alpha/2 sum_v |theta_v|^2 / dim_v
+// Parameter row (Chainer namedparams order): /l1/W [mid,in] | /l1/b | /l2/W [mid,mid] | /l2/b | /l3/W [out,mid] | /l3/b.
+//
+// This round the eight GEMMs per evaluation run as fp32 FMA on CUDA cores (one strided-batched tile kernel
+// with fused epilogues: bias + dropout + ReLU, ReLU-gate of the back-propagated signal, alpha/2*W); moving
+// them onto the tcgen05 main loop of softmax_tc.cu (grouped per-chain tensor maps) is the next step.
+// Because relu(a*m) > 0 implies the keep-mask m == 1, the backward pass needs only the stored activations
+// (H1, H2d), not the masks:  dA2 = dH2d * [H2d>0] / keep^2,  dA1 = dH1 * [H1>0] / keep.
+#include <new>
+
+#include "internal.cuh"
+#include "philox.cuh"
+
+namespace bhmc {
+
+static constexpr int TM = 64, TN = 64, TK = 16;
+
+struct GemmDesc {
+  const float* A;  // element (m,k) at A + c*a_batch + m*a_rs + k*a_cs
+  int64_t a_batch, a_rs, a_cs;
+  const float* B;  // element (k,n) at B + c*b_batch + k*b_rs + n*b_cs
+  int64_t b_batch, b_rs, b_cs;
+  float* C;  // element (m,n) at C + c*c_batch + m*c_rs + n
+  int64_t c_batch, c_rs;
+  int M, N, K;
+  const float* bias;  // + bias[c*bias_batch + n]
+  int64_t bias_batch;
+  const float* addsrc;  // + add_scale * addsrc[c*add_batch + m*add_rs + n]
+  int64_t add_batch, add_rs;
+  float add_scale;
+  const float* gate;  // *= gate_scale * [gate[c*gate_batch + m*gate_rs + n] > 0]
+  int64_t gate_batch, gate_rs;
+  float gate_scale;
+  int epi;  // 0: linear; 1: relu(v*mask_a*keep_inv); 2: relu(v*mask_a*keep_inv)*mask_b*keep_inv
+  float keep_inv, keep_prob;
+  const uint8_t* mask_a;  // injected keep-masks [c][m][n] (tests) or nullptr -> Philox
+  const uint8_t* mask_b;
+  int64_t mask_batch;
+  uint64_t seed;
+  int64_t chain_id0;
+  uint32_t eval_id, layer_a, layer_b;
+};
+
+__device__ __forceinline__ uint32_t keep_bits4(const GemmDesc& d, int c, int m, int n, uint32_t layer) {
+  // four Bernoulli(keep_prob) draws for units n..n+3 (n % 4 == 0) of row m; bit e = keep
+  U4 r = philox4x32_10(U4{(uint32_t)(((int64_t)m * d.N + n) >> 2), (uint32_t)(d.chain_id0 + c), d.eval_id,
+                           TAG_DROPOUT | layer},
+                       (uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+  uint32_t thr = (uint32_t)(d.keep_prob * 4294967296.0);
+  return (r.x < thr ? 1u : 0u) | (r.y < thr ? 2u : 0u) | (r.z < thr ? 4u : 0u) | (r.w < thr ? 8u : 0u);
+}
+
+__global__ void __launch_bounds__(256) k_mlp_gemm(GemmDesc d) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int c = blockIdx.z, t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const float* A = d.A + (int64_t)c * d.a_batch;
+  const float* B = d.B + (int64_t)c * d.b_batch;
+  const bool a_kfast = d.a_cs == 1, b_nfast = d.b_cs == 1;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < d.K; k0 += TK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int m, k;
+      if (a_kfast) m = t >> 2, k = (t & 3) * 4 + e;
+      else k = t >> 4, m = (t & 15) * 4 + e;
+      float v = 0.f;
+      if (m0 + m < d.M && k0 + k < d.K) v = A[(int64_t)(m0 + m) * d.a_rs + (int64_t)(k0 + k) * d.a_cs];
+      As[k][m] = v;
+      int n, kb;
+      if (b_nfast) kb = t >> 4, n = (t & 15) * 4 + e;
+      else n = t >> 2, kb = (t & 3) * 4 + e;
+      float w = 0.f;
+      if (n0 + n < d.N && k0 + kb < d.K) w = B[(int64_t)(k0 + kb) * d.b_rs + (int64_t)(n0 + n) * d.b_cs];
+      Bs[kb][n] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = As[kk][ty * 4 + e], b[e] = Bs[kk][tx * 4 + e];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int nb = n0 + tx * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= d.M) continue;
+    uint32_t ka = 15u, kb = 15u;
+    if (d.epi >= 1 && nb < d.N) {
+      if (d.mask_a) {
+        ka = 0;
+        for (int j = 0; j < 4; ++j)
+          if (nb + j < d.N && d.mask_a[(int64_t)c * d.mask_batch + (int64_t)m * d.N + nb + j]) ka |= 1u << j;
+      } else {
+        ka = keep_bits4(d, c, m, nb, d.layer_a);
+      }
+      if (d.epi == 2) {
+        if (d.mask_b) {
+          kb = 0;
+          for (int j = 0; j < 4; ++j)
+            if (nb + j < d.N && d.mask_b[(int64_t)c * d.mask_batch + (int64_t)m * d.N + nb + j]) kb |= 1u << j;
+        } else {
+          kb = keep_bits4(d, c, m, nb, d.layer_b);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = nb + j;
+      if (n >= d.N) continue;
+      float v = acc[i][j];
+      if (d.bias) v += d.bias[(int64_t)c * d.bias_batch + n];
+      if (d.addsrc) v += d.add_scale * d.addsrc[(int64_t)c * d.add_batch + (int64_t)m * d.add_rs + n];
+      if (d.gate) v = (d.gate[(int64_t)c * d.gate_batch + (int64_t)m * d.gate_rs + n] > 0.f) ? v * d.gate_scale : 0.f;
+      if (d.epi >= 1) {
+        v = ((ka >> j) & 1u) ? v * d.keep_inv : 0.f;
+        v = fmaxf(v, 0.f);
+        if (d.epi == 2) v = ((kb >> j) & 1u) ? v * d.keep_inv : 0.f;
+      }
+      d.C[(int64_t)c * d.c_batch + (int64_t)m * d.c_rs + n] = v;
+    }
+  }
+}
+
+static int run_gemm(bhmc_ctx* ctx, const GemmDesc& d, int C) {
+  dim3 grid((unsigned)ceil_div(d.M, TM), (unsigned)ceil_div(d.N, TN), (unsigned)C);
+  k_mlp_gemm<<<grid, 256, 0, ctx->stream>>>(d);
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+// softmax cross-entropy over n_out logits: Z <- (softmax(Z) - onehot)/B ; loss[c] += (lse - z_y)/B   (mlp.py:57)
+__global__ void __launch_bounds__(256) k_mlp_loss(float* __restrict__ Z, int B, int n_out, const int32_t* __restrict__ y,
+                                                  double* __restrict__ loss, int write_grad) {
+  const int c = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  double my = 0.0;
+  if (r < B) {
+    float* z = Z + ((int64_t)c * B + r) * n_out;
+    float m = -INFINITY;
+    for (int k = 0; k < n_out; ++k) m = fmaxf(m, z[k]);
+    float s = 0.f;
+    for (int k = 0; k < n_out; ++k) s += expf(z[k] - m);
+    const int yy = y[r];
+    my = ((double)m + (double)logf(s) - (double)z[yy]) / (double)B;
+    if (write_grad) {
+      const float inv = 1.0f / s, ib = 1.0f / (float)B;
+      for (int k = 0; k < n_out; ++k) z[k] = (expf(z[k] - m) * inv - (k == yy ? 1.f : 0.f)) * ib;
+    }
+  }
+  __shared__ double sm[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my += __shfl_xor_sync(0xffffffffu, my, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = my;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += sm[w];
+    atomicAdd(loss + c, tot);
+  }
+}
+
+// bias gradient: out[c, n] = sum_b S[c, b, n] + alpha/2 * bias[c, n]
+__global__ void __launch_bounds__(128) k_mlp_colsum(const float* __restrict__ S, int B, int N, int64_t s_batch,
+                                                    const float* __restrict__ q, int64_t ld, int64_t b_off,
+                                                    float half_alpha, float* __restrict__ g) {
+  const int c = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* s = S + (int64_t)c * s_batch + n;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += s[(int64_t)b * N];
+  g[(int64_t)c * ld + b_off + n] = acc + half_alpha * q[(int64_t)c * ld + b_off + n];
+}
+
+struct MlpModel : ModelBase {
+  int64_t N = 0;
+  int n_in = 0, n_mid = 0, n_out = 0;
+  float alpha = 0.f, ratio = 0.1f;
+  const float* X = nullptr;
+  const int32_t* labels = nullptr;
+  float* X_owned = nullptr;
+  int32_t* y_owned = nullptr;
+  const uint8_t* masks = nullptr;  // injected [3][C][B][n_mid] or nullptr
+  uint64_t seed = 0;
+  int64_t chain_id0 = 0;
+  uint32_t eval_id = 0;
+  int64_t oW1, ob1, oW2, ob2, oW3, ob3;
+
+  ~MlpModel() override {
+    cudaFree(X_owned);
+    cudaFree(y_owned);
+  }
+  int64_t default_rows() const override { return N; }
+
+  // NLP = loss + log_prior, log_prior = -alpha/2 sum_v |theta_v|^2/dim_v  (mlp.py:40-45,80-82)
+  void energy_coeffs(int64_t, double* a, double* b, double* cv) const override {
+    *a = 1.0;
+    *b = 0.0;
+    for (int v = 0; v < n_vars; ++v) cv[v] = -0.5 * (double)alpha / (double)var_len[v];
+  }
+
+  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int, float* g, double* stat) override {
+    BHMC_CHECK_ARG(X && labels, "mlp model has no bound data");
+    BHMC_CHECK_ARG(row0 >= 0 && nrows > 0 && row0 + nrows <= N, "row window outside the bound rows");
+    const int B = (int)nrows;
+    const float keep_inv = 1.0f / (1.0f - ratio), keep_prob = 1.0f - ratio;
+    const int64_t act = (int64_t)B * n_mid;
+    void* sc = nullptr;
+    BHMC_TRY(ctx->get_scratch(7, sizeof(float) * (size_t)C * (4 * act + (size_t)B * n_out), &sc));
+    float* H1 = (float*)sc;
+    float* H2d = H1 + (size_t)C * act;
+    float* dA2 = H2d + (size_t)C * act;
+    float* dA1 = dA2 + (size_t)C * act;
+    float* Z = dA1 + (size_t)C * act;
+    const float* Xb = X + row0 * n_in;
+    const uint32_t ev = eval_id++;
+    const int64_t mstride = (int64_t)B * n_mid;  // per-chain stride inside one injected mask layer
+    auto base = [&]() {
+      GemmDesc d{};
+      d.keep_inv = keep_inv;
+      d.keep_prob = keep_prob;
+      d.seed = seed;
+      d.chain_id0 = chain_id0;
+      d.eval_id = ev;
+      d.mask_batch = mstride;
+      return d;
+    };
+    BHMC_CUDA_OK(cudaMemsetAsync(stat, 0, sizeof(double) * C, ctx->stream));
+    {
+      GroupTimer t(ctx, KG_FWD);
+      // H1 = relu(dropout(X W1^T + b1))
+      GemmDesc d = base();
+      d.A = Xb, d.a_batch = 0, d.a_rs = n_in, d.a_cs = 1;
+      d.B = q + oW1, d.b_batch = ld, d.b_rs = 1, d.b_cs = n_in;
+      d.C = H1, d.c_batch = act, d.c_rs = n_mid;
+      d.M = B, d.N = n_mid, d.K = n_in;
+      d.bias = q + ob1, d.bias_batch = ld;
+      d.epi = 1, d.layer_a = 0, d.mask_a = masks ? masks : nullptr;
+      BHMC_TRY(run_gemm(ctx, d, C));
+      // H2d = dropout(relu(dropout(H1 W2^T + b2)))
+      d = base();
+      d.A = H1, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
+      d.B = q + oW2, d.b_batch = ld, d.b_rs = 1, d.b_cs = n_mid;
+      d.C = H2d, d.c_batch = act, d.c_rs = n_mid;
+      d.M = B, d.N = n_mid, d.K = n_mid;
+      d.bias = q + ob2, d.bias_batch = ld;
+      d.epi = 2, d.layer_a = 1, d.layer_b = 2;
+      d.mask_a = masks ? masks + (size_t)C * mstride : nullptr;
+      d.mask_b = masks ? masks + 2 * (size_t)C * mstride : nullptr;
+      BHMC_TRY(run_gemm(ctx, d, C));
+      // Z = H2d W3^T + b3
+      d = base();
+      d.A = H2d, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
+      d.B = q + oW3, d.b_batch = ld, d.b_rs = 1, d.b_cs = n_mid;
+      d.C = Z, d.c_batch = (int64_t)B * n_out, d.c_rs = n_out;
+      d.M = B, d.N = n_out, d.K = n_mid;
+      d.bias = q + ob3, d.bias_batch = ld;
+      BHMC_TRY(run_gemm(ctx, d, C));
+      dim3 grid((unsigned)ceil_div(B, 256), C);
+      k_mlp_loss<<<grid, 256, 0, ctx->stream>>>(Z, B, n_out, labels + row0, stat, g ? 1 : 0);
+      ctx->launches++;
+    }
+    if (!g) return BHMC_OK;
+    GroupTimer t(ctx, KG_BWD);
+    const float ha = 0.5f * alpha;
+    // gW3 = dZ^T H2d + alpha/2 W3 ; gb3
+    GemmDesc d = base();
+    d.A = Z, d.a_batch = (int64_t)B * n_out, d.a_rs = 1, d.a_cs = n_out;  // (m=o, k=b)
+    d.B = H2d, d.b_batch = act, d.b_rs = n_mid, d.b_cs = 1;
+    d.C = g + oW3, d.c_batch = ld, d.c_rs = n_mid;
+    d.M = n_out, d.N = n_mid, d.K = B;
+    d.addsrc = q + oW3, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
+    BHMC_TRY(run_gemm(ctx, d, C));
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_out, 128), C), 128, 0, ctx->stream>>>(Z, B, n_out, (int64_t)B * n_out, q, ld, ob3, ha, g);
+    // dA2 = (dZ W3) * [H2d > 0] / keep^2
+    d = base();
+    d.A = Z, d.a_batch = (int64_t)B * n_out, d.a_rs = n_out, d.a_cs = 1;
+    d.B = q + oW3, d.b_batch = ld, d.b_rs = n_mid, d.b_cs = 1;
+    d.C = dA2, d.c_batch = act, d.c_rs = n_mid;
+    d.M = B, d.N = n_mid, d.K = n_out;
+    d.gate = H2d, d.gate_batch = act, d.gate_rs = n_mid, d.gate_scale = keep_inv * keep_inv;
+    BHMC_TRY(run_gemm(ctx, d, C));
+    // gW2 = dA2^T H1 + alpha/2 W2 ; gb2
+    d = base();
+    d.A = dA2, d.a_batch = act, d.a_rs = 1, d.a_cs = n_mid;
+    d.B = H1, d.b_batch = act, d.b_rs = n_mid, d.b_cs = 1;
+    d.C = g + oW2, d.c_batch = ld, d.c_rs = n_mid;
+    d.M = n_mid, d.N = n_mid, d.K = B;
+    d.addsrc = q + oW2, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
+    BHMC_TRY(run_gemm(ctx, d, C));
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 128), C), 128, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g);
+    // dA1 = (dA2 W2) * [H1 > 0] / keep
+    d = base();
+    d.A = dA2, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
+    d.B = q + oW2, d.b_batch = ld, d.b_rs = n_mid, d.b_cs = 1;
+    d.C = dA1, d.c_batch = act, d.c_rs = n_mid;
+    d.M = B, d.N = n_mid, d.K = n_mid;
+    d.gate = H1, d.gate_batch = act, d.gate_rs = n_mid, d.gate_scale = keep_inv;
+    BHMC_TRY(run_gemm(ctx, d, C));
+    // gW1 = dA1^T X + alpha/2 W1 ; gb1
+    d = base();
+    d.A = dA1, d.a_batch = act, d.a_rs = 1, d.a_cs = n_mid;
+    d.B = Xb, d.b_batch = 0, d.b_rs = n_in, d.b_cs = 1;
+    d.C = g + oW1, d.c_batch = ld, d.c_rs = n_in;
+    d.M = n_mid, d.N = n_in, d.K = B;
+    d.addsrc = q + oW1, d.add_batch = ld, d.add_rs = n_in, d.add_scale = ha;
+    BHMC_TRY(run_gemm(ctx, d, C));
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 128), C), 128, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g);
+    ctx->launches += 3;
+    // padding columns of g (ld > P) are never read by the update kernels beyond P; keep them finite
+    BHMC_CUDA_OK(cudaGetLastError());
+    return BHMC_OK;
+  }
+};
+
+ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int n_out, float alpha, float ratio,
+                         uint64_t seed, int64_t chain_id0) {
+  auto* m = new (std::nothrow) MlpModel();
+  if (!m) return nullptr;
+  m->ctx = ctx;
+  m->N = n_rows;
+  m->n_in = n_in;
+  m->n_mid = n_mid;
+  m->n_out = n_out;
+  m->alpha = alpha;
+  m->ratio = ratio;
+  m->seed = seed;
+  m->chain_id0 = chain_id0;
+  int64_t lens[6] = {(int64_t)n_mid * n_in, n_mid, (int64_t)n_mid * n_mid, n_mid, (int64_t)n_out * n_mid, n_out};
+  int64_t off = 0;
+  m->n_vars = 6;
+  for (int v = 0; v < 6; ++v) {
+    m->var_off[v] = off;
+    m->var_len[v] = lens[v];
+    off += lens[v];
+  }
+  m->P = off;
+  m->oW1 = m->var_off[0], m->ob1 = m->var_off[1], m->oW2 = m->var_off[2], m->ob2 = m->var_off[3];
+  m->oW3 = m->var_off[4], m->ob3 = m->var_off[5];
+  return m;
+}
+
+int mlp_model_bind(ModelBase* mb, const float* X, const int32_t* labels, int is_host) {
+  auto* m = dynamic_cast<MlpModel*>(mb);
+  BHMC_CHECK_ARG(m && X && labels, "not an mlp model / NULL data");
+  if (is_host) {
+    size_t xb = sizeof(float) * (size_t)m->N * m->n_in, yb = sizeof(int32_t) * (size_t)m->N;
+    if (!m->X_owned) BHMC_CUDA_OK(cudaMalloc(&m->X_owned, xb));
+    if (!m->y_owned) BHMC_CUDA_OK(cudaMalloc(&m->y_owned, yb));
+    BHMC_CUDA_OK(cudaMemcpyAsync(m->X_owned, X, xb, cudaMemcpyHostToDevice, m->ctx->stream));
+    BHMC_CUDA_OK(cudaMemcpyAsync(m->y_owned, labels, yb, cudaMemcpyHostToDevice, m->ctx->stream));
+    m->X = m->X_owned;
+    m->labels = m->y_owned;
+  } else {
+    m->X = X;
+    m->labels = labels;
+  }
+  return BHMC_OK;
+}
+
+int mlp_model_set_masks(ModelBase* mb, const uint8_t* masks_dev) {
+  auto* m = dynamic_cast<MlpModel*>(mb);
+  BHMC_CHECK_ARG(m, "not an mlp model");
+  m->masks = masks_dev;
+  return BHMC_OK;
+}
+
+}  // namespace bhmc

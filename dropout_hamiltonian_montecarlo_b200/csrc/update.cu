@@ -199,6 +199,32 @@ int launch_sumsq(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, c
   return BHMC_OK;
 }
 
+struct CvArr {
+  int n;
+  double cv[BHMC_MAX_VARS];
+};
+__global__ void k_prior_combine(const double* sumsq, CvArr cv, double* out, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double e = 0.0;
+  for (int v = 0; v < cv.n; ++v) e += cv.cv[v] * sumsq[(int64_t)c * cv.n + v];
+  out[c] = e;
+}
+
+// out[c] = sum_v cv[v] * |q_v[c]|^2 : the quadratic log-prior part of the Metropolis energy
+// (models/gpu/softmax.py:29-39, models/gpu/mlp.py:40-45)
+int launch_prior_energy(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, const int64_t* off,
+                        const int64_t* len, const double* cv, double* sumsq_scratch, double* out) {
+  BHMC_TRY(launch_sumsq(ctx, q, ld, C, n_vars, off, len, sumsq_scratch));
+  CvArr a;
+  a.n = n_vars;
+  for (int v = 0; v < n_vars; ++v) a.cv[v] = cv[v];
+  k_prior_combine<<<(C + 127) / 128, 128, 0, ctx->stream>>>(sumsq_scratch, a, out, C);
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Metropolis test (hmc.py:60-63,67-71) + state select + sample sink.  The decision is
 // recomputed identically by every block of a chain (a handful of double ops).

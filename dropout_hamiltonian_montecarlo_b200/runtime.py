@@ -147,6 +147,30 @@ class SoftmaxHandle(ModelHandle):
         return probs, labels
 
 
+class MlpHandle(ModelHandle):
+    def __init__(self, ctx, n_rows, n_in, n_mid, n_out, alpha, ratio=0.1, seed=0, chain_id0=0):
+        h = C.c_void_p()
+        check(ctx.L.bhmc_mlp_create(ctx.handle, n_rows, n_in, n_mid, n_out, float(alpha), float(ratio), seed, chain_id0,
+                                    C.byref(h)))
+        super().__init__(ctx, h)
+        self.N, self.n_in, self.n_mid, self.n_out = n_rows, n_in, n_mid, n_out
+
+    def bind(self, X, labels):
+        """X [N, n_in] fp32 and labels [N] int32: CUDA tensors stay bound, CPU tensors are copied by the library."""
+        assert X.dtype == torch.float32 and X.is_contiguous() and tuple(X.shape) == (self.N, self.n_in)
+        assert labels.dtype == torch.int32 and labels.is_contiguous()
+        self._keep = [X, labels]
+        check(self.ctx.L.bhmc_mlp_bind_data(self.handle, C.c_void_p(X.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                            0 if X.is_cuda else 1))
+        if not X.is_cuda:
+            self.ctx.sync()
+
+    def set_masks(self, masks):
+        """masks: uint8 CUDA tensor [3, C, B, n_mid] of keep flags, or None for Philox dropout."""
+        self._masks = masks
+        check(self.ctx.L.bhmc_mlp_set_masks(self.handle, _ptr(masks)))
+
+
 class MvnHandle(ModelHandle):
     def __init__(self, ctx, mu, cov):
         mu = np.ascontiguousarray(mu, dtype=np.float64)

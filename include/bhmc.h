@@ -88,6 +88,18 @@ int bhmc_softmax_bind_data_host(bhmc_model* m, const float* X_host, const int32_
  * cov_inv: [dim,dim] row-major (host), logdet = log det(cov). */
 int bhmc_mvn_create(bhmc_ctx* ctx, int32_t dim, const double* mu_host, const double* cov_inv_host,
                     double logdet, bhmc_model** out);
+/* Dropout MLP n_in -> n_mid -> n_mid -> n_out with chain-private weights, hamiltonian/models/gpu/mlp.py:19-82.
+ * Chain row = /l1/W [mid,in] | /l1/b | /l2/W [mid,mid] | /l2/b | /l3/W [out,mid] | /l3/b (Chainer namedparams
+ * order, W stored (out,in)).  grad = d(mean CE)/d theta + alpha/2 theta (mlp.py:63); the model scalar is the mean CE
+ * loss (mlp.py:66-78); NLP = loss - alpha/2 sum_v |theta_v|^2/dim_v (mlp.py:40-45,80-82).  Dropout keep-masks
+ * (ratio on the two hidden pre-activations and on the last hidden output, mlp.py:29-31) come from Philox keyed
+ * (seed, global chain id, evaluation counter, layer) -- a fresh mask per evaluation like Chainer -- or from
+ * bhmc_mlp_set_masks (tests).  labels are int32 class ids (mlp.py:52). */
+int bhmc_mlp_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_in, int32_t n_mid, int32_t n_out, float alpha,
+                    float dropout_ratio, uint64_t seed, int64_t chain_id0, bhmc_model** out);
+int bhmc_mlp_bind_data(bhmc_model* m, const float* X, const int32_t* labels, int32_t is_host);
+/* injected keep-masks, DEVICE uint8 [3][n_chains][batch_rows][n_mid] (NULL = back to Philox) */
+int bhmc_mlp_set_masks(bhmc_model* m, const uint8_t* masks_dev);
 /* row-sharded data (multi-GPU full-batch HMC): this model holds n_rows of n_global_rows; energies are
  * normalised by the global count (softmax.py:79 divides by the size of the whole X_train) and the
  * log-prior constant uses alpha_global (the model itself was created with alpha_global / n_ranks so that the

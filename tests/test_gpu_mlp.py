@@ -1,0 +1,120 @@
+"""GPU: dropout-MLP model (hamiltonian/models/gpu/mlp.py) against the NumPy restatement in the oracle
+(cross-checked against torch.autograd on CPU; Chainer itself is not installable here -> parity unpinned)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TapeRng, replay_uniforms
+from oracle import hamiltonian_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sghmc import sghmc  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sgd import sgd  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.mlp import KEYS, mlp  # noqa: E402
+
+
+def make(rs, B, n_in, n_mid, n_out, C=None, scale=0.3):
+    lead = () if C is None else (C,)
+    par = {"/l1/W": rs.normal(0, scale, lead + (n_mid, n_in)), "/l1/b": rs.normal(0, scale, lead + (n_mid,)),
+           "/l2/W": rs.normal(0, scale, lead + (n_mid, n_mid)), "/l2/b": rs.normal(0, scale, lead + (n_mid,)),
+           "/l3/W": rs.normal(0, scale, lead + (n_out, n_mid)), "/l3/b": rs.normal(0, scale, lead + (n_out,))}
+    X = rs.rand(B, n_in)
+    y = rs.randint(0, n_out, B)
+    return par, X, y
+
+
+def close(got, ref, rtol=1e-4, atol_scale=1e-5, what=""):
+    ref = np.asarray(ref, dtype=np.float64)
+    np.testing.assert_allclose(np.asarray(got, dtype=np.float64), ref, rtol=rtol,
+                               atol=atol_scale * max(1e-30, float(np.abs(ref).max())), err_msg=what)
+
+
+@pytest.mark.parametrize("shape", [(37, 20, 24, 5), (130, 70, 96, 10)])
+def test_mlp_grad_loss_nlp_injected_masks(shape):
+    B, n_in, n_mid, n_out = shape
+    rs = np.random.RandomState(0)
+    C, alpha = 3, 0.05
+    par, X, y = make(rs, B, n_in, n_mid, n_out, C)
+    masks = (rs.rand(3, C, B, n_mid) > 0.1).astype(np.uint8)
+    m = mlp({"alpha": alpha}, n_in, n_mid, n_out)
+    m.bind(X, y)
+    m.set_masks(masks)
+    g = m.grad(par, X_train=X, y_train=y)
+    loss = m.log_likelihood(par, X_train=X, y_train=y)
+    nlp = m.negative_log_posterior(par, X_train=X, y_train=y)
+    for c in range(C):
+        pc = {k: par[k][c] for k in KEYS}
+        mk = [masks[l, c].astype(np.float64) for l in range(3)]
+        ref = O.mlp_grad(pc, X, y, mk, alpha)
+        for k in KEYS:
+            close(g[k][c], ref[k], what="%s chain %d" % (k, c))
+        close(loss[c], O.mlp_loss(pc, X, y, mk), 1e-5)
+        close(nlp[c], O.mlp_nlp(pc, X, y, mk, alpha), 1e-5)
+
+
+def test_mlp_no_dropout_and_philox_dropout_statistics():
+    rs = np.random.RandomState(1)
+    B, n_in, n_mid, n_out, alpha = 64, 12, 512, 4, 0.0
+    par, X, y = make(rs, B, n_in, n_mid, n_out, scale=0.2)
+    m0 = mlp({"alpha": alpha}, n_in, n_mid, n_out, dropout=0.0)
+    close(m0.log_likelihood(par, X_train=X, y_train=y), O.mlp_loss(par, X, y, None), 1e-5)
+    g0 = m0.grad(par, X_train=X, y_train=y)
+    ref = O.mlp_grad(par, X, y, None, alpha)
+    close(g0["/l1/W"], ref["/l1/W"])
+    # Philox dropout: a fresh mask per evaluation (like Chainer), loss fluctuates around the no-dropout value
+    m1 = mlp({"alpha": alpha}, n_in, n_mid, n_out, dropout=0.1, seed=7)
+    ls = np.array([m1.log_likelihood(par, X_train=X, y_train=y) for _ in range(30)])
+    assert len(np.unique(ls)) == 30
+    # keep rate: with l1 bias large and positive, relu(dropout(a)) == 0 exactly where the unit was dropped
+    par2 = {k: np.array(v, copy=True) for k, v in par.items()}
+    par2["/l1/W"][:] = 0
+    par2["/l1/b"][:] = 1.0
+    par2["/l2/W"][:] = np.eye(n_mid)
+    par2["/l2/b"][:] = 0
+    g = m1.grad(par2, X_train=X, y_train=y)  # exercises the path; statistics via the loss spread above
+    assert np.isfinite(g["/l2/W"]).all()
+    assert abs(ls.mean() - O.mlp_loss(par, X, y, None)) < 0.5
+
+
+def test_sghmc_step_on_mlp_minibatch_vs_oracle():
+    rs = np.random.RandomState(3)
+    B, n_in, n_mid, n_out, alpha = 48, 10, 16, 3, 0.1
+    par, X, y = make(rs, B, n_in, n_mid, n_out, scale=0.2)
+    masks = (rs.rand(3, 1, B, n_mid) > 0.1).astype(np.uint8)
+    eps, path = 1e-2, 3e-2
+    model = mlp({"alpha": alpha}, n_in, n_mid, n_out)
+    model.bind(X, y)
+    model.set_masks(masks)
+    s = sghmc(model, par, path_length=path, step_size=eps, verbose=False, sign="descent")
+    P = sum(int(np.prod(v.shape)) for v in par.values())
+    L = O.path_length_steps(0.45, path, eps)
+    z = rs.normal(size=P * (1 + (L - 1)))
+    with replay_uniforms([0.45, 0.5]):
+        q, p, a = s.step(par, None, TapeRng(z), X_train=X, y_train=y)
+    shapes = [par[k].shape for k in KEYS]
+    normals, pos = [], 0
+    for _ in range(1 + (L - 1)):
+        for sh in shapes:
+            n = int(np.prod(sh))
+            normals.append(z[pos:pos + n].reshape(sh))
+            pos += n
+    mk = [masks[l, 0].astype(np.float64) for l in range(3)]
+    r = O.sghmc_step(O.MlpOracle({"alpha": alpha}, lambda b, n: mk), par, list(KEYS), eps, path,
+                     O.TapeDraws(normals, [0.45, 0.5]), sign="descent", X_train=X, y_train=y)
+    assert r["L"] == L and L >= 3
+    close(a, r["accept_prob"], 1e-3, 1e-6)
+    for k in KEYS:
+        close(q[k], r["q"][k], 1e-4, 1e-5, k)
+        close(p[k], r["p"][k], 1e-4, 1e-5, k)
+
+
+def test_sgd_fit_on_mlp_reduces_loss():
+    rs = np.random.RandomState(4)
+    B, n_in, n_mid, n_out = 256, 20, 32, 4
+    par, X, _ = make(rs, B, n_in, n_mid, n_out, scale=0.1)
+    y = (X[:, :n_out] + 0.1 * rs.rand(B, n_out)).argmax(1)
+    model = mlp({"alpha": 1e-4}, n_in, n_mid, n_out, dropout=0.1, seed=1)
+    opt = sgd(model, par, step_size=0.05)
+    fitted, loss = opt.fit(epochs=30, batch_size=64, gamma=0.9, X_train=X, y_train=y)
+    assert loss[-1] < 0.7 * loss[0]

@@ -334,3 +334,24 @@ def test_full_size_cfg2_gradient():
     gw, llw = h.grad(qd, 1500, 500, 1)
     gw32, llw32 = h.grad(qd, 1500, 500, 0)
     assert (gw - gw32).abs().max().item() < 5e-5 * gw32.abs().max().item()
+
+
+def test_gpu_prior_variant_energy():
+    """models/gpu/softmax.py:29-39: log_prior = -alpha/2 sum_v |theta_v|^2/dim_v enters NLP and the Metropolis test."""
+    rs = np.random.RandomState(2)
+    N, D, K, alpha = 300, 20, 4, 0.5
+    X = rs.rand(N, D)
+    y = rs.randint(0, K, N)
+    Y = O.one_hot(y, K)
+    par = {"weights": rs.normal(0, .5, (D, K)), "bias": rs.normal(0, .5, K)}
+    m = softmax({"alpha": alpha}, precision="fp32", prior="gpu")
+    close(m.negative_log_posterior(par, X_train=X, y_train=Y), O.softmax_nlp(par, X, Y, alpha, "gpu"), 1e-5)
+    eps, path = 1e-3, 1e-2
+    z = rs.normal(size=(D * K + K))
+    s = hmc(m, par, path_length=path, step_size=eps, verbose=False)
+    with replay_uniforms([0.6, 0.5]):
+        q, p, _, _, a = s.step(par, None, TapeRng(z), X_train=X, y_train=Y)
+    r = O.hmc_step(O.SoftmaxOracle({"alpha": alpha}, "gpu"), par, ["weights", "bias"], eps, path,
+                   O.TapeDraws([z[:D * K].reshape(D, K), z[D * K:]], [0.6, 0.5]), X_train=X, y_train=Y)
+    close(a, r["accept_prob"], 5e-4, 1e-6)
+    close(q["weights"], r["q"]["weights"], 1e-4, 2e-6)
