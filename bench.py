@@ -293,6 +293,36 @@ def run_ours(args, wl):
         e2e = {"value": n_e2e / dt, "unit": "grad-evals/s", "h2d_bytes_per_step": int(N * D * 4 + N * 4),
                "d2h_bytes_per_step": int(d2h), "api": "hmc.sample(niter=1, X_train=<pinned host>, y_train=<pinned host>)"}
 
+    # ---- ESS / s (second half of BASELINE's metric): a short run at settings where proposals are accepted
+    # (eps=3e-7, path_length=3e-5 -> E[L]=100, accept ~0.5 at N=60000), Geyer IPS estimator
+    ess_info = None
+    if not args.no_ess:
+        from dropout_hamiltonian_montecarlo_b200.ess import ess as ess_fn
+        s2 = SamplerHandle(ctx, h, 0, C, seed=4321, chain_id0=rank * C, precision=PREC[prec], shared_path=shared)
+        s2.set_q(np.zeros((C, h.P), np.float32))
+        e_eps, e_path = 3e-7, 3e-5
+        s2.hmc_run(args.ess_burnin, e_eps, e_path, step0=0, keep_samples=False)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        oe = s2.hmc_run(args.ess_steps, e_eps, e_path, step0=args.ess_burnin, keep_samples=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        t_ess = ev0.elapsed_time(ev1) * 1e-3
+        r = ess_fn(oe["samples"].cpu().numpy(), max_params=48)
+        st = torch.tensor([t_ess, r["min"], r["median"], float(oe["accept_prob"].mean().item())], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = st.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = st.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            st = torch.stack([mx[0], sm[1], sm[2], sm[3] / world])
+        ess_info = {"ess_min_per_s": float(st[1] / st[0]), "ess_median_per_s": float(st[2] / st[0]),
+                    "steps": args.ess_steps, "burnin": args.ess_burnin, "step_size": e_eps, "path_length": e_path,
+                    "mean_accept_prob": float(st[3]), "estimator": "Geyer initial positive sequence, summed over chains, "
+                    "48 random parameters", "seconds": float(st[0])}
+        s2.close()
+
     if rank == 0:
         peak_tf, peak_bw, src = peaks()
         flops_fwd = 2.0 * N * D * K * C  # algorithmic flops of one forward launch (all chains)
@@ -321,6 +351,8 @@ def run_ours(args, wl):
                          "group_ms": {"fwd": t_fwd, "bwd": t_bwd, "prep": t_prep, "update": t_upd, "step_total": ms}},
             "gpu_launches": int(launches), "clocks": clk,
         }
+        if ess_info is not None:
+            line["ess"] = ess_info
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
@@ -340,6 +372,9 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--path-mode", default="per_chain", choices=["per_chain", "shared"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ess", action="store_true")
+    ap.add_argument("--ess-steps", type=int, default=40)
+    ap.add_argument("--ess-burnin", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -87,6 +87,7 @@ _PROTOS = {
                                      C.c_uint32, C.c_uint32]),
     "bhmc_philox_uniform_host": (C.c_double, [C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32]),
     "bhmc_philox4x32_host": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "bhmc_bench_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_double)]),
     "bhmc_sampler_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SamplerConfig), C.POINTER(C.c_void_p)]),
     "bhmc_sampler_destroy": (C.c_int, [C.c_void_p]),
     "bhmc_sampler_set_grad_hook": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -891,3 +891,63 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
 }
 
 }  // extern "C"
+
+extern "C" int bhmc_bench_update(bhmc_ctx* ctx, int32_t which, int32_t C, int64_t P, int32_t reps, double* ms_per_launch) {
+  BHMC_CHECK_ARG(ctx && ms_per_launch && C > 0 && P > 0 && reps > 0 && which >= 0 && which <= 4, "bad argument");
+  BHMC_CUDA_OK(cudaSetDevice(ctx->device));
+  const int64_t ld = round_up(P, 4);
+  const size_t row = (size_t)C * ld;
+  float* buf = nullptr;
+  double* scal = nullptr;
+  int32_t* L = nullptr;
+  BHMC_CUDA_OK(cudaMalloc(&buf, sizeof(float) * row * 6));
+  BHMC_CUDA_OK(cudaMalloc(&scal, sizeof(double) * C * 8));
+  BHMC_CUDA_OK(cudaMalloc(&L, sizeof(int32_t) * C));
+  BHMC_CUDA_OK(cudaMemsetAsync(buf, 0, sizeof(float) * row * 6, ctx->stream));
+  BHMC_CUDA_OK(cudaMemsetAsync(scal, 0, sizeof(double) * C * 8, ctx->stream));
+  std::vector<int32_t> Lh(C, 1000000);
+  BHMC_CUDA_OK(cudaMemcpyAsync(L, Lh.data(), sizeof(int32_t) * C, cudaMemcpyHostToDevice, ctx->stream));
+  float *q = buf, *p = buf + row, *g = buf + 2 * row, *qn = buf + 3 * row, *pn = buf + 4 * row, *smp = buf + 5 * row;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int rc = BHMC_OK;
+  for (int r = -3; r < reps && rc == BHMC_OK; ++r) {  // 3 warm-up launches
+    if (r == 0) cudaEventRecord(e0, ctx->stream);
+    if (which == 0 || which == 1) {
+      UpdateArgs u{};
+      u.q = q, u.p = p, u.g = g, u.ld = ld, u.P = P, u.C = C, u.L = L, u.eps = 1e-3f;
+      u.post_off = 0, u.post_len = P, u.it_post = 0, u.pre_off = 0, u.pre_len = P, u.it_pre = 0;
+      u.f_post = which ? 0.999f : 1.f, u.a_post = 1e-3f, u.n_post = which ? 2e-3f : 0.f, u.a_pre = which ? 0.f : 5e-4f;
+      u.seed = 1, u.stream_lo = (uint32_t)r, u.stream_hi = TAG_NOISE;
+      rc = launch_hmc_update(ctx, u);
+    } else if (which == 2) {
+      SgldArgs a{};
+      a.q = q, a.p = p, a.g = g, a.ld = ld, a.P = P, a.C = C, a.eps = 1e-5f, a.seed = 1, a.stream_lo = (uint32_t)r, a.stream_hi = TAG_NOISE;
+      rc = launch_sgld_update(ctx, a);
+    } else if (which == 3) {
+      AcceptArgs a{};
+      a.q = q, a.q_new = qn, a.p_out = p, a.p_new = pn, a.ld = ld, a.P = P, a.C = C, a.p_sign = -1.f;
+      a.stat_cur = scal, a.stat_new = scal + C, a.ea = 0.0, a.eb = 0.0, a.kin0 = scal + 2 * C, a.kin1 = scal + 3 * C;
+      a.u = scal + 4 * C;  // u = 0 < A = 1 -> every chain accepts
+      a.sample = smp;
+      rc = launch_accept(ctx, a);
+    } else {
+      BeginArgs b{};
+      b.q = q, b.q_new = qn, b.p0 = p, b.p_new = pn, b.ld = ld, b.P = P, b.C = C, b.seed = 1, b.stream_lo = (uint32_t)r;
+      b.stream_hi = TAG_MOMENTUM, b.kin0 = scal + 2 * C;
+      rc = launch_hmc_begin(ctx, b);
+    }
+  }
+  cudaEventRecord(e1, ctx->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_per_launch = (double)ms / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(scal);
+  cudaFree(L);
+  return rc;
+}

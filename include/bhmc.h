@@ -210,6 +210,13 @@ typedef struct bhmc_sg_run {
 /* SGLD (kind SGLD) / SGD (kind SGD) epochs over sequential minibatches */
 int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run);
 
+/* ---- measurement helper: time one fused update kernel in isolation (CUDA events on the context stream).
+ * which: 0 = HMC kick+drift (20 B/param), 1 = SGHMC friction+Philox noise+drift (20 B/param),
+ *        2 = SGLD with Philox noise (16 B/param), 3 = accept/select + sample sink (20 B/param),
+ *        4 = momentum draw (Philox) + proposal copy + kinetic energy (16 B/param).
+ * Allocates its own [n_chains, P] buffers; returns the mean milliseconds per launch over reps. */
+int bhmc_bench_update(bhmc_ctx* ctx, int32_t which, int32_t n_chains, int64_t P, int32_t reps, double* ms_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -355,3 +355,46 @@ def test_gpu_prior_variant_energy():
                    O.TapeDraws([z[:D * K].reshape(D, K), z[D * K:]], [0.6, 0.5]), X_train=X, y_train=Y)
     close(a, r["accept_prob"], 5e-4, 1e-6)
     close(q["weights"], r["q"]["weights"], 1e-4, 2e-6)
+
+
+def test_posterior_statistics_softmax_independent_rng():
+    """North-star criterion 2: under INDEPENDENT random numbers (NumPy streams for the oracle, in-kernel Philox
+    for the CUDA path) the two samplers produce the same distribution.  Because of the reference's energy
+    mismatch (sum-gradient dynamics, mean-NLP acceptance) chains mix slowly, so the comparison is made on the
+    ensemble distribution after T transitions from a common start: 96 oracle chains vs 4096 CUDA chains.
+    Tolerances: ensemble means within 4.5 standard errors of the oracle ensemble, ensemble standard deviations
+    within 35 %, mean acceptance within 0.05, accuracy of the ensemble-mean predictor within 0.05."""
+    rs = np.random.RandomState(0)
+    N, D, K, alpha, eps, path, T = 60, 4, 3, 2.0, 1e-2, 0.2, 30
+    X = rs.rand(N, D)
+    Wt = rs.normal(0, 2, (D, K))
+    y = np.argmax(X @ Wt + rs.gumbel(size=(N, K)), 1)
+    Y = O.one_hot(y, K)
+    start = {"weights": np.zeros((D, K)), "bias": np.zeros(K)}
+    n_or = 96
+    finals, accs = [], []
+    for c in range(n_or):
+        d = O.StreamDraws(np.random.RandomState(1000 + c), np.random.RandomState(5000 + c))
+        post, _, info = O.hmc_sample(O.SoftmaxOracle({"alpha": alpha}), start, eps, path, T, 0, d, X_train=X, y_train=Y)
+        finals.append(np.concatenate([post["weights"][-1].ravel(), post["bias"][-1]]))
+        accs.append(info["accept_prob"].mean())
+    finals = np.array(finals)
+    s = hmc(softmax({"alpha": alpha}, precision="bf16x3"), start, path_length=path, step_size=eps, verbose=False,
+            n_chains=4096, seed=17)
+    post, loss, _, _ = s.sample(niter=T, burnin=0, X_train=X, y_train=Y)
+    got = np.concatenate([post["weights"][-1].reshape(4096, -1), post["bias"][-1]], axis=1)
+    se = finals.std(0, ddof=1) / np.sqrt(n_or)
+    zscore = np.abs(got.mean(0) - finals.mean(0)) / se
+    assert zscore.max() < 4.5, zscore
+    ratio = got.std(0) / finals.std(0, ddof=1)
+    assert np.all((ratio > 0.65) & (ratio < 1.35)), ratio
+    assert abs(s.last_run["accept_prob"].mean() - np.mean(accs)) < 0.05
+    def acc_of(v):
+        W, b = v[:D * K].reshape(D, K), v[D * K:]
+        return float(((X @ W + b).argmax(1) == y).mean())
+    assert abs(acc_of(got.mean(0)) - acc_of(finals.mean(0))) <= 0.05
+    # and the library's own predict() agrees with that accuracy (softmax.py:82-89)
+    m = softmax({"alpha": alpha}, precision="fp32")
+    pm = got.mean(0)
+    pred = m.predict({"weights": pm[:D * K].reshape(D, K), "bias": pm[D * K:]}, X)
+    assert abs(float((pred == y).mean()) - acc_of(pm)) < 1e-9

@@ -1,0 +1,96 @@
+"""Secondary workloads (not the driver's headline): BASELINE configs 3 and 4 and the fused-update roofline.
+
+    python tools/bench_extra.py sgld   [--chains 128] [--epochs 2]      cfg3: SGLD softmax, minibatch 500
+    python tools/bench_extra.py mlp    [--chains 16]  [--steps 20]      cfg4: SGHMC MLP 784-512-512-10, minibatch 500
+    python tools/bench_extra.py update [--chains 64]                    fused update kernels vs HBM peak (cfg4-sized state)
+Prints one JSON line each."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from bench import peaks, synth
+from dropout_hamiltonian_montecarlo_b200._lib import KIND, PREC
+from dropout_hamiltonian_montecarlo_b200.runtime import MlpHandle, SamplerHandle, SoftmaxHandle, default_context
+
+ap = argparse.ArgumentParser()
+ap.add_argument("what", choices=["sgld", "mlp", "update"])
+ap.add_argument("--chains", type=int, default=0)
+ap.add_argument("--epochs", type=int, default=2)
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--precision", default="bf16x3")
+a = ap.parse_args()
+ctx = default_context()
+dev = ctx.device
+peak_tf, peak_bw, src = peaks()
+N, D, K, B = 60000, 784, 10, 500
+X, y = synth(N, D, K, 0, device=dev)
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3, out
+
+
+if a.what == "sgld":
+    C = a.chains or 128
+    h = SoftmaxHandle(ctx, N, D, K, 0.01)
+    h.bind(X, y, 1 | (1 << PREC[a.precision]))
+    s = SamplerHandle(ctx, h, KIND["sgld"], C, seed=1, precision=PREC[a.precision])
+    s.set_q(np.zeros((C, h.P), np.float32))
+    s.sg_run(0, 1, B, 1e-5, n_rows=N)  # warm-up epoch
+    l0 = ctx.launches
+    dt, out = timed(lambda: s.sg_run(a.epochs, 0, B, 1e-5, n_rows=N))
+    nb = N // B
+    print(json.dumps({"workload": "cfg3 SGLD softmax 60000x784x10, minibatch 500, %d chains/GPU" % C, "precision": a.precision,
+                      "grad_evals_per_s": out["n_grad_evals"] / dt, "us_per_minibatch_step": 1e6 * dt / (a.epochs * nb),
+                      "launches_per_step": (ctx.launches - l0) / (a.epochs * nb),
+                      "algorithmic_tflops": out["n_grad_evals"] * 4.0 * B * D * K / dt / 1e12}))
+elif a.what == "mlp":
+    C = a.chains or 16
+    n_mid = 512
+    h = MlpHandle(ctx, N, D, n_mid, K, 0.01, 0.1, seed=3)
+    h.bind(X, y)
+    s = SamplerHandle(ctx, h, KIND["sghmc"], C, seed=1, precision=0, sweep=[(0, h.P)], shared_path=True, sghmc_descent=True)
+    rs = np.random.RandomState(0)
+    s.set_q(rs.normal(0, 0.05, (C, h.P)).astype(np.float32))
+    eps, path = 1e-3, 5e-3  # E[L] = 5
+    s.hmc_run(2, eps, path, row0=0, nrows=B, keep_samples=False)
+    n_grad = 0
+
+    def run():
+        global n_grad
+        for i in range(a.steps):
+            o = s.hmc_run(1, eps, path, row0=(i % (N // B)) * B, nrows=B, step0=10 + i, keep_samples=False)
+            n_grad += o["n_grad_evals"]
+    dt, _ = timed(run)
+    flops = 6.0 * B * (D * n_mid + n_mid * n_mid + n_mid * K) - 2.0 * B * D * n_mid
+    print(json.dumps({"workload": "cfg4 SGHMC MLP 784-512-512-10 dropout 0.1, minibatch 500, %d chains/GPU, joint sweep" % C,
+                      "precision": "fp32 (CUDA cores)", "grad_evals_per_s": n_grad / dt,
+                      "algorithmic_tflops": n_grad * flops / dt / 1e12, "ms_per_sghmc_step": 1e3 * dt / a.steps}))
+else:
+    import ctypes as Ct
+    from dropout_hamiltonian_montecarlo_b200._lib import check
+    C = a.chains or 64
+    out = {"peak_hbm_gbs": peak_bw, "peak_source": src, "kernels": {}}
+    names = {0: ("hmc kick+drift", 20), 1: ("sghmc friction+philox+drift", 20), 2: ("sgld philox", 16),
+             3: ("accept/select+sample sink", 20), 4: ("momentum draw philox", 16)}
+    for label, P in (("cfg4 MLP P=669706", 669706), ("cfg2 softmax P=7850", 7850)):
+        for which, (nm, bpp) in names.items():
+            ms = Ct.c_double()
+            check(ctx.L.bhmc_bench_update(ctx.handle, which, C, P, 50, Ct.byref(ms)))
+            gbs = bpp * C * P / (ms.value * 1e-3) / 1e9
+            out["kernels"]["%s | %s" % (label, nm)] = {"ms": ms.value, "bytes_per_param": bpp, "achieved_gbs": gbs,
+                                                        "frac_of_hbm_peak": gbs / peak_bw}
+    out["chains"] = C
+    print(json.dumps(out))
