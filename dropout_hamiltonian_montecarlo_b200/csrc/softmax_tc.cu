@@ -192,6 +192,8 @@ struct TcParams {
   int m_tiles, n_tiles, n_split;  // work items = n_split * m_tiles * n_tiles
   int k_chunks;                   // BK-chunks of the contraction dimension (total)
   int chunks_per_split;
+  int sub_chunks;                 // accumulation chain length in BK-chunks: the TMEM accumulator is drained into
+                                  // fp32 registers (round-to-nearest adds) every sub_chunks chunks (backward only)
   int BN;                         // UMMA N (multiple of 16, <= 256)
   int stages;
   int split3;                     // 1: hi/lo operands, 3 MMAs per product
@@ -320,15 +322,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = wi0; w < num_work; w += wi_step, ++it) {
+      for (int w = wi0; w < num_work; w += wi_step) {
         BHMC_DECODE_WORK(w)
         int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
+        for (int kb = k_begin; kb < k_end; kb += p.sub_chunks, ++it) {
+        const int ke = min(k_end, kb + p.sub_chunks);
         int buf = it & 1;
         uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
-        for (int k = k_begin; k < k_end; ++k) {
+        for (int k = kb; k < ke; ++k) {
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tcgen05_fence_after();
           uint32_t sa = smem_base + stage * stage_bytes;
@@ -339,7 +343,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #pragma unroll
           for (int ks = 0; ks < BK / UMMA_K; ++ks) {
             uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle span
-            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (k > k_begin || ks > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (k > kb || ks > 0) ? 1u : 0u);
             if (p.split3) {
               umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
               umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
@@ -351,7 +355,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           else umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == p.stages) stage = 0, phase ^= 1u;
         }
-        umma_commit(smem_u32(&bar_tfull[buf]));  // accumulator complete
+        umma_commit(smem_u32(&bar_tfull[buf]));  // accumulator (of this sub-slab) complete
+        }
       }
     }
   } else if (warp >= 4) {
@@ -361,11 +366,58 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     constexpr int PARTS = EW / 4;
     const int t = ew * 32 + lane;        // accumulator row handled by this thread
     int it = 0;
-    for (int w = wi0; w < num_work; w += wi_step, ++it) {
+    for (int w = wi0; w < num_work; w += wi_step) {
       BHMC_DECODE_WORK(w)
       const bool tile_ok = mt < p.m_tiles && nt < p.n_tiles;  // odd tile counts leave a phantom tile in the last pair
-      int buf = it & 1;
-      uint32_t use = (uint32_t)(it >> 1);
+      if constexpr (MODE == MODE_BWD) {
+        // backward: drain the accumulator every sub_chunks chunks into fp32 registers (short tensor-core
+        // accumulation chains), store the sum once per work item (coalesced per row) to the split-K partials
+        constexpr int MAXCH = 3;  // 16-column chunks per thread: BN <= 192 with 16 epilogue warps
+        float acc[MAXCH][16];
+#pragma unroll
+        for (int i = 0; i < MAXCH; ++i)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+        const int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
+        for (int kb = k_begin; kb < k_end; kb += p.sub_chunks, ++it) {
+          const int buf = it & 1;
+          const uint32_t use = (uint32_t)(it >> 1);
+          mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+          tcgen05_fence_after();
+          const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+#pragma unroll
+          for (int i = 0; i < MAXCH; ++i) {
+            const int j0 = (part + i * PARTS) * 16;
+            if (j0 < p.BN) {  // warp-uniform
+              uint32_t raw[16];
+              tmem_ld<16>(tacc + (uint32_t)j0, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[i][j] += __uint_as_float(raw[j]);
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive(smem_u32(&bar_tempty[buf]));
+        }
+        if (tile_ok) {
+          const int64_t rows = (int64_t)p.m_tiles * BM, cols = (int64_t)p.n_tiles * p.BN;
+          float* dst = p.part + ((int64_t)s * rows + (int64_t)mt * BM + t) * cols + (int64_t)nt * p.BN;
+#pragma unroll
+          for (int i = 0; i < MAXCH; ++i) {
+            const int j0 = (part + i * PARTS) * 16;
+            if (j0 < p.BN) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                *reinterpret_cast<float4*>(dst + j0 + 4 * v) =
+                    make_float4(acc[i][4 * v], acc[i][4 * v + 1], acc[i][4 * v + 2], acc[i][4 * v + 3]);
+            }
+          }
+        }
+        continue;
+      }
+      // forward: one accumulation chain per work item
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
@@ -433,21 +485,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
           if (lane == 0) atomicAdd(p.loglik + c, (double)ll);
         }
-      } else {
-        // backward: dump the fp32 accumulator tile to the split-K partial buffer (coalesced per row)
-        const int64_t rows = (int64_t)p.m_tiles * BM, cols = (int64_t)p.n_tiles * p.BN;
-        float* dst = p.part + ((int64_t)s * rows + (int64_t)mt * BM + t) * cols + (int64_t)nt * p.BN;
-        for (int j0 = part * 16; j0 < p.BN; j0 += 16 * PARTS) {
-          uint32_t raw[16];
-          tmem_ld<16>(tacc + (uint32_t)j0, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int v = 0; v < 4; ++v)
-            *reinterpret_cast<uint4*>(dst + j0 + 4 * v) = make_uint4(raw[4 * v], raw[4 * v + 1], raw[4 * v + 2], raw[4 * v + 3]);
-        }
       }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[buf]));
+      ++it;
     }
   }
   // ---- teardown ----
@@ -597,7 +638,7 @@ static int pick_cpt(int KP, int C) {
   while ((unit * KP) % 16) ++unit;
   int best = unit;
   double best_cost = 1e30;
-  for (int cpt = unit; cpt * KP <= 256; cpt += unit) {
+  for (int cpt = unit; cpt * KP <= 192; cpt += unit) {  // 192: the backward epilogue keeps BN/64 chunks in registers
     int tiles = (C + cpt - 1) / cpt;
     // padded columns + a small per-tile overhead that favours wide tiles
     double cost = (double)tiles * cpt * KP * (1.0 + 24.0 / (cpt * KP));
@@ -790,6 +831,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.n_split = 1;
   p.k_chunks = (int)ceil_div(D, BK);
   p.chunks_per_split = p.k_chunks;
+  p.sub_chunks = p.k_chunks;  // forward: K = D is short (13 chunks at D=784), one accumulation chain
   p.BN = BN;
   p.stages = stages;
   p.split3 = split3 ? 1 : 0;
@@ -838,6 +880,13 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   want = std::min(want, std::max(1, b.k_chunks / 4));  // keep >= 4 chunks per slab
   b.chunks_per_split = (int)ceil_div(b.k_chunks, want);
   b.n_split = (int)ceil_div(b.k_chunks, b.chunks_per_split);
+  // <= 192 MMAs per tensor-core accumulation chain, then round-to-nearest fp32 adds (BHMC_SUB_CHUNKS overrides)
+  static int sub_env = -1;
+  if (sub_env < 0) {
+    const char* e = getenv("BHMC_SUB_CHUNKS");
+    sub_env = e ? std::max(1, atoi(e)) : 16;
+  }
+  b.sub_chunks = sub_env;
   b.BN = BN;
   b.stages = stages;
   b.split3 = split3 ? 1 : 0;
@@ -862,7 +911,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   }
   {
     GroupTimer t(ctx, KG_BWD);
-    BHMC_TRY((launch_gemm<MODE_BWD, 1>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
+    BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
     dim3 grid((unsigned)ceil_div(ld, 256), C);
     k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, K, KP, P, q, g, ld, alpha);
     ctx->launches++;

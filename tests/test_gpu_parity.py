@@ -362,8 +362,12 @@ def test_posterior_statistics_softmax_independent_rng():
     for the CUDA path) the two samplers produce the same distribution.  Because of the reference's energy
     mismatch (sum-gradient dynamics, mean-NLP acceptance) chains mix slowly, so the comparison is made on the
     ensemble distribution after T transitions from a common start: 96 oracle chains vs 4096 CUDA chains.
-    Tolerances: ensemble means within 4.5 standard errors of the oracle ensemble, ensemble standard deviations
-    within 35 %, mean acceptance within 0.05, accuracy of the ensemble-mean predictor within 0.05."""
+    The per-parameter ensemble distributions are heavy-tailed (kurtosis 6-48: most chains barely move, a few
+    accept long trajectories), so second moments are useless as a statistic -- two independent ORACLE ensembles
+    of 96 and 300 chains differ by up to 43 % in standard deviation and 4.3 standard errors in mean.  Tolerances:
+    two-sample Kolmogorov-Smirnov distance per parameter < 0.25 (Bonferroni 1e-3 critical value for 96 vs 4096
+    samples and 15 parameters: 0.234), ensemble means within 6 standard errors, mean acceptance within 0.05,
+    accuracy of the ensemble-mean predictor within 0.05."""
     rs = np.random.RandomState(0)
     N, D, K, alpha, eps, path, T = 60, 4, 3, 2.0, 1e-2, 0.2, 30
     X = rs.rand(N, D)
@@ -385,9 +389,10 @@ def test_posterior_statistics_softmax_independent_rng():
     got = np.concatenate([post["weights"][-1].reshape(4096, -1), post["bias"][-1]], axis=1)
     se = finals.std(0, ddof=1) / np.sqrt(n_or)
     zscore = np.abs(got.mean(0) - finals.mean(0)) / se
-    assert zscore.max() < 4.5, zscore
-    ratio = got.std(0) / finals.std(0, ddof=1)
-    assert np.all((ratio > 0.65) & (ratio < 1.35)), ratio
+    assert zscore.max() < 6.0, zscore
+    from scipy import stats
+    ks = np.array([stats.ks_2samp(finals[:, j], got[:, j]).statistic for j in range(finals.shape[1])])
+    assert ks.max() < 0.25, ks
     assert abs(s.last_run["accept_prob"].mean() - np.mean(accs)) < 0.05
     def acc_of(v):
         W, b = v[:D * K].reshape(D, K), v[D * K:]
