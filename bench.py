@@ -114,7 +114,7 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_rate(wl, seconds_target=15.0, max_steps=3):
+def cpu_reference_rate(wl, seconds_target=12.0, max_steps=20):
     """Oracle port of hmc.step (hamiltonian/inference/cpu/hmc.py:39-64 + models/cpu/softmax.py) on the
     host cores: one chain, fp64, same data shape; bounded sample (path length pinned to L=11 per step)."""
     from oracle import hamiltonian_oracle as O

@@ -213,6 +213,7 @@ struct TcParams {
   __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
   double* loglik;
   int write_dm;
+  int debug;                      // BHMC_DEBUG_EPI (measurement only): 1 = skip the forward epilogue, 2 = skip its atomics
   // backward epilogue
   float* part;                    // [n_split, m_tiles*128, n_tiles*BN]
 };
@@ -230,7 +231,7 @@ __device__ __forceinline__ float lg2_approx(float x) {
 
 // EW = number of epilogue warps (multiple of 4).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the
 // EW/4 warps that share a lane quarter split the tile's chains (forward) / column chunks (backward).
-template <int MODE, int KP, int EW>
+template <int MODE, int KP, int EW, bool EXACT>
 __global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
@@ -290,6 +291,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         for (int k = k_begin; k < k_end; ++k) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           uint32_t full = smem_u32(&bar_full[stage]);
+          if (p.debug >= 4) {  // measurement: no TMA traffic at all
+            mbar_arrive(full);
+            if (++stage == p.stages) stage = 0, phase ^= 1u;
+            continue;
+          }
           mbar_expect_tx(full, (uint32_t)stage_bytes);
           uint32_t sa = smem_base + stage * stage_bytes;  // [A_hi | A_lo | B_hi | B_lo]
           uint32_t sb = sa + nmat * a_bytes;
@@ -341,7 +347,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           uint64_t b_hi = make_smem_desc(sa + (p.split3 ? 2 : 1) * a_bytes);
           uint64_t b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          for (int ks = 0; ks < ((p.debug == 3 || p.debug == 5 || p.debug == 7) ? 0 : BK / UMMA_K); ++ks) {
             uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle span
             umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (k > kb || ks > 0) ? 1u : 0u);
             if (p.split3) {
@@ -421,14 +427,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      if (!tile_ok) {
+      if (!tile_ok || p.debug == 1 || p.debug == 6 || p.debug == 7) {
         // nothing to store; only the barrier protocol below
       } else if constexpr (MODE == MODE_FWD) {
         const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
         const int64_t r = (int64_t)mt * BM + t;  // row inside the window
         const bool valid = r < p.nrows;
         const int y = valid ? p.labels[r] : -1;
-        const int K = p.K;
+        const int K = EXACT ? KP : p.K;  // EXACT: no padded classes, every class loop is branch-free
         for (int cc = part; cc < p.cpt; cc += PARTS) {
           const int c = nt * p.cpt + cc;
           if (c >= p.C) break;  // warp-uniform
@@ -437,22 +443,31 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
           float bv[KP];
 #pragma unroll
-          for (int k = 0; k < KP; ++k) bv[k] = (k < K) ? __ldg(bias + k) : 0.f;
+          for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
           tmem_ld_wait();
           float z[KP];
           float m = -INFINITY, zy = 0.f;
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
-            float v = fmaxf(fminf(__uint_as_float(raw[k]) + bv[k], CLIP_HI), CLIP_LO);  // softmax.py:40-41
-            if (k >= K) v = -INFINITY;                                                   // padded classes
+            // softmax.py:40-41 clips to [-708.4, 36.04].  The lower clip only matters for the label's logit
+            // (exp(z - max) underflows to 0 in fp32 either way), so it is applied to zy alone below.
+            float v = fminf(__uint_as_float(raw[k]) + bv[k], CLIP_HI);
+            if (!EXACT && k >= K) v = -INFINITY;  // padded classes
             z[k] = v;
             m = fmaxf(m, v);
             zy = (k == y) ? v : zy;
           }
+          zy = fmaxf(zy, CLIP_LO);
+          if (m < CLIP_LO) {  // every logit below the lower clip (diverged chain): take the slow, literal path
+            m = CLIP_LO;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+              if (EXACT || k < K) z[k] = CLIP_LO;
+          }
           float ssum = 0.f;
 #pragma unroll
           for (int k = 0; k < KP; ++k) {
-            z[k] = ex2_approx((z[k] - m) * L2E);  // exp(z - max); exp(-inf) = 0 for padded classes
+            z[k] = ex2_approx((z[k] - m) * L2E);  // exp(clip(z) - max); 0 for padded classes
             ssum += z[k];
           }
           const float inv = __fdividef(1.0f, ssum);
@@ -463,7 +478,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
 #pragma unroll
             for (int k = 0; k < KP; ++k) {
-              if (k < K) {
+              if (EXACT || k < K) {
                 float d = valid ? fmaf(z[k], inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
                 __nv_bfloat16 h = __float2bfloat16_rn(d);
                 *dh = h;
@@ -483,7 +498,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
-          if (lane == 0) atomicAdd(p.loglik + c, (double)ll);
+          if (lane == 0 && p.debug != 2) atomicAdd(p.loglik + c, (double)ll);
         }
       }
       tcgen05_fence_before();
@@ -718,19 +733,19 @@ static int epilogue_warps() {
   if (!ew) {
     const char* e = getenv("BHMC_EPI_WARPS");
     ew = e ? atoi(e) : 16;
-    if (ew != 8 && ew != 16) ew = 16;
+    if (ew != 8 && ew != 16 && ew != 24) ew = 16;
   }
   return ew;
 }
 
-template <int MODE, int KP, int EW>
+template <int MODE, int KP, int EW, bool EXACT>
 static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                           const CUtensorMap& b_lo, const TcParams& p) {
   int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + p.BN * BK * 2);
   size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, KP, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, KP, EW, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int m_items = p.pair == 1 ? (p.m_tiles + 1) / 2 : p.m_tiles;
@@ -750,7 +765,7 @@ static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, KP, EW>, a_hi, a_lo, b_hi, b_lo, p));
+  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, KP, EW, EXACT>, a_hi, a_lo, b_hi, b_lo, p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
@@ -759,8 +774,16 @@ static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
 template <int MODE, int KP>
 static int launch_gemm(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                        const CUtensorMap& b_lo, const TcParams& p) {
-  if (epilogue_warps() == 8) return launch_gemm_ew<MODE, KP, 8>(ctx, a_hi, a_lo, b_hi, b_lo, p);
-  return launch_gemm_ew<MODE, KP, 16>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+  const bool exact = p.K == KP;
+  if (epilogue_warps() == 8) {
+    if (exact) return launch_gemm_ew<MODE, KP, 8, true>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+    return launch_gemm_ew<MODE, KP, 8, false>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+  }
+  if constexpr (KP <= 16 && MODE == MODE_FWD) {
+    if (exact && epilogue_warps() == 24) return launch_gemm_ew<MODE, KP, 24, true>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+  }
+  if (exact) return launch_gemm_ew<MODE, KP, 16, true>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+  return launch_gemm_ew<MODE, KP, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, p);
 }
 
 template <int KP>
@@ -786,7 +809,8 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const int64_t P = (int64_t)(D + 1) * K;
   const int nmat = split3 ? 2 : 1;
   const int stage_bytes = nmat * (BM * BK * 2 + BN * BK * 2);
-  const int stages = std::max(2, std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes)));
+  int stages = std::max(2, std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes)));
+  if (const char* e = getenv("BHMC_STAGES")) stages = std::max(1, std::min(stages, atoi(e)));
 
   // scratch: slot 1 = Wt hi|lo, slot 2 = DmT hi|lo, slot 3 = split-K partials
   void* wt = nullptr;
@@ -852,6 +876,14 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.dmt_lo = dmt_lo;
   p.loglik = loglik;
   p.write_dm = g ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("BHMC_DEBUG_EPI");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   p.part = nullptr;
   {
     GroupTimer t(ctx, KG_FWD);
@@ -911,7 +943,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   }
   {
     GroupTimer t(ctx, KG_BWD);
-    BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
+    BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
     dim3 grid((unsigned)ceil_div(ld, 256), C);
     k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, K, KP, P, q, g, ld, alpha);
     ctx->launches++;

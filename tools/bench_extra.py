@@ -19,17 +19,22 @@ from dropout_hamiltonian_montecarlo_b200._lib import KIND, PREC
 from dropout_hamiltonian_montecarlo_b200.runtime import MlpHandle, SamplerHandle, SoftmaxHandle, default_context
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["sgld", "mlp", "update"])
+ap.add_argument("what", choices=["sgld", "mlp", "update", "rows"])
+ap.add_argument("--rows", type=int, default=1000000)
+ap.add_argument("--features", type=int, default=2048)
+ap.add_argument("--classes", type=int, default=38)
 ap.add_argument("--chains", type=int, default=0)
 ap.add_argument("--epochs", type=int, default=2)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--precision", default="bf16x3")
 a = ap.parse_args()
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
 ctx = default_context()
 dev = ctx.device
 peak_tf, peak_bw, src = peaks()
 N, D, K, B = 60000, 784, 10, 500
-X, y = synth(N, D, K, 0, device=dev)
+if a.what != "rows":
+    X, y = synth(N, D, K, 0, device=dev)
 
 
 def timed(fn):
@@ -42,7 +47,45 @@ def timed(fn):
     return e0.elapsed_time(e1) * 1e-3, out
 
 
-if a.what == "sgld":
+if a.what == "rows":
+    # BASELINE config 5: full-batch HMC, rows sharded over the ranks, one all-reduce (NCCL) per gradient evaluation.
+    # Launch with torchrun; every rank synthesises only its own shard (abs(N(0,1)) features).
+    import torch.distributed as dist
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.hmc import hmc
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.softmax import softmax
+    from dropout_hamiltonian_montecarlo_b200.parallel import shard_rows
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    Nt, Dt, Kt, C = a.rows, a.features, a.classes, a.chains or 8
+    r0, nloc = shard_rows(Nt, rank, world)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    Xs = torch.randn(nloc, Dt, generator=g, device=dev).abs_()
+    ys = torch.randint(0, Kt, (nloc,), generator=g, device=dev, dtype=torch.int32)
+    m = softmax({"alpha": 0.01}, precision=a.precision, row_sharded=world > 1)
+    eps, path = 1e-7, 1e-6  # E[L] = 10
+    smp = hmc(m, {"weights": np.zeros((Dt, Kt), np.float32), "bias": np.zeros(Kt, np.float32)}, path_length=path,
+              step_size=eps, verbose=False, n_chains=C, seed=3, path_length_mode="shared")
+    smp.sample(niter=1, burnin=0, X_train=Xs, y_train=ys)  # warm-up (binds, allocates)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    smp.sample(niter=a.steps, burnin=0, X_train=Xs, y_train=ys)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    n_grad = smp.last_run["n_grad_evals"]
+    if rank == 0:
+        print(json.dumps({"workload": "cfg5 full-batch HMC softmax %dx%dx%d, %d chains replicated, rows sharded over %d GPU(s)"
+                          % (Nt, Dt, Kt, C, world), "precision": a.precision, "grad_evals_per_s": n_grad / dt,
+                          "ms_per_grad_eval_all_chains": 1e3 * dt / (n_grad / C),
+                          "algorithmic_tflops_total": n_grad * 4.0 * Nt * Dt * Kt / dt / 1e12, "n_gpus": world,
+                          "allreduce_bytes_per_eval": 4 * C * m._bound[1].ld + 8 * C}))
+    if world > 1:
+        dist.destroy_process_group()
+elif a.what == "sgld":
     C = a.chains or 128
     h = SoftmaxHandle(ctx, N, D, K, 0.01)
     h.bind(X, y, 1 | (1 << PREC[a.precision]))
