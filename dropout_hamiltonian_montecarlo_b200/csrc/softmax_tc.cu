@@ -33,7 +33,15 @@
 namespace bhmc {
 
 static constexpr int BM = 128;        // UMMA M
-static constexpr int BK = 64;         // bf16 elements per stage row = 128 B = one swizzle span
+// K extent of one pipeline stage.  64 elements = 128 B rows (SWIZZLE_128B); 32 elements = 64 B rows (SWIZZLE_64B).
+// Both are implemented and parity-tested; measured on B200 the half-size stages (twice the ring depth) are SLOWER
+// (forward 222 us vs 185 us at cfg2): the main loop pays ~450 cycles per chunk that do not overlap with the MMAs,
+// so fewer, larger chunks win.  Build with -DBHMC_BK=32 to reproduce.
+#ifndef BHMC_BK
+#define BHMC_BK 64
+#endif
+static constexpr int BK = BHMC_BK;
+static_assert(BK == 32 || BK == 64, "BK must be 32 (SWIZZLE_64B) or 64 (SWIZZLE_128B)");
 static constexpr int UMMA_K = 16;
 static constexpr int MAX_STAGES = 8;
 static constexpr int NON_EPI_THREADS = 128;  // warps 0-3: TMA, MMA, TMEM alloc, spare
@@ -124,14 +132,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+// K-major swizzled operand tile: rows of BK*2 bytes, 8-row groups (one swizzle atom) SBO bytes apart, version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t kSbo = (8 * BK * 2) >> 4;          // 1024 B (SW128) or 512 B (SW64), in 16-byte units
+  constexpr uint64_t kLayout = (BK == 64) ? 2 : 4;      // UMMA::LayoutType::SWIZZLE_128B / SWIZZLE_64B
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;           // leading byte offset: unused for swizzled K-major
-  d |= (uint64_t)(1024 >> 4) << 32; // stride byte offset
-  d |= (uint64_t)1 << 46;           // descriptor version
-  d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+  d |= (uint64_t)1 << 16;  // leading byte offset: unused for swizzled K-major
+  d |= kSbo << 32;         // stride byte offset
+  d |= (uint64_t)1 << 46;  // descriptor version
+  d |= kLayout << 61;
   return d;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -630,7 +640,8 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t o
   cuuint32_t box[2] = {(cuuint32_t)BK, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu stride=%llu box=%u", (int)r, base,
@@ -809,7 +820,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const int64_t P = (int64_t)(D + 1) * K;
   const int nmat = split3 ? 2 : 1;
   const int stage_bytes = nmat * (BM * BK * 2 + BN * BK * 2);
-  int stages = std::max(2, std::min(MAX_STAGES, (int)((220 * 1024) / stage_bytes)));
+  int stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
   if (const char* e = getenv("BHMC_STAGES")) stages = std::max(1, std::min(stages, atoi(e)));
 
   // scratch: slot 1 = Wt hi|lo, slot 2 = DmT hi|lo, slot 3 = split-K partials
@@ -918,7 +929,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     const char* e = getenv("BHMC_SUB_CHUNKS");
     sub_env = e ? std::max(1, atoi(e)) : 16;
   }
-  b.sub_chunks = sub_env;
+  b.sub_chunks = sub_env * (64 / BK);  // expressed in 64-element units
   b.BN = BN;
   b.stages = stages;
   b.split3 = split3 ? 1 : 0;
