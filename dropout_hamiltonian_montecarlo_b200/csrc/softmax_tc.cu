@@ -105,9 +105,12 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -119,16 +122,23 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tcgen05.mma / tcgen05.commit are issued by ONE elected lane of a converged warp (the commit tracks the MMAs
+// issued by the same thread; elect.sync returns the same leader for the full mask every time).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -223,6 +233,7 @@ struct TcParams {
   __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
   double* loglik;
   int write_dm;
+  long long* prof;                // optional [grid][8] cycle counters (BHMC_PROF=1): see tools/profile_grad.py
   int debug;                      // BHMC_DEBUG_EPI (measurement only): 1 = skip the forward epilogue, 2 = skip its atomics
   // backward epilogue
   float* part;                    // [n_split, m_tiles*128, n_tiles*BN]
@@ -294,7 +305,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = wi0; w < num_work; w += wi_step) {
+      for (int w = wi0; w < num_work && p.debug != 9 && p.debug != 10; w += wi_step) {
         BHMC_DECODE_WORK(w)
         int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
         const int nmat = p.split3 ? 2 : 1;
@@ -332,48 +343,77 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int w = wi0; w < num_work; w += wi_step) {
-        BHMC_DECODE_WORK(w)
-        int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
-        for (int kb = k_begin; kb < k_end; kb += p.sub_chunks, ++it) {
+    // The whole warp runs this loop in warp-uniform control flow and one elected lane issues: keeping the
+    // operands warp-uniform lets ptxas hold descriptors in uniform registers.  (Issuing from inside a divergent
+    // `if (lane == 0)` made it wrap every UTCHMMA in an ELECT / 5x R2UR / BRA.ANY loop, ~90 cycles per MMA --
+    // more than the 80 cycles the MMA itself takes; measured: 1070 cycles of issue per 12-MMA chunk.)
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const bool do_mma = !(p.debug == 3 || p.debug == 5 || p.debug == 7);
+    const bool do_wait = !(p.debug == 9 || p.debug == 10);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    long long t_tempty = 0, t_full = 0, t_issue = 0, t_start = clock64(), n_chunks = 0;
+    for (int w = wi0; w < num_work; w += wi_step) {
+      BHMC_DECODE_WORK(w)
+      const int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
+      for (int kb = k_begin; kb < k_end; kb += p.sub_chunks, ++it) {
         const int ke = min(k_end, kb + p.sub_chunks);
-        int buf = it & 1;
-        uint32_t use = (uint32_t)(it >> 1);
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        long long c0 = p.prof ? clock64() : 0;
         mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+        if (p.prof) t_tempty += clock64() - c0;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
         for (int k = kb; k < ke; ++k) {
-          mbar_wait(smem_u32(&bar_full[stage]), phase);
-          tcgen05_fence_after();
-          uint32_t sa = smem_base + stage * stage_bytes;
-          uint64_t a_hi = make_smem_desc(sa);
-          uint64_t a_lo = make_smem_desc(sa + a_bytes);
-          uint64_t b_hi = make_smem_desc(sa + (p.split3 ? 2 : 1) * a_bytes);
-          uint64_t b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
-#pragma unroll
-          for (int ks = 0; ks < ((p.debug == 3 || p.debug == 5 || p.debug == 7) ? 0 : BK / UMMA_K); ++ks) {
-            uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle span
-            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (k > kb || ks > 0) ? 1u : 0u);
+          long long c1 = p.prof ? clock64() : 0;
+          if (do_wait) {
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            tcgen05_fence_after();
+          }
+          long long c2 = p.prof ? clock64() : 0;
+          if (p.prof) t_full += c2 - c1, ++n_chunks;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t first = (k > kb) ? 1u : 0u;
+          if (do_mma) {
             if (p.split3) {
-              umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+              const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+              const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+              for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);  // +32 B per K step inside the swizzle span
+                umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+                umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            } else {
+              const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+              for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+                umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+              }
             }
           }
           // smem slot reusable once these MMAs retire; in pair mode the peer's producer also writes into this
           // CTA's slot, so the release is multicast to both CTAs (empty barriers count 2 arrivals)
-          if (p.pair) umma_commit_mc(smem_u32(&bar_empty[stage]), 3);
-          else umma_commit(smem_u32(&bar_empty[stage]));
+          if (p.debug == 9) {
+          } else if (p.debug == 10 || !p.pair) {
+            umma_commit(smem_u32(&bar_empty[stage]));
+          } else {
+            umma_commit_mc(smem_u32(&bar_empty[stage]), 3);
+          }
+          if (p.prof) t_issue += clock64() - c2;
           if (++stage == p.stages) stage = 0, phase ^= 1u;
         }
         umma_commit(smem_u32(&bar_tfull[buf]));  // accumulator (of this sub-slab) complete
-        }
       }
+    }
+    if (p.prof && lane == 0) {
+      long long* o = p.prof + (size_t)blockIdx.x * 8;
+      o[0] = clock64() - t_start, o[1] = t_tempty, o[2] = t_full, o[3] = t_issue, o[4] = n_chunks, o[5] = it;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -437,7 +477,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      if (!tile_ok || p.debug == 1 || p.debug == 6 || p.debug == 7) {
+      if (!tile_ok || p.debug == 1 || p.debug == 6 || p.debug == 7 || p.debug >= 9) {
         // nothing to store; only the barrier protocol below
       } else if constexpr (MODE == MODE_FWD) {
         const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
@@ -887,6 +927,15 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.dmt_lo = dmt_lo;
   p.loglik = loglik;
   p.write_dm = g ? 1 : 0;
+  p.prof = nullptr;
+  static int want_prof = -1;
+  if (want_prof < 0) want_prof = getenv("BHMC_PROF") ? 1 : 0;
+  void* prof_dev = nullptr;
+  if (want_prof) {
+    BHMC_TRY(ctx->get_scratch(5, sizeof(long long) * 8 * 1024, &prof_dev));
+    BHMC_CUDA_OK(cudaMemsetAsync(prof_dev, 0, sizeof(long long) * 8 * 1024, ctx->stream));
+    p.prof = (long long*)prof_dev;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -910,6 +959,17 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
       default: set_error("unsupported KP %d", KP); rc = BHMC_ERR_UNSUPPORTED;
     }
     BHMC_TRY(rc);
+  }
+  if (want_prof) {
+    std::vector<long long> hp(8 * 148);
+    BHMC_CUDA_OK(cudaMemcpyAsync(hp.data(), prof_dev, sizeof(long long) * 8 * 148, cudaMemcpyDeviceToHost, ctx->stream));
+    BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    double tot = 0, te = 0, tf = 0, ti = 0, nc = 0, nt = 0;
+    int n = 0;
+    for (int b = 0; b < 148; ++b)
+      if (hp[b * 8] > 0) tot += hp[b * 8], te += hp[b * 8 + 1], tf += hp[b * 8 + 2], ti += hp[b * 8 + 3], nc += hp[b * 8 + 4], nt += hp[b * 8 + 5], ++n;
+    if (n)
+      fprintf(stderr, "[bhmc prof fwd] MMA thread, mean over %d CTAs: total %.0f cyc; wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f tiles %.0f -> per chunk: full-wait %.0f issue %.0f\n", n, tot / n, te / n, tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
   }
   if (!g) return BHMC_OK;
 
