@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libbhmc.so")
-SOURCES = ["capi.cu", "update.cu", "softmax_simt.cu", "softmax_tc.cu", "mlp.cu"]
+SOURCES = ["capi.cu", "update.cu", "softmax_simt.cu", "softmax_tc.cu", "mlp.cu", "tc_bgemm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

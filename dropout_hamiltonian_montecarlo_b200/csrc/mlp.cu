@@ -7,9 +7,9 @@
 //   :40-45  log_prior = -alpha/2 sum_v |theta_v|^2 / dim_v
 // Parameter row (Chainer namedparams order): /l1/W [mid,in] | /l1/b | /l2/W [mid,mid] | /l2/b | /l3/W [out,mid] | /l3/b.
 //
-// This round the eight GEMMs per evaluation run as fp32 FMA on CUDA cores (one strided-batched tile kernel
-// with fused epilogues: bias + dropout + ReLU, ReLU-gate of the back-propagated signal, alpha/2*W); moving
-// them onto the tcgen05 main loop of softmax_tc.cu (grouped per-chain tensor maps) is the next step.
+// The eight GEMMs per evaluation are strided-batched over chains with fused epilogues (bias + dropout + ReLU,
+// ReLU-gate of the back-propagated signal, alpha/2*W).  BHMC_PREC_FP32 runs them as fp32 FMA on CUDA cores
+// (k_mlp_gemm below); BHMC_PREC_BF16X3 / BF16 send the five large ones to tcgen05 (tc_bgemm.cu).
 // Because relu(a*m) > 0 implies the keep-mask m == 1, the backward pass needs only the stored activations
 // (H1, H2d), not the masks:  dA2 = dH2d * [H2d>0] / keep^2,  dA1 = dH1 * [H1>0] / keep.
 #include <new>
@@ -21,40 +21,10 @@ namespace bhmc {
 
 static constexpr int TM = 64, TN = 64, TK = 16;
 
-struct GemmDesc {
-  const float* A;  // element (m,k) at A + c*a_batch + m*a_rs + k*a_cs
-  int64_t a_batch, a_rs, a_cs;
-  const float* B;  // element (k,n) at B + c*b_batch + k*b_rs + n*b_cs
-  int64_t b_batch, b_rs, b_cs;
-  float* C;  // element (m,n) at C + c*c_batch + m*c_rs + n
-  int64_t c_batch, c_rs;
-  int M, N, K;
-  const float* bias;  // + bias[c*bias_batch + n]
-  int64_t bias_batch;
-  const float* addsrc;  // + add_scale * addsrc[c*add_batch + m*add_rs + n]
-  int64_t add_batch, add_rs;
-  float add_scale;
-  const float* gate;  // *= gate_scale * [gate[c*gate_batch + m*gate_rs + n] > 0]
-  int64_t gate_batch, gate_rs;
-  float gate_scale;
-  int epi;  // 0: linear; 1: relu(v*mask_a*keep_inv); 2: relu(v*mask_a*keep_inv)*mask_b*keep_inv
-  float keep_inv, keep_prob;
-  const uint8_t* mask_a;  // injected keep-masks [c][m][n] (tests) or nullptr -> Philox
-  const uint8_t* mask_b;
-  int64_t mask_batch;
-  uint64_t seed;
-  int64_t chain_id0;
-  uint32_t eval_id, layer_a, layer_b;
-};
+#include "mlp_common.cuh"
 
-__device__ __forceinline__ uint32_t keep_bits4(const GemmDesc& d, int c, int m, int n, uint32_t layer) {
-  // four Bernoulli(keep_prob) draws for units n..n+3 (n % 4 == 0) of row m; bit e = keep
-  U4 r = philox4x32_10(U4{(uint32_t)(((int64_t)m * d.N + n) >> 2), (uint32_t)(d.chain_id0 + c), d.eval_id,
-                           TAG_DROPOUT | layer},
-                       (uint32_t)d.seed, (uint32_t)(d.seed >> 32));
-  uint32_t thr = (uint32_t)(d.keep_prob * 4294967296.0);
-  return (r.x < thr ? 1u : 0u) | (r.y < thr ? 2u : 0u) | (r.z < thr ? 4u : 0u) | (r.w < thr ? 8u : 0u);
-}
+// tc_bgemm.cu: the same GEMM + epilogue on the tensor cores (bf16 hi/lo split or single bf16 pass)
+int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3);
 
 __global__ void __launch_bounds__(256) k_mlp_gemm(GemmDesc d) {
   __shared__ float As[TK][TM + 4];
@@ -215,7 +185,7 @@ struct MlpModel : ModelBase {
     for (int v = 0; v < n_vars; ++v) cv[v] = -0.5 * (double)alpha / (double)var_len[v];
   }
 
-  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int, float* g, double* stat) override {
+  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) override {
     BHMC_CHECK_ARG(X && labels, "mlp model has no bound data");
     BHMC_CHECK_ARG(row0 >= 0 && nrows > 0 && row0 + nrows <= N, "row window outside the bound rows");
     const int B = (int)nrows;
@@ -240,6 +210,13 @@ struct MlpModel : ModelBase {
       d.eval_id = ev;
       d.mask_batch = mstride;
       return d;
+    };
+    // the five large GEMMs go to the tensor cores unless the fp32 CUDA-core path is requested; the three GEMMs
+    // that touch the n_out-wide logits (N, M or K = n_out ~ 10) stay on CUDA cores
+    const bool use_tc = prec != BHMC_PREC_FP32, split3 = prec == BHMC_PREC_BF16X3;
+    auto run_gemm = [&](bhmc_ctx* cx, const GemmDesc& gd, int batch) -> int {
+      if (use_tc && gd.M >= 64 && gd.N >= 64 && gd.K >= 64) return tc_bgemm(cx, gd, batch, split3);
+      return bhmc::run_gemm(cx, gd, batch);
     };
     BHMC_CUDA_OK(cudaMemsetAsync(stat, 0, sizeof(double) * C, ctx->stream));
     {

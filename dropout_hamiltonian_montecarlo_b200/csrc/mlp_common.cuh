@@ -1,0 +1,40 @@
+// Shared by mlp.cu (fp32 CUDA-core GEMMs) and tc_bgemm.cu (tcgen05 batched GEMMs): the description of one
+// strided-batched GEMM with its fused epilogue, and the Philox dropout mask both paths must agree on.
+// Include inside `namespace bhmc` after internal.cuh and philox.cuh.
+#pragma once
+
+struct GemmDesc {
+  const float* A;  // element (m,k) at A + c*a_batch + m*a_rs + k*a_cs
+  int64_t a_batch, a_rs, a_cs;
+  const float* B;  // element (k,n) at B + c*b_batch + k*b_rs + n*b_cs
+  int64_t b_batch, b_rs, b_cs;
+  float* C;  // element (m,n) at C + c*c_batch + m*c_rs + n
+  int64_t c_batch, c_rs;
+  int M, N, K;
+  const float* bias;  // + bias[c*bias_batch + n]
+  int64_t bias_batch;
+  const float* addsrc;  // + add_scale * addsrc[c*add_batch + m*add_rs + n]
+  int64_t add_batch, add_rs;
+  float add_scale;
+  const float* gate;  // *= gate_scale * [gate[c*gate_batch + m*gate_rs + n] > 0]
+  int64_t gate_batch, gate_rs;
+  float gate_scale;
+  int epi;  // 0: linear; 1: relu(v*mask_a*keep_inv); 2: relu(v*mask_a*keep_inv)*mask_b*keep_inv
+  float keep_inv, keep_prob;
+  const uint8_t* mask_a;  // injected keep-masks [c][m][n] (tests) or nullptr -> Philox
+  const uint8_t* mask_b;
+  int64_t mask_batch;
+  uint64_t seed;
+  int64_t chain_id0;
+  uint32_t eval_id, layer_a, layer_b;
+};
+
+__device__ __forceinline__ uint32_t keep_bits4(const GemmDesc& d, int c, int m, int n, uint32_t layer) {
+  // four Bernoulli(keep_prob) draws for units n..n+3 (n % 4 == 0) of row m; bit e = keep
+  U4 r = philox4x32_10(U4{(uint32_t)(((int64_t)m * d.N + n) >> 2), (uint32_t)(d.chain_id0 + c), d.eval_id,
+                           TAG_DROPOUT | layer},
+                       (uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+  uint32_t thr = (uint32_t)(d.keep_prob * 4294967296.0);
+  return (r.x < thr ? 1u : 0u) | (r.y < thr ? 2u : 0u) | (r.z < thr ? 4u : 0u) | (r.w < thr ? 8u : 0u);
+}
+

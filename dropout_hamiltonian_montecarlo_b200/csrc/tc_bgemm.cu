@@ -1,0 +1,348 @@
+// Strided-batched GEMM on the 5th-generation tensor cores for the dropout MLP (hamiltonian/models/gpu/mlp.py):
+//   C[z] = epilogue( A[z] (M x K) . B[z] (K x N) ),  z = chain, fp32 in / fp32 out,
+// computed as bf16 hi/lo split products (3 tcgen05.mma per K step, fp32 accumulation in TMEM) or one bf16 pass.
+// It takes the same GemmDesc (operand strides + fused epilogue: bias, alpha/2*W, ReLU gate, Philox / injected
+// dropout + ReLU) as the CUDA-core kernel in mlp.cu, so the two paths are interchangeable per GEMM.
+//
+// Pipeline: (1) k_split_operand writes K-major bf16 hi/lo copies of A ([z][M][Kp]) and of B^T ([z][N][Kp]) -- the
+// transposition, if any, is absorbed here through a 32x32 shared-memory tile; (2) k_tc_bgemm: persistent CTAs,
+// warp 0 = TMA producer (3-D tensor maps: k, row, chain), warp 1 = MMA issuer (warp-uniform, elect.sync),
+// warp 2 = TMEM allocator, 16 epilogue warps (tcgen05.ld -> fused epilogue -> fp32 stores, 64 B per thread per chunk);
+// accumulators double-buffered in TMEM.  Same main loop as k_tc_gemm in softmax_tc.cu.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "internal.cuh"
+#include "philox.cuh"
+
+namespace bhmc {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int UMMA_K = 16;
+static constexpr int MAX_STAGES = 8;
+static constexpr int NON_EPI_THREADS = 128;
+static constexpr int EW = 16;
+static constexpr int TMEM_COLS = 512;
+static constexpr int TMEM_BUF_COLS = 256;
+
+#include "tc_common.cuh"
+#include "mlp_common.cuh"
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+struct BgParams {
+  int batch, m_tiles, n_tiles, k_chunks, BN, stages, split3;
+  int a_shared, b_shared;  // operand identical for every chain (e.g. the data matrix)
+  GemmDesc d;              // sizes + epilogue (the A/B pointers inside are unused here)
+};
+
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
+k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const BgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_bytes = BM * BK * 2, b_bytes = p.BN * BK * 2;
+  const int nmat = p.split3 ? 2 : 1;
+  const int stage_bytes = nmat * (a_bytes + b_bytes);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int num_work = p.batch * tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int z = w / tiles, rem = w % tiles, mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        const int za = p.a_shared ? 0 : z, zb = p.b_shared ? 0 : z;
+        for (int k = 0; k < p.k_chunks; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_expect_tx(full, (uint32_t)stage_bytes);
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + nmat * a_bytes;
+          tma_load_3d(sa, &tmA_hi, full, k * BK, mt * BM, za);
+          if (p.split3) tma_load_3d(sa + a_bytes, &tmA_lo, full, k * BK, mt * BM, za);
+          tma_load_3d(sb, &tmB_hi, full, k * BK, nt * p.BN, zb);
+          if (p.split3) tma_load_3d(sb + b_bytes, &tmB_lo, full, k * BK, nt * p.BN, zb);
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // warp-uniform MMA issue loop, one elected lane issues (see softmax_tc.cu)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+      for (int k = 0; k < p.k_chunks; ++k) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint32_t first = k > 0 ? 1u : 0u;
+        if (p.split3) {
+          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+          const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+        } else {
+          const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+          }
+        }
+        umma_commit(smem_u32(&bar_empty[stage]));
+        if (++stage == p.stages) stage = 0, phase ^= 1u;
+      }
+      umma_commit(smem_u32(&bar_tfull[buf]));
+    }
+  } else if (warp >= 4) {
+    const GemmDesc& d = p.d;
+    const int ew = warp & 3, part = (warp - 4) >> 2;
+    constexpr int PARTS = EW / 4;
+    const int t = ew * 32 + lane;
+    int it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      const int z = w / tiles, rem = w % tiles, mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+      const int m = mt * BM + t;
+      for (int j0 = part * 16; j0 < p.BN; j0 += 16 * PARTS) {
+        uint32_t raw[16];
+        tmem_ld<16>(tacc + (uint32_t)j0, raw);  // all lanes take part (.sync.aligned), stores are predicated below
+        tmem_ld_wait();
+        const int n0 = nt * p.BN + j0;
+        if (m < d.M && n0 < d.N) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {  // four columns at a time (one Philox call per quad)
+            const int n = n0 + 4 * qd;
+            if (n >= d.N) break;
+            uint32_t ka = 15u, kb = 15u;
+            if (d.epi >= 1) {
+              if (d.mask_a) {
+                ka = 0;
+                for (int j = 0; j < 4; ++j)
+                  if (n + j < d.N && d.mask_a[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) ka |= 1u << j;
+              } else {
+                ka = keep_bits4(d, z, m, n, d.layer_a);
+              }
+              if (d.epi == 2) {
+                if (d.mask_b) {
+                  kb = 0;
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < d.N && d.mask_b[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) kb |= 1u << j;
+                } else {
+                  kb = keep_bits4(d, z, m, n, d.layer_b);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n + j >= d.N) continue;
+              float x = v[4 * qd + j];
+              if (d.bias) x += d.bias[(int64_t)z * d.bias_batch + n + j];
+              if (d.addsrc) x += d.add_scale * d.addsrc[(int64_t)z * d.add_batch + (int64_t)m * d.add_rs + n + j];
+              if (d.gate) x = (d.gate[(int64_t)z * d.gate_batch + (int64_t)m * d.gate_rs + n + j] > 0.f) ? x * d.gate_scale : 0.f;
+              if (d.epi >= 1) {
+                x = ((ka >> j) & 1u) ? x * d.keep_inv : 0.f;
+                x = fmaxf(x, 0.f);
+                if (d.epi == 2) x = ((kb >> j) & 1u) ? x * d.keep_inv : 0.f;
+              }
+              d.C[(int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n + j] = x;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(&bar_tempty[buf]));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// dst_{hi,lo}[z][r][k] (k < Kp contiguous) = split(src[z*sb + r*rs + k*cs]) for k < K, 0 for K <= k < Kp.
+// One 32x32 tile per block through shared memory, so both cs == 1 (row-major source) and rs == 1 (transposed
+// source) read and write coalesced.
+__global__ void __launch_bounds__(256) k_split_operand(const float* __restrict__ src, int64_t sb, int64_t rs, int64_t cs,
+                                                       int R, int K, int64_t Kp, __nv_bfloat16* __restrict__ hi,
+                                                       __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int z = blockIdx.z;
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const float* s = src + (int64_t)z * sb;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  if (cs == 1 || rs != 1) {
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, k = k0 + tx;
+      tile[i][tx] = (r < R && k < K) ? s[(int64_t)r * rs + (int64_t)k * cs] : 0.f;
+    }
+  } else {  // rows are the contiguous index of the source: read along r
+    for (int i = ty; i < 32; i += 8) {
+      const int k = k0 + i, r = r0 + tx;
+      tile[tx][i] = (r < R && k < K) ? s[(int64_t)r * rs + (int64_t)k * cs] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, k = k0 + tx;
+    if (r < R && k < Kp) {
+      const float v = tile[i][tx];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const int64_t o = ((int64_t)z * R + r) * Kp + k;
+      hi[o] = h;
+      if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 [Z][R][Kp] (K contiguous), box [1][box_rows][64], 128B swizzle, OOB rows / k read as zero
+static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, uint64_t Z, uint64_t Kp, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return BHMC_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {K, R, Z};
+  cuuint64_t strides[2] = {Kp * 2, R * Kp * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed (%d): K=%llu R=%llu Z=%llu Kp=%llu box=%u", (int)r, (unsigned long long)K,
+              (unsigned long long)R, (unsigned long long)Z, (unsigned long long)Kp, box_rows);
+    return BHMC_ERR_CUDA;
+  }
+  return BHMC_OK;
+}
+
+// C[z] = epilogue(A[z] . B[z]) for z < batch, operands described by d (fp32, arbitrary strides).
+// scratch slots 1..2 of the context hold the bf16 operand copies.
+int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
+  const int64_t Kp = round_up(d.K, 64);
+  const bool a_shared = d.a_batch == 0, b_shared = d.b_batch == 0;
+  const int za = a_shared ? 1 : batch, zb = b_shared ? 1 : batch;
+  const size_t a_elems = (size_t)za * d.M * Kp, b_elems = (size_t)zb * d.N * Kp;
+  void *sa = nullptr, *sb = nullptr;
+  BHMC_TRY(ctx->get_scratch(1, a_elems * 2 * 2, &sa));
+  BHMC_TRY(ctx->get_scratch(2, b_elems * 2 * 2, &sb));
+  __nv_bfloat16 *a_hi = (__nv_bfloat16*)sa, *a_lo = a_hi + a_elems;
+  __nv_bfloat16 *b_hi = (__nv_bfloat16*)sb, *b_lo = b_hi + b_elems;
+  {
+    GroupTimer t(ctx, KG_PREP);
+    dim3 ga((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(d.M, 32), (unsigned)za);
+    k_split_operand<<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, a_hi, split3 ? a_lo : nullptr);
+    // B is (k, n) with strides (b_rs, b_cs): its K-major copy has rows n
+    dim3 gb((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(d.N, 32), (unsigned)zb);
+    k_split_operand<<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, b_hi, split3 ? b_lo : nullptr);
+    ctx->launches += 2;
+  }
+  BgParams p{};
+  p.batch = batch;
+  p.BN = d.N >= 128 ? 128 : (int)round_up(d.N, 16);
+  p.m_tiles = (int)ceil_div(d.M, BM);
+  p.n_tiles = (int)ceil_div(d.N, p.BN);
+  p.k_chunks = (int)ceil_div(d.K, BK);
+  p.split3 = split3 ? 1 : 0;
+  p.a_shared = a_shared;
+  p.b_shared = b_shared;
+  p.d = d;
+  const int stage_bytes = (split3 ? 2 : 1) * (BM * BK * 2 + p.BN * BK * 2);
+  p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  BHMC_TRY(make_map3(&mA_hi, a_hi, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, (uint64_t)Kp, BM));
+  BHMC_TRY(make_map3(&mB_hi, b_hi, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, (uint32_t)p.BN));
+  if (split3) {
+    BHMC_TRY(make_map3(&mA_lo, a_lo, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, (uint64_t)Kp, BM));
+    BHMC_TRY(make_map3(&mB_lo, b_lo, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, (uint32_t)p.BN));
+  } else {
+    mA_lo = mA_hi;
+    mB_lo = mB_hi;
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int work = batch * p.m_tiles * p.n_tiles;
+  const int grid = std::min(work, ctx->sm_count);
+  k_tc_bgemm<<<grid, NON_EPI_THREADS + 32 * EW, smem, ctx->stream>>>(mA_hi, mA_lo, mB_hi, mB_lo, p);
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+}  // namespace bhmc

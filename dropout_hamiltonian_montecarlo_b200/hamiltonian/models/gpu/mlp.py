@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from ... import _base
+from ...._lib import PREC
 from ....runtime import MlpHandle
 
 KEYS = ("/l1/W", "/l1/b", "/l2/W", "/l2/b", "/l3/W", "/l3/b")
@@ -19,14 +20,15 @@ KEYS = ("/l1/W", "/l1/b", "/l2/W", "/l2/b", "/l3/W", "/l3/b")
 class mlp(_base.ChainModel):
     var_names = KEYS
 
-    def __init__(self, _hyper, n_in, n_mid_units, n_out, *, dropout=0.1, seed=0, chain_id0=0, device=None):
+    def __init__(self, _hyper, n_in, n_mid_units, n_out, *, dropout=0.1, seed=0, chain_id0=0, device=None,
+                 precision="bf16x3"):
         super().__init__(device)
         self.hyper = _hyper
         self.n_in, self.n_mid, self.n_out = int(n_in), int(n_mid_units), int(n_out)
         self.dropout = dropout
         self.seed = seed
         self.chain_id0 = chain_id0
-        self.precision = "fp32"
+        self.precision = precision  # "bf16x3" / "bf16": large GEMMs on tcgen05; "fp32": CUDA cores
         self._bound = None
 
     def var_shapes(self, handle=None):
@@ -67,14 +69,14 @@ class mlp(_base.ChainModel):
         """mlp.py:47-64."""
         h = self.handle_for(**args)
         q, squeeze, like = self.flatten(par, self.var_shapes())
-        g, _ = h.grad(h.pack(q), 0, h.N, 0, True)
+        g, _ = h.grad(h.pack(q), 0, h.N, PREC[self.precision], True)
         return self.unflatten(g[:, : h.P], self.var_shapes(), squeeze, like)
 
     def log_likelihood(self, par, **args):
         """mlp.py:66-78 -- returns the (positive) mean cross-entropy, as the reference does."""
         h = self.handle_for(**args)
         q, squeeze, _ = self.flatten(par, self.var_shapes())
-        _, ll = h.grad(h.pack(q), 0, h.N, 0, False)
+        _, ll = h.grad(h.pack(q), 0, h.N, PREC[self.precision], False)
         out = ll.cpu().numpy()
         return float(out[0]) if squeeze else out
 
@@ -87,5 +89,5 @@ class mlp(_base.ChainModel):
         """mlp.py:80-82."""
         h = self.handle_for(**args)
         q, squeeze, _ = self.flatten(par, self.var_shapes())
-        out = h.nlp(h.pack(q), 0, h.N, 0).cpu().numpy()
+        out = h.nlp(h.pack(q), 0, h.N, PREC[self.precision]).cpu().numpy()
         return float(out[0]) if squeeze else out

@@ -30,14 +30,16 @@ def close(got, ref, rtol=1e-4, atol_scale=1e-5, what=""):
                                atol=atol_scale * max(1e-30, float(np.abs(ref).max())), err_msg=what)
 
 
-@pytest.mark.parametrize("shape", [(37, 20, 24, 5), (130, 70, 96, 10)])
-def test_mlp_grad_loss_nlp_injected_masks(shape):
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("shape", [(37, 20, 24, 5), (130, 70, 96, 10), (500, 784, 512, 10)])
+def test_mlp_grad_loss_nlp_injected_masks(shape, prec):
+    """(500, 784, 512, 10) is BASELINE config 4's layer shape; the five large GEMMs run on tcgen05 for bf16x3."""
     B, n_in, n_mid, n_out = shape
     rs = np.random.RandomState(0)
-    C, alpha = 3, 0.05
-    par, X, y = make(rs, B, n_in, n_mid, n_out, C)
+    C, alpha = (2 if B == 500 else 3), 0.05
+    par, X, y = make(rs, B, n_in, n_mid, n_out, C, scale=(0.05 if B == 500 else 0.3))
     masks = (rs.rand(3, C, B, n_mid) > 0.1).astype(np.uint8)
-    m = mlp({"alpha": alpha}, n_in, n_mid, n_out)
+    m = mlp({"alpha": alpha}, n_in, n_mid, n_out, precision=prec)
     m.bind(X, y)
     m.set_masks(masks)
     g = m.grad(par, X_train=X, y_train=y)
@@ -48,7 +50,19 @@ def test_mlp_grad_loss_nlp_injected_masks(shape):
         mk = [masks[l, c].astype(np.float64) for l in range(3)]
         ref = O.mlp_grad(pc, X, y, mk, alpha)
         for k in KEYS:
-            close(g[k][c], ref[k], what="%s chain %d" % (k, c))
+            err = np.abs(g[k][c] - ref[k]).max() / np.abs(ref[k]).max()
+            print("%s %s chain %d %-6s max err / max|g| = %.2e" % (shape, prec, c, k, err))
+        for k in KEYS:
+            if prec == "fp32":
+                close(g[k][c], ref[k], what="%s chain %d" % (k, c))
+            else:
+                # ReLU kinks: a pre-activation within ~1e-5 of zero can fall on the other side of the gate in
+                # split-bf16 arithmetic, which changes that sample's contribution to one gradient row.  Require
+                # rtol 1e-4 for >= 99.5 % of the entries and cap every entry at 1e-3 of the largest one.
+                r, gk = np.asarray(ref[k], dtype=np.float64), np.asarray(g[k][c], dtype=np.float64)
+                bad = np.abs(gk - r) > 1e-4 * np.abs(r) + 1e-5 * np.abs(r).max()
+                assert bad.mean() <= 5e-3, (k, c, bad.mean())
+                assert np.abs(gk - r).max() <= 1e-3 * np.abs(r).max(), (k, c)
         close(loss[c], O.mlp_loss(pc, X, y, mk), 1e-5)
         close(nlp[c], O.mlp_nlp(pc, X, y, mk, alpha), 1e-5)
 
@@ -57,7 +71,7 @@ def test_mlp_no_dropout_and_philox_dropout_statistics():
     rs = np.random.RandomState(1)
     B, n_in, n_mid, n_out, alpha = 64, 12, 512, 4, 0.0
     par, X, y = make(rs, B, n_in, n_mid, n_out, scale=0.2)
-    m0 = mlp({"alpha": alpha}, n_in, n_mid, n_out, dropout=0.0)
+    m0 = mlp({"alpha": alpha}, n_in, n_mid, n_out, dropout=0.0, precision="bf16x3")
     close(m0.log_likelihood(par, X_train=X, y_train=y), O.mlp_loss(par, X, y, None), 1e-5)
     g0 = m0.grad(par, X_train=X, y_train=y)
     ref = O.mlp_grad(par, X, y, None, alpha)

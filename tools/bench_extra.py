@@ -104,7 +104,8 @@ elif a.what == "mlp":
     n_mid = 512
     h = MlpHandle(ctx, N, D, n_mid, K, 0.01, 0.1, seed=3)
     h.bind(X, y)
-    s = SamplerHandle(ctx, h, KIND["sghmc"], C, seed=1, precision=0, sweep=[(0, h.P)], shared_path=True, sghmc_descent=True)
+    s = SamplerHandle(ctx, h, KIND["sghmc"], C, seed=1, precision=PREC[a.precision], sweep=[(0, h.P)], shared_path=True,
+                      sghmc_descent=True)
     rs = np.random.RandomState(0)
     s.set_q(rs.normal(0, 0.05, (C, h.P)).astype(np.float32))
     eps, path = 1e-3, 5e-3  # E[L] = 5
@@ -119,7 +120,7 @@ elif a.what == "mlp":
     dt, _ = timed(run)
     flops = 6.0 * B * (D * n_mid + n_mid * n_mid + n_mid * K) - 2.0 * B * D * n_mid
     print(json.dumps({"workload": "cfg4 SGHMC MLP 784-512-512-10 dropout 0.1, minibatch 500, %d chains/GPU, joint sweep" % C,
-                      "precision": "fp32 (CUDA cores)", "grad_evals_per_s": n_grad / dt,
+                      "precision": a.precision, "grad_evals_per_s": n_grad / dt,
                       "algorithmic_tflops": n_grad * flops / dt / 1e12, "ms_per_sghmc_step": 1e3 * dt / a.steps}))
 else:
     import ctypes as Ct
