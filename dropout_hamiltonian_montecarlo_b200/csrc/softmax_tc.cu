@@ -558,16 +558,17 @@ static int pick_kp(int K) {
   return 0;
 }
 
-// chains per N tile: BN = cpt*KP must be a multiple of 16 and <= 256; minimise padded work
+// chains per N tile: BN = cpt*KP must be a multiple of 16 and <= 192 (the backward epilogue keeps BN/64 chunks of
+// 16 columns in registers).  Both GEMMs are bound by operand delivery (L2 -> shared memory), so the cost of a
+// tiling is the bytes it streams: every N tile re-reads the 128-row A tile and reads its own BN-row B tile.
 static int pick_cpt(int KP, int C) {
   int unit = 1;
   while ((unit * KP) % 16) ++unit;
   int best = unit;
   double best_cost = 1e30;
-  for (int cpt = unit; cpt * KP <= 192; cpt += unit) {  // 192: the backward epilogue keeps BN/64 chunks in registers
-    int tiles = (C + cpt - 1) / cpt;
-    // padded columns + a small per-tile overhead that favours wide tiles
-    double cost = (double)tiles * cpt * KP * (1.0 + 24.0 / (cpt * KP));
+  for (int cpt = unit; cpt * KP <= 192; cpt += unit) {
+    const int tiles = (C + cpt - 1) / cpt;
+    const double cost = (double)tiles * (BM + cpt * KP + 16);  // +16: per-tile epilogue / scheduling overhead
     if (cost < best_cost - 1e-9) best_cost = cost, best = cpt;
   }
   return best;
@@ -838,11 +839,24 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   b.m_tiles = (int)ceil_div(d.Dt, BM);
   b.n_tiles = n_tiles;
   b.k_chunks = (int)ceil_div(nrows + shift, BK);
-  int tiles = b.m_tiles * b.n_tiles;
-  int want = std::max(1, ctx->sm_count / tiles);
-  want = std::min(want, std::max(1, b.k_chunks / 4));  // keep >= 4 chunks per slab
-  b.chunks_per_split = (int)ceil_div(b.k_chunks, want);
-  b.n_split = (int)ceil_div(b.k_chunks, b.chunks_per_split);
+  // split the contraction (rows) so that one round of work items fills the machine; choose between plain CTAs and
+  // CTA pairs (two N tiles sharing the X^T tile) by the length of the critical path: rounds x chunks per item
+  auto plan = [&](int pair, int* n_split, int* cps) {
+    const int units = pair ? ctx->sm_count / 2 : ctx->sm_count;
+    const int items = b.m_tiles * (pair ? (b.n_tiles + 1) / 2 : b.n_tiles);
+    int want = std::max(1, units / items);
+    want = std::min(want, std::max(1, b.k_chunks / 4));  // keep >= 4 chunks per slab
+    *cps = (int)ceil_div(b.k_chunks, want);
+    *n_split = (int)ceil_div(b.k_chunks, *cps);
+    const int rounds = (int)ceil_div((int64_t)items * *n_split, units);
+    return (double)rounds * *cps * (pair ? 0.97 : 1.0);
+  };
+  int ns0, cps0, ns2, cps2;
+  const double cost0 = plan(0, &ns0, &cps0);
+  const double cost2 = (pairing_enabled() && b.n_tiles >= 2) ? plan(2, &ns2, &cps2) : 1e30;
+  b.pair = cost2 < cost0 ? 2 : 0;
+  b.n_split = b.pair ? ns2 : ns0;
+  b.chunks_per_split = b.pair ? cps2 : cps0;
   // <= 192 MMAs per tensor-core accumulation chain, then round-to-nearest fp32 adds (BHMC_SUB_CHUNKS overrides)
   static int sub_env = -1;
   if (sub_env < 0) {
@@ -855,8 +869,6 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   b.split3 = split3 ? 1 : 0;
   b.a_k0 = (int)(row0 - shift);
   b.a_m0 = 0;
-  // backward: pairs of N tiles share the X^T tile
-  b.pair = (pairing_enabled() && b.n_tiles >= 2 && b.n_split * b.m_tiles * b.n_tiles >= ctx->sm_count / 2) ? 2 : 0;
   const uint32_t bwd_abox = (uint32_t)(b.pair ? BM / 2 : BM);
   int64_t prow = (int64_t)b.m_tiles * BM, pcol = (int64_t)b.n_tiles * BN;
   void* part = nullptr;
