@@ -87,6 +87,43 @@ struct TcParams {
   float* part;                    // [n_split, m_tiles*128, n_tiles*BN]
 };
 
+// ---- cta_group::2 (one MMA spans the two CTAs of a cluster: M = 256, each CTA holds half of the B tile) ----
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the shared::cluster
+// address cleared), data lands in the issuing CTA's own shared memory
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -96,6 +133,85 @@ __device__ __forceinline__ float lg2_approx(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Forward epilogue of one 128 x BN accumulator tile (softmax.py:38-43,52,63-72): thread = row, the EW/4 warps of
+// a TMEM lane quarter split the tile's chains.  Per chain: tcgen05.ld KP columns, + bias, clip, row max, exp2,
+// sum, P - Y split to bf16 hi/lo and stored transposed, z_y - logsumexp warp-reduced into one fp64 red.
+template <int KP, int EW, bool EXACT>
+__device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t tacc, int mt, int nt, int part, int lane,
+                                                  int t) {
+  constexpr int PARTS = EW / 4;
+  const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const int64_t r = (int64_t)mt * BM + t;  // row inside the window
+  const bool valid = r < p.nrows;
+  const int y = valid ? p.labels[r] : -1;
+  const int K = EXACT ? KP : p.K;  // EXACT: no padded classes, every class loop is branch-free
+  for (int cc = part; cc < p.cpt; cc += PARTS) {
+    const int c = nt * p.cpt + cc;
+    if (c >= p.C) break;  // warp-uniform
+    uint32_t raw[KP];
+    tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
+    const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
+    float bv[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
+    tmem_ld_wait();
+    float z[KP];
+    float m = -INFINITY, zy = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      // softmax.py:40-41 clips to [-708.4, 36.04].  The lower clip only matters for the label's logit
+      // (exp(z - max) underflows to 0 in fp32 either way), so it is applied to zy alone below.
+      float v = fminf(__uint_as_float(raw[k]) + bv[k], CLIP_HI);
+      if (!EXACT && k >= K) v = -INFINITY;  // padded classes
+      z[k] = v;
+      m = fmaxf(m, v);
+      zy = (k == y) ? v : zy;
+    }
+    zy = fmaxf(zy, CLIP_LO);
+    if (m < CLIP_LO) {  // every logit below the lower clip (diverged chain): take the slow, literal path
+      m = CLIP_LO;
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+        if (EXACT || k < K) z[k] = CLIP_LO;
+    }
+    float ssum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      z[k] = ex2_approx((z[k] - m) * L2E);  // exp(clip(z) - max); 0 for padded classes
+      ssum += z[k];
+    }
+    const float inv = __fdividef(1.0f, ssum);
+    float ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
+    if (p.write_dm) {
+      const int64_t o = ((int64_t)c * KP) * p.Mpad + p.dm_shift + r;
+      __nv_bfloat16* dh = p.dmt_hi + o;
+      __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        if (EXACT || k < K) {
+          float d = valid ? fmaf(z[k], inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
+          __nv_bfloat16 h = __float2bfloat16_rn(d);
+          *dh = h;
+          if (p.split3) *dl = __float2bfloat16_rn(d - __bfloat162float(h));
+        }
+        dh += p.Mpad;
+        dl += p.Mpad;
+      }
+      if (mt == 0 && t < p.dm_shift) {  // zero the alignment prefix (columns before the window)
+        __nv_bfloat16* zh = p.dmt_hi + ((int64_t)c * KP) * p.Mpad + t;
+        __nv_bfloat16* zl = p.dmt_lo + ((int64_t)c * KP) * p.Mpad + t;
+        for (int k = 0; k < K; ++k) {
+          zh[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
+          if (p.split3) zl[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+    if (lane == 0 && p.debug != 2) atomicAdd(p.loglik + c, (double)ll);
+  }
 }
 
 // EW = number of epilogue warps (multiple of 4).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the
@@ -328,76 +444,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       if (!tile_ok || p.debug == 1 || p.debug == 6 || p.debug == 7 || p.debug >= 9) {
         // nothing to store; only the barrier protocol below
       } else if constexpr (MODE == MODE_FWD) {
-        const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-        const int64_t r = (int64_t)mt * BM + t;  // row inside the window
-        const bool valid = r < p.nrows;
-        const int y = valid ? p.labels[r] : -1;
-        const int K = EXACT ? KP : p.K;  // EXACT: no padded classes, every class loop is branch-free
-        for (int cc = part; cc < p.cpt; cc += PARTS) {
-          const int c = nt * p.cpt + cc;
-          if (c >= p.C) break;  // warp-uniform
-          uint32_t raw[KP];
-          tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
-          const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
-          float bv[KP];
-#pragma unroll
-          for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
-          tmem_ld_wait();
-          float z[KP];
-          float m = -INFINITY, zy = 0.f;
-#pragma unroll
-          for (int k = 0; k < KP; ++k) {
-            // softmax.py:40-41 clips to [-708.4, 36.04].  The lower clip only matters for the label's logit
-            // (exp(z - max) underflows to 0 in fp32 either way), so it is applied to zy alone below.
-            float v = fminf(__uint_as_float(raw[k]) + bv[k], CLIP_HI);
-            if (!EXACT && k >= K) v = -INFINITY;  // padded classes
-            z[k] = v;
-            m = fmaxf(m, v);
-            zy = (k == y) ? v : zy;
-          }
-          zy = fmaxf(zy, CLIP_LO);
-          if (m < CLIP_LO) {  // every logit below the lower clip (diverged chain): take the slow, literal path
-            m = CLIP_LO;
-#pragma unroll
-            for (int k = 0; k < KP; ++k)
-              if (EXACT || k < K) z[k] = CLIP_LO;
-          }
-          float ssum = 0.f;
-#pragma unroll
-          for (int k = 0; k < KP; ++k) {
-            z[k] = ex2_approx((z[k] - m) * L2E);  // exp(clip(z) - max); 0 for padded classes
-            ssum += z[k];
-          }
-          const float inv = __fdividef(1.0f, ssum);
-          float ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
-          if (p.write_dm) {
-            const int64_t o = ((int64_t)c * KP) * p.Mpad + p.dm_shift + r;
-            __nv_bfloat16* dh = p.dmt_hi + o;
-            __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
-#pragma unroll
-            for (int k = 0; k < KP; ++k) {
-              if (EXACT || k < K) {
-                float d = valid ? fmaf(z[k], inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
-                __nv_bfloat16 h = __float2bfloat16_rn(d);
-                *dh = h;
-                if (p.split3) *dl = __float2bfloat16_rn(d - __bfloat162float(h));
-              }
-              dh += p.Mpad;
-              dl += p.Mpad;
-            }
-            if (mt == 0 && t < p.dm_shift) {  // zero the alignment prefix (columns before the window)
-              __nv_bfloat16* zh = p.dmt_hi + ((int64_t)c * KP) * p.Mpad + t;
-              __nv_bfloat16* zl = p.dmt_lo + ((int64_t)c * KP) * p.Mpad + t;
-              for (int k = 0; k < K; ++k) {
-                zh[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
-                if (p.split3) zl[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
-              }
-            }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
-          if (lane == 0 && p.debug != 2) atomicAdd(p.loglik + c, (double)ll);
-        }
+        fwd_epilogue_tile<KP, EW, EXACT>(p, tacc, mt, nt, part, lane, t);
       }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[buf]));
@@ -411,6 +458,144 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward GEMM with cta_group::2: a cluster of two CTAs computes a 256 x BN tile pair per work item.  Each CTA
+// loads its own 128 rows of X (hi, lo) and only HALF of the W tile (BN/2 rows); the leader CTA's elected thread
+// issues tcgen05.mma.cta_group::2 (M = 256), which reads A and the two B halves from both CTAs' shared memory and
+// writes rows 0-127 / 128-255 of the accumulator into the two CTAs' tensor memory.  Per CTA and K chunk this
+// moves 52 KB instead of 72 KB through L2 (the main loop is bound by operand delivery) and leaves room for 4 stages.
+//   full[s]   : leader's barrier, 1 arrival (leader's expect_tx covers both CTAs' bytes; the peer's TMA credits it)
+//   empty[s]  : per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[b]  : per CTA, same multicast; tempty[b]: leader's, 2 x 32 x EW arrivals (peer's threads arrive remotely)
+template <int KP, int EW, bool EXACT>
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
+k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int nmat = p.split3 ? 2 : 1;
+  const int a_bytes = BM * BK * 2, bh_bytes = (p.BN / 2) * BK * 2;  // this CTA's share of the B tile
+  const int stage_bytes = nmat * (a_bytes + bh_bytes);
+  const int m_items = (p.m_tiles + 1) / 2;
+  const int num_work = m_items * p.n_tiles;
+  const int wi0 = blockIdx.x / 2, wi_step = gridDim.x / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 2 * 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // both CTAs' warp 2 take part in the pair-wide allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = wi0; w < num_work; w += wi_step) {
+        const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+        for (int k = 0; k < p.k_chunks; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);  // same offset in the leader CTA
+          if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + nmat * a_bytes;
+          const int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN + rank * (p.BN / 2);
+          tma_load_2d_2sm(sa, &tmA_hi, full, ak, am);
+          if (p.split3) tma_load_2d_2sm(sa + a_bytes, &tmA_lo, full, ak, am);
+          tma_load_2d_2sm(sb, &tmB_hi, full, bk, bn);
+          if (p.split3) tma_load_2d_2sm(sb + bh_bytes, &tmB_lo, full, bk, bn);
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only; warp-uniform loop, elected lane issues) =====
+    if (leader) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = wi0; w < num_work; w += wi_step, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+        for (int k = 0; k < p.k_chunks; ++k) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t first = k > 0 ? 1u : 0u;
+          if (p.split3) {
+            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+            const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + bh_bytes);
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          } else {
+            const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+            }
+          }
+          umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);  // frees the stage in BOTH CTAs
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+        umma_commit_2sm(smem_u32(&bar_tfull[buf]), 3);  // accumulator halves complete in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, each on its own 128 rows) =====
+    const int ew = warp & 3, part = (warp - 4) >> 2;
+    const int t = ew * 32 + lane;
+    int it = 0;
+    for (int w = wi0; w < num_work; w += wi_step, ++it) {
+      const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+      if (mt < p.m_tiles) fwd_epilogue_tile<KP, EW, EXACT>(p, tacc, mt, nt, part, lane, t);
+      tcgen05_fence_before();
+      if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
+      else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -683,10 +868,46 @@ static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
   return BHMC_OK;
 }
 
+template <int KP, int EW, bool EXACT>
+static int launch_fwd2_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                          const CUtensorMap& b_lo, const TcParams& p) {
+  const int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + (p.BN / 2) * BK * 2);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_fwd2<KP, EW, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int work = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int grid = 2 * std::min(work, ctx->sm_count / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NON_EPI_THREADS + 32 * EW);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_fwd2<KP, EW, EXACT>, a_hi, a_lo, b_hi, b_lo, p));
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
 template <int MODE, int KP>
 static int launch_gemm(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                        const CUtensorMap& b_lo, const TcParams& p) {
   const bool exact = p.K == KP;
+  if constexpr (MODE == MODE_FWD) {
+    if (p.pair == 3) {  // cta_group::2 forward
+      if (exact) return launch_fwd2_ew<KP, 16, true>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+      return launch_fwd2_ew<KP, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, p);
+    }
+  }
   if (epilogue_warps() == 8) {
     if (exact) return launch_gemm_ew<MODE, KP, 8, true>(ctx, a_hi, a_lo, b_hi, b_lo, p);
     return launch_gemm_ew<MODE, KP, 8, false>(ctx, a_hi, a_lo, b_hi, b_lo, p);
@@ -750,7 +971,15 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   // ---- forward: Z[rows, C*KP] = Xa[rows, Dp] . Wt^T ----
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   // forward: pairs of M tiles share the W tile (each CTA fetches half of it and multicasts)
-  const int fwd_pair = (pairing_enabled() && Mfwd / BM >= 2 && (Mfwd / BM) * n_tiles >= ctx->sm_count) ? 1 : 0;
+  // forward CTA pairing: 3 = cta_group::2 MMA (each CTA stores half of the W tile), 1 = two independent MMAs sharing
+  // the W tile by TMA multicast, 0 = single CTAs.  BHMC_FWD2=0 falls back from 3 to 1.
+  static int fwd2 = -1;
+  if (fwd2 < 0) {
+    const char* e = getenv("BHMC_FWD2");
+    fwd2 = e ? atoi(e) : 1;
+  }
+  const bool big = pairing_enabled() && Mfwd / BM >= 2 && (Mfwd / BM) * n_tiles >= ctx->sm_count;
+  const int fwd_pair = big ? (fwd2 ? 3 : 1) : 0;
   const uint32_t fwd_bbox = (uint32_t)(fwd_pair ? BN / 2 : BN);
   BHMC_TRY(make_map(&a_hi, d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
   BHMC_TRY(make_map(&b_hi, wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
@@ -769,7 +998,8 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.chunks_per_split = p.k_chunks;
   p.sub_chunks = p.k_chunks;  // forward: K = D is short (13 chunks at D=784), one accumulation chain
   p.BN = BN;
-  p.stages = stages;
+  p.stages = fwd_pair == 3 ? std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / (nmat * (BM * BK * 2 + (BN / 2) * BK * 2)))))
+                           : stages;
   p.split3 = split3 ? 1 : 0;
   p.a_k0 = 0;
   p.a_m0 = (int)row0;
