@@ -39,6 +39,11 @@ WORKLOADS = {
     # name: N, D, K, chains per GPU, eps, path_length
     "cfg2": dict(N=60000, D=784, K=10, C=64, eps=1e-4, path=1e-2, alpha=0.01,
                  desc="HMC softmax 60000x784x10 full batch, 64 chains/GPU"),
+    # BASELINE configs[4] (rows shard over GPUs; the 1-GPU shapes are profiling targets of tools/profile_grad.py)
+    "cfg5": dict(N=1000000, D=2048, K=38, C=8, eps=1e-7, path=1e-6, alpha=0.01,
+                 desc="HMC softmax 1000000x2048x38 full batch, 8 chains"),
+    "cfg5-half": dict(N=500000, D=2048, K=38, C=8, eps=1e-7, path=1e-6, alpha=0.01,
+                      desc="HMC softmax 500000x2048x38 full batch, 8 chains (one of two row shards)"),
     "cfg2-small": dict(N=2048, D=784, K=10, C=16, eps=1e-4, path=2e-3, alpha=0.01,
                        desc="HMC softmax 2048x784x10 (debug size)"),
 }
@@ -111,6 +116,21 @@ def peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops_sustained", 1400.8), d.get("hbm_gbs", 6552.3), "measured"
     return 1400.0, 6650.0, "fallback"
+
+
+def ncu_traffic(kernel, prec, wl, chains_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json; captured at full launches of the cfg2 workload).
+    Returned only when the timed launches are the captured shape (same workload, precision, all chains)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t["%s/%s/%s" % (wl["desc"], prec, kernel)]
+        if abs(chains_per_launch - e["chains_per_launch"]) < 0.5:
+            return e["dram_bytes"], e["source"]
+        return None, "ncu capture is of a full %d-chain launch; this run averaged %.1f chains per launch" % (
+            e["chains_per_launch"], chains_per_launch)
+    except Exception:
+        return None, "no ncu capture for this workload/precision"
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -249,6 +269,7 @@ def run_ours(args, wl):
     ctx.timing(False)
     launches = ctx.launches - launches0
     clk = clocks.stop()
+    n_launched_local = float(n_launched)  # chain-gradient evaluations this rank's GEMM launches processed
     stats = torch.tensor([ms, float(n_applied), float(n_launched)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
@@ -325,12 +346,17 @@ def run_ours(args, wl):
 
     if rank == 0:
         peak_tf, peak_bw, src = peaks()
-        flops_fwd = 2.0 * N * D * K * C  # algorithmic flops of one forward launch (all chains)
-        avg_fwd = (t_fwd / max(1, n_fwd)) * 1e-3
-        avg_bwd = (t_bwd / max(1, n_bwd)) * 1e-3
+        # Algorithmic work of the dominant GEMM over the timed region: 2*N*D*K flops per chain-gradient evaluation
+        # and per GEMM (4*N*D*K for forward + backward).  Ragged trajectories make the launches
+        # process between 1 and C chains, so the figure is total flops / total kernel time, not a full-launch
+        # figure divided by the mean duration.
+        flops_eval = 2.0 * N * D * K
         dom = "fwd" if t_fwd >= t_bwd else "bwd"
-        avg = avg_fwd if dom == "fwd" else avg_bwd
-        achieved = flops_fwd / avg / 1e12 if avg > 0 else 0.0
+        t_dom, n_dom = (t_fwd, n_fwd) if dom == "fwd" else (t_bwd, n_bwd)
+        avg = (t_dom / max(1, n_dom)) * 1e-3
+        flops_launch = flops_eval * n_launched_local / max(1, n_dom)
+        achieved = flops_launch / avg / 1e12 if avg > 0 else 0.0
+        traffic, traffic_src = ncu_traffic(dom, prec, wl, n_launched_local / max(1, n_dom))
         mma_mult = 3.0 if prec == "bf16x3" else 1.0
         cpu = None if args.no_cpu_baseline else cpu_reference_rate(wl)
         line = {
@@ -345,8 +371,9 @@ def run_ours(args, wl):
                        "l2": "inputs larger than L2 (X 94-376 MB + (P-Y)^T 77-245 MB per evaluation)",
                        "grad_evals_launched_incl_masked": n_launched},
             "roofline": {"bound": "tensor", "kernel": "k_tc_gemm<%s>" % dom, "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": src,
-                         "algorithmic_flops_per_launch": flops_fwd, "avg_launch_ms": avg * 1e3,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": src, "algorithmic_flops_per_launch": flops_launch,
+                         "chains_per_launch_mean": n_launched_local / max(1, n_dom), "avg_launch_ms": avg * 1e3,
                          "mma_flops_issued_over_algorithmic": mma_mult,
                          "group_ms": {"fwd": t_fwd, "bwd": t_bwd, "prep": t_prep, "update": t_upd, "step_total": ms}},
             "gpu_launches": int(launches), "clocks": clk,
