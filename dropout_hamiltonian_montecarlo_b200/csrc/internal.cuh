@@ -220,10 +220,14 @@ struct SoftmaxData {
   // tensor-core operand copies (built by tc_bind): bf16 hi / lo
   int Kp = 0;                       // classes padded per chain (even)
   int64_t Dp = 0;                   // feature stride of Xa (multiple of 8 elements)
-  int64_t Npad = 0;                 // row stride of Xt (multiple of 8 elements)
+  int64_t Npad = 0;                 // rows covered by the Xt slabs (n_slabs * slab)
+  int64_t slab = 0;                 // rows of X per Xt slab (multiple of 64)
+  int64_t slab_ld = 0;              // row stride of an Xt slab: slab + 64 (a power-of-two stride would map the 128
+                                    // rows of a tile onto the same L2 sets)
+  int64_t Dt_pad = 0;               // Xt rows per slab (D+1 rounded up to the 128-row tile, zero filled)
   void* Xa_hi = nullptr;            // [N, Dp]   K-major A of the forward GEMM
   void* Xa_lo = nullptr;
-  void* Xt_hi = nullptr;            // [Dt, Npad] K-major A of the backward GEMM (row D = ones)
+  void* Xt_hi = nullptr;            // [Npad/slab][Dt_pad, slab] K-major A of the backward GEMM (row D = ones)
   void* Xt_lo = nullptr;
   int64_t Dt = 0;                   // D+1 rows (ones row feeds the bias gradient)
   bool has_lo = false;

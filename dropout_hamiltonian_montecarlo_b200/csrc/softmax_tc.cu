@@ -8,9 +8,12 @@
 //
 // Layout in HBM (all bf16 operands are "K-major": the contraction index is contiguous)
 //   Xa_{hi,lo} [N, Dp]        forward A, built once at bind time   (Dp = D rounded up to 8)
-//   Xt_{hi,lo} [D+1, Npad]    backward A = X^T plus a row of ones that yields the bias gradient
+//   Xt_{hi,lo} [Npad/S][Dt_pad, S]  backward A = X^T plus a row of ones that yields the bias gradient, stored in
+//                             slabs of S = 8192 rows of X: a CTA walking the contraction index stays inside one
+//                             (D+1) x 16 KB slab instead of touching a different 2 MB page per feature row
 //   Wt_{hi,lo} [C*KP, Dp]     forward B, rebuilt from the fp32 chain state before every evaluation
-//   DmT_{hi,lo}[C*KP, Mpad]   (P - Y)^T written by the forward epilogue, backward B
+//   DmT_{hi,lo}[slabs][Nt*BN, Sd]  (P - Y)^T written by the forward epilogue, backward B; same slab scheme as Xt
+//                             (Sd = 8192 window rows per slab; one slab for minibatch-sized windows)
 //   part [S, Mt*128, Nt*BN]   fp32 split-K partials of the backward GEMM (deterministic reduce)
 // bf16x3: every fp32 value v is split v = hi + lo (two bf16); a product uses 3 MMAs
 // (hi*hi + hi*lo + lo*hi) accumulated in fp32, which restores ~fp32 accuracy.
@@ -66,6 +69,10 @@ struct TcParams {
   int stages;
   int split3;                     // 1: hi/lo operands, 3 MMAs per product
   int a_k0, a_m0;                 // coordinate offsets of A in its tensor map (contraction, row)
+  int b_slab, b_slab_rows;        // same for B
+  int hint_a, hint_b;             // L2 eviction priority of the operand streams (make_l2_policy)
+  int a_slab, a_slab_rows;        // backward A is stored in slabs of a_slab contraction indices (0 = plain matrix):
+                                  // element (m, k) lives at row (k / a_slab) * a_slab_rows + m, column k % a_slab
   int pair;                       // CTA pairs (cluster of 2) sharing one operand through TMA multicast:
                                   // 0 = off, 1 = two M tiles share the B tile, 2 = two N tiles share the A tile
   // forward epilogue
@@ -75,8 +82,10 @@ struct TcParams {
   const float* q;                 // bias lives at q[c*ld + D*K + k]
   const int32_t* labels;          // already offset to the row window
   int64_t nrows;
-  int64_t Mpad;                   // row stride of DmT
-  int dm_shift;                   // DmT column of window row 0 (row0 % 8: TMA needs 16 B aligned inner coordinates)
+  int dm_slab, dm_slab_rows;      // DmT slabs: window column j of row i lives at row (j / dm_slab) * dm_slab_rows + i,
+  int dm_ld;                      // column j % dm_slab; row stride dm_ld = dm_slab + 64 (not a power of two)
+  int dm_tail;                    // columns after the last written row that the backward's last chunk still reads
+  int dm_shift;                   // DmT column of window row 0 (row0 % BK: backward chunks start on absolute multiples of BK)
   __nv_bfloat16* dmt_hi;
   __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
   double* loglik;
@@ -147,6 +156,9 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
   const bool valid = r < p.nrows;
   const int y = valid ? p.labels[r] : -1;
   const int K = EXACT ? KP : p.K;  // EXACT: no padded classes, every class loop is branch-free
+  // DmT position of this thread's row (chain-independent part): slab, column inside the slab
+  const int dm_col = p.dm_shift + (int)r, dm_sl = dm_col / p.dm_slab;
+  const int64_t dm_off = (int64_t)dm_sl * p.dm_slab_rows * p.dm_ld + (dm_col - dm_sl * p.dm_slab);
   for (int cc = part; cc < p.cpt; cc += PARTS) {
     const int c = nt * p.cpt + cc;
     if (c >= p.C) break;  // warp-uniform
@@ -185,7 +197,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
     const float inv = __fdividef(1.0f, ssum);
     float ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
     if (p.write_dm) {
-      const int64_t o = ((int64_t)c * KP) * p.Mpad + p.dm_shift + r;
+      const int64_t o = dm_off + (int64_t)c * KP * p.dm_ld;
       __nv_bfloat16* dh = p.dmt_hi + o;
       __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
 #pragma unroll
@@ -196,15 +208,20 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
           *dh = h;
           if (p.split3) *dl = __float2bfloat16_rn(d - __bfloat162float(h));
         }
-        dh += p.Mpad;
-        dl += p.Mpad;
+        dh += p.dm_ld;
+        dl += p.dm_ld;
       }
-      if (mt == 0 && t < p.dm_shift) {  // zero the alignment prefix (columns before the window)
-        __nv_bfloat16* zh = p.dmt_hi + ((int64_t)c * KP) * p.Mpad + t;
-        __nv_bfloat16* zl = p.dmt_lo + ((int64_t)c * KP) * p.Mpad + t;
+      // zero what the backward chunks read but no row writes: the alignment prefix (columns before the window) and
+      // the columns between the last tile row and the end of the last BK-chunk
+      int zc = -1;
+      if (mt == 0 && t < p.dm_shift) zc = t;  // dm_shift, dm_tail < 64: threads 0..63 / 64..127 of the tile
+      else if (mt == p.m_tiles - 1 && t >= 64 && t - 64 < p.dm_tail) zc = p.dm_shift + p.m_tiles * BM + (t - 64);
+      if (zc >= 0) {
+        const int zs = zc / p.dm_slab;
+        const int64_t zo = (zs * p.dm_slab_rows + (int64_t)c * KP) * p.dm_ld + (zc - zs * p.dm_slab);
         for (int k = 0; k < K; ++k) {
-          zh[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
-          if (p.split3) zl[(int64_t)k * p.Mpad] = __float2bfloat16_rn(0.f);
+          p.dmt_hi[zo + (int64_t)k * p.dm_ld] = __float2bfloat16_rn(0.f);
+          if (p.split3) p.dmt_lo[zo + (int64_t)k * p.dm_ld] = __float2bfloat16_rn(0.f);
         }
       }
     }
@@ -269,6 +286,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_a = make_l2_policy(p.hint_a), pol_b = make_l2_policy(p.hint_b);
       for (int w = wi0; w < num_work && p.debug != 9 && p.debug != 10; w += wi_step) {
         BHMC_DECODE_WORK(w)
         int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
@@ -285,21 +303,31 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           uint32_t sa = smem_base + stage * stage_bytes;  // [A_hi | A_lo | B_hi | B_lo]
           uint32_t sb = sa + nmat * a_bytes;
           int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN;
+          if (p.a_slab) {  // chunks never straddle a slab: a_k0 and a_slab are multiples of BK
+            const int sl = ak / p.a_slab;
+            ak -= sl * p.a_slab;
+            am += sl * p.a_slab_rows;
+          }
+          if (p.b_slab) {
+            const int sl = bk / p.b_slab;
+            bk -= sl * p.b_slab;
+            bn += sl * p.b_slab_rows;
+          }
           if (p.pair == 2) {  // A tile shared by the pair: each CTA fetches 64 of its 128 rows for both
             uint32_t off = (uint32_t)rank * (BM / 2) * (BK * 2);
-            tma_load_2d_mc(sa + off, &tmA_hi, full, ak, am + rank * (BM / 2), 3);
-            if (p.split3) tma_load_2d_mc(sa + a_bytes + off, &tmA_lo, full, ak, am + rank * (BM / 2), 3);
+            tma_load_2d_mc_hint(sa + off, &tmA_hi, full, ak, am + rank * (BM / 2), 3, pol_a);
+            if (p.split3) tma_load_2d_mc_hint(sa + a_bytes + off, &tmA_lo, full, ak, am + rank * (BM / 2), 3, pol_a);
           } else {
-            tma_load_2d(sa, &tmA_hi, full, ak, am);
-            if (p.split3) tma_load_2d(sa + a_bytes, &tmA_lo, full, ak, am);
+            tma_load_2d_hint(sa, &tmA_hi, full, ak, am, pol_a);
+            if (p.split3) tma_load_2d_hint(sa + a_bytes, &tmA_lo, full, ak, am, pol_a);
           }
           if (p.pair == 1) {  // B tile shared by the pair: each CTA fetches BN/2 of its rows for both
             uint32_t off = (uint32_t)rank * (p.BN / 2) * (BK * 2);
-            tma_load_2d_mc(sb + off, &tmB_hi, full, bk, bn + rank * (p.BN / 2), 3);
-            if (p.split3) tma_load_2d_mc(sb + b_bytes + off, &tmB_lo, full, bk, bn + rank * (p.BN / 2), 3);
+            tma_load_2d_mc_hint(sb + off, &tmB_hi, full, bk, bn + rank * (p.BN / 2), 3, pol_b);
+            if (p.split3) tma_load_2d_mc_hint(sb + b_bytes + off, &tmB_lo, full, bk, bn + rank * (p.BN / 2), 3, pol_b);
           } else {
-            tma_load_2d(sb, &tmB_hi, full, bk, bn);
-            if (p.split3) tma_load_2d(sb + b_bytes, &tmB_lo, full, bk, bn);
+            tma_load_2d_hint(sb, &tmB_hi, full, bk, bn, pol_b);
+            if (p.split3) tma_load_2d_hint(sb + b_bytes, &tmB_lo, full, bk, bn, pol_b);
           }
           if (++stage == p.stages) stage = 0, phase ^= 1u;
         }
@@ -620,8 +648,9 @@ __global__ void k_split_rows(const float* __restrict__ X, int64_t N, int D, int6
   }
 }
 
-// Xt[d, n] = split(X[n, d]) for d < D ; Xt[D, n] = 1 ; zero padding n in [N, Npad)
-__global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D, int64_t Npad,
+// Xt slab s = n / S holds Xt[d, n % S] = split(X[n, d]) for d < D and Xt[D, n % S] = 1; everything else (rows
+// D+1..Dt_pad-1, columns of rows n >= N) stays zero from the memset at bind time
+__global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D, int64_t S, int64_t ld, int64_t Dt_pad,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float tile[32][33];
   int64_t n0 = (int64_t)blockIdx.x * 32;
@@ -637,11 +666,12 @@ __global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D,
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int d = d0 + i;
     int64_t n = n0 + threadIdx.x;
-    if (d <= D && n < Npad) {
+    if (d <= D && n < N) {
       __nv_bfloat16 h, l;
       split_bf16(tile[threadIdx.x][i], h, l);
-      hi[(int64_t)d * Npad + n] = h;
-      if (lo) lo[(int64_t)d * Npad + n] = l;
+      const int64_t o = ((n / S) * Dt_pad + d) * ld + n % S;
+      hi[o] = h;
+      if (lo) lo[o] = l;
     }
   }
 }
@@ -766,15 +796,19 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
     return BHMC_ERR_UNSUPPORTED;
   }
   // re-binding the same shape (fresh host data every step) reuses the operand buffers
-  const bool reuse = d.Xa_hi && d.Kp == kp && d.Dp == round_up(d.D, dp_align()) && d.Npad == round_up(d.N, 8) &&
-                     d.Dt == d.D + 1 && (d.has_lo || !want_lo);
+  const int64_t slab = std::min<int64_t>(8192, round_up(d.N, 64));
+  const bool reuse = d.Xa_hi && d.Kp == kp && d.Dp == round_up(d.D, dp_align()) && d.slab == slab &&
+                     d.Npad == round_up(d.N, slab) && d.Dt == d.D + 1 && (d.has_lo || !want_lo);
   if (!reuse) {
     tc_softmax_release(d);
     d.Kp = kp;
     d.Dp = round_up(d.D, dp_align());
-    d.Npad = round_up(d.N, 8);
+    d.slab = slab;
+    d.slab_ld = slab + 64;
+    d.Npad = round_up(d.N, slab);
     d.Dt = d.D + 1;
-    size_t a_bytes = (size_t)d.N * d.Dp * 2, t_bytes = (size_t)d.Dt * d.Npad * 2;
+    d.Dt_pad = round_up(d.Dt, BM);
+    size_t a_bytes = (size_t)d.N * d.Dp * 2, t_bytes = (size_t)d.Dt_pad * (d.Npad / d.slab) * d.slab_ld * 2;
     BHMC_CUDA_OK(cudaMalloc(&d.Xa_hi, a_bytes));
     BHMC_CUDA_OK(cudaMalloc(&d.Xt_hi, t_bytes));
     if (want_lo) {
@@ -796,8 +830,11 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
     }
   }
   {
-    dim3 grid((unsigned)ceil_div(d.Npad, 32), (unsigned)ceil_div(d.Dt, 32));
-    k_split_transpose<<<grid, dim3(32, 8), 0, ctx->stream>>>(d.X, d.N, d.D, d.Npad, (__nv_bfloat16*)d.Xt_hi,
+    const size_t t_bytes = (size_t)d.Dt_pad * (d.Npad / d.slab) * d.slab_ld * 2;
+    BHMC_CUDA_OK(cudaMemsetAsync(d.Xt_hi, 0, t_bytes, ctx->stream));
+    if (want_lo) BHMC_CUDA_OK(cudaMemsetAsync(d.Xt_lo, 0, t_bytes, ctx->stream));
+    dim3 grid((unsigned)ceil_div(d.N, 32), (unsigned)ceil_div(d.Dt, 32));
+    k_split_transpose<<<grid, dim3(32, 8), 0, ctx->stream>>>(d.X, d.N, d.D, d.slab, d.slab_ld, d.Dt_pad, (__nv_bfloat16*)d.Xt_hi,
                                                              want_lo ? (__nv_bfloat16*)d.Xt_lo : nullptr);
     ctx->launches++;
   }
@@ -937,8 +974,21 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const int n_tiles = (int)ceil_div(C, cpt);
   const int64_t ncols = (int64_t)C * KP;  // rows of Wt / DmT
   const int64_t Mfwd = round_up(nrows, BM);          // rows covered by the forward tiles
-  const int shift = (int)(row0 % 8);                 // TMA inner coordinates must be 16 B aligned (8 bf16)
-  const int64_t Mpad = round_up(Mfwd + shift, 8);    // row stride of DmT
+  // The backward contraction index is the absolute row: its BK-chunks must start on multiples of BK so that no
+  // chunk straddles two Xt slabs (and TMA inner coordinates must be 16 B aligned anyway), hence (P-Y)^T is
+  // written `shift` columns to the right
+  const int shift = (int)(row0 % BK);
+  const int dm_tail = (BK - shift) % BK;             // columns the last backward chunk reads past the last tile row
+  const int64_t dm_cols = Mfwd + BK;                 // >= shift + Mfwd + dm_tail
+  static int64_t dm_slab_max = 0;  // BHMC_DM_SLAB overrides the slab width (A/B measurements; multiple of 64)
+  if (!dm_slab_max) {
+    const char* e = getenv("BHMC_DM_SLAB");
+    dm_slab_max = e ? std::max<int64_t>(64, round_up(atoll(e), 64)) : 8192;
+  }
+  const int64_t dm_slab = std::min<int64_t>(dm_slab_max, dm_cols);  // multiple of 64 either way
+  const int64_t dm_nslab = ceil_div(dm_cols, dm_slab), dm_ld = dm_slab + 64;
+  const int64_t dm_rows = (int64_t)n_tiles * BN;     // rows per slab (>= C*KP; the padding rows are never written
+                                                     // and only feed accumulator columns nobody reads)
   const int64_t P = (int64_t)(D + 1) * K;
   const int nmat = split3 ? 2 : 1;
   const int stage_bytes = nmat * (BM * BK * 2 + BN * BK * 2);
@@ -960,7 +1010,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   }
 
   void* dmt = nullptr;
-  size_t dmt_bytes = (size_t)ncols * Mpad * 2;
+  size_t dmt_bytes = (size_t)(dm_nslab * dm_rows * dm_ld) * 2;
   __nv_bfloat16 *dmt_hi = nullptr, *dmt_lo = nullptr;
   if (g) {
     BHMC_TRY(ctx->get_scratch(2, dmt_bytes * 2, &dmt));
@@ -1012,7 +1062,10 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.q = q;
   p.labels = d.labels + row0;
   p.nrows = nrows;
-  p.Mpad = Mpad;
+  p.dm_slab = (int)dm_slab;
+  p.dm_ld = (int)dm_ld;
+  p.dm_slab_rows = (int)dm_rows;
+  p.dm_tail = dm_tail;
   p.dm_shift = shift;
   p.dmt_hi = dmt_hi;
   p.dmt_lo = dmt_lo;
@@ -1099,17 +1152,34 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   b.split3 = split3 ? 1 : 0;
   b.a_k0 = (int)(row0 - shift);
   b.a_m0 = 0;
+  // L2 priorities: an operand tile is re-read by every work item that shares it.  (P-Y)^T tiles are re-read by all
+  // m_tiles row tiles of X^T -- at N = 1e6 they were evicted by the X^T stream and re-fetched from HBM 17 times.
+  static int l2hint = -1;
+  if (l2hint < 0) {
+    const char* e = getenv("BHMC_L2HINT");
+    l2hint = e ? atoi(e) : 1;
+  }
+  if (l2hint) {
+    const int a_reuse = b.pair == 2 ? (b.n_tiles + 1) / 2 : b.n_tiles, b_reuse = b.m_tiles;
+    b.hint_a = a_reuse <= 1 ? 1 : 0;
+    b.hint_b = b_reuse >= 4 ? 2 : 0;
+  }
+  b.b_slab = (int)dm_slab;
+  b.b_slab_rows = (int)dm_rows;
+  b.a_slab = (int)d.slab;
+  b.a_slab_rows = (int)d.Dt_pad;
   const uint32_t bwd_abox = (uint32_t)(b.pair ? BM / 2 : BM);
   int64_t prow = (int64_t)b.m_tiles * BM, pcol = (int64_t)b.n_tiles * BN;
   void* part = nullptr;
   BHMC_TRY(ctx->get_scratch(3, sizeof(float) * (size_t)b.n_split * prow * pcol, &part));
   b.part = (float*)part;
-  BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, bwd_abox));
-  // inner extent = written columns only: anything beyond is zero-filled by TMA
-  BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)(Mfwd + shift), (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
+  const uint64_t xt_rows = (uint64_t)(d.Npad / d.slab) * d.Dt_pad;
+  BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, bwd_abox));
+  // every column a backward chunk reads is written by the forward epilogue (rows, alignment prefix, tail)
+  BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
   if (split3) {
-    BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.Npad, (uint64_t)d.Dt, (uint64_t)d.Npad, bwd_abox));
-    BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)(Mfwd + shift), (uint64_t)ncols, (uint64_t)Mpad, (uint32_t)BN));
+    BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, bwd_abox));
+    BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
   } else {
     a_lo = a_hi;
     b_lo = b_hi;

@@ -53,6 +53,34 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
+// L2 eviction-priority policies for operand streams: 1 = evict_first (read once), 2 = evict_last (re-read by many
+// CTAs), anything else = evict_normal
+__device__ __forceinline__ uint64_t make_l2_policy(int kind) {
+  uint64_t pol;
+  if (kind == 1)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2)
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                    uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5, %6;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
