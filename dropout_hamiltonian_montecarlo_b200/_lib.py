@@ -48,6 +48,7 @@ class SgRun(C.Structure):
         ("step_size", C.c_double), ("gamma", C.c_double), ("step0", C.c_int64),
         ("z_dev", C.c_void_p), ("samples_dev", C.c_void_p), ("logp_dev", C.c_void_p),
         ("n_grad_evals", C.c_int64), ("final_step_size", C.c_double),
+        ("dropout_keep", C.c_double), ("mask_dev", C.c_void_p),
     ]
 
 
@@ -63,6 +64,7 @@ _PROTOS = {
     "bhmc_ctx_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "bhmc_softmax_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32,
                                       C.POINTER(C.c_void_p)]),
+    "bhmc_logistic_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.POINTER(C.c_void_p)]),
     "bhmc_softmax_bind_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "bhmc_softmax_bind_data_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "bhmc_mvn_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_void_p)]),

@@ -183,8 +183,52 @@ struct bhmc_model {
 
 namespace bhmc {
 
+// logistic regression (models/cpu/logistic.py) rides on the softmax kernels: sigmoid(z) is the class-1 probability of
+// a two-class softmax whose class-0 weights and bias are pinned to zero.  The chain state keeps the reference layout
+// (weights[D], bias) and is expanded to / contracted from the two-class layout around every evaluation.
+__global__ void k_logistic_expand(const float* __restrict__ q, int64_t ld, int D, float* __restrict__ q2, int64_t ld2) {
+  const int c = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into the two-class row
+  if (i >= ld2) return;
+  float v = 0.f;
+  if ((i & 1) && (i >> 1) <= D) v = q[(int64_t)c * ld + (i >> 1)];  // weights[d,1] = w[d]; bias[1] = b
+  q2[(int64_t)c * ld2 + i] = v;
+}
+__global__ void k_logistic_contract(const float* __restrict__ g2, int64_t ld2, int D, float* __restrict__ g, int64_t ld) {
+  const int c = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  g[(int64_t)c * ld + i] = i <= D ? g2[(int64_t)c * ld2 + 2 * i + 1] : 0.f;
+}
+
+// Xb[r, j] = X[row0 + r, j] * keep(r, j): the masked minibatch of sgd.fit_dropout (sgd.py:60-61)
+__global__ void k_input_dropout(const float* __restrict__ X, int D, int64_t n, const uint8_t* __restrict__ mask, float keep,
+                                uint64_t seed, uint32_t stream, float* __restrict__ out) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float k[4];
+  if (mask) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) k[j] = (i4 + j < n && mask[i4 + j]) ? 1.f : 0.f;
+  } else {
+    U4 c{(uint32_t)(i4 >> 2), (uint32_t)((uint64_t)i4 >> 34), stream, TAG_DROPOUT | 0x800000u};
+    U4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    k[0] = u01_open(r.x) < keep ? 1.f : 0.f;
+    k[1] = u01_open(r.y) < keep ? 1.f : 0.f;
+    k[2] = u01_open(r.z) < keep ? 1.f : 0.f;
+    k[3] = u01_open(r.w) < keep ? 1.f : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i4 + j < n) out[i4 + j] = X[i4 + j] * k[j];
+}
+
 struct SoftmaxModel : ModelBase {
   SoftmaxData d;
+  SoftmaxData db;            // masked-minibatch view used by grad_input_dropout (owns its operand copies)
+  float* Xb = nullptr;       // [batch, D] fp32 masked rows
+  int64_t Xb_rows = 0;
+  bool logistic = false;
   float alpha = 0.f;
   int prior = BHMC_PRIOR_CPU;
   float* X_owned = nullptr;
@@ -192,14 +236,61 @@ struct SoftmaxModel : ModelBase {
 
   ~SoftmaxModel() override {
     tc_softmax_release(d);
+    tc_softmax_release(db);
+    cudaFree(Xb);
     cudaFree(X_owned);
     cudaFree(y_owned);
   }
   int64_t default_rows() const override { return d.N; }
+  int64_t n_features() const override { return d.D; }
   int64_t global_rows = 0;
   float alpha_energy = -1.f;  // alpha of the log-prior constant when it differs from the gradient's (row shards)
 
   int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) override {
+    if (logistic) {
+      const int64_t ld2 = round_up(2 * ((int64_t)d.D + 1), 4);
+      void* buf = nullptr;
+      BHMC_TRY(ctx->get_scratch(7, sizeof(float) * 2 * (size_t)C * ld2, &buf));
+      float* q2 = (float*)buf;
+      float* g2 = g ? q2 + (size_t)C * ld2 : nullptr;
+      k_logistic_expand<<<dim3((unsigned)ceil_div(ld2, 256), C), 256, 0, ctx->stream>>>(q, ld, d.D, q2, ld2);
+      ctx->launches++;
+      BHMC_TRY(grad_softmax(q2, C, ld2, row0, nrows, prec, g2, stat));
+      if (g) {
+        k_logistic_contract<<<dim3((unsigned)ceil_div(ld, 256), C), 256, 0, ctx->stream>>>(g2, ld2, d.D, g, ld);
+        ctx->launches++;
+      }
+      BHMC_CUDA_OK(cudaGetLastError());
+      return BHMC_OK;
+    }
+    return grad_softmax(q, C, ld, row0, nrows, prec, g, stat);
+  }
+  int grad_input_dropout(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g,
+                         double* stat, const uint8_t* mask, float keep, uint64_t seed, uint32_t stream) override {
+    BHMC_CHECK_ARG(row0 >= 0 && nrows > 0 && row0 + nrows <= d.N, "row window outside the bound rows");
+    if (Xb_rows < nrows) {
+      cudaFree(Xb);
+      Xb = nullptr;
+      BHMC_CUDA_OK(cudaMalloc(&Xb, sizeof(float) * (size_t)nrows * d.D));
+      Xb_rows = nrows;
+    }
+    const int64_t n = nrows * d.D;
+    k_input_dropout<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, ctx->stream>>>(d.X + row0 * d.D, d.D, n, mask, keep,
+                                                                                   seed, stream, Xb);
+    ctx->launches++;
+    BHMC_CUDA_OK(cudaGetLastError());
+    db.N = nrows;
+    db.D = d.D;
+    db.K = d.K;
+    db.X = Xb;
+    db.labels = d.labels + row0;
+    if (prec != BHMC_PREC_FP32) BHMC_TRY(tc_softmax_bind(ctx, db, prec == BHMC_PREC_BF16X3));
+    std::swap(d, db);  // evaluate on the masked view through the ordinary (logistic-aware) path
+    const int rc = grad(q, C, ld, 0, nrows, prec, g, stat);
+    std::swap(d, db);
+    return rc;
+  }
+  int grad_softmax(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) {
     switch (prec) {
       case BHMC_PREC_FP32: return simt_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat);
       case BHMC_PREC_BF16X3: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, true);
@@ -215,7 +306,11 @@ struct SoftmaxModel : ModelBase {
     double lp = 0.0;
     for (int v = 0; v < n_vars; ++v) {
       cv[v] = 0.0;
-      if (prior == BHMC_PRIOR_CPU)  // softmax.py:22-30: -(dim/2 log 2pi - dim/2 log alpha)
+      const double al = (double)(alpha_energy > 0.f ? alpha_energy : alpha);
+      if (logistic) {  // logistic.py:15-21: dim/2 log(alpha/2pi) - alpha/2 |theta_v|^2
+        lp += 0.5 * (double)var_len[v] * std::log(al / (2.0 * M_PI));
+        cv[v] = 0.5 * al / (double)nrows;
+      } else if (prior == BHMC_PRIOR_CPU)  // softmax.py:22-30: -(dim/2 log 2pi - dim/2 log alpha)
         lp -= 0.5 * (double)var_len[v] * std::log(2.0 * M_PI) - 0.5 * (double)var_len[v] * std::log((double)(alpha_energy > 0.f ? alpha_energy : alpha));
       else  // models/gpu/softmax.py:29-39: -alpha/2 |theta_v|^2 / dim_v
         cv[v] = 0.5 * (double)(alpha_energy > 0.f ? alpha_energy : alpha) / ((double)var_len[v] * (double)nrows);
@@ -287,6 +382,17 @@ int bhmc_softmax_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_features, int32
   bhmc_model* h = new bhmc_model();
   h->impl = m;
   *out = h;
+  return BHMC_OK;
+}
+
+int bhmc_logistic_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_features, float alpha, bhmc_model** out) {
+  BHMC_TRY(bhmc_softmax_create(ctx, n_rows, n_features, 2, alpha, BHMC_PRIOR_CPU, out));
+  auto* m = static_cast<SoftmaxModel*>((*out)->impl);
+  m->logistic = true;
+  m->P = (int64_t)n_features + 1;
+  m->var_len[0] = n_features;
+  m->var_off[1] = n_features;
+  m->var_len[1] = 1;
   return BHMC_OK;
 }
 
@@ -843,7 +949,14 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
     const bool sampling = e >= run->burnin;
     for (int64_t j = 0; j < nb; ++j, ++k) {
       const int64_t row0 = j * run->batch_size;
-      BHMC_TRY(s->eval(s->q, C, row0, run->batch_size, s->g, stat));
+      if (run->dropout_keep > 0.0) {
+        BHMC_CHECK_ARG(sgd && !s->hook, "input dropout is sgd.fit_dropout only (single GPU)");
+        const uint8_t* mk = run->mask_dev ? run->mask_dev + (size_t)k * run->batch_size * mb->n_features() : nullptr;
+        BHMC_TRY(mb->grad_input_dropout(s->q, C, ld, row0, run->batch_size, cfg.precision, s->g, stat, mk,
+                                        (float)run->dropout_keep, cfg.seed, (uint32_t)(run->step0 + k)));
+      } else {
+        BHMC_TRY(s->eval(s->q, C, row0, run->batch_size, s->g, stat));
+      }
       run->n_grad_evals += C;
       if (sgd) {
         BHMC_TRY(launch_sgd_update(ctx, s->q, s->p, s->g, ld, P, C, (float)run->gamma, (float)run->step_size));
@@ -874,6 +987,11 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
         double a, b, cv[BHMC_MAX_VARS];
         mb->energy_coeffs(run->batch_size, &a, &b, cv);
         BHMC_TRY(s->eval(s->q, C, row0, run->batch_size, nullptr, stat));
+        if (run->dropout_keep > 0.0) {  // sgd.py:67: loss = -log_likelihood(par, last batch), no prior, no 1/n
+          BHMC_TRY(launch_affine(ctx, stat, -1.0, 0.0, nullptr, run->logp_dev + (size_t)i * C, C));
+          if (run->samples_dev) BHMC_TRY(launch_copy_rows(ctx, s->q, ld, run->samples_dev + (size_t)i * C * P, P, P, C));
+          continue;
+        }
         bool need_extra = false;
         for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
         double* extra = nullptr;

@@ -100,6 +100,14 @@ struct ModelBase {
   // potential used by the Metropolis test: U = a*stat + b (+ sum_v cv[v]*|q_v|^2)
   virtual void energy_coeffs(int64_t nrows, double* a, double* b, double* cv) const = 0;
   virtual int64_t default_rows() const { return 0; }
+  virtual int64_t n_features() const { return 0; }
+  // sgd.fit_dropout: gradient on rows [row0, row0+nrows) multiplied elementwise by a Bernoulli(keep) mask
+  // (mask != nullptr: injected [nrows, D] keep flags; else Philox keyed by (seed, stream))
+  virtual int grad_input_dropout(const float*, int, int64_t, int64_t, int64_t, int, float*, double*, const uint8_t*,
+                                 float, uint64_t, uint32_t) {
+    set_error("this model has no input-dropout gradient (sgd.fit_dropout)");
+    return BHMC_ERR_UNSUPPORTED;
+  }
 };
 
 // ---- update.cu --------------------------------------------------------------------------

@@ -153,8 +153,24 @@ class hmc(_ChainSampler):
         a = float(a[0]) if squeeze else a
         return q, p, [state], [None], a
 
+    def backend_mean(self, multi_backend, niter, ncores=None):
+        """hmc.py:132-138 over the files written by ``sample(backend=...)``."""
+        from ...sink import backend_mean
+        return backend_mean(multi_backend, niter, self.start)
+
     def sample(self, niter=1e4, burnin=1e3, rng=None, **args):
-        """hmc.py:90-119 -> (posterior, loss, sample_positions, sample_momentums)."""
+        """hmc.py:90-119 -> (posterior, loss, sample_positions, sample_momentums).
+
+        Extensions (keyword-only, consumed before the data kwargs reach the model):
+          * ``backend="path"``: stream the samples to disk (``hamiltonian/sink.py``; the layout of the reference's
+            multicore samplers) instead of returning them -- ``posterior`` is then ``{var: filename}``.
+          * ``adapt_step_size=True``: wire ``DualAveragingStepSize`` (hmc.py:141-176; instantiated but never used by
+            the reference, :100-104) into burn-in: one ``update(mean accept prob over chains)`` per burn-in step, the
+            noisy step size drives the next step, sampling runs at the averaged step size.  ``self.step_size`` is
+            updated and the trace is kept in ``last_run['step_sizes']``."""
+        backend = args.pop("backend", None)
+        adapt = args.pop("adapt_step_size", False)
+        target_accept = args.pop("target_accept", 0.8)
         niter, burnin = int(niter), int(burnin)
         h, shapes, squeeze, like, q0, s = self._setup(**args)
         s.set_q(q0)
@@ -167,12 +183,18 @@ class hmc(_ChainSampler):
         accept_sum = 0.0
         chunk = max(1, min(512, (256 << 20) // max(1, 4 * C * h.P)))  # bound injected-tape / sample memory
 
-        def run(n, keep):
+        sink = None
+        if backend is not None:
+            from ...sink import SampleSink
+            sink = SampleSink(backend, {v: shapes[v] for v in self.model.var_names}, niter, C, squeeze)
+        step_sizes = []
+
+        def run(n, keep, per_step=None):
             nonlocal n_grad, accept_sum
             outs = []
             done = 0
             while done < n:
-                m = min(chunk, n - done)
+                m = 1 if per_step is not None else min(chunk, n - done)
                 kw = {}
                 if rng is not None:
                     z, u1, u2 = self._host_draws(rng, m, C, h, shapes)
@@ -181,14 +203,33 @@ class hmc(_ChainSampler):
                 self._steps_done += m
                 n_grad += o["n_grad_evals"]
                 if keep:
-                    outs.append((o["samples"].cpu().numpy(), o["loss"].cpu().numpy(), o["accept_prob"].cpu().numpy()))
+                    smp = o["samples"].cpu().numpy()
+                    if sink is not None:
+                        sink.append(smp)
+                        smp = smp[:0]
+                    outs.append((smp, o["loss"].cpu().numpy(), o["accept_prob"].cpu().numpy()))
                 else:
-                    accept_sum += float(o["accept_prob"].sum().item())
+                    a_sum = float(o["accept_prob"].sum().item())
+                    accept_sum += a_sum
+                    if per_step is not None:
+                        per_step(a_sum / C)
                 done += m
             return outs
 
-        run(burnin, False)
-        if self.verbose and burnin > 0:
+        if adapt and burnin > 0:
+            da = DualAveragingStepSize(self.step_size, target_accept=target_accept)
+            avg = [self.step_size]
+
+            def tune(p_accept):
+                self.step_size, a = da.update(p_accept)
+                avg[0] = a
+                step_sizes.append((float(p_accept), float(self.step_size), float(a)))
+
+            run(burnin, False, per_step=tune)
+            self.step_size = float(avg[0])
+        else:
+            run(burnin, False)
+        if self.verbose and burnin > 0 and not adapt:
             _, avg = DualAveragingStepSize(self.step_size).update(accept_sum / max(1, burnin * C))
             print("adapted step size : ", avg)
         outs = run(niter, True)
@@ -200,13 +241,17 @@ class hmc(_ChainSampler):
             samples = np.zeros((0, C, h.P), np.float32)
             loss = np.zeros((0, C))
             acc = np.zeros((0, C))
-        posterior = self.model.unflatten(samples, shapes, squeeze, like)
+        if sink is not None:
+            posterior = sink.close()
+        else:
+            posterior = self.model.unflatten(samples, shapes, squeeze, like)
         if squeeze:
             loss = loss[:, 0]
         if self.verbose and niter > 0:
             for i in range(0, niter, max(1, niter // 10)):
                 print("loss: {0:.4f}".format(float(np.mean(loss[i]))))
-        self.last_run = dict(n_grad_evals=n_grad, accept_prob=acc, n_chains=C)
+        self.last_run = dict(n_grad_evals=n_grad, accept_prob=acc, n_chains=C, step_sizes=step_sizes,
+                             step_size=self.step_size)
         # hmc.py:110-111 returns the pre-step position/momentum of every iteration; positions are
         # recoverable from the samples, momenta are not kept on the device ring.
         return posterior, loss, None, None

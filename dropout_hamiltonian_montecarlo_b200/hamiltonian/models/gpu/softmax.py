@@ -64,7 +64,7 @@ class softmax(_base.ChainModel):
         if isinstance(X, torch.Tensor) and X.is_cuda:
             Xd = X.to(torch.float32).contiguous()
             n, d = Xd.shape
-            h = SoftmaxHandle(ctx, n, d, k, self._alpha_local(), PRIOR[self.prior])
+            h = self._new_handle(ctx, n, d, k)
             h.bind(Xd, torch.as_tensor(labels).to(ctx.device), mask)
         else:
             # host buffers cross the C ABI as they are (bhmc_softmax_bind_data_host does the H2D copy)
@@ -76,7 +76,7 @@ class softmax(_base.ChainModel):
                 h = old  # same shape: refresh the device copies in place (keeps the sampler state alive)
                 self._bound = None
             else:
-                h = SoftmaxHandle(ctx, n, d, k, self._alpha_local(), PRIOR[self.prior])
+                h = self._new_handle(ctx, n, d, k)
             h.bind_host(Xh, torch.as_tensor(np.ascontiguousarray(labels)), mask)
             ctx.sync()  # the host buffers may be released by the caller after bind returns
         if self._bound is not None:
@@ -89,6 +89,9 @@ class softmax(_base.ChainModel):
             h.global_rows = int(tot.item())
         self._bound = (key, h, (X, y))
         return h
+
+    def _new_handle(self, ctx, n, d, k):
+        return SoftmaxHandle(ctx, n, d, k, self._alpha_local(), PRIOR[self.prior])
 
     def _alpha_local(self):
         if not self.row_sharded:

@@ -147,6 +147,16 @@ class SoftmaxHandle(ModelHandle):
         return probs, labels
 
 
+class LogisticHandle(SoftmaxHandle):
+    """models/cpu/logistic.py on the softmax kernels (two-class softmax, class 0 pinned to zero): P = D + 1."""
+
+    def __init__(self, ctx, n_rows, n_features, alpha):
+        h = C.c_void_p()
+        check(ctx.L.bhmc_logistic_create(ctx.handle, n_rows, n_features, float(alpha), C.byref(h)))
+        ModelHandle.__init__(self, ctx, h)
+        self.N, self.D, self.K = n_rows, n_features, 2
+
+
 class MlpHandle(ModelHandle):
     def __init__(self, ctx, n_rows, n_in, n_mid, n_out, alpha, ratio=0.1, seed=0, chain_id0=0):
         h = C.c_void_p()
@@ -277,7 +287,7 @@ class SamplerHandle:
         return out
 
     def sg_run(self, epochs, burnin, batch_size, step_size, *, n_rows=0, gamma=0.9, step0=0, z=None,
-               keep_samples=True):
+               keep_samples=True, dropout_keep=0.0, masks=None):
         ctx = self.ctx
         run = SgRun()
         run.epochs, run.burnin, run.batch_size, run.n_rows = epochs, burnin, batch_size, n_rows
@@ -285,6 +295,10 @@ class SamplerHandle:
         if z is not None:
             z = z.to(ctx.device, torch.float32).contiguous()
             run.z_dev = z.data_ptr()
+        run.dropout_keep = float(dropout_keep)
+        if masks is not None:  # [(burnin+epochs)*n_batches, batch_size, D] keep flags (sgd.fit_dropout injection)
+            masks = masks.to(ctx.device, torch.uint8).contiguous()
+            run.mask_dev = masks.data_ptr()
         out = {}
         if keep_samples:
             out["samples"] = ctx.empty((epochs, self.C, self.P))
@@ -294,5 +308,5 @@ class SamplerHandle:
         check(ctx.L.bhmc_sampler_sg_run(self.handle, C.byref(run)))
         out["n_grad_evals"] = int(run.n_grad_evals)
         out["final_step_size"] = float(run.final_step_size)
-        out["_keep"] = z
+        out["_keep"] = (z, masks)
         return out

@@ -74,6 +74,12 @@ int bhmc_ctx_timing(bhmc_ctx* ctx, int enable);
  *      negative_log_posterior, hamiltonian/models/cpu/softmax.py:45-79 ---------------------- */
 int bhmc_softmax_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_features, int32_t n_classes,
                         float alpha, int32_t prior_variant, bhmc_model** out);
+/* logistic regression, hamiltonian/models/cpu/logistic.py:15-72: parameters weights[D] (the reference's [D,1]) and
+ * bias[1]; labels are 0/1.  grad = X^T(sigmoid(z) - y) + alpha*theta (:24-40), log-lik = sum y log s + (1-y) log(1-s)
+ * (:64-72), log-prior = dim/2 log(alpha/2pi) - alpha/2 |theta|^2 (:15-21) so the Metropolis energy carries the quadratic
+ * term.  Evaluated by the softmax kernels as a two-class softmax with class 0 pinned to zero; bind data with
+ * bhmc_softmax_bind_data / _host. */
+int bhmc_logistic_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_features, float alpha, bhmc_model** out);
 /* bind X [n_rows, n_features] fp32 row-major and integer labels [n_rows] (the argmax of the
  * reference's one-hot y_train).  The library builds its own resident bf16 hi/lo operand copies
  * (precision_mask: bit i set = prepare BHMC_PREC_i).  X_dev/labels_dev stay bound (needed by
@@ -206,6 +212,12 @@ typedef struct bhmc_sg_run {
   double* logp_dev;        /* [epochs, n_chains] NLP(q, last batch) (sgmcmc.py:79)             */
   int64_t n_grad_evals;    /* out */
   double final_step_size;  /* out */
+  /* sgd.fit_dropout (sgd.py:47-70): the gradient of minibatch k sees X_batch * Z_k, Z ~ Bernoulli(dropout_keep)
+   * (no rescaling), and the per-epoch loss is -log_likelihood(theta, last batch) on the unmasked rows (:67).
+   * dropout_keep = 0 disables.  mask_dev: injected keep flags [(burnin+epochs)*n_batches, batch_size, D] uint8,
+   * or NULL for in-kernel Philox draws keyed (seed, minibatch, row, feature). */
+  double dropout_keep;
+  const uint8_t* mask_dev;
 } bhmc_sg_run;
 /* SGLD (kind SGLD) / SGD (kind SGD) epochs over sequential minibatches */
 int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run);

@@ -192,6 +192,70 @@ class SoftmaxOracle:
 
 
 # --------------------------------------------------------------------------------------
+# logistic regression model -- hamiltonian/models/cpu/logistic.py
+# --------------------------------------------------------------------------------------
+def logistic_net(par: Par, X: np.ndarray) -> np.ndarray:
+    """sigmoid of the clipped linear predictor, shape [N,1]. logistic.py:42-53."""
+    z = X @ par["weights"] + par["bias"]
+    z = np.minimum(z, CLIP_HI)
+    z = np.maximum(z, CLIP_LO)
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+def logistic_grad(par: Par, X: np.ndarray, y: np.ndarray, alpha: float) -> Par:
+    """logistic.py:24-40: ``-(X^T (y - yhat) - alpha w)`` and ``-(sum (y - yhat) - alpha b)`` (sums over rows)."""
+    diff = np.asarray(y).reshape(-1, 1) - logistic_net(par, X)
+    gw = X.T @ diff - alpha * par["weights"]
+    gb = diff.sum(axis=0) - alpha * par["bias"]
+    return {"weights": -1.0 * gw, "bias": -1.0 * gb}
+
+
+def logistic_log_likelihood(par: Par, X: np.ndarray, y: np.ndarray) -> float:
+    """logistic.py:64-72: ``sum y log yhat + (1-y) log(1-yhat)``."""
+    yp = np.squeeze(logistic_net(par, X), axis=1)
+    y = np.asarray(y)
+    return float(np.sum(y * np.log(yp) + (1.0 - y) * np.log(1.0 - yp)))
+
+
+def logistic_log_prior(par: Par, alpha: float) -> float:
+    """logistic.py:15-21: ``sum_v dim_v/2 log(alpha/2pi) - alpha/2 |theta_v|^2`` -- WITH the quadratic term."""
+    k = 0.0
+    for v in par:
+        dim = np.asarray(par[v]).size
+        k += dim * 0.5 * np.log(alpha / (2 * np.pi))
+        k -= 0.5 * alpha * np.sum(np.square(par[v]))
+    return float(k)
+
+
+def logistic_nlp(par: Par, X, y, alpha: float) -> float:
+    """logistic.py:55-60: ``-(LL + log_prior)/N``."""
+    n = np.asarray(X).shape[0]
+    return (-1.0 / n) * (logistic_log_likelihood(par, X, y) + logistic_log_prior(par, alpha))
+
+
+class LogisticOracle:
+    """Duck-typed like reference ``logistic(hyper)``."""
+
+    def __init__(self, hyper):
+        self.hyper = hyper
+
+    def grad(self, par, **args):
+        return logistic_grad(par, args["X_train"], args["y_train"], self.hyper["alpha"])
+
+    def log_likelihood(self, par, **args):
+        return logistic_log_likelihood(par, args["X_train"], args["y_train"])
+
+    def negative_log_posterior(self, par, **args):
+        return logistic_nlp(par, args["X_train"], args["y_train"], self.hyper["alpha"])
+
+    def predict(self, par, X, prob=False, batchsize=32):
+        """logistic.py:75-87: whole batches only (remainder dropped), flattened."""
+        n = (X.shape[0] // batchsize) * batchsize
+        yhat = logistic_net(par, X[:n])
+        return yhat.flatten() if prob else (yhat > 0.5).astype(int).flatten()
+
+
+# --------------------------------------------------------------------------------------
 # 2-D Gaussian target -- hamiltonian/models/cpu/mvn_gaussian.py
 # --------------------------------------------------------------------------------------
 class MvnGaussianOracle:
@@ -490,6 +554,28 @@ def sgd_fit(model, start: Par, eps: float, epochs: int, batch_size: int, gamma: 
                 par[v] = par[v] + mom[v]
         a, b = wins[-1]
         loss[i] = model.negative_log_posterior(par, X_train=X[a:b], y_train=Y[a:b])
+    return par, loss
+
+
+def sgd_fit_dropout(model, start: Par, eps: float, epochs: int, batch_size: int, gamma: float, X, Y, masks):
+    """sgd.py:47-70: like ``fit`` but the gradient sees ``X_batch * Z`` with ``Z ~ Binomial(1, p)`` drawn per
+    minibatch from the global ``np.random`` (``masks[k]`` = the k-th drawn Z, injected), and the per-epoch loss is
+    ``-log_likelihood(theta, last batch)`` on the UNMASKED batch (:67)."""
+    order = list(start.keys())
+    par = {v: np.array(start[v], dtype=np.float64, copy=True) for v in order}
+    mom = {v: np.zeros_like(par[v]) for v in order}
+    loss = np.zeros(int(epochs))
+    wins = minibatch_windows(X.shape[0], batch_size)
+    k = 0
+    for i in range(int(epochs)):
+        for (a, b) in wins:
+            g = model.grad(par, X_train=X[a:b] * masks[k], y_train=Y[a:b])
+            k += 1
+            for v in order:
+                mom[v] = gamma * mom[v] - eps * g[v]
+                par[v] = par[v] + mom[v]
+        a, b = wins[-1]
+        loss[i] = -1.0 * model.log_likelihood(par, X_train=X[a:b], y_train=Y[a:b])
     return par, loss
 
 

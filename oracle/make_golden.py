@@ -193,5 +193,74 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def main_next_rows():
+    """logistic model (models/cpu/logistic.py), hmc.sample on it, sgd.fit_dropout (sgd.py:47-70)."""
+    os.makedirs(OUT, exist_ok=True)
+    ref = load_reference()
+    # ---- 8. logistic grad / log-lik / NLP / predict ----------------------------------------
+    cases = {}
+    for name, (n, d, alpha, wscale, xscale) in {"small": (64, 16, 0.01, 0.3, 1.0), "d100": (96, 100, 1.0, 0.1, 1.0),
+                                                 "clip": (48, 24, 0.01, 6.0, 3.0)}.items():
+        rs = np.random.RandomState(200 + len(cases))
+        X = rs.rand(n, d) * xscale
+        w_true = rs.normal(0, 1.0, (d, 1))
+        y = (rs.rand(n) < 1.0 / (1.0 + np.exp(-(X - X.mean()) @ w_true).ravel())).astype(np.float64)
+        par = {"weights": rs.normal(0, wscale, (d, 1)), "bias": rs.normal(0, wscale, 1)}
+        m = ref.logistic({"alpha": alpha})
+        with np.errstate(all="ignore"):
+            g = m.grad(par, X_train=X, y_train=y)
+            cases[name] = dict(X=X, y=y, W=par["weights"], b=par["bias"], alpha=alpha, gW=g["weights"], gb=g["bias"],
+                               ll=m.log_likelihood(par, X_train=X, y_train=y),
+                               nlp=m.negative_log_posterior(par, X_train=X, y_train=y),
+                               yhat=m.net(par, X_train=X), pred=m.predict(par, X, batchsize=32),
+                               log_prior=m.log_prior(par))
+    np.savez_compressed(os.path.join(OUT, "logistic_model.npz"),
+                        **{f"{c}.{k}": v for c, d_ in cases.items() for k, v in d_.items()})
+    # ---- 9. hmc.sample on logistic: the accept energy carries the quadratic prior term ---------
+    n, d, alpha = 120, 10, 1.0
+    rs = np.random.RandomState(61)
+    X = rs.normal(0, 1, (n, d))
+    y = (rs.rand(n) < 1.0 / (1.0 + np.exp(-X @ rs.normal(0, 1, d)))).astype(np.float64)
+    start = {"weights": rs.normal(0, 0.1, (d, 1)), "bias": np.zeros(1)}
+    eps, path = 5e-3, 5e-2
+    s = ref.hmc(ref.logistic({"alpha": alpha}), start, path_length=path, step_size=eps, verbose=False)
+    rng = RecordingRng(62)
+    with patched_global_rand(seed=63) as urec, quiet():
+        post, loss, _, _ = s.sample(niter=16, burnin=4, rng=rng, X_train=X, y_train=y)
+    np.savez_compressed(os.path.join(OUT, "hmc_sample_logistic.npz"), X=X, y=y, alpha=alpha, eps=eps, path=path,
+                        W0=start["weights"], b0=start["bias"], z=pack_normals(rng.normals), u=np.array(urec),
+                        postW=post["weights"], postb=post["bias"], loss=loss, niter=16, burnin=4)
+    # ---- 10. sgd.fit_dropout on softmax with the Bernoulli input masks recorded ------------------
+    d, k, alpha, n2, bs = 12, 4, 0.01, 130, 32
+    X2, y2 = synth_softmax(n2, d, k, seed=12)
+    Y2 = ref.one_hot(y2, k)
+    start = {"weights": np.zeros((d, k)), "bias": np.zeros(k)}
+    s = ref.sgd(ref.softmax({"alpha": alpha}), start, step_size=1e-2)
+    masks = []
+    orig = np.random.binomial
+    rs = np.random.RandomState(71)
+
+    def binomial(nn, pp, size=None):
+        z = rs.binomial(nn, pp, size=size)
+        masks.append(np.array(z, dtype=np.uint8))
+        return z
+
+    np.random.binomial = binomial
+    try:
+        with quiet():
+            par, loss = s.fit_dropout(epochs=3, batch_size=bs, gamma=0.9, p=0.7, X_train=X2, y_train=Y2)
+    finally:
+        np.random.binomial = orig
+    np.savez_compressed(os.path.join(OUT, "sgd_fit_dropout_softmax.npz"), X=X2, y=y2, alpha=alpha, eps=1e-2,
+                        batch_size=bs, epochs=3, gamma=0.9, p=0.7, masks=np.stack(masks), W=par["weights"],
+                        b=par["bias"], loss=loss)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "next":
+        main_next_rows()
+    else:
+        main()

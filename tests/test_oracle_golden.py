@@ -159,3 +159,47 @@ def test_mlp_grad_matches_autograd():
     np.testing.assert_allclose(O.mlp_loss(par, X, y, masks), loss.item(), rtol=1e-12)
     for k in par:
         np.testing.assert_allclose(g[k], tp[k].grad.numpy() + 0.5 * alpha * par[k], rtol=1e-9, atol=1e-12)
+
+
+# ---- logistic model, hmc on it, sgd.fit_dropout ---------------------------------
+@pytest.mark.parametrize("case", ["small", "d100", "clip"])
+def test_logistic_model(case):
+    g = load_golden("logistic_model.npz")[case]
+    par = {"weights": g["W"], "bias": g["b"]}
+    with np.errstate(all="ignore"):
+        got = O.logistic_grad(par, g["X"], g["y"], g["alpha"])
+        np.testing.assert_allclose(got["weights"], g["gW"], **TOL)
+        np.testing.assert_allclose(got["bias"], g["gb"], **TOL)
+        np.testing.assert_allclose(O.logistic_log_likelihood(par, g["X"], g["y"]), g["ll"], **TOL)
+        np.testing.assert_allclose(O.logistic_nlp(par, g["X"], g["y"], g["alpha"]), g["nlp"], **TOL)
+    np.testing.assert_allclose(O.logistic_log_prior(par, g["alpha"]), g["log_prior"], **TOL)
+    np.testing.assert_allclose(O.logistic_net(par, g["X"]), g["yhat"], **TOL)
+    np.testing.assert_array_equal(O.LogisticOracle({"alpha": g["alpha"]}).predict(par, g["X"], batchsize=32), g["pred"])
+
+
+def test_hmc_sample_logistic():
+    g = load_golden("hmc_sample_logistic.npz")
+    d = g["W0"].shape[0]
+    normals, used = split_tape(g["z"], [(d, 1), (1,)], 1 + g["niter"] + g["burnin"])
+    assert used == g["z"].size
+    draws = O.TapeDraws(normals, list(g["u"]))
+    post, loss, info = O.hmc_sample(O.LogisticOracle({"alpha": g["alpha"]}), {"weights": g["W0"], "bias": g["b0"]},
+                                    g["eps"], g["path"], g["niter"], g["burnin"], draws, X_train=g["X"], y_train=g["y"])
+    assert draws.u_pos == g["u"].size
+    np.testing.assert_allclose(post["weights"], g["postW"], **TOL)
+    np.testing.assert_allclose(post["bias"], g["postb"], **TOL)
+    np.testing.assert_allclose(loss, g["loss"], **TOL)
+    moved = np.any(np.diff(g["postW"], axis=0) != 0, axis=(1, 2))
+    assert moved.any() and not moved.all()  # accepts and rejects both occur
+
+
+def test_sgd_fit_dropout():
+    g = load_golden("sgd_fit_dropout_softmax.npz")
+    d, k = g["W"].shape
+    par, loss = O.sgd_fit_dropout(O.SoftmaxOracle({"alpha": g["alpha"]}), {"weights": np.zeros((d, k)), "bias": np.zeros(k)},
+                                  g["eps"], g["epochs"], g["batch_size"], g["gamma"], g["X"], O.one_hot(g["y"], k),
+                                  g["masks"].astype(np.float64))
+    np.testing.assert_allclose(par["weights"], g["W"], **TOL)
+    np.testing.assert_allclose(par["bias"], g["b"], **TOL)
+    np.testing.assert_allclose(loss, g["loss"], **TOL)
+    assert 0.6 < g["masks"].mean() < 0.8

@@ -103,3 +103,36 @@ def test_dual_averaging_live():
     st = dict(mu=np.log(10 * 0.1), target_accept=0.8, gamma=0.05, t=10.0, kappa=0.75, error_sum=0.0, log_averaged_step=0.0)
     for a in [0.9, 0.3, 0.7, 1.0, 0.0]:
         assert np.allclose(da.update(a), O.dual_averaging_update(st, a), rtol=1e-13)
+
+
+def test_logistic_hmc_live():
+    """models/cpu/logistic.py under hmc.sample: the accept energy carries the quadratic prior term."""
+    ref = load_reference()
+    rs = np.random.RandomState(11)
+    X = rs.normal(0, 1, (90, 8))
+    y = (rs.rand(90) < 0.5).astype(np.float64)
+    start = {"weights": rs.normal(0, .1, (8, 1)), "bias": np.zeros(1)}
+    s = ref.hmc(ref.logistic({"alpha": 0.5}), {k: v.copy() for k, v in start.items()}, path_length=5e-2, step_size=5e-3,
+                verbose=False)
+    np.random.seed(31)
+    with quiet():
+        post, loss, _, _ = s.sample(niter=12, burnin=3, rng=np.random.RandomState(32), X_train=X, y_train=y)
+    draws = O.StreamDraws(np.random.RandomState(32), np.random.RandomState(31))
+    opost, oloss, _ = O.hmc_sample(O.LogisticOracle({"alpha": 0.5}), start, 5e-3, 5e-2, 12, 3, draws, X_train=X, y_train=y)
+    np.testing.assert_allclose(opost["weights"], post["weights"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(oloss, loss, rtol=1e-12)
+
+
+def test_sgd_fit_dropout_live():
+    ref = load_reference()
+    X, y, Y = data(n=210)
+    start = {"weights": np.zeros((20, 6)), "bias": np.zeros(6)}
+    s = ref.sgd(ref.softmax({"alpha": 0.1}), {k: v.copy() for k, v in start.items()}, step_size=5e-3)
+    np.random.seed(17)
+    with quiet():
+        par, loss = s.fit_dropout(epochs=3, batch_size=50, gamma=0.9, p=0.6, X_train=X, y_train=Y)
+    rs = np.random.RandomState(17)
+    masks = [rs.binomial(1, 0.6, size=(50, 20)) for _ in range(3 * 4)]
+    opar, oloss = O.sgd_fit_dropout(O.SoftmaxOracle({"alpha": 0.1}), start, 5e-3, 3, 50, 0.9, X, Y, masks)
+    np.testing.assert_allclose(opar["weights"], par["weights"], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(oloss, loss, rtol=1e-12)
