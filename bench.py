@@ -76,6 +76,7 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.rows = []
+        self.first = 0
         self.proc = None
 
     def start(self):
@@ -91,13 +92,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported.  (nvidia-smi is started before
+        the warm-up because its NVML initialisation takes ~1 s during which kernel launches can stall.)"""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -233,30 +239,32 @@ def run_ours(args, wl):
     shared = args.path_mode == "shared"
     s = SamplerHandle(ctx, h, 0, C, seed=1234, chain_id0=rank * C, precision=PREC[prec], shared_path=shared)
     s.set_q(np.zeros((C, h.P), np.float32))
-    samples = ctx.empty((1, C, h.P))
 
-    def step(i):
-        return s.hmc_run(1, wl["eps"], wl["path"], step0=i, keep_samples=True, keep_stats=True)
+    def run_steps(i0, n):
+        """n HMC transitions of every chain in ONE library call (what hmc.sample(niter=n) issues): with per-chain path
+        lengths the call runs the streaming schedule -- a chain starts its next transition as soon as its own
+        trajectory ends -- so the K timed steps are K transitions per chain, not K barriers."""
+        return s.hmc_run(n, wl["eps"], wl["path"], step0=i0, keep_samples=True, keep_stats=True, schedule=args.schedule)
 
-    for i in range(args.warmup):
-        step(i)
+    clocks = ClockSampler(local)
+    clocks.start()
+    if args.warmup > 0:
+        run_steps(0, args.warmup)
     ctx.sync()
     # L2 note: one gradient evaluation streams X (94-376 MB) + (P-Y)^T (77-245 MB) -- far larger than the
     # 126 MB L2 -- so consecutive launches cannot be served from cache; no explicit flush is needed.
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.mark()
     ctx.timing(True)
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_applied = n_launched = 0
     e0.record()
-    for i in range(args.steps):
-        o = step(args.warmup + i)
-        n_applied += o["n_grad_evals"]
-        n_launched += o["n_grad_launched"]
+    o = run_steps(args.warmup, args.steps)
+    n_applied += o["n_grad_evals"]
+    n_launched += o["n_grad_launched"]
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -367,6 +375,8 @@ def run_ours(args, wl):
             "data": "synthetic",
             "config": {"workload": wl["desc"], "N": N, "D": D, "K": K, "chains_per_gpu": C, "step_size": wl["eps"],
                        "path_length": wl["path"], "precision": prec, "path_length_mode": args.path_mode,
+                       "schedule": ("streaming (asynchronous chains, %d gradient launches)" % o["n_phases"]) if o["n_phases"]
+                       else "lockstep",
                        "sweep": "reference (Gauss-Seidel, 2 gradients per leapfrog iteration)",
                        "l2": "inputs larger than L2 (X 94-376 MB + (P-Y)^T 77-245 MB per evaluation)",
                        "grad_evals_launched_incl_masked": n_launched},
@@ -392,12 +402,13 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--path-mode", default="per_chain", choices=["per_chain", "shared"])
+    ap.add_argument("--schedule", default="auto", choices=["auto", "lockstep", "streaming"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--ess-steps", type=int, default=40)

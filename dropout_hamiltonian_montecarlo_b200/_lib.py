@@ -39,6 +39,7 @@ class HmcRun(C.Structure):
         ("samples_dev", C.c_void_p), ("loss_dev", C.c_void_p), ("accept_prob_dev", C.c_void_p),
         ("accepted_dev", C.c_void_p),
         ("n_grad_evals", C.c_int64), ("n_grad_launched", C.c_int64),
+        ("schedule", C.c_int32), ("n_phases", C.c_int32),
     ]
 
 

@@ -161,6 +161,18 @@ int bhmc_ctx_timing(bhmc_ctx* ctx, int enable) {
   BHMC_TRY(ctx->flush_timing());
   ctx->timing = enable != 0;
   for (int g = 0; g < KG_COUNT; ++g) ctx->ms_acc[g] = 0, ctx->n_acc[g] = 0;
+  if (ctx->timing) {
+    // create the whole event pool now: cudaEventCreate costs microseconds and would otherwise be paid lazily
+    // inside the region being timed (8 events per gradient evaluation)
+    BHMC_CUDA_OK(cudaSetDevice(ctx->device));
+    for (int g = 0; g < KG_COUNT; ++g)
+      while (ctx->pool[g].size() < 4096) {
+        EventPair ep;
+        BHMC_CUDA_OK(cudaEventCreate(&ep.a));
+        BHMC_CUDA_OK(cudaEventCreate(&ep.b));
+        ctx->pool[g].push_back(ep);
+      }
+  }
   return BHMC_OK;
 }
 
@@ -695,6 +707,216 @@ int bhmc_sampler_get(bhmc_sampler* s, int32_t which, float* dst, int32_t is_host
   return BHMC_OK;
 }
 
+// ---- HMC, streaming schedule (asynchronous chains) -----------------------------------------------------------
+// Path lengths are fresh uniforms per chain and step (hmc.py:46), so in lockstep the chains of one transition finish
+// at very different times (E[L]/max L ~ 0.5 for 64 chains).  Chains are independent, so nothing forces them to start
+// transition t+1 together: here every chain walks through its own sequence of transitions back to back, and every
+// gradient launch carries all chains that still have work.  The host knows every L in advance (host Philox == device
+// Philox), so it compiles the whole run into one op code per (phase, row); rows are sorted by total work so that the
+// rows still busy at the end of the run form a prefix.  Draws are keyed by (chain, step): the samples are the ones
+// the lockstep schedule produces.
+static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vector<int32_t>& L /* [n_steps][C] */) {
+  const bhmc_sampler_config& cfg = s->cfg;
+  bhmc_ctx* ctx = s->ctx;
+  ModelBase* mb = s->model;
+  const int C = cfg.n_chains, nsw = cfg.n_sweep, n_steps = run->n_steps;
+  const int64_t P = s->P, ld = s->ld;
+  const int64_t nrows = run->nrows > 0 ? run->nrows : mb->default_rows();
+  const float eps = (float)run->step_size;
+  double* stat = s->scal;
+  double* stat_cur = stat + C;
+  double* stat_new = stat + 2 * C;
+  double* kin1 = stat + 4 * C;
+  double* extra_cur = stat + 5 * C;
+  double* extra_new = stat + 6 * C;
+  double* sumsq = stat + 8 * C;
+  double ea, eb, cv[BHMC_MAX_VARS];
+  mb->energy_coeffs(nrows, &ea, &eb, cv);
+  bool need_extra = false;
+  for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
+
+  // total gradient slots per chain: per transition 1 (start point) + (L-1)*nsw (sub-steps)
+  std::vector<int64_t> T(C, 0);
+  run->n_grad_evals = 0;
+  for (int t = 0; t < n_steps; ++t)
+    for (int c = 0; c < C; ++c) T[c] += 1 + (int64_t)std::max(L[(size_t)t * C + c] - 1, 0) * nsw;
+  std::vector<int32_t> perm(C);
+  for (int c = 0; c < C; ++c) perm[c] = c, run->n_grad_evals += T[c];
+  std::stable_sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) { return T[x] > T[y]; });
+  const int64_t J = T[perm[0]];  // gradient launches; elementwise phases are 0..J (phase T_c finishes chain c)
+  BHMC_CHECK_ARG(J < (1LL << 24), "run too long for one call (%lld phases): lower n_steps", (long long)J);
+
+  // ---- compile the op table -----------------------------------------------------------------------------------
+  const size_t n_ops = (size_t)(J + 1) * C;
+  const size_t code_bytes = round_up(sizeof(uint32_t) * n_ops, 64), perm_bytes = round_up(sizeof(int32_t) * C, 64);
+  const size_t u_bytes = sizeof(double) * (size_t)n_steps * C;
+  if (ctx->pinned_inflight) {
+    BHMC_CUDA_OK(cudaEventSynchronize(ctx->pinned_ev));
+    ctx->pinned_inflight = false;
+  }
+  void* pin = nullptr;
+  BHMC_TRY(ctx->get_pinned(2 * code_bytes + perm_bytes + u_bytes, &pin));
+  uint32_t* code_h = (uint32_t*)pin;
+  int32_t* step_h = (int32_t*)((char*)pin + code_bytes);
+  int32_t* perm_h = (int32_t*)((char*)pin + 2 * code_bytes);
+  double* uacc_h = (double*)((char*)pin + 2 * code_bytes + perm_bytes);
+  memset(code_h, 0, 2 * code_bytes);
+  std::vector<int> rows_el(J + 2, 0), rows_grad(J + 1, 0);  // active row counts per phase
+  std::vector<char> ev_finish(J + 1, 0), ev_begin(J + 1, 0);
+  for (int r = 0; r < C; ++r) {
+    const int c = perm[r];
+    perm_h[r] = c;
+    int64_t j = 0;
+    for (int t = 0; t < n_steps; ++t) {
+      const int Lt = L[(size_t)t * C + c];
+      // phase j: (finish t-1,) begin t; the launch that follows evaluates the start point
+      code_h[j * C + r] |= OP_BEGIN;
+      if (t == 0) step_h[j * C + r] = 0;  // with FINISH the field holds t-1 and BEGIN adds one
+      ev_begin[j] = 1;
+      ++j;
+      // phase j: latch the start-point statistics, then either the first sub-step or (L <= 1) nothing
+      code_h[j * C + r] |= OP_LATCH;
+      step_h[j * C + r] = t;
+      const int iters = std::max(Lt - 1, 0);
+      for (int it = 0; it < iters; ++it)
+        for (int v = 0; v < nsw; ++v) {
+          const bool first = it == 0 && v == 0;
+          const int pv = v == 0 ? nsw - 1 : v - 1;
+          code_h[j * C + r] |= OP_PRE | ((uint32_t)v << 12) | (first ? 0u : (OP_POST | ((uint32_t)pv << 8)));
+          step_h[j * C + r] = t;
+          ++j;
+        }
+      // phase j (== the next transition's begin phase, or the chain's last phase): closing kick + Metropolis test
+      if (iters > 0) code_h[j * C + r] |= OP_POST | ((uint32_t)(nsw - 1) << 8);
+      code_h[j * C + r] |= OP_FINISH;
+      step_h[j * C + r] = t;
+      ev_finish[j] = 1;
+    }
+    // j == T[c]: the chain takes part in elementwise phases 0..T and gradient launches 0..T-1
+    for (int64_t k = 0; k <= j; ++k) rows_el[k] = r + 1;  // rows sorted by T descending -> prefix
+    for (int64_t k = 0; k < j; ++k) rows_grad[k] = r + 1;
+  }
+  if (run->u_accept_host) memcpy(uacc_h, run->u_accept_host, u_bytes);
+  void* dev = nullptr;
+  BHMC_TRY(ctx->get_scratch(6, 2 * code_bytes + perm_bytes + u_bytes, &dev));
+  const uint32_t* code_d = (const uint32_t*)dev;
+  const int32_t* step_d = (const int32_t*)((char*)dev + code_bytes);
+  const int32_t* perm_d = (const int32_t*)((char*)dev + 2 * code_bytes);
+  const double* uacc_d = (const double*)((char*)dev + 2 * code_bytes + perm_bytes);
+  BHMC_CUDA_OK(cudaMemcpyAsync(dev, pin, 2 * code_bytes + perm_bytes + (run->u_accept_host ? u_bytes : 0),
+                               cudaMemcpyHostToDevice, ctx->stream));
+  if (!ctx->pinned_ev) BHMC_CUDA_OK(cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming));
+  BHMC_CUDA_OK(cudaEventRecord(ctx->pinned_ev, ctx->stream));
+  ctx->pinned_inflight = true;
+  // start-of-step kinetic energies: two parity buffers (a step's buffer is re-zeroed while the other one is in use)
+  void* kbuf = nullptr;
+  BHMC_TRY(ctx->get_scratch(4, sizeof(double) * ((size_t)2 * C + (size_t)C * (mb->n_vars + 1)), &kbuf));
+  double* kin0 = (double*)kbuf;
+  double* extra_tmp = kin0 + 2 * (size_t)C;
+  (void)sumsq;
+  BHMC_CUDA_OK(cudaMemsetAsync(kin0, 0, sizeof(double) * 2 * C, ctx->stream));
+
+  StreamUpdateArgs u{};
+  u.q = s->q_new;
+  u.p = s->p_new;
+  u.g = s->g;
+  u.ld = ld;
+  u.P = P;
+  u.n_vars = nsw;
+  for (int v = 0; v < nsw; ++v) u.off[v] = cfg.sweep_off[v], u.len[v] = cfg.sweep_len[v];
+  u.a_pre = 0.5f * eps;                         // hmc.py:51
+  u.a_post = cfg.leapfrog ? 0.5f * eps : eps;   // hmc.py:54 applies a FULL eps kick
+  u.eps = eps;
+  u.stat = stat;
+  u.stat_cur = stat_cur;
+  u.stat_new = stat_new;
+  u.kin0 = kin0;
+  u.kin1 = kin1;
+  u.C_total = C;
+
+  run->n_grad_launched = 0;
+  for (int64_t j = 0; j <= J; ++j) {
+    const int rows = rows_el[j];
+    const uint32_t* cj = code_d + j * C;
+    const int32_t* sj = step_d + j * C;
+    if (j > 0) {
+      u.rows = rows;
+      u.code = cj;
+      u.step = sj;
+      BHMC_TRY(launch_stream_update(ctx, u));
+    }
+    if (ev_finish[j]) {
+      BHMC_TRY(launch_stream_kinetic(ctx, s->p_new, ld, P, rows, cj, kin1));
+      if (need_extra)
+        BHMC_TRY(launch_prior_energy(ctx, s->q_new, ld, rows, mb->n_vars, mb->var_off, mb->var_len, cv, extra_tmp + C,
+                                     extra_new, cj, OP_FINISH));
+      AcceptArgs a{};
+      a.q = s->q;
+      a.q_new = s->q_new;
+      a.p_out = s->p;
+      a.p_new = s->p_new;
+      a.ld = ld;
+      a.P = P;
+      a.C = rows;
+      a.p_sign = -1.f;  // hmc.py:58-59
+      a.stat_cur = stat_cur;
+      a.stat_new = stat_new;
+      a.ea = ea;
+      a.eb = eb;
+      a.extra_cur = need_extra ? extra_cur : nullptr;
+      a.extra_new = need_extra ? extra_new : nullptr;
+      a.kin0 = kin0;
+      a.kin1 = kin1;
+      a.u = run->u_accept_host ? uacc_d : nullptr;
+      a.seed = cfg.seed;
+      a.chain_id0 = cfg.chain_id0;
+      a.stream_lo = (uint32_t)run->step0;
+      a.stream_hi = TAG_ACCEPT;
+      a.reject_nan = cfg.reject_nan;
+      a.sample = run->samples_dev;
+      a.loss = run->loss_dev;
+      a.accept_prob = run->accept_prob_dev;
+      a.accepted = run->accepted_dev;
+      a.perm = perm_d;
+      a.code = cj;
+      a.step = sj;
+      a.C_total = C;
+      BHMC_TRY(launch_accept(ctx, a));
+    }
+    if (j == J) break;
+    if (ev_begin[j]) {
+      BeginArgs b{};
+      b.q = s->q;
+      b.q_new = s->q_new;
+      b.p0 = s->p;
+      b.p_new = s->p_new;
+      b.ld = ld;
+      b.P = P;
+      b.C = rows_grad[j];
+      b.z = run->z_momentum_dev;
+      b.ld_z = P;
+      b.z_step_stride = (int64_t)C * P;
+      b.seed = cfg.seed;
+      b.chain_id0 = cfg.chain_id0;
+      b.stream_lo = (uint32_t)run->step0;
+      b.stream_hi = TAG_MOMENTUM;
+      b.kin0 = kin0;
+      b.perm = perm_d;
+      b.code = cj;
+      b.step = sj;
+      b.C_total = C;
+      BHMC_TRY(launch_hmc_begin(ctx, b));
+      if (need_extra)  // quadratic log-prior part of U(q) at the start point
+        BHMC_TRY(launch_prior_energy(ctx, s->q_new, ld, rows_grad[j], mb->n_vars, mb->var_off, mb->var_len, cv, extra_tmp + C,
+                                     extra_cur, cj, OP_BEGIN));
+    }
+    BHMC_TRY(s->eval(s->q_new, rows_grad[j], run->row0, nrows, s->g, stat));
+    run->n_grad_launched += rows_grad[j];
+  }
+  run->n_phases = (int32_t)J;
+  return BHMC_OK;
+}
+
 // ---- HMC / SGHMC ---------------------------------------------------------------------------------
 int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
   BHMC_CHECK_ARG(s && run, "NULL argument");
@@ -740,13 +962,9 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
   double* uacc_h = (double*)((char*)pin + 2 * l_bytes);
   std::vector<int> lmax(n_steps, 0);
   std::vector<int> Ltmp(C);
-  bool ragged = false;
-  run->n_grad_evals = 0;
-  run->n_grad_launched = 0;
+  std::vector<int32_t> Lraw((size_t)n_steps * C);
   for (int t = 0; t < n_steps; ++t) {
     uint32_t step = (uint32_t)(run->step0 + t);
-    int32_t* Lt = Lh + (size_t)t * C;
-    int32_t* pt = perm_h + (size_t)t * C;
     for (int c = 0; c < C; ++c) {
       double u;
       if (run->u_path_host)
@@ -754,7 +972,30 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
       else
         u = philox_uniform(cfg.seed, cfg.shared_path ? -1 : cfg.chain_id0 + c, step, TAG_PATH);
       double Ld = std::ceil(2.0 * u * run->path_length / run->step_size);
-      Ltmp[c] = Ld > 1e9 ? 1000000000 : (int)Ld;
+      Lraw[(size_t)t * C + c] = Ld > 1e9 ? 1000000000 : (int)Ld;
+    }
+  }
+  {
+    static int sched_env = -1;  // BHMC_SCHEDULE=1|2 overrides AUTO (A/B measurements)
+    if (sched_env < 0) {
+      const char* e = getenv("BHMC_SCHEDULE");
+      sched_env = e ? atoi(e) : 0;
+    }
+    int sched = run->schedule ? run->schedule : sched_env;
+    const bool can_stream = !sghmc && C > 1;
+    if (sched == BHMC_SCHED_AUTO) sched = (can_stream && !cfg.shared_path && n_steps >= 2) ? BHMC_SCHED_STREAMING : BHMC_SCHED_LOCKSTEP;
+    BHMC_CHECK_ARG(sched != BHMC_SCHED_STREAMING || !sghmc, "the streaming schedule is implemented for HMC only");
+    if (sched == BHMC_SCHED_STREAMING) return hmc_run_streaming(s, run, Lraw);
+  }
+  bool ragged = false;
+  run->n_grad_evals = 0;
+  run->n_grad_launched = 0;
+  run->n_phases = 0;
+  for (int t = 0; t < n_steps; ++t) {
+    int32_t* Lt = Lh + (size_t)t * C;
+    int32_t* pt = perm_h + (size_t)t * C;
+    for (int c = 0; c < C; ++c) {
+      Ltmp[c] = Lraw[(size_t)t * C + c];
       pt[c] = c;
       run->n_grad_evals += 1 + (int64_t)std::max(Ltmp[c] - 1, 0) * nsw;
       if (run->u_accept_host) uacc_h[(size_t)t * C + c] = run->u_accept_host[(size_t)t * C + c];

@@ -139,6 +139,36 @@ struct UpdateArgs {
 };
 int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a);
 
+// ---- streaming schedule (asynchronous chains): every working row follows its OWN position in its own sequence of
+// HMC transitions; one 32-bit op code per (phase, row) says what the row does between two gradient launches.
+enum : uint32_t {
+  OP_LATCH = 1u,    // the previous launch evaluated the step's start point: stat_cur = stat_new = stat
+  OP_POST = 2u,     // closing kick of variable (code >> 8) & 15; also latches stat_new = stat
+  OP_PRE = 4u,      // opening half kick + drift of variable (code >> 12) & 15
+  OP_FINISH = 8u,   // kinetic energy + Metropolis test of step op_step[row]
+  OP_BEGIN = 16u,   // momentum draw / proposal := state for step op_step[row] + (FINISH ? 1 : 0)
+};
+struct StreamUpdateArgs {
+  float* q;
+  float* p;
+  const float* g;
+  int64_t ld, P;
+  int rows;
+  const uint32_t* code;   // [rows] ops of this phase
+  const int32_t* step;    // [rows] step index the row's op refers to
+  int n_vars;
+  int64_t off[BHMC_MAX_VARS], len[BHMC_MAX_VARS];
+  float a_pre, a_post, eps;
+  const double* stat;
+  double *stat_cur, *stat_new;
+  double* kin0;           // [2][C_total] kinetic energy at the start of the step, buffer = step parity
+  double* kin1;           // [C_total] zeroed here for the kinetic kernel of this phase
+  int C_total;
+};
+int launch_stream_update(bhmc_ctx* ctx, const StreamUpdateArgs& a);
+int launch_stream_kinetic(bhmc_ctx* ctx, const float* p, int64_t ld, int64_t P, int rows, const uint32_t* code,
+                          double* kin);
+
 struct BeginArgs {
   const float* q;
   float* q_new;
@@ -156,6 +186,12 @@ struct BeginArgs {
   // longest first, so the active set is always a prefix); nullptr = identity.  q / p0 / z are chain-indexed,
   // q_new / p_new / kin0 are row-indexed.
   const int32_t* perm;
+  // streaming schedule: only rows whose op has OP_BEGIN take part; their step index is step[r] (+1 after a FINISH);
+  // stream_lo is the run's first step, z / kin0 are offset by the step (kin0: parity buffers of C_total doubles)
+  const uint32_t* code;
+  const int32_t* step;
+  int64_t z_step_stride;
+  int C_total;
 };
 int launch_hmc_begin(bhmc_ctx* ctx, const BeginArgs& a);
 
@@ -165,7 +201,8 @@ int launch_sumsq(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, c
                  const int64_t* len, double* out);
 
 int launch_prior_energy(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, const int64_t* off,
-                        const int64_t* len, const double* cv, double* sumsq_scratch, double* out);
+                        const int64_t* len, const double* cv, double* sumsq_scratch, double* out,
+                        const uint32_t* code = nullptr, uint32_t flag = 0);  // code: write out[r] only where code[r] & flag
 
 struct AcceptArgs {
   float* q;            // in/out: current state, overwritten by the proposal where accepted
@@ -192,6 +229,11 @@ struct AcceptArgs {
   double* accept_prob; // [C] or nullptr
   int32_t* accepted;   // [C] or nullptr
   const int32_t* perm; // row -> chain (see BeginArgs); q / p_out / u / outputs are chain-indexed
+  // streaming schedule: only rows with OP_FINISH; t = step[r] offsets the Philox stream, u, the outputs (t*C_total
+  // rows) and selects the kin0 parity buffer
+  const uint32_t* code;
+  const int32_t* step;
+  int C_total;
 };
 int launch_accept(bhmc_ctx* ctx, const AcceptArgs& a);
 

@@ -54,6 +54,15 @@ __device__ __forceinline__ float4 load_z(const float* z, int64_t ld_z, int c, in
 __global__ void __launch_bounds__(TPB) k_hmc_begin(BeginArgs a) {
   int r = blockIdx.y;                    // working row
   int c = a.perm ? a.perm[r] : r;        // chain held by this row
+  int t = 0;
+  if (a.code) {  // streaming schedule: block-uniform opt-out, per-row step
+    const uint32_t op = a.code[r];
+    if (!(op & OP_BEGIN)) return;
+    t = a.step[r] + ((op & OP_FINISH) ? 1 : 0);
+    a.kin0 += (int64_t)(t & 1) * a.C_total;
+    if (a.z) a.z += (int64_t)t * a.z_step_stride;
+    a.stream_lo += (uint32_t)t;
+  }
   int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 4;
   double k = 0.0;
   if (i < a.P) {
@@ -73,7 +82,7 @@ __global__ void __launch_bounds__(TPB) k_hmc_begin(BeginArgs a) {
 
 int launch_hmc_begin(bhmc_ctx* ctx, const BeginArgs& a) {
   GroupTimer t(ctx, KG_UPDATE);
-  BHMC_CUDA_OK(cudaMemsetAsync(a.kin0, 0, sizeof(double) * a.C, ctx->stream));
+  if (!a.code) BHMC_CUDA_OK(cudaMemsetAsync(a.kin0, 0, sizeof(double) * a.C, ctx->stream));
   dim3 grid((unsigned)ceil_div(ceil_div(a.P, 4), TPB), a.C);
   k_hmc_begin<<<grid, TPB, 0, ctx->stream>>>(a);
   ctx->launches++;
@@ -131,6 +140,84 @@ int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a) {
     k_hmc_update<true><<<grid, TPB, 0, ctx->stream>>>(a);
   else
     k_hmc_update<false><<<grid, TPB, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Streaming schedule: the same kick / drift arithmetic as k_hmc_update (hmc.py:51-54), but every row executes the op
+// its own trajectory has reached.  Thread 0 of a row's first block also does the row's scalar bookkeeping.
+__global__ void __launch_bounds__(TPB) k_stream_update(StreamUpdateArgs a) {
+  const int r = blockIdx.y;
+  const uint32_t op = a.code[r];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.kin1[r] = 0.0;  // consumed by the previous phase's accept; re-accumulated by this phase's kinetic kernel
+    if (op & OP_LATCH) {
+      a.stat_cur[r] = a.stat[r];
+      a.stat_new[r] = a.stat[r];
+      a.kin0[(int64_t)((a.step[r] + 1) & 1) * a.C_total + r] = 0.0;  // the NEXT step's start-of-step buffer
+    }
+    if (op & OP_POST) a.stat_new[r] = a.stat[r];
+  }
+  if (!(op & (OP_POST | OP_PRE))) return;
+  const int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 4;
+  if (i >= a.P) return;
+  const int pv = (op >> 8) & 15, v = (op >> 12) & 15;
+  const int64_t post_off = a.off[pv], post_len = (op & OP_POST) ? a.len[pv] : 0;
+  const int64_t pre_off = a.off[v], pre_len = (op & OP_PRE) ? a.len[v] : 0;
+  const bool hit_post = post_len > 0 && i < post_off + post_len && i + 4 > post_off;
+  const bool hit_pre = pre_len > 0 && i < pre_off + pre_len && i + 4 > pre_off;
+  if (!hit_post && !hit_pre) return;
+  const int64_t o = (int64_t)r * a.ld + i;
+  float4 p4 = ld4(a.p + o);
+  float4 g4 = ld4(a.g + o);
+  float4 q4 = hit_pre ? ld4(a.q + o) : make_float4(0, 0, 0, 0);
+  float pe[4] = {p4.x, p4.y, p4.z, p4.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, qe[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t idx = i + e;
+    if (idx >= post_off && idx < post_off + post_len) pe[e] = 1.0f * pe[e] - a.a_post * ge[e];
+    if (idx >= pre_off && idx < pre_off + pre_len) {
+      pe[e] = pe[e] - a.a_pre * ge[e];
+      qe[e] = qe[e] + a.eps * pe[e];
+    }
+  }
+  st4(a.p + o, make_float4(pe[0], pe[1], pe[2], pe[3]));
+  if (hit_pre) st4(a.q + o, make_float4(qe[0], qe[1], qe[2], qe[3]));
+}
+
+int launch_stream_update(bhmc_ctx* ctx, const StreamUpdateArgs& a) {
+  GroupTimer t(ctx, KG_UPDATE);
+  dim3 grid((unsigned)ceil_div(ceil_div(a.P, 4), TPB), a.rows);
+  k_stream_update<<<grid, TPB, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+__global__ void __launch_bounds__(TPB) k_stream_kinetic(const float* p, int64_t ld, int64_t P, const uint32_t* code,
+                                                        double* kin) {
+  const int r = blockIdx.y;
+  if (!(code[r] & OP_FINISH)) return;
+  const int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 4;
+  double k = 0.0;
+  if (i < P) {
+    float4 v = ld4(p + (int64_t)r * ld + i);
+    k = (double)v.x * v.x;
+    if (i + 1 < P) k += (double)v.y * v.y;
+    if (i + 2 < P) k += (double)v.z * v.z;
+    if (i + 3 < P) k += (double)v.w * v.w;
+    k *= 0.5;
+  }
+  block_atomic_add(k, kin + r);
+}
+
+int launch_stream_kinetic(bhmc_ctx* ctx, const float* p, int64_t ld, int64_t P, int rows, const uint32_t* code,
+                          double* kin) {
+  GroupTimer t(ctx, KG_UPDATE);
+  dim3 grid((unsigned)ceil_div(ceil_div(P, 4), TPB), rows);
+  k_stream_kinetic<<<grid, TPB, 0, ctx->stream>>>(p, ld, P, code, kin);
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
@@ -203,9 +290,10 @@ struct CvArr {
   int n;
   double cv[BHMC_MAX_VARS];
 };
-__global__ void k_prior_combine(const double* sumsq, CvArr cv, double* out, int C) {
+__global__ void k_prior_combine(const double* sumsq, CvArr cv, double* out, int C, const uint32_t* code, uint32_t flag) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (code && !(code[c] & flag)) return;
   double e = 0.0;
   for (int v = 0; v < cv.n; ++v) e += cv.cv[v] * sumsq[(int64_t)c * cv.n + v];
   out[c] = e;
@@ -214,12 +302,13 @@ __global__ void k_prior_combine(const double* sumsq, CvArr cv, double* out, int 
 // out[c] = sum_v cv[v] * |q_v[c]|^2 : the quadratic log-prior part of the Metropolis energy
 // (models/gpu/softmax.py:29-39, models/gpu/mlp.py:40-45)
 int launch_prior_energy(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_vars, const int64_t* off,
-                        const int64_t* len, const double* cv, double* sumsq_scratch, double* out) {
+                        const int64_t* len, const double* cv, double* sumsq_scratch, double* out, const uint32_t* code,
+                        uint32_t flag) {
   BHMC_TRY(launch_sumsq(ctx, q, ld, C, n_vars, off, len, sumsq_scratch));
   CvArr a;
   a.n = n_vars;
   for (int v = 0; v < n_vars; ++v) a.cv[v] = cv[v];
-  k_prior_combine<<<(C + 127) / 128, 128, 0, ctx->stream>>>(sumsq_scratch, a, out, C);
+  k_prior_combine<<<(C + 127) / 128, 128, 0, ctx->stream>>>(sumsq_scratch, a, out, C, code, flag);
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
@@ -231,6 +320,17 @@ int launch_prior_energy(bhmc_ctx* ctx, const float* q, int64_t ld, int C, int n_
 __global__ void __launch_bounds__(TPB) k_accept(AcceptArgs a) {
   int r = blockIdx.y;                    // working row (energies, proposal)
   int c = a.perm ? a.perm[r] : r;        // chain (state, draws, outputs)
+  if (a.code) {  // streaming schedule: block-uniform opt-out, per-row step
+    if (!(a.code[r] & OP_FINISH)) return;
+    const int64_t t = a.step[r];
+    a.kin0 += (t & 1) * a.C_total;
+    a.stream_lo += (uint32_t)t;
+    if (a.u) a.u += t * a.C_total;
+    if (a.sample) a.sample += t * a.C_total * a.P;
+    if (a.loss) a.loss += t * a.C_total;
+    if (a.accept_prob) a.accept_prob += t * a.C_total;
+    if (a.accepted) a.accepted += t * a.C_total;
+  }
   double u_cur = a.ea * a.stat_cur[r] + a.eb, u_new = a.ea * a.stat_new[r] + a.eb;
   if (a.extra_cur) {
     u_cur += a.extra_cur[r];

@@ -248,13 +248,14 @@ class SamplerHandle:
         return out
 
     def hmc_run(self, n_steps, step_size, path_length, *, row0=0, nrows=0, step0=0, z_momentum=None, u_path=None,
-                u_accept=None, z_noise=None, keep_samples=True, keep_stats=True):
+                u_accept=None, z_noise=None, keep_samples=True, keep_stats=True, schedule="auto"):
         """Runs n_steps transitions.  Injected draws: z_momentum [n,C,P] device fp32; u_path / u_accept
         [n,C] host float64; z_noise [n, iters, C, P] device fp32 (SGHMC).  Returns a dict of device tensors."""
         ctx = self.ctx
         run = HmcRun()
         run.n_steps, run.step_size, run.path_length = n_steps, step_size, path_length
         run.row0, run.nrows, run.step0 = row0, nrows, step0
+        run.schedule = {"auto": 0, "lockstep": 1, "streaming": 2}[schedule]
         keep = []
         if z_momentum is not None:
             z_momentum = z_momentum.to(ctx.device, torch.float32).contiguous()
@@ -283,6 +284,7 @@ class SamplerHandle:
         check(ctx.L.bhmc_sampler_hmc_run(self.handle, C.byref(run)))
         out["n_grad_evals"] = int(run.n_grad_evals)
         out["n_grad_launched"] = int(run.n_grad_launched)
+        out["n_phases"] = int(run.n_phases)  # gradient launches of the streaming schedule (0 = lockstep ran)
         out["_keep"] = (keep, z_momentum, z_noise)
         return out
 

@@ -195,7 +195,18 @@ typedef struct bhmc_hmc_run {
   /* outputs, HOST                                                                          */
   int64_t n_grad_evals;   /* chain-gradient evaluations applied (masked chains excluded)     */
   int64_t n_grad_launched;/* chain-gradient evaluations computed (incl. masked)              */
+  /* schedule of the chains across the n_steps transitions of this call:
+   *   BHMC_SCHED_AUTO (0)      streaming for HMC with per-chain path lengths and n_steps >= 2, else lockstep
+   *   BHMC_SCHED_LOCKSTEP (1)  every chain starts transition t together; short trajectories idle (compacted away)
+   *   BHMC_SCHED_STREAMING (2) asynchronous chains: a chain starts its next transition as soon as its own trajectory
+   *                            ends, so every gradient launch carries all unfinished chains.  Same draws (Philox keyed
+   *                            by chain and step, or the same injected tapes), same arithmetic -> same samples. */
+  int32_t schedule;
+  int32_t n_phases;       /* out: gradient launches issued                                   */
 } bhmc_hmc_run;
+#define BHMC_SCHED_AUTO 0
+#define BHMC_SCHED_LOCKSTEP 1
+#define BHMC_SCHED_STREAMING 2
 /* run n_steps transitions of HMC (kind HMC) or SGHMC (kind SGHMC) for all chains */
 int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run);
 

@@ -213,8 +213,9 @@ def test_sgd_fit_golden(prec):
 # ------------------------------------------------------------------------------------------------
 # batched chains with ragged path lengths vs independent oracle chains
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sched", ["lockstep", "streaming"])
 @pytest.mark.parametrize("prec", PRECS)
-def test_hmc_ragged_chains_vs_oracle(prec):
+def test_hmc_ragged_chains_vs_oracle(prec, sched):
     rs = np.random.RandomState(5)
     N, D, K, C, alpha, eps, path = 400, 30, 10, 6, 0.01, 5e-4, 4e-3
     X = rs.rand(N, D)
@@ -232,7 +233,9 @@ def test_hmc_ragged_chains_vs_oracle(prec):
     z = rs.normal(size=(n_steps, C, h.P))
     u1 = rs.rand(n_steps, C)
     u2 = rs.rand(n_steps, C)
-    out = s.hmc_run(n_steps, eps, path, z_momentum=torch.as_tensor(z, dtype=torch.float32), u_path=u1, u_accept=u2)
+    out = s.hmc_run(n_steps, eps, path, z_momentum=torch.as_tensor(z, dtype=torch.float32), u_path=u1, u_accept=u2,
+                    schedule=sched)
+    assert (out["n_phases"] > 0) == (sched == "streaming")
     samples = out["samples"].cpu().numpy()
     acc = out["accept_prob"].cpu().numpy()
     n_grad = 0
@@ -403,3 +406,45 @@ def test_posterior_statistics_softmax_independent_rng():
     pm = got.mean(0)
     pred = m.predict({"weights": pm[:D * K].reshape(D, K), "bias": pm[D * K:]}, X)
     assert abs(float((pred == y).mean()) - acc_of(pm)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming schedule (asynchronous chains) == lockstep schedule
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prior", ["cpu", "gpu"])
+@pytest.mark.parametrize("prec", PRECS)
+def test_streaming_schedule_matches_lockstep(prec, prior):
+    """A chain starts its next transition as soon as its own trajectory ends (bhmc_hmc_run.schedule): draws are keyed
+    by (chain, step), so the accept decisions and (to round-off) the samples must be the ones of the lockstep schedule, while
+    the number of gradient launches drops from sum_t max_c(L) to max_c sum_t(L)."""
+    from dropout_hamiltonian_montecarlo_b200._lib import PREC, PRIOR
+    from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle, SoftmaxHandle, default_context
+    rs = np.random.RandomState(3)
+    n, d, K, C, steps = 300, 24, 5, 13, 7
+    X = torch.as_tensor(rs.rand(n, d).astype(np.float32)).cuda()
+    y = torch.as_tensor(rs.randint(0, K, n).astype(np.int32)).cuda()
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, n, d, K, 0.5, PRIOR[prior])
+    h.bind(X, y, 1 | (1 << PREC[prec]))
+    q0 = rs.normal(0, 0.1, (C, h.P)).astype(np.float32)
+    outs = {}
+    for sched in ("lockstep", "streaming"):
+        s = SamplerHandle(ctx, h, 0, C, seed=11, precision=PREC[prec], sweep=list(zip(h.var_off, h.var_len)))
+        s.set_q(q0)
+        o = s.hmc_run(steps, 2e-3, 3e-2, step0=5, schedule=sched)  # E[L] = 15, includes L <= 1 steps
+        outs[sched] = {k: o[k].cpu().numpy() for k in ("samples", "loss", "accept_prob", "accepted")}
+        outs[sched]["q"] = s.get(0).copy()
+        outs[sched]["meta"] = (o["n_grad_evals"], o["n_grad_launched"], o["n_phases"])
+        s.close()
+    a, b = outs["lockstep"], outs["streaming"]
+    assert a["meta"][0] == b["meta"][0] and b["meta"][2] > 0 and a["meta"][2] == 0
+    assert b["meta"][1] <= a["meta"][1]  # never more masked work than lockstep
+    np.testing.assert_array_equal(a["accepted"], b["accepted"])
+    assert 0 < a["accepted"].mean() < 1
+    # identical decisions; positions agree to fp32 round-off only: a gradient launch of a different set of chains
+    # uses a different split of the row reduction (split-K plan), i.e. a different fp32 summation order
+    np.testing.assert_allclose(a["samples"], b["samples"], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(a["q"], b["q"], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)
+    np.testing.assert_allclose(a["accept_prob"], b["accept_prob"], rtol=1e-4, atol=1e-9)
+    h.close()
