@@ -67,7 +67,9 @@ def synth(N, D, K, seed, device=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region, every 100 ms, in-process through NVML
+    (nvidia_ml_py).  A polling `nvidia-smi -lms 100` subprocess was measured to stall kernel launches for 0.2-0.3 s
+    at a time (stage21 logs), which lands in the timed region; it remains the fallback when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -75,45 +77,81 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []     # (sm_mhz, max_mhz, set of reasons)
         self.first = 0
         self.proc = None
+        self._stop = False
+        self.source = None
+
+    # ---- NVML path ----
+    def _nvml_loop(self, nv, h):
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(n, getattr(nv, a, None) or getattr(nv, b, 0)) for n, a, b in names]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(h))
+                self.rows.append((sm, mx, {n for n, b in bits if b and (r & b)}))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    # ---- nvidia-smi fallback ----
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                reasons = {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8])
+                           if v.lower().startswith("active")}
+                self.rows.append((float(r[1]), float(r[2]), reasons))
+            except Exception:
+                pass
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.source = "nvml"
+            threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True).start()
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi"
+            threading.Thread(target=self._smi_loop, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def mark(self):
-        """Start of the timed region: only samples taken from here on are reported.  (nvidia-smi is started before
-        the warm-up because its NVML initialisation takes ~1 s during which kernel launches can stall.)"""
+        """Start of the timed region: only samples taken from here on are reported (the sampler is started before
+        the warm-up so that its initialisation is over by then)."""
         self.first = len(self.rows)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows[self.first:]:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
+        time.sleep(0.12)
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = self.rows[self.first:]
+        sm = [r[0] for r in rows]
+        mx = [r[1] for r in rows]
+        reasons = set().union(*[r[2] for r in rows]) if rows else set()
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def peaks():
@@ -247,9 +285,17 @@ def run_ours(args, wl):
         return s.hmc_run(n, wl["eps"], wl["path"], step0=i0, keep_samples=True, keep_stats=True, schedule=args.schedule)
 
     clocks = ClockSampler(local)
-    clocks.start()
+    if not os.environ.get("BENCH_NO_CLOCKS"):  # diagnosis only: a line without clocks is not a valid bench line
+        clocks.start()
+    warm_groups = None
     if args.warmup > 0:
-        run_steps(0, args.warmup)
+        ctx.timing(1)  # every kernel group, for the share table (the timed region records the GEMM groups only)
+        ow = run_steps(0, args.warmup)
+        ctx.sync()
+        tw = [ctx.kernel_time(g)[0] for g in range(4)]
+        warm_groups = {"fwd": tw[0], "bwd": tw[1], "prep": tw[2], "update": tw[3],
+                       "per": "warm-up region (%d steps, %d chain-evals), all kernel groups timed" % (args.warmup, ow["n_grad_evals"])}
+        ctx.timing(0)
     ctx.sync()
     # L2 note: one gradient evaluation streams X (94-376 MB) + (P-Y)^T (77-245 MB) -- far larger than the
     # 126 MB L2 -- so consecutive launches cannot be served from cache; no explicit flush is needed.
@@ -257,7 +303,11 @@ def run_ours(args, wl):
         dist.barrier()
     torch.cuda.synchronize()
     clocks.mark()
-    ctx.timing(True)
+    # live kernel timing for the roofline: CUDA events around every 8th forward / backward launch (every record
+    # costs stream overlap; sampling keeps the perturbation of `value` below 1 %); the chains those launches carried
+    # are counted with them, so flops / time is exact for the sample
+    ctx.timing_stride(int(os.environ.get("BENCH_KTIMING_STRIDE", "8")))
+    ctx.timing(0 if os.environ.get("BENCH_NO_KTIMING") else 2)
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_applied = n_launched = 0
@@ -272,12 +322,13 @@ def run_ours(args, wl):
     ms = e0.elapsed_time(e1)
     t_fwd, n_fwd = ctx.kernel_time(0)
     t_bwd, n_bwd = ctx.kernel_time(1)
-    t_prep, _ = ctx.kernel_time(2)
-    t_upd, _ = ctx.kernel_time(3)
-    ctx.timing(False)
+    u_fwd, u_bwd = ctx.kernel_units(0), ctx.kernel_units(1)
+    ctx.timing_stride(1)
+    ctx.timing(0)
     launches = ctx.launches - launches0
     clk = clocks.stop()
     n_launched_local = float(n_launched)  # chain-gradient evaluations this rank's GEMM launches processed
+    stride = int(os.environ.get("BENCH_KTIMING_STRIDE", "8"))
     stats = torch.tensor([ms, float(n_applied), float(n_launched)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
@@ -329,7 +380,7 @@ def run_ours(args, wl):
         from dropout_hamiltonian_montecarlo_b200.ess import ess as ess_fn
         s2 = SamplerHandle(ctx, h, 0, C, seed=4321, chain_id0=rank * C, precision=PREC[prec], shared_path=shared)
         s2.set_q(np.zeros((C, h.P), np.float32))
-        e_eps, e_path = 3e-7, 3e-5
+        e_eps, e_path = args.ess_eps, args.ess_eps * args.ess_L
         s2.hmc_run(args.ess_burnin, e_eps, e_path, step0=0, keep_samples=False)
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -360,11 +411,11 @@ def run_ours(args, wl):
         # figure divided by the mean duration.
         flops_eval = 2.0 * N * D * K
         dom = "fwd" if t_fwd >= t_bwd else "bwd"
-        t_dom, n_dom = (t_fwd, n_fwd) if dom == "fwd" else (t_bwd, n_bwd)
+        t_dom, n_dom, u_dom = (t_fwd, n_fwd, u_fwd) if dom == "fwd" else (t_bwd, n_bwd, u_bwd)
         avg = (t_dom / max(1, n_dom)) * 1e-3
-        flops_launch = flops_eval * n_launched_local / max(1, n_dom)
+        flops_launch = flops_eval * u_dom / max(1, n_dom)   # chains carried by the bracketed launches
         achieved = flops_launch / avg / 1e12 if avg > 0 else 0.0
-        traffic, traffic_src = ncu_traffic(dom, prec, wl, n_launched_local / max(1, n_dom))
+        traffic, traffic_src = ncu_traffic(dom, prec, wl, u_dom / max(1, n_dom))
         mma_mult = 3.0 if prec == "bf16x3" else 1.0
         cpu = None if args.no_cpu_baseline else cpu_reference_rate(wl)
         line = {
@@ -383,9 +434,12 @@ def run_ours(args, wl):
             "roofline": {"bound": "tensor", "kernel": "k_tc_gemm<%s>" % dom, "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": src, "algorithmic_flops_per_launch": flops_launch,
-                         "chains_per_launch_mean": n_launched_local / max(1, n_dom), "avg_launch_ms": avg * 1e3,
+                         "chains_per_launch_mean": u_dom / max(1, n_dom), "avg_launch_ms": avg * 1e3,
+                         "launches_timed": int(n_dom), "timing": "CUDA events around every %d-th launch of the GEMM groups "
+                         "inside the timed region" % stride,
                          "mma_flops_issued_over_algorithmic": mma_mult,
-                         "group_ms": {"fwd": t_fwd, "bwd": t_bwd, "prep": t_prep, "update": t_upd, "step_total": ms}},
+                         "group_ms": {"fwd_sampled": t_fwd, "bwd_sampled": t_bwd, "step_total": ms},
+                         "warmup_group_ms": warm_groups},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if ess_info is not None:
@@ -413,6 +467,8 @@ def main():
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--ess-steps", type=int, default=40)
     ap.add_argument("--ess-burnin", type=int, default=10)
+    ap.add_argument("--ess-eps", type=float, default=3e-7)
+    ap.add_argument("--ess-L", type=float, default=100.0, help="path_length / step_size of the ESS run (E[L])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -63,6 +63,8 @@ _PROTOS = {
     "bhmc_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "bhmc_ctx_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "bhmc_ctx_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "bhmc_ctx_timing_stride": (C.c_int, [C.c_void_p, C.c_int]),
+    "bhmc_ctx_kernel_units": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "bhmc_softmax_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32,
                                       C.POINTER(C.c_void_p)]),
     "bhmc_logistic_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.POINTER(C.c_void_p)]),

@@ -7,6 +7,7 @@
 // for C chains at once, enqueueing kernels on one stream with no host round-trip inside a step.
 #include <stdarg.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -53,6 +54,9 @@ int bhmc_ctx::get_scratch(int slot, size_t bytes, void** out) {
 
 int bhmc_ctx::get_pinned(size_t bytes, void** out) {
   if (bytes > pinned_bytes) {
+    // page-locking is slow and erratic (measured: up to 0.7 s for a few MB on a busy host) and a re-allocation lands
+    // inside whatever call needed the larger buffer: start with 32 MB and grow geometrically
+    bytes = std::max(bytes + bytes / 2, (size_t)32 << 20);
     if (pinned) {
       BHMC_CUDA_OK(cudaStreamSynchronize(stream));
       BHMC_CUDA_OK(cudaFreeHost(pinned));
@@ -67,9 +71,15 @@ int bhmc_ctx::get_pinned(size_t bytes, void** out) {
 }
 
 void bhmc_ctx::begin_group(int g) {
-  if (!timing) return;
+  sampled[g] = false;
+  if (!timing || (timing == 2 && g >= KG_PREP)) return;
+  if ((seen[g]++ % timing_stride) != 0) return;
+  sampled[g] = true;
+  units_acc[g] += (double)cur_units;
   if (used[g] == pool[g].size()) {
-    if (pool[g].size() >= 4096) {
+    // flushing synchronises the stream and reads every event back (cudaEventElapsedTime, ~10 us each): the GPU
+    // idles for 0.1-0.7 s, which would land inside whatever region is being timed -> only when the pool is huge
+    if (pool[g].size() >= 65536) {
       flush_timing();
     } else {
       EventPair ep;
@@ -82,7 +92,7 @@ void bhmc_ctx::begin_group(int g) {
 }
 
 void bhmc_ctx::end_group(int g) {
-  if (!timing) return;
+  if (!sampled[g]) return;
   cudaEventRecord(pool[g][used[g]].b, stream);
   used[g]++;
 }
@@ -159,20 +169,33 @@ int64_t bhmc_ctx_launch_count(const bhmc_ctx* ctx) { return ctx ? ctx->launches 
 int bhmc_ctx_timing(bhmc_ctx* ctx, int enable) {
   BHMC_CHECK_ARG(ctx, "ctx is NULL");
   BHMC_TRY(ctx->flush_timing());
-  ctx->timing = enable != 0;
-  for (int g = 0; g < KG_COUNT; ++g) ctx->ms_acc[g] = 0, ctx->n_acc[g] = 0;
+  ctx->timing = enable;  // 1 = every kernel group; 2 = the GEMM groups only (every event record between two kernels
+                         // costs ~1-2 us of overlap on the stream: half the records, half the perturbation)
+  for (int g = 0; g < KG_COUNT; ++g) ctx->ms_acc[g] = 0, ctx->n_acc[g] = 0, ctx->seen[g] = 0, ctx->units_acc[g] = 0;
   if (ctx->timing) {
     // create the whole event pool now: cudaEventCreate costs microseconds and would otherwise be paid lazily
     // inside the region being timed (8 events per gradient evaluation)
     BHMC_CUDA_OK(cudaSetDevice(ctx->device));
     for (int g = 0; g < KG_COUNT; ++g)
-      while (ctx->pool[g].size() < 4096) {
+      while (ctx->pool[g].size() < 8192) {
         EventPair ep;
         BHMC_CUDA_OK(cudaEventCreate(&ep.a));
         BHMC_CUDA_OK(cudaEventCreate(&ep.b));
         ctx->pool[g].push_back(ep);
       }
   }
+  return BHMC_OK;
+}
+
+int bhmc_ctx_timing_stride(bhmc_ctx* ctx, int stride) {
+  BHMC_CHECK_ARG(ctx && stride >= 1, "bad argument");
+  ctx->timing_stride = stride;
+  return BHMC_OK;
+}
+
+int bhmc_ctx_kernel_units(bhmc_ctx* ctx, int group, double* units) {
+  BHMC_CHECK_ARG(ctx && units && group >= 0 && group < KG_COUNT, "bad argument");
+  *units = ctx->units_acc[group];
   return BHMC_OK;
 }
 
@@ -301,6 +324,10 @@ struct SoftmaxModel : ModelBase {
     const int rc = grad(q, C, ld, 0, nrows, prec, g, stat);
     std::swap(d, db);
     return rc;
+  }
+  int grad_fused_step(int C, int64_t ld, int64_t row0, int64_t nrows, int prec, double* stat, const FusedStep& fs) override {
+    if (logistic || prec == BHMC_PREC_FP32) return BHMC_ERR_UNSUPPORTED;
+    return tc_softmax_grad(ctx, d, fs.q, C, ld, alpha, row0, nrows, nullptr, stat, prec == BHMC_PREC_BF16X3, &fs);
   }
   int grad_softmax(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) {
     switch (prec) {
@@ -611,6 +638,7 @@ struct bhmc_sampler {
   void* hook_user = nullptr;
   // gradient (or log-lik only when g == nullptr) of the first `rows` working rows, then the optional hook
   int eval(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat) {
+    ctx->cur_units = rows;
     BHMC_TRY(model->grad(q, rows, ld, row0, nrows, cfg.precision, g, stat));
     if (hook && hook(hook_user, g, stat, rows, ld) != 0) {
       bhmc::set_error("gradient hook reported a failure");
@@ -735,6 +763,8 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   bool need_extra = false;
   for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
 
+  struct timespec ts_setup;
+  clock_gettime(CLOCK_MONOTONIC, &ts_setup);
   // total gradient slots per chain: per transition 1 (start point) + (L-1)*nsw (sub-steps)
   std::vector<int64_t> T(C, 0);
   run->n_grad_evals = 0;
@@ -798,7 +828,7 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   }
   if (run->u_accept_host) memcpy(uacc_h, run->u_accept_host, u_bytes);
   void* dev = nullptr;
-  BHMC_TRY(ctx->get_scratch(6, 2 * code_bytes + perm_bytes + u_bytes, &dev));
+  BHMC_TRY(ctx->get_scratch(6, std::max(2 * code_bytes + perm_bytes + u_bytes, (size_t)32 << 20), &dev));
   const uint32_t* code_d = (const uint32_t*)dev;
   const int32_t* step_d = (const int32_t*)((char*)dev + code_bytes);
   const int32_t* perm_d = (const int32_t*)((char*)dev + 2 * code_bytes);
@@ -835,6 +865,14 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   u.C_total = C;
 
   run->n_grad_launched = 0;
+  static int prof_host = -1;
+  if (prof_host < 0) prof_host = getenv("BHMC_PROF_HOST") ? 1 : 0;
+  struct timespec ts0, ts1;
+  if (prof_host) {
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    fprintf(stderr, "[bhmc prof host] streaming run: setup (op table, staging buffers, upload) %.2f ms\n",
+            1e3 * ((ts0.tv_sec - ts_setup.tv_sec) + 1e-9 * (ts0.tv_nsec - ts_setup.tv_nsec)));
+  }
   for (int64_t j = 0; j <= J; ++j) {
     const int rows = rows_el[j];
     const uint32_t* cj = code_d + j * C;
@@ -914,6 +952,12 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
     run->n_grad_launched += rows_grad[j];
   }
   run->n_phases = (int32_t)J;
+  if (prof_host) {
+    clock_gettime(CLOCK_MONOTONIC, &ts1);
+    const double host_s = (ts1.tv_sec - ts0.tv_sec) + 1e-9 * (ts1.tv_nsec - ts0.tv_nsec);
+    fprintf(stderr, "[bhmc prof host] streaming run: %lld phases enqueued in %.1f ms of host time (%.1f us per phase, "
+                    "asynchronous: the GPU may still be running)\n", (long long)J, 1e3 * host_s, 1e6 * host_s / (double)J);
+  }
   return BHMC_OK;
 }
 
@@ -1186,10 +1230,43 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
   int64_t k = 0;  // global minibatch counter (indexes the injected tape and the Philox stream)
   run->n_grad_evals = 0;
   const bool sgd = cfg.kind == BHMC_KIND_SGD;
+  // fused gradient + update + next operand preparation (tensor-core softmax path, single GPU): 3 launches per
+  // minibatch instead of 5.  BHMC_FUSED_STEP=0 keeps the separate kernels (A/B measurements).
+  static int fused_env = -1;
+  if (fused_env < 0) {
+    const char* e = getenv("BHMC_FUSED_STEP");
+    fused_env = e ? atoi(e) : 1;
+  }
+  bool try_fused = fused_env && !s->hook && !(run->dropout_keep > 0.0);
+  bool wt_ready = false;
   for (int e = 0; e < run->burnin + run->epochs; ++e) {
     const bool sampling = e >= run->burnin;
     for (int64_t j = 0; j < nb; ++j, ++k) {
       const int64_t row0 = j * run->batch_size;
+      if (try_fused) {
+        FusedStep fs{};
+        fs.kind = cfg.kind;
+        fs.q = s->q;
+        fs.p = s->p;
+        fs.eps = sgd ? (float)run->step_size : (float)eps;
+        fs.gamma = (float)run->gamma;
+        fs.z = run->z_dev ? run->z_dev + (size_t)k * C * P : nullptr;
+        fs.ld_z = P;
+        fs.seed = cfg.seed;
+        fs.chain_id0 = cfg.chain_id0;
+        fs.stream_lo = (uint32_t)(run->step0 + k);
+        fs.stream_hi = TAG_NOISE | (uint32_t)(((uint64_t)(run->step0 + k) >> 32) & 0xffffff);
+        fs.wt_ready = wt_ready;
+        const int rc = mb->grad_fused_step(C, ld, row0, run->batch_size, cfg.precision, stat, fs);
+        if (rc == BHMC_OK) {
+          wt_ready = true;
+          run->n_grad_evals += C;
+          if (!sgd && sampling) eps = run->step_size * (1.0 / (1.0 + (double)j * decay * num_batches));
+          continue;
+        }
+        if (rc != BHMC_ERR_UNSUPPORTED) return rc;
+        try_fused = false;
+      }
       if (run->dropout_keep > 0.0) {
         BHMC_CHECK_ARG(sgd && !s->hook, "input dropout is sgd.fit_dropout only (single GPU)");
         const uint8_t* mk = run->mask_dev ? run->mask_dev + (size_t)k * run->batch_size * mb->n_features() : nullptr;
@@ -1228,6 +1305,7 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
         double a, b, cv[BHMC_MAX_VARS];
         mb->energy_coeffs(run->batch_size, &a, &b, cv);
         BHMC_TRY(s->eval(s->q, C, row0, run->batch_size, nullptr, stat));
+        wt_ready = false;  // that forward accumulated into stat: the next fused step must re-zero it (k_tc_prep)
         if (run->dropout_keep > 0.0) {  // sgd.py:67: loss = -log_likelihood(par, last batch), no prior, no 1/n
           BHMC_TRY(launch_affine(ctx, stat, -1.0, 0.0, nullptr, run->logp_dev + (size_t)i * C, C));
           if (run->samples_dev) BHMC_TRY(launch_copy_rows(ctx, s->q, ld, run->samples_dev + (size_t)i * C * P, P, P, C));

@@ -51,11 +51,18 @@ struct bhmc_ctx {
   int sm_count = 148;
   int64_t launches = 0;
   // optional per-group device timing (CUDA events on the launching stream)
-  bool timing = false;
+  int timing = 0;  // 0 off, 1 every kernel group, 2 only the GEMM groups (KG_FWD, KG_BWD)
   std::vector<bhmc::EventPair> pool[bhmc::KG_COUNT];
   size_t used[bhmc::KG_COUNT] = {0, 0, 0, 0};
   double ms_acc[bhmc::KG_COUNT] = {0, 0, 0, 0};
   int64_t n_acc[bhmc::KG_COUNT] = {0, 0, 0, 0};
+  // sampled timing: only every timing_stride-th launch group of a kind is bracketed by events; units_acc sums the
+  // work units (chains) of exactly the bracketed launches, so time / units stays consistent under ragged launches
+  int timing_stride = 1;
+  int64_t seen[bhmc::KG_COUNT] = {0, 0, 0, 0};
+  bool sampled[bhmc::KG_COUNT] = {false, false, false, false};
+  double units_acc[bhmc::KG_COUNT] = {0, 0, 0, 0};
+  int64_t cur_units = 0;  // set by the callers of model->grad (rows of this launch)
   // grow-only device scratch
   void* scratch[8] = {nullptr};
   size_t scratch_bytes[8] = {0};
@@ -84,6 +91,21 @@ struct GroupTimer {
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Minibatch samplers (SGLD / SGD) on small windows are bound by launch latency, not throughput: the split-K reduce,
+// the parameter update and the operand preparation of the NEXT evaluation are one kernel (k_tc_reduce_step).
+struct FusedStep {
+  int kind;            // BHMC_KIND_SGLD: p = 2 eps z - eps/2 g, q += p (sgld.py:31-46); BHMC_KIND_SGD: m = gamma m - eps g, q += m
+  float* q;            // chain state, updated in place (the gradient is evaluated at its value on entry)
+  float* p;            // SGLD: momentum out; SGD: heavy-ball momentum in/out
+  float eps, gamma;
+  const float* z;      // injected N(0,1) tape [C, ld_z] or nullptr (Philox)
+  int64_t ld_z;
+  uint64_t seed;
+  int64_t chain_id0;
+  uint32_t stream_lo, stream_hi;
+  bool wt_ready;       // the previous fused step already wrote the bf16 operand copy of q and zeroed loglik
+};
+
 // ---------------------------------------------------------------------------------------
 // model interface used by the sampler drivers
 // ---------------------------------------------------------------------------------------
@@ -101,6 +123,9 @@ struct ModelBase {
   virtual void energy_coeffs(int64_t nrows, double* a, double* b, double* cv) const = 0;
   virtual int64_t default_rows() const { return 0; }
   virtual int64_t n_features() const { return 0; }
+  // gradient at fs.q followed by the sampler's parameter update in the same launch sequence (no g materialised);
+  // BHMC_ERR_UNSUPPORTED = caller falls back to grad() + the separate update kernel
+  virtual int grad_fused_step(int, int64_t, int64_t, int64_t, int, double*, const FusedStep&) { return BHMC_ERR_UNSUPPORTED; }
   // sgd.fit_dropout: gradient on rows [row0, row0+nrows) multiplied elementwise by a Bernoulli(keep) mask
   // (mask != nullptr: injected [nrows, D] keep flags; else Philox keyed by (seed, stream))
   virtual int grad_input_dropout(const float*, int, int64_t, int64_t, int64_t, int, float*, double*, const uint8_t*,
@@ -292,7 +317,7 @@ int simt_softmax_predict(bhmc_ctx* ctx, int D, int K, const float* q, int C, int
 int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo);
 void tc_softmax_release(SoftmaxData& d);
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
-                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3);
+                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs = nullptr);
 
 // ---- mlp.cu -----------------------------------------------------------------------------------
 ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int n_out, float alpha, float ratio,

@@ -32,6 +32,7 @@
 #include <algorithm>
 
 #include "internal.cuh"
+#include "philox.cuh"
 
 namespace bhmc {
 
@@ -711,6 +712,78 @@ __global__ void k_tc_reduce(const float* __restrict__ part, int n_split, int64_t
   g[(int64_t)c * ld + i] = v;
 }
 
+// k_tc_reduce + the SGLD / SGD parameter update + k_tc_prep of the NEXT evaluation in one launch.  One thread owns four
+// consecutive parameters (the float4 / Philox block granularity of k_sgld, so the noise is element-for-element the
+// one the separate kernel draws).  g is not materialised.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_tc_reduce_step(const float* __restrict__ part, int n_split, int64_t rows, int64_t cols, int D, int K, int KP, int64_t P,
+                 int64_t ld, float alpha, FusedStep fs, int64_t Dp, __nv_bfloat16* __restrict__ wt_hi,
+                 __nv_bfloat16* __restrict__ wt_lo, double* __restrict__ loglik) {
+  const int c = blockIdx.y;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i == 0 && loglik) loglik[c] = 0.0;  // for the next forward pass
+  if (i >= P) return;
+  float* qrow = fs.q + (int64_t)c * ld + i;
+  float* prow = fs.p + (int64_t)c * ld + i;
+  const float4 q4 = *reinterpret_cast<const float4*>(qrow);
+  float qe[4] = {q4.x, q4.y, q4.z, q4.w}, ge[4], pe[4];
+  int dd[4], kk[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t idx = i + e;
+    dd[e] = (int)(idx / K);
+    kk[e] = (int)(idx - (int64_t)dd[e] * K);
+    float v = 0.f;
+    if (idx < P) {
+      const float* src = part + (int64_t)dd[e] * cols + (int64_t)c * KP + kk[e];
+      for (int s = 0; s < n_split; ++s) v += src[(int64_t)s * rows * cols];
+      v += alpha * qe[e];
+    }
+    ge[e] = v;
+  }
+  if (KIND == BHMC_KIND_SGLD) {
+    float4 z;
+    if (fs.z) {
+      const float* r = fs.z + (int64_t)c * fs.ld_z + i;
+      z.x = r[0];
+      z.y = (i + 1 < P) ? r[1] : 0.f;
+      z.z = (i + 2 < P) ? r[2] : 0.f;
+      z.w = (i + 3 < P) ? r[3] : 0.f;
+    } else {
+      z = philox_normal4(fs.seed, fs.chain_id0 + c, (uint32_t)(i >> 2), fs.stream_lo, fs.stream_hi);
+    }
+    const float ze[4] = {z.x, z.y, z.z, z.w};
+    const float s2 = 2.0f * fs.eps, h = 0.5f * fs.eps;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      pe[e] = s2 * ze[e] - h * ge[e];
+      qe[e] = qe[e] + pe[e];
+    }
+  } else {
+    const float4 m4 = *reinterpret_cast<const float4*>(prow);
+    const float me[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      pe[e] = fs.gamma * me[e] - fs.eps * ge[e];
+      qe[e] = qe[e] + pe[e];
+    }
+  }
+  *reinterpret_cast<float4*>(prow) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+  *reinterpret_cast<float4*>(qrow) = make_float4(qe[0], qe[1], qe[2], qe[3]);
+  // bf16 operand copy of the updated weights (rows of Wt for k >= K or d >= D stay zero from the first k_tc_prep)
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (i + e < P && dd[e] < D) {
+      __nv_bfloat16 hb, lb;
+      split_bf16(qe[e], hb, lb);
+      const int64_t o = ((int64_t)c * KP + kk[e]) * Dp + dd[e];
+      wt_hi[o] = hb;
+      if (wt_lo) wt_lo[o] = lb;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -775,15 +848,24 @@ static int pick_kp(int K) {
 
 // chains per N tile: BN = cpt*KP must be a multiple of 16 and <= 192 (the backward epilogue keeps BN/64 chunks of
 // 16 columns in registers).  Both GEMMs are bound by operand delivery (L2 -> shared memory), so the cost of a
-// tiling is the bytes it streams: every N tile re-reads the 128-row A tile and reads its own BN-row B tile.
-static int pick_cpt(int KP, int C) {
+// tiling is the bytes one work item streams -- every N tile re-reads the 128-row A tile and reads its own BN-row B
+// tile -- times the number of rounds the persistent CTAs need.  Minibatch windows have fewer work items than SMs
+// (one round whatever the tiling), where the narrowest tile wins: 2.26 -> 2.58 M grad-evals/s at cfg3.
+static int pick_cpt(int KP, int C, int64_t m_tiles, int sm_count) {
   int unit = 1;
   while ((unit * KP) % 16) ++unit;
+  static int forced = -1;  // BHMC_CPT: chains per N tile override (A/B measurements)
+  if (forced < 0) {
+    const char* e = getenv("BHMC_CPT");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0 && forced % unit == 0 && forced * KP <= 192) return forced;
   int best = unit;
   double best_cost = 1e30;
   for (int cpt = unit; cpt * KP <= 192; cpt += unit) {
     const int tiles = (C + cpt - 1) / cpt;
-    const double cost = (double)tiles * (BM + cpt * KP + 16);  // +16: per-tile epilogue / scheduling overhead
+    const double rounds = std::max(1.0, (double)m_tiles * tiles / (double)sm_count);
+    const double cost = rounds * (BM + cpt * KP + 16);  // +16: per-tile epilogue / scheduling overhead
     if (cost < best_cost - 1e-9) best_cost = cost, best = cpt;
   }
   return best;
@@ -963,13 +1045,14 @@ static int launch_fwd_kp(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorM
 }
 
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
-                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3) {
+                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs) {
+  BHMC_CHECK_ARG(!fs || (q == fs->q && loglik), "fused step: the gradient must be evaluated at the state it updates");
   BHMC_CHECK_ARG(d.tc_ready, "tensor-core operands were not prepared at bind time (precision_mask)");
   BHMC_CHECK_ARG(!split3 || d.has_lo, "bf16x3 needs the lo operand copies (precision_mask bit 1 at bind time)");
   BHMC_CHECK_ARG(row0 >= 0 && nrows > 0 && row0 + nrows <= d.N, "row window [%lld,+%lld) outside the %lld bound rows",
                  (long long)row0, (long long)nrows, (long long)d.N);
   const int KP = d.Kp, K = d.K, D = d.D;
-  const int cpt = pick_cpt(KP, C);
+  const int cpt = pick_cpt(KP, C, ceil_div(nrows, BM), ctx->sm_count);
   const int BN = cpt * KP;
   const int n_tiles = (int)ceil_div(C, cpt);
   const int64_t ncols = (int64_t)C * KP;  // rows of Wt / DmT
@@ -1002,7 +1085,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   __nv_bfloat16* wt_hi = (__nv_bfloat16*)wt;
   __nv_bfloat16* wt_lo = (__nv_bfloat16*)((char*)wt + wt_bytes);
 
-  {
+  if (!(fs && fs->wt_ready)) {
     GroupTimer t(ctx, KG_PREP);
     dim3 grid((unsigned)ceil_div(d.Dp, 128), C);
     k_tc_prep<<<grid, 128, 0, ctx->stream>>>(q, ld, D, K, KP, d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
@@ -1012,7 +1095,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   void* dmt = nullptr;
   size_t dmt_bytes = (size_t)(dm_nslab * dm_rows * dm_ld) * 2;
   __nv_bfloat16 *dmt_hi = nullptr, *dmt_lo = nullptr;
-  if (g) {
+  if (g || fs) {
     BHMC_TRY(ctx->get_scratch(2, dmt_bytes * 2, &dmt));
     dmt_hi = (__nv_bfloat16*)dmt;
     dmt_lo = split3 ? (__nv_bfloat16*)((char*)dmt + dmt_bytes) : nullptr;
@@ -1070,7 +1153,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.dmt_hi = dmt_hi;
   p.dmt_lo = dmt_lo;
   p.loglik = loglik;
-  p.write_dm = g ? 1 : 0;
+  p.write_dm = (g || fs) ? 1 : 0;
   p.prof = nullptr;
   static int want_prof = -1;
   if (want_prof < 0) want_prof = getenv("BHMC_PROF") ? 1 : 0;
@@ -1115,7 +1198,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     if (n)
       fprintf(stderr, "[bhmc prof fwd] MMA thread, mean over %d CTAs: total %.0f cyc; wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f tiles %.0f -> per chunk: full-wait %.0f issue %.0f\n", n, tot / n, te / n, tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
   }
-  if (!g) return BHMC_OK;
+  if (!g && !fs) return BHMC_OK;
 
   // ---- backward: G[D+1, C*KP] = Xt[D+1, rows] . DmT^T, split over row slabs ----
   TcParams b{};
@@ -1187,8 +1270,18 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   {
     GroupTimer t(ctx, KG_BWD);
     BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
-    dim3 grid((unsigned)ceil_div(ld, 256), C);
-    k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, K, KP, P, q, g, ld, alpha);
+    if (fs) {
+      dim3 grid((unsigned)ceil_div(ceil_div(ld, 4), 256), C);
+      if (fs->kind == BHMC_KIND_SGLD)
+        k_tc_reduce_step<BHMC_KIND_SGLD><<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, D, K, KP, P, ld, alpha, *fs,
+                                                                        d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
+      else
+        k_tc_reduce_step<BHMC_KIND_SGD><<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, D, K, KP, P, ld, alpha, *fs,
+                                                                       d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
+    } else {
+      dim3 grid((unsigned)ceil_div(ld, 256), C);
+      k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, K, KP, P, q, g, ld, alpha);
+    }
     ctx->launches++;
   }
   BHMC_CUDA_OK(cudaGetLastError());

@@ -40,7 +40,15 @@ class Context:
         return int(self.L.bhmc_ctx_launch_count(self.handle))
 
     def timing(self, enable):
-        check(self.L.bhmc_ctx_timing(self.handle, 1 if enable else 0))
+        check(self.L.bhmc_ctx_timing(self.handle, int(enable)))  # 0 off, 1 all kernel groups, 2 GEMM groups only
+
+    def timing_stride(self, stride):
+        check(self.L.bhmc_ctx_timing_stride(self.handle, int(stride)))
+
+    def kernel_units(self, group):
+        u = C.c_double()
+        check(self.L.bhmc_ctx_kernel_units(self.handle, group, C.byref(u)))
+        return u.value
 
     def kernel_time(self, group):
         ms, n = C.c_double(), C.c_int64()

@@ -68,7 +68,12 @@ int64_t bhmc_ctx_launch_count(const bhmc_ctx* ctx);
 /* time (ms, CUDA events on the context stream) and launch count of the named kernel group
  * since the last reset; groups: 0 = grad fwd, 1 = grad bwd, 2 = prep, 3 = update/accept */
 int bhmc_ctx_kernel_time(bhmc_ctx* ctx, int group, double* ms, int64_t* launches);
+/* enable: 0 = off, 1 = every kernel group, 2 = the two GEMM groups only (fewer event records on the stream) */
 int bhmc_ctx_timing(bhmc_ctx* ctx, int enable);
+/* bracket only every stride-th launch of a group with events (default 1); bhmc_ctx_kernel_units returns the work
+ * units (chains) of exactly the bracketed launches of the sampler drivers since the last bhmc_ctx_timing call */
+int bhmc_ctx_timing_stride(bhmc_ctx* ctx, int stride);
+int bhmc_ctx_kernel_units(bhmc_ctx* ctx, int group, double* units);
 
 /* ---- model protocol (seam 1): replaces softmax.grad / log_likelihood /
  *      negative_log_posterior, hamiltonian/models/cpu/softmax.py:45-79 ---------------------- */

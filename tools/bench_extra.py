@@ -19,7 +19,7 @@ from dropout_hamiltonian_montecarlo_b200._lib import KIND, PREC
 from dropout_hamiltonian_montecarlo_b200.runtime import MlpHandle, SamplerHandle, SoftmaxHandle, default_context
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["sgld", "mlp", "update", "rows"])
+ap.add_argument("what", choices=["sgld", "mlp", "update", "rows", "stream"])
 ap.add_argument("--rows", type=int, default=1000000)
 ap.add_argument("--features", type=int, default=2048)
 ap.add_argument("--classes", type=int, default=38)
@@ -47,7 +47,24 @@ def timed(fn):
     return e0.elapsed_time(e1) * 1e-3, out
 
 
-if a.what == "rows":
+if a.what == "stream":
+    # profiling target for the elementwise kernels of the streaming schedule at the cfg4-sized state (P = 669 706)
+    # where they are HBM-bound: a toy MVN model would not do, so a wide softmax stands in: D*K + K ~ 670k parameters
+    Ns, Ds, Ks, C = 256, 65535, 10, 32
+    g = torch.Generator(device=dev).manual_seed(1)
+    Xs = torch.rand(Ns, Ds, generator=g, device=dev)
+    ys = torch.randint(0, Ks, (Ns,), generator=g, device=dev, dtype=torch.int32)
+    h = SoftmaxHandle(ctx, Ns, Ds, Ks, 0.01)
+    h.bind(Xs, ys, 1 | (1 << PREC["bf16"]))
+    s = SamplerHandle(ctx, h, KIND["hmc"], C, seed=1, precision=PREC["bf16"], sweep=list(zip(h.var_off, h.var_len)))
+    s.set_q(np.zeros((C, h.P), np.float32))
+    s.hmc_run(2, 1e-4, 5e-4, keep_samples=False, schedule="streaming")
+    ctx.timing(True)
+    dt, out = timed(lambda: s.hmc_run(a.steps, 1e-4, 1e-3, step0=2, keep_samples=True, schedule="streaming"))
+    t_upd, n_upd = ctx.kernel_time(3)
+    print(json.dumps({"workload": "streaming-schedule elementwise kernels, P=%d, %d chains" % (h.P, C), "phases": out["n_phases"],
+                      "update_group_ms": t_upd, "update_group_launches": n_upd, "seconds": dt}))
+elif a.what == "rows":
     # BASELINE config 5: full-batch HMC, rows sharded over the ranks, one all-reduce (NCCL) per gradient evaluation.
     # Launch with torchrun; every rank synthesises only its own shard (abs(N(0,1)) features).
     import torch.distributed as dist
