@@ -281,7 +281,11 @@ struct SoftmaxModel : ModelBase {
   int64_t global_rows = 0;
   float alpha_energy = -1.f;  // alpha of the log-prior constant when it differs from the gradient's (row shards)
 
-  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) override {
+  ZCache zcache;
+  bool cheap_slice(int64_t off, int64_t) const override { return !logistic && off >= (int64_t)d.D * d.K; }  // bias only
+
+  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat,
+           uint32_t hint) override {
     if (logistic) {
       const int64_t ld2 = round_up(2 * ((int64_t)d.D + 1), 4);
       void* buf = nullptr;
@@ -298,7 +302,7 @@ struct SoftmaxModel : ModelBase {
       BHMC_CUDA_OK(cudaGetLastError());
       return BHMC_OK;
     }
-    return grad_softmax(q, C, ld, row0, nrows, prec, g, stat);
+    return grad_softmax(q, C, ld, row0, nrows, prec, g, stat, hint);
   }
   int grad_input_dropout(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g,
                          double* stat, const uint8_t* mask, float keep, uint64_t seed, uint32_t stream) override {
@@ -321,7 +325,7 @@ struct SoftmaxModel : ModelBase {
     db.labels = d.labels + row0;
     if (prec != BHMC_PREC_FP32) BHMC_TRY(tc_softmax_bind(ctx, db, prec == BHMC_PREC_BF16X3));
     std::swap(d, db);  // evaluate on the masked view through the ordinary (logistic-aware) path
-    const int rc = grad(q, C, ld, 0, nrows, prec, g, stat);
+    const int rc = grad(q, C, ld, 0, nrows, prec, g, stat, 0);
     std::swap(d, db);
     return rc;
   }
@@ -329,11 +333,18 @@ struct SoftmaxModel : ModelBase {
     if (logistic || prec == BHMC_PREC_FP32) return BHMC_ERR_UNSUPPORTED;
     return tc_softmax_grad(ctx, d, fs.q, C, ld, alpha, row0, nrows, nullptr, stat, prec == BHMC_PREC_BF16X3, &fs);
   }
-  int grad_softmax(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) {
+  int grad_softmax(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat,
+                   uint32_t hint = 0) {
+    static int zc_env = -1;  // BHMC_ZCACHE=0 disables the X.W cache (A/B measurements)
+    if (zc_env < 0) {
+      const char* e = getenv("BHMC_ZCACHE");
+      zc_env = e ? atoi(e) : 1;
+    }
+    const int zmode = !zc_env ? ZMODE_NONE : (hint & GRAD_HINT_CHEAP_MOVE) ? ZMODE_USE : (hint & GRAD_HINT_KEEP) ? ZMODE_STORE : ZMODE_NONE;
     switch (prec) {
       case BHMC_PREC_FP32: return simt_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat);
-      case BHMC_PREC_BF16X3: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, true);
-      case BHMC_PREC_BF16: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, false);
+      case BHMC_PREC_BF16X3: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, true, nullptr, &zcache, zmode);
+      case BHMC_PREC_BF16: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, false, nullptr, &zcache, zmode);
     }
     set_error("unknown precision %d", prec);
     return BHMC_ERR_ARG;
@@ -379,7 +390,7 @@ struct MvnModel : ModelBase {
   double logdet = 0.0;
   double* dev = nullptr;  // mu | cov_inv
   ~MvnModel() override { cudaFree(dev); }
-  int grad(const float* q, int C, int64_t ld, int64_t, int64_t, int, float* g, double* stat) override {
+  int grad(const float* q, int C, int64_t ld, int64_t, int64_t, int, float* g, double* stat, uint32_t) override {
     GroupTimer t(ctx, KG_FWD);
     k_mvn<<<(C + 127) / 128, 128, 0, ctx->stream>>>(q, ld, dim, dev, dev + dim, g, stat, C);
     ctx->launches++;
@@ -637,9 +648,9 @@ struct bhmc_sampler {
   bhmc_grad_hook hook = nullptr;
   void* hook_user = nullptr;
   // gradient (or log-lik only when g == nullptr) of the first `rows` working rows, then the optional hook
-  int eval(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat) {
+  int eval(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat, uint32_t hint = 0) {
     ctx->cur_units = rows;
-    BHMC_TRY(model->grad(q, rows, ld, row0, nrows, cfg.precision, g, stat));
+    BHMC_TRY(model->grad(q, rows, ld, row0, nrows, cfg.precision, g, stat, hint));
     if (hook && hook(hook_user, g, stat, rows, ld) != 0) {
       bhmc::set_error("gradient hook reported a failure");
       return BHMC_ERR_STATE;
@@ -740,9 +751,16 @@ int bhmc_sampler_get(bhmc_sampler* s, int32_t which, float* dst, int32_t is_host
 // at very different times (E[L]/max L ~ 0.5 for 64 chains).  Chains are independent, so nothing forces them to start
 // transition t+1 together: here every chain walks through its own sequence of transitions back to back, and every
 // gradient launch carries all chains that still have work.  The host knows every L in advance (host Philox == device
-// Philox), so it compiles the whole run into one op code per (phase, row); rows are sorted by total work so that the
-// rows still busy at the end of the run form a prefix.  Draws are keyed by (chain, step): the samples are the ones
-// the lockstep schedule produces.
+// Philox), so it compiles the whole call into op codes per (phase, row); rows are sorted by total work so that the
+// rows still busy at the end of the call form a prefix.  Draws are keyed by (chain, step): the decisions are the ones
+// the lockstep schedule takes.
+//
+// The gradient at the start point of transition t+1 is not re-evaluated: after an accepted proposal it is the last
+// evaluation of transition t, after a rejection it is the start-point gradient of transition t (kept in g_start).
+// Every transition therefore occupies (L-1)*nsw launches -- a multiple of the sweep length -- so ALL rows move the
+// same variable before a given launch: launch j follows a move of sweep group (j-1) mod nsw.  That uniformity is
+// what lets the model reuse X.W after bias-only moves (GRAD_HINT_CHEAP_MOVE) for whole launches.  A transition with
+// L <= 1 (no leapfrog iteration, A = 1) idles for one sweep so that the alternation holds.
 static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vector<int32_t>& L /* [n_steps][C] */) {
   const bhmc_sampler_config& cfg = s->cfg;
   bhmc_ctx* ctx = s->ctx;
@@ -757,26 +775,32 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   double* kin1 = stat + 4 * C;
   double* extra_cur = stat + 5 * C;
   double* extra_new = stat + 6 * C;
-  double* sumsq = stat + 8 * C;
   double ea, eb, cv[BHMC_MAX_VARS];
   mb->energy_coeffs(nrows, &ea, &eb, cv);
   bool need_extra = false;
   for (int v = 0; v < mb->n_vars; ++v) need_extra |= cv[v] != 0.0;
-
   struct timespec ts_setup;
   clock_gettime(CLOCK_MONOTONIC, &ts_setup);
-  // total gradient slots per chain: per transition 1 (start point) + (L-1)*nsw (sub-steps)
-  std::vector<int64_t> T(C, 0);
+
+  // launches per chain: 1 (start point of its first transition) + per transition max(L-1, 1)*nsw
+  auto slots = [&](int Lt) { return (int64_t)std::max(Lt - 1, 1) * nsw; };
+  std::vector<int64_t> T(C, 1);
   run->n_grad_evals = 0;
-  for (int t = 0; t < n_steps; ++t)
-    for (int c = 0; c < C; ++c) T[c] += 1 + (int64_t)std::max(L[(size_t)t * C + c] - 1, 0) * nsw;
+  for (int c = 0; c < C; ++c) {
+    run->n_grad_evals += 1;
+    for (int t = 0; t < n_steps; ++t) {
+      T[c] += slots(L[(size_t)t * C + c]);
+      run->n_grad_evals += (int64_t)std::max(L[(size_t)t * C + c] - 1, 0) * nsw;  // evaluations that moved a chain
+    }
+  }
   std::vector<int32_t> perm(C);
-  for (int c = 0; c < C; ++c) perm[c] = c, run->n_grad_evals += T[c];
+  for (int c = 0; c < C; ++c) perm[c] = c;
   std::stable_sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) { return T[x] > T[y]; });
   const int64_t J = T[perm[0]];  // gradient launches; elementwise phases are 0..J (phase T_c finishes chain c)
   BHMC_CHECK_ARG(J < (1LL << 24), "run too long for one call (%lld phases): lower n_steps", (long long)J);
 
-  // ---- compile the op table -----------------------------------------------------------------------------------
+  // ---- compile the op tables: code1 = update before the Metropolis tests of the phase, code2 = update after the
+  // begins of the phase (first half kick + drift of the transitions that start in it) -------------------------------
   const size_t n_ops = (size_t)(J + 1) * C;
   const size_t code_bytes = round_up(sizeof(uint32_t) * n_ops, 64), perm_bytes = round_up(sizeof(int32_t) * C, 64);
   const size_t u_bytes = sizeof(double) * (size_t)n_steps * C;
@@ -785,42 +809,45 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
     ctx->pinned_inflight = false;
   }
   void* pin = nullptr;
-  BHMC_TRY(ctx->get_pinned(2 * code_bytes + perm_bytes + u_bytes, &pin));
-  uint32_t* code_h = (uint32_t*)pin;
-  int32_t* step_h = (int32_t*)((char*)pin + code_bytes);
-  int32_t* perm_h = (int32_t*)((char*)pin + 2 * code_bytes);
-  double* uacc_h = (double*)((char*)pin + 2 * code_bytes + perm_bytes);
-  memset(code_h, 0, 2 * code_bytes);
+  const size_t tab_bytes = 4 * code_bytes + perm_bytes;
+  BHMC_TRY(ctx->get_pinned(tab_bytes + u_bytes, &pin));
+  uint32_t* code1_h = (uint32_t*)pin;
+  uint32_t* code2_h = (uint32_t*)((char*)pin + code_bytes);
+  int32_t* step1_h = (int32_t*)((char*)pin + 2 * code_bytes);
+  int32_t* step2_h = (int32_t*)((char*)pin + 3 * code_bytes);
+  int32_t* perm_h = (int32_t*)((char*)pin + 4 * code_bytes);
+  double* uacc_h = (double*)((char*)pin + tab_bytes);
+  memset(pin, 0, 4 * code_bytes);
   std::vector<int> rows_el(J + 2, 0), rows_grad(J + 1, 0);  // active row counts per phase
   std::vector<char> ev_finish(J + 1, 0), ev_begin(J + 1, 0);
   for (int r = 0; r < C; ++r) {
     const int c = perm[r];
     perm_h[r] = c;
-    int64_t j = 0;
+    code1_h[0 * C + r] = OP_BEGIN;  // phase 0: begin transition 0; launch 0 evaluates its start point
+    step1_h[0 * C + r] = 0;
+    ev_begin[0] = 1;
+    int64_t j = 1;
     for (int t = 0; t < n_steps; ++t) {
       const int Lt = L[(size_t)t * C + c];
-      // phase j: (finish t-1,) begin t; the launch that follows evaluates the start point
-      code_h[j * C + r] |= OP_BEGIN;
-      if (t == 0) step_h[j * C + r] = 0;  // with FINISH the field holds t-1 and BEGIN adds one
-      ev_begin[j] = 1;
-      ++j;
-      // phase j: latch the start-point statistics, then either the first sub-step or (L <= 1) nothing
-      code_h[j * C + r] |= OP_LATCH;
-      step_h[j * C + r] = t;
       const int iters = std::max(Lt - 1, 0);
-      for (int it = 0; it < iters; ++it)
-        for (int v = 0; v < nsw; ++v) {
-          const bool first = it == 0 && v == 0;
-          const int pv = v == 0 ? nsw - 1 : v - 1;
-          code_h[j * C + r] |= OP_PRE | ((uint32_t)v << 12) | (first ? 0u : (OP_POST | ((uint32_t)pv << 8)));
-          step_h[j * C + r] = t;
-          ++j;
-        }
-      // phase j (== the next transition's begin phase, or the chain's last phase): closing kick + Metropolis test
-      if (iters > 0) code_h[j * C + r] |= OP_POST | ((uint32_t)(nsw - 1) << 8);
-      code_h[j * C + r] |= OP_FINISH;
-      step_h[j * C + r] = t;
+      // phase j: first sub-step of transition t.  t == 0: in the ordinary update (after the start-point launch);
+      // t > 0: in the post-begin update of the phase in which transition t-1 was finished
+      uint32_t* first_code = t == 0 ? code1_h : code2_h;
+      int32_t* first_step = t == 0 ? step1_h : step2_h;
+      first_code[j * C + r] |= (t == 0 ? OP_LATCH : OP_LATCH_CACHED) | (iters > 0 ? OP_PRE | (0u << 12) : 0u);
+      first_step[j * C + r] = t;
+      for (int64_t k = 1; k < slots(Lt); ++k) {  // remaining sub-steps: closing kick of the previous + opening of this
+        const int v = (int)(k % nsw), pv = v == 0 ? nsw - 1 : v - 1;
+        if (iters > 0) code1_h[(j + k) * C + r] |= OP_POST | ((uint32_t)pv << 8) | OP_PRE | ((uint32_t)v << 12);
+        step1_h[(j + k) * C + r] = t;
+      }
+      j += slots(Lt);
+      // phase j: closing kick of the last variable, Metropolis test, begin of transition t+1
+      if (iters > 0) code1_h[j * C + r] |= OP_POST | ((uint32_t)(nsw - 1) << 8);
+      code1_h[j * C + r] |= OP_FINISH | (t + 1 < n_steps ? OP_BEGIN : 0u);
+      step1_h[j * C + r] = t;
       ev_finish[j] = 1;
+      if (t + 1 < n_steps) ev_begin[j] = 1;
     }
     // j == T[c]: the chain takes part in elementwise phases 0..T and gradient launches 0..T-1
     for (int64_t k = 0; k <= j; ++k) rows_el[k] = r + 1;  // rows sorted by T descending -> prefix
@@ -828,23 +855,31 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   }
   if (run->u_accept_host) memcpy(uacc_h, run->u_accept_host, u_bytes);
   void* dev = nullptr;
-  BHMC_TRY(ctx->get_scratch(6, std::max(2 * code_bytes + perm_bytes + u_bytes, (size_t)32 << 20), &dev));
-  const uint32_t* code_d = (const uint32_t*)dev;
-  const int32_t* step_d = (const int32_t*)((char*)dev + code_bytes);
-  const int32_t* perm_d = (const int32_t*)((char*)dev + 2 * code_bytes);
-  const double* uacc_d = (const double*)((char*)dev + 2 * code_bytes + perm_bytes);
-  BHMC_CUDA_OK(cudaMemcpyAsync(dev, pin, 2 * code_bytes + perm_bytes + (run->u_accept_host ? u_bytes : 0),
-                               cudaMemcpyHostToDevice, ctx->stream));
+  BHMC_TRY(ctx->get_scratch(6, std::max(tab_bytes + u_bytes, (size_t)32 << 20), &dev));
+  const uint32_t* code1_d = (const uint32_t*)dev;
+  const uint32_t* code2_d = (const uint32_t*)((char*)dev + code_bytes);
+  const int32_t* step1_d = (const int32_t*)((char*)dev + 2 * code_bytes);
+  const int32_t* step2_d = (const int32_t*)((char*)dev + 3 * code_bytes);
+  const int32_t* perm_d = (const int32_t*)((char*)dev + 4 * code_bytes);
+  const double* uacc_d = (const double*)((char*)dev + tab_bytes);
+  BHMC_CUDA_OK(cudaMemcpyAsync(dev, pin, tab_bytes + (run->u_accept_host ? u_bytes : 0), cudaMemcpyHostToDevice, ctx->stream));
   if (!ctx->pinned_ev) BHMC_CUDA_OK(cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming));
   BHMC_CUDA_OK(cudaEventRecord(ctx->pinned_ev, ctx->stream));
   ctx->pinned_inflight = true;
-  // start-of-step kinetic energies: two parity buffers (a step's buffer is re-zeroed while the other one is in use)
+  // per-row scalars of this schedule: kin0 parity buffers [2C], prior-energy scratch [C*(n_vars+1)], stat_next [C],
+  // extra_next [C], acc_flag [C]; and the start-of-step gradients g_start [C, ld]
   void* kbuf = nullptr;
-  BHMC_TRY(ctx->get_scratch(4, sizeof(double) * ((size_t)2 * C + (size_t)C * (mb->n_vars + 1)), &kbuf));
+  const size_t n_dbl = (size_t)2 * C + (size_t)C * (mb->n_vars + 1) + 2 * (size_t)C;
+  BHMC_TRY(ctx->get_scratch(4, sizeof(double) * n_dbl + sizeof(int32_t) * C, &kbuf));
   double* kin0 = (double*)kbuf;
   double* extra_tmp = kin0 + 2 * (size_t)C;
-  (void)sumsq;
+  double* stat_next = extra_tmp + (size_t)C * (mb->n_vars + 1);
+  double* extra_next = stat_next + C;
+  int32_t* acc_flag = (int32_t*)(extra_next + C);
   BHMC_CUDA_OK(cudaMemsetAsync(kin0, 0, sizeof(double) * 2 * C, ctx->stream));
+  void* gbuf = nullptr;
+  BHMC_TRY(ctx->get_scratch(9, sizeof(float) * (size_t)C * ld, &gbuf));
+  float* g_start = (float*)gbuf;
 
   StreamUpdateArgs u{};
   u.q = s->q_new;
@@ -863,6 +898,14 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   u.kin0 = kin0;
   u.kin1 = kin1;
   u.C_total = C;
+  u.g_start = g_start;
+  u.stat_next = stat_next;
+  u.extra_next = need_extra ? extra_next : nullptr;
+  u.extra_cur = extra_cur;
+
+  bool cheap[BHMC_MAX_VARS];
+  for (int v = 0; v < nsw; ++v) cheap[v] = mb->cheap_slice(cfg.sweep_off[v], cfg.sweep_len[v]);
+  bool kept = false;  // the previous launch kept what a cheap move can reuse, for every active row
 
   run->n_grad_launched = 0;
   static int prof_host = -1;
@@ -875,8 +918,8 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   }
   for (int64_t j = 0; j <= J; ++j) {
     const int rows = rows_el[j];
-    const uint32_t* cj = code_d + j * C;
-    const int32_t* sj = step_d + j * C;
+    const uint32_t* cj = code1_d + j * C;
+    const int32_t* sj = step1_d + j * C;
     if (j > 0) {
       u.rows = rows;
       u.code = cj;
@@ -919,6 +962,9 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
       a.code = cj;
       a.step = sj;
       a.C_total = C;
+      a.stat_next = stat_next;
+      a.extra_next = need_extra ? extra_next : nullptr;
+      a.acc_flag = acc_flag;
       BHMC_TRY(launch_accept(ctx, a));
     }
     if (j == J) break;
@@ -943,12 +989,35 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
       b.code = cj;
       b.step = sj;
       b.C_total = C;
+      b.g = s->g;
+      b.g_start = g_start;
+      b.acc_flag = acc_flag;
       BHMC_TRY(launch_hmc_begin(ctx, b));
-      if (need_extra)  // quadratic log-prior part of U(q) at the start point
-        BHMC_TRY(launch_prior_energy(ctx, s->q_new, ld, rows_grad[j], mb->n_vars, mb->var_off, mb->var_len, cv, extra_tmp + C,
-                                     extra_cur, cj, OP_BEGIN));
+      if (j == 0) {
+        if (need_extra)  // quadratic log-prior part of U(q) at the very first start point
+          BHMC_TRY(launch_prior_energy(ctx, s->q_new, ld, rows_grad[j], mb->n_vars, mb->var_off, mb->var_len, cv, extra_tmp + C,
+                                       extra_cur, cj, OP_BEGIN));
+      } else {  // first half kick + drift of the transitions that just began
+        u.rows = rows_grad[j];
+        u.code = code2_d + j * C;
+        u.step = step2_d + j * C;
+        BHMC_TRY(launch_stream_update(ctx, u));
+      }
     }
-    BHMC_TRY(s->eval(s->q_new, rows_grad[j], run->row0, nrows, s->g, stat));
+    // what moved since the previous launch: nothing before launch 0 (start points), else sweep group (j-1) % nsw for
+    // every row; a begin in this phase re-seats q_new, which a cheap move alone would not tell the model
+    uint32_t hint = 0;
+    if (j > 0) {
+      const int v = (int)((j - 1) % nsw), vn = (int)(j % nsw);
+      if (kept && cheap[v] && !ev_begin[j]) hint |= GRAD_HINT_CHEAP_MOVE;
+      const bool keep_next = cheap[vn] && j + 1 < J;  // a cheap evaluation leaves the kept data valid, a full one renews it
+      if (keep_next) hint |= GRAD_HINT_KEEP;
+      kept = keep_next;
+    } else {
+      kept = cheap[0];
+      if (kept) hint |= GRAD_HINT_KEEP;
+    }
+    BHMC_TRY(s->eval(s->q_new, rows_grad[j], run->row0, nrows, s->g, stat, hint));
     run->n_grad_launched += rows_grad[j];
   }
   run->n_phases = (int32_t)J;
@@ -1099,7 +1168,13 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     if (need_extra)  // quadratic log-prior part of U(q) (row-indexed like the other energies)
       BHMC_TRY(launch_prior_energy(ctx, s->q_new, ld, C, mb->n_vars, mb->var_off, mb->var_len, cv, sumsq, extra_cur));
     // 2. gradient at the current point (hmc.py:47); its log-likelihood doubles as NLP(q)
-    BHMC_TRY(s->eval(s->q_new, C, run->row0, nrows, s->g, stat));
+    // evaluation hints: a sub-step that moved only a cheap slice (softmax: the bias) lets the model reuse X.W of
+    // the previous evaluation, provided that one was asked to keep it
+    bool cheap[BHMC_MAX_VARS];
+    for (int v = 0; v < nsw; ++v) cheap[v] = mb->cheap_slice(cfg.sweep_off[v], cfg.sweep_len[v]);
+    const int iters_pre = std::max(lmax[t] - 1, 0);
+    bool kept = iters_pre > 0 && cheap[0];
+    BHMC_TRY(s->eval(s->q_new, C, run->row0, nrows, s->g, stat, kept ? GRAD_HINT_KEEP : 0u));
     run->n_grad_launched += C;
     BHMC_CUDA_OK(cudaMemcpyAsync(stat_cur, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
     BHMC_CUDA_OK(cudaMemcpyAsync(stat_new, stat, sizeof(double) * C, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1149,7 +1224,13 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
           u.stream_hi = TAG_NOISE | (uint32_t)((pit * nsw + pv) & 0xffffff);
         }
         BHMC_TRY(launch_hmc_update(ctx, u));
-        BHMC_TRY(s->eval(s->q_new, rows, run->row0, nrows, s->g, stat));
+        const bool last = it == iters - 1 && v == nsw - 1;
+        const int vn = v == nsw - 1 ? 0 : v + 1;
+        uint32_t hint = (kept && cheap[v]) ? GRAD_HINT_CHEAP_MOVE : 0u;
+        const bool keep_next = !last && cheap[vn] && (cheap[v] ? kept : true);
+        if (keep_next) hint |= GRAD_HINT_KEEP;
+        kept = keep_next;
+        BHMC_TRY(s->eval(s->q_new, rows, run->row0, nrows, s->g, stat, hint));
         run->n_grad_launched += rows;
         rows_prev = rows;
       }

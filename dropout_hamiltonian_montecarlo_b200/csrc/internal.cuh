@@ -64,14 +64,15 @@ struct bhmc_ctx {
   double units_acc[bhmc::KG_COUNT] = {0, 0, 0, 0};
   int64_t cur_units = 0;  // set by the callers of model->grad (rows of this launch)
   // grow-only device scratch
-  void* scratch[8] = {nullptr};
-  size_t scratch_bytes[8] = {0};
+  void* scratch[12] = {nullptr};
+  size_t scratch_bytes[12] = {0};
   // pinned staging for small per-step host->device uploads
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_ev = nullptr;
   bool pinned_inflight = false;
 
+  const void* zcache_owner = nullptr;  // ZCache descriptor whose data scratch slot 8 currently holds
   int get_scratch(int slot, size_t bytes, void** out);
   int get_pinned(size_t bytes, void** out);
   void begin_group(int group);
@@ -109,6 +110,10 @@ struct FusedStep {
 // ---------------------------------------------------------------------------------------
 // model interface used by the sampler drivers
 // ---------------------------------------------------------------------------------------
+enum : uint32_t {
+  GRAD_HINT_CHEAP_MOVE = 1u,  // since the previous evaluation of these rows only a cheap_slice() moved
+  GRAD_HINT_KEEP = 2u,        // the NEXT evaluation of these rows will follow a cheap move: keep what it can reuse
+};
 struct ModelBase {
   bhmc_ctx* ctx = nullptr;
   int64_t P = 0;
@@ -117,8 +122,12 @@ struct ModelBase {
   int64_t var_len[BHMC_MAX_VARS] = {0};
   virtual ~ModelBase() {}
   // g may be nullptr (log-lik only). stat[c] (double, device) receives the model's scalar.
+  // hint (GRAD_HINT_*): what the caller knows about q relative to the previous evaluation of the same rows
   virtual int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g,
-                   double* stat) = 0;
+                   double* stat, uint32_t hint = 0) = 0;
+  // true when moving only parameters [off, off+len) leaves the expensive part of the forward pass unchanged
+  // (softmax: the slice lies inside the bias) -> the next evaluation may be requested with GRAD_HINT_CHEAP_MOVE
+  virtual bool cheap_slice(int64_t, int64_t) const { return false; }
   // potential used by the Metropolis test: U = a*stat + b (+ sum_v cv[v]*|q_v|^2)
   virtual void energy_coeffs(int64_t nrows, double* a, double* b, double* cv) const = 0;
   virtual int64_t default_rows() const { return 0; }
@@ -167,11 +176,15 @@ int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a);
 // ---- streaming schedule (asynchronous chains): every working row follows its OWN position in its own sequence of
 // HMC transitions; one 32-bit op code per (phase, row) says what the row does between two gradient launches.
 enum : uint32_t {
-  OP_LATCH = 1u,    // the previous launch evaluated the step's start point: stat_cur = stat_new = stat
+  OP_LATCH = 1u,    // the previous launch evaluated the step's start point (first step of a call only):
+                    // stat_cur = stat_new = stat, g_start = g
   OP_POST = 2u,     // closing kick of variable (code >> 8) & 15; also latches stat_new = stat
   OP_PRE = 4u,      // opening half kick + drift of variable (code >> 12) & 15
   OP_FINISH = 8u,   // kinetic energy + Metropolis test of step op_step[row]
-  OP_BEGIN = 16u,   // momentum draw / proposal := state for step op_step[row] + (FINISH ? 1 : 0)
+  OP_BEGIN = 16u,   // momentum draw / proposal := state for step op_step[row] + (FINISH ? 1 : 0); after a FINISH the
+                    // gradient at the new start point is NOT re-evaluated: accepted -> g_start = g, rejected -> g = g_start
+  OP_LATCH_CACHED = 32u,  // start-of-step statistics taken from what the Metropolis test left: stat_cur = stat_new =
+                          // stat_next, extra_cur = extra_next
 };
 struct StreamUpdateArgs {
   float* q;
@@ -189,6 +202,10 @@ struct StreamUpdateArgs {
   double* kin0;           // [2][C_total] kinetic energy at the start of the step, buffer = step parity
   double* kin1;           // [C_total] zeroed here for the kinetic kernel of this phase
   int C_total;
+  float* g_start;         // [rows, ld] gradient at the start point of the row's current step
+  const double* stat_next;   // written by the Metropolis test: statistic / prior energy of the state it selected
+  const double* extra_next;  // (may be nullptr)
+  double* extra_cur;
 };
 int launch_stream_update(bhmc_ctx* ctx, const StreamUpdateArgs& a);
 int launch_stream_kinetic(bhmc_ctx* ctx, const float* p, int64_t ld, int64_t P, int rows, const uint32_t* code,
@@ -217,6 +234,9 @@ struct BeginArgs {
   const int32_t* step;
   int64_t z_step_stride;
   int C_total;
+  float* g;                 // streaming: working gradient and its start-of-step copy (see OP_BEGIN)
+  float* g_start;
+  const int32_t* acc_flag;  // [rows] decision of the Metropolis test that preceded this begin
 };
 int launch_hmc_begin(bhmc_ctx* ctx, const BeginArgs& a);
 
@@ -259,6 +279,9 @@ struct AcceptArgs {
   const uint32_t* code;
   const int32_t* step;
   int C_total;
+  double* stat_next;   // [rows] streaming: statistic / prior energy of the selected state, decision flag
+  double* extra_next;
+  int32_t* acc_flag;
 };
 int launch_accept(bhmc_ctx* ctx, const AcceptArgs& a);
 
@@ -316,8 +339,17 @@ int simt_softmax_predict(bhmc_ctx* ctx, int D, int K, const float* q, int C, int
 
 int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo);
 void tc_softmax_release(SoftmaxData& d);
+// Z cache (X.W of the last full forward pass, scratch slot 8) and how an evaluation may use it
+struct ZCache {
+  bool valid = false;
+  int64_t row0 = 0, nrows = 0;
+  int C = 0, KP = 0, slab_rows = 0;
+  int64_t slab = 0, ld = 0;
+};
+enum { ZMODE_NONE = 0, ZMODE_STORE = 1, ZMODE_USE = 2 };  // USE falls back to a full pass when the cache does not fit
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
-                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs = nullptr);
+                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs = nullptr,
+                    ZCache* zc = nullptr, int zmode = ZMODE_NONE);
 
 // ---- mlp.cu -----------------------------------------------------------------------------------
 ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int n_out, float alpha, float ratio,

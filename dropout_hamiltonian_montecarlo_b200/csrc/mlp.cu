@@ -185,7 +185,8 @@ struct MlpModel : ModelBase {
     for (int v = 0; v < n_vars; ++v) cv[v] = -0.5 * (double)alpha / (double)var_len[v];
   }
 
-  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat) override {
+  int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat,
+           uint32_t) override {
     BHMC_CHECK_ARG(X && labels, "mlp model has no bound data");
     BHMC_CHECK_ARG(row0 >= 0 && nrows > 0 && row0 + nrows <= N, "row window outside the bound rows");
     const int B = (int)nrows;

@@ -86,6 +86,11 @@ struct TcParams {
   int dm_slab, dm_slab_rows;      // DmT slabs: window column j of row i lives at row (j / dm_slab) * dm_slab_rows + i,
   int dm_ld;                      // column j % dm_slab; row stride dm_ld = dm_slab + 64 (not a power of two)
   int dm_tail;                    // columns after the last written row that the backward's last chunk still reads
+  // Z cache: X.W (before the bias) of every (row, chain, class), fp32, transposed like DmT (same slab width / row
+  // stride, its own rows-per-slab fixed when it was stored).  Forward kernels store it when zt != nullptr; the
+  // evaluation after a sub-step that moved only the bias rebuilds softmax / (P-Y)^T / log-lik from it (k_softmax_from_z)
+  float* zt;
+  int zt_slab_rows;
   int dm_shift;                   // DmT column of window row 0 (row0 % BK: backward chunks start on absolute multiples of BK)
   __nv_bfloat16* dmt_hi;
   __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
@@ -148,7 +153,7 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // Forward epilogue of one 128 x BN accumulator tile (softmax.py:38-43,52,63-72): thread = row, the EW/4 warps of
 // a TMEM lane quarter split the tile's chains.  Per chain: tcgen05.ld KP columns, + bias, clip, row max, exp2,
 // sum, P - Y split to bf16 hi/lo and stored transposed, z_y - logsumexp warp-reduced into one fp64 red.
-template <int KP, int EW, bool EXACT>
+template <int KP, int EW, bool EXACT, bool FROM_Z = false>
 __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t tacc, int mt, int nt, int part, int lane,
                                                   int t) {
   constexpr int PARTS = EW / 4;
@@ -160,16 +165,31 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
   // DmT position of this thread's row (chain-independent part): slab, column inside the slab
   const int dm_col = p.dm_shift + (int)r, dm_sl = dm_col / p.dm_slab;
   const int64_t dm_off = (int64_t)dm_sl * p.dm_slab_rows * p.dm_ld + (dm_col - dm_sl * p.dm_slab);
+  const int64_t zt_off = (int64_t)dm_sl * p.zt_slab_rows * p.dm_ld + (dm_col - dm_sl * p.dm_slab);
   for (int cc = part; cc < p.cpt; cc += PARTS) {
     const int c = nt * p.cpt + cc;
     if (c >= p.C) break;  // warp-uniform
     uint32_t raw[KP];
-    tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
+    if constexpr (FROM_Z) {
+      const float* zp = p.zt + zt_off + (int64_t)c * KP * p.dm_ld;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) raw[k] = (EXACT || k < K) ? __float_as_uint(__ldcs(zp + (int64_t)k * p.dm_ld)) : 0u;
+    } else {
+      tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
+    }
     const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
     float bv[KP];
 #pragma unroll
     for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
-    tmem_ld_wait();
+    if constexpr (!FROM_Z) {
+      tmem_ld_wait();
+      if (p.zt) {  // keep X.W for the next evaluation (streaming stores: read back once, by another kernel)
+        float* zp = p.zt + zt_off + (int64_t)c * KP * p.dm_ld;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          if (EXACT || k < K) __stcs(zp + (int64_t)k * p.dm_ld, __uint_as_float(raw[k]));
+      }
+    }
     float z[KP];
     float m = -INFINITY, zy = 0.f;
 #pragma unroll
@@ -228,8 +248,28 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
-    if (lane == 0 && p.debug != 2) atomicAdd(p.loglik + c, (double)ll);
+    if constexpr (FROM_Z) {  // 4 warps, one chain per block: one atomic per block
+      __shared__ float sll[4];
+      if (lane == 0) sll[t >> 5] = ll;
+      __syncthreads();
+      if (t == 0) atomicAdd(p.loglik + c, (double)sll[0] + (double)sll[1] + (double)sll[2] + (double)sll[3]);
+    } else {
+      if (lane == 0 && p.debug != 2) atomicAdd(p.loglik + c, (double)ll);
+    }
   }
+}
+
+// The evaluation after a sub-step that moved only the bias (Gauss-Seidel sweep, hmc.py:50-53): X.W is unchanged, so
+// the forward GEMM is replaced by this HBM-bound pass over the cached Z^T: + new bias, clip, softmax, (P-Y)^T hi/lo,
+// log-likelihood -- the forward epilogue with global memory in place of tensor memory.  Block = 128 rows of ONE
+// chain (grid = row tiles x chains): with 4 chains per thread the kernel ran at 1.9 TB/s, every warp waiting a full
+// DRAM latency on its 10 loads (ncu: 41 % of the samples on the first use); one chain per thread and 12-16 resident
+// blocks per SM keep ~4x the bytes in flight.
+template <int KP, bool EXACT>
+__global__ void __launch_bounds__(128, (KP <= 16 ? 12 : 4)) k_softmax_from_z(const TcParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // blockIdx.x = chain (fastest): concurrently resident blocks spread their log-likelihood atomics over all chains
+  fwd_epilogue_tile<KP, 4, EXACT, true>(p, 0u, (int)blockIdx.y, (int)blockIdx.x, 0, lane, warp * 32 + lane);  // p.cpt == 1
 }
 
 // EW = number of epilogue warps (multiple of 4).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the
@@ -1045,7 +1085,8 @@ static int launch_fwd_kp(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorM
 }
 
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
-                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs) {
+                    int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs, ZCache* zc,
+                    int zmode) {
   BHMC_CHECK_ARG(!fs || (q == fs->q && loglik), "fused step: the gradient must be evaluated at the state it updates");
   BHMC_CHECK_ARG(d.tc_ready, "tensor-core operands were not prepared at bind time (precision_mask)");
   BHMC_CHECK_ARG(!split3 || d.has_lo, "bf16x3 needs the lo operand copies (precision_mask bit 1 at bind time)");
@@ -1085,7 +1126,12 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   __nv_bfloat16* wt_hi = (__nv_bfloat16*)wt;
   __nv_bfloat16* wt_lo = (__nv_bfloat16*)((char*)wt + wt_bytes);
 
-  if (!(fs && fs->wt_ready)) {
+  // ---- Z cache -------------------------------------------------------------------------------------------------
+  if (!zc || fs) zmode = ZMODE_NONE;
+  const bool use_z = zmode == ZMODE_USE && zc->valid && ctx->zcache_owner == zc && zc->row0 == row0 && zc->nrows == nrows && zc->KP == KP &&
+                     C <= zc->C && zc->ld == dm_ld && zc->slab == dm_slab;
+  if (zmode == ZMODE_USE && !use_z) zmode = ZMODE_NONE;
+  if (!use_z && !(fs && fs->wt_ready)) {
     GroupTimer t(ctx, KG_PREP);
     dim3 grid((unsigned)ceil_div(d.Dp, 128), C);
     k_tc_prep<<<grid, 128, 0, ctx->stream>>>(q, ld, D, K, KP, d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
@@ -1172,7 +1218,34 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     p.debug = dbg;
   }
   p.part = nullptr;
-  {
+  // Z cache: slot 8 holds X.W (fp32, transposed) of the last full forward pass that was asked to keep it
+  if (use_z || zmode == ZMODE_STORE) {
+    const int zrows = use_z ? zc->slab_rows : (int)dm_rows;
+    void* zbuf = nullptr;
+    BHMC_TRY(ctx->get_scratch(8, sizeof(float) * (size_t)(dm_nslab * zrows * dm_ld), &zbuf));
+    p.zt = (float*)zbuf;
+    p.zt_slab_rows = zrows;
+  }
+  if (use_z) {
+    GroupTimer t(ctx, KG_FWD);
+    BHMC_CUDA_OK(cudaMemsetAsync(loglik, 0, sizeof(double) * C, ctx->stream));
+    dim3 grid((unsigned)C, (unsigned)p.m_tiles);
+    const bool exact = K == KP;
+    TcParams pz = p;
+    pz.cpt = 1;  // one chain per block: chain index = blockIdx.y
+#define BHMC_FROM_Z(KPV)                                                    \
+  case KPV:                                                                 \
+    if (exact) k_softmax_from_z<KPV, true><<<grid, 128, 0, ctx->stream>>>(pz); \
+    else k_softmax_from_z<KPV, false><<<grid, 128, 0, ctx->stream>>>(pz);      \
+    break;
+    switch (KP) {
+      BHMC_FROM_Z(4) BHMC_FROM_Z(8) BHMC_FROM_Z(10) BHMC_FROM_Z(16) BHMC_FROM_Z(24) BHMC_FROM_Z(40) BHMC_FROM_Z(64)
+      default: set_error("unsupported KP %d", KP); return BHMC_ERR_UNSUPPORTED;
+    }
+#undef BHMC_FROM_Z
+    ctx->launches++;
+    BHMC_CUDA_OK(cudaGetLastError());
+  } else {
     GroupTimer t(ctx, KG_FWD);
     int rc;
     switch (KP) {
@@ -1186,6 +1259,19 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
       default: set_error("unsupported KP %d", KP); rc = BHMC_ERR_UNSUPPORTED;
     }
     BHMC_TRY(rc);
+    if (zmode == ZMODE_STORE) {
+      ctx->zcache_owner = zc;
+      zc->valid = true;
+      zc->row0 = row0;
+      zc->nrows = nrows;
+      zc->C = C;
+      zc->KP = KP;
+      zc->slab_rows = (int)dm_rows;
+      zc->slab = dm_slab;
+      zc->ld = dm_ld;
+    } else if (zc && !use_z) {
+      zc->valid = false;  // a full pass that did not keep Z: whatever slot 8 holds belongs to older weights
+    }
   }
   if (want_prof) {
     std::vector<long long> hp(8 * 148);

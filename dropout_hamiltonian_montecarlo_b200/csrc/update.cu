@@ -75,6 +75,10 @@ __global__ void __launch_bounds__(TPB) k_hmc_begin(BeginArgs a) {
     st4(a.q_new + orow, ld4(a.q + oc));
     st4(a.p0 + oc, z);
     st4(a.p_new + orow, z);
+    if (a.g_start && (a.code[r] & OP_FINISH)) {  // streaming: the gradient at the start point is already known
+      if (a.acc_flag[r]) st4(a.g_start + orow, ld4(a.g + orow));   // accepted: it is the last evaluation
+      else st4(a.g + orow, ld4(a.g_start + orow));                  // rejected: it is the previous start point's
+    }
     k = 0.5 * ((double)z.x * z.x + (double)z.y * z.y + (double)z.z * z.z + (double)z.w * z.w);
   }
   block_atomic_add(k, a.kin0 + r);
@@ -158,11 +162,19 @@ __global__ void __launch_bounds__(TPB) k_stream_update(StreamUpdateArgs a) {
       a.stat_new[r] = a.stat[r];
       a.kin0[(int64_t)((a.step[r] + 1) & 1) * a.C_total + r] = 0.0;  // the NEXT step's start-of-step buffer
     }
+    if (op & OP_LATCH_CACHED) {
+      const double s0 = a.stat_next[r];
+      a.stat_cur[r] = s0;
+      a.stat_new[r] = s0;
+      if (a.extra_next) a.extra_cur[r] = a.extra_next[r];
+      a.kin0[(int64_t)((a.step[r] + 1) & 1) * a.C_total + r] = 0.0;
+    }
     if (op & OP_POST) a.stat_new[r] = a.stat[r];
   }
-  if (!(op & (OP_POST | OP_PRE))) return;
   const int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 4;
   if (i >= a.P) return;
+  if (op & OP_LATCH) st4(a.g_start + (int64_t)r * a.ld + i, ld4(a.g + (int64_t)r * a.ld + i));
+  if (!(op & (OP_POST | OP_PRE))) return;
   const int pv = (op >> 8) & 15, v = (op >> 12) & 15;
   const int64_t post_off = a.off[pv], post_len = (op & OP_POST) ? a.len[pv] : 0;
   const int64_t pre_off = a.off[v], pre_len = (op & OP_PRE) ? a.len[v] : 0;
@@ -344,6 +356,9 @@ __global__ void __launch_bounds__(TPB) k_accept(AcceptArgs a) {
   double u = a.u ? a.u[c] : philox_uniform(a.seed, a.chain_id0 + c, a.stream_lo, a.stream_hi);
   bool acc = isfinite(A) && (u < A);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (a.stat_next) a.stat_next[r] = acc ? a.stat_new[r] : a.stat_cur[r];
+    if (a.extra_next && a.extra_cur) a.extra_next[r] = acc ? a.extra_new[r] : a.extra_cur[r];
+    if (a.acc_flag) a.acc_flag[r] = acc ? 1 : 0;
     if (a.accept_prob) a.accept_prob[c] = A;
     if (a.accepted) a.accepted[c] = acc ? 1 : 0;
     if (a.loss) a.loss[c] = acc ? u_new : u_cur;
