@@ -455,6 +455,7 @@ static int softmax_of(bhmc_model* m, SoftmaxModel** out) {
 }
 
 static int bind_common(SoftmaxModel* s, int32_t mask) {
+  s->zcache.valid = false;  // new data: whatever X.W the cache holds belongs to the old rows
   if (mask & ((1 << BHMC_PREC_BF16X3) | (1 << BHMC_PREC_BF16)))
     BHMC_TRY(tc_softmax_bind(s->ctx, s->d, (mask & (1 << BHMC_PREC_BF16X3)) != 0));
   return BHMC_OK;

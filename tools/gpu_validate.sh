@@ -16,6 +16,8 @@ $B > gpurun_out/bench_for_ncu.json 2> gpurun_out/bench_for_ncu.err &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 600 --csv --log-file gpurun_out/launches_r01_bench.csv $B > gpurun_out/ncu_launch.log 2>&1
 python tools/profile_grad.py --evals 4 > gpurun_out/profile_plain.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_tc_fwd2|k_tc_gemm|k_tc_reduce|k_tc_prep" -s 4 -c 4 -o gpurun_out/prof_tc_r01f python tools/profile_grad.py --evals 4 > gpurun_out/ncu_full.log 2>&1
+BZ="python bench.py --steps 1 --warmup 1 --no-e2e --no-ess --no-cpu-baseline --path-mode shared"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_softmax_from_z|k_tc_fwd2" -s 6 -c 2 -o gpurun_out/prof_fromz_r01 $BZ > gpurun_out/ncu_fromz.log 2>&1
 B2="python tools/bench_extra.py stream --steps 3"
 timeout 300 $B2 > gpurun_out/extra_stream.json 2>gpurun_out/extra_stream.err &&
 timeout 900 ncu --set full --clock-control none -k regex:"k_stream_update|k_accept|k_hmc_begin|k_stream_kinetic" -s 40 -c 12 -o gpurun_out/prof_stream_r01 $B2 > gpurun_out/ncu_stream.log 2>&1
