@@ -9,11 +9,14 @@
 // Layout in HBM (all bf16 operands are "K-major": the contraction index is contiguous)
 //   Xa_{hi,lo} [N, Dp]        forward A, built once at bind time   (Dp = D rounded up to 8)
 //   Xt_{hi,lo} [Npad/S][Dt_pad, S]  backward A = X^T plus a row of ones that yields the bias gradient, stored in
-//                             slabs of S = 8192 rows of X: a CTA walking the contraction index stays inside one
-//                             (D+1) x 16 KB slab instead of touching a different 2 MB page per feature row
+//                             slabs of S rows of X.  Default S = BK = 64 with an unpadded row stride = the fully
+//                             BLOCKED layout: every TMA box (128 feature rows x one 64-row chunk) is one contiguous
+//                             16 KB block.  (Plain [D+1, N] rows put every feature row of a tile into a different
+//                             2 MB page at N = 1e6 and thrashed the TLB; S = 8192 slabs fixed that; blocks are
+//                             another 10 % faster for launches that carry few chains.)
 //   Wt_{hi,lo} [C*KP, Dp]     forward B, rebuilt from the fp32 chain state before every evaluation
-//   DmT_{hi,lo}[slabs][Nt*BN, Sd]  (P - Y)^T written by the forward epilogue, backward B; same slab scheme as Xt
-//                             (Sd = 8192 window rows per slab; one slab for minibatch-sized windows)
+//   DmT_{hi,lo}[slabs][Nt*BN, Sd]  (P - Y)^T written by the forward epilogue, backward B; same scheme as Xt
+//                             (Sd = BK: [chunk][class row][64 window rows], a chain's classes are 128 B apart)
 //   part [S, Mt*128, Nt*BN]   fp32 split-K partials of the backward GEMM (deterministic reduce)
 // bf16x3: every fp32 value v is split v = hi + lo (two bf16); a product uses 3 MMAs
 // (hi*hi + hi*lo + lo*hi) accumulated in fp32, which restores ~fp32 accuracy.
@@ -911,6 +914,24 @@ static int pick_cpt(int KP, int C, int64_t m_tiles, int sm_count) {
   return best;
 }
 
+// Layout knobs of the backward operands (A/B measurements): slab widths in contraction indices and the padding of
+// the slab row stride.  Width BK with padding 0 is the fully blocked layout: every TMA box is one contiguous
+// 128-row x 128-byte block.
+static int64_t env_i64(const char* name, int64_t dflt) {
+  const char* e = getenv(name);
+  return e ? atoll(e) : dflt;
+}
+static int64_t xt_slab_width() {
+  static int64_t v = 0;
+  if (!v) v = std::max<int64_t>(BK, round_up(env_i64("BHMC_XT_SLAB", BK), BK));
+  return v;
+}
+static int64_t slab_pad() {
+  static int64_t v = -1;
+  if (v < 0) v = round_up(std::max<int64_t>(0, env_i64("BHMC_SLAB_PAD", 0)), 8);
+  return v;
+}
+
 int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
   const int kp = pick_kp(d.K);
   if (!kp) {
@@ -918,7 +939,7 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
     return BHMC_ERR_UNSUPPORTED;
   }
   // re-binding the same shape (fresh host data every step) reuses the operand buffers
-  const int64_t slab = std::min<int64_t>(8192, round_up(d.N, 64));
+  const int64_t slab = std::min<int64_t>(xt_slab_width(), round_up(d.N, 64));
   const bool reuse = d.Xa_hi && d.Kp == kp && d.Dp == round_up(d.D, dp_align()) && d.slab == slab &&
                      d.Npad == round_up(d.N, slab) && d.Dt == d.D + 1 && (d.has_lo || !want_lo);
   if (!reuse) {
@@ -926,7 +947,7 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
     d.Kp = kp;
     d.Dp = round_up(d.D, dp_align());
     d.slab = slab;
-    d.slab_ld = slab + 64;
+    d.slab_ld = slab + slab_pad();
     d.Npad = round_up(d.N, slab);
     d.Dt = d.D + 1;
     d.Dt_pad = round_up(d.Dt, BM);
@@ -1107,10 +1128,10 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   static int64_t dm_slab_max = 0;  // BHMC_DM_SLAB overrides the slab width (A/B measurements; multiple of 64)
   if (!dm_slab_max) {
     const char* e = getenv("BHMC_DM_SLAB");
-    dm_slab_max = e ? std::max<int64_t>(64, round_up(atoll(e), 64)) : 8192;
+    dm_slab_max = e ? std::max<int64_t>(64, round_up(atoll(e), 64)) : BK;
   }
   const int64_t dm_slab = std::min<int64_t>(dm_slab_max, dm_cols);  // multiple of 64 either way
-  const int64_t dm_nslab = ceil_div(dm_cols, dm_slab), dm_ld = dm_slab + 64;
+  const int64_t dm_nslab = ceil_div(dm_cols, dm_slab), dm_ld = dm_slab + slab_pad();
   const int64_t dm_rows = (int64_t)n_tiles * BN;     // rows per slab (>= C*KP; the padding rows are never written
                                                      // and only feed accumulator columns nobody reads)
   const int64_t P = (int64_t)(D + 1) * K;
@@ -1353,9 +1374,28 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     a_lo = a_hi;
     b_lo = b_hi;
   }
+  if (want_prof) {
+    BHMC_CUDA_OK(cudaMemsetAsync(prof_dev, 0, sizeof(long long) * 8 * 1024, ctx->stream));
+    b.prof = (long long*)prof_dev;
+  }
   {
     GroupTimer t(ctx, KG_BWD);
     BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
+    if (want_prof) {
+      std::vector<long long> hp(8 * 148);
+      BHMC_CUDA_OK(cudaMemcpyAsync(hp.data(), prof_dev, sizeof(long long) * 8 * 148, cudaMemcpyDeviceToHost, ctx->stream));
+      BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      double tot = 0, te = 0, tf = 0, ti = 0, nc = 0, nt = 0, mx = 0;
+      int n = 0;
+      for (int bb = 0; bb < 148; ++bb)
+        if (hp[bb * 8] > 0) {
+          tot += hp[bb * 8], te += hp[bb * 8 + 1], tf += hp[bb * 8 + 2], ti += hp[bb * 8 + 3], nc += hp[bb * 8 + 4], nt += hp[bb * 8 + 5], ++n;
+          mx = std::max(mx, (double)hp[bb * 8]);
+        }
+      if (n)
+        fprintf(stderr, "[bhmc prof bwd] n_split %d cps %d pair %d BN %d stages %d | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
+                b.n_split, b.chunks_per_split, b.pair, b.BN, b.stages, n, tot / n, mx, te / n, tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
+    }
     if (fs) {
       dim3 grid((unsigned)ceil_div(ceil_div(ld, 4), 256), C);
       if (fs->kind == BHMC_KIND_SGLD)
