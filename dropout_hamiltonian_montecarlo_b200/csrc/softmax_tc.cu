@@ -103,6 +103,11 @@ struct TcParams {
   int debug;                      // BHMC_DEBUG_EPI (measurement only): 1 = skip the forward epilogue, 2 = skip its atomics
   // backward epilogue
   float* part;                    // [n_split, m_tiles*128, n_tiles*BN]
+  // k_tc_bwd2 only: an odd last row tile is processed AFTER the main items by the same launch as a pair whose second
+  // half is a phantom tile (its rows are out of range and its results are dropped), with its own row-slab split
+  int prefetch;                   // k_tc_bwd2: L2 prefetch distance in chunks (0 = off)
+  int left_n_split, left_cps;     // 0 = no odd tile
+  float* part_left;               // [left_n_split, 128, n_tiles*BN]
 };
 
 // ---- cta_group::2 (one MMA spans the two CTAs of a cluster: M = 256, each CTA holds half of the B tile) ----
@@ -672,6 +677,232 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward GEMM with cta_group::2.  In-kernel counters showed the single-CTA backward starved for operands (270 of
+// 1264 cycles per chunk waiting on the `full` barrier with 72 KB entering every SM per chunk): here a CTA pair owns
+// TWO adjacent 128-row tiles of X^T (M = 256), each CTA stages its own X^T tile and only half of the (P-Y)^T tile
+// (52 KB per chunk, 4 stages).  Work item = (row-slab s, tile pair, N tile); the accumulator is drained into fp32
+// registers every sub_chunks chunks by both CTAs' epilogue warps; partial tiles go to part[s][row][col].
+template <int EW>
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
+k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int nmat = p.split3 ? 2 : 1;
+  const int a_bytes = BM * BK * 2, bh_bytes = (p.BN / 2) * BK * 2;
+  const int stage_bytes = nmat * (a_bytes + bh_bytes);
+  const int m_pairs = p.m_tiles / 2;  // p.m_tiles is even; an odd last tile is the "left" work below
+  const int per_split = m_pairs * p.n_tiles;
+  const int num_main = p.n_split * per_split;
+  const int num_work = num_main + p.left_n_split * p.n_tiles;
+  const int wi0 = blockIdx.x / 2, wi_step = gridDim.x / 2;
+#define BHMC_DECODE_BWD2(wi)                                                                              \
+  const bool left = (wi) >= num_main;                                                                     \
+  const int wl = left ? (wi) - num_main : (wi);                                                           \
+  const int s = left ? wl / p.n_tiles : wl / per_split;                                                   \
+  const int rem = left ? wl % p.n_tiles : wl % per_split;                                                 \
+  const int mt = (left ? p.m_tiles : 2 * (rem / p.n_tiles)) + rank, nt = rem % p.n_tiles;                 \
+  const int cps_w = left ? p.left_cps : p.chunks_per_split;                                               \
+  const int k_begin = s * cps_w, k_end = min(p.k_chunks, k_begin + cps_w);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 2 * 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint64_t pol_a = make_l2_policy(p.hint_a), pol_b = make_l2_policy(p.hint_b);
+      (void)pol_a;
+      (void)pol_b;
+      for (int w = wi0; w < num_work; w += wi_step) {
+        BHMC_DECODE_BWD2(w)
+        for (int k = k_begin; k < k_end; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + nmat * a_bytes;
+          int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN + rank * (p.BN / 2);
+          if (p.a_slab) {
+            const int sl = ak / p.a_slab;
+            ak -= sl * p.a_slab;
+            am += sl * p.a_slab_rows;
+          }
+          if (p.b_slab) {
+            const int sl = bk / p.b_slab;
+            bk -= sl * p.b_slab;
+            bn += sl * p.b_slab_rows;
+          }
+          tma_load_2d_2sm(sa, &tmA_hi, full, ak, am);
+          if (p.split3) tma_load_2d_2sm(sa + a_bytes, &tmA_lo, full, ak, am);
+          tma_load_2d_2sm(sb, &tmB_hi, full, bk, bn);
+          if (p.split3) tma_load_2d_2sm(sb + bh_bytes, &tmB_lo, full, bk, bn);
+          if (p.prefetch && k + p.prefetch < k_end) {  // pull a later chunk of this item's operands into L2
+            int pak = p.a_k0 + (k + p.prefetch) * BK, pam = p.a_m0 + mt * BM, pbk = (k + p.prefetch) * BK;
+            int pbn = nt * p.BN + rank * (p.BN / 2);
+            if (p.a_slab) {
+              const int sl = pak / p.a_slab;
+              pak -= sl * p.a_slab;
+              pam += sl * p.a_slab_rows;
+            }
+            if (p.b_slab) {
+              const int sl = pbk / p.b_slab;
+              pbk -= sl * p.b_slab;
+              pbn += sl * p.b_slab_rows;
+            }
+            tma_prefetch_2d(&tmA_hi, pak, pam);
+            if (p.split3) tma_prefetch_2d(&tmA_lo, pak, pam);
+            tma_prefetch_2d(&tmB_hi, pbk, pbn);
+            if (p.split3) tma_prefetch_2d(&tmB_lo, pbk, pbn);
+          }
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {  // ===== MMA issuer (leader CTA; warp-uniform loop, elected lane issues) =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      long long t_tempty = 0, t_full = 0, t_issue = 0, t_start = clock64(), n_chunks = 0;
+      for (int w = wi0; w < num_work; w += wi_step) {
+        BHMC_DECODE_BWD2(w)
+        (void)mt;
+        (void)nt;
+        for (int kb = k_begin; kb < k_end; kb += p.sub_chunks, ++it) {
+          const int ke = min(k_end, kb + p.sub_chunks);
+          const int buf = it & 1;
+          const uint32_t use = (uint32_t)(it >> 1);
+          long long c0 = p.prof ? clock64() : 0;
+          mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+          tcgen05_fence_after();
+          if (p.prof) t_tempty += clock64() - c0;
+          const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+          for (int k = kb; k < ke; ++k) {
+            long long c1 = p.prof ? clock64() : 0;
+            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            tcgen05_fence_after();
+            long long c2 = p.prof ? clock64() : 0;
+            if (p.prof) t_full += c2 - c1, ++n_chunks;
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint32_t first = (k > kb) ? 1u : 0u;
+            if (p.split3) {
+              const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+              const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + bh_bytes);
+#pragma unroll
+              for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+                umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+                umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            } else {
+              const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+              for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+                umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+              }
+            }
+            umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);
+            if (p.prof) t_issue += clock64() - c2;
+            if (++stage == p.stages) stage = 0, phase ^= 1u;
+          }
+          umma_commit_2sm(smem_u32(&bar_tfull[buf]), 3);  // this sub-slab's accumulator halves are complete in both CTAs
+        }
+      }
+      if (p.prof && lane == 0) {
+        long long* o = p.prof + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - t_start, o[1] = t_tempty, o[2] = t_full, o[3] = t_issue, o[4] = n_chunks, o[5] = it;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, each on its own 128 rows) =====
+    const int ew = warp & 3, part = (warp - 4) >> 2;
+    constexpr int PARTS = EW / 4;
+    const int t = ew * 32 + lane;
+    int it = 0;
+    for (int w = wi0; w < num_work; w += wi_step) {
+      BHMC_DECODE_BWD2(w)
+      constexpr int MAXCH = 3;  // 16-column chunks per thread: BN <= 192 with 16 epilogue warps
+      float acc[MAXCH][16];
+#pragma unroll
+      for (int i = 0; i < MAXCH; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+      for (int kb = k_begin; kb < k_end; kb += p.sub_chunks, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+#pragma unroll
+        for (int i = 0; i < MAXCH; ++i) {
+          const int j0 = (part + i * PARTS) * 16;
+          if (j0 < p.BN) {  // warp-uniform
+            uint32_t raw[16];
+            tmem_ld<16>(tacc + (uint32_t)j0, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[i][j] += __uint_as_float(raw[j]);
+          }
+        }
+        tcgen05_fence_before();
+        if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
+        else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
+      }
+      const int64_t cols = (int64_t)p.n_tiles * p.BN;
+      float* dst = left ? p.part_left + ((int64_t)s * BM + t) * cols + (int64_t)nt * p.BN  // [s][128 rows of the odd tile]
+                        : p.part + ((int64_t)s * p.m_tiles * BM + (int64_t)mt * BM + t) * cols + (int64_t)nt * p.BN;
+      if (!(left && rank == 1)) {  // the phantom half of the odd pair has nothing to keep
+#pragma unroll
+        for (int i = 0; i < MAXCH; ++i) {
+          const int j0 = (part + i * PARTS) * 16;
+          if (j0 < p.BN) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              *reinterpret_cast<float4*>(dst + j0 + 4 * v) =
+                  make_float4(acc[i][4 * v], acc[i][4 * v + 1], acc[i][4 * v + 2], acc[i][4 * v + 3]);
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+#undef BHMC_DECODE_BWD2
+}
+
+// ---------------------------------------------------------------------------------------------
 // small helper kernels
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -739,8 +970,37 @@ __global__ void k_tc_prep(const float* __restrict__ q, int64_t ld, int D, int K,
 }
 
 // g[c, d*K + k] = alpha*q[c, d*K + k] + sum_s part[s, d, c*KP + k]      (d <= D: row D is the bias gradient)
-__global__ void k_tc_reduce(const float* __restrict__ part, int n_split, int64_t rows, int64_t cols, int K, int KP,
-                            int64_t P, const float* __restrict__ q, float* __restrict__ g, int64_t ld, float alpha) {
+// split-K partials of the backward GEMM: rows [0, split_row) come from the cta_group::2 launch (part0), the odd last
+// row tile (if any) from the single-CTA launch (part1); each region has its own number of row slabs
+struct PartRegions {
+  const float* part0;
+  const float* part1;
+  int n_split0, n_split1;
+  int64_t rows0, rows1;   // rows per slab of each region
+  int64_t split_row;      // first output row of region 1
+  int64_t cols;
+};
+__device__ __forceinline__ float sum_partials(const PartRegions& r, int64_t d, int64_t col) {
+  const bool main = d < r.split_row;
+  const float* src = (main ? r.part0 + d * r.cols : r.part1 + (d - r.split_row) * r.cols) + col;
+  const int ns = main ? r.n_split0 : r.n_split1;
+  const int64_t slab = (main ? r.rows0 : r.rows1) * r.cols;
+  // loads in batches of 8 (a plain `v += src[..]` loop serialises one DRAM latency per slab), summed in slab order
+  float v = 0.f;
+  int s = 0;
+  for (; s + 8 <= ns; s += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = src[(int64_t)(s + j) * slab];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += t[j];
+  }
+  for (; s < ns; ++s) v += src[(int64_t)s * slab];
+  return v;
+}
+
+__global__ void k_tc_reduce(PartRegions r, int K, int KP, int64_t P, const float* __restrict__ q, float* __restrict__ g,
+                            int64_t ld, float alpha) {
   int c = blockIdx.y;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ld) return;
@@ -748,8 +1008,7 @@ __global__ void k_tc_reduce(const float* __restrict__ part, int n_split, int64_t
   if (i < P) {
     int64_t d = i / K;
     int k = (int)(i - d * K);
-    const float* src = part + d * cols + (int64_t)c * KP + k;
-    for (int s = 0; s < n_split; ++s) v += src[(int64_t)s * rows * cols];
+    v = sum_partials(r, d, (int64_t)c * KP + k);
     v += alpha * q[(int64_t)c * ld + i];
   }
   g[(int64_t)c * ld + i] = v;
@@ -760,7 +1019,7 @@ __global__ void k_tc_reduce(const float* __restrict__ part, int n_split, int64_t
 // one the separate kernel draws).  g is not materialised.
 template <int KIND>
 __global__ void __launch_bounds__(256)
-k_tc_reduce_step(const float* __restrict__ part, int n_split, int64_t rows, int64_t cols, int D, int K, int KP, int64_t P,
+k_tc_reduce_step(PartRegions r, int D, int K, int KP, int64_t P,
                  int64_t ld, float alpha, FusedStep fs, int64_t Dp, __nv_bfloat16* __restrict__ wt_hi,
                  __nv_bfloat16* __restrict__ wt_lo, double* __restrict__ loglik) {
   const int c = blockIdx.y;
@@ -779,8 +1038,7 @@ k_tc_reduce_step(const float* __restrict__ part, int n_split, int64_t rows, int6
     kk[e] = (int)(idx - (int64_t)dd[e] * K);
     float v = 0.f;
     if (idx < P) {
-      const float* src = part + (int64_t)dd[e] * cols + (int64_t)c * KP + kk[e];
-      for (int s = 0; s < n_split; ++s) v += src[(int64_t)s * rows * cols];
+      v = sum_partials(r, dd[e], (int64_t)c * KP + kk[e]);
       v += alpha * qe[e];
     }
     ge[e] = v;
@@ -1078,6 +1336,35 @@ static int launch_fwd2_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
   return BHMC_OK;
 }
 
+static int launch_bwd2(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                       const CUtensorMap& b_lo, const TcParams& p) {
+  const int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + (p.BN / 2) * BK * 2);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bwd2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int work = p.n_split * (p.m_tiles / 2) * p.n_tiles + p.left_n_split * p.n_tiles;
+  const int grid = 2 * std::min(work, ctx->sm_count / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NON_EPI_THREADS + 32 * 16);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bwd2<16>, a_hi, a_lo, b_hi, b_lo, p));
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
 template <int MODE, int KP>
 static int launch_gemm(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                        const CUtensorMap& b_lo, const TcParams& p) {
@@ -1308,79 +1595,151 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   if (!g && !fs) return BHMC_OK;
 
   // ---- backward: G[D+1, C*KP] = Xt[D+1, rows] . DmT^T, split over row slabs ----
-  TcParams b{};
-  b.m_tiles = (int)ceil_div(d.Dt, BM);
-  b.n_tiles = n_tiles;
-  b.k_chunks = (int)ceil_div(nrows + shift, BK);
-  // split the contraction (rows) so that one round of work items fills the machine; choose between plain CTAs and
-  // CTA pairs (two N tiles sharing the X^T tile) by the length of the critical path: rounds x chunks per item
-  auto plan = [&](int pair, int* n_split, int* cps) {
-    const int units = pair ? ctx->sm_count / 2 : ctx->sm_count;
-    const int items = b.m_tiles * (pair ? (b.n_tiles + 1) / 2 : b.n_tiles);
-    int want = std::max(1, units / items);
-    want = std::min(want, std::max(1, b.k_chunks / 4));  // keep >= 4 chunks per slab
-    *cps = (int)ceil_div(b.k_chunks, want);
-    *n_split = (int)ceil_div(b.k_chunks, *cps);
-    const int rounds = (int)ceil_div((int64_t)items * *n_split, units);
-    return (double)rounds * *cps * (pair ? 0.97 : 1.0);
-  };
-  int ns0, cps0, ns2, cps2;
-  const double cost0 = plan(0, &ns0, &cps0);
-  const double cost2 = (pairing_enabled() && b.n_tiles >= 2) ? plan(2, &ns2, &cps2) : 1e30;
-  b.pair = cost2 < cost0 ? 2 : 0;
-  b.n_split = b.pair ? ns2 : ns0;
-  b.chunks_per_split = b.pair ? cps2 : cps0;
+  const int m_tiles_all = (int)ceil_div(d.Dt, BM);
+  const int k_chunks_b = (int)ceil_div(nrows + shift, BK);
+  // k_tc_bwd2 (cta_group::2 MMAs: two adjacent row tiles per CTA pair, 52 KB per SM per chunk instead of 72 KB) is
+  // OPT-IN (BHMC_BWD2=1, =2 also for launches with < 3 N tiles).  Timed alone it is 9 % faster than the single-CTA
+  // kernel (ncu: 152.5 + 9.9 us vs 167.6 + 11.1 us at cfg2, MMA thread at ~1005 cycles per chunk = the tensor
+  // roofline), but inside a long run the GPU sits at its 1 kW power cap: the busier tensor pipe plus the phantom half
+  // of the odd tile pair pull the SM clock from 1.53 to 1.37 GHz and the whole step gets SLOWER (169 k -> 162 k
+  // grad-evals/s, three A/B repetitions).  The run is energy-bound, not pipe-bound: removing flops helps, raising
+  // utilisation does not.
+  static int bwd2_env = -1;
+  if (bwd2_env < 0) {
+    const char* e = getenv("BHMC_BWD2");
+    bwd2_env = e ? atoi(e) : 0;
+  }
+  // (measured at cfg2: faster from ~3 N tiles on; launches that carry few chains are better off with more row slabs)
+  const bool use_bwd2 = bwd2_env && pairing_enabled() && m_tiles_all >= 2 && k_chunks_b >= 64 && BN % 16 == 0 &&
+                        (n_tiles >= 3 || bwd2_env >= 2);
+  const int m2 = use_bwd2 ? 2 * (m_tiles_all / 2) : 0;   // row tiles handled pairwise by k_tc_bwd2
+  const int m_left = use_bwd2 ? m_tiles_all - m2 : 0;    // odd last tile: extra work items of the same launch
+  const int m1 = use_bwd2 ? 0 : m_tiles_all;             // row tiles handled by the single-CTA kernel
   // <= 192 MMAs per tensor-core accumulation chain, then round-to-nearest fp32 adds (BHMC_SUB_CHUNKS overrides)
   static int sub_env = -1;
   if (sub_env < 0) {
     const char* e = getenv("BHMC_SUB_CHUNKS");
     sub_env = e ? std::max(1, atoi(e)) : 16;
   }
-  b.sub_chunks = sub_env * (64 / BK);  // expressed in 64-element units
-  b.BN = BN;
-  b.stages = stages;
-  b.split3 = split3 ? 1 : 0;
-  b.a_k0 = (int)(row0 - shift);
-  b.a_m0 = 0;
-  // L2 priorities: an operand tile is re-read by every work item that shares it.  (P-Y)^T tiles are re-read by all
-  // m_tiles row tiles of X^T -- at N = 1e6 they were evicted by the X^T stream and re-fetched from HBM 17 times.
   static int l2hint = -1;
   if (l2hint < 0) {
     const char* e = getenv("BHMC_L2HINT");
     l2hint = e ? atoi(e) : 1;
   }
-  if (l2hint) {
-    const int a_reuse = b.pair == 2 ? (b.n_tiles + 1) / 2 : b.n_tiles, b_reuse = b.m_tiles;
-    b.hint_a = a_reuse <= 1 ? 1 : 0;
-    b.hint_b = b_reuse >= 4 ? 2 : 0;
-  }
+  TcParams b{};
+  b.n_tiles = n_tiles;
+  b.k_chunks = k_chunks_b;
+  b.sub_chunks = sub_env * (64 / BK);  // expressed in 64-element units
+  b.BN = BN;
+  b.split3 = split3 ? 1 : 0;
+  b.a_k0 = (int)(row0 - shift);
   b.b_slab = (int)dm_slab;
   b.b_slab_rows = (int)dm_rows;
   b.a_slab = (int)d.slab;
   b.a_slab_rows = (int)d.Dt_pad;
-  const uint32_t bwd_abox = (uint32_t)(b.pair ? BM / 2 : BM);
-  int64_t prow = (int64_t)b.m_tiles * BM, pcol = (int64_t)b.n_tiles * BN;
-  void* part = nullptr;
-  BHMC_TRY(ctx->get_scratch(3, sizeof(float) * (size_t)b.n_split * prow * pcol, &part));
-  b.part = (float*)part;
+  const int64_t pcol = (int64_t)n_tiles * BN;
   const uint64_t xt_rows = (uint64_t)(d.Npad / d.slab) * d.Dt_pad;
-  BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, bwd_abox));
-  // every column a backward chunk reads is written by the forward epilogue (rows, alignment prefix, tail)
-  BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
-  if (split3) {
-    BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, bwd_abox));
-    BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
+
+  // plan of the pair kernel: split the contraction so that one round of (pair, N tile, slab) items fills the clusters
+  TcParams b2 = b;
+  if (m2) {
+    const int units = ctx->sm_count / 2, items = (m2 / 2) * n_tiles;
+    int want = std::max(1, units / items);
+    want = std::min(want, std::max(1, k_chunks_b / 4));
+    b2.chunks_per_split = (int)ceil_div(k_chunks_b, want);
+    b2.n_split = (int)ceil_div(k_chunks_b, b2.chunks_per_split);
+    b2.m_tiles = m2;
+    b2.a_m0 = 0;
+    b2.pair = 3;
+    const int st_bytes = nmat * (BM * BK * 2 + (BN / 2) * BK * 2);
+    b2.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / st_bytes)));
+    static int pf_env = -1;  // BHMC_PF: L2 prefetch distance of the pair kernel in chunks
+    if (pf_env < 0) {
+      const char* e = getenv("BHMC_PF");
+      pf_env = e ? std::max(0, atoi(e)) : 0;
+    }
+    b2.prefetch = pf_env;
+    if (m_left) {  // one more item per cluster: (odd tile + phantom) x N tile x row slab
+      int want_l = std::max(1, units / n_tiles);
+      want_l = std::min(want_l, std::max(1, k_chunks_b / 4));
+      b2.left_cps = (int)ceil_div(k_chunks_b, want_l);
+      b2.left_n_split = (int)ceil_div(k_chunks_b, b2.left_cps);
+    }
   } else {
-    a_lo = a_hi;
-    b_lo = b_hi;
+    b2.n_split = 0;
   }
+  // plan of the single-CTA kernel (all row tiles, or only the odd last one): plain CTAs or CTA pairs sharing the X^T
+  // tile between two N tiles, whichever has the shorter critical path (rounds x chunks per item)
+  TcParams b1 = b;
+  if (m1) {
+    b1.m_tiles = m1;
+    b1.a_m0 = m2 * BM;
+    auto plan = [&](int pair, int* n_split, int* cps) {
+      const int units = pair ? ctx->sm_count / 2 : ctx->sm_count;
+      const int items = m1 * (pair ? (n_tiles + 1) / 2 : n_tiles);
+      int want = std::max(1, units / items);
+      want = std::min(want, std::max(1, k_chunks_b / 4));  // keep >= 4 chunks per slab
+      *cps = (int)ceil_div(k_chunks_b, want);
+      *n_split = (int)ceil_div(k_chunks_b, *cps);
+      const int rounds = (int)ceil_div((int64_t)items * *n_split, units);
+      return (double)rounds * *cps * (pair ? 0.97 : 1.0);
+    };
+    int ns0, cps0, ns2 = 1, cps2 = 1;
+    const double cost0 = plan(0, &ns0, &cps0);
+    const double cost2 = (pairing_enabled() && n_tiles >= 2) ? plan(2, &ns2, &cps2) : 1e30;
+    b1.pair = cost2 < cost0 ? 2 : 0;
+    b1.n_split = b1.pair ? ns2 : ns0;
+    b1.chunks_per_split = b1.pair ? cps2 : cps0;
+    b1.stages = stages;
+    if (l2hint) {
+      const int a_reuse = b1.pair == 2 ? (n_tiles + 1) / 2 : n_tiles;
+      b1.hint_a = a_reuse <= 1 ? 1 : 0;
+      b1.hint_b = m1 >= 4 ? 2 : 0;
+    }
+  } else {
+    b1.n_split = 0;
+  }
+  const int64_t rows2 = (int64_t)m2 * BM, rows1 = (int64_t)m1 * BM;
+  void* part = nullptr;
+  const size_t part2_elems = (size_t)b2.n_split * rows2 * pcol;
+  const size_t part1_elems = m2 ? (size_t)b2.left_n_split * BM * pcol : (size_t)b1.n_split * rows1 * pcol;
+  BHMC_TRY(ctx->get_scratch(3, sizeof(float) * (part2_elems + part1_elems), &part));
+  b2.part = (float*)part;
+  b2.part_left = (float*)part + part2_elems;
+  b1.part = (float*)part + part2_elems;
   if (want_prof) {
     BHMC_CUDA_OK(cudaMemsetAsync(prof_dev, 0, sizeof(long long) * 8 * 1024, ctx->stream));
-    b.prof = (long long*)prof_dev;
+    b2.prof = (long long*)prof_dev;
+    if (!m2) b1.prof = (long long*)prof_dev;
   }
   {
     GroupTimer t(ctx, KG_BWD);
-    BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, b)));
+    // every column a backward chunk reads is written by the forward epilogue (rows, alignment prefix, tail)
+    if (m2) {
+      BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, BM));
+      BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)(BN / 2)));
+      if (split3) {
+        BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, BM));
+        BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)(BN / 2)));
+      } else {
+        a_lo = a_hi;
+        b_lo = b_hi;
+      }
+      BHMC_TRY(launch_bwd2(ctx, a_hi, a_lo, b_hi, b_lo, b2));
+    }
+    if (m1) {
+      const uint32_t abox = (uint32_t)(b1.pair ? BM / 2 : BM);
+      BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, abox));
+      BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
+      if (split3) {
+        BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, abox));
+        BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
+      } else {
+        a_lo = a_hi;
+        b_lo = b_hi;
+      }
+      BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, b1)));
+    }
     if (want_prof) {
       std::vector<long long> hp(8 * 148);
       BHMC_CUDA_OK(cudaMemcpyAsync(hp.data(), prof_dev, sizeof(long long) * 8 * 148, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1392,21 +1751,32 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
           tot += hp[bb * 8], te += hp[bb * 8 + 1], tf += hp[bb * 8 + 2], ti += hp[bb * 8 + 3], nc += hp[bb * 8 + 4], nt += hp[bb * 8 + 5], ++n;
           mx = std::max(mx, (double)hp[bb * 8]);
         }
+      const TcParams& bp = m2 ? b2 : b1;
       if (n)
-        fprintf(stderr, "[bhmc prof bwd] n_split %d cps %d pair %d BN %d stages %d | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
-                b.n_split, b.chunks_per_split, b.pair, b.BN, b.stages, n, tot / n, mx, te / n, tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
+        fprintf(stderr, "[bhmc prof bwd] %s n_split %d cps %d pair %d BN %d stages %d (+ %d odd tile: n_split %d cps %d) | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
+                m2 ? "cta_group::2" : "single", bp.n_split, bp.chunks_per_split, bp.pair, bp.BN, bp.stages, m_left,
+                b2.left_n_split, b2.left_cps, n, tot / n, mx, te / n, tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
     }
+    PartRegions pr{};
+    pr.part0 = m2 ? b2.part : b1.part;
+    pr.n_split0 = m2 ? b2.n_split : b1.n_split;
+    pr.rows0 = m2 ? rows2 : rows1;
+    pr.part1 = m2 ? b2.part_left : b1.part;
+    pr.n_split1 = m2 ? b2.left_n_split : b1.n_split;
+    pr.rows1 = m2 ? BM : rows1;
+    pr.split_row = m2 ? rows2 : ((int64_t)1 << 40);
+    pr.cols = pcol;
     if (fs) {
       dim3 grid((unsigned)ceil_div(ceil_div(ld, 4), 256), C);
       if (fs->kind == BHMC_KIND_SGLD)
-        k_tc_reduce_step<BHMC_KIND_SGLD><<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, D, K, KP, P, ld, alpha, *fs,
-                                                                        d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
+        k_tc_reduce_step<BHMC_KIND_SGLD><<<grid, 256, 0, ctx->stream>>>(pr, D, K, KP, P, ld, alpha, *fs, d.Dp, wt_hi,
+                                                                        split3 ? wt_lo : nullptr, loglik);
       else
-        k_tc_reduce_step<BHMC_KIND_SGD><<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, D, K, KP, P, ld, alpha, *fs,
-                                                                       d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
+        k_tc_reduce_step<BHMC_KIND_SGD><<<grid, 256, 0, ctx->stream>>>(pr, D, K, KP, P, ld, alpha, *fs, d.Dp, wt_hi,
+                                                                       split3 ? wt_lo : nullptr, loglik);
     } else {
       dim3 grid((unsigned)ceil_div(ld, 256), C);
-      k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(b.part, b.n_split, prow, pcol, K, KP, P, q, g, ld, alpha);
+      k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(pr, K, KP, P, q, g, ld, alpha);
     }
     ctx->launches++;
   }

@@ -81,6 +81,10 @@ __device__ __forceinline__ void tma_load_2d_mc_hint(uint32_t dst, const CUtensor
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(policy)
       : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): hides HBM latency ahead of the real TMA load
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
