@@ -102,6 +102,9 @@ _PROTOS = {
     "bhmc_sampler_get": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "bhmc_sampler_hmc_run": (C.c_int, [C.c_void_p, C.POINTER(HmcRun)]),
     "bhmc_sampler_sg_run": (C.c_int, [C.c_void_p, C.POINTER(SgRun)]),
+    "bhmc_stream_plan_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
 }
 
 GRAD_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64)

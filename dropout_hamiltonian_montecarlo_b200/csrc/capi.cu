@@ -747,6 +747,99 @@ int bhmc_sampler_get(bhmc_sampler* s, int32_t which, float* dst, int32_t is_host
   return BHMC_OK;
 }
 
+// Host-only planner of the streaming schedule (no CUDA): everything the launch loop needs, from the path lengths.
+struct StreamPlan {
+  int64_t J = 0;                      // gradient launches; elementwise phases are 0..J
+  int64_t n_grad_evals = 0;           // chain-evaluations that move a chain (+ one start point per chain)
+  std::vector<int32_t> perm;          // row -> chain, most total work first
+  std::vector<int> rows_el, rows_grad;  // active rows of elementwise phase j / gradient launch j (prefixes)
+  std::vector<char> ev_finish, ev_begin;
+};
+static int64_t stream_slots(int Lt, int nsw) { return (int64_t)std::max(Lt - 1, 1) * nsw; }
+// pass 1: sizes and row order
+static void stream_plan_order(const int32_t* L, int C, int n_steps, int nsw, StreamPlan* pl) {
+  std::vector<int64_t> T(C, 1);  // launches per chain: 1 (start point of its first transition) + max(L-1,1)*nsw each
+  pl->n_grad_evals = 0;
+  for (int c = 0; c < C; ++c) {
+    pl->n_grad_evals += 1;
+    for (int t = 0; t < n_steps; ++t) {
+      T[c] += stream_slots(L[(size_t)t * C + c], nsw);
+      pl->n_grad_evals += (int64_t)std::max(L[(size_t)t * C + c] - 1, 0) * nsw;
+    }
+  }
+  pl->perm.resize(C);
+  for (int c = 0; c < C; ++c) pl->perm[c] = c;
+  std::stable_sort(pl->perm.begin(), pl->perm.end(), [&](int32_t x, int32_t y) { return T[x] > T[y]; });
+  pl->J = T[pl->perm[0]];
+}
+// pass 2: op tables, [J+1][C] each, zero-initialised by the caller.  code1 = update before the Metropolis tests of a
+// phase, code2 = update after the begins of the phase (first half kick + drift of the transitions that start in it)
+static void stream_plan_ops(const int32_t* L, int C, int n_steps, int nsw, StreamPlan* pl, uint32_t* code1, uint32_t* code2,
+                            int32_t* step1, int32_t* step2) {
+  const int64_t J = pl->J;
+  pl->rows_el.assign(J + 2, 0);
+  pl->rows_grad.assign(J + 1, 0);
+  pl->ev_finish.assign(J + 1, 0);
+  pl->ev_begin.assign(J + 1, 0);
+  for (int r = 0; r < C; ++r) {
+    const int c = pl->perm[r];
+    code1[0 * C + r] = OP_BEGIN;  // phase 0: begin transition 0; launch 0 evaluates its start point
+    step1[0 * C + r] = 0;
+    pl->ev_begin[0] = 1;
+    int64_t j = 1;
+    for (int t = 0; t < n_steps; ++t) {
+      const int Lt = L[(size_t)t * C + c];
+      const int iters = std::max(Lt - 1, 0);
+      // phase j: first sub-step of transition t.  t == 0: in the ordinary update (after the start-point launch);
+      // t > 0: in the post-begin update of the phase in which transition t-1 was finished
+      uint32_t* first_code = t == 0 ? code1 : code2;
+      int32_t* first_step = t == 0 ? step1 : step2;
+      first_code[j * C + r] |= (t == 0 ? OP_LATCH : OP_LATCH_CACHED) | (iters > 0 ? OP_PRE | (0u << 12) : 0u);
+      first_step[j * C + r] = t;
+      const int64_t ns = stream_slots(Lt, nsw);
+      for (int64_t k = 1; k < ns; ++k) {  // remaining sub-steps: closing kick of the previous + opening of this
+        const int v = (int)(k % nsw), pv = v == 0 ? nsw - 1 : v - 1;
+        if (iters > 0) code1[(j + k) * C + r] |= OP_POST | ((uint32_t)pv << 8) | OP_PRE | ((uint32_t)v << 12);
+        step1[(j + k) * C + r] = t;
+      }
+      j += ns;
+      // phase j: closing kick of the last variable, Metropolis test, begin of transition t+1
+      if (iters > 0) code1[j * C + r] |= OP_POST | ((uint32_t)(nsw - 1) << 8);
+      code1[j * C + r] |= OP_FINISH | (t + 1 < n_steps ? OP_BEGIN : 0u);
+      step1[j * C + r] = t;
+      pl->ev_finish[j] = 1;
+      if (t + 1 < n_steps) pl->ev_begin[j] = 1;
+    }
+    // j == T[c]: the chain takes part in elementwise phases 0..T and gradient launches 0..T-1
+    for (int64_t k = 0; k <= j; ++k) pl->rows_el[k] = r + 1;  // rows sorted by T descending -> prefix
+    for (int64_t k = 0; k < j; ++k) pl->rows_grad[k] = r + 1;
+  }
+}
+
+// Test hook (host only, no device needed): compiles the plan for path lengths L[n_steps][n_chains].  Call with
+// code1 == NULL to get the sizes (n_phases = J), then with four [(J+1)*n_chains] arrays, perm[n_chains] and
+// rows_el[J+1] / rows_grad[J+1].
+extern "C" int bhmc_stream_plan_host(const int32_t* L, int32_t n_chains, int32_t n_steps, int32_t n_sweep, int64_t* n_phases,
+                                     int64_t* n_grad_evals, uint32_t* code1, uint32_t* code2, int32_t* step1, int32_t* step2,
+                                     int32_t* perm, int32_t* rows_el, int32_t* rows_grad) {
+  BHMC_CHECK_ARG(L && n_chains > 0 && n_steps > 0 && n_sweep > 0 && n_sweep <= BHMC_MAX_VARS && n_phases, "bad argument");
+  StreamPlan pl;
+  stream_plan_order(L, n_chains, n_steps, n_sweep, &pl);
+  *n_phases = pl.J;
+  if (n_grad_evals) *n_grad_evals = pl.n_grad_evals;
+  if (!code1) return BHMC_OK;
+  BHMC_CHECK_ARG(code2 && step1 && step2 && perm && rows_el && rows_grad, "output array is NULL");
+  const size_t n = (size_t)(pl.J + 1) * n_chains;
+  memset(code1, 0, sizeof(uint32_t) * n);
+  memset(code2, 0, sizeof(uint32_t) * n);
+  memset(step1, 0, sizeof(int32_t) * n);
+  memset(step2, 0, sizeof(int32_t) * n);
+  stream_plan_ops(L, n_chains, n_steps, n_sweep, &pl, code1, code2, step1, step2);
+  for (int c = 0; c < n_chains; ++c) perm[c] = pl.perm[c];
+  for (int64_t j = 0; j <= pl.J; ++j) rows_el[j] = pl.rows_el[j], rows_grad[j] = j < pl.J ? pl.rows_grad[j] : 0;
+  return BHMC_OK;
+}
+
 // ---- HMC, streaming schedule (asynchronous chains) -----------------------------------------------------------
 // Path lengths are fresh uniforms per chain and step (hmc.py:46), so in lockstep the chains of one transition finish
 // at very different times (E[L]/max L ~ 0.5 for 64 chains).  Chains are independent, so nothing forces them to start
@@ -783,25 +876,11 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   struct timespec ts_setup;
   clock_gettime(CLOCK_MONOTONIC, &ts_setup);
 
-  // launches per chain: 1 (start point of its first transition) + per transition max(L-1, 1)*nsw
-  auto slots = [&](int Lt) { return (int64_t)std::max(Lt - 1, 1) * nsw; };
-  std::vector<int64_t> T(C, 1);
-  run->n_grad_evals = 0;
-  for (int c = 0; c < C; ++c) {
-    run->n_grad_evals += 1;
-    for (int t = 0; t < n_steps; ++t) {
-      T[c] += slots(L[(size_t)t * C + c]);
-      run->n_grad_evals += (int64_t)std::max(L[(size_t)t * C + c] - 1, 0) * nsw;  // evaluations that moved a chain
-    }
-  }
-  std::vector<int32_t> perm(C);
-  for (int c = 0; c < C; ++c) perm[c] = c;
-  std::stable_sort(perm.begin(), perm.end(), [&](int32_t x, int32_t y) { return T[x] > T[y]; });
-  const int64_t J = T[perm[0]];  // gradient launches; elementwise phases are 0..J (phase T_c finishes chain c)
+  StreamPlan pl;
+  stream_plan_order(L.data(), C, n_steps, nsw, &pl);
+  run->n_grad_evals = pl.n_grad_evals;
+  const int64_t J = pl.J;
   BHMC_CHECK_ARG(J < (1LL << 24), "run too long for one call (%lld phases): lower n_steps", (long long)J);
-
-  // ---- compile the op tables: code1 = update before the Metropolis tests of the phase, code2 = update after the
-  // begins of the phase (first half kick + drift of the transitions that start in it) -------------------------------
   const size_t n_ops = (size_t)(J + 1) * C;
   const size_t code_bytes = round_up(sizeof(uint32_t) * n_ops, 64), perm_bytes = round_up(sizeof(int32_t) * C, 64);
   const size_t u_bytes = sizeof(double) * (size_t)n_steps * C;
@@ -819,41 +898,12 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   int32_t* perm_h = (int32_t*)((char*)pin + 4 * code_bytes);
   double* uacc_h = (double*)((char*)pin + tab_bytes);
   memset(pin, 0, 4 * code_bytes);
-  std::vector<int> rows_el(J + 2, 0), rows_grad(J + 1, 0);  // active row counts per phase
-  std::vector<char> ev_finish(J + 1, 0), ev_begin(J + 1, 0);
-  for (int r = 0; r < C; ++r) {
-    const int c = perm[r];
-    perm_h[r] = c;
-    code1_h[0 * C + r] = OP_BEGIN;  // phase 0: begin transition 0; launch 0 evaluates its start point
-    step1_h[0 * C + r] = 0;
-    ev_begin[0] = 1;
-    int64_t j = 1;
-    for (int t = 0; t < n_steps; ++t) {
-      const int Lt = L[(size_t)t * C + c];
-      const int iters = std::max(Lt - 1, 0);
-      // phase j: first sub-step of transition t.  t == 0: in the ordinary update (after the start-point launch);
-      // t > 0: in the post-begin update of the phase in which transition t-1 was finished
-      uint32_t* first_code = t == 0 ? code1_h : code2_h;
-      int32_t* first_step = t == 0 ? step1_h : step2_h;
-      first_code[j * C + r] |= (t == 0 ? OP_LATCH : OP_LATCH_CACHED) | (iters > 0 ? OP_PRE | (0u << 12) : 0u);
-      first_step[j * C + r] = t;
-      for (int64_t k = 1; k < slots(Lt); ++k) {  // remaining sub-steps: closing kick of the previous + opening of this
-        const int v = (int)(k % nsw), pv = v == 0 ? nsw - 1 : v - 1;
-        if (iters > 0) code1_h[(j + k) * C + r] |= OP_POST | ((uint32_t)pv << 8) | OP_PRE | ((uint32_t)v << 12);
-        step1_h[(j + k) * C + r] = t;
-      }
-      j += slots(Lt);
-      // phase j: closing kick of the last variable, Metropolis test, begin of transition t+1
-      if (iters > 0) code1_h[j * C + r] |= OP_POST | ((uint32_t)(nsw - 1) << 8);
-      code1_h[j * C + r] |= OP_FINISH | (t + 1 < n_steps ? OP_BEGIN : 0u);
-      step1_h[j * C + r] = t;
-      ev_finish[j] = 1;
-      if (t + 1 < n_steps) ev_begin[j] = 1;
-    }
-    // j == T[c]: the chain takes part in elementwise phases 0..T and gradient launches 0..T-1
-    for (int64_t k = 0; k <= j; ++k) rows_el[k] = r + 1;  // rows sorted by T descending -> prefix
-    for (int64_t k = 0; k < j; ++k) rows_grad[k] = r + 1;
-  }
+  stream_plan_ops(L.data(), C, n_steps, nsw, &pl, code1_h, code2_h, step1_h, step2_h);
+  for (int r = 0; r < C; ++r) perm_h[r] = pl.perm[r];
+  const std::vector<int>& rows_el = pl.rows_el;
+  const std::vector<int>& rows_grad = pl.rows_grad;
+  const std::vector<char>& ev_finish = pl.ev_finish;
+  const std::vector<char>& ev_begin = pl.ev_begin;
   if (run->u_accept_host) memcpy(uacc_h, run->u_accept_host, u_bytes);
   void* dev = nullptr;
   BHMC_TRY(ctx->get_scratch(6, std::max(tab_bytes + u_bytes, (size_t)32 << 20), &dev));

@@ -238,6 +238,14 @@ typedef struct bhmc_sg_run {
 /* SGLD (kind SGLD) / SGD (kind SGD) epochs over sequential minibatches */
 int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run);
 
+/* ---- test hook, host only (no device needed): compiles the streaming schedule for path lengths L[n_steps][n_chains].
+ * Call with code1 == NULL to get n_phases (gradient launches J) and n_grad_evals, then with code1/code2/step1/step2 of
+ * (J+1)*n_chains entries each (ops of the update before / after the begins of a phase and the transition index they
+ * refer to), perm[n_chains] (row -> chain), rows_el[J+1], rows_grad[J+1] (active rows per phase / launch). */
+int bhmc_stream_plan_host(const int32_t* L, int32_t n_chains, int32_t n_steps, int32_t n_sweep, int64_t* n_phases,
+                          int64_t* n_grad_evals, uint32_t* code1, uint32_t* code2, int32_t* step1, int32_t* step2,
+                          int32_t* perm, int32_t* rows_el, int32_t* rows_grad);
+
 /* ---- measurement helper: time one fused update kernel in isolation (CUDA events on the context stream).
  * which: 0 = HMC kick+drift (20 B/param), 1 = SGHMC friction+Philox noise+drift (20 B/param),
  *        2 = SGLD with Philox noise (16 B/param), 3 = accept/select + sample sink (20 B/param),
