@@ -75,6 +75,8 @@ _PROTOS = {
                                   C.c_uint64, C.c_int64, C.POINTER(C.c_void_p)]),
     "bhmc_mlp_bind_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "bhmc_mlp_set_masks": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bhmc_mlp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                   C.c_void_p, C.c_void_p]),
     "bhmc_model_set_global_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_float]),
     "bhmc_model_destroy": (C.c_int, [C.c_void_p]),
     "bhmc_model_n_params": (C.c_int64, [C.c_void_p]),

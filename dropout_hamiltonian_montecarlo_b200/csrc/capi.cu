@@ -532,6 +532,13 @@ int bhmc_mlp_set_masks(bhmc_model* m, const uint8_t* masks_dev) {
   return mlp_model_set_masks(m->impl, masks_dev);
 }
 
+int bhmc_mlp_predict(bhmc_model* m, const float* q, int32_t C, int64_t ld, const float* X_dev, int64_t nrows, int32_t prec,
+                     float* probs_dev, int32_t* labels_dev) {
+  BHMC_CHECK_ARG(m && m->impl, "model is NULL");
+  BHMC_CUDA_OK(cudaSetDevice(m->impl->ctx->device));
+  return mlp_model_predict(m->impl, q, C, ld, X_dev, nrows, prec, probs_dev, labels_dev);
+}
+
 int bhmc_model_set_global_rows(bhmc_model* m, int64_t n_global_rows, float alpha_global) {
   SoftmaxModel* s;
   BHMC_TRY(softmax_of(m, &s));

@@ -356,5 +356,7 @@ ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int
                          uint64_t seed, int64_t chain_id0);
 int mlp_model_bind(ModelBase* m, const float* X, const int32_t* labels, int is_host);
 int mlp_model_set_masks(ModelBase* m, const uint8_t* masks_dev);
+int mlp_model_predict(ModelBase* m, const float* q, int C, int64_t ld, const float* X_dev, int64_t nrows, int prec,
+                      float* probs_dev, int32_t* labels_dev);
 
 }  // namespace bhmc

@@ -171,6 +171,7 @@ struct MlpModel : ModelBase {
   int64_t chain_id0 = 0;
   uint32_t eval_id = 0;
   int64_t oW1, ob1, oW2, ob2, oW3, ob3;
+  float* logits_sink = nullptr;  // predict: grad() stops after the forward pass and leaves the logits here
 
   ~MlpModel() override {
     cudaFree(X_owned);
@@ -187,7 +188,7 @@ struct MlpModel : ModelBase {
 
   int grad(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat,
            uint32_t) override {
-    BHMC_CHECK_ARG(X && labels, "mlp model has no bound data");
+    BHMC_CHECK_ARG(X && (labels || logits_sink), "mlp model has no bound data");
     BHMC_CHECK_ARG(row0 >= 0 && nrows > 0 && row0 + nrows <= N, "row window outside the bound rows");
     const int B = (int)nrows;
     const float keep_inv = 1.0f / (1.0f - ratio), keep_prob = 1.0f - ratio;
@@ -250,6 +251,10 @@ struct MlpModel : ModelBase {
       d.M = B, d.N = n_out, d.K = n_mid;
       d.bias = q + ob3, d.bias_batch = ld;
       BHMC_TRY(run_gemm(ctx, d, C));
+      if (logits_sink) {
+        BHMC_CUDA_OK(cudaMemcpyAsync(logits_sink, Z, sizeof(float) * (size_t)C * B * n_out, cudaMemcpyDeviceToDevice, ctx->stream));
+        return BHMC_OK;
+      }
       dim3 grid((unsigned)ceil_div(B, 256), C);
       k_mlp_loss<<<grid, 256, 0, ctx->stream>>>(Z, B, n_out, labels + row0, stat, g ? 1 : 0);
       ctx->launches++;
@@ -349,6 +354,58 @@ int mlp_model_bind(ModelBase* mb, const float* X, const int32_t* labels, int is_
     m->X = X;
     m->labels = labels;
   }
+  return BHMC_OK;
+}
+
+// row softmax / argmax of the logits [C, B, n_out] (mlp.py:84-95)
+__global__ void __launch_bounds__(256) k_mlp_predict(const float* __restrict__ Z, int B, int n_out, float* __restrict__ probs,
+                                                     int32_t* __restrict__ lab) {
+  const int c = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  const float* z = Z + ((int64_t)c * B + r) * n_out;
+  float m = -INFINITY;
+  int am = 0;
+  for (int k = 0; k < n_out; ++k)
+    if (z[k] > m) m = z[k], am = k;
+  if (lab) lab[(int64_t)c * B + r] = am;
+  if (probs) {
+    float s = 0.f;
+    for (int k = 0; k < n_out; ++k) s += expf(z[k] - m);
+    const float inv = 1.0f / s;
+    for (int k = 0; k < n_out; ++k) probs[((int64_t)c * B + r) * n_out + k] = expf(z[k] - m) * inv;
+  }
+}
+
+// mlp.predict (mlp.py:84-95): forward pass of every chain on caller rows X_dev [nrows, n_in] -- dropout stays ON, as in
+// the reference (no train=False there) -- then softmax / argmax.  probs_dev [C, nrows, n_out], labels_dev [C, nrows].
+int mlp_model_predict(ModelBase* mb, const float* q, int C, int64_t ld, const float* X_dev, int64_t nrows, int prec,
+                      float* probs_dev, int32_t* labels_dev) {
+  auto* m = dynamic_cast<MlpModel*>(mb);
+  BHMC_CHECK_ARG(m && q && X_dev && nrows > 0 && (probs_dev || labels_dev), "bad argument");
+  void* zb = nullptr;
+  BHMC_TRY(m->ctx->get_scratch(10, sizeof(float) * (size_t)C * nrows * m->n_out, &zb));
+  const float* X0 = m->X;
+  const int64_t N0 = m->N;
+  const uint8_t* masks0 = m->masks;  // injected masks are shaped for the training batch: predict draws Philox masks
+  m->X = X_dev;
+  m->N = nrows;
+  m->masks = nullptr;
+  m->logits_sink = (float*)zb;
+  double* stat = nullptr;
+  void* sb = nullptr;
+  int rc = m->ctx->get_scratch(11, sizeof(double) * C, &sb);
+  stat = (double*)sb;
+  if (rc == BHMC_OK) rc = m->grad(q, C, ld, 0, nrows, prec, nullptr, stat, 0);
+  m->X = X0;
+  m->N = N0;
+  m->masks = masks0;
+  m->logits_sink = nullptr;
+  BHMC_TRY(rc);
+  dim3 grid((unsigned)ceil_div(nrows, 256), C);
+  k_mlp_predict<<<grid, 256, 0, m->ctx->stream>>>((const float*)zb, (int)nrows, m->n_out, probs_dev, labels_dev);
+  m->ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
 }
 

@@ -91,3 +91,22 @@ class mlp(_base.ChainModel):
         q, squeeze, _ = self.flatten(par, self.var_shapes())
         out = h.nlp(h.pack(q), 0, h.N, PREC[self.precision]).cpu().numpy()
         return float(out[0]) if squeeze else out
+
+    def predict(self, par, X_test, prob=False):
+        """mlp.py:84-95 -- forward pass with dropout ON (the reference never passes ``train=False``), then softmax
+        (``prob=True``) or argmax.  Masks are drawn by the in-kernel Philox generator (injected training masks are
+        shaped for the training batch and are not used here); ``dropout=0`` makes the pass deterministic."""
+        Xd = X_test if (isinstance(X_test, torch.Tensor) and X_test.is_cuda) else torch.as_tensor(
+            np.ascontiguousarray(np.asarray(X_test, dtype=np.float32))).to(self.ctx.device)
+        Xd = Xd.to(torch.float32).contiguous()
+        h = self._bound[1] if self._bound is not None else None
+        own = h is None
+        if own:  # no training data bound: a handle just for the forward pass
+            h = MlpHandle(self.ctx, Xd.shape[0], self.n_in, self.n_mid, self.n_out, float(self.hyper["alpha"]), self.dropout,
+                          self.seed, self.chain_id0)
+        q, squeeze, _ = self.flatten(par, self.var_shapes())
+        probs, labels = h.predict(h.pack(q), Xd, PREC[self.precision], want_probs=prob, want_labels=not prob)
+        out = (probs if prob else labels).cpu().numpy()
+        if own:
+            h.close()
+        return out[0] if squeeze else out

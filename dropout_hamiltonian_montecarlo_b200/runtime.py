@@ -183,6 +183,15 @@ class MlpHandle(ModelHandle):
         if not X.is_cuda:
             self.ctx.sync()
 
+    def predict(self, q_dev, X_dev, precision, want_probs=True, want_labels=True):
+        """mlp.predict on caller rows: (probs [C, n, n_out] or None, labels [C, n] or None)."""
+        Cn, n = q_dev.shape[0], X_dev.shape[0]
+        probs = self.ctx.empty((Cn, n, self.n_out)) if want_probs else None
+        labels = self.ctx.empty((Cn, n), torch.int32) if want_labels else None
+        check(self.ctx.L.bhmc_mlp_predict(self.handle, _ptr(q_dev), Cn, self.ld, _ptr(X_dev), n, precision, _ptr(probs),
+                                          _ptr(labels)))
+        return probs, labels
+
     def set_masks(self, masks):
         """masks: uint8 CUDA tensor [3, C, B, n_mid] of keep flags, or None for Philox dropout."""
         self._masks = masks

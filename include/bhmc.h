@@ -111,6 +111,11 @@ int bhmc_mlp_create(bhmc_ctx* ctx, int64_t n_rows, int32_t n_in, int32_t n_mid, 
 int bhmc_mlp_bind_data(bhmc_model* m, const float* X, const int32_t* labels, int32_t is_host);
 /* injected keep-masks, DEVICE uint8 [3][n_chains][batch_rows][n_mid] (NULL = back to Philox) */
 int bhmc_mlp_set_masks(bhmc_model* m, const uint8_t* masks_dev);
+/* mlp.predict (hamiltonian/models/gpu/mlp.py:84-95) on caller rows X_dev [nrows, n_in]: forward pass of every chain with
+ * dropout ON (the reference never switches it off), then softmax / argmax.  probs_dev [n_chains, nrows, n_out] fp32
+ * and/or labels_dev [n_chains, nrows] int32 (either may be NULL). */
+int bhmc_mlp_predict(bhmc_model* m, const float* q_dev, int32_t n_chains, int64_t ld, const float* X_dev, int64_t nrows,
+                     int32_t precision, float* probs_dev, int32_t* labels_dev);
 /* row-sharded data (multi-GPU full-batch HMC): this model holds n_rows of n_global_rows; energies are
  * normalised by the global count (softmax.py:79 divides by the size of the whole X_train) and the
  * log-prior constant uses alpha_global (the model itself was created with alpha_global / n_ranks so that the

@@ -132,3 +132,31 @@ def test_sgd_fit_on_mlp_reduces_loss():
     opt = sgd(model, par, step_size=0.05)
     fitted, loss = opt.fit(epochs=30, batch_size=64, gamma=0.9, X_train=X, y_train=y)
     assert loss[-1] < 0.7 * loss[0]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_mlp_predict(prec):
+    """mlp.predict (mlp.py:84-95): with dropout=0 the forward pass is deterministic and must match the oracle's
+    forward; with dropout on (reference behaviour) the probabilities are a valid distribution and differ between
+    chains only through their parameters and masks."""
+    rs = np.random.RandomState(3)
+    B, n_in, n_mid, n_out, C = 77, 40, 64, 6, 3
+    par, X, y = make(rs, B, n_in, n_mid, n_out, C)
+    m0 = mlp({"alpha": 0.05}, n_in, n_mid, n_out, precision=prec, dropout=0.0)
+    probs = m0.predict(par, X, prob=True)
+    labels = m0.predict(par, X)
+    assert probs.shape == (C, B, n_out) and labels.shape == (C, B)
+    for c in range(C):
+        pc = {k: par[k][c] for k in KEYS}
+        z = O.mlp_forward(pc, X, None)[0]
+        e = np.exp(z - z.max(axis=1, keepdims=True))
+        ref = e / e.sum(axis=1, keepdims=True)
+        close(probs[c], ref, rtol=2e-4, atol_scale=2e-5, what="chain %d" % c)
+        assert (labels[c] == ref.argmax(axis=1)).mean() > 0.97
+    one = m0.predict({k: par[k][0] for k in KEYS}, X, prob=True)
+    assert one.shape == (B, n_out)
+    close(one, probs[0], rtol=1e-6, atol_scale=1e-7)
+    m1 = mlp({"alpha": 0.05}, n_in, n_mid, n_out, precision=prec, dropout=0.1, seed=7)
+    p1 = m1.predict(par, X, prob=True)
+    np.testing.assert_allclose(p1.sum(axis=2), 1.0, rtol=1e-5)
+    assert np.abs(p1 - probs).max() > 1e-3  # dropout really is on
