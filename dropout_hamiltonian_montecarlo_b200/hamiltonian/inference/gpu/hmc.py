@@ -131,6 +131,22 @@ class _ChainSampler:
 class hmc(_ChainSampler):
     kind = "hmc"
 
+    # ---- the reference's building blocks, for callers that compose their own loop (host side; ``step`` / ``sample``
+    # do not go through them: the device drivers fuse these operations) ------------------------------------------
+    def potential_energy(self, p):
+        """hmc.py:74-79 -- despite its name the kinetic energy ``sum_v 0.5 |p_v|^2``."""
+        return float(sum(0.5 * np.sum(np.square(np.asarray(p[v]))) for v in p))
+
+    def draw_momentum(self, rng):
+        """hmc.py:82-87."""
+        return {v: rng.normal(0, 1, size=np.asarray(self.start[v]).shape) for v in self.start}
+
+    def accept(self, current_q, proposal_q, current_p, proposal_p, **args):
+        """hmc.py:67-71 -- ``min(1, exp(E_cur - E_new))`` with the Python builtin ``min`` (NaN -> 1)."""
+        e_new = self.model.negative_log_posterior(proposal_q, **args) + self.potential_energy(proposal_p)
+        e_cur = self.model.negative_log_posterior(current_q, **args) + self.potential_energy(current_p)
+        return min(1, np.exp(e_cur - e_new))
+
     def step(self, state, momentum, rng, **args):
         """hmc.py:39-64 -> (q, p, positions, momentums, acceptprob); ``momentum`` is ignored, as in
         the reference."""

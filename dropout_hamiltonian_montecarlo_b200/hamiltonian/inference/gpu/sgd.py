@@ -14,6 +14,13 @@ class sgd(_ChainSampler):
     def __init__(self, model, start_p, step_size=0.1, **kw):
         super().__init__(model, start_p, step_size=step_size, verbose=kw.pop("verbose", False), **kw)
 
+    def iterate_minibatches(self, X, y, batchsize):
+        """sgd.py:19-23 -- sequential windows, remainder dropped."""
+        assert X.shape[0] == y.shape[0]
+        for start_idx in range(0, X.shape[0] - batchsize + 1, batchsize):
+            excerpt = slice(start_idx, start_idx + batchsize)
+            yield X[excerpt], y[excerpt]
+
     def fit(self, epochs=1, batch_size=1, gamma=0.9, **args):
         """sgd.py:25-45 -> (par, loss_val)."""
         verbose = args.pop("verbose", None)

@@ -30,3 +30,8 @@ class sgld(sgmcmc):
         q = self.model.unflatten(s.get(0), shapes, squeeze, like)
         p = self.model.unflatten(s.get(1), shapes, squeeze, like)
         return q, p
+
+    def draw_momentum(self, rng, epsilon):
+        """sgld.py:41-46 -- ``N(0, std = 2 eps)`` per variable: 2 eps is passed as the standard deviation."""
+        import numpy as np
+        return {v: rng.normal(0, 2.0 * epsilon, size=np.asarray(self.start[v]).shape) for v in self.start}

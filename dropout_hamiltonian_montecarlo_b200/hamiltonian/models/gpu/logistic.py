@@ -49,6 +49,10 @@ class logistic(softmax):
         k = np.asarray(k)
         return float(k[0]) if k.size == 1 else k
 
+    def sigmoid(self, y_linear):
+        """logistic.py:53-55 (host arrays)."""
+        return 1.0 / (1.0 + np.exp(-np.asarray(y_linear)))
+
     # ---- prediction (logistic.py:42-49,75-87) -----------------------------------------------------
     def _two_class(self, par):
         w = np.asarray(par["weights"].detach().cpu() if isinstance(par["weights"], torch.Tensor) else par["weights"],

@@ -110,6 +110,24 @@ class softmax(_base.ChainModel):
     def handle_for(self, **args):
         return self.bind(args["X_train"], args["y_train"])
 
+    # ---- small host-side helpers of the reference class (not on the hot path; kept for drop-in use) -------
+    def softmax(self, y_linear):
+        """softmax.py:32-36 -- row softmax with max subtraction (host arrays)."""
+        y_linear = np.asarray(y_linear)
+        e = np.exp(y_linear - np.max(y_linear, axis=1).reshape((-1, 1)))
+        return e / np.sum(e, axis=1).reshape((-1, 1))
+
+    def logsumexp(self, log_prob, axis):
+        """models/gpu/softmax.py:17-21."""
+        log_prob = np.asarray(log_prob)
+        m = np.max(log_prob, axis=axis, keepdims=True)
+        return np.squeeze(m, axis=axis) + np.log(np.sum(np.exp(log_prob - m), axis=axis))
+
+    def cross_entropy(self, y_linear, y):
+        """softmax.py:17-20 -- per-row ``sum_k y_k (z_k - logsumexp(z))``."""
+        y_linear, y = np.asarray(y_linear), np.asarray(y)
+        return np.sum(y * (y_linear - self.logsumexp(y_linear, 1)[:, None]), axis=1)
+
     # ---- model protocol --------------------------------------------------------------------------
     def grad(self, par, **args):
         """softmax.py:45-61 -- gradient of the potential, summed over rows, + alpha*theta."""

@@ -53,3 +53,33 @@ def test_sample_sink_roundtrip_cpu(tmp_path):
     one.append(flat[:4, :1])
     f1 = one.close()
     assert np.load(f1["bias"]).shape == (4, 2)
+
+
+def test_reference_helper_methods_cpu():
+    """The small host-side helpers of the reference classes (softmax.softmax / cross_entropy, logistic.sigmoid,
+    hmc.potential_energy / draw_momentum, sgd.iterate_minibatches, sgld.draw_momentum) need no device."""
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.hmc import hmc
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sgd import sgd
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sgld import sgld
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.logistic import logistic
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.softmax import softmax
+    from oracle import hamiltonian_oracle as O
+    rs = np.random.RandomState(0)
+    z = rs.normal(size=(7, 4))
+    y = O.one_hot(rs.randint(0, 4, 7), 4)
+    m = softmax({"alpha": 0.1})
+    np.testing.assert_allclose(m.softmax(z), O.softmax_probs(z), rtol=1e-12)
+    np.testing.assert_allclose(m.cross_entropy(z, y).sum(), np.sum(y * (z - O._logsumexp_rows(z)[:, None])), rtol=1e-12)
+    np.testing.assert_allclose(logistic({"alpha": 0.1}).sigmoid(z), 1 / (1 + np.exp(-z)), rtol=1e-12)
+    start = {"weights": np.zeros((3, 2)), "bias": np.zeros(2)}
+    h = hmc(m, start, verbose=False)
+    p = h.draw_momentum(np.random.RandomState(1))
+    r = np.random.RandomState(1)
+    np.testing.assert_array_equal(p["weights"], r.normal(0, 1, (3, 2)))
+    np.testing.assert_array_equal(p["bias"], r.normal(0, 1, 2))
+    np.testing.assert_allclose(h.potential_energy(p), O.kinetic_energy(p), rtol=1e-12)
+    X, yy = rs.rand(10, 3), rs.rand(10)
+    wins = [xb.shape[0] for xb, _ in sgd(m, start).iterate_minibatches(X, yy, 4)]
+    assert wins == [4, 4]  # remainder of 2 rows dropped
+    eta = sgld(m, start, step_size=0.01, verbose=False).draw_momentum(np.random.RandomState(2), 0.01)
+    np.testing.assert_array_equal(eta["weights"], np.random.RandomState(2).normal(0, 0.02, (3, 2)))

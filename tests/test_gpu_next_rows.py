@@ -161,3 +161,18 @@ def test_dual_averaging_wired_into_burnin():
         np.testing.assert_allclose([noisy, avg], [e_noisy, e_avg], rtol=1e-12)
     np.testing.assert_allclose(s.last_run["step_size"], trace[-1][2], rtol=1e-12)
     assert len({round(t[0], 6) for t in trace}) > 1  # the acceptance really responded to the step size
+
+
+def test_hmc_accept_building_block():
+    """hmc.accept (hmc.py:67-71) composed from the device NLP and the host kinetic energy == the oracle's."""
+    rs = np.random.RandomState(4)
+    n, d, K = 200, 12, 4
+    X = rs.rand(n, d)
+    Y = O.one_hot(rs.randint(0, K, n), K)
+    q1 = {"weights": rs.normal(0, .1, (d, K)), "bias": rs.normal(0, .1, K)}
+    q2 = {"weights": q1["weights"] + rs.normal(0, .01, (d, K)), "bias": q1["bias"] + rs.normal(0, .01, K)}
+    s = hmc(softmax({"alpha": 0.1}, precision="fp32"), q1, path_length=1e-2, step_size=1e-3, verbose=False)
+    p1, p2 = s.draw_momentum(np.random.RandomState(1)), s.draw_momentum(np.random.RandomState(2))
+    a = s.accept(q1, q2, p1, p2, X_train=X, y_train=Y)
+    ref = O.accept_probability(O.SoftmaxOracle({"alpha": 0.1}), q1, q2, p1, p2, X_train=X, y_train=Y)
+    close(a, ref, 1e-4, 1e-6)
