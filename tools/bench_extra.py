@@ -19,7 +19,7 @@ from dropout_hamiltonian_montecarlo_b200._lib import KIND, PREC
 from dropout_hamiltonian_montecarlo_b200.runtime import MlpHandle, SamplerHandle, SoftmaxHandle, default_context
 
 ap = argparse.ArgumentParser()
-ap.add_argument("what", choices=["sgld", "mlp", "update", "rows", "stream"])
+ap.add_argument("what", choices=["sgld", "sghmc", "mlp", "update", "rows", "stream"])
 ap.add_argument("--rows", type=int, default=1000000)
 ap.add_argument("--features", type=int, default=2048)
 ap.add_argument("--classes", type=int, default=38)
@@ -116,6 +116,31 @@ elif a.what == "sgld":
                       "grad_evals_per_s": out["n_grad_evals"] / dt, "us_per_minibatch_step": 1e6 * dt / (a.epochs * nb),
                       "launches_per_step": (ctx.launches - l0) / (a.epochs * nb),
                       "algorithmic_tflops": out["n_grad_evals"] * 4.0 * B * D * K / dt / 1e12}))
+elif a.what == "sghmc":
+    # BASELINE config 3, second half: SGHMC softmax on minibatches of 500 (sghmc.py:19-39 per minibatch: momentum draw,
+    # L-1 friction+noise leapfrog iterations on the window, Metropolis test), shared path lengths, E[L] = 10
+    C = a.chains or 128
+    h = SoftmaxHandle(ctx, N, D, K, 0.01)
+    h.bind(X, y, 1 | (1 << PREC[a.precision]))
+    s = SamplerHandle(ctx, h, KIND["sghmc"], C, seed=1, precision=PREC[a.precision], shared_path=True, sghmc_descent=True)
+    s.set_q(np.zeros((C, h.P), np.float32))
+    eps, path = 1e-5, 1e-4
+    nb = N // B
+    for j in range(8):
+        s.hmc_run(1, eps, path, row0=j * B, nrows=B, step0=j, keep_samples=False, keep_stats=False)
+    n_grad = 0
+    l0 = ctx.launches
+
+    def run():
+        global n_grad
+        for j in range(a.steps):
+            o = s.hmc_run(1, eps, path, row0=(j % nb) * B, nrows=B, step0=8 + j, keep_samples=False, keep_stats=False)
+            n_grad += o["n_grad_evals"]
+    dt, _ = timed(run)
+    print(json.dumps({"workload": "cfg3 SGHMC softmax 60000x784x10, minibatch 500, %d chains/GPU, E[L]=10, shared path lengths" % C,
+                      "precision": a.precision, "grad_evals_per_s": n_grad / dt, "us_per_sghmc_step": 1e6 * dt / a.steps,
+                      "us_per_grad_eval_all_chains": 1e6 * dt / (n_grad / C), "launches_per_step": (ctx.launches - l0) / a.steps,
+                      "algorithmic_tflops": n_grad * 4.0 * B * D * K / dt / 1e12}))
 elif a.what == "mlp":
     C = a.chains or 16
     n_mid = 512
