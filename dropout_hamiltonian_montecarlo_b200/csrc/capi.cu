@@ -333,8 +333,13 @@ struct SoftmaxModel : ModelBase {
     if (logistic || prec == BHMC_PREC_FP32) return BHMC_ERR_UNSUPPORTED;
     return tc_softmax_grad(ctx, d, fs.q, C, ld, alpha, row0, nrows, nullptr, stat, prec == BHMC_PREC_BF16X3, &fs);
   }
+  int grad_fused_stream(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat,
+                        uint32_t hint, const FusedStream& fst) override {
+    if (logistic || prec == BHMC_PREC_FP32) return BHMC_ERR_UNSUPPORTED;
+    return grad_softmax(q, C, ld, row0, nrows, prec, g, stat, hint, &fst);
+  }
   int grad_softmax(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat,
-                   uint32_t hint = 0) {
+                   uint32_t hint = 0, const FusedStream* fst = nullptr) {
     static int zc_env = -1;  // BHMC_ZCACHE=0 disables the X.W cache (A/B measurements)
     if (zc_env < 0) {
       const char* e = getenv("BHMC_ZCACHE");
@@ -343,8 +348,12 @@ struct SoftmaxModel : ModelBase {
     const int zmode = !zc_env ? ZMODE_NONE : (hint & GRAD_HINT_CHEAP_MOVE) ? ZMODE_USE : (hint & GRAD_HINT_KEEP) ? ZMODE_STORE : ZMODE_NONE;
     switch (prec) {
       case BHMC_PREC_FP32: return simt_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat);
-      case BHMC_PREC_BF16X3: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, true, nullptr, &zcache, zmode);
-      case BHMC_PREC_BF16: return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, false, nullptr, &zcache, zmode);
+      case BHMC_PREC_BF16X3:
+        return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, true, nullptr, &zcache, zmode, fst,
+                               (hint & GRAD_HINT_PREPARED) != 0);
+      case BHMC_PREC_BF16:
+        return tc_softmax_grad(ctx, d, q, C, ld, alpha, row0, nrows, g, stat, false, nullptr, &zcache, zmode, fst,
+                               (hint & GRAD_HINT_PREPARED) != 0);
     }
     set_error("unknown precision %d", prec);
     return BHMC_ERR_ARG;
@@ -656,6 +665,13 @@ struct bhmc_sampler {
   bhmc_grad_hook hook = nullptr;
   void* hook_user = nullptr;
   // gradient (or log-lik only when g == nullptr) of the first `rows` working rows, then the optional hook
+  // evaluation whose reduce launch also runs the streaming schedule's next update; BHMC_ERR_UNSUPPORTED = not fused
+  int eval_fused_stream(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat, uint32_t hint,
+                        const FusedStream& fst) {
+    if (hook) return BHMC_ERR_UNSUPPORTED;  // the row-shard all-reduce must see g before any update uses it
+    ctx->cur_units = rows;
+    return model->grad_fused_stream(q, rows, ld, row0, nrows, cfg.precision, g, stat, hint, fst);
+  }
   int eval(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat, uint32_t hint = 0) {
     ctx->cur_units = rows;
     BHMC_TRY(model->grad(q, rows, ld, row0, nrows, cfg.precision, g, stat, hint));
@@ -964,6 +980,14 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   bool cheap[BHMC_MAX_VARS];
   for (int v = 0; v < nsw; ++v) cheap[v] = mb->cheap_slice(cfg.sweep_off[v], cfg.sweep_len[v]);
   bool kept = false;  // the previous launch kept what a cheap move can reuse, for every active row
+  static int fuse_env = -1;  // BHMC_FUSED_STREAM=0: separate reduce / update / prep launches (A/B measurements)
+  if (fuse_env < 0) {
+    const char* e = getenv("BHMC_FUSED_STREAM");
+    fuse_env = e ? atoi(e) : 1;
+  }
+  bool try_fuse = fuse_env != 0;
+  bool update_done = false;  // this phase's pre-event update already ran inside the previous launch's reduce
+  bool prepared = false;     // ... and so did the operand preparation of this phase's launch
 
   run->n_grad_launched = 0;
   static int prof_host = -1;
@@ -978,12 +1002,13 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
     const int rows = rows_el[j];
     const uint32_t* cj = code1_d + j * C;
     const int32_t* sj = step1_d + j * C;
-    if (j > 0) {
+    if (j > 0 && !update_done) {
       u.rows = rows;
       u.code = cj;
       u.step = sj;
       BHMC_TRY(launch_stream_update(ctx, u));
     }
+    update_done = false;
     if (ev_finish[j]) {
       BHMC_TRY(launch_stream_kinetic(ctx, s->p_new, ld, P, rows, cj, kin1));
       if (need_extra)
@@ -1075,7 +1100,34 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
       kept = cheap[0];
       if (kept) hint |= GRAD_HINT_KEEP;
     }
-    BHMC_TRY(s->eval(s->q_new, rows_grad[j], run->row0, nrows, s->g, stat, hint));
+    if (prepared && !ev_begin[j]) hint |= GRAD_HINT_PREPARED;
+    prepared = false;
+    bool fused = false;
+    if (try_fuse) {
+      // the next phase's pre-event update runs on exactly the rows of this launch (rows_el[j+1] == rows_grad[j])
+      FusedStream fst{};
+      fst.u = u;
+      fst.u.rows = rows_grad[j];
+      fst.u.code = code1_d + (j + 1) * C;
+      fst.u.step = step1_d + (j + 1) * C;
+      // operand preparation of launch j+1: only if it is a full forward pass (not a cheap move served by the cache)
+      // and no begin re-seats rows in between; the lo operand copy sits behind the hi copy of ALL rows of a launch,
+      // so the two launches must carry the same number of rows
+      const int vn = (int)(j % nsw);
+      const bool next_cheap = j + 1 < J && kept && cheap[vn] && !ev_begin[j + 1];
+      fst.prep_next = j + 1 < J && !next_cheap && !ev_begin[j + 1] && rows_grad[j + 1] == rows_grad[j];
+      const int rc = s->eval_fused_stream(s->q_new, rows_grad[j], run->row0, nrows, s->g, stat, hint, fst);
+      if (rc == BHMC_OK) {
+        fused = true;
+        update_done = true;
+        prepared = fst.prep_next;
+      } else if (rc != BHMC_ERR_UNSUPPORTED) {
+        return rc;
+      } else {
+        try_fuse = false;
+      }
+    }
+    if (!fused) BHMC_TRY(s->eval(s->q_new, rows_grad[j], run->row0, nrows, s->g, stat, hint));
     run->n_grad_launched += rows_grad[j];
   }
   run->n_phases = (int32_t)J;

@@ -113,7 +113,9 @@ struct FusedStep {
 enum : uint32_t {
   GRAD_HINT_CHEAP_MOVE = 1u,  // since the previous evaluation of these rows only a cheap_slice() moved
   GRAD_HINT_KEEP = 2u,        // the NEXT evaluation of these rows will follow a cheap move: keep what it can reuse
+  GRAD_HINT_PREPARED = 4u,    // the previous fused evaluation already prepared this evaluation's operands from q
 };
+struct FusedStream;
 struct ModelBase {
   bhmc_ctx* ctx = nullptr;
   int64_t P = 0;
@@ -135,6 +137,11 @@ struct ModelBase {
   // gradient at fs.q followed by the sampler's parameter update in the same launch sequence (no g materialised);
   // BHMC_ERR_UNSUPPORTED = caller falls back to grad() + the separate update kernel
   virtual int grad_fused_step(int, int64_t, int64_t, int64_t, int, double*, const FusedStep&) { return BHMC_ERR_UNSUPPORTED; }
+  // gradient (g IS written) + the streaming schedule's next update in the reduce launch; same fallback convention
+  virtual int grad_fused_stream(const float*, int, int64_t, int64_t, int64_t, int, float*, double*, uint32_t,
+                                const FusedStream&) {
+    return BHMC_ERR_UNSUPPORTED;
+  }
   // sgd.fit_dropout: gradient on rows [row0, row0+nrows) multiplied elementwise by a Bernoulli(keep) mask
   // (mask != nullptr: injected [nrows, D] keep flags; else Philox keyed by (seed, stream))
   virtual int grad_input_dropout(const float*, int, int64_t, int64_t, int64_t, int, float*, double*, const uint8_t*,
@@ -208,6 +215,13 @@ struct StreamUpdateArgs {
   double* extra_cur;
 };
 int launch_stream_update(bhmc_ctx* ctx, const StreamUpdateArgs& a);
+// Streaming schedule, fused tail of a gradient evaluation: the split-K reduce also executes the NEXT phase's pre-event
+// update (u: its op codes / rows) and, when the following launch is a full forward pass of unchanged rows, writes the
+// bf16 operand copy of the updated weights (prep_next) -- 3 launches per phase instead of 5.
+struct FusedStream {
+  StreamUpdateArgs u;
+  bool prep_next;
+};
 int launch_stream_kinetic(bhmc_ctx* ctx, const float* p, int64_t ld, int64_t P, int rows, const uint32_t* code,
                           double* kin);
 
@@ -349,7 +363,7 @@ struct ZCache {
 enum { ZMODE_NONE = 0, ZMODE_STORE = 1, ZMODE_USE = 2 };  // USE falls back to a full pass when the cache does not fit
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
                     int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs = nullptr,
-                    ZCache* zc = nullptr, int zmode = ZMODE_NONE);
+                    ZCache* zc = nullptr, int zmode = ZMODE_NONE, const FusedStream* fst = nullptr, bool prepared = false);
 
 // ---- mlp.cu -----------------------------------------------------------------------------------
 ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int n_out, float alpha, float ratio,

@@ -36,6 +36,7 @@
 
 #include "internal.cuh"
 #include "philox.cuh"
+#include "stream_ops.cuh"
 
 namespace bhmc {
 
@@ -1085,6 +1086,56 @@ k_tc_reduce_step(PartRegions r, int D, int K, int KP, int64_t P,
   }
 }
 
+// k_tc_reduce + the streaming schedule's next pre-event update (k_stream_update) + (optionally) k_tc_prep of the next
+// evaluation, one launch.  One thread owns four consecutive parameters of a row; g IS written (the Metropolis / begin
+// kernels of event phases and g_start need it).
+__global__ void __launch_bounds__(256)
+k_tc_reduce_stream(PartRegions r, int D, int K, int KP, int64_t P, int64_t ld, float alpha, float* __restrict__ g,
+                   StreamUpdateArgs u, int prep_next, int64_t Dp, __nv_bfloat16* __restrict__ wt_hi,
+                   __nv_bfloat16* __restrict__ wt_lo, double* __restrict__ loglik) {
+  const int c = blockIdx.y;
+  const uint32_t op = u.code[c];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    stream_row_scalars(u, c, op);          // latches stat (= loglik of this evaluation) where the op says so ...
+    if (prep_next) loglik[c] = 0.0;        // ... then clears it for the next forward pass (k_tc_prep's job)
+  }
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= ld) return;
+  const int64_t o = (int64_t)c * ld + i;
+  const float4 q4 = *reinterpret_cast<const float4*>(u.q + o);
+  float qe[4] = {q4.x, q4.y, q4.z, q4.w}, ge[4];
+  int dd[4], kk[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t idx = i + e;
+    dd[e] = (int)(idx / K);
+    kk[e] = (int)(idx - (int64_t)dd[e] * K);
+    ge[e] = idx < P ? sum_partials(r, dd[e], (int64_t)c * KP + kk[e]) + alpha * qe[e] : 0.f;
+  }
+  *reinterpret_cast<float4*>(g + o) = make_float4(ge[0], ge[1], ge[2], ge[3]);
+  if (op & OP_LATCH) *reinterpret_cast<float4*>(u.g_start + o) = make_float4(ge[0], ge[1], ge[2], ge[3]);
+  bool moved = false;
+  if (op & (OP_POST | OP_PRE)) {
+    const float4 p4 = *reinterpret_cast<const float4*>(u.p + o);
+    float pe[4] = {p4.x, p4.y, p4.z, p4.w};
+    moved = stream_apply4(u, op, i, pe, ge, qe);
+    *reinterpret_cast<float4*>(u.p + o) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+    if (moved) *reinterpret_cast<float4*>(u.q + o) = make_float4(qe[0], qe[1], qe[2], qe[3]);
+  }
+  if (prep_next) {  // bf16 operand copy of the (possibly updated) weights for the next forward pass
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (i + e < P && dd[e] < D) {
+        __nv_bfloat16 hb, lb;
+        split_bf16(qe[e], hb, lb);
+        const int64_t w = ((int64_t)c * KP + kk[e]) * Dp + dd[e];
+        wt_hi[w] = hb;
+        if (wt_lo) wt_lo[w] = lb;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1394,7 +1445,8 @@ static int launch_fwd_kp(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorM
 
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
                     int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs, ZCache* zc,
-                    int zmode) {
+                    int zmode, const FusedStream* fst, bool prepared) {
+  BHMC_CHECK_ARG(!fst || (g && !fs && q == fst->u.q), "fused stream update: needs g and the working state the update moves");
   BHMC_CHECK_ARG(!fs || (q == fs->q && loglik), "fused step: the gradient must be evaluated at the state it updates");
   BHMC_CHECK_ARG(d.tc_ready, "tensor-core operands were not prepared at bind time (precision_mask)");
   BHMC_CHECK_ARG(!split3 || d.has_lo, "bf16x3 needs the lo operand copies (precision_mask bit 1 at bind time)");
@@ -1439,7 +1491,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const bool use_z = zmode == ZMODE_USE && zc->valid && ctx->zcache_owner == zc && zc->row0 == row0 && zc->nrows == nrows && zc->KP == KP &&
                      C <= zc->C && zc->ld == dm_ld && zc->slab == dm_slab;
   if (zmode == ZMODE_USE && !use_z) zmode = ZMODE_NONE;
-  if (!use_z && !(fs && fs->wt_ready)) {
+  if (!use_z && !(fs && fs->wt_ready) && !prepared) {
     GroupTimer t(ctx, KG_PREP);
     dim3 grid((unsigned)ceil_div(d.Dp, 128), C);
     k_tc_prep<<<grid, 128, 0, ctx->stream>>>(q, ld, D, K, KP, d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
@@ -1774,6 +1826,10 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
       else
         k_tc_reduce_step<BHMC_KIND_SGD><<<grid, 256, 0, ctx->stream>>>(pr, D, K, KP, P, ld, alpha, *fs, d.Dp, wt_hi,
                                                                        split3 ? wt_lo : nullptr, loglik);
+    } else if (fst) {
+      dim3 grid((unsigned)ceil_div(ceil_div(ld, 4), 256), C);
+      k_tc_reduce_stream<<<grid, 256, 0, ctx->stream>>>(pr, D, K, KP, P, ld, alpha, g, fst->u, fst->prep_next ? 1 : 0, d.Dp, wt_hi,
+                                                       split3 ? wt_lo : nullptr, loglik);
     } else {
       dim3 grid((unsigned)ceil_div(ld, 256), C);
       k_tc_reduce<<<grid, 256, 0, ctx->stream>>>(pr, K, KP, P, q, g, ld, alpha);

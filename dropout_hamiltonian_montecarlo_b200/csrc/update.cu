@@ -10,6 +10,7 @@
 // control flow (activity mask, accept decision) is block-uniform.
 #include "internal.cuh"
 #include "philox.cuh"
+#include "stream_ops.cuh"
 
 namespace bhmc {
 
@@ -155,22 +156,7 @@ int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a) {
 __global__ void __launch_bounds__(TPB) k_stream_update(StreamUpdateArgs a) {
   const int r = blockIdx.y;
   const uint32_t op = a.code[r];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    a.kin1[r] = 0.0;  // consumed by the previous phase's accept; re-accumulated by this phase's kinetic kernel
-    if (op & OP_LATCH) {
-      a.stat_cur[r] = a.stat[r];
-      a.stat_new[r] = a.stat[r];
-      a.kin0[(int64_t)((a.step[r] + 1) & 1) * a.C_total + r] = 0.0;  // the NEXT step's start-of-step buffer
-    }
-    if (op & OP_LATCH_CACHED) {
-      const double s0 = a.stat_next[r];
-      a.stat_cur[r] = s0;
-      a.stat_new[r] = s0;
-      if (a.extra_next) a.extra_cur[r] = a.extra_next[r];
-      a.kin0[(int64_t)((a.step[r] + 1) & 1) * a.C_total + r] = 0.0;
-    }
-    if (op & OP_POST) a.stat_new[r] = a.stat[r];
-  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) stream_row_scalars(a, r, op);
   const int64_t i = ((int64_t)blockIdx.x * TPB + threadIdx.x) * 4;
   if (i >= a.P) return;
   if (op & OP_LATCH) st4(a.g_start + (int64_t)r * a.ld + i, ld4(a.g + (int64_t)r * a.ld + i));
@@ -186,15 +172,7 @@ __global__ void __launch_bounds__(TPB) k_stream_update(StreamUpdateArgs a) {
   float4 g4 = ld4(a.g + o);
   float4 q4 = hit_pre ? ld4(a.q + o) : make_float4(0, 0, 0, 0);
   float pe[4] = {p4.x, p4.y, p4.z, p4.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, qe[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int64_t idx = i + e;
-    if (idx >= post_off && idx < post_off + post_len) pe[e] = 1.0f * pe[e] - a.a_post * ge[e];
-    if (idx >= pre_off && idx < pre_off + pre_len) {
-      pe[e] = pe[e] - a.a_pre * ge[e];
-      qe[e] = qe[e] + a.eps * pe[e];
-    }
-  }
+  stream_apply4(a, op, i, pe, ge, qe);
   st4(a.p + o, make_float4(pe[0], pe[1], pe[2], pe[3]));
   if (hit_pre) st4(a.q + o, make_float4(qe[0], qe[1], qe[2], qe[3]));
 }
