@@ -49,18 +49,35 @@ WORKLOADS = {
 }
 
 
+DATA_KIND = "dense"  # set from --data: "dense" = X ~ U[0,1) fp32; "pixels" = 8-bit pixels / 255 (what MNIST holds)
+
+
+def _quantize(X):
+    """U[0,1) -> k/255 with k uniform in 0..255: the value grid of MNIST images scaled as the reference's scripts do."""
+    import torch
+    return torch.div(torch.floor(X * 256.0).clamp_(max=255.0), torch.tensor(255.0, device=X.device))  # IEEE division
+
+
+def data_desc():
+    return "synthetic" if DATA_KIND == "dense" else "synthetic (8-bit pixels / 255, MNIST's value grid)"
+
+
 def synth(N, D, K, seed, device=None):
-    """MNIST-shaped synthetic data: X ~ U[0,1), labels = argmax(X W* + Gumbel)."""
+    """MNIST-shaped synthetic data: X ~ U[0,1) (or 8-bit pixels / 255), labels = argmax(X W* + Gumbel)."""
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)
     Wt = torch.randn(D, K, generator=g) * 0.1
     if device is not None:
         gd = torch.Generator(device=device).manual_seed(seed)
         X = torch.rand(N, D, generator=gd, device=device, dtype=torch.float32)
+        if DATA_KIND == "pixels":
+            X = _quantize(X)
         u = torch.rand(N, K, generator=gd, device=device).clamp_(1e-12, 1 - 1e-7)
         y = (X @ Wt.to(device) - torch.log(-torch.log(u))).argmax(1).to(torch.int32)
         return X, y
     X = torch.rand(N, D, generator=g, dtype=torch.float32)
+    if DATA_KIND == "pixels":
+        X = _quantize(X)
     u = torch.rand(N, K, generator=g).clamp_(1e-12, 1 - 1e-7)
     y = (X @ Wt - torch.log(-torch.log(u))).argmax(1).to(torch.int32)
     return X, y
@@ -243,7 +260,7 @@ def run_reference(args, wl):
     line = {"impl": "reference", "metric": "grad evals/sec (chains x leapfrog) on MNIST-shape softmax BNN",
             "value": val, "unit": "grad-evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": data_desc(),
             "config": {"workload": wl["desc"], "sample": "1 chain, L=%d per step (%d grad evals/step)" % (L, 1 + (L - 1) * 2)},
             "cpu_baseline": {"value": val, "unit": "grad-evals/s", "cores": int(threads), "kind": "port",
                              "sample": "%d timed HMC steps of 1 chain, L=%d, fp64 NumPy oracle port "
@@ -417,21 +434,24 @@ def run_ours(args, wl):
         flops_launch = flops_eval * u_dom / max(1, n_dom)   # chains carried by the bracketed launches
         achieved = flops_launch / avg / 1e12 if avg > 0 else 0.0
         traffic, traffic_src = ncu_traffic(dom, prec, wl, u_dom / max(1, n_dom))
-        mma_mult = 3.0 if prec == "bf16x3" else 1.0
+        x_exact, x_scale = h.operand_info()
+        mma_mult = (2.0 if x_exact else 3.0) if prec == "bf16x3" else 1.0
         cpu = None if args.no_cpu_baseline else cpu_reference_rate(wl)
         line = {
             "metric": "grad evals/sec (chains x leapfrog) on MNIST-shape softmax BNN",
             "value": value, "unit": "grad-evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (bf16 hi/lo split x3 on tcgen05, fp32 accumulate)" if prec == "bf16x3" else prec,
-            "data": "synthetic",
+            "data": data_desc(),
             "config": {"workload": wl["desc"], "N": N, "D": D, "K": K, "chains_per_gpu": C, "step_size": wl["eps"],
                        "path_length": wl["path"], "precision": prec, "path_length_mode": args.path_mode,
                        "schedule": ("streaming (asynchronous chains, %d gradient launches)" % o["n_phases"]) if o["n_phases"]
                        else "lockstep",
                        "sweep": "reference (Gauss-Seidel, 2 gradients per leapfrog iteration)",
                        "l2": "inputs larger than L2 (X 94-376 MB + (P-Y)^T 77-245 MB per evaluation)",
-                       "grad_evals_launched_incl_masked": n_launched},
+                       "grad_evals_launched_incl_masked": n_launched,
+                       "x_operand": ("exact in bf16 after scaling by %g: 2 MMAs per product" % x_scale) if x_exact
+                       else "fp32 values: hi/lo split, 3 MMAs per product"},
             "roofline": {"bound": "tensor", "kernel": "k_tc_gemm<%s>" % dom, "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": src, "algorithmic_flops_per_launch": flops_launch,
@@ -464,6 +484,8 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--path-mode", default="per_chain", choices=["per_chain", "shared"])
     ap.add_argument("--schedule", default="auto", choices=["auto", "lockstep", "streaming"])
+    ap.add_argument("--data", default="dense", choices=["dense", "pixels"],
+                    help="dense: X ~ U[0,1) fp32; pixels: 8-bit pixels / 255 (MNIST's value grid; exact-operand path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--ess-steps", type=int, default=40)
@@ -474,6 +496,8 @@ def main():
     ap.add_argument("--ess-L", type=float, default=30.0, help="path_length / step_size of the ESS run (E[L])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global DATA_KIND
+    DATA_KIND = args.data
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)

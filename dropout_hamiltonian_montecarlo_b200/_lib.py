@@ -70,6 +70,7 @@ _PROTOS = {
     "bhmc_logistic_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.POINTER(C.c_void_p)]),
     "bhmc_softmax_bind_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "bhmc_softmax_bind_data_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "bhmc_softmax_operand_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "bhmc_mvn_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_void_p)]),
     "bhmc_mlp_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                   C.c_uint64, C.c_int64, C.POINTER(C.c_void_p)]),

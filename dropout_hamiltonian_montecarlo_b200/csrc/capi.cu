@@ -146,7 +146,7 @@ int bhmc_ctx_destroy(bhmc_ctx* ctx) {
   if (!ctx) return BHMC_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < 8; ++i) cudaFree(ctx->scratch[i]);
+  for (int i = 0; i < 16; ++i) cudaFree(ctx->scratch[i]);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
   for (int g = 0; g < KG_COUNT; ++g)
@@ -323,7 +323,8 @@ struct SoftmaxModel : ModelBase {
     db.K = d.K;
     db.X = Xb;
     db.labels = d.labels + row0;
-    if (prec != BHMC_PREC_FP32) BHMC_TRY(tc_softmax_bind(ctx, db, prec == BHMC_PREC_BF16X3));
+    // no exact-operand check on the masked rows (it would cost a host sync per minibatch; x / keep is not exact anyway)
+    if (prec != BHMC_PREC_FP32) BHMC_TRY(tc_softmax_bind(ctx, db, prec == BHMC_PREC_BF16X3, false));
     std::swap(d, db);  // evaluate on the masked view through the ordinary (logistic-aware) path
     const int rc = grad(q, C, ld, 0, nrows, prec, g, stat, 0);
     std::swap(d, db);
@@ -493,6 +494,15 @@ int bhmc_softmax_bind_data_host(bhmc_model* m, const float* X_host, const int32_
   s->d.X = s->X_owned;
   s->d.labels = s->y_owned;
   return bind_common(s, precision_mask);
+}
+
+int bhmc_softmax_operand_info(bhmc_model* m, int32_t* exact, float* x_scale) {
+  SoftmaxModel* s;
+  BHMC_TRY(softmax_of(m, &s));
+  BHMC_CHECK_ARG(s->d.tc_ready, "no tensor-core operands bound");
+  if (exact) *exact = s->d.x_exact ? 1 : 0;
+  if (x_scale) *x_scale = s->d.x_scale;
+  return BHMC_OK;
 }
 
 int bhmc_mvn_create(bhmc_ctx* ctx, int32_t dim, const double* mu_host, const double* cov_inv_host, double logdet,

@@ -64,8 +64,8 @@ struct bhmc_ctx {
   double units_acc[bhmc::KG_COUNT] = {0, 0, 0, 0};
   int64_t cur_units = 0;  // set by the callers of model->grad (rows of this launch)
   // grow-only device scratch
-  void* scratch[12] = {nullptr};
-  size_t scratch_bytes[12] = {0};
+  void* scratch[16] = {nullptr};
+  size_t scratch_bytes[16] = {0};
   // pinned staging for small per-step host->device uploads
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -344,6 +344,10 @@ struct SoftmaxData {
   int64_t Dt = 0;                   // D+1 rows (ones row feeds the bias gradient)
   bool has_lo = false;
   bool tc_ready = false;
+  // exact-operand detection at bind time (softmax_tc.cu:k_detect_exact): the bf16 operand copies hold x_scale * X; when
+  // that is exact for every element (x_exact) bf16x3 needs no lo copy of X and runs 2 MMAs per product instead of 3
+  float x_scale = 1.f;
+  bool x_exact = false;
 };
 
 int simt_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
@@ -351,7 +355,7 @@ int simt_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C
 int simt_softmax_predict(bhmc_ctx* ctx, int D, int K, const float* q, int C, int64_t ld, const float* X,
                          int64_t nrows, float* probs, int32_t* labels);
 
-int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo);
+int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo, bool detect_exact = true);
 void tc_softmax_release(SoftmaxData& d);
 // Z cache (X.W of the last full forward pass, scratch slot 8) and how an evaluation may use it
 struct ZCache {

@@ -72,7 +72,8 @@ struct TcParams {
                                   // fp32 registers (round-to-nearest adds) every sub_chunks chunks (backward only)
   int BN;                         // UMMA N (multiple of 16, <= 256)
   int stages;
-  int split3;                     // 1: hi/lo operands, 3 MMAs per product
+  int split3;                     // 1: hi/lo operands, 3 MMAs per product; 2: A is exact in bf16 (no lo copy is
+                                  // staged), 2 MMAs per product; 0: single pass
   int a_k0, a_m0;                 // coordinate offsets of A in its tensor map (contraction, row)
   int b_slab, b_slab_rows;        // same for B
   int hint_a, hint_b;             // L2 eviction priority of the operand streams (make_l2_policy)
@@ -294,7 +295,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_bytes = BM * BK * 2, b_bytes = p.BN * BK * 2;
-  const int stage_bytes = (p.split3 ? 2 : 1) * (a_bytes + b_bytes);
+  const int na = p.split3 == 1 ? 2 : 1, nb = p.split3 ? 2 : 1;  // matrices staged per operand
+  const int stage_bytes = na * a_bytes + nb * b_bytes;
   // work items are handed out per cluster (1 or 2 CTAs); a pair splits two adjacent M (or N) tiles
   const int csize = p.pair ? 2 : 1;
   const int rank = p.pair ? (int)cluster_ctarank() : 0;
@@ -340,7 +342,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       for (int w = wi0; w < num_work && p.debug != 9 && p.debug != 10; w += wi_step) {
         BHMC_DECODE_WORK(w)
         int k_begin = s * p.chunks_per_split, k_end = min(p.k_chunks, k_begin + p.chunks_per_split);
-        const int nmat = p.split3 ? 2 : 1;
         for (int k = k_begin; k < k_end; ++k) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           uint32_t full = smem_u32(&bar_full[stage]);
@@ -351,7 +352,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           }
           mbar_expect_tx(full, (uint32_t)stage_bytes);
           uint32_t sa = smem_base + stage * stage_bytes;  // [A_hi | A_lo | B_hi | B_lo]
-          uint32_t sb = sa + nmat * a_bytes;
+          uint32_t sb = sa + na * a_bytes;
           int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN;
           if (p.a_slab) {  // chunks never straddle a slab: a_k0 and a_slab are multiples of BK
             const int sl = ak / p.a_slab;
@@ -366,10 +367,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           if (p.pair == 2) {  // A tile shared by the pair: each CTA fetches 64 of its 128 rows for both
             uint32_t off = (uint32_t)rank * (BM / 2) * (BK * 2);
             tma_load_2d_mc_hint(sa + off, &tmA_hi, full, ak, am + rank * (BM / 2), 3, pol_a);
-            if (p.split3) tma_load_2d_mc_hint(sa + a_bytes + off, &tmA_lo, full, ak, am + rank * (BM / 2), 3, pol_a);
+            if (na == 2) tma_load_2d_mc_hint(sa + a_bytes + off, &tmA_lo, full, ak, am + rank * (BM / 2), 3, pol_a);
           } else {
             tma_load_2d_hint(sa, &tmA_hi, full, ak, am, pol_a);
-            if (p.split3) tma_load_2d_hint(sa + a_bytes, &tmA_lo, full, ak, am, pol_a);
+            if (na == 2) tma_load_2d_hint(sa + a_bytes, &tmA_lo, full, ak, am, pol_a);
           }
           if (p.pair == 1) {  // B tile shared by the pair: each CTA fetches BN/2 of its rows for both
             uint32_t off = (uint32_t)rank * (p.BN / 2) * (BK * 2);
@@ -420,7 +421,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t first = (k > kb) ? 1u : 0u;
           if (do_mma) {
-            if (p.split3) {
+            if (p.split3 == 1) {
               const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
               const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
 #pragma unroll
@@ -429,6 +430,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                 umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
                 umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
                 umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            } else if (p.split3 == 2) {  // A exact in bf16: a_lo == 0, its product is not issued
+              const uint64_t a_hi = make_smem_desc(sa);
+              const uint64_t b_hi = make_smem_desc(sa + a_bytes), b_lo = make_smem_desc(sa + a_bytes + b_bytes);
+#pragma unroll
+              for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+                umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+                umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
               }
             } else {
               const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
@@ -559,9 +569,9 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const bool leader = rank == 0;
-  const int nmat = p.split3 ? 2 : 1;
+  const int na = p.split3 == 1 ? 2 : 1, nb = p.split3 ? 2 : 1;
   const int a_bytes = BM * BK * 2, bh_bytes = (p.BN / 2) * BK * 2;  // this CTA's share of the B tile
-  const int stage_bytes = nmat * (a_bytes + bh_bytes);
+  const int stage_bytes = na * a_bytes + nb * bh_bytes;
   const int m_items = (p.m_tiles + 1) / 2;
   const int num_work = m_items * p.n_tiles;
   const int wi0 = blockIdx.x / 2, wi_step = gridDim.x / 2;
@@ -599,10 +609,10 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);  // same offset in the leader CTA
           if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
-          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + nmat * a_bytes;
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + na * a_bytes;
           const int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN + rank * (p.BN / 2);
           tma_load_2d_2sm(sa, &tmA_hi, full, ak, am);
-          if (p.split3) tma_load_2d_2sm(sa + a_bytes, &tmA_lo, full, ak, am);
+          if (na == 2) tma_load_2d_2sm(sa + a_bytes, &tmA_lo, full, ak, am);
           tma_load_2d_2sm(sb, &tmB_hi, full, bk, bn);
           if (p.split3) tma_load_2d_2sm(sb + bh_bytes, &tmB_lo, full, bk, bn);
           if (++stage == p.stages) stage = 0, phase ^= 1u;
@@ -627,7 +637,7 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t first = k > 0 ? 1u : 0u;
-          if (p.split3) {
+          if (p.split3 == 1) {
             const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
             const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + bh_bytes);
 #pragma unroll
@@ -636,6 +646,15 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
               umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
               umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
               umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          } else if (p.split3 == 2) {  // A exact in bf16
+            const uint64_t a_hi = make_smem_desc(sa);
+            const uint64_t b_hi = make_smem_desc(sa + a_bytes), b_lo = make_smem_desc(sa + a_bytes + bh_bytes);
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
             }
           } else {
             const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
@@ -911,12 +930,36 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
-// Xa[n, d] = split(X[n, d]) with zero padding d in [D, Dp)
+// Exact-operand check at bind time.  If scale*X is exactly representable in bf16 for every element (scale = 1: binary /
+// small-integer features; scale = 255: 8-bit pixels divided by 255, the reference's MNIST input), the lo copy of X is
+// identically zero and the lo(X).hi(W) MMA of the bf16x3 scheme adds nothing: the GEMMs then run on hi(scale*X) alone
+// (2 MMAs per product, a third less tensor work and operand traffic) and 1/scale is folded into W / the gradient.
+// flags[0] |= 1 if some x is not bf16-exact; flags[1] |= 1 if some x is not k/255 for an integer 0 <= k <= 255
+__global__ void k_detect_exact(const float* __restrict__ X, int64_t n, int* __restrict__ flags) {
+  int bad1 = 0, bad255 = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = X[i];
+    bad1 |= __bfloat162float(__float2bfloat16_rn(x)) != x;
+    const float k = rintf(x * 255.0f);
+    // the quotient as fp32 computes it, as fp64 computes it before the cast to fp32 (pixels / 255.0 in NumPy), or as
+    // a multiplication by the rounded reciprocal (what GPU array libraries turn a division by a scalar into)
+    bad255 |= !(k >= 0.f && k <= 255.f &&
+                (x == __fdiv_rn(k, 255.0f) || x == (float)((double)k / 255.0) || x == __fmul_rn(k, 1.0f / 255.0f)));
+  }
+  bad1 = __syncthreads_or(bad1);
+  bad255 = __syncthreads_or(bad255);
+  if (threadIdx.x == 0) {
+    if (bad1) atomicOr(flags, 1);
+    if (bad255) atomicOr(flags + 1, 1);
+  }
+}
+
+// Xa[n, d] = split(scale * X[n, d]) with zero padding d in [D, Dp)
 __global__ void k_split_rows(const float* __restrict__ X, int64_t N, int D, int64_t Dp, __nv_bfloat16* __restrict__ hi,
-                             __nv_bfloat16* __restrict__ lo) {
+                             __nv_bfloat16* __restrict__ lo, float scale) {
   int64_t n = blockIdx.y;
   for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < Dp; d += (int64_t)gridDim.x * blockDim.x) {
-    float v = d < D ? X[n * D + d] : 0.f;
+    float v = d < D ? scale * X[n * D + d] : 0.f;
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
     hi[n * Dp + d] = h;
@@ -924,10 +967,10 @@ __global__ void k_split_rows(const float* __restrict__ X, int64_t N, int D, int6
   }
 }
 
-// Xt slab s = n / S holds Xt[d, n % S] = split(X[n, d]) for d < D and Xt[D, n % S] = 1; everything else (rows
+// Xt slab s = n / S holds Xt[d, n % S] = split(scale * X[n, d]) for d < D and Xt[D, n % S] = scale; everything else (rows
 // D+1..Dt_pad-1, columns of rows n >= N) stays zero from the memset at bind time
 __global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D, int64_t S, int64_t ld, int64_t Dt_pad,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float scale) {
   __shared__ float tile[32][33];
   int64_t n0 = (int64_t)blockIdx.x * 32;
   int d0 = blockIdx.y * 32;
@@ -935,7 +978,7 @@ __global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D,
     int64_t n = n0 + i;
     int d = d0 + threadIdx.x;
     float v = 0.f;
-    if (n < N) v = d < D ? X[n * D + d] : (d == D ? 1.f : 0.f);
+    if (n < N) v = d < D ? scale * X[n * D + d] : (d == D ? scale : 0.f);
     tile[i][threadIdx.x] = v;
   }
   __syncthreads();
@@ -952,16 +995,18 @@ __global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D,
   }
 }
 
-// Wt[(c*KP + k), d] = split(q[c, d*K + k]) (zero for k >= K or d >= D); loglik[c] = 0
+// Wt[(c*KP + k), d] = split(wscale * q[c, d*K + k]) (zero for k >= K or d >= D); loglik[c] = 0
+// wscale = 1 / (scale of the bound X operand, SoftmaxData::x_scale)
 __global__ void k_tc_prep(const float* __restrict__ q, int64_t ld, int D, int K, int KP, int64_t Dp,
-                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, double* __restrict__ loglik) {
+                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, double* __restrict__ loglik,
+                          float wscale) {
   int c = blockIdx.y;
   if (blockIdx.x == 0 && threadIdx.x == 0 && loglik) loglik[c] = 0.0;
   int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= Dp) return;
   const float* src = q + (int64_t)c * ld + d * K;
   for (int k = 0; k < KP; ++k) {
-    float v = (k < K && d < D) ? src[k] : 0.f;
+    float v = (k < K && d < D) ? wscale * src[k] : 0.f;
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
     int64_t o = ((int64_t)c * KP + k) * Dp + d;
@@ -980,6 +1025,7 @@ struct PartRegions {
   int64_t rows0, rows1;   // rows per slab of each region
   int64_t split_row;      // first output row of region 1
   int64_t cols;
+  float scale;            // 1 / (scale of the bound X operand): multiplies the summed partials and the next W operand
 };
 __device__ __forceinline__ float sum_partials(const PartRegions& r, int64_t d, int64_t col) {
   const bool main = d < r.split_row;
@@ -997,7 +1043,7 @@ __device__ __forceinline__ float sum_partials(const PartRegions& r, int64_t d, i
     for (int j = 0; j < 8; ++j) v += t[j];
   }
   for (; s < ns; ++s) v += src[(int64_t)s * slab];
-  return v;
+  return v * r.scale;
 }
 
 __global__ void k_tc_reduce(PartRegions r, int K, int KP, int64_t P, const float* __restrict__ q, float* __restrict__ g,
@@ -1078,7 +1124,7 @@ k_tc_reduce_step(PartRegions r, int D, int K, int KP, int64_t P,
   for (int e = 0; e < 4; ++e) {
     if (i + e < P && dd[e] < D) {
       __nv_bfloat16 hb, lb;
-      split_bf16(qe[e], hb, lb);
+      split_bf16(r.scale * qe[e], hb, lb);
       const int64_t o = ((int64_t)c * KP + kk[e]) * Dp + dd[e];
       wt_hi[o] = hb;
       if (wt_lo) wt_lo[o] = lb;
@@ -1127,7 +1173,7 @@ k_tc_reduce_stream(PartRegions r, int D, int K, int KP, int64_t P, int64_t ld, f
     for (int e = 0; e < 4; ++e) {
       if (i + e < P && dd[e] < D) {
         __nv_bfloat16 hb, lb;
-        split_bf16(qe[e], hb, lb);
+        split_bf16(r.scale * qe[e], hb, lb);
         const int64_t w = ((int64_t)c * KP + kk[e]) * Dp + dd[e];
         wt_hi[w] = hb;
         if (wt_lo) wt_lo[w] = lb;
@@ -1241,7 +1287,7 @@ static int64_t slab_pad() {
   return v;
 }
 
-int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
+int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo, bool detect_exact) {
   const int kp = pick_kp(d.K);
   if (!kp) {
     set_error("tensor-core path supports at most 64 classes (got %d); use BHMC_PREC_FP32", d.K);
@@ -1270,6 +1316,29 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
   }
   want_lo = want_lo || d.Xa_lo != nullptr;
   d.has_lo = want_lo;
+  // exact-operand check (one pass over X and one host sync per bind; BHMC_X_EXACT=0 disables it for A/B measurements)
+  d.x_scale = 1.f;
+  d.x_exact = false;
+  static int exact_env = -1;
+  if (exact_env < 0) {
+    const char* e = getenv("BHMC_X_EXACT");
+    exact_env = e ? atoi(e) : 1;
+  }
+  if (detect_exact && exact_env) {
+    void* fl = nullptr;
+    BHMC_TRY(ctx->get_scratch(12, 2 * sizeof(int), &fl));
+    BHMC_CUDA_OK(cudaMemsetAsync(fl, 0, 2 * sizeof(int), ctx->stream));
+    const int64_t n = d.N * d.D;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(n, 256 * 8), (int64_t)ctx->sm_count * 16);
+    k_detect_exact<<<std::max(blocks, 1u), 256, 0, ctx->stream>>>(d.X, n, (int*)fl);
+    ctx->launches++;
+    int flags[2] = {1, 1};
+    BHMC_CUDA_OK(cudaMemcpyAsync(flags, fl, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (!flags[0]) d.x_exact = true;
+    else if (!flags[1]) d.x_exact = true, d.x_scale = 255.f;
+  }
+  if (d.x_exact) want_lo = false;  // the lo copies (if allocated) are neither written nor read
   {
     dim3 grid((unsigned)std::min<int64_t>(ceil_div(d.Dp, 256), 65535), (unsigned)1);
     // rows can exceed the 65535 limit of gridDim.y -> loop over row blocks
@@ -1277,7 +1346,7 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
       int64_t cnt = std::min<int64_t>(65535, d.N - n0);
       dim3 g(grid.x, (unsigned)cnt);
       k_split_rows<<<g, 256, 0, ctx->stream>>>(d.X + n0 * d.D, cnt, d.D, d.Dp, (__nv_bfloat16*)d.Xa_hi + n0 * d.Dp,
-                                               want_lo ? (__nv_bfloat16*)d.Xa_lo + n0 * d.Dp : nullptr);
+                                               want_lo ? (__nv_bfloat16*)d.Xa_lo + n0 * d.Dp : nullptr, d.x_scale);
       ctx->launches++;
     }
   }
@@ -1287,7 +1356,7 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo) {
     if (want_lo) BHMC_CUDA_OK(cudaMemsetAsync(d.Xt_lo, 0, t_bytes, ctx->stream));
     dim3 grid((unsigned)ceil_div(d.N, 32), (unsigned)ceil_div(d.Dt, 32));
     k_split_transpose<<<grid, dim3(32, 8), 0, ctx->stream>>>(d.X, d.N, d.D, d.slab, d.slab_ld, d.Dt_pad, (__nv_bfloat16*)d.Xt_hi,
-                                                             want_lo ? (__nv_bfloat16*)d.Xt_lo : nullptr);
+                                                             want_lo ? (__nv_bfloat16*)d.Xt_lo : nullptr, d.x_scale);
     ctx->launches++;
   }
   BHMC_CUDA_OK(cudaGetLastError());
@@ -1327,7 +1396,7 @@ static int epilogue_warps() {
 template <int MODE, int KP, int EW, bool EXACT>
 static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                           const CUtensorMap& b_lo, const TcParams& p) {
-  int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + p.BN * BK * 2);
+  int stage_bytes = (p.split3 == 1 ? 2 : 1) * BM * BK * 2 + (p.split3 ? 2 : 1) * p.BN * BK * 2;
   size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static size_t configured = 0;
   if (smem > configured) {
@@ -1360,7 +1429,7 @@ static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
 template <int KP, int EW, bool EXACT>
 static int launch_fwd2_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                           const CUtensorMap& b_lo, const TcParams& p) {
-  const int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + (p.BN / 2) * BK * 2);
+  const int stage_bytes = (p.split3 == 1 ? 2 : 1) * BM * BK * 2 + (p.split3 ? 2 : 1) * (p.BN / 2) * BK * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static size_t configured = 0;
   if (smem > configured) {
@@ -1474,8 +1543,11 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const int64_t dm_rows = (int64_t)n_tiles * BN;     // rows per slab (>= C*KP; the padding rows are never written
                                                      // and only feed accumulator columns nobody reads)
   const int64_t P = (int64_t)(D + 1) * K;
-  const int nmat = split3 ? 2 : 1;
-  const int stage_bytes = nmat * (BM * BK * 2 + BN * BK * 2);
+  // operand split: 0 = single pass, 1 = hi/lo of both operands (3 MMAs), 2 = X exact in bf16 (bind-time check): only
+  // the per-evaluation operand (W / P-Y) carries a lo copy, 2 MMAs
+  const int smode = split3 ? (d.x_exact ? 2 : 1) : 0;
+  const int nmat = split3 ? 2 : 1, na = smode == 1 ? 2 : 1;
+  const int stage_bytes = na * BM * BK * 2 + nmat * BN * BK * 2;
   int stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
   if (const char* e = getenv("BHMC_STAGES")) stages = std::max(1, std::min(stages, atoi(e)));
 
@@ -1494,7 +1566,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   if (!use_z && !(fs && fs->wt_ready) && !prepared) {
     GroupTimer t(ctx, KG_PREP);
     dim3 grid((unsigned)ceil_div(d.Dp, 128), C);
-    k_tc_prep<<<grid, 128, 0, ctx->stream>>>(q, ld, D, K, KP, d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik);
+    k_tc_prep<<<grid, 128, 0, ctx->stream>>>(q, ld, D, K, KP, d.Dp, wt_hi, split3 ? wt_lo : nullptr, loglik, 1.0f / d.x_scale);
     ctx->launches++;
   }
 
@@ -1522,13 +1594,10 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const uint32_t fwd_bbox = (uint32_t)(fwd_pair ? BN / 2 : BN);
   BHMC_TRY(make_map(&a_hi, d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
   BHMC_TRY(make_map(&b_hi, wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
-  if (split3) {
-    BHMC_TRY(make_map(&a_lo, d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
-    BHMC_TRY(make_map(&b_lo, wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
-  } else {
-    a_lo = a_hi;
-    b_lo = b_hi;
-  }
+  a_lo = a_hi;
+  b_lo = b_hi;
+  if (smode == 1) BHMC_TRY(make_map(&a_lo, d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  if (split3) BHMC_TRY(make_map(&b_lo, wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
   TcParams p{};
   p.m_tiles = (int)(Mfwd / BM);
   p.n_tiles = n_tiles;
@@ -1537,9 +1606,9 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.chunks_per_split = p.k_chunks;
   p.sub_chunks = p.k_chunks;  // forward: K = D is short (13 chunks at D=784), one accumulation chain
   p.BN = BN;
-  p.stages = fwd_pair == 3 ? std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / (nmat * (BM * BK * 2 + (BN / 2) * BK * 2)))))
+  p.stages = fwd_pair == 3 ? std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / (na * BM * BK * 2 + nmat * (BN / 2) * BK * 2))))
                            : stages;
-  p.split3 = split3 ? 1 : 0;
+  p.split3 = smode;
   p.a_k0 = 0;
   p.a_m0 = (int)row0;
   p.pair = fwd_pair;
@@ -1662,7 +1731,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     bwd2_env = e ? atoi(e) : 0;
   }
   // (measured at cfg2: faster from ~3 N tiles on; launches that carry few chains are better off with more row slabs)
-  const bool use_bwd2 = bwd2_env && pairing_enabled() && m_tiles_all >= 2 && k_chunks_b >= 64 && BN % 16 == 0 &&
+  const bool use_bwd2 = bwd2_env && smode != 2 && pairing_enabled() && m_tiles_all >= 2 && k_chunks_b >= 64 && BN % 16 == 0 &&
                         (n_tiles >= 3 || bwd2_env >= 2);
   const int m2 = use_bwd2 ? 2 * (m_tiles_all / 2) : 0;   // row tiles handled pairwise by k_tc_bwd2
   const int m_left = use_bwd2 ? m_tiles_all - m2 : 0;    // odd last tile: extra work items of the same launch
@@ -1683,7 +1752,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   b.k_chunks = k_chunks_b;
   b.sub_chunks = sub_env * (64 / BK);  // expressed in 64-element units
   b.BN = BN;
-  b.split3 = split3 ? 1 : 0;
+  b.split3 = smode;
   b.a_k0 = (int)(row0 - shift);
   b.b_slab = (int)dm_slab;
   b.b_slab_rows = (int)dm_rows;
@@ -1783,13 +1852,10 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
       const uint32_t abox = (uint32_t)(b1.pair ? BM / 2 : BM);
       BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, abox));
       BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
-      if (split3) {
-        BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, abox));
-        BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
-      } else {
-        a_lo = a_hi;
-        b_lo = b_hi;
-      }
+      a_lo = a_hi;
+      b_lo = b_hi;
+      if (smode == 1) BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, abox));
+      if (split3) BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
       BHMC_TRY((launch_gemm_ew<MODE_BWD, 1, 16, false>(ctx, a_hi, a_lo, b_hi, b_lo, b1)));
     }
     if (want_prof) {
@@ -1818,6 +1884,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     pr.rows1 = m2 ? BM : rows1;
     pr.split_row = m2 ? rows2 : ((int64_t)1 << 40);
     pr.cols = pcol;
+    pr.scale = 1.0f / d.x_scale;
     if (fs) {
       dim3 grid((unsigned)ceil_div(ceil_div(ld, 4), 256), C);
       if (fs->kind == BHMC_KIND_SGLD)

@@ -146,6 +146,12 @@ class SoftmaxHandle(ModelHandle):
         check(self.ctx.L.bhmc_softmax_bind_data_host(self.handle, C.c_void_p(X_host.data_ptr()),
                                                      C.c_void_p(labels_host.data_ptr()), precision_mask))
 
+    def operand_info(self):
+        """(exact, x_scale) found by the last bind: exact -> bf16x3 runs 2 MMAs per product on bf16(x_scale * X)."""
+        ex, sc = C.c_int32(0), C.c_float(1.0)
+        check(self.ctx.L.bhmc_softmax_operand_info(self.handle, C.byref(ex), C.byref(sc)))
+        return bool(ex.value), float(sc.value)
+
     def predict(self, q_dev, X_dev, want_probs=True, want_labels=True):
         Cn, n = q_dev.shape[0], X_dev.shape[0]
         probs = self.ctx.empty((Cn, n, self.K)) if want_probs else None

@@ -95,6 +95,12 @@ int bhmc_softmax_bind_data(bhmc_model* m, const float* X_dev, const int32_t* lab
  * end-to-end number goes through: the H2D copy happens inside this call) */
 int bhmc_softmax_bind_data_host(bhmc_model* m, const float* X_host, const int32_t* labels_host,
                                 int32_t precision_mask);
+/* What the last bind found about X (tensor-core precisions only): *exact = 1 if x_scale * X is exactly representable in
+ * bf16 for every element (x_scale = 1: binary / small-integer features; 255: 8-bit pixels / 255, the reference's MNIST
+ * input, hamiltonian/utils.py scaling).  BHMC_PREC_BF16X3 then needs no lo copy of X and issues 2 MMAs per product
+ * instead of 3, with 1/x_scale folded into the W operand and the gradient -- same result up to fp32 rounding.
+ * Environment BHMC_X_EXACT=0 turns the check off. */
+int bhmc_softmax_operand_info(bhmc_model* m, int32_t* exact, float* x_scale);
 /* 2-D (d-dimensional) Gaussian target, hamiltonian/models/cpu/mvn_gaussian.py:14-31.
  * cov_inv: [dim,dim] row-major (host), logdet = log det(cov). */
 int bhmc_mvn_create(bhmc_ctx* ctx, int32_t dim, const double* mu_host, const double* cov_inv_host,

@@ -451,3 +451,86 @@ def test_streaming_schedule_matches_lockstep(prec, prior):
     np.testing.assert_allclose(a["loss"], b["loss"], rtol=1e-6)
     np.testing.assert_allclose(a["accept_prob"], b["accept_prob"], rtol=1e-4, atol=1e-9)
     h.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# exact-operand path: scale*X exactly representable in bf16 -> bf16x3 runs 2 MMAs per product (no lo copy of X)
+# ------------------------------------------------------------------------------------------------
+def _pixel_data(rs, N, D, kind):
+    if kind == "pixels":  # 8-bit pixels / 255 as the reference's MNIST scripts feed them (float64 quotient)
+        return rs.randint(0, 256, (N, D)) / 255.0
+    if kind == "pixels_f32":  # the same quotient taken in fp32
+        return (rs.randint(0, 256, (N, D)).astype(np.float32) / np.float32(255.0)).astype(np.float64)
+    if kind == "pixels_recip":  # multiplication by the rounded reciprocal (torch on CUDA: tensor / 255.0)
+        return (rs.randint(0, 256, (N, D)).astype(np.float32) * (np.float32(1.0) / np.float32(255.0))).astype(np.float64)
+    if kind == "binary":
+        return (rs.rand(N, D) < 0.3).astype(np.float64)
+    if kind == "almost":  # one element off the pixel grid: the check must refuse the fast path
+        X = rs.randint(0, 256, (N, D)) / 255.0
+        X[N // 2, D // 3] += 1e-6
+        return X
+    return rs.rand(N, D)
+
+
+@pytest.mark.parametrize("kind,expect", [("pixels", (True, 255.0)), ("pixels_f32", (True, 255.0)),
+                                         ("pixels_recip", (True, 255.0)), ("binary", (True, 1.0)),
+                                         ("almost", (False, 1.0)), ("dense", (False, 1.0))])
+def test_exact_operand_detection_and_grad(kind, expect):
+    from dropout_hamiltonian_montecarlo_b200.runtime import SoftmaxHandle, default_context
+    rs = np.random.RandomState(11)
+    N, D, K, C, alpha = 1000, 100, 10, 5, 0.01
+    X = _pixel_data(rs, N, D, kind)
+    y = rs.randint(0, K, N).astype(np.int32)
+    q = rs.normal(0, .2, (C, (D + 1) * K)).astype(np.float32)
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, N, D, K, alpha)
+    h.bind(torch.as_tensor(X.astype(np.float32)).cuda(), torch.as_tensor(y).cuda())
+    assert h.operand_info() == expect
+    X32 = X.astype(np.float32).astype(np.float64)
+    for prec in (1, 2):  # bf16x3, bf16
+        for (r0, n) in [(0, N), (130, 500)]:
+            g, ll = h.grad(h.pack(q), r0, n, prec)
+            g = g[:, :h.P].cpu().numpy()
+            ll = ll.cpu().numpy()
+            for c in range(C):
+                par = {"weights": q[c, :D * K].reshape(D, K).astype(np.float64), "bias": q[c, D * K:].astype(np.float64)}
+                ref = O.softmax_grad(par, X32[r0:r0 + n], O.one_hot(y[r0:r0 + n], K), alpha)
+                rtol, scale = ((1e-4, 2e-5) if prec == 1 else (5e-2, 2e-2))
+                close(g[c], O.flatten_par(ref, ["weights", "bias"]), rtol, scale, "%s prec %d window %d+%d" % (kind, prec, r0, n))
+                if prec == 1:
+                    close(ll[c], O.softmax_log_likelihood(par, X32[r0:r0 + n], O.one_hot(y[r0:r0 + n], K)), 5e-6)
+
+
+@pytest.mark.parametrize("sched", ["lockstep", "streaming"])
+def test_hmc_pixels_vs_oracle(sched):
+    """Ragged batched chains on 8-bit pixel data (2-MMA path, X.W cache, fused streaming update) vs oracle chains."""
+    rs = np.random.RandomState(6)
+    N, D, K, C, alpha, eps, path = 500, 40, 10, 5, 0.01, 5e-4, 4e-3
+    X = _pixel_data(rs, N, D, "pixels")
+    y = rs.randint(0, K, N)
+    Y = O.one_hot(y, K)
+    W0 = rs.normal(0, .1, (C, D, K))
+    b0 = rs.normal(0, .1, (C, K))
+    n_steps = 3
+    from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle
+    m = softmax({"alpha": alpha}, precision="bf16x3")
+    h = m.bind(X, Y)
+    assert h.operand_info() == (True, 255.0)
+    s = SamplerHandle(h.ctx, h, 0, C, precision=1)
+    s.set_q(np.concatenate([W0.reshape(C, -1), b0], axis=1))
+    z = rs.normal(size=(n_steps, C, h.P))
+    u1 = rs.rand(n_steps, C)
+    u2 = rs.rand(n_steps, C)
+    out = s.hmc_run(n_steps, eps, path, z_momentum=torch.as_tensor(z, dtype=torch.float32), u_path=u1, u_accept=u2,
+                    schedule=sched)
+    samples = out["samples"].cpu().numpy()
+    acc = out["accept_prob"].cpu().numpy()
+    X32 = X.astype(np.float32).astype(np.float64)
+    for c in range(C):
+        q = {"weights": W0[c], "bias": b0[c]}
+        for t in range(n_steps):
+            draws = O.TapeDraws([z[t, c, :D * K].reshape(D, K), z[t, c, D * K:]], [u1[t, c], u2[t, c]])
+            r = O.hmc_step(O.SoftmaxOracle({"alpha": alpha}), q, ["weights", "bias"], eps, path, draws, X_train=X32, y_train=Y)
+            q = r["q"]
+            close(acc[t, c], r["accept_prob"], 5e-4, 1e-6, "accept chain %d step %d" % (c, t))
+            close(samples[t, c], O.flatten_par(q, ["weights", "bias"]), 1e-4, 2e-6, "chain %d step %d" % (c, t))
