@@ -17,7 +17,10 @@ ap.add_argument("--precision", default="bf16x3")
 ap.add_argument("--evals", type=int, default=3)
 ap.add_argument("--chains", type=int, default=0)
 ap.add_argument("--loglik", action="store_true")
+ap.add_argument("--data", default="dense", choices=["dense", "pixels"])
 a = ap.parse_args()
+import bench
+bench.DATA_KIND = a.data
 wl = WORKLOADS[a.workload]
 C = a.chains or wl["C"]
 dev = torch.device("cuda", 0)
