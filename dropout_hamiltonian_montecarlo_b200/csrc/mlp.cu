@@ -14,6 +14,10 @@
 // (H1, H2d), not the masks:  dA2 = dH2d * [H2d>0] / keep^2,  dA1 = dH1 * [H1>0] / keep.
 #include <new>
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "internal.cuh"
 #include "philox.cuh"
 
@@ -106,9 +110,170 @@ __global__ void __launch_bounds__(256) k_mlp_gemm(GemmDesc d) {
   }
 }
 
+// ---- skinny GEMMs of the n_out-wide output layer (N, M or K = n_out ~ 10) -------------------------------------------
+// The 64x64 tile kernel above wastes 84 % of a tile on them (ncu: 46 / 51 / 25 us at 16 chains); each gets a kernel
+// shaped like its own data movement.  Plain-epilogue subsets only (what mlp.cu needs): run_gemm() falls back to
+// k_mlp_gemm for anything else.
+static constexpr int SKINNY = 16;
+
+// N <= 16, A rows contiguous in k (a_cs == 1), B(k, n) contiguous in k (b_rs == 1); + bias.  Block = 32 rows (8 warps
+// x 4 rows), B staged in shared memory as [n][K]; lanes split k, butterfly reduction, lane n stores column n.
+__global__ void __launch_bounds__(256) k_mlp_gemm_small_n(GemmDesc d) {
+  extern __shared__ float Bs[];  // [N][K]
+  const int c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* A = d.A + (int64_t)c * d.a_batch;
+  const float* B = d.B + (int64_t)c * d.b_batch;
+  for (int i = threadIdx.x; i < d.N * d.K; i += 256) {
+    const int n = i / d.K, k = i - n * d.K;
+    Bs[i] = B[(int64_t)k + (int64_t)n * d.b_cs];
+  }
+  __syncthreads();
+  const int m0 = (blockIdx.x * 8 + warp) * 4;
+  float acc[4][SKINNY];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int n = 0; n < SKINNY; ++n) acc[r][n] = 0.f;
+#pragma unroll 4
+  for (int k = lane; k < d.K; k += 32) {
+    float a[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[r] = (m0 + r < d.M) ? A[(int64_t)(m0 + r) * d.a_rs + k] : 0.f;
+#pragma unroll
+    for (int n = 0; n < SKINNY; ++n) {
+      if (n < d.N) {
+        const float b = Bs[n * d.K + k];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][n] = fmaf(a[r], b, acc[r][n]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < SKINNY; ++n) {
+      float v = acc[r][n];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == n) mine = v;
+    }
+    if (m0 + r < d.M && lane < d.N) {
+      if (d.bias) mine += d.bias[(int64_t)c * d.bias_batch + lane];
+      d.C[(int64_t)c * d.c_batch + (int64_t)(m0 + r) * d.c_rs + lane] = mine;
+    }
+  }
+}
+
+// M <= 16, B(k, n) contiguous in n (b_cs == 1); + add_scale * addsrc.  Block = 32 columns x 16 k-groups; A (K x M, a few
+// KB) is staged in shared memory as [k][m]; every thread keeps the M partial sums of its column over every 16th k, the
+// groups are combined in a fixed order through the same shared memory.
+static constexpr int SM_GROUPS = 16;
+__global__ void __launch_bounds__(32 * SM_GROUPS) k_mlp_gemm_small_m(GemmDesc d) {
+  extern __shared__ float sm_buf[];  // max(K*M, SM_GROUPS*M*33) floats
+  const int c = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const float* A = d.A + (int64_t)c * d.a_batch;
+  const float* B = d.B + (int64_t)c * d.b_batch;
+  for (int i = threadIdx.x; i < d.K * d.M; i += 32 * SM_GROUPS) {
+    int k, m;
+    if (d.a_rs == 1) k = i / d.M, m = i - k * d.M;  // source is [k][m]-contiguous
+    else m = i / d.K, k = i - m * d.K;
+    sm_buf[k * d.M + m] = A[(int64_t)m * d.a_rs + (int64_t)k * d.a_cs];
+  }
+  __syncthreads();
+  float acc[SKINNY];
+#pragma unroll
+  for (int m = 0; m < SKINNY; ++m) acc[m] = 0.f;
+  if (n < d.N) {
+#pragma unroll 4
+    for (int k = ty; k < d.K; k += SM_GROUPS) {
+      const float b = B[(int64_t)k * d.b_rs + n];
+      const float* a = sm_buf + k * d.M;
+#pragma unroll
+      for (int m = 0; m < SKINNY; ++m)
+        if (m < d.M) acc[m] = fmaf(a[m], b, acc[m]);
+    }
+  }
+  __syncthreads();  // A is no longer needed: the buffer now holds the partial sums [group][m][33]
+#pragma unroll
+  for (int m = 0; m < SKINNY; ++m)
+    if (m < d.M) sm_buf[(ty * d.M + m) * 33 + tx] = acc[m];
+  __syncthreads();
+  if (n < d.N) {
+    for (int m = ty; m < d.M; m += SM_GROUPS) {
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < SM_GROUPS; ++i) v += sm_buf[(i * d.M + m) * 33 + tx];
+      if (d.addsrc) v = fmaf(d.add_scale, d.addsrc[(int64_t)c * d.add_batch + (int64_t)m * d.add_rs + n], v);
+      d.C[(int64_t)c * d.c_batch + (int64_t)m * d.c_rs + n] = v;
+    }
+  }
+}
+
+// K <= 16, B(k, n) contiguous in n (b_cs == 1), N % 4 == 0, 16-byte aligned rows; * gate.  HBM-bound: a thread produces
+// four consecutive columns of four rows (K float4 loads of B from L1/L2 shared by the rows, 4K broadcast loads of A,
+// four float4 stores).
+__global__ void __launch_bounds__(128) k_mlp_gemm_small_k(GemmDesc d) {
+  const int c = blockIdx.z, m0 = blockIdx.y * 4;
+  const int n = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (n >= d.N) return;
+  const float* A = d.A + (int64_t)c * d.a_batch;
+  const float* B = d.B + (int64_t)c * d.b_batch + n;
+  float4 acc[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < SKINNY; ++k) {
+    if (k < d.K) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(B + (int64_t)k * d.b_rs));
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float a = (m0 + r < d.M) ? __ldg(A + (int64_t)(m0 + r) * d.a_rs + (int64_t)k * d.a_cs) : 0.f;
+        acc[r].x = fmaf(a, b.x, acc[r].x), acc[r].y = fmaf(a, b.y, acc[r].y);
+        acc[r].z = fmaf(a, b.z, acc[r].z), acc[r].w = fmaf(a, b.w, acc[r].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int m = m0 + r;
+    if (m >= d.M) break;
+    float4 v = acc[r];
+    if (d.gate) {
+      const float4 gt = __ldg(reinterpret_cast<const float4*>(d.gate + (int64_t)c * d.gate_batch + (int64_t)m * d.gate_rs + n));
+      v.x = gt.x > 0.f ? v.x * d.gate_scale : 0.f;
+      v.y = gt.y > 0.f ? v.y * d.gate_scale : 0.f;
+      v.z = gt.z > 0.f ? v.z * d.gate_scale : 0.f;
+      v.w = gt.w > 0.f ? v.w * d.gate_scale : 0.f;
+    }
+    *reinterpret_cast<float4*>(d.C + (int64_t)c * d.c_batch + (int64_t)m * d.c_rs + n) = v;
+  }
+}
+
 static int run_gemm(bhmc_ctx* ctx, const GemmDesc& d, int C) {
-  dim3 grid((unsigned)ceil_div(d.M, TM), (unsigned)ceil_div(d.N, TN), (unsigned)C);
-  k_mlp_gemm<<<grid, 256, 0, ctx->stream>>>(d);
+  auto al16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  const bool plain = d.epi == 0 && !d.mask_a && !d.mask_b;
+  static int skinny_env = -1;  // BHMC_MLP_SKINNY=0: generic tile kernel for every shape (A/B measurements)
+  if (skinny_env < 0) {
+    const char* e = getenv("BHMC_MLP_SKINNY");
+    skinny_env = e ? atoi(e) : 1;
+  }
+  if (skinny_env && plain && d.N <= SKINNY && d.M > SKINNY && d.a_cs == 1 && d.b_rs == 1 && !d.addsrc && !d.gate &&
+      (size_t)d.N * d.K * sizeof(float) <= 48 * 1024) {
+    k_mlp_gemm_small_n<<<dim3((unsigned)ceil_div(d.M, 32), C), 256, sizeof(float) * d.N * d.K, ctx->stream>>>(d);
+  } else if (skinny_env && plain && d.M <= SKINNY && d.N > SKINNY && d.b_cs == 1 && !d.bias && !d.gate &&
+             (size_t)d.K * d.M * sizeof(float) <= 44 * 1024) {
+    const size_t sm = sizeof(float) * std::max((size_t)d.K * d.M, (size_t)SM_GROUPS * d.M * 33);
+    k_mlp_gemm_small_m<<<dim3((unsigned)ceil_div(d.N, 32), C), 32 * SM_GROUPS, sm, ctx->stream>>>(d);
+  } else if (skinny_env && plain && d.K <= SKINNY && d.M <= 4 * 65535 && d.b_cs == 1 && d.N % 4 == 0 && !d.bias && !d.addsrc && al16(d.B) &&
+             d.b_batch % 4 == 0 && d.b_rs % 4 == 0 && al16(d.C) && d.c_batch % 4 == 0 && d.c_rs % 4 == 0 &&
+             (!d.gate || (al16(d.gate) && d.gate_batch % 4 == 0 && d.gate_rs % 4 == 0))) {
+    k_mlp_gemm_small_k<<<dim3((unsigned)ceil_div(d.N, 512), (unsigned)ceil_div(d.M, 4), C), 128, 0, ctx->stream>>>(d);
+  } else {
+    dim3 grid((unsigned)ceil_div(d.M, TM), (unsigned)ceil_div(d.N, TN), (unsigned)C);
+    k_mlp_gemm<<<grid, 256, 0, ctx->stream>>>(d);
+  }
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
@@ -146,16 +311,36 @@ __global__ void __launch_bounds__(256) k_mlp_loss(float* __restrict__ Z, int B, 
 }
 
 // bias gradient: out[c, n] = sum_b S[c, b, n] + alpha/2 * bias[c, n]
-__global__ void __launch_bounds__(128) k_mlp_colsum(const float* __restrict__ S, int B, int N, int64_t s_batch,
-                                                    const float* __restrict__ q, int64_t ld, int64_t b_off,
-                                                    float half_alpha, float* __restrict__ g) {
+// block = 32 columns x 32 row groups of one chain (a thread per column walking all B rows left 64 blocks on the GPU and
+// took 40 us: one DRAM latency per row); each thread sums every 32nd row with four independent accumulators, the
+// groups are combined in a fixed order through shared memory (deterministic)
+__global__ void __launch_bounds__(1024) k_mlp_colsum(const float* __restrict__ S, int B, int N, int64_t s_batch,
+                                                     const float* __restrict__ q, int64_t ld, int64_t b_off,
+                                                     float half_alpha, float* __restrict__ g) {
+  __shared__ float part[32][33];
   const int c = blockIdx.y;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const float* s = S + (int64_t)c * s_batch + n;
-  float acc = 0.f;
-  for (int b = 0; b < B; ++b) acc += s[(int64_t)b * N];
-  g[(int64_t)c * ld + b_off + n] = acc + half_alpha * q[(int64_t)c * ld + b_off + n];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (n < N) {
+    const float* s = S + (int64_t)c * s_batch + n;
+    int b = ty;
+    for (; b + 96 < B; b += 128) {
+      a0 += s[(int64_t)b * N];
+      a1 += s[(int64_t)(b + 32) * N];
+      a2 += s[(int64_t)(b + 64) * N];
+      a3 += s[(int64_t)(b + 96) * N];
+    }
+    for (; b < B; b += 32) a0 += s[(int64_t)b * N];
+  }
+  part[ty][tx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc += part[i][tx];
+    g[(int64_t)c * ld + b_off + n] = acc + half_alpha * q[(int64_t)c * ld + b_off + n];
+  }
 }
 
 struct MlpModel : ModelBase {
@@ -270,7 +455,7 @@ struct MlpModel : ModelBase {
     d.M = n_out, d.N = n_mid, d.K = B;
     d.addsrc = q + oW3, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
     BHMC_TRY(run_gemm(ctx, d, C));
-    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_out, 128), C), 128, 0, ctx->stream>>>(Z, B, n_out, (int64_t)B * n_out, q, ld, ob3, ha, g);
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_out, 32), C), 1024, 0, ctx->stream>>>(Z, B, n_out, (int64_t)B * n_out, q, ld, ob3, ha, g);
     // dA2 = (dZ W3) * [H2d > 0] / keep^2
     d = base();
     d.A = Z, d.a_batch = (int64_t)B * n_out, d.a_rs = n_out, d.a_cs = 1;
@@ -287,7 +472,7 @@ struct MlpModel : ModelBase {
     d.M = n_mid, d.N = n_mid, d.K = B;
     d.addsrc = q + oW2, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
     BHMC_TRY(run_gemm(ctx, d, C));
-    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 128), C), 128, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g);
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g);
     // dA1 = (dA2 W2) * [H1 > 0] / keep
     d = base();
     d.A = dA2, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
@@ -304,7 +489,7 @@ struct MlpModel : ModelBase {
     d.M = n_mid, d.N = n_in, d.K = B;
     d.addsrc = q + oW1, d.add_batch = ld, d.add_rs = n_in, d.add_scale = ha;
     BHMC_TRY(run_gemm(ctx, d, C));
-    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 128), C), 128, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g);
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g);
     ctx->launches += 3;
     // padding columns of g (ld > P) are never read by the update kernels beyond P; keep them finite
     BHMC_CUDA_OK(cudaGetLastError());

@@ -41,6 +41,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 struct BgParams {
   int batch, m_tiles, n_tiles, k_chunks, BN, stages, split3;
   int a_shared, b_shared;  // operand identical for every chain (e.g. the data matrix)
+  int vec;                 // epilogue may use 16-byte loads / stores (N % 4 == 0, strides % 4 == 0, 16 B aligned bases)
   GemmDesc d;              // sizes + epilogue (the A/B pointers inside are unused here)
 };
 
@@ -160,46 +161,110 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
         tmem_ld_wait();
         const int n0 = nt * p.BN + j0;
         if (m < d.M && n0 < d.N) {
+          // Every input of the 16 outputs is fetched BEFORE the first store: with loads and stores interleaved per
+          // element the compiler must keep them in program order (C may alias the inputs for all it knows), which
+          // made the epilogue one dependent DRAM round trip per element (ncu: 104 us for the W1-gradient GEMM, tensor
+          // pipe 14 %).  p.vec: row strides and base addresses allow 16-byte accesses.
+          const int nq = min(4, (d.N - n0 + 3) >> 2);  // quads with at least one valid column
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+          if (d.bias) {
+            const float* bp = d.bias + (int64_t)z * d.bias_batch + n0;
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {  // four columns at a time (one Philox call per quad)
-            const int n = n0 + 4 * qd;
-            if (n >= d.N) break;
-            uint32_t ka = 15u, kb = 15u;
-            if (d.epi >= 1) {
+            for (int j = 0; j < 16; ++j)
+              if (n0 + j < d.N) v[j] += __ldg(bp + j);
+          }
+          if (d.addsrc) {
+            const float* ap = d.addsrc + (int64_t)z * d.add_batch + (int64_t)m * d.add_rs + n0;
+            if (p.vec) {
+              float4 t4[4];
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) t4[qd] = qd < nq ? __ldg(reinterpret_cast<const float4*>(ap) + qd) : make_float4(0, 0, 0, 0);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                v[4 * qd] = fmaf(d.add_scale, t4[qd].x, v[4 * qd]);
+                v[4 * qd + 1] = fmaf(d.add_scale, t4[qd].y, v[4 * qd + 1]);
+                v[4 * qd + 2] = fmaf(d.add_scale, t4[qd].z, v[4 * qd + 2]);
+                v[4 * qd + 3] = fmaf(d.add_scale, t4[qd].w, v[4 * qd + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + j < d.N) v[j] = fmaf(d.add_scale, __ldg(ap + j), v[j]);
+            }
+          }
+          if (d.gate) {
+            const float* gp = d.gate + (int64_t)z * d.gate_batch + (int64_t)m * d.gate_rs + n0;
+            if (p.vec) {
+              float4 t4[4];
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) t4[qd] = qd < nq ? __ldg(reinterpret_cast<const float4*>(gp) + qd) : make_float4(0, 0, 0, 0);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                v[4 * qd] = t4[qd].x > 0.f ? v[4 * qd] * d.gate_scale : 0.f;
+                v[4 * qd + 1] = t4[qd].y > 0.f ? v[4 * qd + 1] * d.gate_scale : 0.f;
+                v[4 * qd + 2] = t4[qd].z > 0.f ? v[4 * qd + 2] * d.gate_scale : 0.f;
+                v[4 * qd + 3] = t4[qd].w > 0.f ? v[4 * qd + 3] * d.gate_scale : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (n0 + j < d.N) v[j] = __ldg(gp + j) > 0.f ? v[j] * d.gate_scale : 0.f;
+            }
+          }
+          uint32_t ka = 0xFFFFu, kb = 0xFFFFu;  // keep bits of the 16 columns
+          if (d.epi >= 1) {
+            ka = 0;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              if (qd >= nq) break;
+              const int n = n0 + 4 * qd;
+              uint32_t k4 = 0;
               if (d.mask_a) {
-                ka = 0;
                 for (int j = 0; j < 4; ++j)
-                  if (n + j < d.N && d.mask_a[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) ka |= 1u << j;
+                  if (n + j < d.N && d.mask_a[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
               } else {
-                ka = keep_bits4(d, z, m, n, d.layer_a);
+                k4 = keep_bits4(d, z, m, n, d.layer_a);
               }
-              if (d.epi == 2) {
-                if (d.mask_b) {
-                  kb = 0;
-                  for (int j = 0; j < 4; ++j)
-                    if (n + j < d.N && d.mask_b[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) kb |= 1u << j;
-                } else {
-                  kb = keep_bits4(d, z, m, n, d.layer_b);
-                }
-              }
+              ka |= k4 << (4 * qd);
             }
+            if (d.epi == 2) {
+              kb = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n + j >= d.N) continue;
-              float x = v[4 * qd + j];
-              if (d.bias) x += d.bias[(int64_t)z * d.bias_batch + n + j];
-              if (d.addsrc) x += d.add_scale * d.addsrc[(int64_t)z * d.add_batch + (int64_t)m * d.add_rs + n + j];
-              if (d.gate) x = (d.gate[(int64_t)z * d.gate_batch + (int64_t)m * d.gate_rs + n + j] > 0.f) ? x * d.gate_scale : 0.f;
-              if (d.epi >= 1) {
-                x = ((ka >> j) & 1u) ? x * d.keep_inv : 0.f;
-                x = fmaxf(x, 0.f);
-                if (d.epi == 2) x = ((kb >> j) & 1u) ? x * d.keep_inv : 0.f;
+              for (int qd = 0; qd < 4; ++qd) {
+                if (qd >= nq) break;
+                const int n = n0 + 4 * qd;
+                uint32_t k4 = 0;
+                if (d.mask_b) {
+                  for (int j = 0; j < 4; ++j)
+                    if (n + j < d.N && d.mask_b[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
+                } else {
+                  k4 = keep_bits4(d, z, m, n, d.layer_b);
+                }
+                kb |= k4 << (4 * qd);
               }
-              d.C[(int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n + j] = x;
             }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = v[j];
+            if (d.epi >= 1) {
+              x = ((ka >> j) & 1u) ? x * d.keep_inv : 0.f;
+              x = fmaxf(x, 0.f);
+              if (d.epi == 2) x = ((kb >> j) & 1u) ? x * d.keep_inv : 0.f;
+            }
+            v[j] = x;
+          }
+          float* cp = d.C + (int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n0;
+          if (p.vec) {
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd)
+              if (qd < nq) reinterpret_cast<float4*>(cp)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + j < d.N) cp[j] = v[j];
           }
         }
       }
@@ -215,37 +280,48 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
   }
 }
 
-// dst_{hi,lo}[z][r][k] (k < Kp contiguous) = split(src[z*sb + r*rs + k*cs]) for k < K, 0 for K <= k < Kp.
-// One 32x32 tile per block through shared memory, so both cs == 1 (row-major source) and rs == 1 (transposed
-// source) read and write coalesced.
+// dst_{hi,lo}[z][r][k] (k < Kp contiguous, Kp % 64 == 0) = split(src[z*sb + r*rs + k*cs]) for k < K, 0 for K <= k < Kp.
+// One 32 (rows) x 64 (k) tile per block through shared memory, so both cs == 1 (row-major source) and rs == 1
+// (transposed source) read coalesced; every thread writes a bf16 pair (128 B per warp and row).
 __global__ void __launch_bounds__(256) k_split_operand(const float* __restrict__ src, int64_t sb, int64_t rs, int64_t cs,
                                                        int R, int K, int64_t Kp, __nv_bfloat16* __restrict__ hi,
                                                        __nv_bfloat16* __restrict__ lo) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[32][65];
   const int z = blockIdx.z;
-  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
   const float* s = src + (int64_t)z * sb;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   if (cs == 1 || rs != 1) {
     for (int i = ty; i < 32; i += 8) {
-      const int r = r0 + i, k = k0 + tx;
-      tile[i][tx] = (r < R && k < K) ? s[(int64_t)r * rs + (int64_t)k * cs] : 0.f;
+      const int r = r0 + i;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = k0 + tx + 32 * h;
+        tile[i][tx + 32 * h] = (r < R && k < K) ? s[(int64_t)r * rs + (int64_t)k * cs] : 0.f;
+      }
     }
   } else {  // rows are the contiguous index of the source: read along r
-    for (int i = ty; i < 32; i += 8) {
+    for (int i = ty; i < 64; i += 8) {
       const int k = k0 + i, r = r0 + tx;
       tile[tx][i] = (r < R && k < K) ? s[(int64_t)r * rs + (int64_t)k * cs] : 0.f;
     }
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, k = k0 + tx;
-    if (r < R && k < Kp) {
-      const float v = tile[i][tx];
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const int r = r0 + i, k = k0 + 2 * tx;
+    if (r < R) {
+      const float v0 = tile[i][2 * tx], v1 = tile[i][2 * tx + 1];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
       const int64_t o = ((int64_t)z * R + r) * Kp + k;
-      hi[o] = h;
-      if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      __nv_bfloat162 hv;
+      hv.x = h0, hv.y = h1;
+      *reinterpret_cast<__nv_bfloat162*>(hi + o) = hv;
+      if (lo) {
+        __nv_bfloat162 lv;
+        lv.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+        lv.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+        *reinterpret_cast<__nv_bfloat162*>(lo + o) = lv;
+      }
     }
   }
 }
@@ -302,10 +378,10 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   __nv_bfloat16 *b_hi = (__nv_bfloat16*)sb, *b_lo = b_hi + b_elems;
   {
     GroupTimer t(ctx, KG_PREP);
-    dim3 ga((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(d.M, 32), (unsigned)za);
+    dim3 ga((unsigned)(Kp / 64), (unsigned)ceil_div(d.M, 32), (unsigned)za);
     k_split_operand<<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, a_hi, split3 ? a_lo : nullptr);
     // B is (k, n) with strides (b_rs, b_cs): its K-major copy has rows n
-    dim3 gb((unsigned)ceil_div(Kp, 32), (unsigned)ceil_div(d.N, 32), (unsigned)zb);
+    dim3 gb((unsigned)(Kp / 64), (unsigned)ceil_div(d.N, 32), (unsigned)zb);
     k_split_operand<<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, b_hi, split3 ? b_lo : nullptr);
     ctx->launches += 2;
   }
@@ -319,6 +395,13 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   p.a_shared = a_shared;
   p.b_shared = b_shared;
   p.d = d;
+  {
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+    bool v = d.N % 4 == 0 && al16(d.C) && d.c_batch % 4 == 0 && d.c_rs % 4 == 0;
+    if (d.addsrc) v = v && al16(d.addsrc) && d.add_batch % 4 == 0 && d.add_rs % 4 == 0;
+    if (d.gate) v = v && al16(d.gate) && d.gate_batch % 4 == 0 && d.gate_rs % 4 == 0;
+    p.vec = v ? 1 : 0;
+  }
   const int stage_bytes = (split3 ? 2 : 1) * (BM * BK * 2 + p.BN * BK * 2);
   p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
