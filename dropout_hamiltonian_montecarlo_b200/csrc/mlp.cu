@@ -117,36 +117,29 @@ __global__ void __launch_bounds__(256) k_mlp_gemm(GemmDesc d) {
 static constexpr int SKINNY = 16;
 
 // N <= 16, A rows contiguous in k (a_cs == 1), B(k, n) contiguous in k (b_rs == 1); + bias.  Block = 32 rows (8 warps
-// x 4 rows), B staged in shared memory as [n][K]; lanes split k, butterfly reduction, lane n stores column n.
+// x 4 rows); lanes split k (coalesced 128-byte loads of the A rows and of the B columns, which stay in L1 -- a few KB
+// per chain), butterfly reduction, lane n stores column n.  No staging phase: every load of the k loop is independent.
 __global__ void __launch_bounds__(256) k_mlp_gemm_small_n(GemmDesc d) {
-  extern __shared__ float Bs[];  // [N][K]
   const int c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* A = d.A + (int64_t)c * d.a_batch;
   const float* B = d.B + (int64_t)c * d.b_batch;
-  for (int i = threadIdx.x; i < d.N * d.K; i += 256) {
-    const int n = i / d.K, k = i - n * d.K;
-    Bs[i] = B[(int64_t)k + (int64_t)n * d.b_cs];
-  }
-  __syncthreads();
   const int m0 = (blockIdx.x * 8 + warp) * 4;
   float acc[4][SKINNY];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int n = 0; n < SKINNY; ++n) acc[r][n] = 0.f;
-#pragma unroll 4
+#pragma unroll 2
   for (int k = lane; k < d.K; k += 32) {
-    float a[4];
+    float a[4], b[SKINNY];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) a[r] = (m0 + r < d.M) ? A[(int64_t)(m0 + r) * d.a_rs + k] : 0.f;
+    for (int r = 0; r < 4; ++r) a[r] = (m0 + r < d.M) ? __ldg(A + (int64_t)(m0 + r) * d.a_rs + k) : 0.f;
 #pragma unroll
-    for (int n = 0; n < SKINNY; ++n) {
-      if (n < d.N) {
-        const float b = Bs[n * d.K + k];
+    for (int n = 0; n < SKINNY; ++n) b[n] = (n < d.N) ? __ldg(B + (int64_t)n * d.b_cs + k) : 0.f;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r][n] = fmaf(a[r], b, acc[r][n]);
-      }
-    }
+    for (int n = 0; n < SKINNY; ++n)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r][n] = fmaf(a[r], b[n], acc[r][n]);
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -259,9 +252,8 @@ static int run_gemm(bhmc_ctx* ctx, const GemmDesc& d, int C) {
     const char* e = getenv("BHMC_MLP_SKINNY");
     skinny_env = e ? atoi(e) : 1;
   }
-  if (skinny_env && plain && d.N <= SKINNY && d.M > SKINNY && d.a_cs == 1 && d.b_rs == 1 && !d.addsrc && !d.gate &&
-      (size_t)d.N * d.K * sizeof(float) <= 48 * 1024) {
-    k_mlp_gemm_small_n<<<dim3((unsigned)ceil_div(d.M, 32), C), 256, sizeof(float) * d.N * d.K, ctx->stream>>>(d);
+  if (skinny_env && plain && d.N <= SKINNY && d.M > SKINNY && d.a_cs == 1 && d.b_rs == 1 && !d.addsrc && !d.gate) {
+    k_mlp_gemm_small_n<<<dim3((unsigned)ceil_div(d.M, 32), C), 256, 0, ctx->stream>>>(d);
   } else if (skinny_env && plain && d.M <= SKINNY && d.N > SKINNY && d.b_cs == 1 && !d.bias && !d.gate &&
              (size_t)d.K * d.M * sizeof(float) <= 44 * 1024) {
     const size_t sm = sizeof(float) * std::max((size_t)d.K * d.M, (size_t)SM_GROUPS * d.M * 33);
