@@ -283,16 +283,18 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
 // dst_{hi,lo}[z][r][k] (k < Kp contiguous, Kp % 64 == 0) = split(src[z*sb + r*rs + k*cs]) for k < K, 0 for K <= k < Kp.
 // One 32 (rows) x 64 (k) tile per block through shared memory, so both cs == 1 (row-major source) and rs == 1
 // (transposed source) read coalesced; every thread writes a bf16 pair (128 B per warp and row).
+template <int TR>  // tile rows (32 or 64): 64 keeps twice the loads in flight per thread
 __global__ void __launch_bounds__(256) k_split_operand(const float* __restrict__ src, int64_t sb, int64_t rs, int64_t cs,
                                                        int R, int K, int64_t Kp, __nv_bfloat16* __restrict__ hi,
                                                        __nv_bfloat16* __restrict__ lo) {
-  __shared__ float tile[32][65];
+  __shared__ float tile[TR][65];
   const int z = blockIdx.z;
-  const int r0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
+  const int r0 = blockIdx.y * TR, k0 = blockIdx.x * 64;
   const float* s = src + (int64_t)z * sb;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   if (cs == 1 || rs != 1) {
-    for (int i = ty; i < 32; i += 8) {
+#pragma unroll
+    for (int i = ty; i < TR; i += 8) {
       const int r = r0 + i;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -301,13 +303,19 @@ __global__ void __launch_bounds__(256) k_split_operand(const float* __restrict__
       }
     }
   } else {  // rows are the contiguous index of the source: read along r
+#pragma unroll
     for (int i = ty; i < 64; i += 8) {
-      const int k = k0 + i, r = r0 + tx;
-      tile[tx][i] = (r < R && k < K) ? s[(int64_t)r * rs + (int64_t)k * cs] : 0.f;
+      const int k = k0 + i;
+#pragma unroll
+      for (int h = 0; h < TR / 32; ++h) {
+        const int r = r0 + tx + 32 * h;
+        tile[tx + 32 * h][i] = (r < R && k < K) ? s[(int64_t)r * rs + (int64_t)k * cs] : 0.f;
+      }
     }
   }
   __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
+#pragma unroll
+  for (int i = ty; i < TR; i += 8) {
     const int r = r0 + i, k = k0 + 2 * tx;
     if (r < R) {
       const float v0 = tile[i][2 * tx], v1 = tile[i][2 * tx + 1];
@@ -378,16 +386,48 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   __nv_bfloat16 *b_hi = (__nv_bfloat16*)sb, *b_lo = b_hi + b_elems;
   {
     GroupTimer t(ctx, KG_PREP);
-    dim3 ga((unsigned)(Kp / 64), (unsigned)ceil_div(d.M, 32), (unsigned)za);
-    k_split_operand<<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, a_hi, split3 ? a_lo : nullptr);
+    static int tr_env = -1;  // BHMC_SPLIT_TR: tile rows of the split kernel (32 or 64; A/B measurements)
+    if (tr_env < 0) {
+      const char* e = getenv("BHMC_SPLIT_TR");
+      tr_env = e && atoi(e) == 64 ? 64 : 32;  // measured at cfg4: 44.3 k (32) vs 43.2 k (64) grad-evals/s
+    }
     // B is (k, n) with strides (b_rs, b_cs): its K-major copy has rows n
-    dim3 gb((unsigned)(Kp / 64), (unsigned)ceil_div(d.N, 32), (unsigned)zb);
-    k_split_operand<<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, b_hi, split3 ? b_lo : nullptr);
+    if (tr_env == 64) {
+      dim3 ga((unsigned)(Kp / 64), (unsigned)ceil_div(d.M, 64), (unsigned)za), gb((unsigned)(Kp / 64), (unsigned)ceil_div(d.N, 64), (unsigned)zb);
+      k_split_operand<64><<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, a_hi, split3 ? a_lo : nullptr);
+      k_split_operand<64><<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, b_hi, split3 ? b_lo : nullptr);
+    } else {
+      dim3 ga((unsigned)(Kp / 64), (unsigned)ceil_div(d.M, 32), (unsigned)za), gb((unsigned)(Kp / 64), (unsigned)ceil_div(d.N, 32), (unsigned)zb);
+      k_split_operand<32><<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, a_hi, split3 ? a_lo : nullptr);
+      k_split_operand<32><<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, b_hi, split3 ? b_lo : nullptr);
+    }
     ctx->launches += 2;
   }
   BgParams p{};
   p.batch = batch;
   p.BN = d.N >= 128 ? 128 : (int)round_up(d.N, 16);
+  {
+    // BHMC_BG_BN=auto: N-tile width from a rounds x operand-bytes model (a tile streams BM + BN rows per K chunk; the
+    // persistent CTAs need ceil(items / SMs) rounds); BHMC_BG_BN=<n>: forced width for N >= n.  Default: 128.
+    static int bn_env = -2;
+    if (bn_env == -2) {
+      const char* e = getenv("BHMC_BG_BN");
+      bn_env = !e ? 0 : (e[0] == 'a' ? -1 : atoi(e));
+    }
+    const int m_tiles = (int)ceil_div(d.M, BM);
+    if (bn_env > 0 && bn_env % 16 == 0 && bn_env <= 256 && d.N >= bn_env) p.BN = bn_env;
+    if (bn_env == -1 && d.N >= 128) {
+      double best = 1e30;
+      for (int bn = 128; bn <= 256; bn += 16) {
+        const int stg = (int)((225 * 1024) / ((split3 ? 2 : 1) * (BM * BK * 2 + bn * BK * 2)));
+        if (stg < 2) continue;
+        const int64_t items = (int64_t)batch * m_tiles * ceil_div(d.N, bn);
+        const double rounds = (double)ceil_div(items, (int64_t)ctx->sm_count);
+        const double cost = rounds * (BM + bn + 32) * (stg == 2 ? 1.1 : 1.0);
+        if (cost < best - 1e-9) best = cost, p.BN = bn;
+      }
+    }
+  }
   p.m_tiles = (int)ceil_div(d.M, BM);
   p.n_tiles = (int)ceil_div(d.N, p.BN);
   p.k_chunks = (int)ceil_div(d.K, BK);
