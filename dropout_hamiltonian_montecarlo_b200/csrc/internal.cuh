@@ -348,6 +348,7 @@ struct SoftmaxData {
   // that is exact for every element (x_exact) bf16x3 needs no lo copy of X and runs 2 MMAs per product instead of 3
   float x_scale = 1.f;
   bool x_exact = false;
+  bool xa_blocked = false;          // Xa is stored k-chunk-major: [Dp/64][N][64] (one contiguous 16 KB block per TMA box)
 };
 
 int simt_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,

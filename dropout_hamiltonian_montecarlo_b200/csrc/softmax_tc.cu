@@ -610,7 +610,13 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           const uint32_t full = smem_u32(&bar_full[stage]);  // same offset in the leader CTA
           if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
           const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + na * a_bytes;
-          const int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN + rank * (p.BN / 2);
+          int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM;
+          const int bk = k * BK, bn = nt * p.BN + rank * (p.BN / 2);
+          if (p.a_slab) {  // k-chunk-major X: chunk sl starts at row sl * a_slab_rows
+            const int sl = ak / p.a_slab;
+            ak -= sl * p.a_slab;
+            am += sl * p.a_slab_rows;
+          }
           tma_load_2d_2sm(sa, &tmA_hi, full, ak, am);
           if (na == 2) tma_load_2d_2sm(sa + a_bytes, &tmA_lo, full, ak, am);
           tma_load_2d_2sm(sb, &tmB_hi, full, bk, bn);
@@ -954,16 +960,19 @@ __global__ void k_detect_exact(const float* __restrict__ X, int64_t n, int* __re
   }
 }
 
-// Xa[n, d] = split(scale * X[n, d]) with zero padding d in [D, Dp)
-__global__ void k_split_rows(const float* __restrict__ X, int64_t N, int D, int64_t Dp, __nv_bfloat16* __restrict__ hi,
-                             __nv_bfloat16* __restrict__ lo, float scale) {
-  int64_t n = blockIdx.y;
+// Xa[n, d] = split(scale * X[n, d]) with zero padding d in [D, Dp).  blk_rows == 0: plain [N, Dp] rows; else the
+// k-chunk-major layout [Dp/64][blk_rows][64]: the 128 rows x 64 features a forward TMA box fetches are one contiguous
+// 16 KB block (with plain rows every box row sits in a different DRAM page: 128-byte pieces at a 1664-byte stride)
+__global__ void k_split_rows(const float* __restrict__ X, int64_t n0, int D, int64_t Dp, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, float scale, int64_t blk_rows) {
+  const int64_t n = n0 + blockIdx.y;
   for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < Dp; d += (int64_t)gridDim.x * blockDim.x) {
     float v = d < D ? scale * X[n * D + d] : 0.f;
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
-    hi[n * Dp + d] = h;
-    if (lo) lo[n * Dp + d] = l;
+    const int64_t o = blk_rows ? ((d >> 6) * blk_rows + n) * 64 + (d & 63) : n * Dp + d;
+    hi[o] = h;
+    if (lo) lo[o] = l;
   }
 }
 
@@ -1316,6 +1325,15 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo, bool detect_exa
   }
   want_lo = want_lo || d.Xa_lo != nullptr;
   d.has_lo = want_lo;
+  // BHMC_XA_BLOCKED=1: k-chunk-major forward operand.  Measured neutral at cfg2 for 8..64 chains per launch (forward
+  // 66.7 / 80.2 / 110.4 / 148.0 us vs 72.0 / 76.7 / 110.1 / 148.4 us with plain rows; bench 171.5 k vs 171.7 k): the
+  // forward is not limited by DRAM page locality, so the plain layout stays the default.
+  static int xa_blk_env = -1;
+  if (xa_blk_env < 0) {
+    const char* e = getenv("BHMC_XA_BLOCKED");
+    xa_blk_env = e ? atoi(e) : 0;
+  }
+  d.xa_blocked = xa_blk_env != 0 && BK == 64 && d.Dp % 64 == 0 && (d.Dp / 64) * d.N < ((int64_t)1 << 31);
   // exact-operand check (one pass over X and one host sync per bind; BHMC_X_EXACT=0 disables it for A/B measurements)
   d.x_scale = 1.f;
   d.x_exact = false;
@@ -1345,8 +1363,9 @@ int tc_softmax_bind(bhmc_ctx* ctx, SoftmaxData& d, bool want_lo, bool detect_exa
     for (int64_t n0 = 0; n0 < d.N; n0 += 65535) {
       int64_t cnt = std::min<int64_t>(65535, d.N - n0);
       dim3 g(grid.x, (unsigned)cnt);
-      k_split_rows<<<g, 256, 0, ctx->stream>>>(d.X + n0 * d.D, cnt, d.D, d.Dp, (__nv_bfloat16*)d.Xa_hi + n0 * d.Dp,
-                                               want_lo ? (__nv_bfloat16*)d.Xa_lo + n0 * d.Dp : nullptr, d.x_scale);
+      k_split_rows<<<g, 256, 0, ctx->stream>>>(d.X, n0, d.D, d.Dp, (__nv_bfloat16*)d.Xa_hi,
+                                               want_lo ? (__nv_bfloat16*)d.Xa_lo : nullptr, d.x_scale,
+                                               d.xa_blocked ? d.N : 0);
       ctx->launches++;
     }
   }
@@ -1592,11 +1611,13 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   const bool big = pairing_enabled() && Mfwd / BM >= 2 && (Mfwd / BM) * n_tiles >= ctx->sm_count;
   const int fwd_pair = big ? (fwd2 ? 3 : 1) : 0;
   const uint32_t fwd_bbox = (uint32_t)(fwd_pair ? BN / 2 : BN);
-  BHMC_TRY(make_map(&a_hi, d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  // forward A: plain rows [N, Dp] or k-chunk-major blocks [Dp/64][N][64] (coordinates: k inside the chunk, chunk*N + row)
+  const uint64_t xa_inner = d.xa_blocked ? 64 : (uint64_t)d.Dp, xa_outer = d.xa_blocked ? (uint64_t)(d.Dp / 64) * d.N : (uint64_t)d.N;
+  BHMC_TRY(make_map(&a_hi, d.Xa_hi, xa_inner, xa_outer, xa_inner, BM));
   BHMC_TRY(make_map(&b_hi, wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
   a_lo = a_hi;
   b_lo = b_hi;
-  if (smode == 1) BHMC_TRY(make_map(&a_lo, d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  if (smode == 1) BHMC_TRY(make_map(&a_lo, d.Xa_lo, xa_inner, xa_outer, xa_inner, BM));
   if (split3) BHMC_TRY(make_map(&b_lo, wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, fwd_bbox));
   TcParams p{};
   p.m_tiles = (int)(Mfwd / BM);
@@ -1611,6 +1632,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.split3 = smode;
   p.a_k0 = 0;
   p.a_m0 = (int)row0;
+  if (d.xa_blocked) p.a_slab = 64, p.a_slab_rows = (int)d.N;
   p.pair = fwd_pair;
   p.C = C;
   p.K = K;

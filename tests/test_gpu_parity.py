@@ -534,3 +534,22 @@ def test_hmc_pixels_vs_oracle(sched):
             q = r["q"]
             close(acc[t, c], r["accept_prob"], 5e-4, 1e-6, "accept chain %d step %d" % (c, t))
             close(samples[t, c], O.flatten_par(q, ["weights", "bias"]), 1e-4, 2e-6, "chain %d step %d" % (c, t))
+
+
+def test_sgd_fit_pixels_vs_oracle():
+    """Minibatch path on pixel data: the fused reduce + update + next-operand kernel carries the 1/255 scale."""
+    rs = np.random.RandomState(8)
+    N, D, K, alpha, eps, gamma, B = 600, 48, 10, 0.01, 1e-3, 0.9, 100
+    X = _pixel_data(rs, N, D, "pixels")
+    y = rs.randint(0, K, N)
+    Y = O.one_hot(y, K)
+    m = softmax({"alpha": alpha}, precision="bf16x3")
+    s = sgd(m, {"weights": np.zeros((D, K)), "bias": np.zeros(K)}, step_size=eps)
+    par, loss = s.fit(epochs=2, batch_size=B, gamma=gamma, X_train=X, y_train=Y)
+    assert m._bound[1].operand_info() == (True, 255.0)
+    X32 = X.astype(np.float32).astype(np.float64)
+    rp, rl = O.sgd_fit(O.SoftmaxOracle({"alpha": alpha}), {"weights": np.zeros((D, K)), "bias": np.zeros(K)}, eps, 2, B,
+                       gamma, X32, Y)
+    close(par["weights"], rp["weights"], 1e-4, 2e-6)
+    close(par["bias"], rp["bias"], 1e-4, 2e-6)
+    close(loss, rl, 1e-5)
