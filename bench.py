@@ -58,6 +58,21 @@ def _quantize(X):
     return torch.div(torch.floor(X * 256.0).clamp_(max=255.0), torch.tensor(255.0, device=X.device))  # IEEE division
 
 
+def use_all_host_threads():
+    """The CPU arms use every host core the process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which pinned the NumPy oracle to one BLAS thread (measured: 6.3 instead of 27-35 grad-evals/s at --gpus 2)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def data_desc():
     return "synthetic" if DATA_KIND == "dense" else "synthetic (8-bit pixels / 255, MNIST's value grid)"
 
@@ -200,6 +215,7 @@ def cpu_reference_rate(wl, seconds_target=12.0, max_steps=20):
     host cores: one chain, fp64, same data shape; bounded sample (path length pinned to L=11 per step)."""
     from oracle import hamiltonian_oracle as O
     import torch
+    use_all_host_threads()
     X, y = synth(wl["N"], wl["D"], wl["K"], 0)
     X = X.numpy().astype(np.float64)
     Y = O.one_hot(y.numpy(), wl["K"])
@@ -232,6 +248,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     per_step = []
+    use_all_host_threads()
     from oracle import hamiltonian_oracle as O
     X, y = synth(wl["N"], wl["D"], wl["K"], 0)
     X = X.numpy().astype(np.float64)
@@ -283,6 +300,7 @@ def run_ours(args, wl):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     N, D, K, C = wl["N"], wl["D"], wl["K"], wl["C"]
