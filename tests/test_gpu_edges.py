@@ -1,0 +1,76 @@
+"""GPU (B200): edge shapes and error behaviour of the model entry points, through the C ABI.
+The reference has no error convention beyond Python exceptions; the ABI returns negative codes that the
+Python mirror raises as BhmcError -- never a silent fallback."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hamiltonian_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from dropout_hamiltonian_montecarlo_b200._lib import BhmcError  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.runtime import SoftmaxHandle, default_context  # noqa: E402
+
+
+def _case(N, D, K, C, seed):
+    rs = np.random.RandomState(seed)
+    X = rs.rand(N, D).astype(np.float32)
+    y = rs.randint(0, K, N).astype(np.int32)
+    q = rs.normal(0, .2, (C, (D + 1) * K)).astype(np.float32)
+    return X, y, q
+
+
+def _check(h, X, y, q, r0, n, prec, alpha, rtol, scale):
+    D, K = X.shape[1], h.K
+    g, ll = h.grad(h.pack(q), r0, n, prec)
+    g = g[:, :h.P].cpu().numpy().astype(np.float64)
+    ll = ll.cpu().numpy()
+    for c in range(q.shape[0]):
+        par = {"weights": q[c, :D * K].reshape(D, K).astype(np.float64), "bias": q[c, D * K:].astype(np.float64)}
+        Xs, Ys = X[r0:r0 + n].astype(np.float64), O.one_hot(y[r0:r0 + n], K)
+        ref = O.flatten_par(O.softmax_grad(par, Xs, Ys, alpha), ["weights", "bias"])
+        atol = scale * max(1.0, float(np.abs(ref).max()))
+        np.testing.assert_allclose(g[c], ref, rtol=rtol, atol=atol, err_msg="N=%d D=%d K=%d prec=%d" % (n, D, K, prec))
+        np.testing.assert_allclose(ll[c], O.softmax_log_likelihood(par, Xs, Ys), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("N,D,K,C", [(1, 5, 3, 1), (130, 3, 2, 3), (257, 70, 64, 2), (64, 784, 10, 1), (1000, 9, 38, 5),
+                                     (129, 65, 11, 7)])
+def test_edge_shapes(N, D, K, C):
+    """one row, tiny feature counts, the largest class count of the tensor path, class counts that need padding,
+    row counts one past a tile"""
+    X, y, q = _case(N, D, K, C, 3)
+    h = SoftmaxHandle(default_context(), N, D, K, 0.01)
+    h.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda())
+    _check(h, X, y, q, 0, N, 0, 0.01, 2e-5, 2e-6)
+    _check(h, X, y, q, 0, N, 1, 0.01, 1e-4, 2e-5)
+    if N > 2:
+        _check(h, X, y, q, 1, N - 2, 1, 0.01, 1e-4, 2e-5)
+
+
+def test_more_classes_than_the_tensor_path_supports():
+    N, D, K = 200, 12, 65
+    X, y, q = _case(N, D, K, 2, 4)
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, N, D, K, 0.01)
+    with pytest.raises(BhmcError):
+        h.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda(), 0b111)
+    h2 = SoftmaxHandle(ctx, N, D, K, 0.01)
+    h2.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda(), 0b001)  # the fp32 path has no such limit
+    _check(h2, X, y, q, 0, N, 0, 0.01, 2e-5, 2e-6)
+    with pytest.raises(BhmcError):  # ... and a tensor precision that was not prepared is an error, not a fallback
+        h2.grad(h2.pack(q), 0, N, 1)
+
+
+def test_row_window_outside_the_bound_rows():
+    N, D, K = 300, 10, 4
+    X, y, q = _case(N, D, K, 2, 5)
+    h = SoftmaxHandle(default_context(), N, D, K, 0.01)
+    h.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda())
+    for prec in (0, 1):
+        with pytest.raises(BhmcError):
+            h.grad(h.pack(q), 200, 200, prec)
+        with pytest.raises(BhmcError):
+            h.grad(h.pack(q), -1, 10, prec)
+    _check(h, X, y, q, 200, 100, 1, 0.01, 1e-4, 2e-5)  # the handle is still usable after the errors
