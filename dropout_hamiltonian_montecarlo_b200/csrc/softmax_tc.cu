@@ -33,6 +33,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "internal.cuh"
 #include "philox.cuh"
@@ -719,9 +720,9 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const bool leader = rank == 0;
-  const int nmat = p.split3 ? 2 : 1;
+  const int na = p.split3 == 1 ? 2 : 1, nb = p.split3 ? 2 : 1;
   const int a_bytes = BM * BK * 2, bh_bytes = (p.BN / 2) * BK * 2;
-  const int stage_bytes = nmat * (a_bytes + bh_bytes);
+  const int stage_bytes = na * a_bytes + nb * bh_bytes;
   const int m_pairs = p.m_tiles / 2;  // p.m_tiles is even; an odd last tile is the "left" work below
   const int per_split = m_pairs * p.n_tiles;
   const int num_main = p.n_split * per_split;
@@ -771,7 +772,7 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
           if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
-          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + nmat * a_bytes;
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + na * a_bytes;
           int ak = p.a_k0 + k * BK, am = p.a_m0 + mt * BM, bk = k * BK, bn = nt * p.BN + rank * (p.BN / 2);
           if (p.a_slab) {
             const int sl = ak / p.a_slab;
@@ -784,7 +785,7 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             bn += sl * p.b_slab_rows;
           }
           tma_load_2d_2sm(sa, &tmA_hi, full, ak, am);
-          if (p.split3) tma_load_2d_2sm(sa + a_bytes, &tmA_lo, full, ak, am);
+          if (na == 2) tma_load_2d_2sm(sa + a_bytes, &tmA_lo, full, ak, am);
           tma_load_2d_2sm(sb, &tmB_hi, full, bk, bn);
           if (p.split3) tma_load_2d_2sm(sb + bh_bytes, &tmB_lo, full, bk, bn);
           if (p.prefetch && k + p.prefetch < k_end) {  // pull a later chunk of this item's operands into L2
@@ -801,7 +802,7 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
               pbn += sl * p.b_slab_rows;
             }
             tma_prefetch_2d(&tmA_hi, pak, pam);
-            if (p.split3) tma_prefetch_2d(&tmA_lo, pak, pam);
+            if (na == 2) tma_prefetch_2d(&tmA_lo, pak, pam);
             tma_prefetch_2d(&tmB_hi, pbk, pbn);
             if (p.split3) tma_prefetch_2d(&tmB_lo, pbk, pbn);
           }
@@ -837,7 +838,7 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             if (p.prof) t_full += c2 - c1, ++n_chunks;
             const uint32_t sa = smem_base + stage * stage_bytes;
             const uint32_t first = (k > kb) ? 1u : 0u;
-            if (p.split3) {
+            if (p.split3 == 1) {
               const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
               const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + bh_bytes);
 #pragma unroll
@@ -846,6 +847,15 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                 umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
                 umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
                 umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            } else if (p.split3 == 2) {  // X^T exact in bf16: no lo copy staged, 2 MMAs per product
+              const uint64_t a_hi = make_smem_desc(sa);
+              const uint64_t b_hi = make_smem_desc(sa + a_bytes), b_lo = make_smem_desc(sa + a_bytes + bh_bytes);
+#pragma unroll
+              for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+                umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+                umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
               }
             } else {
               const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
@@ -1213,6 +1223,35 @@ static EncodeTiledFn get_encode_fn() {
 // bf16 matrix [outer, inner] (inner contiguous, row stride in elements), box = [box_outer, 64], 128B swizzle
 static int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
                     uint32_t box_outer) {
+  // The same few maps are rebuilt for every evaluation (X, X^T and the scratch operands keep their addresses; a row
+  // window is a kernel parameter, not part of the map).  Minibatch steps last ~45 us with three launches, so eight
+  // driver calls per step are a visible share of the host time: keep the encoded maps (BHMC_MAP_CACHE=0 disables).
+  struct Key {
+    const void* base;
+    uint64_t inner, outer, stride;
+    uint32_t box;
+    bool operator==(const Key& o) const {
+      return base == o.base && inner == o.inner && outer == o.outer && stride == o.stride && box == o.box;
+    }
+  };
+  struct Entry {
+    Key k;
+    CUtensorMap m;
+  };
+  static thread_local std::vector<Entry> cache;
+  static int cache_env = -1;
+  if (cache_env < 0) {
+    const char* e = getenv("BHMC_MAP_CACHE");
+    cache_env = e ? atoi(e) : 1;
+  }
+  const Key key{base, inner, outer, row_stride_elems, box_outer};
+  if (cache_env) {
+    for (const Entry& e : cache)
+      if (e.k == key) {
+        *m = e.m;
+        return BHMC_OK;
+      }
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
@@ -1230,6 +1269,10 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t o
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu stride=%llu box=%u", (int)r, base,
               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_elems, box_outer);
     return BHMC_ERR_CUDA;
+  }
+  if (cache_env) {
+    if (cache.size() >= 64) cache.clear();  // a map only describes addresses and shapes: a stale entry is never wrong
+    cache.push_back(Entry{key, *m});
   }
   return BHMC_OK;
 }
@@ -1477,7 +1520,7 @@ static int launch_fwd2_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
 
 static int launch_bwd2(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                        const CUtensorMap& b_lo, const TcParams& p) {
-  const int stage_bytes = (p.split3 ? 2 : 1) * (BM * BK * 2 + (p.BN / 2) * BK * 2);
+  const int stage_bytes = (p.split3 == 1 ? 2 : 1) * BM * BK * 2 + (p.split3 ? 2 : 1) * (p.BN / 2) * BK * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   static size_t configured = 0;
   if (smem > configured) {
@@ -1753,7 +1796,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     bwd2_env = e ? atoi(e) : 0;
   }
   // (measured at cfg2: faster from ~3 N tiles on; launches that carry few chains are better off with more row slabs)
-  const bool use_bwd2 = bwd2_env && smode != 2 && pairing_enabled() && m_tiles_all >= 2 && k_chunks_b >= 64 && BN % 16 == 0 &&
+  const bool use_bwd2 = bwd2_env && pairing_enabled() && m_tiles_all >= 2 && k_chunks_b >= 64 && BN % 16 == 0 &&
                         (n_tiles >= 3 || bwd2_env >= 2);
   const int m2 = use_bwd2 ? 2 * (m_tiles_all / 2) : 0;   // row tiles handled pairwise by k_tc_bwd2
   const int m_left = use_bwd2 ? m_tiles_all - m2 : 0;    // odd last tile: extra work items of the same launch
@@ -1794,7 +1837,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     b2.m_tiles = m2;
     b2.a_m0 = 0;
     b2.pair = 3;
-    const int st_bytes = nmat * (BM * BK * 2 + (BN / 2) * BK * 2);
+    const int st_bytes = na * BM * BK * 2 + nmat * (BN / 2) * BK * 2;
     b2.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / st_bytes)));
     static int pf_env = -1;  // BHMC_PF: L2 prefetch distance of the pair kernel in chunks
     if (pf_env < 0) {
@@ -1861,13 +1904,10 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     if (m2) {
       BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, BM));
       BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)(BN / 2)));
-      if (split3) {
-        BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, BM));
-        BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)(BN / 2)));
-      } else {
-        a_lo = a_hi;
-        b_lo = b_hi;
-      }
+      a_lo = a_hi;
+      b_lo = b_hi;
+      if (smode == 1) BHMC_TRY(make_map(&a_lo, d.Xt_lo, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, BM));
+      if (split3) BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)(BN / 2)));
       BHMC_TRY(launch_bwd2(ctx, a_hi, a_lo, b_hi, b_lo, b2));
     }
     if (m1) {

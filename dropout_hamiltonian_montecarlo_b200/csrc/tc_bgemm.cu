@@ -13,6 +13,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "internal.cuh"
 #include "philox.cuh"
@@ -352,6 +353,27 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 [Z][R][Kp] (K contiguous), box [1][box_rows][64], 128B swizzle, OOB rows / k read as zero
 static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, uint64_t Z, uint64_t Kp, uint32_t box_rows) {
+  // an encoded map is a pure function of these arguments and the scratch operands keep their addresses: the 20 driver
+  // calls per MLP evaluation are served from a small cache (BHMC_MAP_CACHE=0 disables)
+  struct Entry {
+    const void* base;
+    uint64_t K, R, Z, Kp;
+    uint32_t box;
+    CUtensorMap m;
+  };
+  static thread_local std::vector<Entry> cache;
+  static int cache_env = -1;
+  if (cache_env < 0) {
+    const char* e = getenv("BHMC_MAP_CACHE");
+    cache_env = e ? atoi(e) : 1;
+  }
+  if (cache_env) {
+    for (const Entry& e : cache)
+      if (e.base == base && e.K == K && e.R == R && e.Z == Z && e.Kp == Kp && e.box == box_rows) {
+        *m = e.m;
+        return BHMC_OK;
+      }
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -368,6 +390,10 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, u
     set_error("cuTensorMapEncodeTiled(3d) failed (%d): K=%llu R=%llu Z=%llu Kp=%llu box=%u", (int)r, (unsigned long long)K,
               (unsigned long long)R, (unsigned long long)Z, (unsigned long long)Kp, box_rows);
     return BHMC_ERR_CUDA;
+  }
+  if (cache_env) {
+    if (cache.size() >= 64) cache.clear();
+    cache.push_back(Entry{base, K, R, Z, Kp, box_rows, *m});
   }
   return BHMC_OK;
 }
