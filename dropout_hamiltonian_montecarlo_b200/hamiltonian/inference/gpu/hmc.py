@@ -169,6 +169,15 @@ class hmc(_ChainSampler):
         a = float(a[0]) if squeeze else a
         return q, p, [state], [None], a
 
+    def find_reasonable_epsilon(self, p_accept, **args):
+        """hmc.py:122-130: the dual-averaging update of ``DualAveragingStepSize.update`` written against attributes
+        (``self.t``, ``self.mu`` ...) that the reference's ``hmc`` never sets, so calling it there raises
+        AttributeError.  Here the same recurrence runs on a ``DualAveragingStepSize`` created on first use from the
+        current step size -> (noisy step size, averaged step size)."""
+        if getattr(self, "_dual_avg", None) is None:
+            self._dual_avg = DualAveragingStepSize(self.step_size)
+        return self._dual_avg.update(p_accept)
+
     def backend_mean(self, multi_backend, niter, ncores=None):
         """hmc.py:132-138 over the files written by ``sample(backend=...)``."""
         from ...sink import backend_mean

@@ -38,6 +38,17 @@ class sghmc(_ChainSampler):
         u2 = np.random.rand()
         return z, np.array([[u1]]), np.array([[u2]]), zn
 
+    def lr_schedule(self, initial_step_size, step, decay_factor, num_batches):
+        """sgmcmc.py:88-89 (the reference's sghmc inherits it from sgmcmc)."""
+        return initial_step_size * (1.0 / (1.0 + step * decay_factor * num_batches))
+
+    def iterate_minibatches(self, X, y, batchsize):
+        """sgmcmc.py:34-38 (inherited from sgmcmc in the reference)."""
+        assert X.shape[0] == y.shape[0]
+        for start_idx in range(0, X.shape[0] - batchsize + 1, batchsize):
+            excerpt = slice(start_idx, start_idx + batchsize)
+            yield X[excerpt], y[excerpt]
+
     def step(self, state, momentum, rng, **args):
         """sghmc.py:19-39 -> (q, p, acceptprob)."""
         saved = self.start

@@ -14,6 +14,13 @@ from .sgmcmc import sgmcmc
 class sgld(sgmcmc):
     kind = "sgld"
 
+    def step2(self, state, momentum, rng, **args):
+        """sgld.py:15-29 is dead code in the reference: it reads the undefined names ``n_batch`` and ``norm`` and raises
+        NameError when called; ``sample`` only ever calls ``step``.  Kept so that the attribute exists, with the same
+        outcome (an exception) and a message that says why."""
+        raise NameError("sgld.step2 is not runnable in the reference either (undefined n_batch / norm, sgld.py:27); "
+                        "use sgld.step")
+
     def step(self, state, momentum, rng, **args):
         """One SGLD update on the batch passed as X_train / y_train -> (q, p)."""
         saved = self.start

@@ -136,3 +136,25 @@ def test_sgd_fit_dropout_live():
     opar, oloss = O.sgd_fit_dropout(O.SoftmaxOracle({"alpha": 0.1}), start, 5e-3, 3, 50, 0.9, X, Y, masks)
     np.testing.assert_allclose(opar["weights"], par["weights"], rtol=1e-10, atol=1e-13)
     np.testing.assert_allclose(oloss, loss, rtol=1e-12)
+
+
+def test_public_api_surface_matches_the_reference():
+    """Every public method of the reference's hot-path classes exists on the drop-in classes with the same leading
+    positional parameters (module paths hamiltonian.inference.gpu.* / hamiltonian.models.gpu.*)."""
+    import importlib
+    import inspect
+    load_reference()  # applies the compatibility shim and puts the reference tree on sys.path
+    pairs = [("hamiltonian.inference.cpu.hmc", "hmc", "inference.gpu.hmc"), ("hamiltonian.inference.cpu.sgld", "sgld", "inference.gpu.sgld"),
+             ("hamiltonian.inference.cpu.sghmc", "sghmc", "inference.gpu.sghmc"), ("hamiltonian.inference.cpu.sgd", "sgd", "inference.gpu.sgd"),
+             ("hamiltonian.models.cpu.softmax", "softmax", "models.gpu.softmax"), ("hamiltonian.models.cpu.logistic", "logistic", "models.gpu.logistic"),
+             ("hamiltonian.models.cpu.mvn_gaussian", "mvn_gaussian", "models.gpu.mvn_gaussian")]
+    for ref_mod, cls, ours_mod in pairs:
+        R = getattr(importlib.import_module(ref_mod), cls)
+        Ours = getattr(importlib.import_module("dropout_hamiltonian_montecarlo_b200.hamiltonian." + ours_mod), cls)
+        ref_methods = dict(inspect.getmembers(R, inspect.isfunction))
+        our_methods = dict(inspect.getmembers(Ours, inspect.isfunction))
+        for name, fn in ref_methods.items():
+            assert name in our_methods, "%s.%s is missing" % (cls, name)
+            want = [p.name for p in inspect.signature(fn).parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+            got = [p.name for p in inspect.signature(our_methods[name]).parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+            assert got[:len(want)] == want, "%s.%s%s vs reference %s" % (cls, name, got, want)
