@@ -328,11 +328,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();
   tcgen05_fence_before();
   if (p.pair) cluster_sync_all();  // peer barriers must be initialised before anything is multicast into them
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above touched only shared / tensor memory
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -594,10 +596,12 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above touched only shared / tensor memory
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
@@ -754,10 +758,12 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();
   tcgen05_fence_before();
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above touched only shared / tensor memory
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer (both CTAs) =====
@@ -1019,6 +1025,7 @@ __global__ void k_split_transpose(const float* __restrict__ X, int64_t N, int D,
 __global__ void k_tc_prep(const float* __restrict__ q, int64_t ld, int D, int K, int KP, int64_t Dp,
                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, double* __restrict__ loglik,
                           float wscale) {
+  pdl_launch_dependents();
   int c = blockIdx.y;
   if (blockIdx.x == 0 && threadIdx.x == 0 && loglik) loglik[c] = 0.0;
   int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1067,6 +1074,7 @@ __device__ __forceinline__ float sum_partials(const PartRegions& r, int64_t d, i
 
 __global__ void k_tc_reduce(PartRegions r, int K, int KP, int64_t P, const float* __restrict__ q, float* __restrict__ g,
                             int64_t ld, float alpha) {
+  pdl_launch_dependents();
   int c = blockIdx.y;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ld) return;
@@ -1088,6 +1096,7 @@ __global__ void __launch_bounds__(256)
 k_tc_reduce_step(PartRegions r, int D, int K, int KP, int64_t P,
                  int64_t ld, float alpha, FusedStep fs, int64_t Dp, __nv_bfloat16* __restrict__ wt_hi,
                  __nv_bfloat16* __restrict__ wt_lo, double* __restrict__ loglik) {
+  pdl_launch_dependents();
   const int c = blockIdx.y;
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i == 0 && loglik) loglik[c] = 0.0;  // for the next forward pass
@@ -1158,6 +1167,7 @@ __global__ void __launch_bounds__(256)
 k_tc_reduce_stream(PartRegions r, int D, int K, int KP, int64_t P, int64_t ld, float alpha, float* __restrict__ g,
                    StreamUpdateArgs u, int prep_next, int64_t Dp, __nv_bfloat16* __restrict__ wt_hi,
                    __nv_bfloat16* __restrict__ wt_lo, double* __restrict__ loglik) {
+  pdl_launch_dependents();
   const int c = blockIdx.y;
   const uint32_t op = u.code[c];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1435,6 +1445,18 @@ void tc_softmax_release(SoftmaxData& d) {
   d.tc_ready = false;
 }
 
+// The GEMM kernels are launched with programmatic stream serialization (see tc_common.cuh): their prologue overlaps the
+// tail of the kernel before them.  Measured: cfg3 SGLD 49.7 / 48.4 -> 43.3 / 43.1 us per minibatch step, cfg2 170.9 k ->
+// 173.6 k grad-evals/s; parity suite green either way.  BHMC_PDL=0 launches them plainly (A/B measurements).
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BHMC_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 // BHMC_PAIR=0 disables the CTA-pair multicast (debug / A-B comparison)
 static bool pairing_enabled() {
   static int v = -1;
@@ -1475,13 +1497,15 @@ static int launch_gemm_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
   cfg.blockDim = dim3(NON_EPI_THREADS + 32 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, KP, EW, EXACT>, a_hi, a_lo, b_hi, b_lo, p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
@@ -1505,13 +1529,15 @@ static int launch_fwd2_ew(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensor
   cfg.blockDim = dim3(NON_EPI_THREADS + 32 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_fwd2<KP, EW, EXACT>, a_hi, a_lo, b_hi, b_lo, p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
@@ -1534,13 +1560,15 @@ static int launch_bwd2(bhmc_ctx* ctx, const CUtensorMap& a_hi, const CUtensorMap
   cfg.blockDim = dim3(NON_EPI_THREADS + 32 * 16);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bwd2<16>, a_hi, a_lo, b_hi, b_lo, p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());

@@ -102,6 +102,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+// Programmatic dependent launch (the GEMM launches carry the attribute unless BHMC_PDL=0): a kernel lets the next one
+// in the stream start its prologue (barrier init, TMEM allocation) early, and must itself not touch global memory
+// before pdl_wait(), which returns once every preceding grid has completed and its writes are visible.  Without the
+// launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // tcgen05.mma / tcgen05.commit are issued by ONE elected lane of a converged warp (the commit tracks the MMAs
 // issued by the same thread; elect.sync returns the same leader for the full mask every time).
