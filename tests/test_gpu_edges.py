@@ -74,3 +74,32 @@ def test_row_window_outside_the_bound_rows():
         with pytest.raises(BhmcError):
             h.grad(h.pack(q), -1, 10, prec)
     _check(h, X, y, q, 200, 100, 1, 0.01, 1e-4, 2e-5)  # the handle is still usable after the errors
+
+
+@pytest.mark.parametrize("sched", ["lockstep", "streaming"])
+def test_grad_hook_path_matches_the_fused_path(sched):
+    """The row-shard all-reduce hook (a no-op with one rank) forces the unfused launch sequence -- separate split-K
+    reduce, update and operand preparation: same draws, same decisions, samples equal to fp32 round-off."""
+    from dropout_hamiltonian_montecarlo_b200.parallel import RowShardHook
+    from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle
+    rs = np.random.RandomState(12)
+    N, D, K, C, n_steps = 700, 50, 10, 6, 3
+    X, y, _ = _case(N, D, K, C, 12)
+    q0 = rs.normal(0, .1, (C, (D + 1) * K)).astype(np.float32)
+    h = SoftmaxHandle(default_context(), N, D, K, 0.01)
+    h.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda())
+    z = torch.as_tensor(rs.normal(size=(n_steps, C, h.P)), dtype=torch.float32)
+    u1, u2 = rs.rand(n_steps, C), rs.rand(n_steps, C)
+    outs = []
+    for with_hook in (False, True):
+        s = SamplerHandle(h.ctx, h, 0, C, precision=1)
+        hook = RowShardHook(s) if with_hook else None
+        s.set_q(q0)
+        o = s.hmc_run(n_steps, 5e-4, 4e-3, z_momentum=z, u_path=u1, u_accept=u2, schedule=sched)
+        outs.append((o["samples"].cpu().numpy(), o["accept_prob"].cpu().numpy(), o["n_grad_evals"]))
+        if with_hook:
+            assert hook.calls > 0
+    (s0, a0, n0), (s1, a1, n1) = outs
+    assert n0 == n1
+    np.testing.assert_allclose(a1, a0, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(s1, s0, rtol=1e-5, atol=1e-6)
