@@ -24,8 +24,10 @@ def install_as_hamiltonian():
 
     root = importlib.import_module(__name__ + ".hamiltonian")
     sys.modules["hamiltonian"] = root
-    for sub in ("utils", "models", "models.gpu", "models.gpu.softmax", "models.gpu.mvn_gaussian", "models.gpu.mlp",
-                "inference", "inference.gpu", "inference.gpu.hmc", "inference.gpu.sgmcmc",
-                "inference.gpu.sgld", "inference.gpu.sghmc", "inference.gpu.sgd"):
-        sys.modules["hamiltonian." + sub] = importlib.import_module(__name__ + ".hamiltonian." + sub)
+    import pkgutil
+
+    # every module of the tree, discovered rather than listed (a hand-kept list once missed models.gpu.logistic)
+    for info in pkgutil.walk_packages(root.__path__, root.__name__ + "."):
+        mod = importlib.import_module(info.name)
+        sys.modules["hamiltonian." + info.name[len(root.__name__) + 1:]] = mod
     return root

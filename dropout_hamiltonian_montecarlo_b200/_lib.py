@@ -50,6 +50,7 @@ class SgRun(C.Structure):
         ("z_dev", C.c_void_p), ("samples_dev", C.c_void_p), ("logp_dev", C.c_void_p),
         ("n_grad_evals", C.c_int64), ("final_step_size", C.c_double),
         ("dropout_keep", C.c_double), ("mask_dev", C.c_void_p),
+        ("first_step_size", C.c_double), ("keep_momentum", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -105,6 +106,15 @@ _PROTOS = {
     "bhmc_sampler_get": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "bhmc_sampler_hmc_run": (C.c_int, [C.c_void_p, C.POINTER(HmcRun)]),
     "bhmc_sampler_sg_run": (C.c_int, [C.c_void_p, C.POINTER(SgRun)]),
+    "bhmc_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "bhmc_comm_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bhmc_comm_wrap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "bhmc_comm_destroy": (C.c_int, [C.c_void_p]),
+    "bhmc_comm_world": (C.c_int32, [C.c_void_p]),
+    "bhmc_nccl_version": (C.c_int, []),
+    "bhmc_allreduce_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "bhmc_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "bhmc_sampler_set_row_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bhmc_stream_plan_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64),
                                         C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libbhmc.so")
-SOURCES = ["capi.cu", "update.cu", "softmax_simt.cu", "softmax_tc.cu", "mlp.cu", "tc_bgemm.cu"]
+SOURCES = ["capi.cu", "update.cu", "softmax_simt.cu", "softmax_tc.cu", "mlp.cu", "tc_bgemm.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
         list(ex.map(compile_one, jobs))
     if jobs or not os.path.exists(LIB):
         r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                                   "-cudart", "static"],
+                                                                   "-cudart", "static", "-ldl"],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])

@@ -674,17 +674,19 @@ struct bhmc_sampler {
   int32_t* Ldev = nullptr;
   bhmc_grad_hook hook = nullptr;
   void* hook_user = nullptr;
+  bhmc_comm* row_comm = nullptr;  // rows sharded over ranks: all-reduce after every evaluation (comm.cu)
   // gradient (or log-lik only when g == nullptr) of the first `rows` working rows, then the optional hook
   // evaluation whose reduce launch also runs the streaming schedule's next update; BHMC_ERR_UNSUPPORTED = not fused
   int eval_fused_stream(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat, uint32_t hint,
                         const FusedStream& fst) {
-    if (hook) return BHMC_ERR_UNSUPPORTED;  // the row-shard all-reduce must see g before any update uses it
+    if (hook || row_comm) return BHMC_ERR_UNSUPPORTED;  // the row-shard all-reduce must see g before any update uses it
     ctx->cur_units = rows;
     return model->grad_fused_stream(q, rows, ld, row0, nrows, cfg.precision, g, stat, hint, fst);
   }
   int eval(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat, uint32_t hint = 0) {
     ctx->cur_units = rows;
     BHMC_TRY(model->grad(q, rows, ld, row0, nrows, cfg.precision, g, stat, hint));
+    if (row_comm) BHMC_TRY(bhmc_comm_allreduce(row_comm, g, g ? (int64_t)rows * ld : 0, stat, rows));
     if (hook && hook(hook_user, g, stat, rows, ld) != 0) {
       bhmc::set_error("gradient hook reported a failure");
       return BHMC_ERR_STATE;
@@ -751,6 +753,12 @@ int bhmc_sampler_set_grad_hook(bhmc_sampler* s, bhmc_grad_hook hook, void* user)
   BHMC_CHECK_ARG(s, "sampler is NULL");
   s->hook = hook;
   s->hook_user = user;
+  return BHMC_OK;
+}
+
+int bhmc_sampler_set_row_comm(bhmc_sampler* s, bhmc_comm* comm) {
+  BHMC_CHECK_ARG(s, "sampler is NULL");
+  s->row_comm = comm;
   return BHMC_OK;
 }
 
@@ -913,7 +921,6 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
   stream_plan_order(L.data(), C, n_steps, nsw, &pl);
   run->n_grad_evals = pl.n_grad_evals;
   const int64_t J = pl.J;
-  BHMC_CHECK_ARG(J < (1LL << 24), "run too long for one call (%lld phases): lower n_steps", (long long)J);
   const size_t n_ops = (size_t)(J + 1) * C;
   const size_t code_bytes = round_up(sizeof(uint32_t) * n_ops, 64), perm_bytes = round_up(sizeof(int32_t) * C, 64);
   const size_t u_bytes = sizeof(double) * (size_t)n_steps * C;
@@ -1218,7 +1225,55 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
     const bool can_stream = !sghmc && C > 1;
     if (sched == BHMC_SCHED_AUTO) sched = (can_stream && !cfg.shared_path && n_steps >= 2) ? BHMC_SCHED_STREAMING : BHMC_SCHED_LOCKSTEP;
     BHMC_CHECK_ARG(sched != BHMC_SCHED_STREAMING || !sghmc, "the streaming schedule is implemented for HMC only");
-    if (sched == BHMC_SCHED_STREAMING) return hmc_run_streaming(s, run, Lraw);
+    if (sched == BHMC_SCHED_STREAMING) {
+      // The op tables hold 16 bytes per (phase, row) in pinned memory and again on the device; a long call at a small
+      // step size (many leapfrog iterations per transition) must not turn into multi-GB allocations or an error:
+      // over the budget the call is cut into consecutive streaming sub-calls (draws are keyed by the absolute step
+      // index, so the samples are the same), and a single transition that alone exceeds it runs in lockstep, which
+      // needs no table.  BHMC_STREAM_OPS_MAX overrides the budget (tests).
+      static int64_t ops_max = 0;
+      if (!ops_max) {
+        const char* e = getenv("BHMC_STREAM_OPS_MAX");
+        ops_max = e ? std::max<int64_t>(1, atoll(e)) : ((int64_t)4 << 20);
+      }
+      StreamPlan pl;
+      stream_plan_order(Lraw.data(), C, n_steps, nsw, &pl);
+      if ((pl.J + 1) * (int64_t)C <= ops_max) return hmc_run_streaming(s, run, Lraw);
+      std::vector<int64_t> T(C);
+      int64_t tot_evals = 0, tot_launched = 0, tot_phases = 0;
+      int t0 = 0;
+      while (t0 < n_steps) {
+        std::fill(T.begin(), T.end(), 1);
+        int m = 0;
+        for (int t = t0; t < n_steps; ++t, ++m) {
+          int64_t mx = 0;
+          for (int c = 0; c < C; ++c) mx = std::max(mx, T[c] + stream_slots(Lraw[(size_t)t * C + c], nsw));
+          if ((mx + 1) * (int64_t)C > ops_max) break;
+          for (int c = 0; c < C; ++c) T[c] += stream_slots(Lraw[(size_t)t * C + c], nsw);
+        }
+        bhmc_hmc_run sub = *run;
+        sub.n_steps = std::max(m, 1);
+        sub.schedule = m >= 2 ? BHMC_SCHED_STREAMING : BHMC_SCHED_LOCKSTEP;
+        sub.step0 = run->step0 + t0;
+        const size_t oc = (size_t)t0 * C, op = oc * (size_t)P;
+        if (run->z_momentum_dev) sub.z_momentum_dev = run->z_momentum_dev + op;
+        if (run->u_path_host) sub.u_path_host = run->u_path_host + oc;
+        if (run->u_accept_host) sub.u_accept_host = run->u_accept_host + oc;
+        if (run->samples_dev) sub.samples_dev = run->samples_dev + op;
+        if (run->loss_dev) sub.loss_dev = run->loss_dev + oc;
+        if (run->accept_prob_dev) sub.accept_prob_dev = run->accept_prob_dev + oc;
+        if (run->accepted_dev) sub.accepted_dev = run->accepted_dev + oc;
+        BHMC_TRY(bhmc_sampler_hmc_run(s, &sub));
+        tot_evals += sub.n_grad_evals;
+        tot_launched += sub.n_grad_launched;
+        tot_phases += sub.n_phases;
+        t0 += sub.n_steps;
+      }
+      run->n_grad_evals = tot_evals;
+      run->n_grad_launched = tot_launched;
+      run->n_phases = (int32_t)std::min<int64_t>(tot_phases, INT32_MAX);
+      return BHMC_OK;
+    }
   }
   bool ragged = false;
   run->n_grad_evals = 0;
@@ -1427,10 +1482,14 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
   const double num_batches = std::ceil((double)n_rows / (double)run->batch_size);  // sgmcmc.py:50
   const double decay = run->step_size / num_batches;                                // sgmcmc.py:51
   double* stat = s->scal;
-  double eps = run->step_size;
+  double eps = run->first_step_size > 0.0 ? run->first_step_size : run->step_size;
   int64_t k = 0;  // global minibatch counter (indexes the injected tape and the Philox stream)
   run->n_grad_evals = 0;
   const bool sgd = cfg.kind == BHMC_KIND_SGD;
+  // sgd.py:35,57: every fit() / fit_dropout() call starts from momentum = zeros_like(par); the sampler object (and
+  // its momentum buffer) outlives the call, so it is cleared here unless the caller chains calls on purpose
+  if (sgd && !run->keep_momentum)
+    BHMC_CUDA_OK(cudaMemsetAsync(s->p, 0, sizeof(float) * (size_t)C * ld, ctx->stream));
   // fused gradient + update + next operand preparation (tensor-core softmax path, single GPU): 3 launches per
   // minibatch instead of 5.  BHMC_FUSED_STEP=0 keeps the separate kernels (A/B measurements).
   static int fused_env = -1;
@@ -1438,7 +1497,7 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
     const char* e = getenv("BHMC_FUSED_STEP");
     fused_env = e ? atoi(e) : 1;
   }
-  bool try_fused = fused_env && !s->hook && !(run->dropout_keep > 0.0);
+  bool try_fused = fused_env && !s->hook && !s->row_comm && !(run->dropout_keep > 0.0);
   bool wt_ready = false;
   for (int e = 0; e < run->burnin + run->epochs; ++e) {
     const bool sampling = e >= run->burnin;
@@ -1469,7 +1528,7 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
         try_fused = false;
       }
       if (run->dropout_keep > 0.0) {
-        BHMC_CHECK_ARG(sgd && !s->hook, "input dropout is sgd.fit_dropout only (single GPU)");
+        BHMC_CHECK_ARG(sgd && !s->hook && !s->row_comm, "input dropout is sgd.fit_dropout only (single GPU)");
         const uint8_t* mk = run->mask_dev ? run->mask_dev + (size_t)k * run->batch_size * mb->n_features() : nullptr;
         BHMC_TRY(mb->grad_input_dropout(s->q, C, ld, row0, run->batch_size, cfg.precision, s->g, stat, mk,
                                         (float)run->dropout_keep, cfg.seed, (uint32_t)(run->step0 + k)));

@@ -55,8 +55,10 @@ enum : uint32_t {
   TAG_TEST = 0x7f000000u
 };
 
-// uniform in (0,1): 24 random bits, never 0 or 1 (safe under log)
-__host__ __device__ __forceinline__ float u01_open(uint32_t r) { return ((r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in (0,1): 23 random bits.  (k + 0.5) * 2^-23 with k < 2^23 is exact in fp32 (k + 0.5 needs 24 significant
+// bits), so the value is never 0 or 1 (safe under log) and every one of the 2^23 grid points is equally likely.
+// (With 24 bits, k + 0.5 is not representable for k >= 2^23: it rounded to even, and k = 2^24 - 1 gave exactly 1.0f.)
+__host__ __device__ __forceinline__ float u01_open(uint32_t r) { return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 // uniform in [0,1) with 53 bits, identical on host and device
 __host__ __device__ __forceinline__ double u01_double(uint32_t hi, uint32_t lo) {

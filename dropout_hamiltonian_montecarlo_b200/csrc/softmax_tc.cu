@@ -180,69 +180,149 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
   for (int cc = part; cc < p.cpt; cc += PARTS) {
     const int c = nt * p.cpt + cc;
     if (c >= p.C) break;  // warp-uniform
-    uint32_t raw[KP];
-    if constexpr (FROM_Z) {
-      const float* zp = p.zt + zt_off + (int64_t)c * KP * p.dm_ld;
-#pragma unroll
-      for (int k = 0; k < KP; ++k) raw[k] = (EXACT || k < K) ? __float_as_uint(__ldcs(zp + (int64_t)k * p.dm_ld)) : 0u;
-    } else {
-      tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
-    }
     const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
-    float bv[KP];
+    float ll;
+    if constexpr (KP >= 24 && !FROM_Z) {
+      // Wide class counts (KP = 24 / 40 / 64; cfg5 has K = 38): holding a whole row of logits (+ exps) per thread does
+      // not fit the 96-register budget of the 640-thread CTA and spilled (ptxas: 80-156 B at KP = 40, ~900 B at
+      // KP = 64).  Tensor memory is cheap to re-read, so the row is walked three times in 8-column pieces instead:
+      // max, sum of exps, then P - Y.  Twice the ex2 work, no local memory.
+      constexpr int CH = 8;
+      const uint32_t tcol = tacc + (uint32_t)(cc * KP);
+      float m = -INFINITY, zy = 0.f;
+      float* zp = p.zt ? p.zt + zt_off + (int64_t)c * KP * p.dm_ld : nullptr;
+#pragma unroll 1
+      for (int k0 = 0; k0 < KP; k0 += CH) {
+        uint32_t r8[CH];
+        tmem_ld<CH>(tcol + (uint32_t)k0, r8);
+        tmem_ld_wait();
 #pragma unroll
-    for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
-    if constexpr (!FROM_Z) {
-      tmem_ld_wait();
-      if (p.zt) {  // keep X.W for the next evaluation (streaming stores: read back once, by another kernel)
-        float* zp = p.zt + zt_off + (int64_t)c * KP * p.dm_ld;
-#pragma unroll
-        for (int k = 0; k < KP; ++k)
-          if (EXACT || k < K) __stcs(zp + (int64_t)k * p.dm_ld, __uint_as_float(raw[k]));
+        for (int j = 0; j < CH; ++j) {
+          const int k = k0 + j;
+          if (EXACT || k < K) {
+            if (zp) __stcs(zp + (int64_t)k * p.dm_ld, __uint_as_float(r8[j]));
+            const float v = fminf(__uint_as_float(r8[j]) + __ldg(bias + k), CLIP_HI);
+            m = fmaxf(m, v);
+            zy = (k == y) ? v : zy;
+          }
+        }
       }
-    }
-    float z[KP];
-    float m = -INFINITY, zy = 0.f;
+      zy = fmaxf(zy, CLIP_LO);
+      const bool all_low = m < CLIP_LO;  // every logit below the lower clip: the literal path (all classes at CLIP_LO)
+      if (all_low) m = CLIP_LO;
+      float ssum = 0.f;
+#pragma unroll 1
+      for (int k0 = 0; k0 < KP; k0 += CH) {
+        uint32_t r8[CH];
+        tmem_ld<CH>(tcol + (uint32_t)k0, r8);
+        tmem_ld_wait();
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      // softmax.py:40-41 clips to [-708.4, 36.04].  The lower clip only matters for the label's logit
-      // (exp(z - max) underflows to 0 in fp32 either way), so it is applied to zy alone below.
-      float v = fminf(__uint_as_float(raw[k]) + bv[k], CLIP_HI);
-      if (!EXACT && k >= K) v = -INFINITY;  // padded classes
-      z[k] = v;
-      m = fmaxf(m, v);
-      zy = (k == y) ? v : zy;
-    }
-    zy = fmaxf(zy, CLIP_LO);
-    if (m < CLIP_LO) {  // every logit below the lower clip (diverged chain): take the slow, literal path
-      m = CLIP_LO;
+        for (int j = 0; j < CH; ++j) {
+          const int k = k0 + j;
+          if (EXACT || k < K) {
+            const float v = all_low ? CLIP_LO : fminf(__uint_as_float(r8[j]) + __ldg(bias + k), CLIP_HI);
+            ssum += ex2_approx((v - m) * L2E);
+          }
+        }
+      }
+      const float inv = __fdividef(1.0f, ssum);
+      ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;
+      if (p.write_dm) {
+        const int64_t o = dm_off + (int64_t)c * KP * p.dm_ld;
+#pragma unroll 1
+        for (int k0 = 0; k0 < KP; k0 += CH) {
+          uint32_t r8[CH];
+          tmem_ld<CH>(tcol + (uint32_t)k0, r8);
+          tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < KP; ++k)
-        if (EXACT || k < K) z[k] = CLIP_LO;
-    }
-    float ssum = 0.f;
+          for (int j = 0; j < CH; ++j) {
+            const int k = k0 + j;
+            if (EXACT || k < K) {
+              const float v = all_low ? CLIP_LO : fminf(__uint_as_float(r8[j]) + __ldg(bias + k), CLIP_HI);
+              const float e = ex2_approx((v - m) * L2E);
+              const float d = valid ? fmaf(e, inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
+              const __nv_bfloat16 h = __float2bfloat16_rn(d);
+              p.dmt_hi[o + (int64_t)k * p.dm_ld] = h;
+              if (p.split3) p.dmt_lo[o + (int64_t)k * p.dm_ld] = __float2bfloat16_rn(d - __bfloat162float(h));
+            }
+          }
+        }
+      }
+    } else {
+      uint32_t raw[KP];
+      if constexpr (FROM_Z) {
+        const float* zp = p.zt + zt_off + (int64_t)c * KP * p.dm_ld;
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      z[k] = ex2_approx((z[k] - m) * L2E);  // exp(clip(z) - max); 0 for padded classes
-      ssum += z[k];
-    }
-    const float inv = __fdividef(1.0f, ssum);
-    float ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
-    if (p.write_dm) {
-      const int64_t o = dm_off + (int64_t)c * KP * p.dm_ld;
-      __nv_bfloat16* dh = p.dmt_hi + o;
-      __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
+        for (int k = 0; k < KP; ++k) raw[k] = (EXACT || k < K) ? __float_as_uint(__ldcs(zp + (int64_t)k * p.dm_ld)) : 0u;
+      } else {
+        tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
+      }
+      // Up to 16 classes the bias is fetched while the tcgen05.ld is in flight.  Wider class counts (KP = 24 / 40 / 64:
+      // cfg5's K = 38) would keep raw[KP] + bv[KP] live at once and spill under the 96-register budget of the
+      // 640-thread CTA (ptxas: 60-84 B at KP = 40), so there the bias is read where it is consumed (L1 hits).
+      constexpr bool PRELOAD_BIAS = KP <= 16;
+      float bv[PRELOAD_BIAS ? KP : 1];
+      if constexpr (PRELOAD_BIAS) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
+      }
+      if constexpr (!FROM_Z) {
+        tmem_ld_wait();
+        if (p.zt) {  // keep X.W for the next evaluation (streaming stores: read back once, by another kernel)
+          float* zp = p.zt + zt_off + (int64_t)c * KP * p.dm_ld;
+#pragma unroll
+          for (int k = 0; k < KP; ++k)
+            if (EXACT || k < K) __stcs(zp + (int64_t)k * p.dm_ld, __uint_as_float(raw[k]));
+        }
+      }
+      float z[KP];
+      float m = -INFINITY, zy = 0.f;
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
-        if (EXACT || k < K) {
-          float d = valid ? fmaf(z[k], inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
-          __nv_bfloat16 h = __float2bfloat16_rn(d);
-          *dh = h;
-          if (p.split3) *dl = __float2bfloat16_rn(d - __bfloat162float(h));
-        }
-        dh += p.dm_ld;
-        dl += p.dm_ld;
+        // softmax.py:40-41 clips to [-708.4, 36.04].  The lower clip only matters for the label's logit
+        // (exp(z - max) underflows to 0 in fp32 either way), so it is applied to zy alone below.
+        float bk;
+        if constexpr (PRELOAD_BIAS) bk = bv[k];
+        else bk = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
+        float v = fminf(__uint_as_float(raw[k]) + bk, CLIP_HI);
+        if (!EXACT && k >= K) v = -INFINITY;  // padded classes
+        z[k] = v;
+        m = fmaxf(m, v);
+        zy = (k == y) ? v : zy;
       }
+      zy = fmaxf(zy, CLIP_LO);
+      if (m < CLIP_LO) {  // every logit below the lower clip (diverged chain): take the slow, literal path
+        m = CLIP_LO;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+          if (EXACT || k < K) z[k] = CLIP_LO;
+      }
+      float ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        z[k] = ex2_approx((z[k] - m) * L2E);  // exp(clip(z) - max); 0 for padded classes
+        ssum += z[k];
+      }
+      const float inv = __fdividef(1.0f, ssum);
+      ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
+      if (p.write_dm) {
+        const int64_t o = dm_off + (int64_t)c * KP * p.dm_ld;
+        __nv_bfloat16* dh = p.dmt_hi + o;
+        __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          if (EXACT || k < K) {
+            float d = valid ? fmaf(z[k], inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
+            __nv_bfloat16 h = __float2bfloat16_rn(d);
+            *dh = h;
+            if (p.split3) *dl = __float2bfloat16_rn(d - __bfloat162float(h));
+          }
+          dh += p.dm_ld;
+          dl += p.dm_ld;
+        }
+      }
+    }
+    if (p.write_dm) {
       // zero what the backward chunks read but no row writes: the alignment prefix (columns before the window) and
       // the columns between the last tile row and the end of the last BK-chunk
       int zc = -1;
@@ -281,6 +361,116 @@ __global__ void __launch_bounds__(128, (KP <= 16 ? 12 : 4)) k_softmax_from_z(con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // blockIdx.x = chain (fastest): concurrently resident blocks spread their log-likelihood atomics over all chains
   fwd_epilogue_tile<KP, 4, EXACT, true>(p, 0u, (int)blockIdx.y, (int)blockIdx.x, 0, lane, warp * 32 + lane);  // p.cpt == 1
+}
+
+// Vectorised form of k_softmax_from_z (default).  The first version (thread = one row of one chain, scalar loads and
+// 2-byte stores) ran at 3.6 TB/s = 55 % of the copy peak and was ISSUE-bound (ncu r01: smsp issue active 80 %, 60 M warp
+// instructions per launch) -- per element: one 4-byte load, two 2-byte stores, address arithmetic and the class
+// predicates.  Here a thread owns VEC consecutive DmT columns (= window rows) of one chain: one 16-byte load per class
+// (VEC = 4), one 8-byte store per class and operand half, index arithmetic paid once per VEC rows.  It walks the DmT
+// COLUMNS (alignment prefix and chunk tail included: those get zeros), so no separate zero-fill is needed.
+// grid = (chains, column groups); block = 128 threads = 128 * VEC columns of one chain.
+template <int VEC> struct ZVec;
+template <> struct ZVec<4> { using f = float4; using h = uint2; };
+template <> struct ZVec<2> { using f = float2; using h = uint32_t; };
+template <int KP, bool EXACT, int VEC>
+__global__ void __launch_bounds__(128) k_softmax_from_z_vec(const TcParams p, int n_cols) {
+  using FV = typename ZVec<VEC>::f;
+  using HV = typename ZVec<VEC>::h;
+  static_assert(VEC % 2 == 0, "bf16 pairs");
+  // logits are kept in the log2 domain (x * log2 e): one FFMA adds the bias and scales, ex2 needs no multiply
+  const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const float HI2 = CLIP_HI * L2E, LO2 = CLIP_LO * L2E;
+  const int c = blockIdx.x;
+  const int K = EXACT ? KP : p.K;
+  const int col0 = ((int)blockIdx.y * 128 + (int)threadIdx.x) * VEC;  // first DmT column of this thread
+  float ll = 0.f;
+  if (col0 < n_cols) {
+    const int sl = col0 / p.dm_slab, cin = col0 - sl * p.dm_slab;  // dm_slab % 64 == 0 and col0 % VEC == 0: one slab
+    const float* zp = p.zt + ((int64_t)sl * p.zt_slab_rows + (int64_t)c * KP) * p.dm_ld + cin;
+    const int64_t doff = ((int64_t)sl * p.dm_slab_rows + (int64_t)c * KP) * p.dm_ld + cin;
+    const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
+    int y[VEC];
+    bool valid[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int r = col0 + j - p.dm_shift;
+      valid[j] = r >= 0 && r < p.nrows;
+      y[j] = valid[j] ? __ldg(p.labels + r) : -1;
+    }
+    FV raw[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {  // all loads of the thread in flight before the first use
+      if (EXACT || k < K) raw[k] = __ldcs(reinterpret_cast<const FV*>(zp));
+      zp += p.dm_ld;
+    }
+    float z[KP][VEC];
+    float m[VEC], zy[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) m[j] = -INFINITY, zy[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (EXACT || k < K) {
+        const float b2 = __ldg(bias + k) * L2E;
+        const float* vv = reinterpret_cast<const float*>(&raw[k]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float x = fminf(fmaf(vv[j], L2E, b2), HI2);  // (z + b) log2 e, upper clip (softmax.py:40)
+          z[k][j] = x;
+          m[j] = fmaxf(m[j], x);
+          if (k == y[j]) zy[j] = x;
+        }
+      }
+    }
+    float inv[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      zy[j] = fmaxf(zy[j], LO2);
+      const bool all_low = m[j] < LO2;  // every logit below the lower clip: the literal path (softmax.py:41)
+      if (all_low) m[j] = LO2;
+      float ssum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        if (EXACT || k < K) {
+          const float e = ex2_approx((all_low ? LO2 : z[k][j]) - m[j]);
+          z[k][j] = e;
+          ssum += e;
+        }
+      }
+      // columns outside the window (alignment prefix, chunk tail) read whatever the scratch buffer held: fminf() above
+      // maps a NaN to the clip value, so every e is finite and ssum >= 1; inv = 0 (and y = -1) then gives exact zeros
+      inv[j] = valid[j] ? __fdividef(1.0f, ssum) : 0.f;
+      ll += valid[j] ? LN2 * ((zy[j] - m[j]) - lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
+    }
+    if (p.write_dm) {
+      __nv_bfloat16* dh = p.dmt_hi + doff;
+      __nv_bfloat16* dl = p.dmt_lo + doff;  // only dereferenced in split mode
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        if (EXACT || k < K) {
+          __nv_bfloat162 hi[VEC / 2], lo[VEC / 2];
+#pragma unroll
+          for (int j = 0; j < VEC; j += 2) {
+            float d0 = z[k][j] * inv[j], d1 = z[k][j + 1] * inv[j + 1];  // P - Y
+            if (k == y[j]) d0 -= 1.f;
+            if (k == y[j + 1]) d1 -= 1.f;
+            hi[j / 2] = __floats2bfloat162_rn(d0, d1);
+            lo[j / 2] = __floats2bfloat162_rn(d0 - __low2float(hi[j / 2]), d1 - __high2float(hi[j / 2]));
+          }
+          *reinterpret_cast<HV*>(dh) = *reinterpret_cast<const HV*>(hi);
+          if (p.split3) *reinterpret_cast<HV*>(dl) = *reinterpret_cast<const HV*>(lo);
+        }
+        dh += p.dm_ld;
+        dl += p.dm_ld;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+  __shared__ float sll[4];
+  if ((threadIdx.x & 31) == 0) sll[threadIdx.x >> 5] = ll;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(p.loglik + c, (double)sll[0] + (double)sll[1] + (double)sll[2] + (double)sll[3]);
 }
 
 // EW = number of epilogue warps (multiple of 4).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the
@@ -1299,6 +1489,8 @@ static int dp_align() {
   return v;
 }
 
+static inline int k_chunks_of(int64_t cols) { return (int)ceil_div(cols, BK); }
+
 static int pick_kp(int K) {
   const int opts[] = {4, 8, 10, 16, 24, 40, 64};
   for (int o : opts)
@@ -1755,6 +1947,28 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     const bool exact = K == KP;
     TcParams pz = p;
     pz.cpt = 1;  // one chain per block: chain index = blockIdx.y
+    static int fz_vec = -1;  // BHMC_FROM_Z_VEC=0: the scalar kernel (A/B measurements)
+    if (fz_vec < 0) {
+      const char* e = getenv("BHMC_FROM_Z_VEC");
+      fz_vec = e ? atoi(e) : 1;
+    }
+    const int n_cols = k_chunks_of(nrows + shift) * BK;  // every column the backward chunks read
+    bool done_vec = false;
+    if (fz_vec && KP <= 40) {
+#define BHMC_FROM_ZV(KPV, VEC)                                                                                \
+  case KPV: {                                                                                                 \
+    dim3 gv((unsigned)C, (unsigned)ceil_div(n_cols, 128 * VEC));                                              \
+    if (exact) k_softmax_from_z_vec<KPV, true, VEC><<<gv, 128, 0, ctx->stream>>>(pz, n_cols);                 \
+    else k_softmax_from_z_vec<KPV, false, VEC><<<gv, 128, 0, ctx->stream>>>(pz, n_cols);                      \
+    done_vec = true;                                                                                          \
+  } break;
+      switch (KP) {
+        BHMC_FROM_ZV(4, 4) BHMC_FROM_ZV(8, 4) BHMC_FROM_ZV(10, 4) BHMC_FROM_ZV(16, 4) BHMC_FROM_ZV(24, 2) BHMC_FROM_ZV(40, 2)
+        default: break;
+      }
+#undef BHMC_FROM_ZV
+    }
+    if (!done_vec) {
 #define BHMC_FROM_Z(KPV)                                                    \
   case KPV:                                                                 \
     if (exact) k_softmax_from_z<KPV, true><<<grid, 128, 0, ctx->stream>>>(pz); \
@@ -1765,6 +1979,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
       default: set_error("unsupported KP %d", KP); return BHMC_ERR_UNSUPPORTED;
     }
 #undef BHMC_FROM_Z
+    }
     ctx->launches++;
     BHMC_CUDA_OK(cudaGetLastError());
   } else {

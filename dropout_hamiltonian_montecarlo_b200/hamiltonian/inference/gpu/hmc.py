@@ -41,6 +41,36 @@ class DualAveragingStepSize:
         return np.exp(log_step), np.exp(self.log_averaged_step)
 
 
+class _StepTrace:
+    """``sample_positions`` / ``sample_momentums`` of hmc.py:108-111,119: one entry per sampling iteration, entry ``i`` =
+    ``[dict]`` -- the position (or the momentum drawn by ``step``, :41-44) at the START of iteration ``i``.  The
+    reference builds these lists by deep-copying every state; here the entries are materialised on access from what
+    the run already holds (the samples; the injected tape or the counter-based generator), so a long run does not
+    pay for a second and third copy of the chain unless the caller actually reads them."""
+
+    def __init__(self, n, make):
+        self._n, self._make = int(n), make
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError("iteration %d out of range [0, %d)" % (i, self._n))
+        return [self._make(i)]
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+
+TAG_MOMENTUM = 0x01000000  # csrc/philox.cuh: stream of the N(0,1) momentum draws, stream_lo = absolute step index
+
+
 class _ChainSampler:
     """Shared plumbing of hmc / sgld / sghmc / sgd: start-point handling and handle caching."""
 
@@ -105,8 +135,13 @@ class _ChainSampler:
                               shared_path=self.path_length_mode == "shared", leapfrog=self.integrator == "leapfrog",
                               sghmc_descent=self.sign == "descent", reject_nan=self.reject_nan)
             if getattr(model, "row_sharded", False):
-                from ....parallel import RowShardHook
-                s._row_hook = RowShardHook(s, getattr(model, "group", None))  # keeps the callback alive
+                from ....parallel import RowShardHook, row_comm_for
+                comm = row_comm_for(h.ctx, getattr(model, "group", None))
+                if comm is not None:  # grouped NCCL all-reduce enqueued by the C driver after every evaluation
+                    comm.attach(s)
+                    s._row_comm = comm
+                else:                 # not an NCCL group (gloo tests) or BHMC_ROW_COMM=hook
+                    s._row_hook = RowShardHook(s, getattr(model, "group", None))  # keeps the callback alive
             self._sampler = (key, s)
         return h, shapes, squeeze, like, q0, self._sampler[1]
 
@@ -126,6 +161,17 @@ class _ChainSampler:
                 u1[t, c] = np.random.rand()
                 u2[t, c] = np.random.rand()
         return z, u1, u2
+
+
+    def _drawn_momentum(self, s, step):
+        """The N(0,1) momentum the device drew for absolute step index ``step`` (csrc/update.cu:k_hmc_begin keys it by
+        (seed, global chain id, step, TAG_MOMENTUM)): regenerated from the counter-based generator -> [C, P] numpy."""
+        import ctypes as C
+        from ...._lib import check
+        out = torch.empty((s.C, s.P), dtype=torch.float32, device=s.ctx.device)
+        check(s.ctx.L.bhmc_philox_normal(s.ctx.handle, C.c_void_p(out.data_ptr()), s.C, s.P, s.P, self.seed,
+                                         self.chain_id0, int(step) & 0xffffffff, TAG_MOMENTUM))
+        return out.cpu().numpy()
 
 
 class hmc(_ChainSampler):
@@ -161,13 +207,19 @@ class hmc(_ChainSampler):
         if rng is not None:
             z, u1, u2 = self._host_draws(rng, 1, s.C, h, shapes)
             kw = dict(z_momentum=torch.as_tensor(z), u_path=u1, u_accept=u2)
-        out = s.hmc_run(1, self.step_size, self.path_length, step0=self._steps_done, keep_samples=False, **kw)
+        step_index = self._steps_done
+        out = s.hmc_run(1, self.step_size, self.path_length, step0=step_index, keep_samples=False, **kw)
         self._steps_done += 1
         q = self.model.unflatten(s.get(0), shapes, squeeze, like)
         p = self.model.unflatten(s.get(1), shapes, squeeze, like)
         a = out["accept_prob"].cpu().numpy()[0]
         a = float(a[0]) if squeeze else a
-        return q, p, [state], [None], a
+        # hmc.py:44: positions, momentums = [deepcopy(q)], [deepcopy(p)] -- copies of the start point and of the
+        # momentum drawn at :41 (not of the caller's objects)
+        p0 = z[0] if rng is not None else self._drawn_momentum(s, step_index)
+        positions = [self.model.unflatten(q0.copy(), shapes, squeeze, like)]
+        momentums = [self.model.unflatten(p0, shapes, squeeze, like)]
+        return q, p, positions, momentums, a
 
     def find_reasonable_epsilon(self, p_accept, **args):
         """hmc.py:122-130: the dual-averaging update of ``DualAveragingStepSize.update`` written against attributes
@@ -214,6 +266,8 @@ class hmc(_ChainSampler):
             sink = SampleSink(backend, {v: shapes[v] for v in self.model.var_names}, niter, C, squeeze)
         step_sizes = []
 
+        z_kept = []  # injected momentum tapes of the sampling iterations (rng given): sample_momentums reads them
+
         def run(n, keep, per_step=None):
             nonlocal n_grad, accept_sum
             outs = []
@@ -224,6 +278,8 @@ class hmc(_ChainSampler):
                 if rng is not None:
                     z, u1, u2 = self._host_draws(rng, m, C, h, shapes)
                     kw = dict(z_momentum=torch.as_tensor(z), u_path=u1, u_accept=u2)
+                    if keep:
+                        z_kept.append(z)
                 o = s.hmc_run(m, self.step_size, self.path_length, step0=self._steps_done, keep_samples=keep, **kw)
                 self._steps_done += m
                 n_grad += o["n_grad_evals"]
@@ -257,6 +313,8 @@ class hmc(_ChainSampler):
         if self.verbose and burnin > 0 and not adapt:
             _, avg = DualAveragingStepSize(self.step_size).update(accept_sum / max(1, burnin * C))
             print("adapted step size : ", avg)
+        q_start = s.get(0) if niter > 0 else None  # position at the start of sampling iteration 0
+        step_first = self._steps_done
         outs = run(niter, True)
         if outs:
             samples = np.concatenate([o[0] for o in outs], axis=0)
@@ -277,6 +335,16 @@ class hmc(_ChainSampler):
                 print("loss: {0:.4f}".format(float(np.mean(loss[i]))))
         self.last_run = dict(n_grad_evals=n_grad, accept_prob=acc, n_chains=C, step_sizes=step_sizes,
                              step_size=self.step_size)
-        # hmc.py:110-111 returns the pre-step position/momentum of every iteration; positions are
-        # recoverable from the samples, momenta are not kept on the device ring.
-        return posterior, loss, None, None
+        # hmc.py:108-111,119: per-iteration [position], [momentum] at the start of each step (lazy, see _StepTrace).
+        # With a disk backend the samples are not held in memory: positions are then read back from the sink's arrays
+        # by the caller (posterior[var] names the files) and only the momentums are offered.
+        unfl = self.model.unflatten
+        positions = None
+        if sink is None:
+            positions = _StepTrace(niter, lambda i: unfl((q_start if i == 0 else samples[i - 1]).copy(), shapes, squeeze, like))
+        if rng is not None:
+            ztape = np.concatenate(z_kept, axis=0) if z_kept else np.zeros((0, C, h.P), np.float32)
+            momentums = _StepTrace(niter, lambda i: unfl(ztape[i].copy(), shapes, squeeze, like))
+        else:
+            momentums = _StepTrace(niter, lambda i: unfl(self._drawn_momentum(s, step_first + i), shapes, squeeze, like))
+        return posterior, loss, positions, momentums

@@ -73,9 +73,10 @@ class sghmc(_ChainSampler):
         return q, p, (float(a[0]) if squeeze else a)
 
     def sample(self, epochs=1, burnin=1, batch_size=1, rng=None, **args):
-        """Minibatch SGHMC with the sgmcmc.sample epoch structure (sgmcmc.py:40-86); Philox draws only."""
-        if rng is not None:
-            raise NotImplementedError("sghmc.sample uses the in-kernel Philox generator; use step() for injected draws")
+        """Minibatch SGHMC with the sgmcmc.sample epoch structure (sgmcmc.py:40-86): every minibatch is one ``step``
+        (sghmc.py:19-39) on that row window.  ``rng=None``: in-kernel Philox draws.  With an ``rng`` the draws of every
+        step are taken on the host in the reference's consumption order (``_draws``: momentum, path-length uniform,
+        per-iteration noise, accept uniform) and injected; like ``step`` that is a single-chain mode."""
         epochs, burnin, batch_size = int(epochs), int(burnin), int(batch_size)
         h, shapes, squeeze, like, q0, s = self._setup(**args)
         s.set_q(q0)
@@ -84,8 +85,12 @@ class sghmc(_ChainSampler):
         samples, logp = [], []
         for e in range(burnin + epochs):
             for j in range(nb):
+                kw = {}
+                if rng is not None:
+                    z, u1, u2, zn = self._draws(rng, h, shapes, s.C)
+                    kw = dict(z_momentum=torch.as_tensor(z), u_path=u1, u_accept=u2, z_noise=torch.as_tensor(zn))
                 o = s.hmc_run(1, self.step_size, self.path_length, row0=j * batch_size, nrows=batch_size,
-                              step0=self._steps_done, keep_samples=False, keep_stats=(j == nb - 1))
+                              step0=self._steps_done, keep_samples=False, keep_stats=(j == nb - 1), **kw)
                 self._steps_done += 1
                 n_grad += o["n_grad_evals"]
             if e >= burnin:

@@ -45,11 +45,30 @@ class sgmcmc(_ChainSampler):
         h, shapes, squeeze, like, q0, s = self._setup(**args)
         s.set_q(q0)
         nb = (h.N - batch_size) // batch_size + 1
-        z = None
-        if rng is not None:
-            z = torch.as_tensor(self._noise_tape(rng, nb * (epochs + burnin), s.C, h, shapes))
-        out = s.sg_run(epochs, burnin, batch_size, self.step_size, n_rows=h.N, step0=self._steps_done, z=z)
-        self._steps_done += nb * (epochs + burnin)
+        if rng is None:
+            out = s.sg_run(epochs, burnin, batch_size, self.step_size, n_rows=h.N, step0=self._steps_done)
+            self._steps_done += nb * (epochs + burnin)
+        else:
+            # Injected noise (parity mode): the tape of ONE epoch at a time ([n_batches, C, P] fp32) instead of the whole
+            # run's -- MNIST softmax at 100 epochs would be 1.9 GB per chain.  The library call is cut at epoch
+            # boundaries; what carries over is the step size of the next epoch's first batch (sgmcmc.py:72-73: eps is
+            # re-assigned AFTER batch j, so batch 0 of epoch e >= 1 runs at lr(n_batches - 1)).
+            samples, logps, n_grad = [], [], 0
+            first = 0.0  # 0 = start at step_size
+            for e in range(burnin + epochs):
+                z = torch.as_tensor(self._noise_tape(rng, nb, s.C, h, shapes))
+                sampling = e >= burnin
+                o = s.sg_run(1 if sampling else 0, 0 if sampling else 1, batch_size, self.step_size, n_rows=h.N,
+                             step0=self._steps_done, z=z, first_step_size=first)
+                self._steps_done += nb
+                n_grad += o["n_grad_evals"]
+                if sampling:
+                    first = o["final_step_size"]
+                    samples.append(o["samples"])
+                    logps.append(o["logp"])
+            out = {"samples": torch.cat(samples) if samples else s.ctx.empty((0, s.C, s.P)),
+                   "logp": torch.cat(logps) if logps else s.ctx.empty((0, s.C), torch.float64),
+                   "n_grad_evals": n_grad, "final_step_size": first if epochs > 0 else self.step_size}
         posterior = self.model.unflatten(out["samples"], shapes, squeeze, like)
         logp = out["logp"].cpu().numpy()
         if squeeze:

@@ -133,7 +133,8 @@ class softmax(_base.ChainModel):
         """softmax.py:45-61 -- gradient of the potential, summed over rows, + alpha*theta."""
         h = self.handle_for(**args)
         q, squeeze, like = self.flatten(par, self.var_shapes(h))
-        g, _ = h.grad(h.pack(q), 0, h.N, PREC[self.precision], True)
+        g, ll = h.grad(h.pack(q), 0, h.N, PREC[self.precision], True)
+        self._allreduce_rows(g, ll)
         return self.unflatten(g[:, : h.P], self.var_shapes(h), squeeze, like)
 
     def log_likelihood(self, par, **args):
@@ -141,8 +142,21 @@ class softmax(_base.ChainModel):
         h = self.handle_for(**args)
         q, squeeze, _ = self.flatten(par, self.var_shapes(h))
         _, ll = h.grad(h.pack(q), 0, h.N, PREC[self.precision], False)
+        self._allreduce_rows(None, ll)
         out = ll.cpu().numpy()
         return float(out[0]) if squeeze else out
+
+    def _allreduce_rows(self, g, ll):
+        """row_sharded: the model protocol returns GLOBAL quantities -- partial sums over this rank's rows are summed
+        over the group (grouped NCCL call from C when the group is NCCL, torch.distributed otherwise)."""
+        if not self.row_sharded:
+            return
+        from ....parallel import allreduce_sum_, row_comm_for
+        comm = row_comm_for(self.ctx, self.group)
+        if comm is not None:
+            comm.allreduce(g, ll)
+        else:
+            allreduce_sum_([ll, g], self.group)
 
     def log_prior(self, par, **args):
         """softmax.py:22-30 (``prior='cpu'``, a constant) or models/gpu/softmax.py:29-39."""
@@ -159,6 +173,18 @@ class softmax(_base.ChainModel):
         """softmax.py:74-79: -(LL + log_prior)/N."""
         h = self.handle_for(**args)
         q, squeeze, _ = self.flatten(par, self.var_shapes(h))
+        if self.row_sharded:  # -(sum over ALL rows of LL + log_prior) / N_global; the prior enters once, not once per rank
+            _, ll = h.grad(h.pack(q), 0, h.N, PREC[self.precision], False)
+            self._allreduce_rows(None, ll)
+            lp = np.zeros(q.shape[0])
+            alpha = float(self.hyper["alpha"])
+            for o, n in zip(h.var_off, h.var_len):
+                if self.prior == "cpu":
+                    lp -= 0.5 * n * np.log(2 * np.pi) - 0.5 * n * np.log(alpha)
+                else:
+                    lp -= 0.5 * alpha * np.sum(np.square(q[:, o:o + n].astype(np.float64)), axis=1) / n
+            out = -(ll.cpu().numpy() + lp) / float(h.global_rows)
+            return float(out[0]) if squeeze else out
         out = h.nlp(h.pack(q), 0, h.N, PREC[self.precision]).cpu().numpy()
         return float(out[0]) if squeeze else out
 

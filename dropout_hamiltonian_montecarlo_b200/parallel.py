@@ -6,11 +6,16 @@ Two ways the path shards; the reference has neither (host multipro
   contiguous block of global chain ids; Philox streams are keyed by the global id, so the union
   of all ranks' chains is the same set of chains for any world size.
 * **rows** -- full-batch HMC on a row-sharded data matrix (BASELINE config 5): every rank holds
-  all chains and ``N/G`` rows; each gradient evaluation is followed by ONE all-reduce(sum) of the
-  ``[g | loglik]`` buffers (NCCL over NVLink).  The Gaussian-prior term ``alpha*q`` is added once by
-  giving every rank ``alpha/G``; energies are normalised by the global row count.  Everything after
-  the all-reduce (update, Philox draws, accept) runs redundantly and identically on every rank.
+  all chains and ``N/G`` rows; each gradient evaluation is followed by ONE grouped NCCL all-reduce(sum)
+  of the gradient (fp32) and the log-likelihoods (fp64), enqueued by the C driver on the context
+  stream (``RowComm`` -> ``bhmc_sampler_set_row_comm``; csrc/comm.cu).  The Gaussian-prior term
+  ``alpha*q`` is added once by giving every rank ``alpha/G``; energies are normalised by the global
+  row count.  Everything after the all-reduce (update, Philox draws, accept) runs redundantly and
+  identically on every rank.  ``RowShardHook`` (two torch.distributed collectives from a ctypes
+  callback per evaluation) is the round-1 mechanism; it remains for process groups that are not NCCL
+  (the gloo CPU tests) and as the A/B partner of the C path (``BHMC_ROW_COMM=hook``).
 """
+import os
 import ctypes as C
 
 import numpy as np
@@ -45,6 +50,55 @@ def allreduce_sum_(tensors, group=None):
     for t in tensors:
         if t is not None:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+class RowComm:
+    """NCCL communicator owned by libbhmc.so (csrc/comm.cu) over the ranks of a torch.distributed group: rank 0 makes
+    the NCCL unique id, the 128 bytes travel through the existing process group, every rank joins."""
+
+    def __init__(self, ctx, group=None):
+        self.ctx = ctx
+        L = ctx.L
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(L.bhmc_comm_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        h = C.c_void_p()
+        _lib.check(L.bhmc_comm_create(ctx.handle, ident, rank, world, C.byref(h)))
+        self.handle, self.rank, self.world = h, rank, world
+
+    def allreduce(self, g=None, stat=None):
+        """In-place sum over ranks of a device fp32 tensor and/or a device fp64 tensor (one grouped NCCL call)."""
+        _lib.check(self.ctx.L.bhmc_comm_allreduce(self.handle, C.c_void_p(g.data_ptr() if g is not None else 0),
+                                                  g.numel() if g is not None else 0,
+                                                  C.c_void_p(stat.data_ptr() if stat is not None else 0),
+                                                  stat.numel() if stat is not None else 0))
+
+    def attach(self, sampler):
+        _lib.check(self.ctx.L.bhmc_sampler_set_row_comm(sampler.handle, self.handle))
+
+    def close(self):
+        if self.handle is not None:
+            self.ctx.L.bhmc_comm_destroy(self.handle)
+            self.handle = None
+
+
+_row_comms = {}
+
+
+def row_comm_for(ctx, group=None):
+    """One RowComm per (context, group), or None when the C path does not apply (not NCCL, or BHMC_ROW_COMM=hook)."""
+    if os.environ.get("BHMC_ROW_COMM", "c") == "hook":
+        return None
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend(group) != "nccl":
+        return None
+    key = (id(ctx), id(group))
+    if key not in _row_comms:
+        _row_comms[key] = RowComm(ctx, group)
+    return _row_comms[key]
 
 
 class RowShardHook:

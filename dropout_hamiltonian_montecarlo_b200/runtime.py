@@ -312,11 +312,12 @@ class SamplerHandle:
         return out
 
     def sg_run(self, epochs, burnin, batch_size, step_size, *, n_rows=0, gamma=0.9, step0=0, z=None,
-               keep_samples=True, dropout_keep=0.0, masks=None):
+               keep_samples=True, dropout_keep=0.0, masks=None, first_step_size=0.0, keep_momentum=False):
         ctx = self.ctx
         run = SgRun()
         run.epochs, run.burnin, run.batch_size, run.n_rows = epochs, burnin, batch_size, n_rows
         run.step_size, run.gamma, run.step0 = step_size, gamma, step0
+        run.first_step_size, run.keep_momentum = float(first_step_size), int(bool(keep_momentum))
         if z is not None:
             z = z.to(ctx.device, torch.float32).contiguous()
             run.z_dev = z.data_ptr()

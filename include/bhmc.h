@@ -245,9 +245,41 @@ typedef struct bhmc_sg_run {
    * or NULL for in-kernel Philox draws keyed (seed, minibatch, row, feature). */
   double dropout_keep;
   const uint8_t* mask_dev;
+  /* Chunked calls (one epoch, or a bounded number of minibatches' worth of injected noise, per call): the step size of
+   * this call's FIRST minibatch.  0 = step_size.  The reference re-assigns eps after every batch of a sampling epoch
+   * (sgmcmc.py:72-73), so batch 0 of epoch e >= 1 runs at lr(n_batches - 1): pass the previous call's final_step_size. */
+  double first_step_size;
+  /* SGD only.  0 (default): the heavy-ball momentum starts from zero, as every sgd.fit / fit_dropout call of the
+   * reference does (sgd.py:35,57: momentum = zeros_like(par)); 1: continue from the momentum of the previous call. */
+  int32_t keep_momentum;
+  int32_t reserved_;
 } bhmc_sg_run;
 /* SGLD (kind SGLD) / SGD (kind SGD) epochs over sequential minibatches */
 int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run);
+
+/* ---- multi-GPU, rows sharded (full-batch HMC on large N; no reference counterpart -- the reference only has host
+ *      multiprocessing, hamiltonian/inference/cpu/hmc_multicore.py).  Every rank binds ITS rows and runs ALL chains;
+ *      after each evaluation the gradient and the log-likelihoods are summed over the ranks by ONE grouped NCCL
+ *      all-reduce enqueued by the C driver on the context stream (no host callback).  libnccl.so.2 is resolved with
+ *      dlopen at first use; single-GPU use never loads it. ------------------------------------------------------ */
+#define BHMC_COMM_ID_BYTES 128
+typedef struct bhmc_comm bhmc_comm;
+/* rank 0: create the rendezvous id (ncclGetUniqueId) and hand its 128 bytes to the other ranks by any means */
+int bhmc_comm_unique_id(uint8_t* id_out);
+/* collective over all ranks: ncclCommInitRank on the context's device */
+int bhmc_comm_create(bhmc_ctx* ctx, const uint8_t* id, int32_t rank, int32_t world, bhmc_comm** out);
+/* adopt a communicator the host program already owns (ncclComm_t); it is not destroyed by bhmc_comm_destroy */
+int bhmc_comm_wrap(bhmc_ctx* ctx, void* nccl_comm, int32_t rank, int32_t world, bhmc_comm** out);
+int bhmc_comm_destroy(bhmc_comm* c);
+int32_t bhmc_comm_world(const bhmc_comm* c);
+int bhmc_nccl_version(void); /* 0 when libnccl cannot be loaded */
+/* sum over ranks, in place: g_dev [g_count] fp32 and stat_dev [n_stat] fp64 (either may be NULL); one grouped call */
+int bhmc_allreduce_grad(bhmc_ctx* ctx, void* nccl_comm, float* g_dev, int64_t g_count, double* stat_dev, int32_t n_stat);
+int bhmc_comm_allreduce(bhmc_comm* c, float* g_dev, int64_t g_count, double* stat_dev, int32_t n_stat);
+/* from now on every gradient / log-likelihood evaluation of this sampler's drivers is followed by the all-reduce of
+ * the rows it produced (NULL detaches).  The model must have been created with alpha / world and told the global row
+ * count (bhmc_model_set_global_rows) so that the prior term and the energies come out once. */
+int bhmc_sampler_set_row_comm(bhmc_sampler* s, bhmc_comm* comm);
 
 /* ---- test hook, host only (no device needed): compiles the streaming schedule for path lengths L[n_steps][n_chains].
  * Call with code1 == NULL to get n_phases (gradient launches J) and n_grad_evals, then with code1/code2/step1/step2 of
