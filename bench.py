@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- headline metric of BASELINE.json: gradient evaluations / second
-(chains x leapfrog) on the MNIST-shaped softmax BNN.
+(chains x leapfrog) on the MNIST-shaped softmax BNN; ESS / second.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
 
-Workload at N=1 = BASELINE configs[1]: full-batch HMC, softmax regression, synthetic
+Headline workload at N=1 = BASELINE configs[1]: full-batch HMC, softmax regression, synthetic
 60 000 x 784, 10 classes, 64 chains (per GPU; weak scaling: chains are independent units and
 shard over ranks with no data-path collective).  A "step" is one HMC transition of every chain:
 momentum draw, L-1 Gauss-Seidel leapfrog sweeps (each sub-step one full gradient = forward +
@@ -15,11 +15,22 @@ backward GEMM), Metropolis test, sample store.
 `e2e`    : same metric through the public API (`hmc.sample`) with HOST buffers: every step binds the
            data from pinned host memory (H2D + operand preparation inside the timed region) and
            reads the samples / losses back (D2H).
-`roofline`: dominant kernel (forward GEMM + fused softmax epilogue), algorithmic flops
-           2*N*D*K*C per launch / its mean duration (CUDA events on the launching stream, measured
-           live inside the timed region) against the measured sustained bf16 peak.
+`roofline`: dominant kernel of the timed region (the backward GEMM k_tc_gemm<bwd> in every run so far; the
+           line names whichever group took longer), algorithmic flops 2*N*D*K per chain it carried / its
+           duration (CUDA events on the launching stream, sampled live inside the timed region)
+           against the measured sustained bf16 peak.
 `cpu_baseline`: the NumPy oracle port of the reference path (fp64, BLAS threads = host cores) on a
-           bounded sample of the same workload, same box.
+           bounded sample of the same workload, same box; plus ESS/s of the CPU arm with the same
+           estimator on the small-N variant SURVEY 8(d) names.
+
+The other BASELINE configs ride on the same JSON line as secondary blocks (driver-visible, each with its
+own value / ms_per_step / roofline):
+`cfg3`   : configs[2] -- SGLD and SGHMC softmax, minibatch 500, 128 chains per GPU (1024 over 8).
+`cfg4`   : configs[3] -- SGHMC Bayesian MLP 784-512-512-10, minibatch 500, Philox noise + dropout.
+`cfg5_row_sharded`: configs[4] -- full-batch HMC softmax 1 000 000 x 2048 x 38, 8 chains replicated,
+           rows sharded over the N ranks, one grouped NCCL all-reduce per gradient evaluation
+           (STRONG scaling: the total work is fixed); with N > 1 the run asserts that the replicas
+           stay identical and that a row-sharded gradient matches a 1-rank gradient.
 """
 import argparse
 import json
@@ -195,26 +206,53 @@ def peaks():
 
 
 def ncu_traffic(kernel, prec, wl, chains_per_launch):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/ncu_traffic.json; captured at full launches of the cfg2 workload).
-    Returned only when the timed launches are the captured shape (same workload, precision, all chains)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` captures (profiles/ncu_traffic.json).  Trajectories are ragged, so the timed launches carry fewer
+    chains on average than a full launch: the captures are taken at several launch widths (chains per launch) and the
+    figure for this run's mean width is interpolated linearly between the two nearest ones -- the traffic of these
+    GEMMs is affine in the width (the X operand is streamed once whatever the width, the (P-Y)^T operand and the
+    partials grow with it).  Returns (bytes, description)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        e = t["%s/%s/%s" % (wl["desc"], prec, kernel)]
-        if abs(chains_per_launch - e["chains_per_launch"]) < 0.5:
-            return e["dram_bytes"], e["source"]
-        return None, "ncu capture is of a full %d-chain launch; this run averaged %.1f chains per launch" % (
-            e["chains_per_launch"], chains_per_launch)
-    except Exception:
-        return None, "no ncu capture for this workload/precision"
+        pts = sorted((e["chains_per_launch"], e["dram_bytes"], e["source"]) for k, e in t.items()
+                     if k.startswith("%s/%s/%s" % (wl["desc"], prec, kernel)))
+        if not pts:
+            return None, "no ncu capture for this workload/precision"
+        lo = max([q for q in pts if q[0] <= chains_per_launch] or [pts[0]], key=lambda q: q[0])
+        hi = min([q for q in pts if q[0] >= chains_per_launch] or [pts[-1]], key=lambda q: q[0])
+        if lo[0] == hi[0]:
+            if abs(lo[0] - chains_per_launch) > 8:
+                return None, "nearest ncu capture is of %d-chain launches; this run averaged %.1f" % (lo[0], chains_per_launch)
+            return lo[1], "%s (captured at %d chains per launch; run mean %.1f)" % (lo[2], lo[0], chains_per_launch)
+        w = (chains_per_launch - lo[0]) / (hi[0] - lo[0])
+        return (1 - w) * lo[1] + w * hi[1], ("interpolated at the run's mean of %.1f chains per launch between the ncu "
+                                            "captures at %d and %d chains (%s; %s)" % (chains_per_launch, lo[0], hi[0], lo[2], hi[2]))
+    except Exception as e:
+        return None, "ncu_traffic.json unreadable: %r" % (e,)
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_rate(wl, seconds_target=12.0, max_steps=20):
-    """Oracle port of hmc.step (hamiltonian/inference/cpu/hmc.py:39-64 + models/cpu/softmax.py) on the
-    host cores: one chain, fp64, same data shape; bounded sample (path length pinned to L=11 per step)."""
+# ESS comparison workload (SURVEY 8(d), "small-N variant"): the reference's energy is the MEAN NLP while its dynamics
+# use the SUM gradient, so at N = 60 000 the chain only moves for eps <~ 3e-7 and 500 CPU steps would take half an
+# hour.  At N = 2 000 the oracle does a transition in ~30 ms, so BOTH arms can run >= 300 transitions with the same
+# settings and the same estimator (Geyer initial positive sequence, dropout_hamiltonian_montecarlo_b200/ess.py).
+ESS_SMALL = dict(N=2000, D=784, K=10, eps=1e-5, path=2e-4, alpha=0.01, burnin=50,
+                 desc="HMC softmax 2000x784x10 full batch (small-N ESS variant), eps 1e-5, E[L] 20")
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return int(max([i.get("num_threads", 1) for i in threadpool_info()] + [1]))
+    except Exception:
+        return int(os.cpu_count() or 1)
+
+
+def cpu_hmc_steps(wl, n_steps, warmup, L=None, seconds_target=None):
+    """Oracle port of hmc.step (hamiltonian/inference/cpu/hmc.py:39-64 + models/cpu/softmax.py) on the host cores:
+    one chain, fp64, the workload's data shape.  L pins the path length of every step (bounded sample); None draws it
+    as the reference does.  Returns (per-step seconds of the timed steps, grad evals of the timed steps)."""
     from oracle import hamiltonian_oracle as O
-    import torch
     use_all_host_threads()
     X, y = synth(wl["N"], wl["D"], wl["K"], 0)
     X = X.numpy().astype(np.float64)
@@ -222,68 +260,320 @@ def cpu_reference_rate(wl, seconds_target=12.0, max_steps=20):
     model = O.SoftmaxOracle({"alpha": wl["alpha"]})
     q = {"weights": np.zeros((wl["D"], wl["K"])), "bias": np.zeros(wl["K"])}
     rs = np.random.RandomState(0)
-    L = 11
-    u_len = (L - 0.5) * wl["eps"] / (2 * wl["path"])
-    n_grad, t0 = 0, time.perf_counter()
-    steps = 0
-    while steps < max_steps and (time.perf_counter() - t0 < seconds_target or steps == 0):
+    per_step, n_grad = [], 0
+    t_begin = time.perf_counter()
+    for i in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        u_len = (L - 0.5) * wl["eps"] / (2 * wl["path"]) if L else rs.rand()
         draws = O.TapeDraws([rs.normal(size=q["weights"].shape), rs.normal(size=q["bias"].shape)], [u_len, rs.rand()])
         r = O.hmc_step(model, q, ["weights", "bias"], wl["eps"], wl["path"], draws, X_train=X, y_train=Y)
         q = r["q"]
-        n_grad += r["n_grad"]
-        steps += 1
+        if i >= warmup:
+            per_step.append(time.perf_counter() - t0)
+            n_grad += r["n_grad"]
+            if seconds_target and time.perf_counter() - t_begin > seconds_target:
+                break
+    return per_step, n_grad
+
+
+def cpu_ess_small(seconds_target=12.0, max_steps=400):
+    """ESS/s of the CPU arm: the oracle port runs the small-N variant for up to max_steps transitions (bounded by
+    seconds_target) and its samples go through the SAME estimator as the device run."""
+    from oracle import hamiltonian_oracle as O
+    from dropout_hamiltonian_montecarlo_b200.ess import ess as ess_fn
+    use_all_host_threads()
+    w = ESS_SMALL
+    X, y = synth(w["N"], w["D"], w["K"], 0)
+    X = X.numpy().astype(np.float64)
+    Y = O.one_hot(y.numpy(), w["K"])
+    model = O.SoftmaxOracle({"alpha": w["alpha"]})
+    q = {"weights": np.zeros((w["D"], w["K"])), "bias": np.zeros(w["K"])}
+    rs = np.random.RandomState(1)
+    samples, acc, n_grad = [], [], 0
+    t0 = None
+    for i in range(w["burnin"] + max_steps):
+        if i == w["burnin"]:
+            t0 = time.perf_counter()
+        draws = O.TapeDraws([rs.normal(size=q["weights"].shape), rs.normal(size=q["bias"].shape)], [rs.rand(), rs.rand()])
+        r = O.hmc_step(model, q, ["weights", "bias"], w["eps"], w["path"], draws, X_train=X, y_train=Y)
+        q = r["q"]
+        if i >= w["burnin"]:
+            samples.append(np.concatenate([q["weights"].ravel(), q["bias"].ravel()]))
+            acc.append(r["accept_prob"])
+            n_grad += r["n_grad"]
+            if time.perf_counter() - t0 > seconds_target and len(samples) >= 100:
+                break
     dt = time.perf_counter() - t0
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    except Exception:
-        threads = os.cpu_count()
-    return dict(value=n_grad / dt, unit="grad-evals/s", cores=int(threads), kind="port",
+    e = ess_fn(np.asarray(samples)[:, None, :], max_params=48)
+    return {"ess_min_per_s": e["min"] / dt, "ess_median_per_s": e["median"] / dt, "steps": len(samples),
+            "burnin": w["burnin"], "chains": 1, "mean_accept_prob": float(np.mean(acc)), "grad_evals_per_s": n_grad / dt,
+            "seconds": dt, "cores": blas_threads(), "workload": w["desc"],
+            "estimator": "Geyer initial positive sequence, 48 random parameters (same code as the device run)"}
+
+
+def cpu_reference_rate(wl, seconds_target=12.0, max_steps=20):
+    """cpu_baseline of the headline: bounded sample (path length pinned to L=11 per step) of the same workload."""
+    L = 11
+    per_step, n_grad = cpu_hmc_steps(wl, max_steps, 0, L=L, seconds_target=seconds_target)
+    dt = sum(per_step)
+    return dict(value=n_grad / dt, unit="grad-evals/s", cores=blas_threads(), kind="port",
                 sample="%d HMC steps of 1 chain, L=%d (%d grad evals), fp64 NumPy oracle port of hmc.step, %s"
-                       % (steps, L, n_grad, wl["desc"]), seconds=dt)
+                       % (len(per_step), L, n_grad, wl["desc"]), seconds=dt)
+
+
+def base_config(args, wl):
+    """The part of `config` both arms share: what the workload IS (the arms differ in how much of it they sample)."""
+    return {"workload": wl["desc"], "N": wl["N"], "D": wl["D"], "K": wl["K"], "chains_per_gpu": wl["C"],
+            "step_size": wl["eps"], "path_length": wl["path"], "path_length_mode": args.path_mode,
+            "sweep": "reference (Gauss-Seidel, 2 gradients per leapfrog iteration)"}
 
 
 def run_reference(args, wl):
+    """Reference arm: the reference's own CPU algorithm for the path (oracle port: the reference tree is not on the
+    GPU box) on the box's host cores, every step a bounded sample of the workload: one chain, path length pinned to
+    L = 6 (11 gradient evaluations per step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = []
-    use_all_host_threads()
-    from oracle import hamiltonian_oracle as O
-    X, y = synth(wl["N"], wl["D"], wl["K"], 0)
-    X = X.numpy().astype(np.float64)
-    Y = O.one_hot(y.numpy(), wl["K"])
-    model = O.SoftmaxOracle({"alpha": wl["alpha"]})
-    q = {"weights": np.zeros((wl["D"], wl["K"])), "bias": np.zeros(wl["K"])}
-    rs = np.random.RandomState(0)
-    L = 6  # bounded sample: 11 gradient evaluations per step
-    u_len = (L - 0.5) * wl["eps"] / (2 * wl["path"])
-    n_grad = 0
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        draws = O.TapeDraws([rs.normal(size=q["weights"].shape), rs.normal(size=q["bias"].shape)], [u_len, rs.rand()])
-        r = O.hmc_step(model, q, ["weights", "bias"], wl["eps"], wl["path"], draws, X_train=X, y_train=Y)
-        q = r["q"]
-        if i >= args.warmup:
-            per_step.append(time.perf_counter() - t0)
-            n_grad += r["n_grad"]
+    L = 6
+    per_step, n_grad = cpu_hmc_steps(wl, args.steps, args.warmup, L=L)
     total = sum(per_step)
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-    except Exception:
-        threads = os.cpu_count()
+    threads = blas_threads()
     val = n_grad / total
+    ess_cpu = None if args.no_ess else cpu_ess_small()
     line = {"impl": "reference", "metric": "grad evals/sec (chains x leapfrog) on MNIST-shape softmax BNN",
             "value": val, "unit": "grad-evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": data_desc(),
-            "config": {"workload": wl["desc"], "sample": "1 chain, L=%d per step (%d grad evals/step)" % (L, 1 + (L - 1) * 2)},
-            "cpu_baseline": {"value": val, "unit": "grad-evals/s", "cores": int(threads), "kind": "port",
-                             "sample": "%d timed HMC steps of 1 chain, L=%d, fp64 NumPy oracle port "
-                                       "(the reference tree is not present on the GPU box)" % (args.steps, L)},
+            "ms_per_step": 1e3 * total / max(1, len(per_step)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": data_desc(), "config": base_config(args, wl),
+            "cpu_baseline": {"value": val, "unit": "grad-evals/s", "cores": threads, "kind": "port",
+                             "sample": "%d timed HMC steps of 1 chain, path length pinned to L=%d (%d grad evals per step), "
+                                       "fp64 NumPy oracle port (the reference tree is not present on the GPU box)"
+                                       % (len(per_step), L, 1 + (L - 1) * 2)},
             "e2e": {"value": val, "unit": "grad-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if ess_cpu is not None:
+        line["ess"] = ess_cpu
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# secondary blocks: BASELINE configs 3, 4, 5 (one JSON object each, merged into the headline line)
+def _agg_time_count(dev, world, ms, count):
+    """(max over ranks of the device time in ms, sum over ranks of the work count)."""
+    import torch
+    import torch.distributed as dist
+    st = torch.tensor([ms, float(count)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx, sm = st.clone(), st.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        return float(mx[0]), float(sm[1])
+    return float(st[0]), float(st[1])
+
+
+def _timed(world, fn):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return e0.elapsed_time(e1), out
+
+
+def _group_roofline(ctx, run_once, flops_per_launch, peak_tf, names=("fwd", "bwd", "prep", "update")):
+    """Per-launch-group device times of ONE extra untimed pass with every kernel group bracketed by CUDA events
+    (bracketing costs stream overlap, so it is never on inside a timed region): the dominant group, its mean
+    duration, and the algorithmic rate of the GEMM group that took longest against the tensor peak."""
+    ctx.timing(1)
+    run_once()
+    ctx.sync()
+    t = [ctx.kernel_time(g) for g in range(4)]
+    ctx.timing(0)
+    groups = {names[g]: {"ms_total": t[g][0], "launch_groups": int(t[g][1]),
+                         "avg_ms": (t[g][0] / t[g][1]) if t[g][1] else None} for g in range(4)}
+    dom = max((0, 1), key=lambda g: t[g][0])
+    avg = (t[dom][0] / t[dom][1]) * 1e-3 if t[dom][1] else 0.0
+    achieved = flops_per_launch[dom] / avg / 1e12 if avg > 0 else 0.0
+    return {"bound": "tensor", "kernel_group": names[dom], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved / peak_tf, "avg_launch_ms": avg * 1e3, "algorithmic_flops_per_launch": flops_per_launch[dom],
+            "groups": groups, "timing": "one extra pass, every kernel group bracketed by CUDA events on the launching stream"}
+
+
+def bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf, epochs=5):
+    """BASELINE configs[2]: SGLD and SGHMC softmax on sequential minibatches of 500, 128 chains per GPU (1024 chains
+    over 8 GPUs; chains shard with no collective -> weak scaling).  sgld.py:31-46 / sghmc.py:19-39 + sgmcmc.py:40-86."""
+    from dropout_hamiltonian_montecarlo_b200._lib import KIND, PREC
+    from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle
+    N, D, K, B, C = h.N, h.D, h.K, 500, 128
+    nb = N // B
+    flops_gemm = 2.0 * B * D * K * C  # one GEMM of one minibatch evaluation of all chains
+    out = {"workload": "SGLD / SGHMC softmax %dx%dx%d, minibatch %d, %d chains/GPU" % (N, D, K, B, C), "n_gpus": world,
+           "scaling": "weak", "precision": prec, "unit": "grad-evals/s", "algorithmic_flops_per_chain_eval": 4.0 * B * D * K}
+    # ---- SGLD: one library call runs whole epochs
+    s = SamplerHandle(ctx, h, KIND["sgld"], C, seed=1, chain_id0=rank * C, precision=PREC[prec])
+    s.set_q(np.zeros((C, h.P), np.float32))
+    s.sg_run(0, 1, B, 1e-5, n_rows=N)  # warm-up epoch (burn-in: constant step size)
+    l0 = ctx.launches
+    ms, o = _timed(world, lambda: s.sg_run(epochs, 0, B, 1e-5, n_rows=N, step0=nb))
+    launches = ctx.launches - l0
+    ms, n = _agg_time_count(dev, world, ms, o["n_grad_evals"])
+    roof = _group_roofline(ctx, lambda: s.sg_run(1, 0, B, 1e-5, n_rows=N, step0=nb * (epochs + 1)),
+                           {0: flops_gemm, 1: flops_gemm}, peak_tf)
+    out["sgld"] = {"value": n / (ms * 1e-3), "ms_per_step": ms / (epochs * nb), "steps": epochs * nb,
+                   "step": "one minibatch update of every chain (gradient + Philox noise + update)",
+                   "gpu_launches_per_step": launches / (epochs * nb),
+                   "algorithmic_tflops": n * 4.0 * B * D * K / (ms * 1e-3) / 1e12 / world, "roofline": roof}
+    s.close()
+    # ---- SGHMC: every minibatch is one sghmc.step (momentum draw, L-1 friction + noise iterations, Metropolis test)
+    s = SamplerHandle(ctx, h, KIND["sghmc"], C, seed=1, chain_id0=rank * C, precision=PREC[prec], shared_path=True,
+                      sghmc_descent=True)
+    s.set_q(np.zeros((C, h.P), np.float32))
+    eps, path, steps = 1e-5, 1e-4, 60
+    for j in range(8):
+        s.hmc_run(1, eps, path, row0=j * B, nrows=B, step0=j, keep_samples=False, keep_stats=False)
+
+    def run(j0, n_steps):
+        tot = 0
+        for j in range(j0, j0 + n_steps):
+            tot += s.hmc_run(1, eps, path, row0=(j % nb) * B, nrows=B, step0=j, keep_samples=False, keep_stats=False)["n_grad_evals"]
+        return tot
+    l0 = ctx.launches
+    ms, n_local = _timed(world, lambda: run(8, steps))
+    launches = ctx.launches - l0
+    ms, n = _agg_time_count(dev, world, ms, n_local)
+    roof = _group_roofline(ctx, lambda: run(8 + steps, 10), {0: flops_gemm, 1: flops_gemm}, peak_tf)
+    out["sghmc"] = {"value": n / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+                    "step": "one sghmc.step of every chain on one minibatch, E[L] = 10, shared path lengths, descent sign",
+                    "ms_per_grad_eval_all_chains": ms / (n_local / C), "gpu_launches_per_step": launches / steps,
+                    "algorithmic_tflops": n * 4.0 * B * D * K / (ms * 1e-3) / 1e12 / world, "roofline": roof}
+    s.close()
+    out["value"] = out["sgld"]["value"]
+    out["ms_per_step"] = out["sgld"]["ms_per_step"]
+    out["roofline"] = {k: roof_v for k, roof_v in out["sgld"]["roofline"].items() if k != "groups"}
+    return out
+
+
+def bench_cfg4(ctx, X, y, rank, world, dev, prec, peak_tf, steps=20, C=16):
+    """BASELINE configs[3]: SGHMC on the dropout MLP 784-512-512-10 (models/gpu/mlp.py:19-82), minibatch 500, Philox
+    noise + dropout masks, chains shard over GPUs (weak scaling)."""
+    from dropout_hamiltonian_montecarlo_b200._lib import KIND, PREC
+    from dropout_hamiltonian_montecarlo_b200.runtime import MlpHandle, SamplerHandle
+    N, D = X.shape
+    K, B, n_mid = int(y.max().item()) + 1, 500, 512
+    h = MlpHandle(ctx, N, D, n_mid, K, 0.01, 0.1, seed=3, chain_id0=rank * C)
+    h.bind(X, y)
+    s = SamplerHandle(ctx, h, KIND["sghmc"], C, seed=1, chain_id0=rank * C, precision=PREC[prec], sweep=[(0, h.P)],
+                      shared_path=True, sghmc_descent=True)
+    s.set_q(np.random.RandomState(0).normal(0, 0.05, (C, h.P)).astype(np.float32))
+    eps, path = 1e-3, 5e-3  # E[L] = 5
+    nb = N // B
+    s.hmc_run(2, eps, path, row0=0, nrows=B, keep_samples=False)
+
+    def run(i0, n_steps):
+        tot = 0
+        for i in range(i0, i0 + n_steps):
+            tot += s.hmc_run(1, eps, path, row0=(i % nb) * B, nrows=B, step0=i, keep_samples=False)["n_grad_evals"]
+        return tot
+    l0 = ctx.launches
+    ms, n_local = _timed(world, lambda: run(10, steps))
+    launches = ctx.launches - l0
+    ms, n = _agg_time_count(dev, world, ms, n_local)
+    sw = D * n_mid + n_mid * n_mid + n_mid * K
+    flops = 6.0 * B * sw - 2.0 * B * D * n_mid       # SURVEY 8(d): 1.606 GFLOP at B = 500
+    f_fwd, f_bwd = 2.0 * B * sw * C, (4.0 * B * sw - 2.0 * B * D * n_mid) * C
+    roof = _group_roofline(ctx, lambda: run(10 + steps, 5), {0: f_fwd, 1: f_bwd}, peak_tf,
+                           names=("forward (3 GEMMs + epilogues)", "backward (5 GEMMs + reductions)", "operand splits", "update"))
+    out = {"workload": "SGHMC MLP %d-%d-%d-%d dropout 0.1, minibatch %d, %d chains/GPU, joint sweep, E[L] = 5"
+                       % (D, n_mid, n_mid, K, B, C), "n_gpus": world, "scaling": "weak", "precision": prec,
+           "value": n / (ms * 1e-3), "unit": "grad-evals/s", "ms_per_step": ms / steps, "steps": steps,
+           "step": "one sghmc.step of every chain on one minibatch", "gpu_launches_per_step": launches / steps,
+           "algorithmic_flops_per_chain_eval": flops, "algorithmic_tflops": n * flops / (ms * 1e-3) / 1e12 / world,
+           "roofline": roof, "parity": "unpinned (no runnable Chainer reference): NumPy restatement cross-checked against torch.autograd"}
+    s.close()
+    h.close()
+    return out
+
+
+def bench_cfg5_rows(ctx, rank, world, dev, prec, peak_tf, steps=4, rows=1000000, D=2048, K=38, C=8):
+    """BASELINE configs[4]: full-batch HMC softmax, N = 1 M rows x 2048 features x 38 classes, 8 chains replicated on
+    every rank, rows sharded N/G per rank, ONE grouped NCCL all-reduce (gradient + log-lik) per evaluation enqueued by
+    the C driver.  Strong scaling: the total work is the same at every N."""
+    import torch
+    import torch.distributed as dist
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.hmc import hmc
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.softmax import softmax
+    from dropout_hamiltonian_montecarlo_b200.parallel import shard_rows
+    out = {"workload": "HMC softmax %dx%dx%d full batch, %d chains replicated, rows sharded over %d GPU(s)" % (rows, D, K, C, world),
+           "n_gpus": world, "scaling": "strong", "precision": prec, "unit": "grad-evals/s",
+           "collective": "none (1 rank)" if world == 1 else
+           "ncclAllReduce(sum) of [%d x %d] fp32 + [%d] fp64 grouped into one call per evaluation, enqueued from C" % (C, (D + 1) * K, C)}
+    # ---- in-run check (N > 1): a row-sharded gradient equals the 1-rank gradient of the same rows
+    if world > 1:
+        nchk = 65536
+        g = torch.Generator(device=dev).manual_seed(7)
+        Xc = torch.randn(nchk, D, generator=g, device=dev).abs_()
+        yc = torch.randint(0, K, (nchk,), generator=g, device=dev, dtype=torch.int32)
+        rs = np.random.RandomState(3)
+        par = {"weights": rs.normal(0, 0.02, (C, D, K)).astype(np.float32), "bias": rs.normal(0, 0.02, (C, K)).astype(np.float32)}
+        r0, nl = shard_rows(nchk, rank, world)
+        m_sh = softmax({"alpha": 0.01}, precision=prec, row_sharded=True)
+        g_sh = m_sh.grad(par, X_train=Xc[r0:r0 + nl].contiguous(), y_train=yc[r0:r0 + nl].contiguous())
+        ll_sh = m_sh.log_likelihood(par, X_train=m_sh._bound[2][0], y_train=m_sh._bound[2][1])
+        m_sh.unbind()
+        err = torch.zeros(2, dtype=torch.float64, device=dev)
+        if rank == 0:
+            m_1 = softmax({"alpha": 0.01}, precision=prec)
+            g_1 = m_1.grad(par, X_train=Xc, y_train=yc)
+            ll_1 = m_1.log_likelihood(par, X_train=Xc, y_train=yc)
+            m_1.unbind()
+            err[0] = float(np.abs(g_sh["weights"] - g_1["weights"]).max() / np.abs(g_1["weights"]).max())
+            err[1] = float(np.abs(ll_sh - ll_1).max() / np.abs(ll_1).max())
+        dist.broadcast(err, src=0)
+        out["check_grad_vs_1rank"] = {"rows": nchk, "max_rel_err_grad": float(err[0]), "max_rel_err_loglik": float(err[1]),
+                                      "ok": bool(err[0] < 1e-4 and err[1] < 1e-9)}
+        del Xc, yc
+    # ---- the workload: every rank synthesises ITS shard (post-ReLU-like features abs(N(0,1)), SURVEY 8(d))
+    r0, nloc = shard_rows(rows, rank, world)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    Xs = torch.randn(nloc, D, generator=g, device=dev).abs_()
+    ys = torch.randint(0, K, (nloc,), generator=g, device=dev, dtype=torch.int32)
+    m = softmax({"alpha": 0.01}, precision=prec, row_sharded=world > 1)
+    eps, path = 1e-7, 1e-6  # E[L] = 10; one path length shared by the chains (every launch carries all 8)
+    smp = hmc(m, {"weights": np.zeros((D, K), np.float32), "bias": np.zeros(K, np.float32)}, path_length=path,
+              step_size=eps, verbose=False, n_chains=C, seed=3, path_length_mode="shared")
+    smp.sample(niter=1, burnin=0, X_train=Xs, y_train=ys)  # warm-up: binds (operand copies), allocates
+    l0 = ctx.launches
+    ms, res = _timed(world, lambda: smp.sample(niter=steps, burnin=0, X_train=Xs, y_train=ys))
+    launches = ctx.launches - l0
+    n_grad = smp.last_run["n_grad_evals"]  # identical on every rank (replicated chains)
+    st = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    ms = float(st[0])
+    flops_eval = 4.0 * rows * D * K
+    h = m._bound[1]
+    f_gemm = 2.0 * nloc * D * K * C
+    roof = _group_roofline(ctx, lambda: smp.sample(niter=1, burnin=0, X_train=Xs, y_train=ys), {0: f_gemm, 1: f_gemm}, peak_tf)
+    out.update({"value": n_grad / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+                "step": "one HMC transition of the 8 chains (E[L] = 10: ~19 full-data gradient evaluations)",
+                "ms_per_grad_eval_all_chains": ms / (n_grad / C), "rows_per_gpu": nloc, "gpu_launches_per_step": launches / steps,
+                "algorithmic_flops_per_chain_eval": flops_eval, "algorithmic_tflops_total": n_grad * flops_eval / (ms * 1e-3) / 1e12,
+                "allreduce_bytes_per_eval": 4 * C * h.ld + 8 * C, "roofline": roof})
+    if world > 1:  # replicas must stay bit-identical: same draws, same all-reduced gradients
+        post = res[0]
+        t = torch.as_tensor(np.ascontiguousarray(post["weights"][-1])).to(dev)
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        out["check_replicas_identical"] = bool(all(torch.equal(gathered[0], x) for x in gathered))
+        out["check_moved"] = bool(np.abs(post["weights"][-1]).max() > 0)
+    m.unbind()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -408,36 +698,51 @@ def run_ours(args, wl):
         e2e = {"value": n_e2e / dt, "unit": "grad-evals/s", "h2d_bytes_per_step": int(N * D * 4 + N * 4),
                "d2h_bytes_per_step": int(d2h), "api": "hmc.sample(niter=1, X_train=<pinned host>, y_train=<pinned host>)"}
 
-    # ---- ESS / s (second half of BASELINE's metric): a short run at settings where proposals are accepted
-    # (the sum-gradient / mean-energy mismatch of the reference makes the chain move only for
-    # eps <~ 3e-7 at N=60000), Geyer IPS estimator
+    # ---- ESS / s (second half of BASELINE's metric), Geyer initial-positive-sequence estimator.  Two runs:
+    # (1) the headline data at settings where proposals are accepted (the sum-gradient / mean-energy
+    #     mismatch of the reference makes the chain move only for eps <~ 3e-7 at N = 60 000), >= 500 transitions;
+    # (2) the small-N variant (ESS_SMALL) that the CPU arm can also run for hundreds of transitions: both arms, same
+    #     settings, same estimator -> `ess.small_n` here, `cpu_baseline.ess` / the reference arm's `ess` there.
     ess_info = None
     if not args.no_ess:
         from dropout_hamiltonian_montecarlo_b200.ess import ess as ess_fn
-        s2 = SamplerHandle(ctx, h, 0, C, seed=4321, chain_id0=rank * C, precision=PREC[prec], shared_path=shared)
-        s2.set_q(np.zeros((C, h.P), np.float32))
-        e_eps, e_path = args.ess_eps, args.ess_eps * args.ess_L
-        s2.hmc_run(args.ess_burnin, e_eps, e_path, step0=0, keep_samples=False)
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        oe = s2.hmc_run(args.ess_steps, e_eps, e_path, step0=args.ess_burnin, keep_samples=True)
-        ev1.record()
-        torch.cuda.synchronize()
-        t_ess = ev0.elapsed_time(ev1) * 1e-3
-        r = ess_fn(oe["samples"].cpu().numpy(), max_params=48)
-        st = torch.tensor([t_ess, r["min"], r["median"], float(oe["accept_prob"].mean().item())], dtype=torch.float64, device=dev)
-        if world > 1:
-            mx = st.clone()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sm = st.clone()
-            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            st = torch.stack([mx[0], sm[1], sm[2], sm[3] / world])
-        ess_info = {"ess_min_per_s": float(st[1] / st[0]), "ess_median_per_s": float(st[2] / st[0]),
-                    "steps": args.ess_steps, "burnin": args.ess_burnin, "step_size": e_eps, "path_length": e_path,
-                    "mean_accept_prob": float(st[3]), "estimator": "Geyer initial positive sequence, summed over chains, "
-                    "48 random parameters", "seconds": float(st[0])}
-        s2.close()
+
+        def device_ess(hh, e_eps, e_path, n_steps, n_burn, seed):
+            s2 = SamplerHandle(ctx, hh, 0, C, seed=seed, chain_id0=rank * C, precision=PREC[prec], shared_path=shared)
+            s2.set_q(np.zeros((C, hh.P), np.float32))
+            s2.hmc_run(n_burn, e_eps, e_path, step0=0, keep_samples=False)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            oe = s2.hmc_run(n_steps, e_eps, e_path, step0=n_burn, keep_samples=True)
+            ev1.record()
+            torch.cuda.synchronize()
+            t_ess = ev0.elapsed_time(ev1) * 1e-3
+            idx = np.sort(np.random.RandomState(0).choice(hh.P, 48, replace=False))  # the estimator runs on 48 parameters
+            sub = oe["samples"][:, :, torch.as_tensor(idx, device=dev)].cpu().numpy()
+            r = ess_fn(sub, max_params=48)
+            st = torch.tensor([t_ess, r["min"], r["median"], float(oe["accept_prob"].mean().item()), float(oe["n_grad_evals"])],
+                              dtype=torch.float64, device=dev)
+            if world > 1:
+                mx = st.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                sm = st.clone()
+                dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+                st = torch.stack([mx[0], sm[1], sm[2], sm[3] / world, sm[4]])
+            s2.close()
+            return {"ess_min_per_s": float(st[1] / st[0]), "ess_median_per_s": float(st[2] / st[0]), "steps": n_steps,
+                    "burnin": n_burn, "chains": C * world, "step_size": e_eps, "path_length": e_path,
+                    "mean_accept_prob": float(st[3]), "grad_evals_per_s": float(st[4] / st[0]), "seconds": float(st[0]),
+                    "estimator": "Geyer initial positive sequence per chain, summed over chains, 48 random parameters"}
+
+        ess_info = device_ess(h, args.ess_eps, args.ess_eps * args.ess_L, args.ess_steps, args.ess_burnin, 4321)
+        ws = ESS_SMALL
+        Xs_, ys_ = synth(ws["N"], ws["D"], ws["K"], 0, device=dev)
+        ms_ = softmax({"alpha": ws["alpha"]}, precision=prec)
+        hs_ = ms_.bind(Xs_, ys_, n_classes=ws["K"])
+        ess_info["small_n"] = dict(device_ess(hs_, ws["eps"], ws["path"], 400, ws["burnin"], 777), workload=ws["desc"])
+        ms_.unbind()
+        del Xs_, ys_
 
     # ---- same workload on MNIST's value grid (8-bit pixels / 255): the bind-time check finds X exact in bf16 after
     # scaling by 255 and bf16x3 issues 2 MMAs per product instead of 3.  Reported beside the headline, not as it.
@@ -471,6 +776,30 @@ def run_ours(args, wl):
                       "x_operand": ("exact in bf16 after scaling by %g: 2 MMAs per product" % psc) if pex else "not exact"}
         del sp, hp, mp, Xp
 
+    # ---- BASELINE configs 3, 4, 5 as secondary blocks of the same line.  A failure in one of them must not lose the
+    # headline: it is reported in the block instead ("error").
+    secondary = {}
+    peak_tf_all = peaks()[0]
+    want = set(args.blocks.split(",")) if args.blocks else set()
+    for name, fn in (("cfg3", lambda: bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf_all)),
+                     ("cfg4", lambda: bench_cfg4(ctx, X, y, rank, world, dev, prec, peak_tf_all)),
+                     ("cfg5_row_sharded", lambda: bench_cfg5_rows(ctx, rank, world, dev, prec, peak_tf_all,
+                                                                  rows=args.cfg5_rows))):
+        if name not in want:
+            continue
+        try:
+            t0_ = time.perf_counter()
+            blk = fn()
+            blk["block_wall_s"] = time.perf_counter() - t0_
+            secondary[name] = blk
+        except Exception as e:  # noqa: BLE001 -- the block is reported as failed, the line still prints
+            import traceback
+            traceback.print_exc()
+            secondary[name] = {"error": repr(e)[:400]}
+            if world > 1:
+                raise  # ranks would deadlock in the next collective if only one of them failed
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peak_tf, peak_bw, src = peaks()
         # Algorithmic work of the dominant GEMM over the timed region: 2*N*D*K flops per chain-gradient evaluation
@@ -487,22 +816,24 @@ def run_ours(args, wl):
         x_exact, x_scale = h.operand_info()
         mma_mult = (2.0 if x_exact else 3.0) if prec == "bf16x3" else 1.0
         cpu = None if args.no_cpu_baseline else cpu_reference_rate(wl)
+        if cpu is not None and not args.no_ess:
+            cpu["ess"] = cpu_ess_small()
         line = {
             "metric": "grad evals/sec (chains x leapfrog) on MNIST-shape softmax BNN",
             "value": value, "unit": "grad-evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (bf16 hi/lo split x3 on tcgen05, fp32 accumulate)" if prec == "bf16x3" else prec,
             "data": data_desc(),
-            "config": {"workload": wl["desc"], "N": N, "D": D, "K": K, "chains_per_gpu": C, "step_size": wl["eps"],
-                       "path_length": wl["path"], "precision": prec, "path_length_mode": args.path_mode,
+            "config": dict(base_config(args, wl), **{
+                       "precision": prec,
                        "schedule": ("streaming (asynchronous chains, %d gradient launches)" % o["n_phases"]) if o["n_phases"]
                        else "lockstep",
-                       "sweep": "reference (Gauss-Seidel, 2 gradients per leapfrog iteration)",
                        "l2": "inputs larger than L2 (X 94-376 MB + (P-Y)^T 77-245 MB per evaluation)",
                        "grad_evals_launched_incl_masked": n_launched,
                        "x_operand": ("exact in bf16 after scaling by %g: 2 MMAs per product" % x_scale) if x_exact
-                       else "fp32 values: hi/lo split, 3 MMAs per product"},
-            "roofline": {"bound": "tensor", "kernel": "k_tc_gemm<%s>" % dom, "achieved": achieved, "peak": peak_tf,
+                       else "fp32 values: hi/lo split, 3 MMAs per product"}),
+            "roofline": {"bound": "tensor", "kernel": "backward GEMM (X^T (P-Y), split over rows)" if dom == "bwd"
+                         else "forward GEMM (X W + softmax epilogue)", "kernel_group": dom, "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": src, "algorithmic_flops_per_launch": flops_launch,
                          "chains_per_launch_mean": u_dom / max(1, n_dom), "avg_launch_ms": avg * 1e3,
@@ -521,6 +852,8 @@ def run_ours(args, wl):
             line["cpu_baseline"] = cpu
         if pixel_info is not None:
             line["pixel_data"] = pixel_info
+        for k_, v_ in secondary.items():
+            line[k_] = v_
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -541,8 +874,11 @@ def main():
     ap.add_argument("--no-pixels", action="store_true", help="skip the secondary run on 8-bit pixel data")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ess", action="store_true")
-    ap.add_argument("--ess-steps", type=int, default=40)
-    ap.add_argument("--ess-burnin", type=int, default=10)
+    ap.add_argument("--ess-steps", type=int, default=500)
+    ap.add_argument("--ess-burnin", type=int, default=50)
+    ap.add_argument("--blocks", default="cfg3,cfg4,cfg5_row_sharded",
+                    help="secondary blocks to run after the headline (comma separated; empty = none)")
+    ap.add_argument("--cfg5-rows", type=int, default=1000000, help="total rows of the row-sharded workload")
     # ESS settings: swept on B200 (gpurun_out/stage19.log): eps in {5e-8..3e-7} x E[L] in {100, 30}; the shorter
     # trajectories give ~3x the ESS/s (195-226 vs 63-72) because a transition costs 1/3 and accepts more often
     ap.add_argument("--ess-eps", type=float, default=2e-7)

@@ -1,0 +1,317 @@
+"""GPU (B200): parity AT THE SIZES bench.py RUNS.  The golden / small-shape tests exercise the single-CTA kernels and
+other split-K plans; these run the kernel combination the headline and the secondary blocks actually time --
+``k_tc_fwd2`` (cta_group::2) + X.W cache / ``k_softmax_from_z`` + fused reduce/stream-update at 60 000 x 784 x 10 with 64
+ragged chains, the K = 38 / D = 2048 shape of BASELINE config 5, and 128-chain minibatch windows of config 3 -- against
+the fp64 NumPy oracle on the same injected draws.
+
+Tolerance (BASELINE.json north_star): rtol 1e-4 in fp32; here stated per element: an entry passes when
+|got - ref| <= 1e-4 |ref| + atol with atol = 2e-5 max|ref| (gradients, bf16x3) or 2e-6 max|ref| (states), and the worst
+per-element RELATIVE error over all entries larger than 1e-3 max|ref| is printed and bounded, so that "rtol 1e-4" can
+be read off the log instead of being hidden behind a max-norm.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hamiltonian_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from dropout_hamiltonian_montecarlo_b200.hamiltonian.models.gpu.softmax import softmax  # noqa: E402
+from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle, SoftmaxHandle, default_context  # noqa: E402
+
+
+def rel_err_report(got, ref, what, floor=1e-3):
+    """Worst per-element relative error over the entries above floor * max|ref| (+ the max-norm error)."""
+    got, ref = np.asarray(got, np.float64).ravel(), np.asarray(ref, np.float64).ravel()
+    mx = np.abs(ref).max()
+    big = np.abs(ref) > floor * mx
+    worst = float((np.abs(got - ref)[big] / np.abs(ref)[big]).max()) if big.any() else 0.0
+    maxnorm = float(np.abs(got - ref).max() / mx) if mx > 0 else 0.0
+    print("%-44s worst rel err over |ref| > %.0e max: %.2e   max-norm err: %.2e   (%d of %d entries)"
+          % (what, floor, worst, maxnorm, int(big.sum()), ref.size))
+    return worst, maxnorm
+
+
+def close(got, ref, rtol, atol_scale, what):
+    ref = np.asarray(ref, dtype=np.float64)
+    atol = atol_scale * max(1e-300, float(np.abs(ref).max()))
+    np.testing.assert_allclose(np.asarray(got, dtype=np.float64), ref, rtol=rtol, atol=atol, err_msg=what)
+
+
+def test_cfg2_full_size_streaming_trajectories_vs_oracle():
+    """BASELINE configs[1] at full size: 60 000 x 784 x 10, 64 chains, two transitions of the streaming schedule with
+    injected momenta / path-length / accept uniforms (ragged: L between 1 and 6 per chain and step).  Chains 0 and 63
+    are replayed through the fp64 oracle (hmc.py:39-64): samples, accept probabilities and decisions must agree."""
+    N, D, K, C, alpha = 60000, 784, 10, 64, 0.01
+    eps, path, n_steps = 2e-7, 6e-7, 2  # L = ceil(6 u): the chain moves at this step size (SURVEY 8(a'))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X = torch.rand(N, D, generator=g, device="cuda")
+    y = torch.randint(0, K, (N,), generator=g, device="cuda", dtype=torch.int32)
+    rs = np.random.RandomState(5)
+    q0 = rs.normal(0, 0.02, (C, (D + 1) * K)).astype(np.float32)
+    z = rs.normal(size=(n_steps, C, (D + 1) * K)).astype(np.float32)
+    u1 = rs.rand(n_steps, C)
+    u2 = rs.rand(n_steps, C)
+    u1[:, 0] = [0.95, 0.70]   # chain 0: L = 6, then 5
+    u1[:, C - 1] = [0.60, 0.99]  # chain 63: L = 4, then 6
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, N, D, K, alpha)
+    h.bind(X, y)
+    s = SamplerHandle(ctx, h, 0, C, precision=1)
+    s.set_q(q0)
+    out = s.hmc_run(n_steps, eps, path, z_momentum=torch.as_tensor(z), u_path=u1, u_accept=u2, schedule="streaming")
+    assert out["n_phases"] > 0, "the streaming schedule did not run"
+    L = np.ceil(2 * u1 * path / eps)
+    assert out["n_grad_evals"] == int(C + (np.maximum(L - 1, 0) * 2).sum())  # one start point per chain + 2 per iteration
+    samples = out["samples"].cpu().numpy()
+    acc = out["accept_prob"].cpu().numpy()
+    dec = out["accepted"].cpu().numpy()
+    loss = out["loss"].cpu().numpy()
+    Xn, Y = X.cpu().numpy().astype(np.float64), O.one_hot(y.cpu().numpy(), K)
+    model = O.SoftmaxOracle({"alpha": alpha})
+    worst_all = 0.0
+    for c in (0, C - 1):
+        q = {"weights": q0[c, :D * K].reshape(D, K).astype(np.float64), "bias": q0[c, D * K:].astype(np.float64)}
+        for t in range(n_steps):
+            draws = O.TapeDraws([z[t, c, :D * K].reshape(D, K), z[t, c, D * K:]], [u1[t, c], u2[t, c]])
+            r = O.hmc_step(model, q, ["weights", "bias"], eps, path, draws, X_train=Xn, y_train=Y)
+            q = r["q"]
+            ref = O.flatten_par(q, ["weights", "bias"])
+            w, _ = rel_err_report(samples[t, c], ref, "cfg2 chain %d step %d (L=%d) state" % (c, t, r["L"]))
+            worst_all = max(worst_all, w)
+            close(samples[t, c], ref, 1e-4, 2e-6, "chain %d step %d" % (c, t))
+            close(acc[t, c], r["accept_prob"], 5e-4, 1e-6, "accept prob chain %d step %d" % (c, t))
+            if abs(u2[t, c] - r["accept_prob"]) > 1e-6:  # north star: identical except at draws within 1e-6 of the threshold
+                assert bool(dec[t, c]) == r["accepted"], "decision chain %d step %d" % (c, t)
+            close(loss[t, c], model.negative_log_posterior(q, X_train=Xn, y_train=Y), 1e-5, 1e-9, "loss")
+    assert worst_all < 1e-4, worst_all
+    s.close()
+    h.close()
+
+
+def test_cfg2_full_size_gradient_per_element_error():
+    """The full-size gradient (64 chains in one launch) with the error stated per element, not as a max-norm."""
+    N, D, K, C, alpha = 60000, 784, 10, 64, 0.01
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.rand(N, D, generator=g, device="cuda")
+    y = torch.randint(0, K, (N,), generator=g, device="cuda", dtype=torch.int32)
+    q = (torch.randn(C, (D + 1) * K, generator=g, device="cuda") * 0.02)
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, N, D, K, alpha)
+    h.bind(X, y)
+    g3, ll3 = h.grad(h.pack(q), 0, N, 1)
+    Xn, Y = X.cpu().numpy().astype(np.float64), O.one_hot(y.cpu().numpy(), K)
+    for c in (0, 31, C - 1):
+        qc = q[c].cpu().numpy().astype(np.float64)
+        par = {"weights": qc[:D * K].reshape(D, K), "bias": qc[D * K:]}
+        ref = O.flatten_par(O.softmax_grad(par, Xn, Y, alpha), ["weights", "bias"])
+        worst, maxnorm = rel_err_report(g3[c, :h.P].cpu().numpy(), ref, "cfg2 gradient chain %d (bf16x3)" % c)
+        assert maxnorm < 5e-5 and worst < 2e-2, (worst, maxnorm)  # cancellation: entries at 1e-3 max carry 1e-3 of their size
+        close(g3[c, :h.P].cpu().numpy(), ref, 1e-4, 2e-5, "chain %d" % c)
+    h.close()
+
+
+def test_cfg5_shape_gradient_vs_oracle():
+    """BASELINE configs[4] shape: D = 2048, K = 38 (padded to 40 classes per chain in the GEMMs), 8 chains, 65 536 rows
+    of abs(N(0,1)) features: gradient and log-likelihood of three chains against the fp64 oracle (softmax.py:45-72)."""
+    N, D, K, C, alpha = 65536, 2048, 38, 8, 0.01
+    g = torch.Generator(device="cuda").manual_seed(2)
+    X = torch.randn(N, D, generator=g, device="cuda").abs_()
+    y = torch.randint(0, K, (N,), generator=g, device="cuda", dtype=torch.int32)
+    q = torch.randn(C, (D + 1) * K, generator=g, device="cuda") * 0.01
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, N, D, K, alpha)
+    h.bind(X, y)
+    qd = h.pack(q)
+    g3, ll3 = h.grad(qd, 0, N, 1)
+    g32, ll32 = h.grad(qd, 0, N, 0)
+    assert (g3 - g32).abs().max().item() < 1e-4 * g32.abs().max().item()
+    Xn, Y = X.cpu().numpy().astype(np.float64), O.one_hot(y.cpu().numpy(), K)
+    for c in (0, 3, C - 1):
+        qc = q[c].cpu().numpy().astype(np.float64)
+        par = {"weights": qc[:D * K].reshape(D, K), "bias": qc[D * K:]}
+        ref = O.flatten_par(O.softmax_grad(par, Xn, Y, alpha), ["weights", "bias"])
+        worst, maxnorm = rel_err_report(g3[c, :h.P].cpu().numpy(), ref, "cfg5-shape gradient chain %d (bf16x3)" % c)
+        assert maxnorm < 5e-5, maxnorm
+        close(g3[c, :h.P].cpu().numpy(), ref, 1e-4, 2e-5, "bf16x3 chain %d" % c)
+        close(ll3[c].item(), O.softmax_log_likelihood(par, Xn, Y), 2e-6, 0.0, "log-lik chain %d" % c)
+    # one HMC transition of the 8 chains (shared path length, as bench.py runs config 5) against the oracle, chain 0:
+    # covers the X.W cache at KP = 40 (wide-class epilogue + k_softmax_from_z_vec<40>)
+    eps, path = 2e-7, 6e-7
+    s = SamplerHandle(ctx, h, 0, C, precision=1, shared_path=True)
+    q0 = q.cpu().numpy()
+    s.set_q(q0)
+    rs = np.random.RandomState(9)
+    z = rs.normal(size=(1, C, h.P)).astype(np.float32)
+    u1 = np.full((1, C), 0.55)  # L = 4
+    u2 = rs.rand(1, C)
+    out = s.hmc_run(1, eps, path, z_momentum=torch.as_tensor(z), u_path=u1, u_accept=u2)
+    model = O.SoftmaxOracle({"alpha": alpha})
+    par = {"weights": q0[0, :D * K].reshape(D, K).astype(np.float64), "bias": q0[0, D * K:].astype(np.float64)}
+    r = O.hmc_step(model, par, ["weights", "bias"], eps, path,
+                   O.TapeDraws([z[0, 0, :D * K].reshape(D, K), z[0, 0, D * K:]], [u1[0, 0], u2[0, 0]]), X_train=Xn, y_train=Y)
+    rel_err_report(out["samples"][0, 0].cpu().numpy(), O.flatten_par(r["q"], ["weights", "bias"]), "cfg5-shape HMC step, chain 0")
+    close(out["samples"][0, 0].cpu().numpy(), O.flatten_par(r["q"], ["weights", "bias"]), 1e-4, 2e-6, "state")
+    close(out["accept_prob"][0, 0].item(), r["accept_prob"], 5e-4, 1e-6, "accept prob")
+    s.close()
+    h.close()
+
+
+def test_cfg3_shape_sgld_128_chains_vs_oracle():
+    """BASELINE configs[2] shape: 128 chains, minibatches of 500 rows, 784 x 10 -- six sequential minibatch updates in
+    one library call (fused reduce + update + next-operand kernel, 128-chain windows) with injected noise, three chains
+    replayed through the oracle (sgld.py:31-46 + the step-size schedule of sgmcmc.py:67-73)."""
+    N, D, K, C, B, alpha, eps0 = 3000, 784, 10, 128, 500, 0.01, 1e-5
+    rs = np.random.RandomState(11)
+    X = rs.rand(N, D).astype(np.float32)
+    y = rs.randint(0, K, N).astype(np.int32)
+    q0 = rs.normal(0, 0.05, (C, (D + 1) * K)).astype(np.float32)
+    nb = N // B
+    z = rs.normal(size=(nb, C, (D + 1) * K)).astype(np.float32)
+    ctx = default_context()
+    h = SoftmaxHandle(ctx, N, D, K, alpha)
+    h.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda())
+    s = SamplerHandle(ctx, h, 1, C, precision=1)
+    s.set_q(q0)
+    out = s.sg_run(1, 0, B, eps0, n_rows=N, z=torch.as_tensor(z))
+    got = out["samples"][0].cpu().numpy()
+    Xn, Y = X.astype(np.float64), O.one_hot(y, K)
+    model = O.SoftmaxOracle({"alpha": alpha})
+    for c in (0, 64, C - 1):
+        start = {"weights": q0[c, :D * K].reshape(D, K).astype(np.float64), "bias": q0[c, D * K:].astype(np.float64)}
+        tape = []
+        for j in range(nb):
+            tape += [z[j, c, :D * K].reshape(D, K), z[j, c, D * K:]]
+        post, logp, info = O.sgmcmc_sample(O.sgld_step, model, start, eps0, 1, 0, B, O.TapeDraws(tape, []), Xn, Y)
+        ref = np.concatenate([post["weights"][0].ravel(), post["bias"][0].ravel()])
+        worst, _ = rel_err_report(got[c], ref, "cfg3-shape SGLD chain %d after %d minibatches" % (c, nb))
+        assert worst < 1e-4, worst
+        close(got[c], ref, 1e-4, 2e-6, "chain %d" % c)
+        close(out["logp"][0, c].item(), logp[0], 1e-5, 0.0, "logp chain %d" % c)
+        assert abs(out["final_step_size"] - info["final_eps"]) < 1e-18
+    s.close()
+    h.close()
+
+
+def test_predict_stochastic_injected_mask():
+    """softmax.predict_stochastic (models/cpu/softmax.py:91-100): a Bernoulli(p) mask from the global NumPy generator
+    multiplies X, then net().  The mask is injected by replaying np.random.binomial."""
+    rs = np.random.RandomState(3)
+    N, D, K, C = 300, 50, 7, 3
+    X = rs.rand(N, D)
+    W = rs.normal(0, .5, (C, D, K))
+    b = rs.normal(0, .5, (C, K))
+    Z = rs.binomial(1, 0.7, size=X.shape)
+    m = softmax({"alpha": 0.01})
+    orig = np.random.binomial
+    calls = []
+
+    def fake(n, p, size=None):
+        calls.append((n, p, tuple(size)))
+        return Z
+
+    np.random.binomial = fake
+    try:
+        probs = m.predict_stochastic({"weights": W, "bias": b}, X, prob=True, p=0.7)
+        labels = m.predict_stochastic({"weights": W[0], "bias": b[0]}, X, prob=False, p=0.7)
+    finally:
+        np.random.binomial = orig
+    assert calls == [(1, 0.7, X.shape), (1, 0.7, X.shape)]
+    Xt = np.multiply(X, Z)
+    for c in range(C):
+        ref = O.softmax_probs(O.softmax_logits({"weights": W[c], "bias": b[c]}, Xt))
+        close(probs[c], ref, 1e-4, 1e-6, "probs chain %d" % c)
+    ref0 = O.softmax_probs(O.softmax_logits({"weights": W[0], "bias": b[0]}, Xt))
+    top2 = np.sort(ref0, axis=1)
+    sure = (top2[:, -1] - top2[:, -2]) > 1e-4  # rows whose argmax is not a numerical tie
+    assert np.array_equal(labels[sure], ref0.argmax(1)[sure])
+
+
+def test_sgd_fit_twice_restarts_the_momentum():
+    """sgd.py:35: every fit() starts from momentum = zeros_like(par) -- a second fit() on the same object (and a
+    fit_dropout() after a fit(), the usual MAP-start recipe) must not inherit the first call's heavy-ball momentum."""
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.sgd import sgd
+    rs = np.random.RandomState(4)
+    N, D, K, alpha, eps, gamma, B = 600, 30, 5, 0.01, 1e-3, 0.9, 100
+    X = rs.rand(N, D)
+    y = rs.randint(0, K, N)
+    Y = O.one_hot(y, K)
+    start = {"weights": rs.normal(0, .1, (D, K)), "bias": rs.normal(0, .1, K)}
+    m = softmax({"alpha": alpha}, precision="fp32")
+    s = sgd(m, start, step_size=eps)
+    ref_p, ref_l = O.sgd_fit(O.SoftmaxOracle({"alpha": alpha}), start, eps, 2, B, gamma, X.astype(np.float32).astype(np.float64), Y)
+    for attempt in range(2):
+        par, loss = s.fit(epochs=2, batch_size=B, gamma=gamma, X_train=X, y_train=Y)
+        close(par["weights"], ref_p["weights"], 1e-4, 2e-6, "fit #%d weights" % attempt)
+        close(par["bias"], ref_p["bias"], 1e-4, 2e-6, "fit #%d bias" % attempt)
+        close(loss, ref_l, 1e-5, 0.0, "fit #%d loss" % attempt)
+
+
+def test_streaming_schedule_split_when_over_budget():
+    """A call whose op tables would exceed the budget is cut into consecutive streaming sub-calls (a single oversized
+    transition runs in lockstep): same draws -> same samples as the unsplit call."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle, SoftmaxHandle, default_context
+rs = np.random.RandomState(0)
+N, D, K, C = 400, 24, 4, 6
+X = torch.as_tensor(rs.rand(N, D).astype(np.float32)).cuda(); y = torch.as_tensor(rs.randint(0, K, N).astype(np.int32)).cuda()
+ctx = default_context(); h = SoftmaxHandle(ctx, N, D, K, 0.01); h.bind(X, y)
+s = SamplerHandle(ctx, h, 0, C, seed=3, precision=0); s.set_q(rs.normal(0, .1, (C, h.P)).astype(np.float32))
+o = s.hmc_run(7, 1e-3, 8e-3, schedule="streaming")
+np.save(sys.argv[1], o["samples"].cpu().numpy()); print(o["n_phases"], o["n_grad_evals"])
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    import tempfile
+    outs = []
+    for budget in ("", "150"):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            env = dict(os.environ)
+            if budget:
+                env["BHMC_STREAM_OPS_MAX"] = budget  # 6 chains: at most 25 phases per sub-call
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append((np.load(f.name), r.stdout.split()))
+    (a, ia), (b, ib) = outs
+    assert int(ib[0]) != int(ia[0])  # the budget really cut the call (sub-calls re-evaluate their start points)
+    np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
+
+
+def test_hmc_returns_positions_and_drawn_momentums():
+    """hmc.py:44,108-111: step() returns copies of the start point and of the momentum it drew; sample() returns one
+    [position] / [momentum] entry per iteration.  With a path length so short that L <= 1 no leapfrog iteration runs
+    and the proposal (q, -p0) is accepted with A = 1, so the returned momentum must be minus the drawn one."""
+    from dropout_hamiltonian_montecarlo_b200.hamiltonian.inference.gpu.hmc import hmc
+    rs = np.random.RandomState(12)
+    N, D, K = 200, 12, 3
+    X, y = rs.rand(N, D), rs.randint(0, K, N)
+    Y = O.one_hot(y, K)
+    start = {"weights": rs.normal(0, .1, (D, K)), "bias": rs.normal(0, .1, K)}
+    s = hmc(softmax({"alpha": 0.01}, precision="fp32"), start, path_length=1e-9, step_size=1e-3, verbose=False, seed=21)
+    q, p, positions, momentums, a = s.step(start, None, None, X_train=X, y_train=Y)
+    assert a == 1.0 and len(positions) == 1 and len(momentums) == 1
+    assert positions[0]["weights"] is not start["weights"]
+    np.testing.assert_allclose(positions[0]["weights"], start["weights"], rtol=1e-6)
+    np.testing.assert_allclose(momentums[0]["weights"], -p["weights"], rtol=1e-6)
+    np.testing.assert_allclose(momentums[0]["bias"], -p["bias"], rtol=1e-6)
+    assert abs(np.std(momentums[0]["weights"]) - 1.0) < 0.35
+    # sample(): lazy traces, three chains, Philox draws
+    s3 = hmc(softmax({"alpha": 0.01}, precision="fp32"), start, path_length=1e-9, step_size=1e-3, verbose=False, seed=22,
+             n_chains=3)
+    post, loss, pos, mom = s3.sample(niter=4, burnin=2, X_train=X, y_train=Y)
+    assert len(pos) == 4 and len(mom) == 4 and post["weights"].shape == (4, 3, D, K)
+    for i in range(4):
+        np.testing.assert_allclose(pos[i][0]["weights"][1], start["weights"], rtol=1e-6)  # the chain never moves (L <= 1)
+    last_p = s3._sampler[1].get(1)  # momentum after the last transition = -(momentum drawn in iteration 3)
+    np.testing.assert_allclose(np.concatenate([mom[3][0]["weights"].reshape(3, -1), mom[3][0]["bias"]], axis=1), -last_p, rtol=1e-6)
+    assert not np.allclose(mom[0][0]["weights"], mom[1][0]["weights"])
+    # injected draws: the trace hands back the tape
+    from conftest import TapeRng
+    zt = rs.normal(size=(1 + 2) * (D * K + K))  # one discarded draw (hmc.py:93) + two iterations
+    s1 = hmc(softmax({"alpha": 0.01}, precision="fp32"), start, path_length=1e-9, step_size=1e-3, verbose=False)
+    _, _, pos1, mom1 = s1.sample(niter=2, burnin=0, rng=TapeRng(zt), X_train=X, y_train=Y)
+    np.testing.assert_allclose(mom1[1][0]["weights"].ravel(), zt[2 * (D * K + K):2 * (D * K + K) + D * K], rtol=1e-6)
