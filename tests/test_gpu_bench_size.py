@@ -28,8 +28,17 @@ def rel_err_report(got, ref, what, floor=1e-3):
     big = np.abs(ref) > floor * mx
     worst = float((np.abs(got - ref)[big] / np.abs(ref)[big]).max()) if big.any() else 0.0
     maxnorm = float(np.abs(got - ref).max() / mx) if mx > 0 else 0.0
-    print("%-44s worst rel err over |ref| > %.0e max: %.2e   max-norm err: %.2e   (%d of %d entries)"
-          % (what, floor, worst, maxnorm, int(big.sum()), ref.size))
+    line = ("%-44s worst rel err over |ref| > %.0e max: %.2e   max-norm err: %.2e   (%d of %d entries)"
+            % (what, floor, worst, maxnorm, int(big.sum()), ref.size))
+    print(line)
+    try:  # kept next to the other GPU-box logs (gpurun_out/ travels back; profiles/ gets the copy that is committed)
+        import os
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        if os.path.isdir(d):
+            with open(os.path.join(d, "parity_rel_err.log"), "a") as f:
+                f.write(line + "\n")
+    except OSError:
+        pass
     return worst, maxnorm
 
 
