@@ -334,6 +334,13 @@ struct SoftmaxModel : ModelBase {
     if (logistic || prec == BHMC_PREC_FP32) return BHMC_ERR_UNSUPPORTED;
     return tc_softmax_grad(ctx, d, fs.q, C, ld, alpha, row0, nrows, nullptr, stat, prec == BHMC_PREC_BF16X3, &fs);
   }
+  int sg_steps_persistent(int C, int64_t ld, int prec, const FusedStep& fs, int64_t row_first, int64_t batch, int n_steps,
+                          const float* eps_dev, int64_t z_step_stride, uint64_t step0) override {
+    if (logistic || prec == BHMC_PREC_FP32) return BHMC_ERR_UNSUPPORTED;
+    zcache.valid = false;
+    return tc_softmax_sg_persistent(ctx, d, C, ld, alpha, prec == BHMC_PREC_BF16X3, fs, row_first, batch, n_steps, eps_dev,
+                                    z_step_stride, step0);
+  }
   int grad_fused_stream(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, float* g, double* stat,
                         uint32_t hint, const FusedStream& fst) override {
     if (logistic || prec == BHMC_PREC_FP32) return BHMC_ERR_UNSUPPORTED;
@@ -1499,8 +1506,67 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
   }
   bool try_fused = fused_env && !s->hook && !s->row_comm && !(run->dropout_keep > 0.0);
   bool wt_ready = false;
+  // Persistent path (softmax_persist.cuh): a whole epoch of minibatch steps in ONE cooperative launch -- forward,
+  // grid barrier, backward with the update applied from tensor memory, grid barrier, per step.  The step sizes of
+  // every step of the call are computed here (the schedule is host arithmetic, sgmcmc.py:67-73) and uploaded once.
+  // BHMC_PERSIST=0 keeps the per-step launches (A/B measurements).
+  static int persist_env = -1;
+  if (persist_env < 0) {
+    const char* e = getenv("BHMC_PERSIST");
+    persist_env = e ? atoi(e) : 1;
+  }
+  bool try_persist = try_fused && persist_env && nb < (1 << 30);
+  const float* eps_dev = nullptr;
+  if (try_persist) {
+    const int64_t total = (int64_t)(run->burnin + run->epochs) * nb;
+    if (total > 0) {
+      if (ctx->pinned_inflight) {
+        BHMC_CUDA_OK(cudaEventSynchronize(ctx->pinned_ev));
+        ctx->pinned_inflight = false;
+      }
+      void *pin = nullptr, *dev = nullptr;
+      BHMC_TRY(ctx->get_pinned(sizeof(float) * (size_t)total, &pin));
+      BHMC_TRY(ctx->get_scratch(14, sizeof(float) * (size_t)total, &dev));
+      float* eh = (float*)pin;
+      double ee = eps;
+      int64_t kk = 0;
+      for (int e = 0; e < run->burnin + run->epochs; ++e)
+        for (int64_t j = 0; j < nb; ++j, ++kk) {
+          eh[kk] = sgd ? (float)run->step_size : (float)ee;
+          if (!sgd && e >= run->burnin) ee = run->step_size * (1.0 / (1.0 + (double)j * decay * num_batches));
+        }
+      BHMC_CUDA_OK(cudaMemcpyAsync(dev, pin, sizeof(float) * (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+      if (!ctx->pinned_ev) BHMC_CUDA_OK(cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming));
+      BHMC_CUDA_OK(cudaEventRecord(ctx->pinned_ev, ctx->stream));
+      ctx->pinned_inflight = true;
+      eps_dev = (const float*)dev;
+    }
+  }
   for (int e = 0; e < run->burnin + run->epochs; ++e) {
     const bool sampling = e >= run->burnin;
+    if (try_persist && eps_dev) {
+      FusedStep fs{};
+      fs.kind = cfg.kind;
+      fs.q = s->q;
+      fs.p = s->p;
+      fs.gamma = (float)run->gamma;
+      fs.z = run->z_dev ? run->z_dev + (size_t)k * C * P : nullptr;
+      fs.ld_z = P;
+      fs.seed = cfg.seed;
+      fs.chain_id0 = cfg.chain_id0;
+      ctx->cur_units = C;
+      const int rc = mb->sg_steps_persistent(C, ld, cfg.precision, fs, 0, run->batch_size, (int)nb, eps_dev + k, (int64_t)C * P,
+                                             (uint64_t)(run->step0 + k));
+      if (rc == BHMC_OK) {
+        run->n_grad_evals += (int64_t)C * nb;
+        if (!sgd && sampling) eps = run->step_size * (1.0 / (1.0 + (double)(nb - 1) * decay * num_batches));
+        k += nb;
+        wt_ready = false;
+        goto epoch_end;
+      }
+      if (rc != BHMC_ERR_UNSUPPORTED) return rc;
+      try_persist = false;
+    }
     for (int64_t j = 0; j < nb; ++j, ++k) {
       const int64_t row0 = j * run->batch_size;
       if (try_fused) {
@@ -1558,6 +1624,7 @@ int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
         if (sampling) eps = run->step_size * (1.0 / (1.0 + (double)j * decay * num_batches));
       }
     }
+  epoch_end:
     if (sampling) {
       const int i = e - run->burnin;
       if (run->logp_dev) {  // NLP(q, last batch), sgmcmc.py:79 / sgd.py:42

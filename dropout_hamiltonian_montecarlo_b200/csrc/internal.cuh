@@ -137,6 +137,10 @@ struct ModelBase {
   // gradient at fs.q followed by the sampler's parameter update in the same launch sequence (no g materialised);
   // BHMC_ERR_UNSUPPORTED = caller falls back to grad() + the separate update kernel
   virtual int grad_fused_step(int, int64_t, int64_t, int64_t, int, double*, const FusedStep&) { return BHMC_ERR_UNSUPPORTED; }
+  // n_steps minibatch steps (gradient + update each) in one launch; same fallback convention
+  virtual int sg_steps_persistent(int, int64_t, int, const FusedStep&, int64_t, int64_t, int, const float*, int64_t, uint64_t) {
+    return BHMC_ERR_UNSUPPORTED;
+  }
   // gradient (g IS written) + the streaming schedule's next update in the reduce launch; same fallback convention
   virtual int grad_fused_stream(const float*, int, int64_t, int64_t, int64_t, int, float*, double*, uint32_t,
                                 const FusedStream&) {
@@ -369,6 +373,13 @@ enum { ZMODE_NONE = 0, ZMODE_STORE = 1, ZMODE_USE = 2 };  // USE falls back to a
 int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, int64_t ld, float alpha,
                     int64_t row0, int64_t nrows, float* g, double* loglik, bool split3, const FusedStep* fs = nullptr,
                     ZCache* zc = nullptr, int zmode = ZMODE_NONE, const FusedStream* fst = nullptr, bool prepared = false);
+
+// n_steps consecutive minibatch steps (rows row_first + j*batch) of SGLD / SGD in ONE cooperative launch
+// (softmax_persist.cuh); eps_dev[n_steps] = step size of every step; fs.z (if any) advances by z_step_stride per step.
+// BHMC_ERR_UNSUPPORTED = no persistent kernel for this shape: use the per-step path.
+int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t ld, float alpha, bool split3, const FusedStep& fs,
+                             int64_t row_first, int64_t batch, int n_steps, const float* eps_dev, int64_t z_step_stride,
+                             uint64_t step0);
 
 // ---- mlp.cu -----------------------------------------------------------------------------------
 ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int n_out, float alpha, float ratio,

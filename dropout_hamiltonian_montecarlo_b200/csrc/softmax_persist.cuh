@@ -1,0 +1,437 @@
+// Persistent minibatch kernel: MANY SGLD / SGD steps of the softmax model in ONE launch.
+// Included by softmax_tc.cu (inside namespace bhmc, after its kernels and host helpers).
+//
+// Reference path: sgmcmc.sample's minibatch loop (inference/cpu/sgmcmc.py:55-77) calling sgld.step (sgld.py:31-46) /
+// sgd.fit's loop (sgd.py:36-41), each step = softmax.grad on a 500-row window (models/cpu/softmax.py:45-61) + update.
+//
+// Why: at BASELINE config 3 (128 chains, 500-row windows, 784 x 10) one step is ~2 us of tensor work per GEMM, but the
+// three-launch form of round 1 (forward GEMM, backward GEMM, fused reduce/update/prep) cost 41-43 us per step: each
+// launch paid its own ramp (launch latency even with programmatic dependent launch, barrier init, TMEM allocation,
+// pipeline fill, tail) for 13 / 9 K-chunks of work, and the split-K reduce existed only to occupy more SMs.
+// Here one cooperative launch of one CTA per SM runs a whole epoch:
+//   phase F  forward items (row tile x chain tile): TMA -> tcgen05.mma -> softmax epilogue -> (P-Y)^T hi/lo  (as k_tc_gemm)
+//   grid barrier
+//   phase B  backward items (feature tile x chain tile), NO split-K: the item owns its [128 features x cpt chains]
+//            block of the gradient, so its epilogue applies the parameter update directly from tensor memory
+//            (g = acc/s + alpha q; SGLD: p = 2 eps z - eps/2 g, q += p with Philox or injected z; SGD: heavy ball)
+//            and writes the bf16 hi/lo operand copy of the new weights for the next step's forward pass
+//   grid barrier
+// No gradient, no split-K partials and no per-step operand preparation ever reach HBM; mbarrier rings, TMEM and the
+// warp roles live across steps.  Data written with ordinary stores in one phase ((P-Y)^T, W^T operand) and read by
+// TMA (async proxy) in the next is ordered by fence.proxy.async on both sides of the grid barrier.
+
+struct PersistParams {
+  int D, K, C, cpt, BN, n_tiles;  // chains per N tile, UMMA N, chain tiles
+  int k_chunks_f;                 // BK-chunks of the feature dimension
+  int m_tiles_b;                  // 128-row tiles of the D+1 gradient rows (row D = bias)
+  int split3, stages;
+  int64_t ld, Dp;
+  float* q;
+  float* p;
+  const int32_t* labels;          // label of bound row 0
+  int64_t batch, row_first;       // step j works on rows [row_first + j*batch, +batch)
+  int n_steps;
+  const float* eps;               // [n_steps] step size of every step (the schedule is the host's, sgmcmc.py:72-73)
+  float gamma, alpha, scale;      // scale = 1 / (scale of the bound X operand)
+  int kind;                       // BHMC_KIND_SGLD / BHMC_KIND_SGD
+  const float* z;                 // injected N(0,1) tape [n_steps][C, ld_z] or nullptr (Philox)
+  int64_t ld_z, z_step_stride;
+  uint64_t seed;
+  int64_t chain_id0;
+  uint64_t step0;                 // global index of step 0 (Philox stream)
+  __nv_bfloat16 *wt_hi, *wt_lo, *dmt_hi, *dmt_lo;
+  int dm_rows;                    // rows per (P-Y)^T slab = n_tiles * BN
+  int xt_rows;                    // rows per X^T slab (Dt_pad)
+  unsigned int* bar;              // grid barrier counter (zeroed before the launch)
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Grid-wide barrier of a cooperative launch (every CTA resident).  Monotonic counter: the n-th barrier waits for
+// n * gridDim.x arrivals.  Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  fence_proxy_async_all();  // this thread's ordinary stores must be visible to TMA reads issued after the barrier
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > 4000000000LL) {
+        printf("bhmc: grid barrier timed out (block %d, %u of %u)\n", blockIdx.x, v, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  fence_proxy_async_all();
+}
+
+// Update epilogue of one backward tile: thread = gradient row d (feature; d == D is the bias row), EW/4 warps of a TMEM
+// lane quarter split the tile's chains.  Element index inside a chain row: i = d*K + k (weights [D,K] row-major, then
+// the bias), so a thread owns K consecutive parameters per chain.
+template <int KP, int EW, int KIND>
+__device__ __forceinline__ void sg_update_tile(const PersistParams& p, uint32_t tacc, int mt, int nt, int part, int t, int step,
+                                               float eps) {
+  constexpr int PARTS = EW / 4;
+  // Philox blocks (4 normals each) that KP consecutive elements starting at i0 = d*KP can overlap: i0 & 3 is 0 when
+  // KP % 4 == 0, 0 or 2 when KP is even, anything otherwise
+  constexpr int MAXOFF = (KP % 4 == 0) ? 0 : (KP % 2 == 0) ? 2 : 3;
+  constexpr int NB = (MAXOFF + KP + 3) / 4;
+  const int d = mt * BM + t;
+  const bool row_ok = d <= p.D;
+  const int64_t i0 = (int64_t)d * KP;   // KP == K (exact class count)
+  const uint64_t gstep = p.step0 + (uint64_t)step;
+  const uint32_t slo = (uint32_t)gstep, shi = TAG_NOISE | (uint32_t)((gstep >> 32) & 0xffffff);
+  for (int cc = part; cc < p.cpt; cc += PARTS) {
+    const int c = nt * p.cpt + cc;
+    if (c >= p.C) break;  // warp-uniform
+    uint32_t raw[KP];
+    tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
+    float qe[KP], ze[KP];
+    float* qrow = p.q + (int64_t)c * p.ld + i0;
+    float* prow = p.p + (int64_t)c * p.ld + i0;
+    if (row_ok) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) qe[k] = __ldcg(qrow + k);  // L2: another SM wrote it one step ago
+      if (KIND == BHMC_KIND_SGLD) {
+        if (p.z) {
+          const float* zr = p.z + (int64_t)step * p.z_step_stride + (int64_t)c * p.ld_z + i0;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) ze[k] = __ldcs(zr + k);
+        } else {
+          // the generator hands out 4 normals per element block (i >> 2), exactly as k_sgld / k_tc_reduce_step key them
+          float n[NB * 4];
+          const uint32_t b0 = (uint32_t)(i0 >> 2);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const float4 v = philox_normal4(p.seed, p.chain_id0 + c, b0 + (uint32_t)b, slo, shi);
+            n[4 * b] = v.x, n[4 * b + 1] = v.y, n[4 * b + 2] = v.z, n[4 * b + 3] = v.w;
+          }
+          const int off = (int)(i0 & 3);
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            float v = n[k];
+            if constexpr (MAXOFF >= 2) v = off == 2 ? n[k + 2] : v;
+            if constexpr (MAXOFF >= 3) v = off == 1 ? n[k + 1] : off == 3 ? n[k + 3] : v;
+            ze[k] = v;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) ze[k] = __ldcg(prow + k);  // heavy-ball momentum
+      }
+    }
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        const float g = fmaf(p.alpha, qe[k], __uint_as_float(raw[k]) * p.scale);  // X^T(P-Y) + alpha q
+        const float pe = KIND == BHMC_KIND_SGLD ? (2.0f * eps) * ze[k] - (0.5f * eps) * g   // sgld.py:31-46
+                                                : p.gamma * ze[k] - eps * g;                // sgd.py:40
+        qe[k] += pe;
+        prow[k] = pe;
+        qrow[k] = qe[k];
+      }
+      if (d < p.D) {  // operand copy of the new weights for the next forward pass (the bias is added in the epilogue)
+        __nv_bfloat16* wh = p.wt_hi + ((int64_t)c * KP) * p.Dp + d;
+        __nv_bfloat16* wl = p.wt_lo ? p.wt_lo + ((int64_t)c * KP) * p.Dp + d : nullptr;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          __nv_bfloat16 hb, lb;
+          split_bf16(p.scale * qe[k], hb, lb);
+          wh[(int64_t)k * p.Dp] = hb;
+          if (wl) wl[(int64_t)k * p.Dp] = lb;
+        }
+      }
+    }
+  }
+}
+
+template <int KP, int EW>
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
+k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_constant__ CUtensorMap tmXa_lo,
+                const __grid_constant__ CUtensorMap tmWt_hi, const __grid_constant__ CUtensorMap tmWt_lo,
+                const __grid_constant__ CUtensorMap tmXt_hi, const __grid_constant__ CUtensorMap tmXt_lo,
+                const __grid_constant__ CUtensorMap tmDm_hi, const __grid_constant__ CUtensorMap tmDm_lo, const PersistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_bytes = BM * BK * 2, b_bytes = p.BN * BK * 2;
+  const int na = p.split3 == 1 ? 2 : 1, nb = p.split3 ? 2 : 1;
+  const int stage_bytes = na * a_bytes + nb * b_bytes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  // ring / accumulator bookkeeping of each role (lives across phases and steps)
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  unsigned int n_bar = 0;
+
+  // one work item of either phase, seen from the three roles
+  auto produce = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* b_hi, const CUtensorMap* b_lo,
+                     int n_chunks, int a_k0, int a_dk, int a_m0, int a_dm, int b_k0, int b_dk, int b_n0, int b_dn) {
+    // chunk k: A box at (a_k0 + k*a_dk, a_m0 + k*a_dm), B box at (b_k0 + k*b_dk, b_n0 + k*b_dn)
+    for (int k = 0; k < n_chunks; ++k) {
+      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+      const uint32_t full = smem_u32(&bar_full[stage]);
+      mbar_expect_tx(full, (uint32_t)stage_bytes);
+      const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + na * a_bytes;
+      tma_load_2d(sa, a_hi, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
+      if (na == 2) tma_load_2d(sa + a_bytes, a_lo, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
+      tma_load_2d(sb, b_hi, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
+      if (p.split3) tma_load_2d(sb + b_bytes, b_lo, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
+      if (++stage == p.stages) stage = 0, phase ^= 1u;
+    }
+  };
+  auto issue = [&](int n_chunks) {  // whole warp, warp-uniform; the elected lane issues
+    const int buf = it & 1;
+    const uint32_t use = (uint32_t)(it >> 1);
+    mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);
+    tcgen05_fence_after();
+    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+    for (int k = 0; k < n_chunks; ++k) {
+      mbar_wait(smem_u32(&bar_full[stage]), phase);
+      tcgen05_fence_after();
+      const uint32_t sa = smem_base + stage * stage_bytes;
+      const uint32_t first = k > 0 ? 1u : 0u;
+      if (p.split3 == 1) {
+        const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+        const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+          umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+          umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+        }
+      } else if (p.split3 == 2) {  // X exact in bf16: no lo copy of the X operand
+        const uint64_t a_hi = make_smem_desc(sa);
+        const uint64_t b_hi = make_smem_desc(sa + a_bytes), b_lo = make_smem_desc(sa + a_bytes + b_bytes);
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+          umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+          umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+        }
+      } else {
+        const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+          umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+        }
+      }
+      umma_commit(smem_u32(&bar_empty[stage]));
+      if (++stage == p.stages) stage = 0, phase ^= 1u;
+    }
+    umma_commit(smem_u32(&bar_tfull[buf]));
+    ++it;
+  };
+
+  const int ew = warp & 3, part = (warp - 4) >> 2, t = ew * 32 + lane;
+  const int m_tiles_f = (int)((p.batch + BM - 1) / BM);
+  const int items_f = m_tiles_f * p.n_tiles, items_b = p.m_tiles_b * p.n_tiles;
+  // forward-epilogue parameters that do not change from step to step
+  TcParams pf{};
+  pf.K = p.K, pf.C = p.C, pf.cpt = p.cpt, pf.D = p.D, pf.ld = p.ld, pf.q = p.q, pf.nrows = p.batch;
+  pf.dm_slab = BK, pf.dm_slab_rows = p.dm_rows, pf.dm_ld = BK, pf.dmt_hi = p.dmt_hi, pf.dmt_lo = p.dmt_lo;
+  pf.split3 = p.split3, pf.write_dm = 1, pf.m_tiles = m_tiles_f, pf.skip_loglik = 1;
+
+  for (int step = 0; step < p.n_steps; ++step) {
+    const int64_t row0 = p.row_first + (int64_t)step * p.batch;
+    const int shift = (int)(row0 % BK);
+    const int k_chunks_b = (int)((p.batch + shift + BK - 1) / BK);
+    // ---------------- phase F: Z = X_window . W^T, softmax, (P - Y)^T ----------------
+    if (warp == 0) {
+      if (lane == 0)
+        for (int w = blockIdx.x; w < items_f; w += gridDim.x) {
+          const int mt = w / p.n_tiles, nt = w % p.n_tiles;
+          produce(&tmXa_hi, &tmXa_lo, &tmWt_hi, &tmWt_lo, p.k_chunks_f, 0, BK, (int)row0 + mt * BM, 0, 0, BK, nt * p.BN, 0);
+        }
+    } else if (warp == 1) {
+      for (int w = blockIdx.x; w < items_f; w += gridDim.x) issue(p.k_chunks_f);
+    } else if (warp >= 4) {
+      pf.labels = p.labels + row0;
+      pf.dm_shift = shift;
+      pf.dm_tail = (BK - shift) % BK;
+      for (int w = blockIdx.x; w < items_f; w += gridDim.x, ++it) {
+        const int mt = w / p.n_tiles, nt = w % p.n_tiles;
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+        fwd_epilogue_tile<KP, EW, true>(pf, tacc, mt, nt, part, lane, t);
+        tcgen05_fence_before();
+        mbar_arrive(smem_u32(&bar_tempty[buf]));
+      }
+    }
+    grid_barrier(p.bar, ++n_bar * gridDim.x);
+    // ---------------- phase B: G = X_window^T (P - Y), update, next W^T operand ----------------
+    if (warp == 0) {
+      if (lane == 0) {
+        const int slab0 = (int)((row0 - shift) / BK);  // X^T is stored in blocks of BK rows of X: [slab][xt_rows][BK]
+        for (int w = blockIdx.x; w < items_b; w += gridDim.x) {
+          const int mt = w / p.n_tiles, nt = w % p.n_tiles;
+          produce(&tmXt_hi, &tmXt_lo, &tmDm_hi, &tmDm_lo, k_chunks_b, 0, 0, slab0 * p.xt_rows + mt * BM, p.xt_rows, 0, 0,
+                  nt * p.BN, p.dm_rows);
+        }
+      }
+    } else if (warp == 1) {
+      for (int w = blockIdx.x; w < items_b; w += gridDim.x) issue(k_chunks_b);
+    } else if (warp >= 4) {
+      const float eps = p.eps[step];
+      for (int w = blockIdx.x; w < items_b; w += gridDim.x, ++it) {
+        const int mt = w / p.n_tiles, nt = w % p.n_tiles;
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+        if (p.kind == BHMC_KIND_SGLD) sg_update_tile<KP, EW, BHMC_KIND_SGLD>(p, tacc, mt, nt, part, t, step, eps);
+        else sg_update_tile<KP, EW, BHMC_KIND_SGD>(p, tacc, mt, nt, part, t, step, eps);
+        tcgen05_fence_before();
+        mbar_arrive(smem_u32(&bar_tempty[buf]));
+      }
+    }
+    grid_barrier(p.bar, ++n_bar * gridDim.x);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+template <int KP>
+static int launch_sg_persistent(bhmc_ctx* ctx, const CUtensorMap* maps, const PersistParams& p, int grid, size_t smem) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_sg_persistent<KP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NON_EPI_THREADS + 32 * 16);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // every CTA resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_sg_persistent<KP, 16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
+                                  maps[7], p));
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+// n_steps consecutive minibatch steps (windows row_first + j*batch) of SGLD / SGD in one launch.  BHMC_ERR_UNSUPPORTED
+// when this shape / layout has no persistent kernel (the caller falls back to the per-step launches).
+int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t ld, float alpha, bool split3, const FusedStep& fs,
+                             int64_t row_first, int64_t batch, int n_steps, const float* eps_dev, int64_t z_step_stride,
+                             uint64_t step0) {
+  if (!d.tc_ready || (split3 && !d.has_lo)) return BHMC_ERR_UNSUPPORTED;
+  const int KP = d.Kp, K = d.K, D = d.D;
+  if (K != KP || !(KP == 4 || KP == 8 || KP == 10 || KP == 16)) return BHMC_ERR_UNSUPPORTED;
+  if (d.xa_blocked || d.slab != BK || d.slab_ld != BK || BK != 64) return BHMC_ERR_UNSUPPORTED;
+  if (batch < 1 || row_first < 0 || row_first + (int64_t)n_steps * batch > d.N || n_steps < 1) return BHMC_ERR_UNSUPPORTED;
+  if (row_first + (int64_t)n_steps * batch + BM >= ((int64_t)1 << 31)) return BHMC_ERR_UNSUPPORTED;  // 32-bit TMA coordinates
+  int cpt = 1;
+  while ((cpt * KP) % 16) ++cpt;  // narrowest chain tile: more work items than a wide one, and every step is latency-bound
+  const int BN = cpt * KP, n_tiles = (int)ceil_div(C, cpt);
+  const int64_t Mfwd = round_up(batch, BM);
+  if (Mfwd / BM * n_tiles > 4 * ctx->sm_count) return BHMC_ERR_UNSUPPORTED;  // big windows: the throughput kernels win
+  const int smode = split3 ? (d.x_exact ? 2 : 1) : 0;
+  const int nmat = split3 ? 2 : 1, na = smode == 1 ? 2 : 1;
+  const int stage_bytes = na * BM * BK * 2 + nmat * BN * BK * 2;
+  const int stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const int64_t ncols = (int64_t)C * KP;
+  const int64_t dm_rows = (int64_t)n_tiles * BN, dm_nslab = ceil_div(Mfwd + BK, BK);
+  void *wt = nullptr, *dmt = nullptr, *bar = nullptr;
+  const size_t wt_bytes = (size_t)ncols * d.Dp * 2, dmt_bytes = (size_t)(dm_nslab * dm_rows * BK) * 2;
+  BHMC_TRY(ctx->get_scratch(1, wt_bytes * 2, &wt));
+  BHMC_TRY(ctx->get_scratch(2, dmt_bytes * 2, &dmt));
+  BHMC_TRY(ctx->get_scratch(13, 256, &bar));
+  BHMC_CUDA_OK(cudaMemsetAsync(bar, 0, 256, ctx->stream));
+  __nv_bfloat16* wt_hi = (__nv_bfloat16*)wt;
+  __nv_bfloat16* wt_lo = (__nv_bfloat16*)((char*)wt + wt_bytes);
+  {  // operand copy of the start point (later steps write it from the update epilogue)
+    GroupTimer t(ctx, KG_PREP);
+    dim3 grid((unsigned)ceil_div(d.Dp, 128), C);
+    k_tc_prep<<<grid, 128, 0, ctx->stream>>>(fs.q, ld, D, K, KP, d.Dp, wt_hi, split3 ? wt_lo : nullptr, nullptr, 1.0f / d.x_scale);
+    ctx->launches++;
+  }
+  CUtensorMap maps[8];
+  const uint64_t xt_rows_total = (uint64_t)(d.Npad / d.slab) * d.Dt_pad;
+  BHMC_TRY(make_map(&maps[0], d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  maps[1] = maps[0];
+  if (smode == 1) BHMC_TRY(make_map(&maps[1], d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  BHMC_TRY(make_map(&maps[2], wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+  maps[3] = maps[2];
+  if (split3) BHMC_TRY(make_map(&maps[3], wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+  BHMC_TRY(make_map(&maps[4], d.Xt_hi, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, BM));
+  maps[5] = maps[4];
+  if (smode == 1) BHMC_TRY(make_map(&maps[5], d.Xt_lo, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, BM));
+  __nv_bfloat16* dmt_hi = (__nv_bfloat16*)dmt;
+  __nv_bfloat16* dmt_lo = split3 ? (__nv_bfloat16*)((char*)dmt + dmt_bytes) : nullptr;
+  BHMC_TRY(make_map(&maps[6], dmt_hi, (uint64_t)BK, (uint64_t)(dm_nslab * dm_rows), (uint64_t)BK, (uint32_t)BN));
+  maps[7] = maps[6];
+  if (split3) BHMC_TRY(make_map(&maps[7], dmt_lo, (uint64_t)BK, (uint64_t)(dm_nslab * dm_rows), (uint64_t)BK, (uint32_t)BN));
+  PersistParams p{};
+  p.D = D, p.K = K, p.C = C, p.cpt = cpt, p.BN = BN, p.n_tiles = n_tiles;
+  p.k_chunks_f = (int)ceil_div(D, BK);
+  p.m_tiles_b = (int)ceil_div(d.Dt, BM);
+  p.split3 = smode, p.stages = stages;
+  p.ld = ld, p.Dp = d.Dp;
+  p.q = fs.q, p.p = fs.p;
+  p.labels = d.labels;
+  p.batch = batch, p.row_first = row_first, p.n_steps = n_steps;
+  p.eps = eps_dev;
+  p.gamma = fs.gamma, p.alpha = alpha, p.scale = 1.0f / d.x_scale;
+  p.kind = fs.kind;
+  p.z = fs.z, p.ld_z = fs.ld_z, p.z_step_stride = z_step_stride;
+  p.seed = fs.seed, p.chain_id0 = fs.chain_id0, p.step0 = step0;
+  p.wt_hi = wt_hi, p.wt_lo = split3 ? wt_lo : nullptr, p.dmt_hi = dmt_hi, p.dmt_lo = dmt_lo;
+  p.dm_rows = (int)dm_rows, p.xt_rows = (int)d.Dt_pad;
+  p.bar = (unsigned int*)bar;
+  const int items = std::max((int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles);
+  const int grid = std::min(items, ctx->sm_count);
+  GroupTimer t(ctx, KG_FWD);
+  switch (KP) {
+    case 4: return launch_sg_persistent<4>(ctx, maps, p, grid, smem);
+    case 8: return launch_sg_persistent<8>(ctx, maps, p, grid, smem);
+    case 10: return launch_sg_persistent<10>(ctx, maps, p, grid, smem);
+    case 16: return launch_sg_persistent<16>(ctx, maps, p, grid, smem);
+  }
+  return BHMC_ERR_UNSUPPORTED;
+}

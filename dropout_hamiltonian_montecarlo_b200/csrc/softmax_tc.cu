@@ -102,6 +102,7 @@ struct TcParams {
   __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
   double* loglik;
   int write_dm;
+  int skip_loglik;                // persistent minibatch kernel: no per-step log-likelihood (it is evaluated once per epoch)
   long long* prof;                // optional [grid][8] cycle counters (BHMC_PROF=1): see tools/profile_grad.py
   int debug;                      // BHMC_DEBUG_EPI (measurement only): 1 = skip the forward epilogue, 2 = skip its atomics
   // backward epilogue
@@ -201,7 +202,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
           const int k = k0 + j;
           if (EXACT || k < K) {
             if (zp) __stcs(zp + (int64_t)k * p.dm_ld, __uint_as_float(r8[j]));
-            const float v = fminf(__uint_as_float(r8[j]) + __ldg(bias + k), CLIP_HI);
+            const float v = fminf(__uint_as_float(r8[j]) + __ldcg(bias + k), CLIP_HI);
             m = fmaxf(m, v);
             zy = (k == y) ? v : zy;
           }
@@ -220,7 +221,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
         for (int j = 0; j < CH; ++j) {
           const int k = k0 + j;
           if (EXACT || k < K) {
-            const float v = all_low ? CLIP_LO : fminf(__uint_as_float(r8[j]) + __ldg(bias + k), CLIP_HI);
+            const float v = all_low ? CLIP_LO : fminf(__uint_as_float(r8[j]) + __ldcg(bias + k), CLIP_HI);
             ssum += ex2_approx((v - m) * L2E);
           }
         }
@@ -238,7 +239,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
           for (int j = 0; j < CH; ++j) {
             const int k = k0 + j;
             if (EXACT || k < K) {
-              const float v = all_low ? CLIP_LO : fminf(__uint_as_float(r8[j]) + __ldg(bias + k), CLIP_HI);
+              const float v = all_low ? CLIP_LO : fminf(__uint_as_float(r8[j]) + __ldcg(bias + k), CLIP_HI);
               const float e = ex2_approx((v - m) * L2E);
               const float d = valid ? fmaf(e, inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
               const __nv_bfloat16 h = __float2bfloat16_rn(d);
@@ -264,7 +265,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
       float bv[PRELOAD_BIAS ? KP : 1];
       if constexpr (PRELOAD_BIAS) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
+        for (int k = 0; k < KP; ++k) bv[k] = (EXACT || k < K) ? __ldcg(bias + k) : 0.f;
       }
       if constexpr (!FROM_Z) {
         tmem_ld_wait();
@@ -283,7 +284,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
         // (exp(z - max) underflows to 0 in fp32 either way), so it is applied to zy alone below.
         float bk;
         if constexpr (PRELOAD_BIAS) bk = bv[k];
-        else bk = (EXACT || k < K) ? __ldg(bias + k) : 0.f;
+        else bk = (EXACT || k < K) ? __ldcg(bias + k) : 0.f;
         float v = fminf(__uint_as_float(raw[k]) + bk, CLIP_HI);
         if (!EXACT && k >= K) v = -INFINITY;  // padded classes
         z[k] = v;
@@ -345,7 +346,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
       __syncthreads();
       if (t == 0) atomicAdd(p.loglik + c, (double)sll[0] + (double)sll[1] + (double)sll[2] + (double)sll[3]);
     } else {
-      if (lane == 0 && p.debug != 2) atomicAdd(p.loglik + c, (double)ll);
+      if (lane == 0 && p.debug != 2 && !p.skip_loglik) atomicAdd(p.loglik + c, (double)ll);
     }
   }
 }
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(128) k_softmax_from_z_vec(const TcParams p, in
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
       if (EXACT || k < K) {
-        const float b2 = __ldg(bias + k) * L2E;
+        const float b2 = __ldcg(bias + k) * L2E;
         const float* vv = reinterpret_cast<const float*>(&raw[k]);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -2211,5 +2212,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
 }
+
+#include "softmax_persist.cuh"
 
 }  // namespace bhmc

@@ -324,3 +324,47 @@ def test_hmc_returns_positions_and_drawn_momentums():
     s1 = hmc(softmax({"alpha": 0.01}, precision="fp32"), start, path_length=1e-9, step_size=1e-3, verbose=False)
     _, _, pos1, mom1 = s1.sample(niter=2, burnin=0, rng=TapeRng(zt), X_train=X, y_train=Y)
     np.testing.assert_allclose(mom1[1][0]["weights"].ravel(), zt[2 * (D * K + K):2 * (D * K + K) + D * K], rtol=1e-6)
+
+
+def test_persistent_minibatch_kernel_matches_per_step_launches():
+    """softmax_persist.cuh (one cooperative launch per epoch) against the per-step launches (BHMC_PERSIST=0) with the
+    in-kernel Philox noise: the same element-block keys must give the same chain, up to fp32 summation order (the
+    persistent backward has no split-K).  SGLD over an epoch boundary (step-size schedule) and heavy-ball SGD."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle, SoftmaxHandle, default_context
+rs = np.random.RandomState(0)
+N, D, K, C, B = 2100, 784, 10, 37, 500
+X = torch.as_tensor(rs.rand(N, D).astype(np.float32)).cuda(); y = torch.as_tensor(rs.randint(0, K, N).astype(np.int32)).cuda()
+ctx = default_context(); h = SoftmaxHandle(ctx, N, D, K, 0.01); h.bind(X, y)
+q0 = rs.normal(0, .05, (C, h.P)).astype(np.float32)
+s = SamplerHandle(ctx, h, 1, C, seed=5, chain_id0=11, precision=1); s.set_q(q0)
+o = s.sg_run(2, 1, B, 1e-5, n_rows=N, step0=3)
+l0 = ctx.launches
+s.sg_run(1, 0, B, 1e-5, n_rows=N, step0=100)
+launches = ctx.launches - l0
+s2 = SamplerHandle(ctx, h, 3, C, precision=1); s2.set_q(q0)
+o2 = s2.sg_run(2, 0, B, 1e-4, n_rows=N, gamma=0.9)
+np.savez(sys.argv[1], sgld=o["samples"].cpu().numpy(), logp=o["logp"].cpu().numpy(), eps=o["final_step_size"], p=s.get(1),
+         sgd=s2.get(0), sgd_loss=o2["logp"].cpu().numpy(), launches=launches)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    res = []
+    for persist in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".npz") as f:
+            env = dict(os.environ, BHMC_PERSIST=persist)
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-3000:]
+            res.append({k: v for k, v in np.load(f.name).items()})
+    a, b = res
+    assert int(a["launches"]) < int(b["launches"]), (a["launches"], b["launches"])  # one epoch: 1 + a few vs 3 per step
+    for key, tol in (("sgld", 2e-5), ("p", 2e-4), ("sgd", 2e-5)):
+        scale = np.abs(b[key]).max()
+        assert np.abs(a[key] - b[key]).max() < tol * scale, (key, np.abs(a[key] - b[key]).max() / scale)
+    np.testing.assert_allclose(a["logp"], b["logp"], rtol=1e-6)
+    np.testing.assert_allclose(a["sgd_loss"], b["sgd_loss"], rtol=1e-6)
+    assert a["eps"] == b["eps"]
