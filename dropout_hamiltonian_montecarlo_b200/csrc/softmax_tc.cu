@@ -1135,6 +1135,8 @@ k_tc_bwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #undef BHMC_DECODE_BWD2
 }
 
+#include "softmax_bwd_sk.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // small helper kernels
 // ---------------------------------------------------------------------------------------------
@@ -1243,8 +1245,10 @@ struct PartRegions {
   int64_t split_row;      // first output row of region 1
   int64_t cols;
   float scale;            // 1 / (scale of the bound X operand): multiplies the summed partials and the next W operand
+  SkPlan sk;              // sk.on: part0 holds the pieces of k_tc_bwd_sk (softmax_bwd_sk.cuh) instead of row slabs
 };
 __device__ __forceinline__ float sum_partials(const PartRegions& r, int64_t d, int64_t col) {
+  if (r.sk.on) return sk_sum_partials(r.sk, r.part0, (int)d, (int)col) * r.scale;
   const bool main = d < r.split_row;
   const float* src = (main ? r.part0 + d * r.cols : r.part1 + (d - r.split_row) * r.cols) + col;
   const int ns = main ? r.n_split0 : r.n_split1;
@@ -2129,11 +2133,42 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   } else {
     b1.n_split = 0;
   }
+  // ---- swapped operand roles + interleaved stream-K (softmax_bwd_sk.cuh): chain-class rows on M, features on N ----
+  // BHMC_BWD_SK: 0 = off, 1 = where the cost model prefers it (default), 2 = wherever the shape allows (tests)
+  static int sk_env = -1, sk_wh = 0;
+  if (sk_env < 0) {
+    const char* e = getenv("BHMC_BWD_SK");
+    sk_env = e ? atoi(e) : 1;
+    const char* w = getenv("BHMC_SK_WH");  // cost of a half-item chunk relative to wp = 10: measured 9-10 (M = 128 over two
+                                           // CTAs runs at half the rate per row: 154.9 / 146.1 / 148.6 / 153.6 us at 7 / 9 / 10 / 11)
+    sk_wh = w ? std::max(1, std::min(20, atoi(w))) : 9;
+  }
+  SkParams sk{};
+  bool use_sk = false;
+  if (sk_env && pairing_enabled() && BK == 64 && d.slab == BK && d.slab_ld == BK && dm_slab == BK && dm_ld == BK &&
+      k_chunks_b >= 64 && ncols >= 2 * BM) {
+    SkPlan& s = sk.s;
+    // tensor work in units of (128-row tile) x (column) x chunk; the single-CTA kernel pays ~1.25x per unit
+    if (sk_make_plan(ncols, (int)d.Dt, k_chunks_b, ctx->sm_count / 2, sk_wh, &s) &&
+        (sk_env >= 2 || (2.0 * s.n_pair + s.has_half * 2.0 * s.wh / s.wp) * s.n_nt * s.bn < 1.25 * m_tiles_all * (double)pcol)) {
+      sk.split3 = smode;
+      sk.sub_chunks = b.sub_chunks;
+      sk.a_chunk0 = (int)((row0 - shift) / BK);
+      sk.xt_rows = (int)d.Dt_pad;
+      sk.dm_rows = (int)dm_rows;
+      const int st_bytes = (smode ? 2 : 1) * BM * BK * 2 + (smode == 1 ? 2 : 1) * (s.bn / 2) * BK * 2;
+      sk.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / st_bytes)));
+      if (const char* e = getenv("BHMC_STAGES")) sk.stages = std::max(1, std::min(sk.stages, atoi(e)));
+      use_sk = true;
+    }
+  }
   const int64_t rows2 = (int64_t)m2 * BM, rows1 = (int64_t)m1 * BM;
   void* part = nullptr;
   const size_t part2_elems = (size_t)b2.n_split * rows2 * pcol;
   const size_t part1_elems = m2 ? (size_t)b2.left_n_split * BM * pcol : (size_t)b1.n_split * rows1 * pcol;
-  BHMC_TRY(ctx->get_scratch(3, sizeof(float) * (part2_elems + part1_elems), &part));
+  const size_t sk_elems = use_sk ? (size_t)sk.s.n_clusters * SK_MAX_PIECES * sk.s.piece_elems : 0;
+  BHMC_TRY(ctx->get_scratch(3, sizeof(float) * std::max(part2_elems + part1_elems, sk_elems), &part));
+  sk.part = (float*)part;
   b2.part = (float*)part;
   b2.part_left = (float*)part + part2_elems;
   b1.part = (float*)part + part2_elems;
@@ -2145,7 +2180,22 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   {
     GroupTimer t(ctx, KG_BWD);
     // every column a backward chunk reads is written by the forward epilogue (rows, alignment prefix, tail)
-    if (m2) {
+    if (use_sk) {
+      CUtensorMap dh_hi, dh_lo, x_hi, x_lo;
+      const uint64_t dm_outer = (uint64_t)(dm_nslab * dm_rows);
+      BHMC_TRY(make_map(&a_hi, dmt_hi, (uint64_t)BK, dm_outer, (uint64_t)BK, BM));
+      BHMC_TRY(make_map(&dh_hi, dmt_hi, (uint64_t)BK, dm_outer, (uint64_t)BK, BM / 2));
+      BHMC_TRY(make_map(&x_hi, d.Xt_hi, (uint64_t)BK, xt_rows, (uint64_t)BK, (uint32_t)(sk.s.bn / 2)));
+      a_lo = a_hi, dh_lo = dh_hi, x_lo = x_hi;
+      if (smode) {
+        BHMC_TRY(make_map(&a_lo, dmt_lo, (uint64_t)BK, dm_outer, (uint64_t)BK, BM));
+        BHMC_TRY(make_map(&dh_lo, dmt_lo, (uint64_t)BK, dm_outer, (uint64_t)BK, BM / 2));
+      }
+      if (smode == 1) BHMC_TRY(make_map(&x_lo, d.Xt_lo, (uint64_t)BK, xt_rows, (uint64_t)BK, (uint32_t)(sk.s.bn / 2)));
+      if (want_prof) sk.prof = (long long*)prof_dev;
+      BHMC_TRY(launch_bwd_sk(ctx, a_hi, a_lo, dh_hi, dh_lo, x_hi, x_lo, sk));
+    }
+    if (m2 && !use_sk) {
       BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, BM));
       BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)(BN / 2)));
       a_lo = a_hi;
@@ -2154,7 +2204,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
       if (split3) BHMC_TRY(make_map(&b_lo, dmt_lo, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)(BN / 2)));
       BHMC_TRY(launch_bwd2(ctx, a_hi, a_lo, b_hi, b_lo, b2));
     }
-    if (m1) {
+    if (m1 && !use_sk) {
       const uint32_t abox = (uint32_t)(b1.pair ? BM / 2 : BM);
       BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, abox));
       BHMC_TRY(make_map(&b_hi, dmt_hi, (uint64_t)dm_slab, (uint64_t)(dm_nslab * dm_rows), (uint64_t)dm_ld, (uint32_t)BN));
@@ -2176,7 +2226,11 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
           mx = std::max(mx, (double)hp[bb * 8]);
         }
       const TcParams& bp = m2 ? b2 : b1;
-      if (n)
+      if (n && use_sk)
+        fprintf(stderr, "[bhmc prof bwd] stream-K: pairs %d half %d x %d tiles of %d, kc %d, lanes %d/%d, T %d, stages %d | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
+                sk.s.n_pair, sk.s.has_half, sk.s.n_nt, sk.s.bn, sk.s.kc, sk.s.lp, sk.s.lh, sk.s.T, sk.stages, n, tot / n, mx, te / n,
+                tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
+      else if (n)
         fprintf(stderr, "[bhmc prof bwd] %s n_split %d cps %d pair %d BN %d stages %d (+ %d odd tile: n_split %d cps %d) | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
                 m2 ? "cta_group::2" : "single", bp.n_split, bp.chunks_per_split, bp.pair, bp.BN, bp.stages, m_left,
                 b2.left_n_split, b2.left_cps, n, tot / n, mx, te / n, tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
@@ -2191,6 +2245,7 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     pr.split_row = m2 ? rows2 : ((int64_t)1 << 40);
     pr.cols = pcol;
     pr.scale = 1.0f / d.x_scale;
+    if (use_sk) pr.sk = sk.s, pr.part0 = sk.part;
     if (fs) {
       dim3 grid((unsigned)ceil_div(ceil_div(ld, 4), 256), C);
       if (fs->kind == BHMC_KIND_SGLD)

@@ -1,0 +1,75 @@
+"""GPU (B200): the backward GEMM with swapped operand roles and the interleaved stream-K decomposition
+(csrc/softmax_bwd_sk.cuh: cta_group::2 pair items M = 256, half items M = 128 split 64 + 64) against the fp32 CUDA-core
+path and against the row-slab kernels it replaces (reference arithmetic: hamiltonian/models/cpu/softmax.py:52-60).
+
+The kernel choice is an environment switch read once per process (BHMC_BWD_SK: 2 = wherever the shape allows,
+0 = never), so every variant runs in its own interpreter.  Shapes: odd and even 128-row tile counts (pair items only /
+a trailing half item), padded classes (K = 38 -> 40), an unaligned row window, the exact-operand path (2 MMAs per
+product) and the single-pass mode.  Tolerance: |got - ref| <= 1e-4 |ref| + 2e-5 max|ref| per element for bf16x3
+(BASELINE.json north_star: rtol 1e-4 in fp32); the two tensor-core kernels must agree to fp32 summation order.
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CODE = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from dropout_hamiltonian_montecarlo_b200.runtime import SoftmaxHandle, default_context
+ctx = default_context()
+out = {}
+#        name      N     D    K   C  row0 nrows pixels
+cases = [("pair1h", 5000, 100, 10, 26,    0,    0, False),   # 260 rows: one pair item + one half item
+         ("pair2h", 4500, 784, 10, 64,    0,    0, False),   # 640 rows: two pairs + half (the bench shape of the M side)
+         ("k38",    6000, 300, 38,  8,    0,    0, False),   # K = 38 padded to 40: 320 rows, padded class rows unwritten
+         ("window", 6000, 130, 10, 51, 1234, 4200, False),   # 510 rows: two pairs; window starts 18 rows into a chunk
+         ("pixels", 4800, 784, 10, 39,    0,    0, True)]    # X = k/255: exact operand, 2 MMAs per product; 390 rows: pair + pair
+for name, N, D, K, C, row0, nrows, pixels in cases:
+    rs = np.random.RandomState(len(name) + N)
+    Xn = (rs.randint(0, 256, (N, D)) / 255.0).astype(np.float32) if pixels else rs.rand(N, D).astype(np.float32)
+    X = torch.as_tensor(Xn).cuda(); y = torch.as_tensor(rs.randint(0, K, N).astype(np.int32)).cuda()
+    h = SoftmaxHandle(ctx, N, D, K, 0.01); h.bind(X, y)
+    q = h.pack(rs.normal(0, .05, (C, h.P)).astype(np.float32))
+    nr = nrows or N
+    for prec in (0, 1, 2):
+        g, st = h.grad(q, row0, nr, prec)
+        ctx.sync()
+        out["%%s_g%%d" %% (name, prec)] = g[:, :h.P].cpu().numpy()
+        out["%%s_s%%d" %% (name, prec)] = st.cpu().numpy()
+    h.close()
+np.savez(sys.argv[1], **out)
+''' % (ROOT,)
+
+
+def _run(sk):
+    with tempfile.NamedTemporaryFile(suffix=".npz") as f:
+        env = dict(os.environ, BHMC_BWD_SK=sk)
+        r = subprocess.run([sys.executable, "-c", CODE, f.name], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        return {k: v for k, v in np.load(f.name).items()}
+
+
+def test_stream_k_backward_matches_fp32_and_row_slab_kernels():
+    sk, cl = _run("2"), _run("0")
+    for name in ("pair1h", "pair2h", "k38", "window", "pixels"):
+        ref = sk[name + "_g0"].astype(np.float64)  # fp32 CUDA-core path (does not depend on the switch)
+        scale = np.abs(ref).max()
+        # bf16x3 on the stream-K kernel vs fp32
+        np.testing.assert_allclose(sk[name + "_g1"], ref, rtol=1e-4, atol=2e-5 * scale, err_msg=name + " bf16x3 stream-K vs fp32")
+        # the two tensor-core kernels differ only in the fp32 summation order of the partials
+        err = np.abs(sk[name + "_g1"].astype(np.float64) - cl[name + "_g1"]).max() / scale
+        assert err < 1e-5, (name, err)
+        assert np.abs(sk[name + "_g1"] - cl[name + "_g1"]).max() > 0, name  # different kernels really ran
+        # single pass (statistical mode): same kernel structure, loose tolerance
+        err2 = np.abs(sk[name + "_g2"].astype(np.float64) - cl[name + "_g2"]).max() / scale
+        assert err2 < 1e-4, (name, err2)
+        assert np.abs(sk[name + "_g2"].astype(np.float64) - ref).max() / scale < 2e-2, name
+        np.testing.assert_allclose(sk[name + "_s1"], cl[name + "_s1"], rtol=1e-12)  # the forward pass is untouched
