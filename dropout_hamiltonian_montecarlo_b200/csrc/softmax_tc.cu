@@ -2135,29 +2135,39 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   }
   // ---- swapped operand roles + interleaved stream-K (softmax_bwd_sk.cuh): chain-class rows on M, features on N ----
   // BHMC_BWD_SK: 0 = off, 1 = where the cost model prefers it (default), 2 = wherever the shape allows (tests)
-  static int sk_env = -1, sk_wh = 0;
+  // BHMC_SK_WH (per cent, default 90): cost of an M = 128 item relative to an M = 256 one of the same width -- measured
+  // 154.9 / 146.1 / 148.6 / 153.6 us per 64-chain launch at 70 / 90 / 100 / 110; BHMC_SK_T=1: odd tile by transposed items where the plan finds them cheaper
+  static int sk_env = -1;
+  static SkTune sk_tune;
   if (sk_env < 0) {
     const char* e = getenv("BHMC_BWD_SK");
     sk_env = e ? atoi(e) : 1;
-    const char* w = getenv("BHMC_SK_WH");  // cost of a half-item chunk relative to wp = 10: measured 9-10 (M = 128 over two
-                                           // CTAs runs at half the rate per row: 154.9 / 146.1 / 148.6 / 153.6 us at 7 / 9 / 10 / 11)
-    sk_wh = w ? std::max(1, std::min(20, atoi(w))) : 9;
+    const char* w = getenv("BHMC_SK_WH");
+    sk_tune.wh_pct = w ? std::max(10, std::min(300, atoi(w))) : 90;
+    const char* f = getenv("BHMC_SK_WFLOOR");
+    sk_tune.w_floor = f ? std::max(1, std::min(20, atoi(f))) : 5;
+    const char* t = getenv("BHMC_SK_T");
+    sk_tune.transposed = t ? atoi(t) : 0;
+    const char* q = getenv("BHMC_SK_WQ");
+    sk_tune.w_q = q ? std::max(1, std::min(40, atoi(q))) : 10;
+    const char* r = getenv("BHMC_SK_WR");
+    sk_tune.w_r_floor = r ? std::max(1, std::min(40, atoi(r))) : 8;
   }
   SkParams sk{};
   bool use_sk = false;
   if (sk_env && pairing_enabled() && BK == 64 && d.slab == BK && d.slab_ld == BK && dm_slab == BK && dm_ld == BK &&
       k_chunks_b >= 64 && ncols >= 2 * BM) {
     SkPlan& s = sk.s;
-    // tensor work in units of (128-row tile) x (column) x chunk; the single-CTA kernel pays ~1.25x per unit
-    if (sk_make_plan(ncols, (int)d.Dt, k_chunks_b, ctx->sm_count / 2, sk_wh, &s) &&
-        (sk_env >= 2 || (2.0 * s.n_pair + s.has_half * 2.0 * s.wh / s.wp) * s.n_nt * s.bn < 1.25 * m_tiles_all * (double)pcol)) {
+    // tensor work per chunk in units of 1/10 of a 256 x 160 pair chunk; a 128 x 160 tile chunk of the single-CTA kernel
+    // costs 5 x ~1.25 (1250 against 1005 cycles)
+    if (sk_make_plan(ncols, (int)d.Dt, k_chunks_b, ctx->sm_count / 2, sk_tune, &s) &&
+        (sk_env >= 2 || (double)sk_plan_cost(s) < 1.25 * 5.0 * m_tiles_all * (double)pcol / 160.0)) {
       sk.split3 = smode;
       sk.sub_chunks = b.sub_chunks;
       sk.a_chunk0 = (int)((row0 - shift) / BK);
       sk.xt_rows = (int)d.Dt_pad;
       sk.dm_rows = (int)dm_rows;
-      const int st_bytes = (smode ? 2 : 1) * BM * BK * 2 + (smode == 1 ? 2 : 1) * (s.bn / 2) * BK * 2;
-      sk.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / st_bytes)));
+      sk.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / sk_stage(s, smode).bytes)));
       if (const char* e = getenv("BHMC_STAGES")) sk.stages = std::max(1, std::min(sk.stages, atoi(e)));
       use_sk = true;
     }
@@ -2181,19 +2191,28 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
     GroupTimer t(ctx, KG_BWD);
     // every column a backward chunk reads is written by the forward epilogue (rows, alignment prefix, tail)
     if (use_sk) {
-      CUtensorMap dh_hi, dh_lo, x_hi, x_lo;
+      SkMaps maps;
       const uint64_t dm_outer = (uint64_t)(dm_nslab * dm_rows);
-      BHMC_TRY(make_map(&a_hi, dmt_hi, (uint64_t)BK, dm_outer, (uint64_t)BK, BM));
-      BHMC_TRY(make_map(&dh_hi, dmt_hi, (uint64_t)BK, dm_outer, (uint64_t)BK, BM / 2));
-      BHMC_TRY(make_map(&x_hi, d.Xt_hi, (uint64_t)BK, xt_rows, (uint64_t)BK, (uint32_t)(sk.s.bn / 2)));
-      a_lo = a_hi, dh_lo = dh_hi, x_lo = x_hi;
-      if (smode) {
-        BHMC_TRY(make_map(&a_lo, dmt_lo, (uint64_t)BK, dm_outer, (uint64_t)BK, BM));
-        BHMC_TRY(make_map(&dh_lo, dmt_lo, (uint64_t)BK, dm_outer, (uint64_t)BK, BM / 2));
-      }
-      if (smode == 1) BHMC_TRY(make_map(&x_lo, d.Xt_lo, (uint64_t)BK, xt_rows, (uint64_t)BK, (uint32_t)(sk.s.bn / 2)));
+      const bool has_dlo = smode != 0, has_xlo = smode == 1;
+      auto dmap = [&](int at, uint32_t box) -> int {  // DmT hi (+ lo) with a `box`-row box
+        BHMC_TRY(make_map(&maps.m[at], dmt_hi, (uint64_t)BK, dm_outer, (uint64_t)BK, box));
+        maps.m[at + 1] = maps.m[at];
+        if (has_dlo) BHMC_TRY(make_map(&maps.m[at + 1], dmt_lo, (uint64_t)BK, dm_outer, (uint64_t)BK, box));
+        return BHMC_OK;
+      };
+      auto xmap = [&](int at, uint32_t box) -> int {  // X^T hi (+ lo)
+        BHMC_TRY(make_map(&maps.m[at], d.Xt_hi, (uint64_t)BK, xt_rows, (uint64_t)BK, box));
+        maps.m[at + 1] = maps.m[at];
+        if (has_xlo) BHMC_TRY(make_map(&maps.m[at + 1], d.Xt_lo, (uint64_t)BK, xt_rows, (uint64_t)BK, box));
+        return BHMC_OK;
+      };
+      BHMC_TRY(dmap(SKM_D128, BM));
+      BHMC_TRY(dmap(SKM_D64, BM / 2));
+      BHMC_TRY(xmap(SKM_XBN, (uint32_t)(sk.s.bn / 2)));
+      BHMC_TRY(xmap(SKM_X128, BM));
+      BHMC_TRY(xmap(SKM_XR, (uint32_t)(sk.s.bnr ? sk.s.bnr / 2 : 16)));
       if (want_prof) sk.prof = (long long*)prof_dev;
-      BHMC_TRY(launch_bwd_sk(ctx, a_hi, a_lo, dh_hi, dh_lo, x_hi, x_lo, sk));
+      BHMC_TRY(launch_bwd_sk(ctx, maps, sk));
     }
     if (m2 && !use_sk) {
       BHMC_TRY(make_map(&a_hi, d.Xt_hi, (uint64_t)d.slab, xt_rows, (uint64_t)d.slab_ld, BM));
@@ -2227,9 +2246,10 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
         }
       const TcParams& bp = m2 ? b2 : b1;
       if (n && use_sk)
-        fprintf(stderr, "[bhmc prof bwd] stream-K: pairs %d half %d x %d tiles of %d, kc %d, lanes %d/%d, T %d, stages %d | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
-                sk.s.n_pair, sk.s.has_half, sk.s.n_nt, sk.s.bn, sk.s.kc, sk.s.lp, sk.s.lh, sk.s.T, sk.stages, n, tot / n, mx, te / n,
-                tf / n, ti / n, nc / n, nt / n, tf / nc, ti / nc);
+        fprintf(stderr, "[bhmc prof bwd] stream-K: pairs %d x %d tiles of %d, odd %d (Q %d, R width %d), items %d/%d/%d weights %d/%d/%d lanes %d/%d/%d, kc %d, T %d, stages %d | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
+                sk.s.n_pair, sk.s.n_nt, sk.s.bn, sk.s.odd, sk.s.n_fp, sk.s.bnr, sk.s.cnt[0], sk.s.cnt[1], sk.s.cnt[2], sk.s.w[0], sk.s.w[1],
+                sk.s.w[2], sk.s.L[0], sk.s.L[1], sk.s.L[2], sk.s.kc, sk.s.T, sk.stages, n, tot / n, mx, te / n, tf / n, ti / n, nc / n, nt / n,
+                tf / nc, ti / nc);
       else if (n)
         fprintf(stderr, "[bhmc prof bwd] %s n_split %d cps %d pair %d BN %d stages %d (+ %d odd tile: n_split %d cps %d) | MMA thread, mean over %d CTAs: total %.0f cyc (max %.0f); wait tempty %.0f; wait full %.0f; issue+commit %.0f; chunks %.0f drains %.0f -> per chunk: full-wait %.0f issue %.0f\n",
                 m2 ? "cta_group::2" : "single", bp.n_split, bp.chunks_per_split, bp.pair, bp.BN, bp.stages, m_left,

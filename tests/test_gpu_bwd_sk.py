@@ -1,6 +1,7 @@
 """GPU (B200): the backward GEMM with swapped operand roles and the interleaved stream-K decomposition
-(csrc/softmax_bwd_sk.cuh: cta_group::2 pair items M = 256, half items M = 128 split 64 + 64) against the fp32 CUDA-core
-path and against the row-slab kernels it replaces (reference arithmetic: hamiltonian/models/cpu/softmax.py:52-60).
+(csrc/softmax_bwd_sk.cuh: cta_group::2 pair items M = 256; an odd last tile as half items M = 128 split 64 + 64, or as
+transposed pair items + a narrow remainder item) against the fp32 CUDA-core path and against the row-slab kernels it
+replaces (reference arithmetic: hamiltonian/models/cpu/softmax.py:52-60).
 
 The kernel choice is an environment switch read once per process (BHMC_BWD_SK: 2 = wherever the shape allows,
 0 = never), so every variant runs in its own interpreter.  Shapes: odd and even 128-row tile counts (pair items only /
@@ -31,7 +32,9 @@ cases = [("pair1h", 5000, 100, 10, 26,    0,    0, False),   # 260 rows: one pai
          ("pair2h", 4500, 784, 10, 64,    0,    0, False),   # 640 rows: two pairs + half (the bench shape of the M side)
          ("k38",    6000, 300, 38,  8,    0,    0, False),   # K = 38 padded to 40: 320 rows, padded class rows unwritten
          ("window", 6000, 130, 10, 51, 1234, 4200, False),   # 510 rows: two pairs; window starts 18 rows into a chunk
-         ("pixels", 4800, 784, 10, 39,    0,    0, True)]    # X = k/255: exact operand, 2 MMAs per product; 390 rows: pair + pair
+         ("pixels", 4800, 784, 10, 39,    0,    0, True),    # X = k/255: exact operand, 2 MMAs per product; 390 rows: pair + pair
+         ("pix_odd", 4300, 784, 10, 60,   0,    0, True),    # exact operand with an odd tile (600 rows): lo copies swap roles in Q items
+         ("f256",   4400, 255, 10, 38,   64, 4200, False)]   # 256 feature rows: transposed pair without a remainder item
 for name, N, D, K, C, row0, nrows, pixels in cases:
     rs = np.random.RandomState(len(name) + N)
     Xn = (rs.randint(0, 256, (N, D)) / 255.0).astype(np.float32) if pixels else rs.rand(N, D).astype(np.float32)
@@ -49,17 +52,22 @@ np.savez(sys.argv[1], **out)
 ''' % (ROOT,)
 
 
-def _run(sk):
+def _run(sk, transposed="1"):
     with tempfile.NamedTemporaryFile(suffix=".npz") as f:
-        env = dict(os.environ, BHMC_BWD_SK=sk)
+        env = dict(os.environ, BHMC_BWD_SK=sk, BHMC_SK_T=transposed)
         r = subprocess.run([sys.executable, "-c", CODE, f.name], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
         return {k: v for k, v in np.load(f.name).items()}
 
 
 def test_stream_k_backward_matches_fp32_and_row_slab_kernels():
-    sk, cl = _run("2"), _run("0")
-    for name in ("pair1h", "pair2h", "k38", "window", "pixels"):
+    cl = _run("0")
+    for sk in (_run("2", "1"), _run("2", "0")):  # odd tile as transposed items / as half items (default)
+        _compare(sk, cl)
+
+
+def _compare(sk, cl):
+    for name in ("pair1h", "pair2h", "k38", "window", "pixels", "pix_odd", "f256"):
         ref = sk[name + "_g0"].astype(np.float64)  # fp32 CUDA-core path (does not depend on the switch)
         scale = np.abs(ref).max()
         # bf16x3 on the stream-K kernel vs fp32
