@@ -15,8 +15,9 @@ backward GEMM), Metropolis test, sample store.
 `e2e`    : same metric through the public API (`hmc.sample`) with HOST buffers: every step binds the
            data from pinned host memory (H2D + operand preparation inside the timed region) and
            reads the samples / losses back (D2H).
-`roofline`: dominant kernel of the timed region (the backward GEMM k_tc_gemm<bwd> in every run so far; the
-           line names whichever group took longer), algorithmic flops 2*N*D*K per chain it carried / its
+`roofline`: dominant kernel group of the timed region (the backward GEMM -- k_tc_bwd_sk for launches of >= ~20
+           chains, k_tc_gemm<bwd> below -- in every run so far; the line names whichever group took longer),
+           algorithmic flops 2*N*D*K per chain it carried / its
            duration (CUDA events on the launching stream, sampled live inside the timed region)
            against the measured sustained bf16 peak.
 `cpu_baseline`: the NumPy oracle port of the reference path (fp64, BLAS threads = host cores) on a
@@ -386,7 +387,7 @@ def _timed(world, fn):
     return e0.elapsed_time(e1), out
 
 
-def _group_roofline(ctx, run_once, flops_per_launch, peak_tf, names=("fwd", "bwd", "prep", "update")):
+def _group_roofline(ctx, run_once, flops_per_launch, peak_tf, names=("fwd", "bwd", "prep", "update"), persistent_flops=None):
     """Per-launch-group device times of ONE extra untimed pass with every kernel group bracketed by CUDA events
     (bracketing costs stream overlap, so it is never on inside a timed region): the dominant group, its mean
     duration, and the algorithmic rate of the GEMM group that took longest against the tensor peak."""
@@ -399,9 +400,16 @@ def _group_roofline(ctx, run_once, flops_per_launch, peak_tf, names=("fwd", "bwd
                          "avg_ms": (t[g][0] / t[g][1]) if t[g][1] else None} for g in range(4)}
     dom = max((0, 1), key=lambda g: t[g][0])
     avg = (t[dom][0] / t[dom][1]) * 1e-3 if t[dom][1] else 0.0
-    achieved = flops_per_launch[dom] / avg / 1e12 if avg > 0 else 0.0
-    return {"bound": "tensor", "kernel_group": names[dom], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved / peak_tf, "avg_launch_ms": avg * 1e3, "algorithmic_flops_per_launch": flops_per_launch[dom],
+    flops, label = flops_per_launch[dom], names[dom]
+    if persistent_flops is not None and t[1][1] == 0 and t[0][1] > 0:
+        # the persistent minibatch kernel (csrc/softmax_persist.cuh): ONE launch per epoch holds the forward GEMMs, the
+        # backward GEMMs and the updates of all its steps -- it is timed under the forward group and there is no
+        # separate backward launch; its algorithmic work is both GEMMs of every step of the launch
+        flops = persistent_flops / t[0][1]
+        label = "k_sg_persistent (forward + backward GEMM + update of every step of an epoch in one launch)"
+    achieved = flops / avg / 1e12 if avg > 0 else 0.0
+    return {"bound": "tensor", "kernel_group": label, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved / peak_tf, "avg_launch_ms": avg * 1e3, "algorithmic_flops_per_launch": flops,
             "groups": groups, "timing": "one extra pass, every kernel group bracketed by CUDA events on the launching stream"}
 
 
@@ -424,7 +432,7 @@ def bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf, epochs=5):
     launches = ctx.launches - l0
     ms, n = _agg_time_count(dev, world, ms, o["n_grad_evals"])
     roof = _group_roofline(ctx, lambda: s.sg_run(1, 0, B, 1e-5, n_rows=N, step0=nb * (epochs + 1)),
-                           {0: flops_gemm, 1: flops_gemm}, peak_tf)
+                           {0: flops_gemm, 1: flops_gemm}, peak_tf, persistent_flops=2.0 * flops_gemm * nb)
     out["sgld"] = {"value": n / (ms * 1e-3), "ms_per_step": ms / (epochs * nb), "steps": epochs * nb,
                    "step": "one minibatch update of every chain (gradient + Philox noise + update)",
                    "gpu_launches_per_step": launches / (epochs * nb),
@@ -832,7 +840,8 @@ def run_ours(args, wl):
                        "grad_evals_launched_incl_masked": n_launched,
                        "x_operand": ("exact in bf16 after scaling by %g: 2 MMAs per product" % x_scale) if x_exact
                        else "fp32 values: hi/lo split, 3 MMAs per product"}),
-            "roofline": {"bound": "tensor", "kernel": "backward GEMM (X^T (P-Y), split over rows)" if dom == "bwd"
+            "roofline": {"bound": "tensor", "kernel": "backward GEMM X^T (P-Y) + split-K reduce (k_tc_bwd_sk: swapped operand roles, interleaved stream-K, "
+                         "cta_group::2; k_tc_gemm<bwd> for launches of few chains)" if dom == "bwd"
                          else "forward GEMM (X W + softmax epilogue)", "kernel_group": dom, "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": src, "algorithmic_flops_per_launch": flops_launch,

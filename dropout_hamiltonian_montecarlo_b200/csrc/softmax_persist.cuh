@@ -43,6 +43,9 @@ struct PersistParams {
   int dm_rows;                    // rows per (P-Y)^T slab = n_tiles * BN
   int xt_rows;                    // rows per X^T slab (Dt_pad)
   unsigned int* bar;              // grid barrier counter (zeroed before the launch)
+  int prefetch;                   // L2 prefetch of the next phase's X window (BHMC_PERSIST_PF, default on)
+  long long* prof;                // optional [grid][8] cycle counters of one epilogue thread (BHMC_PROF=1): per step
+                                  // phase F work, wait at barrier 1, phase B work, wait at barrier 2 (sums over the steps)
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -71,20 +74,22 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   fence_proxy_async_all();
 }
 
-// Update epilogue of one backward tile: thread = gradient row d (feature; d == D is the bias row), EW/4 warps of a TMEM
-// lane quarter split the tile's chains.  Element index inside a chain row: i = d*K + k (weights [D,K] row-major, then
-// the bias), so a thread owns K consecutive parameters per chain.
+// Update epilogue of one backward tile.  Tensor memory hands a thread one gradient ROW (feature d; d == D is the bias
+// row) with the KP classes of a chain, while a chain's parameters are stored row-major (i = d*K + k): a warp's 32 rows
+// are ONE contiguous block of 32*KP floats.  The first version updated q / p straight from the row layout -- every
+// load / store instruction of a warp touched 32 addresses 4*KP bytes apart, ~340 L1 wavefronts per (warp, chain), and
+// the phase took 44 k cycles per step against 20 k for the (nearly empty) last row tile (in-kernel timers).  Now the
+// gradient rows go through a per-warp shared-memory block and the update runs in the memory order: one float4 per lane
+// and instruction (coalesced q / p traffic, one Philox block per float4 -- the keys of k_sgld, element for element);
+// the new weights go back through the same block for the K-major bf16 operand copy, which IS row-ordered.
 template <int KP, int EW, int KIND>
-__device__ __forceinline__ void sg_update_tile(const PersistParams& p, uint32_t tacc, int mt, int nt, int part, int t, int step,
-                                               float eps) {
+__device__ __forceinline__ void sg_update_tile(const PersistParams& p, uint32_t tacc, int mt, int nt, int part, int ew, int lane,
+                                               int step, float eps, float* S) {
   constexpr int PARTS = EW / 4;
-  // Philox blocks (4 normals each) that KP consecutive elements starting at i0 = d*KP can overlap: i0 & 3 is 0 when
-  // KP % 4 == 0, 0 or 2 when KP is even, anything otherwise
-  constexpr int MAXOFF = (KP % 4 == 0) ? 0 : (KP % 2 == 0) ? 2 : 3;
-  constexpr int NB = (MAXOFF + KP + 3) / 4;
-  const int d = mt * BM + t;
-  const bool row_ok = d <= p.D;
-  const int64_t i0 = (int64_t)d * KP;   // KP == K (exact class count)
+  constexpr int NV = 32 * KP / 4;  // float4s of a warp's block
+  const int d = mt * BM + ew * 32 + lane;
+  const int64_t P = (int64_t)(p.D + 1) * KP;             // KP == K (exact class count)
+  const int64_t i0w = (int64_t)(mt * BM + ew * 32) * KP;  // first parameter of the warp's block (multiple of 32)
   const uint64_t gstep = p.step0 + (uint64_t)step;
   const uint32_t slo = (uint32_t)gstep, shi = TAG_NOISE | (uint32_t)((gstep >> 32) & 0xffffff);
   for (int cc = part; cc < p.cpt; cc += PARTS) {
@@ -92,63 +97,61 @@ __device__ __forceinline__ void sg_update_tile(const PersistParams& p, uint32_t 
     if (c >= p.C) break;  // warp-uniform
     uint32_t raw[KP];
     tmem_ld_cols<KP>(tacc + (uint32_t)(cc * KP), raw);
-    float qe[KP], ze[KP];
-    float* qrow = p.q + (int64_t)c * p.ld + i0;
-    float* prow = p.p + (int64_t)c * p.ld + i0;
-    if (row_ok) {
+    tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < KP; ++k) qe[k] = __ldcg(qrow + k);  // L2: another SM wrote it one step ago
-      if (KIND == BHMC_KIND_SGLD) {
-        if (p.z) {
-          const float* zr = p.z + (int64_t)step * p.z_step_stride + (int64_t)c * p.ld_z + i0;
+    for (int k = 0; k < KP; ++k) S[lane * KP + k] = __uint_as_float(raw[k]) * p.scale;  // X^T (P - Y), row layout
+    __syncwarp();
+    float* qc = p.q + (int64_t)c * p.ld;
+    float* pc = p.p + (int64_t)c * p.ld;
 #pragma unroll
-          for (int k = 0; k < KP; ++k) ze[k] = __ldcs(zr + k);
+    for (int f0 = 0; f0 < NV; f0 += 32) {
+      const int f = f0 + lane;
+      const int64_t gi = i0w + 4 * f;
+      if (f < NV && gi < P) {
+        const float4 q4 = __ldcg(reinterpret_cast<const float4*>(qc + gi));  // L2: another SM wrote it one step ago
+        const float4 g4 = *reinterpret_cast<const float4*>(S + 4 * f);
+        float4 z4;
+        if (KIND == BHMC_KIND_SGLD) {
+          if (p.z) {
+            const float* zr = p.z + (int64_t)step * p.z_step_stride + (int64_t)c * p.ld_z + gi;
+            z4.x = __ldcs(zr);
+            z4.y = gi + 1 < P ? __ldcs(zr + 1) : 0.f;
+            z4.z = gi + 2 < P ? __ldcs(zr + 2) : 0.f;
+            z4.w = gi + 3 < P ? __ldcs(zr + 3) : 0.f;
+          } else {
+            z4 = philox_normal4(p.seed, p.chain_id0 + c, (uint32_t)(gi >> 2), slo, shi);
+          }
         } else {
-          // the generator hands out 4 normals per element block (i >> 2), exactly as k_sgld / k_tc_reduce_step key them
-          float n[NB * 4];
-          const uint32_t b0 = (uint32_t)(i0 >> 2);
-#pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            const float4 v = philox_normal4(p.seed, p.chain_id0 + c, b0 + (uint32_t)b, slo, shi);
-            n[4 * b] = v.x, n[4 * b + 1] = v.y, n[4 * b + 2] = v.z, n[4 * b + 3] = v.w;
-          }
-          const int off = (int)(i0 & 3);
-#pragma unroll
-          for (int k = 0; k < KP; ++k) {
-            float v = n[k];
-            if constexpr (MAXOFF >= 2) v = off == 2 ? n[k + 2] : v;
-            if constexpr (MAXOFF >= 3) v = off == 1 ? n[k + 1] : off == 3 ? n[k + 3] : v;
-            ze[k] = v;
-          }
+          z4 = __ldcg(reinterpret_cast<const float4*>(pc + gi));  // heavy-ball momentum
         }
-      } else {
+        const float qe[4] = {q4.x, q4.y, q4.z, q4.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, ze[4] = {z4.x, z4.y, z4.z, z4.w};
+        float pe[4], qn[4];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) ze[k] = __ldcg(prow + k);  // heavy-ball momentum
+        for (int x = 0; x < 4; ++x) {
+          const float g = fmaf(p.alpha, qe[x], ge[x]);  // + alpha q
+          pe[x] = KIND == BHMC_KIND_SGLD ? (2.0f * eps) * ze[x] - (0.5f * eps) * g   // sgld.py:31-46
+                                         : p.gamma * ze[x] - eps * g;                // sgd.py:40
+          if (gi + x >= P) pe[x] = 0.f;  // padding of the parameter row
+          qn[x] = qe[x] + pe[x];
+        }
+        *reinterpret_cast<float4*>(pc + gi) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+        *reinterpret_cast<float4*>(qc + gi) = make_float4(qn[0], qn[1], qn[2], qn[3]);
+        *reinterpret_cast<float4*>(S + 4 * f) = make_float4(qn[0], qn[1], qn[2], qn[3]);
       }
     }
-    tmem_ld_wait();
-    if (row_ok) {
+    __syncwarp();
+    if (d < p.D) {  // operand copy of the new weights for the next forward pass (the bias is added in the epilogue)
+      __nv_bfloat16* wh = p.wt_hi + ((int64_t)c * KP) * p.Dp + d;
+      __nv_bfloat16* wl = p.wt_lo ? p.wt_lo + ((int64_t)c * KP) * p.Dp + d : nullptr;
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
-        const float g = fmaf(p.alpha, qe[k], __uint_as_float(raw[k]) * p.scale);  // X^T(P-Y) + alpha q
-        const float pe = KIND == BHMC_KIND_SGLD ? (2.0f * eps) * ze[k] - (0.5f * eps) * g   // sgld.py:31-46
-                                                : p.gamma * ze[k] - eps * g;                // sgd.py:40
-        qe[k] += pe;
-        prow[k] = pe;
-        qrow[k] = qe[k];
-      }
-      if (d < p.D) {  // operand copy of the new weights for the next forward pass (the bias is added in the epilogue)
-        __nv_bfloat16* wh = p.wt_hi + ((int64_t)c * KP) * p.Dp + d;
-        __nv_bfloat16* wl = p.wt_lo ? p.wt_lo + ((int64_t)c * KP) * p.Dp + d : nullptr;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          __nv_bfloat16 hb, lb;
-          split_bf16(p.scale * qe[k], hb, lb);
-          wh[(int64_t)k * p.Dp] = hb;
-          if (wl) wl[(int64_t)k * p.Dp] = lb;
-        }
+        __nv_bfloat16 hb, lb;
+        split_bf16(p.scale * S[lane * KP + k], hb, lb);
+        wh[(int64_t)k * p.Dp] = hb;
+        if (wl) wl[(int64_t)k * p.Dp] = lb;
       }
     }
+    __syncwarp();  // the block is reused by the warp's next chain
   }
 }
 
@@ -257,6 +260,9 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   };
 
   const int ew = warp & 3, part = (warp - 4) >> 2, t = ew * 32 + lane;
+  // per-warp block of 32 x KP floats behind the stage ring (update epilogue)
+  float* epi_S = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes) +
+                 (warp >= 4 ? (warp - 4) * 32 * KP : 0);
   const int m_tiles_f = (int)((p.batch + BM - 1) / BM);
   const int items_f = m_tiles_f * p.n_tiles, items_b = p.m_tiles_b * p.n_tiles;
   // forward-epilogue parameters that do not change from step to step
@@ -265,17 +271,33 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   pf.dm_slab = BK, pf.dm_slab_rows = p.dm_rows, pf.dm_ld = BK, pf.dmt_hi = p.dmt_hi, pf.dmt_lo = p.dmt_lo;
   pf.split3 = p.split3, pf.write_dm = 1, pf.m_tiles = m_tiles_f, pf.skip_loglik = 1;
 
+  const bool timer = p.prof && threadIdx.x == NON_EPI_THREADS;  // first epilogue thread
+  long long tF = 0, tW1 = 0, tB = 0, tW2 = 0, t_prev = timer ? clock64() : 0;
   for (int step = 0; step < p.n_steps; ++step) {
     const int64_t row0 = p.row_first + (int64_t)step * p.batch;
     const int shift = (int)(row0 % BK);
     const int k_chunks_b = (int)((p.batch + shift + BK - 1) / BK);
     // ---------------- phase F: Z = X_window . W^T, softmax, (P - Y)^T ----------------
     if (warp == 0) {
-      if (lane == 0)
+      if (lane == 0) {
+        // Every step works on a NEW window of X: its tiles come from HBM in 128-byte pieces of 128 different rows, and
+        // with 13 / 9 dependent chunks per item and 3 stages the phases were bound by that latency (in-kernel timers:
+        // 19 k / 18 k cycles per phase for ~5 k cycles of MMA work).  The window of the next phase is known one phase
+        // ahead, so one CTA per row tile asks for it in L2 while the current phase computes (BHMC_PERSIST_PF=0: off).
+        if (p.prefetch)
+          for (int w = blockIdx.x; w < items_b; w += gridDim.x)
+            if (w % p.n_tiles == 0) {  // X^T window of this step's backward phase
+              const int slab0 = (int)((row0 - shift) / BK), mt = w / p.n_tiles;
+              for (int k = 0; k < k_chunks_b; ++k) {
+                tma_prefetch_2d(&tmXt_hi, 0, (slab0 + k) * p.xt_rows + mt * BM);
+                if (na == 2) tma_prefetch_2d(&tmXt_lo, 0, (slab0 + k) * p.xt_rows + mt * BM);
+              }
+            }
         for (int w = blockIdx.x; w < items_f; w += gridDim.x) {
           const int mt = w / p.n_tiles, nt = w % p.n_tiles;
           produce(&tmXa_hi, &tmXa_lo, &tmWt_hi, &tmWt_lo, p.k_chunks_f, 0, BK, (int)row0 + mt * BM, 0, 0, BK, nt * p.BN, 0);
         }
+      }
     } else if (warp == 1) {
       for (int w = blockIdx.x; w < items_f; w += gridDim.x) issue(p.k_chunks_f);
     } else if (warp >= 4) {
@@ -293,11 +315,22 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
         mbar_arrive(smem_u32(&bar_tempty[buf]));
       }
     }
+    if (timer) { const long long t = clock64(); tF += t - t_prev; t_prev = t; }
     grid_barrier(p.bar, ++n_bar * gridDim.x);
+    if (timer) { const long long t = clock64(); tW1 += t - t_prev; t_prev = t; }
     // ---------------- phase B: G = X_window^T (P - Y), update, next W^T operand ----------------
     if (warp == 0) {
       if (lane == 0) {
         const int slab0 = (int)((row0 - shift) / BK);  // X^T is stored in blocks of BK rows of X: [slab][xt_rows][BK]
+        if (p.prefetch && step + 1 < p.n_steps)
+          for (int w = blockIdx.x; w < items_f; w += gridDim.x)
+            if (w % p.n_tiles == 0) {  // X window of the next step's forward phase
+              const int mt = w / p.n_tiles;
+              for (int k = 0; k < p.k_chunks_f; ++k) {
+                tma_prefetch_2d(&tmXa_hi, k * BK, (int)(row0 + p.batch) + mt * BM);
+                if (na == 2) tma_prefetch_2d(&tmXa_lo, k * BK, (int)(row0 + p.batch) + mt * BM);
+              }
+            }
         for (int w = blockIdx.x; w < items_b; w += gridDim.x) {
           const int mt = w / p.n_tiles, nt = w % p.n_tiles;
           produce(&tmXt_hi, &tmXt_lo, &tmDm_hi, &tmDm_lo, k_chunks_b, 0, 0, slab0 * p.xt_rows + mt * BM, p.xt_rows, 0, 0,
@@ -314,13 +347,19 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
         mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-        if (p.kind == BHMC_KIND_SGLD) sg_update_tile<KP, EW, BHMC_KIND_SGLD>(p, tacc, mt, nt, part, t, step, eps);
-        else sg_update_tile<KP, EW, BHMC_KIND_SGD>(p, tacc, mt, nt, part, t, step, eps);
+        if (p.kind == BHMC_KIND_SGLD) sg_update_tile<KP, EW, BHMC_KIND_SGLD>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S);
+        else sg_update_tile<KP, EW, BHMC_KIND_SGD>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S);
         tcgen05_fence_before();
         mbar_arrive(smem_u32(&bar_tempty[buf]));
       }
     }
+    if (timer) { const long long t = clock64(); tB += t - t_prev; t_prev = t; }
     grid_barrier(p.bar, ++n_bar * gridDim.x);
+    if (timer) { const long long t = clock64(); tW2 += t - t_prev; t_prev = t; }
+  }
+  if (timer) {
+    long long* o = p.prof + (size_t)blockIdx.x * 8;
+    o[0] = tF, o[1] = tW1, o[2] = tB, o[3] = tW2, o[4] = p.n_steps;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -373,8 +412,9 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   const int smode = split3 ? (d.x_exact ? 2 : 1) : 0;
   const int nmat = split3 ? 2 : 1, na = smode == 1 ? 2 : 1;
   const int stage_bytes = na * BM * BK * 2 + nmat * BN * BK * 2;
-  const int stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t epi_bytes = (size_t)16 * 32 * KP * sizeof(float);  // update epilogue: one 32 x KP block per epilogue warp
+  const int stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024 - epi_bytes) / stage_bytes)));
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + epi_bytes;
   const int64_t ncols = (int64_t)C * KP;
   const int64_t dm_rows = (int64_t)n_tiles * BN, dm_nslab = ceil_div(Mfwd + BK, BK);
   void *wt = nullptr, *dmt = nullptr, *bar = nullptr;
@@ -426,12 +466,47 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   p.bar = (unsigned int*)bar;
   const int items = std::max((int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles);
   const int grid = std::min(items, ctx->sm_count);
-  GroupTimer t(ctx, KG_FWD);
-  switch (KP) {
-    case 4: return launch_sg_persistent<4>(ctx, maps, p, grid, smem);
-    case 8: return launch_sg_persistent<8>(ctx, maps, p, grid, smem);
-    case 10: return launch_sg_persistent<10>(ctx, maps, p, grid, smem);
-    case 16: return launch_sg_persistent<16>(ctx, maps, p, grid, smem);
+  static int want_prof = -1, want_pf = -1;
+  if (want_prof < 0) want_prof = getenv("BHMC_PROF") ? 1 : 0;
+  if (want_pf < 0) {
+    const char* e = getenv("BHMC_PERSIST_PF");
+    want_pf = e ? atoi(e) : 1;
   }
-  return BHMC_ERR_UNSUPPORTED;
+  p.prefetch = want_pf;
+  void* prof_dev = nullptr;
+  if (want_prof) {
+    BHMC_TRY(ctx->get_scratch(5, sizeof(long long) * 8 * 1024, &prof_dev));
+    BHMC_CUDA_OK(cudaMemsetAsync(prof_dev, 0, sizeof(long long) * 8 * 1024, ctx->stream));
+    p.prof = (long long*)prof_dev;
+  }
+  int rc = BHMC_ERR_UNSUPPORTED;
+  {
+    GroupTimer t(ctx, KG_FWD);
+    switch (KP) {
+      case 4: rc = launch_sg_persistent<4>(ctx, maps, p, grid, smem); break;
+      case 8: rc = launch_sg_persistent<8>(ctx, maps, p, grid, smem); break;
+      case 10: rc = launch_sg_persistent<10>(ctx, maps, p, grid, smem); break;
+      case 16: rc = launch_sg_persistent<16>(ctx, maps, p, grid, smem); break;
+    }
+  }
+  if (want_prof && rc == BHMC_OK) {
+    std::vector<long long> hp(8 * 148);
+    BHMC_CUDA_OK(cudaMemcpyAsync(hp.data(), prof_dev, sizeof(long long) * 8 * 148, cudaMemcpyDeviceToHost, ctx->stream));
+    BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    double s[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0}, mn[4] = {1e30, 1e30, 1e30, 1e30};
+    int n = 0;
+    for (int b = 0; b < grid && b < 148; ++b) {
+      if (hp[b * 8 + 4] <= 0) continue;
+      ++n;
+      for (int j = 0; j < 4; ++j) {
+        const double v = (double)hp[b * 8 + j] / (double)hp[b * 8 + 4];
+        s[j] += v, mx[j] = std::max(mx[j], v), mn[j] = std::min(mn[j], v);
+      }
+    }
+    if (n)
+      fprintf(stderr, "[bhmc prof persist] %d CTAs, %d steps, items F %d B %d, BN %d stages %d | cycles per step, mean (min..max) over CTAs: phase F %.0f (%.0f..%.0f); barrier 1 %.0f (%.0f..%.0f); phase B %.0f (%.0f..%.0f); barrier 2 %.0f (%.0f..%.0f)\n",
+              n, n_steps, (int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles, BN, stages, s[0] / n, mn[0], mx[0], s[1] / n, mn[1], mx[1], s[2] / n,
+              mn[2], mx[2], s[3] / n, mn[3], mx[3]);
+  }
+  return rc;
 }
