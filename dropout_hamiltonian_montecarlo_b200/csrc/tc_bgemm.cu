@@ -46,6 +46,128 @@ struct BgParams {
   GemmDesc d;              // sizes + epilogue (the A/B pointers inside are unused here)
 };
 
+// Fused epilogue of one 128 x BN accumulator tile (thread = row; the EW/4 warps of a TMEM lane quarter split the 16-column
+// chunks): bias, alpha/2*W, ReLU gate, Philox / injected dropout + ReLU, fp32 stores.
+__device__ __forceinline__ void bg_epilogue_tile(const BgParams& p, uint32_t tacc, int z, int mt, int nt, int part, int t) {
+  const GemmDesc& d = p.d;
+  constexpr int PARTS = EW / 4;
+  const int m = mt * BM + t;
+  for (int j0 = part * 16; j0 < p.BN; j0 += 16 * PARTS) {
+    uint32_t raw[16];
+    tmem_ld<16>(tacc + (uint32_t)j0, raw);  // all lanes take part (.sync.aligned), stores are predicated below
+    tmem_ld_wait();
+    const int n0 = nt * p.BN + j0;
+    if (m < d.M && n0 < d.N) {
+      // Every input of the 16 outputs is fetched BEFORE the first store: with loads and stores interleaved per
+      // element the compiler must keep them in program order (C may alias the inputs for all it knows), which
+      // made the epilogue one dependent DRAM round trip per element (ncu: 104 us for the W1-gradient GEMM, tensor
+      // pipe 14 %).  p.vec: row strides and base addresses allow 16-byte accesses.
+      const int nq = min(4, (d.N - n0 + 3) >> 2);  // quads with at least one valid column
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+      if (d.bias) {
+        const float* bp = d.bias + (int64_t)z * d.bias_batch + n0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + j < d.N) v[j] += __ldg(bp + j);
+      }
+      if (d.addsrc) {
+        const float* ap = d.addsrc + (int64_t)z * d.add_batch + (int64_t)m * d.add_rs + n0;
+        if (p.vec) {
+          float4 t4[4];
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) t4[qd] = qd < nq ? __ldg(reinterpret_cast<const float4*>(ap) + qd) : make_float4(0, 0, 0, 0);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            v[4 * qd] = fmaf(d.add_scale, t4[qd].x, v[4 * qd]);
+            v[4 * qd + 1] = fmaf(d.add_scale, t4[qd].y, v[4 * qd + 1]);
+            v[4 * qd + 2] = fmaf(d.add_scale, t4[qd].z, v[4 * qd + 2]);
+            v[4 * qd + 3] = fmaf(d.add_scale, t4[qd].w, v[4 * qd + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < d.N) v[j] = fmaf(d.add_scale, __ldg(ap + j), v[j]);
+        }
+      }
+      if (d.gate) {
+        const float* gp = d.gate + (int64_t)z * d.gate_batch + (int64_t)m * d.gate_rs + n0;
+        if (p.vec) {
+          float4 t4[4];
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) t4[qd] = qd < nq ? __ldg(reinterpret_cast<const float4*>(gp) + qd) : make_float4(0, 0, 0, 0);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            v[4 * qd] = t4[qd].x > 0.f ? v[4 * qd] * d.gate_scale : 0.f;
+            v[4 * qd + 1] = t4[qd].y > 0.f ? v[4 * qd + 1] * d.gate_scale : 0.f;
+            v[4 * qd + 2] = t4[qd].z > 0.f ? v[4 * qd + 2] * d.gate_scale : 0.f;
+            v[4 * qd + 3] = t4[qd].w > 0.f ? v[4 * qd + 3] * d.gate_scale : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < d.N) v[j] = __ldg(gp + j) > 0.f ? v[j] * d.gate_scale : 0.f;
+        }
+      }
+      uint32_t ka = 0xFFFFu, kb = 0xFFFFu;  // keep bits of the 16 columns
+      if (d.epi >= 1) {
+        ka = 0;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          if (qd >= nq) break;
+          const int n = n0 + 4 * qd;
+          uint32_t k4 = 0;
+          if (d.mask_a) {
+            for (int j = 0; j < 4; ++j)
+              if (n + j < d.N && d.mask_a[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
+          } else {
+            k4 = keep_bits4(d, z, m, n, d.layer_a);
+          }
+          ka |= k4 << (4 * qd);
+        }
+        if (d.epi == 2) {
+          kb = 0;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            if (qd >= nq) break;
+            const int n = n0 + 4 * qd;
+            uint32_t k4 = 0;
+            if (d.mask_b) {
+              for (int j = 0; j < 4; ++j)
+                if (n + j < d.N && d.mask_b[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
+            } else {
+              k4 = keep_bits4(d, z, m, n, d.layer_b);
+            }
+            kb |= k4 << (4 * qd);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = v[j];
+        if (d.epi >= 1) {
+          x = ((ka >> j) & 1u) ? x * d.keep_inv : 0.f;
+          x = fmaxf(x, 0.f);
+          if (d.epi == 2) x = ((kb >> j) & 1u) ? x * d.keep_inv : 0.f;
+        }
+        v[j] = x;
+      }
+      float* cp = d.C + (int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n0;
+      if (p.vec) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+          if (qd < nq) reinterpret_cast<float4*>(cp)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + j < d.N) cp[j] = v[j];
+      }
+    }
+  }
+
+}
+
 __global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
 k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
            const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const BgParams p) {
@@ -145,9 +267,7 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
       umma_commit(smem_u32(&bar_tfull[buf]));
     }
   } else if (warp >= 4) {
-    const GemmDesc& d = p.d;
     const int ew = warp & 3, part = (warp - 4) >> 2;
-    constexpr int PARTS = EW / 4;
     const int t = ew * 32 + lane;
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
@@ -157,120 +277,7 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      const int m = mt * BM + t;
-      for (int j0 = part * 16; j0 < p.BN; j0 += 16 * PARTS) {
-        uint32_t raw[16];
-        tmem_ld<16>(tacc + (uint32_t)j0, raw);  // all lanes take part (.sync.aligned), stores are predicated below
-        tmem_ld_wait();
-        const int n0 = nt * p.BN + j0;
-        if (m < d.M && n0 < d.N) {
-          // Every input of the 16 outputs is fetched BEFORE the first store: with loads and stores interleaved per
-          // element the compiler must keep them in program order (C may alias the inputs for all it knows), which
-          // made the epilogue one dependent DRAM round trip per element (ncu: 104 us for the W1-gradient GEMM, tensor
-          // pipe 14 %).  p.vec: row strides and base addresses allow 16-byte accesses.
-          const int nq = min(4, (d.N - n0 + 3) >> 2);  // quads with at least one valid column
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-          if (d.bias) {
-            const float* bp = d.bias + (int64_t)z * d.bias_batch + n0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + j < d.N) v[j] += __ldg(bp + j);
-          }
-          if (d.addsrc) {
-            const float* ap = d.addsrc + (int64_t)z * d.add_batch + (int64_t)m * d.add_rs + n0;
-            if (p.vec) {
-              float4 t4[4];
-#pragma unroll
-              for (int qd = 0; qd < 4; ++qd) t4[qd] = qd < nq ? __ldg(reinterpret_cast<const float4*>(ap) + qd) : make_float4(0, 0, 0, 0);
-#pragma unroll
-              for (int qd = 0; qd < 4; ++qd) {
-                v[4 * qd] = fmaf(d.add_scale, t4[qd].x, v[4 * qd]);
-                v[4 * qd + 1] = fmaf(d.add_scale, t4[qd].y, v[4 * qd + 1]);
-                v[4 * qd + 2] = fmaf(d.add_scale, t4[qd].z, v[4 * qd + 2]);
-                v[4 * qd + 3] = fmaf(d.add_scale, t4[qd].w, v[4 * qd + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + j < d.N) v[j] = fmaf(d.add_scale, __ldg(ap + j), v[j]);
-            }
-          }
-          if (d.gate) {
-            const float* gp = d.gate + (int64_t)z * d.gate_batch + (int64_t)m * d.gate_rs + n0;
-            if (p.vec) {
-              float4 t4[4];
-#pragma unroll
-              for (int qd = 0; qd < 4; ++qd) t4[qd] = qd < nq ? __ldg(reinterpret_cast<const float4*>(gp) + qd) : make_float4(0, 0, 0, 0);
-#pragma unroll
-              for (int qd = 0; qd < 4; ++qd) {
-                v[4 * qd] = t4[qd].x > 0.f ? v[4 * qd] * d.gate_scale : 0.f;
-                v[4 * qd + 1] = t4[qd].y > 0.f ? v[4 * qd + 1] * d.gate_scale : 0.f;
-                v[4 * qd + 2] = t4[qd].z > 0.f ? v[4 * qd + 2] * d.gate_scale : 0.f;
-                v[4 * qd + 3] = t4[qd].w > 0.f ? v[4 * qd + 3] * d.gate_scale : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (n0 + j < d.N) v[j] = __ldg(gp + j) > 0.f ? v[j] * d.gate_scale : 0.f;
-            }
-          }
-          uint32_t ka = 0xFFFFu, kb = 0xFFFFu;  // keep bits of the 16 columns
-          if (d.epi >= 1) {
-            ka = 0;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-              if (qd >= nq) break;
-              const int n = n0 + 4 * qd;
-              uint32_t k4 = 0;
-              if (d.mask_a) {
-                for (int j = 0; j < 4; ++j)
-                  if (n + j < d.N && d.mask_a[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
-              } else {
-                k4 = keep_bits4(d, z, m, n, d.layer_a);
-              }
-              ka |= k4 << (4 * qd);
-            }
-            if (d.epi == 2) {
-              kb = 0;
-#pragma unroll
-              for (int qd = 0; qd < 4; ++qd) {
-                if (qd >= nq) break;
-                const int n = n0 + 4 * qd;
-                uint32_t k4 = 0;
-                if (d.mask_b) {
-                  for (int j = 0; j < 4; ++j)
-                    if (n + j < d.N && d.mask_b[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
-                } else {
-                  k4 = keep_bits4(d, z, m, n, d.layer_b);
-                }
-                kb |= k4 << (4 * qd);
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = v[j];
-            if (d.epi >= 1) {
-              x = ((ka >> j) & 1u) ? x * d.keep_inv : 0.f;
-              x = fmaxf(x, 0.f);
-              if (d.epi == 2) x = ((kb >> j) & 1u) ? x * d.keep_inv : 0.f;
-            }
-            v[j] = x;
-          }
-          float* cp = d.C + (int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n0;
-          if (p.vec) {
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-              if (qd < nq) reinterpret_cast<float4*>(cp)[qd] = make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + j < d.N) cp[j] = v[j];
-          }
-        }
-      }
+      bg_epilogue_tile(p, tacc, z, mt, nt, part, t);
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[buf]));
     }
@@ -280,6 +287,143 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same GEMM with cta_group::2 (round 2).  ncu of k_tc_bgemm at cfg4: tensor pipe 29-37 %.  A 128 x 128 tile streams
+// 64 KB per K chunk (A and B, hi and lo) for 12 MMAs of 64 cycles -- the ~50 B/clk an SM ingests allow a chunk every
+// ~1 200 cycles where the MMAs need 768.  Here a cluster of two CTAs owns TWO adjacent 128-row tiles (M = 256) and one
+// N tile up to 256 wide: every CTA stages its own A tile and only HALF of the B tile (32 KB + BN/2 rows), the leader's
+// elected thread issues tcgen05.mma.cta_group::2.  At BN = 256 that is 64 KB per CTA for 12 MMAs of 128 cycles: the
+// main loop is bound by the tensor pipe again.  Barrier protocol as in k_tc_fwd2 (softmax_tc.cu).
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
+k_tc_bgemm2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+            const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const BgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int a_bytes = BM * BK * 2, bh_bytes = (p.BN / 2) * BK * 2;  // this CTA's half of the B tile
+  const int nmat = p.split3 ? 2 : 1;
+  const int stage_bytes = nmat * (a_bytes + bh_bytes);
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int tiles = m_pairs * p.n_tiles;
+  const int num_work = p.batch * tiles;
+  const int wi0 = blockIdx.x / 2, wi_step = gridDim.x / 2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 2 * 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  pdl_launch_dependents();
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // only shared / tensor memory was touched so far
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = wi0; w < num_work; w += wi_step) {
+        const int z = w / tiles, rem = w % tiles, mt = 2 * (rem / p.n_tiles) + rank, nt = rem % p.n_tiles;
+        const int za = p.a_shared ? 0 : z, zb = p.b_shared ? 0 : z;
+        for (int k = 0; k < p.k_chunks; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);  // same offset in the leader CTA
+          if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + nmat * a_bytes;
+          // rows beyond M (phantom half of an odd last pair) and beyond N are out of bounds of the map: zero fill
+          tma_load_3d_2sm(sa, &tmA_hi, full, k * BK, mt * BM, za);
+          if (p.split3) tma_load_3d_2sm(sa + a_bytes, &tmA_lo, full, k * BK, mt * BM, za);
+          tma_load_3d_2sm(sb, &tmB_hi, full, k * BK, nt * p.BN + rank * (p.BN / 2), zb);
+          if (p.split3) tma_load_3d_2sm(sb + bh_bytes, &tmB_lo, full, k * BK, nt * p.BN + rank * (p.BN / 2), zb);
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {  // ===== MMA issuer (leader CTA; warp-uniform loop, elected lane issues) =====
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = wi0; w < num_work; w += wi_step, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+        for (int k = 0; k < p.k_chunks; ++k) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t first = k > 0 ? 1u : 0u;
+          if (p.split3) {
+            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+            const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + bh_bytes);
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+          } else {
+            const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+              umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+            }
+          }
+          umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);  // frees the stage in BOTH CTAs
+          if (++stage == p.stages) stage = 0, phase ^= 1u;
+        }
+        umma_commit_2sm(smem_u32(&bar_tfull[buf]), 3);  // accumulator halves complete in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, each on its own 128 rows) =====
+    const int ew = warp & 3, part = (warp - 4) >> 2;
+    const int t = ew * 32 + lane;
+    int it = 0;
+    for (int w = wi0; w < num_work; w += wi_step, ++it) {
+      const int z = w / tiles, rem = w % tiles, mt = 2 * (rem / p.n_tiles) + rank, nt = rem % p.n_tiles;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+      tcgen05_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+      bg_epilogue_tile(p, tacc, z, mt, nt, part, t);  // rows of a phantom tile fail its m < M test
+      tcgen05_fence_before();
+      if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
+      else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
 
@@ -457,9 +601,32 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
       }
     }
   }
+  // cta_group::2 kernel (BHMC_BG2=0: off): two row tiles per cluster and an N tile chosen by a cost model -- a chunk
+  // takes max(12 MMAs of BN/2 cycles, (32 KB + BN/2 rows) at ~52 B/clk of ingest), the clusters need
+  // ceil(items / clusters) rounds, plus the epilogue of a tile per round
+  static int bg2_env = -1;
+  if (bg2_env < 0) {
+    const char* e = getenv("BHMC_BG2");
+    bg2_env = e ? atoi(e) : 0;
+  }
   p.m_tiles = (int)ceil_div(d.M, BM);
-  p.n_tiles = (int)ceil_div(d.N, p.BN);
   p.k_chunks = (int)ceil_div(d.K, BK);
+  const bool pair = bg2_env && p.m_tiles >= 2 && d.N >= 64;
+  if (pair) {
+    const int clusters = ctx->sm_count / 2, m_pairs = (p.m_tiles + 1) / 2;
+    double best = 1e30;
+    for (int bn = 64; bn <= 256; bn += 16) {
+      const int st_b = (split3 ? 2 : 1) * (BM * BK * 2 + (bn / 2) * BK * 2);
+      if ((225 * 1024) / st_b < 2) continue;
+      const int64_t items = (int64_t)batch * m_pairs * ceil_div(d.N, bn);
+      const double rounds = (double)ceil_div(items, (int64_t)clusters);
+      const double chunk = std::max(6.0 * bn * (split3 ? 1.0 : 1.0 / 3.0), (double)st_b / 52.0);
+      const double cost = rounds * (p.k_chunks * chunk + 400.0 + 12.0 * bn);
+      if (cost < best - 1e-9) best = cost, p.BN = bn;
+    }
+    if (bg2_env >= 64 && bg2_env % 16 == 0 && bg2_env <= 256) p.BN = bg2_env;  // BHMC_BG2=<n>: forced N tile (A/B)
+  }
+  p.n_tiles = (int)ceil_div(d.N, p.BN);
   p.split3 = split3 ? 1 : 0;
   p.a_shared = a_shared;
   p.b_shared = b_shared;
@@ -471,26 +638,31 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
     if (d.gate) v = v && al16(d.gate) && d.gate_batch % 4 == 0 && d.gate_rs % 4 == 0;
     p.vec = v ? 1 : 0;
   }
-  const int stage_bytes = (split3 ? 2 : 1) * (BM * BK * 2 + p.BN * BK * 2);
+  const uint32_t b_box = (uint32_t)(pair ? p.BN / 2 : p.BN);
+  const int stage_bytes = (split3 ? 2 : 1) * (BM * BK * 2 + (int)b_box * BK * 2);
   p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   BHMC_TRY(make_map3(&mA_hi, a_hi, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, (uint64_t)Kp, BM));
-  BHMC_TRY(make_map3(&mB_hi, b_hi, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, (uint32_t)p.BN));
+  BHMC_TRY(make_map3(&mB_hi, b_hi, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, b_box));
   if (split3) {
     BHMC_TRY(make_map3(&mA_lo, a_lo, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, (uint64_t)Kp, BM));
-    BHMC_TRY(make_map3(&mB_lo, b_lo, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, (uint32_t)p.BN));
+    BHMC_TRY(make_map3(&mB_lo, b_lo, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, b_box));
   } else {
     mA_lo = mA_hi;
     mB_lo = mB_hi;
   }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured = 0, configured2 = 0;
+  if (!pair && smem > configured) {
     BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const int work = batch * p.m_tiles * p.n_tiles;
-  const int grid = std::min(work, ctx->sm_count);
+  if (pair && smem > configured2) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured2 = smem;
+  }
+  const int work = batch * (pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  const int grid = pair ? 2 * std::min(work, ctx->sm_count / 2) : std::min(work, ctx->sm_count);
   // programmatic dependent launch of the batched GEMM: its prologue runs under the split kernel in front of it
   // (MLP parity tests green with it; cfg4 43.8 k -> 45.4 k grad-evals/s in one A/B pair).  BHMC_PDL_MLP=0: plain launch.
   static int pdl_env = -1;
@@ -503,12 +675,24 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   cfg.blockDim = dim3(NON_EPI_THREADS + 32 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_env) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_env ? 1 : 0;
-  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bgemm, mA_hi, mA_lo, mB_hi, mB_lo, p));
+  cfg.numAttrs = na;
+  if (pair) BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bgemm2, mA_hi, mA_lo, mB_hi, mB_lo, p));
+  else BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bgemm, mA_hi, mA_lo, mB_hi, mB_lo, p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
