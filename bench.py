@@ -568,6 +568,16 @@ def bench_cfg4(ctx, X, y, rank, world, dev, prec, peak_tf, steps=20, C=16):
     return out
 
 
+def _cfg4_both(ctx, X, y, rank, world, dev, prec, peak_tf):
+    """The cfg4 block at 16 chains per GPU (its `value`; the width round 1 reported) with the same run at 64 chains per
+    GPU beside it (SURVEY 8(d) gives 8-64 chains per GPU for this config: wider chain batches fill the machine better)."""
+    out = bench_cfg4(ctx, X, y, rank, world, dev, prec, peak_tf)
+    wide = bench_cfg4(ctx, X, y, rank, world, dev, prec, peak_tf, steps=8, C=64)
+    out["chains_64"] = {k: wide[k] for k in ("workload", "value", "ms_per_step", "steps", "algorithmic_tflops")}
+    out["chains_64"]["roofline_frac"] = wide["roofline"]["frac"]
+    return out
+
+
 def bench_cfg5_rows(ctx, rank, world, dev, prec, peak_tf, steps=4, rows=1000000, D=2048, K=38, C=8):
     """BASELINE configs[4]: full-batch HMC softmax, N = 1 M rows x 2048 features x 38 classes, 8 chains replicated on
     every rank, rows sharded N/G per rank, ONE grouped NCCL all-reduce (gradient + log-lik) per evaluation enqueued by
@@ -850,7 +860,7 @@ def run_ours(args, wl):
     peak_tf_all = peaks()[0]
     want = set(args.blocks.split(",")) if args.blocks else set()
     for name, fn in (("cfg3", lambda: bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf_all)),
-                     ("cfg4", lambda: bench_cfg4(ctx, X, y, rank, world, dev, prec, peak_tf_all)),
+                     ("cfg4", lambda: _cfg4_both(ctx, X, y, rank, world, dev, prec, peak_tf_all)),
                      ("cfg5_row_sharded", lambda: bench_cfg5_rows(ctx, rank, world, dev, prec, peak_tf_all,
                                                                   rows=args.cfg5_rows))):
         if name not in want:
