@@ -791,15 +791,21 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long t_tempty = 0, t_full = 0, t_issue = 0, t_start = clock64(), n_chunks = 0;
       for (int w = wi0; w < num_work; w += wi_step, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
+        long long c0 = p.prof ? clock64() : 0;
         mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
         tcgen05_fence_after();
+        if (p.prof) t_tempty += clock64() - c0;
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
         for (int k = 0; k < p.k_chunks; ++k) {
+          long long c1 = p.prof ? clock64() : 0;
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tcgen05_fence_after();
+          long long c2 = p.prof ? clock64() : 0;
+          if (p.prof) t_full += c2 - c1, ++n_chunks;
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t first = k > 0 ? 1u : 0u;
           if (p.split3 == 1) {
@@ -830,9 +836,14 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             }
           }
           umma_commit_2sm(smem_u32(&bar_empty[stage]), 3);  // frees the stage in BOTH CTAs
+          if (p.prof) t_issue += clock64() - c2;
           if (++stage == p.stages) stage = 0, phase ^= 1u;
         }
         umma_commit_2sm(smem_u32(&bar_tfull[buf]), 3);  // accumulator halves complete in both CTAs
+      }
+      if (p.prof && lane == 0) {
+        long long* o = p.prof + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - t_start, o[1] = t_tempty, o[2] = t_full, o[3] = t_issue, o[4] = n_chunks, o[5] = it;
       }
     }
   } else if (warp >= 4) {
@@ -847,7 +858,7 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      if (mt < p.m_tiles) fwd_epilogue_tile<KP, EW, EXACT>(p, tacc, mt, nt, part, lane, t);
+      if (mt < p.m_tiles && p.debug != 1) fwd_epilogue_tile<KP, EW, EXACT>(p, tacc, mt, nt, part, lane, t);  // debug 1: measurement only
       tcgen05_fence_before();
       if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
       else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
