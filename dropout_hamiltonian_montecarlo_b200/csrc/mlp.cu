@@ -12,6 +12,8 @@
 // (k_mlp_gemm below); BHMC_PREC_BF16X3 / BF16 send the five large ones to tcgen05 (tc_bgemm.cu).
 // Because relu(a*m) > 0 implies the keep-mask m == 1, the backward pass needs only the stored activations
 // (H1, H2d), not the masks:  dA2 = dH2d * [H2d>0] / keep^2,  dA1 = dH1 * [H1>0] / keep.
+#include <cuda_bf16.h>
+
 #include <new>
 
 #include <stdlib.h>
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(256) k_mlp_gemm(GemmDesc d) {
         if (d.epi == 2) v = ((kb >> j) & 1u) ? v * d.keep_inv : 0.f;
       }
       d.C[(int64_t)c * d.c_batch + (int64_t)m * d.c_rs + n] = v;
+      if (d.ck_hi) split_store_pair(v, d.ck_hi, d.ck_lo, (int64_t)c * d.ck_batch + (int64_t)m * d.ck_ld + n);
+      if (d.ct_hi) split_store_pair(v, d.ct_hi, d.ct_lo, (int64_t)c * d.ct_batch + (int64_t)n * d.ct_ld + m);
     }
   }
 }
@@ -241,6 +245,19 @@ __global__ void __launch_bounds__(128) k_mlp_gemm_small_k(GemmDesc d) {
       v.w = gt.w > 0.f ? v.w * d.gate_scale : 0.f;
     }
     *reinterpret_cast<float4*>(d.C + (int64_t)c * d.c_batch + (int64_t)m * d.c_rs + n) = v;
+    if (d.ck_hi) {  // K-major operand copy of the row: four consecutive bf16 = one 8-byte store (ck_ld % 4 == 0, n % 4 == 0)
+      const float ve[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hb[j] = __float2bfloat16_rn(ve[j]);
+        lb[j] = __float2bfloat16_rn(ve[j] - __bfloat162float(hb[j]));
+      }
+      const int64_t o = (int64_t)c * d.ck_batch + (int64_t)m * d.ck_ld + n;
+      *reinterpret_cast<uint2*>(d.ck_hi + o) = *reinterpret_cast<const uint2*>(hb);
+      if (d.ck_lo) *reinterpret_cast<uint2*>(d.ck_lo + o) = *reinterpret_cast<const uint2*>(lb);
+    }
+    // (no transposed copy here: this kernel walks rows, a column-major write would be 2 bytes per 32-byte sector)
   }
 }
 
@@ -260,7 +277,8 @@ static int run_gemm(bhmc_ctx* ctx, const GemmDesc& d, int C) {
     k_mlp_gemm_small_m<<<dim3((unsigned)ceil_div(d.N, 32), C), 32 * SM_GROUPS, sm, ctx->stream>>>(d);
   } else if (skinny_env && plain && d.K <= SKINNY && d.M <= 4 * 65535 && d.b_cs == 1 && d.N % 4 == 0 && !d.bias && !d.addsrc && al16(d.B) &&
              d.b_batch % 4 == 0 && d.b_rs % 4 == 0 && al16(d.C) && d.c_batch % 4 == 0 && d.c_rs % 4 == 0 &&
-             (!d.gate || (al16(d.gate) && d.gate_batch % 4 == 0 && d.gate_rs % 4 == 0))) {
+             (!d.gate || (al16(d.gate) && d.gate_batch % 4 == 0 && d.gate_rs % 4 == 0)) && !d.ct_hi &&
+             (!d.ck_hi || (d.ck_ld % 4 == 0 && d.ck_batch % 4 == 0))) {
     k_mlp_gemm_small_k<<<dim3((unsigned)ceil_div(d.N, 512), (unsigned)ceil_div(d.M, 4), C), 128, 0, ctx->stream>>>(d);
   } else {
     dim3 grid((unsigned)ceil_div(d.M, TM), (unsigned)ceil_div(d.N, TN), (unsigned)C);
@@ -393,6 +411,35 @@ struct MlpModel : ModelBase {
     // the five large GEMMs go to the tensor cores unless the fp32 CUDA-core path is requested; the three GEMMs
     // that touch the n_out-wide logits (N, M or K = n_out ~ 10) stay on CUDA cores
     const bool use_tc = prec != BHMC_PREC_FP32, split3 = prec == BHMC_PREC_BF16X3;
+    // Producer-written operand copies (GemmDesc::ck_* / ct_*, round 2): H1, dA2 and dA1 reach their consumer GEMMs as
+    // bf16 hi/lo matrices written by the epilogue that computed them, in both orientations where two consumers
+    // contract over different indices -- four of the eight large split launches of an evaluation disappear.  The
+    // values are the split of the same fp32 numbers, so the result is bit-identical (BHMC_MLP_FUSE=0: separate splits).
+    static int fuse_env = -1;
+    if (fuse_env < 0) {
+      const char* e = getenv("BHMC_MLP_FUSE");
+      fuse_env = e ? atoi(e) : 1;
+    }
+    const bool fuse = fuse_env && use_tc && g && B >= 64 && n_mid >= 64 && n_in >= 64;
+    const int64_t kp_mid = round_up(n_mid, 64), kp_b = round_up(B, 64);
+    const int64_t e_k = (int64_t)B * kp_mid, e_t = (int64_t)n_mid * kp_b;  // elements per chain of a K-major / transposed copy
+    __nv_bfloat16 *H1k = nullptr, *H1t = nullptr, *dA2k = nullptr, *dA2t = nullptr, *dA1t = nullptr;
+    const int64_t lo_k = (int64_t)C * e_k, lo_t = (int64_t)C * e_t;  // offset of the lo copy inside a buffer
+    if (fuse) {
+      void* cb = nullptr;
+      BHMC_TRY(ctx->get_scratch(15, sizeof(__nv_bfloat16) * 2 * (size_t)(2 * lo_k + 3 * lo_t), &cb));
+      H1k = (__nv_bfloat16*)cb;
+      dA2k = H1k + 2 * lo_k;
+      H1t = dA2k + 2 * lo_k;
+      dA2t = H1t + 2 * lo_t;
+      dA1t = dA2t + 2 * lo_t;
+    }
+    auto out_k = [&](GemmDesc& gd, __nv_bfloat16* buf) {
+      gd.ck_hi = buf, gd.ck_lo = split3 ? buf + lo_k : nullptr, gd.ck_batch = e_k, gd.ck_ld = kp_mid;
+    };
+    auto out_t = [&](GemmDesc& gd, __nv_bfloat16* buf) {
+      gd.ct_hi = buf, gd.ct_lo = split3 ? buf + lo_t : nullptr, gd.ct_batch = e_t, gd.ct_ld = kp_b;
+    };
     auto run_gemm = [&](bhmc_ctx* cx, const GemmDesc& gd, int batch) -> int {
       if (use_tc && gd.M >= 64 && gd.N >= 64 && gd.K >= 64) return tc_bgemm(cx, gd, batch, split3);
       return bhmc::run_gemm(cx, gd, batch);
@@ -408,6 +455,7 @@ struct MlpModel : ModelBase {
       d.M = B, d.N = n_mid, d.K = n_in;
       d.bias = q + ob1, d.bias_batch = ld;
       d.epi = 1, d.layer_a = 0, d.mask_a = masks ? masks : nullptr;
+      if (fuse) out_k(d, H1k), out_t(d, H1t);
       BHMC_TRY(run_gemm(ctx, d, C));
       // H2d = dropout(relu(dropout(H1 W2^T + b2)))
       d = base();
@@ -419,6 +467,7 @@ struct MlpModel : ModelBase {
       d.epi = 2, d.layer_a = 1, d.layer_b = 2;
       d.mask_a = masks ? masks + (size_t)C * mstride : nullptr;
       d.mask_b = masks ? masks + 2 * (size_t)C * mstride : nullptr;
+      if (fuse) d.a_hi = H1k, d.a_lo = split3 ? H1k + lo_k : nullptr, d.a_kp = kp_mid;
       BHMC_TRY(run_gemm(ctx, d, C));
       // Z = H2d W3^T + b3
       d = base();
@@ -455,6 +504,7 @@ struct MlpModel : ModelBase {
     d.C = dA2, d.c_batch = act, d.c_rs = n_mid;
     d.M = B, d.N = n_mid, d.K = n_out;
     d.gate = H2d, d.gate_batch = act, d.gate_rs = n_mid, d.gate_scale = keep_inv * keep_inv;
+    if (fuse) out_k(d, dA2k);  // its transposed copy (for gW2) stays a split launch: see k_mlp_gemm_small_k
     BHMC_TRY(run_gemm(ctx, d, C));
     // gW2 = dA2^T H1 + alpha/2 W2 ; gb2
     d = base();
@@ -463,6 +513,7 @@ struct MlpModel : ModelBase {
     d.C = g + oW2, d.c_batch = ld, d.c_rs = n_mid;
     d.M = n_mid, d.N = n_mid, d.K = B;
     d.addsrc = q + oW2, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
+    if (fuse) d.b_hi = H1t, d.b_lo = split3 ? H1t + lo_t : nullptr, d.b_kp = kp_b;
     BHMC_TRY(run_gemm(ctx, d, C));
     k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g);
     // dA1 = (dA2 W2) * [H1 > 0] / keep
@@ -472,6 +523,10 @@ struct MlpModel : ModelBase {
     d.C = dA1, d.c_batch = act, d.c_rs = n_mid;
     d.M = B, d.N = n_mid, d.K = n_mid;
     d.gate = H1, d.gate_batch = act, d.gate_rs = n_mid, d.gate_scale = keep_inv;
+    if (fuse) {
+      d.a_hi = dA2k, d.a_lo = split3 ? dA2k + lo_k : nullptr, d.a_kp = kp_mid;
+      out_t(d, dA1t);
+    }
     BHMC_TRY(run_gemm(ctx, d, C));
     // gW1 = dA1^T X + alpha/2 W1 ; gb1
     d = base();
@@ -480,6 +535,7 @@ struct MlpModel : ModelBase {
     d.C = g + oW1, d.c_batch = ld, d.c_rs = n_in;
     d.M = n_mid, d.N = n_in, d.K = B;
     d.addsrc = q + oW1, d.add_batch = ld, d.add_rs = n_in, d.add_scale = ha;
+    if (fuse) d.a_hi = dA1t, d.a_lo = split3 ? dA1t + lo_t : nullptr, d.a_kp = kp_b;
     BHMC_TRY(run_gemm(ctx, d, C));
     k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g);
     ctx->launches += 3;

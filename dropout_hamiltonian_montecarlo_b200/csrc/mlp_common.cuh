@@ -27,7 +27,26 @@ struct GemmDesc {
   uint64_t seed;
   int64_t chain_id0;
   uint32_t eval_id, layer_a, layer_b;
+  // Operand copies written by the producer (round 2).  The tensor-core GEMMs read K-major bf16 hi/lo copies of their
+  // fp32 operands; k_split_operand made them in a launch of its own, twice for an activation that one consumer contracts
+  // over its columns and another over its rows (10 launches, 25 % of an evaluation).  A GEMM whose result feeds another
+  // GEMM now writes the copies from its epilogue, in the layout(s) the consumers need:
+  //   ck_*: element (m, n) at ck + c*ck_batch + m*ck_ld + n   (K-major for a consumer that contracts over n)
+  //   ct_*: element (m, n) at ct + c*ct_batch + n*ct_ld + m   (K-major for a consumer that contracts over m)
+  // (lo == nullptr in single-pass mode; padding beyond N / M inside ck_ld / ct_ld is zeroed once by the owner)
+  __nv_bfloat16 *ck_hi, *ck_lo, *ct_hi, *ct_lo;
+  int64_t ck_batch, ck_ld, ct_batch, ct_ld;
+  // ...and a consumer is handed the copies instead of the fp32 matrix: [c][rows][kp] with the contraction index
+  // contiguous; tc_bgemm then skips its split of that operand
+  const __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
+  int64_t a_kp, b_kp;
 };
+
+__device__ __forceinline__ void split_store_pair(float v, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t o) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[o] = h;
+  if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 
 __device__ __forceinline__ uint32_t keep_bits4(const GemmDesc& d, int c, int m, int n, uint32_t layer) {
   // four Bernoulli(keep_prob) draws for units n..n+3 (n % 4 == 0) of row m; bit e = keep

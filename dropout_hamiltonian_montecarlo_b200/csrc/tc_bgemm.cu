@@ -163,6 +163,42 @@ __device__ __forceinline__ void bg_epilogue_tile(const BgParams& p, uint32_t tac
         for (int j = 0; j < 16; ++j)
           if (n0 + j < d.N) cp[j] = v[j];
       }
+      // bf16 hi/lo operand copies for the GEMMs that consume this result (GemmDesc::ck_* / ct_*)
+      if (d.ck_hi || d.ct_hi) {
+        __nv_bfloat16 hb[16], lb[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          hb[j] = __float2bfloat16_rn(v[j]);
+          lb[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hb[j]));
+        }
+        if (d.ck_hi) {  // this row, 16 consecutive columns: 32 bytes per copy
+          const int64_t o = (int64_t)z * d.ck_batch + (int64_t)m * d.ck_ld + n0;
+          if (p.vec && (d.ck_ld & 7) == 0 && n0 + 16 <= d.N) {
+            reinterpret_cast<uint4*>(d.ck_hi + o)[0] = reinterpret_cast<const uint4*>(hb)[0];
+            reinterpret_cast<uint4*>(d.ck_hi + o)[1] = reinterpret_cast<const uint4*>(hb)[1];
+            if (d.ck_lo) {
+              reinterpret_cast<uint4*>(d.ck_lo + o)[0] = reinterpret_cast<const uint4*>(lb)[0];
+              reinterpret_cast<uint4*>(d.ck_lo + o)[1] = reinterpret_cast<const uint4*>(lb)[1];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + j < d.N) {
+                d.ck_hi[o + j] = hb[j];
+                if (d.ck_lo) d.ck_lo[o + j] = lb[j];
+              }
+          }
+        }
+        if (d.ct_hi) {  // transposed: for every column the warp's 32 rows are 64 contiguous bytes
+          const int64_t o = (int64_t)z * d.ct_batch + (int64_t)n0 * d.ct_ld + m;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + j < d.N) {
+              d.ct_hi[o + (int64_t)j * d.ct_ld] = hb[j];
+              if (d.ct_lo) d.ct_lo[o + (int64_t)j * d.ct_ld] = lb[j];
+            }
+        }
+      }
     }
   }
 
@@ -552,29 +588,32 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   const bool a_shared = d.a_batch == 0, b_shared = d.b_batch == 0;
   const int za = a_shared ? 1 : batch, zb = b_shared ? 1 : batch;
   const size_t a_elems = (size_t)za * d.M * Kp, b_elems = (size_t)zb * d.N * Kp;
+  // operands already split by their producer (GemmDesc::a_hi / b_hi) skip the split launch
+  const bool a_pre = d.a_hi != nullptr && d.a_kp == Kp && (!split3 || d.a_lo), b_pre = d.b_hi != nullptr && d.b_kp == Kp && (!split3 || d.b_lo);
   void *sa = nullptr, *sb = nullptr;
-  BHMC_TRY(ctx->get_scratch(1, a_elems * 2 * 2, &sa));
-  BHMC_TRY(ctx->get_scratch(2, b_elems * 2 * 2, &sb));
-  __nv_bfloat16 *a_hi = (__nv_bfloat16*)sa, *a_lo = a_hi + a_elems;
-  __nv_bfloat16 *b_hi = (__nv_bfloat16*)sb, *b_lo = b_hi + b_elems;
-  {
+  if (!a_pre) BHMC_TRY(ctx->get_scratch(1, a_elems * 2 * 2, &sa));
+  if (!b_pre) BHMC_TRY(ctx->get_scratch(2, b_elems * 2 * 2, &sb));
+  const __nv_bfloat16 *a_hi = a_pre ? d.a_hi : (const __nv_bfloat16*)sa, *a_lo = a_pre ? d.a_lo : a_hi + a_elems;
+  const __nv_bfloat16 *b_hi = b_pre ? d.b_hi : (const __nv_bfloat16*)sb, *b_lo = b_pre ? d.b_lo : b_hi + b_elems;
+  if (!a_pre || !b_pre) {
     GroupTimer t(ctx, KG_PREP);
     static int tr_env = -1;  // BHMC_SPLIT_TR: tile rows of the split kernel (32 or 64; A/B measurements)
     if (tr_env < 0) {
       const char* e = getenv("BHMC_SPLIT_TR");
       tr_env = e && atoi(e) == 64 ? 64 : 32;  // measured at cfg4: 44.3 k (32) vs 43.2 k (64) grad-evals/s
     }
+    __nv_bfloat16 *wa_hi = (__nv_bfloat16*)sa, *wa_lo = wa_hi + a_elems, *wb_hi = (__nv_bfloat16*)sb, *wb_lo = wb_hi + b_elems;
     // B is (k, n) with strides (b_rs, b_cs): its K-major copy has rows n
     if (tr_env == 64) {
       dim3 ga((unsigned)(Kp / 64), (unsigned)ceil_div(d.M, 64), (unsigned)za), gb((unsigned)(Kp / 64), (unsigned)ceil_div(d.N, 64), (unsigned)zb);
-      k_split_operand<64><<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, a_hi, split3 ? a_lo : nullptr);
-      k_split_operand<64><<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, b_hi, split3 ? b_lo : nullptr);
+      if (!a_pre) k_split_operand<64><<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, wa_hi, split3 ? wa_lo : nullptr);
+      if (!b_pre) k_split_operand<64><<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, wb_hi, split3 ? wb_lo : nullptr);
     } else {
       dim3 ga((unsigned)(Kp / 64), (unsigned)ceil_div(d.M, 32), (unsigned)za), gb((unsigned)(Kp / 64), (unsigned)ceil_div(d.N, 32), (unsigned)zb);
-      k_split_operand<32><<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, a_hi, split3 ? a_lo : nullptr);
-      k_split_operand<32><<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, b_hi, split3 ? b_lo : nullptr);
+      if (!a_pre) k_split_operand<32><<<ga, 256, 0, ctx->stream>>>(d.A, d.a_batch, d.a_rs, d.a_cs, d.M, d.K, Kp, wa_hi, split3 ? wa_lo : nullptr);
+      if (!b_pre) k_split_operand<32><<<gb, 256, 0, ctx->stream>>>(d.B, d.b_batch, d.b_cs, d.b_rs, d.N, d.K, Kp, wb_hi, split3 ? wb_lo : nullptr);
     }
-    ctx->launches += 2;
+    ctx->launches += (a_pre ? 0 : 1) + (b_pre ? 0 : 1);
   }
   BgParams p{};
   p.batch = batch;

@@ -160,3 +160,50 @@ def test_mlp_predict(prec):
     p1 = m1.predict(par, X, prob=True)
     np.testing.assert_allclose(p1.sum(axis=2), 1.0, rtol=1e-5)
     assert np.abs(p1 - probs).max() > 1e-3  # dropout really is on
+
+
+def test_mlp_producer_written_operand_copies_are_bit_identical():
+    """csrc/mlp.cu (round 2): the GEMM epilogues write the bf16 hi/lo operand copies their consumers need
+    (GemmDesc::ck_* / ct_*) instead of separate split launches.  The copies are the split of the same fp32 values, so
+    the gradient must be BIT-identical to the one of the split-launch path (BHMC_MLP_FUSE=0), for the hi/lo scheme and
+    the single pass; every variant runs in its own interpreter (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from dropout_hamiltonian_montecarlo_b200.runtime import MlpHandle, default_context
+ctx = default_context()
+rs = np.random.RandomState(4)
+out = {}
+for name, (N, n_in, n_mid, n_out, C, row0, B) in {"cfg4": (1200, 784, 512, 10, 5, 500, 500), "odd": (700, 200, 192, 7, 3, 64, 333)}.items():
+    X = torch.as_tensor(rs.rand(N, n_in).astype(np.float32)).cuda(); y = torch.as_tensor(rs.randint(0, n_out, N).astype(np.int32)).cuda()
+    h = MlpHandle(ctx, N, n_in, n_mid, n_out, 0.01, 0.1, seed=3, chain_id0=2); h.bind(X, y)
+    q = h.pack(rs.normal(0, .05, (C, h.P)).astype(np.float32))
+    for prec in (1, 2):
+        g, st = h.grad(q, row0, B, prec)
+        ctx.sync()
+        out["%%s_g%%d" %% (name, prec)] = g[:, :h.P].cpu().numpy(); out["%%s_s%%d" %% (name, prec)] = st.cpu().numpy()
+        l0 = ctx.launches
+        h.grad(q, row0, B, prec); ctx.sync()
+        out["%%s_l%%d" %% (name, prec)] = ctx.launches - l0
+    h.close()
+np.savez(sys.argv[1], **out)
+''' % (root,)
+    res = []
+    for fuse in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".npz") as f:
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=dict(os.environ, BHMC_MLP_FUSE=fuse), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-3000:]
+            res.append({k: v for k, v in np.load(f.name).items()})
+    a, b = res
+    for name in ("cfg4", "odd"):
+        for prec in (1, 2):
+            # Philox dropout masks are keyed by an evaluation counter, identical in both processes
+            np.testing.assert_array_equal(a["%s_g%d" % (name, prec)], b["%s_g%d" % (name, prec)])
+            np.testing.assert_array_equal(a["%s_s%d" % (name, prec)], b["%s_s%d" % (name, prec)])
+            assert int(a["%s_l%d" % (name, prec)]) == int(b["%s_l%d" % (name, prec)]) - 4, (name, prec, a["%s_l%d" % (name, prec)], b["%s_l%d" % (name, prec)])
