@@ -765,6 +765,22 @@ k_tc_fwd2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       for (int w = wi0; w < num_work; w += wi_step) {
         const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
         for (int k = 0; k < p.k_chunks; ++k) {
+          if (p.prefetch) {
+            // (measurement switch, off by default) Launches that carry few chains have one or two N tiles: every X tile
+            // comes straight from HBM and the MMA thread waits 811 of 1 490 cycles per chunk for operands (in-kernel
+            // counters at 16 chains).  Asking for the X tile `prefetch` chunks ahead in L2 did NOT help: see the host side.
+            const int cl = k + p.prefetch, wn = w + (cl / p.k_chunks) * wi_step, kn = cl % p.k_chunks;
+            if (wn < num_work) {
+              int pk = p.a_k0 + kn * BK, pm = p.a_m0 + (2 * (wn / p.n_tiles) + rank) * BM;
+              if (p.a_slab) {
+                const int sl = pk / p.a_slab;
+                pk -= sl * p.a_slab;
+                pm += sl * p.a_slab_rows;
+              }
+              tma_prefetch_2d(&tmA_hi, pk, pm);
+              if (na == 2) tma_prefetch_2d(&tmA_lo, pk, pm);
+            }
+          }
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);  // same offset in the leader CTA
           if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
@@ -1876,6 +1892,17 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.a_m0 = (int)row0;
   if (d.xa_blocked) p.a_slab = 64, p.a_slab_rows = (int)d.N;
   p.pair = fwd_pair;
+  {
+    // L2 prefetch distance of the cta_group::2 forward kernel, in chunks (BHMC_FWD_PF, default 0 = off).  Measured on one
+    // box at 8 / 16 / 32 / 64 chains per launch: 62.8 / 75.2 / 140.8 / 145.7 us without, 71.5 / 84.3 / 127.6 / 165.8 us at a
+    // distance of 8 (4 and 16 alike): it helps only the two-N-tile case and costs 10-14 % everywhere else.
+    static int pf_fwd = -1;
+    if (pf_fwd < 0) {
+      const char* e = getenv("BHMC_FWD_PF");
+      pf_fwd = e ? std::max(0, atoi(e)) : 0;
+    }
+    p.prefetch = pf_fwd;
+  }
   p.C = C;
   p.K = K;
   p.cpt = cpt;
