@@ -5,6 +5,7 @@
 //   sgmcmc.sample + sgld.step      hamiltonian/inference/cpu/sgmcmc.py:40-89, sgld.py:31-46
 //   sgd.fit                        hamiltonian/inference/cpu/sgd.py:25-45
 // for C chains at once, enqueueing kernels on one stream with no host round-trip inside a step.
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <string.h>
 #include <time.h>
@@ -70,7 +71,32 @@ int bhmc_ctx::get_pinned(size_t bytes, void** out) {
   return BHMC_OK;
 }
 
+// NVTX ranges (tracing).  The header-only NVTX v3 resolves the injection library lazily: without a profiler
+// attached a push / pop is a load and a branch.  BHMC_NVTX=1 switches them on: one range per library run
+// (bhmc_sampler_hmc_run / bhmc_sampler_sg_run) and one per kernel group of a gradient evaluation (forward GEMM, backward
+// GEMM + reduce, operand preparation, update), so that `ncu --nvtx --nvtx-include "bhmc.bwd/"` or a timeline tool can cut
+// the launch stream the way DESIGN.md section 4 names it.
+static bool nvtx_on() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BHMC_NVTX");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_on()) {
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
+};
+static const char* const kGroupNames[bhmc::KG_COUNT] = {"bhmc.fwd", "bhmc.bwd", "bhmc.prep", "bhmc.update"};
+
 void bhmc_ctx::begin_group(int g) {
+  if (nvtx_on()) nvtxRangePushA(kGroupNames[g]);
   sampled[g] = false;
   if (!timing || (timing == 2 && g >= KG_PREP)) return;
   if ((seen[g]++ % timing_stride) != 0) return;
@@ -92,6 +118,7 @@ void bhmc_ctx::begin_group(int g) {
 }
 
 void bhmc_ctx::end_group(int g) {
+  if (nvtx_on()) nvtxRangePop();
   if (!sampled[g]) return;
   cudaEventRecord(pool[g][used[g]].b, stream);
   used[g]++;
@@ -1166,6 +1193,7 @@ static int hmc_run_streaming(bhmc_sampler* s, bhmc_hmc_run* run, const std::vect
 
 // ---- HMC / SGHMC ---------------------------------------------------------------------------------
 int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
+  NvtxRange nvtx_run("bhmc_sampler_hmc_run");
   BHMC_CHECK_ARG(s && run, "NULL argument");
   const bhmc_sampler_config& cfg = s->cfg;
   BHMC_CHECK_ARG(cfg.kind == BHMC_KIND_HMC || cfg.kind == BHMC_KIND_SGHMC, "sampler kind %d cannot run hmc_run", cfg.kind);
@@ -1472,6 +1500,7 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
 
 // ---- SGLD / SGD ------------------------------------------------------------------------------------
 int bhmc_sampler_sg_run(bhmc_sampler* s, bhmc_sg_run* run) {
+  NvtxRange nvtx_run("bhmc_sampler_sg_run");
   BHMC_CHECK_ARG(s && run, "NULL argument");
   const bhmc_sampler_config& cfg = s->cfg;
   BHMC_CHECK_ARG(cfg.kind == BHMC_KIND_SGLD || cfg.kind == BHMC_KIND_SGD, "sampler kind %d cannot run sg_run", cfg.kind);
