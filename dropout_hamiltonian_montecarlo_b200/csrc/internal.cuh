@@ -89,6 +89,19 @@ struct GroupTimer {
   ~GroupTimer() { ctx->end_group(group); }
 };
 
+// Order-independent accumulation of energy terms (log-likelihood, kinetic energy, prior energy).  Several blocks add
+// their partial sums to one fp64 cell with atomics, in whatever order they arrive, and fp64 addition is not
+// associative: round 1's energies differed in the last bits from run to run, and with them -- rarely -- an accept
+// decision.  Every addend is now rounded to a multiple of 2^-FRAC first.  Sums of such numbers are EXACT in fp64 while
+// they stay below 2^(53-FRAC), so the result no longer depends on the order: same inputs, same bits.  FRAC = 24: exact up
+// to |sum| < 5.4e8 (a log-likelihood of 1e6 rows is ~4e6), the rounding adds < 6e-8 per partial (relative 1e-10 of such
+// a sum; the fp32 per-row terms carry 1e-7).  Beyond the range it degrades to ordinary rounding, never to a wrong value.
+template <int FRAC = 24>
+__device__ __forceinline__ double quantize_addend(double x) {
+  constexpr double S = (double)(1ull << FRAC);
+  return rint(x * S) * (1.0 / S);
+}
+
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

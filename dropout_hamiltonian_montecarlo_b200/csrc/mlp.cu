@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) k_mlp_loss(float* __restrict__ Z, int B, 
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int w = 0; w < 8; ++w) tot += sm[w];
-    atomicAdd(loss + c, tot);
+    atomicAdd(loss + c, quantize_addend<40>(tot));  // mean CE (< 8192): order-independent, see internal.cuh
   }
 }
 

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_softmax_rows(float* __restrict__ Z, int
     if (threadIdx.x == 0) {
       double tot = 0.0;
       for (int w = 0; w < 8; ++w) tot += sm[w];
-      atomicAdd(ll + c, tot);
+      atomicAdd(ll + c, quantize_addend<24>(tot));  // order-independent: see internal.cuh
     }
   }
 }

@@ -307,9 +307,9 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
       __shared__ float sll[4];
       if (lane == 0) sll[t >> 5] = ll;
       __syncthreads();
-      if (t == 0) atomicAdd(p.loglik + c, (double)sll[0] + (double)sll[1] + (double)sll[2] + (double)sll[3]);
+      if (t == 0) atomicAdd(p.loglik + c, quantize_addend<24>((double)sll[0] + (double)sll[1] + (double)sll[2] + (double)sll[3]));
     } else {
-      if (lane == 0 && p.debug != 2 && !p.skip_loglik) atomicAdd(p.loglik + c, (double)ll);
+      if (lane == 0 && p.debug != 2 && !p.skip_loglik) atomicAdd(p.loglik + c, quantize_addend<24>((double)ll));  // order-independent
     }
   }
 }
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(128) k_softmax_from_z_vec(const TcParams p, in
   __shared__ float sll[4];
   if ((threadIdx.x & 31) == 0) sll[threadIdx.x >> 5] = ll;
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(p.loglik + c, (double)sll[0] + (double)sll[1] + (double)sll[2] + (double)sll[3]);
+  if (threadIdx.x == 0) atomicAdd(p.loglik + c, quantize_addend<24>((double)sll[0] + (double)sll[1] + (double)sll[2] + (double)sll[3]));
 }
 
 // EW = number of epilogue warps (multiple of 4).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the

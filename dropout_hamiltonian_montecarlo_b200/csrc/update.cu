@@ -31,7 +31,7 @@ __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
   if (w == 0) {
     v = (l < TPB / 32) ? sm[l] : 0.0;
     v = warp_sum(v);
-    if (l == 0) atomicAdd(dst, v);
+    if (l == 0) atomicAdd(dst, quantize_addend<24>(v));  // order-independent: see internal.cuh
   }
 }
 

@@ -103,3 +103,30 @@ def test_grad_hook_path_matches_the_fused_path(sched):
     assert n0 == n1
     np.testing.assert_allclose(a1, a0, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(s1, s0, rtol=1e-5, atol=1e-6)
+
+
+def test_energies_and_decisions_are_bit_reproducible():
+    """Energy terms are accumulated with fp64 atomics in arrival order; every addend is rounded to a multiple of 2^-24
+    first (csrc/internal.cuh quantize_addend), so the sums are exact and do not depend on that order: the same call
+    twice gives the same bits -- log-likelihoods, acceptance probabilities, samples.  (Round 1: last-bit differences from
+    run to run.)  Several blocks per chain on purpose: N = 5000 rows, P = 3030."""
+    from dropout_hamiltonian_montecarlo_b200.runtime import SamplerHandle
+    rs = np.random.RandomState(21)
+    N, D, K, C, n_steps = 5000, 100, 30, 9, 4
+    X, y, _ = _case(N, D, K, C, 21)
+    q0 = rs.normal(0, .1, (C, (D + 1) * K)).astype(np.float32)
+    h = SoftmaxHandle(default_context(), N, D, K, 0.01)
+    h.bind(torch.as_tensor(X).cuda(), torch.as_tensor(y).cuda())
+    lls = [h.grad(h.pack(q0), 0, N, 1)[1].cpu().numpy().copy() for _ in range(6)]
+    for ll in lls[1:]:
+        assert np.array_equal(ll.view(np.int64), lls[0].view(np.int64))
+    assert np.all(lls[0] * 2.0 ** 24 == np.rint(lls[0] * 2.0 ** 24))  # on the grid: the sum was exact
+    outs = []
+    for rep in range(3):
+        s = SamplerHandle(h.ctx, h, 0, C, precision=1, seed=5)
+        s.set_q(q0)
+        o = s.hmc_run(n_steps, 2e-4, 2e-3, schedule="streaming")
+        outs.append((o["samples"].cpu().numpy().copy(), o["accept_prob"].cpu().numpy().copy()))
+    for smp, acc in outs[1:]:
+        assert np.array_equal(acc.view(np.int64), outs[0][1].view(np.int64))
+        assert np.array_equal(smp.view(np.int32), outs[0][0].view(np.int32))
