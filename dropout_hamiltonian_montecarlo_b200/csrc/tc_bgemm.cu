@@ -43,6 +43,7 @@ struct BgParams {
   int batch, m_tiles, n_tiles, k_chunks, BN, stages, split3;
   int a_shared, b_shared;  // operand identical for every chain (e.g. the data matrix)
   int vec;                 // epilogue may use 16-byte loads / stores (N % 4 == 0, strides % 4 == 0, 16 B aligned bases)
+  int debug_epi;           // measurement only (BHMC_BG_DEBUG_EPI): 1 = the epilogue does nothing (main loop alone; results wrong)
   GemmDesc d;              // sizes + epilogue (the A/B pointers inside are unused here)
 };
 
@@ -313,7 +314,7 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      bg_epilogue_tile(p, tacc, z, mt, nt, part, t);
+      if (p.debug_epi != 1) bg_epilogue_tile(p, tacc, z, mt, nt, part, t);
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[buf]));
     }
@@ -449,7 +450,7 @@ k_tc_bgemm2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
       tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      bg_epilogue_tile(p, tacc, z, mt, nt, part, t);  // rows of a phantom tile fail its m < M test
+      if (p.debug_epi != 1) bg_epilogue_tile(p, tacc, z, mt, nt, part, t);  // rows of a phantom tile fail its m < M test
       tcgen05_fence_before();
       if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
       else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
@@ -670,6 +671,14 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   p.a_shared = a_shared;
   p.b_shared = b_shared;
   p.d = d;
+  {
+    static int dbg_env = -1;
+    if (dbg_env < 0) {
+      const char* e = getenv("BHMC_BG_DEBUG_EPI");
+      dbg_env = e ? atoi(e) : 0;
+    }
+    p.debug_epi = dbg_env;
+  }
   {
     auto al16 = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
     bool v = d.N % 4 == 0 && al16(d.C) && d.c_batch % 4 == 0 && d.c_rs % 4 == 0;

@@ -258,9 +258,51 @@ def main_next_rows():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def main_mlp():
+    """the UNMODIFIED ``hamiltonian/models/gpu/mlp.py`` executed under ``oracle/chainer_shim.py`` (fake
+    chainer / cupy with Chainer's documented primitive semantics, derivatives by torch.autograd): grad, log_likelihood,
+    negative_log_posterior, log_prior and the logits of ``predict`` with the three dropout keep-masks recorded."""
+    from oracle import chainer_shim as S
+    os.makedirs(OUT, exist_ok=True)
+    M = S.load_reference_mlp()
+    keys = ("/l1/W", "/l1/b", "/l2/W", "/l2/b", "/l3/W", "/l3/b")
+    cases = {}
+    for name, (B, n_in, n_mid, n_out, alpha, scale) in {"tiny": (37, 20, 24, 5, 0.05, 0.3), "tc": (80, 64, 64, 10, 0.01, 0.3),
+                                                         "ragged": (67, 30, 72, 3, 0.5, 0.1)}.items():
+        rs = np.random.RandomState(300 + len(cases))
+        par = {"/l1/W": rs.normal(0, scale, (n_mid, n_in)), "/l1/b": rs.normal(0, scale, n_mid),
+               "/l2/W": rs.normal(0, scale, (n_mid, n_mid)), "/l2/b": rs.normal(0, scale, n_mid),
+               "/l3/W": rs.normal(0, scale, (n_out, n_mid)), "/l3/b": rs.normal(0, scale, n_out)}
+        X = rs.rand(B, n_in)
+        y = rs.randint(0, n_out, B)
+        masks = [(rs.rand(B, n_mid) >= 0.1) for _ in range(3)]
+        m = M.mlp({"alpha": alpha}, n_in, n_mid, n_out)
+        assert [k for k, _ in m.net.namedparams()] == list(keys)
+
+        def with_masks(fn):
+            S.MASKS[:] = [a.copy() for a in masks]
+            out = fn()
+            assert not S.MASKS  # exactly three dropout calls per forward pass (mlp.py:29-31)
+            return out
+
+        g = with_masks(lambda: m.grad(par, X_train=X, y_train=y))
+        d = dict(X=X, y=y, alpha=alpha, masks=np.stack(masks).astype(np.uint8),
+                 loss=with_masks(lambda: m.log_likelihood(par, X_train=X, y_train=y)),
+                 nlp=with_masks(lambda: m.negative_log_posterior(par, X_train=X, y_train=y)),
+                 log_prior=m.log_prior(par), pred=with_masks(lambda: m.predict(par, X)))
+        for k in keys:
+            d["par" + k] = par[k]
+            d["grad" + k] = g[k]
+        cases[name] = d
+    np.savez_compressed(os.path.join(OUT, "mlp_model.npz"), **{f"{c}.{k}": v for c, d_ in cases.items() for k, v in d_.items()})
+    print("mlp_model.npz", os.path.getsize(os.path.join(OUT, "mlp_model.npz")))
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "next":
         main_next_rows()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mlp":
+        main_mlp()
     else:
         main()

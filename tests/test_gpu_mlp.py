@@ -207,3 +207,32 @@ np.savez(sys.argv[1], **out)
             np.testing.assert_array_equal(a["%s_g%d" % (name, prec)], b["%s_g%d" % (name, prec)])
             np.testing.assert_array_equal(a["%s_s%d" % (name, prec)], b["%s_s%d" % (name, prec)])
             assert int(a["%s_l%d" % (name, prec)]) == int(b["%s_l%d" % (name, prec)]) - 4, (name, prec, a["%s_l%d" % (name, prec)], b["%s_l%d" % (name, prec)])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("case", ["tiny", "tc", "ragged"])
+def test_mlp_model_golden_through_cuda(case, prec):
+    """tests/golden/mlp_model.npz holds what the UNMODIFIED reference file models/gpu/mlp.py returned when executed under
+    oracle/chainer_shim.py (fake chainer / cupy, ``python -m oracle.make_golden mlp``), with its three dropout keep-masks
+    recorded: grad (mlp.py:47-64), log_likelihood (:66-78), negative_log_posterior (:80-82).  Tolerance rtol 1e-4 (+ 1e-5
+    of the largest entry for entries near zero); 'tc' has every GEMM dimension >= 64 so the tcgen05 path runs."""
+    from conftest import load_golden
+    g = load_golden("mlp_model.npz")[case]
+    par = {k: g["par" + k] for k in KEYS}
+    X, y, alpha = g["X"], g["y"], float(g["alpha"])
+    n_mid, n_in = par["/l1/W"].shape
+    n_out = par["/l3/W"].shape[0]
+    m = mlp({"alpha": alpha}, n_in, n_mid, n_out, precision=prec)
+    m.bind(X, y)
+    m.set_masks(g["masks"][:, None])  # [3, C = 1, B, n_mid]
+    got = m.grad(par, X_train=X, y_train=y)
+    for k in KEYS:
+        ref = np.asarray(g["grad" + k], dtype=np.float64)
+        gk = np.asarray(got[k], dtype=np.float64).reshape(ref.shape)
+        if prec == "fp32":
+            close(gk, ref, what=k)
+        else:  # ReLU kinks, see test_mlp_grad_loss_nlp_injected_masks
+            bad = np.abs(gk - ref) > 1e-4 * np.abs(ref) + 1e-5 * np.abs(ref).max()
+            assert bad.mean() <= 5e-3 and np.abs(gk - ref).max() <= 1e-3 * np.abs(ref).max(), (k, bad.mean())
+    close(m.log_likelihood(par, X_train=X, y_train=y), g["loss"], 1e-5)
+    close(m.negative_log_posterior(par, X_train=X, y_train=y), g["nlp"], 1e-5)

@@ -161,6 +161,23 @@ def test_mlp_grad_matches_autograd():
         np.testing.assert_allclose(g[k], tp[k].grad.numpy() + 0.5 * alpha * par[k], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("case", ["tiny", "tc", "ragged"])
+def test_mlp_model_golden(case):
+    """tests/golden/mlp_model.npz: outputs of the unmodified models/gpu/mlp.py run under oracle/chainer_shim.py
+    (``python -m oracle.make_golden mlp``) with the three dropout keep-masks recorded."""
+    g = load_golden("mlp_model.npz")[case]
+    par = {k: g["par" + k] for k in O.MLP_KEYS}
+    masks = [g["masks"][i].astype(np.float64) for i in range(3)]
+    alpha = float(g["alpha"])
+    ref = O.mlp_grad(par, g["X"], g["y"], masks, alpha)
+    for k in O.MLP_KEYS:
+        np.testing.assert_allclose(ref[k], g["grad" + k], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(O.mlp_loss(par, g["X"], g["y"], masks), g["loss"], rtol=1e-12)
+    np.testing.assert_allclose(O.mlp_nlp(par, g["X"], g["y"], masks, alpha), g["nlp"], rtol=1e-12)
+    np.testing.assert_allclose(O.mlp_log_prior(par, alpha), g["log_prior"], rtol=1e-12)
+    np.testing.assert_array_equal(O.mlp_forward(par, g["X"], masks)[0].argmax(axis=1), g["pred"])
+
+
 # ---- SURVEY 8(f) rows: logistic model, hmc on it, sgd.fit_dropout ---------------------------------
 @pytest.mark.parametrize("case", ["small", "d100", "clip"])
 def test_logistic_model(case):

@@ -158,3 +158,34 @@ def test_public_api_surface_matches_the_reference():
             want = [p.name for p in inspect.signature(fn).parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
             got = [p.name for p in inspect.signature(our_methods[name]).parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
             assert got[:len(want)] == want, "%s.%s%s vs reference %s" % (cls, name, got, want)
+
+
+def test_mlp_reference_file_under_the_chainer_shim():
+    """models/gpu/mlp.py needs Chainer + CuPy (not installable here).  oracle/chainer_shim.py supplies both as thin
+    stand-ins (Chainer's documented primitive semantics, derivatives by torch.autograd) so that the UNMODIFIED reference
+    file runs: layer order, dropout placement, loss reduction, prior terms, parameter names are the reference's own."""
+    from oracle import chainer_shim as S
+    M = S.load_reference_mlp()
+    rs = np.random.RandomState(5)
+    B, n_in, n_mid, n_out, alpha = 29, 17, 23, 6, 0.07
+    par = {"/l1/W": rs.normal(0, .3, (n_mid, n_in)), "/l1/b": rs.normal(0, .3, n_mid),
+           "/l2/W": rs.normal(0, .3, (n_mid, n_mid)), "/l2/b": rs.normal(0, .3, n_mid),
+           "/l3/W": rs.normal(0, .3, (n_out, n_mid)), "/l3/b": rs.normal(0, .3, n_out)}
+    X, y = rs.rand(B, n_in), rs.randint(0, n_out, B)
+    masks = [(rs.rand(B, n_mid) >= 0.1).astype(np.float64) for _ in range(3)]
+    m = M.mlp({"alpha": alpha}, n_in, n_mid, n_out)
+    assert tuple(k for k, _ in m.net.namedparams()) == O.MLP_KEYS
+    del S.DROPOUT_CALLS[:]
+    S.MASKS[:] = [a.copy() for a in masks]
+    g = m.grad(par, X_train=X, y_train=y)
+    assert S.DROPOUT_CALLS == [(0.1, (B, n_mid))] * 3 and O.MLP_DROPOUT == 0.1  # mlp.py:29-31
+    ref = O.mlp_grad(par, X, y, masks, alpha)
+    for k in O.MLP_KEYS:
+        np.testing.assert_allclose(g[k], ref[k], rtol=1e-10, atol=1e-13)
+    S.MASKS[:] = [a.copy() for a in masks]
+    np.testing.assert_allclose(m.log_likelihood(par, X_train=X, y_train=y), O.mlp_loss(par, X, y, masks), rtol=1e-12)
+    S.MASKS[:] = [a.copy() for a in masks]
+    np.testing.assert_allclose(m.negative_log_posterior(par, X_train=X, y_train=y), O.mlp_nlp(par, X, y, masks, alpha), rtol=1e-12)
+    np.testing.assert_allclose(m.log_prior(par), O.mlp_log_prior(par, alpha), rtol=1e-12)
+    S.MASKS[:] = [a.copy() for a in masks]
+    np.testing.assert_array_equal(m.predict(par, X), O.mlp_forward(par, X, masks)[0].argmax(axis=1))
