@@ -43,6 +43,7 @@ struct BgParams {
   int batch, m_tiles, n_tiles, k_chunks, BN, stages, split3;
   int a_shared, b_shared;  // operand identical for every chain (e.g. the data matrix)
   int vec;                 // epilogue may use 16-byte loads / stores (N % 4 == 0, strides % 4 == 0, 16 B aligned bases)
+  int epi2;                // second epilogue form (per-warp shared-memory block behind the pipeline stages)
   int debug_epi;           // measurement only (BHMC_BG_DEBUG_EPI): 1 = the epilogue does nothing (main loop alone; results wrong)
   GemmDesc d;              // sizes + epilogue (the A/B pointers inside are unused here)
 };
@@ -205,6 +206,165 @@ __device__ __forceinline__ void bg_epilogue_tile(const BgParams& p, uint32_t tac
 
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue, second form (round 2, default when p.vec; BHMC_BG_EPI2=0 selects the one above).  Measured at cfg4 with the
+// epilogue switched off (BHMC_BG_DEBUG_EPI=1): 72 of the 164 us the five GEMMs of an evaluation take are epilogue.  In
+// the TMEM layout a thread owns a row, so every load / store instruction of a warp touches 32 different rows (32 L2
+// sectors, each half used), and the inputs (alpha/2*W, ReLU gate) were fetched only after the accumulator was complete
+// -- one exposed DRAM round trip per 16-column chunk.  Here
+//   * the inputs of a tile are fetched BEFORE the wait on the accumulator barrier (two chunks in flight);
+//   * the accumulator chunk goes through a per-warp 32 x 16 fp32 block in shared memory (quad swizzle, conflict free both
+//     ways) and is processed in memory order: lane l owns columns 4(l%4)..+3 of rows 8i + l/4, i = 0..3 -- every global
+//     access of a warp covers 8 rows x 64 contiguous bytes (full sectors), the bf16 K-major copies 8 x 32 bytes;
+//   * the transposed bf16 copies (ct_*) read the finished block back in the row layout (64 contiguous bytes per store).
+// Same arithmetic per element in the same order, same Philox keys: results are bit-identical to the first form.
+struct EpiPre {
+  float4 a[4];  // addsrc or gate values of the lane's four row groups
+};
+
+__device__ __forceinline__ void bg_epi2_prefetch(const BgParams& p, int z, int mt, int nt, int chunk, int lane, EpiPre& pre) {
+  const GemmDesc& d = p.d;
+  const float* src = d.addsrc ? d.addsrc + (int64_t)z * d.add_batch : (d.gate ? d.gate + (int64_t)z * d.gate_batch : nullptr);
+  if (!src) return;
+  const int64_t rs = d.addsrc ? d.add_rs : d.gate_rs;
+  const int n = nt * p.BN + chunk * 16 + 4 * (lane & 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = mt * BM + (threadIdx.x & 96) + 8 * i + (lane >> 2);  // (threadIdx.x & 96) = 32 * TMEM lane quarter (NON_EPI_THREADS = 128)
+    pre.a[i] = (m < d.M && n < d.N) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)m * rs + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ void bg_epi2_chunk(const BgParams& p, uint32_t tacc, int z, int mt, int nt, int chunk, int lane,
+                                              float4* blk, const EpiPre& pre) {
+  const GemmDesc& d = p.d;
+  const int row0 = mt * BM + (threadIdx.x & 96);
+  // (1) accumulator chunk -> shared memory, thread = row
+  {
+    uint32_t raw[16];
+    tmem_ld<16>(tacc + (uint32_t)(chunk * 16), raw);
+    tmem_ld_wait();
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      blk[lane * 4 + (q ^ sw)] = make_float4(__uint_as_float(raw[4 * q]), __uint_as_float(raw[4 * q + 1]), __uint_as_float(raw[4 * q + 2]),
+                                             __uint_as_float(raw[4 * q + 3]));
+  }
+  __syncwarp();
+  // (2) memory order: lane = (row group l/4, column quad l%4)
+  const int q = lane & 3;
+  const int n = nt * p.BN + chunk * 16 + 4 * q;
+  const bool n_ok = n < d.N;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (d.bias && n_ok) bias4 = __ldg(reinterpret_cast<const float4*>(d.bias + (int64_t)z * d.bias_batch + n));
+  const bool want_t = d.ct_hi != nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2);
+    const int m = row0 + r;
+    const int slot = r * 4 + (q ^ ((r >> 1) & 3));
+    float4 v = blk[slot];
+    if (m < d.M && n_ok) {
+      v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
+      if (d.addsrc) {
+        v.x = fmaf(d.add_scale, pre.a[i].x, v.x), v.y = fmaf(d.add_scale, pre.a[i].y, v.y);
+        v.z = fmaf(d.add_scale, pre.a[i].z, v.z), v.w = fmaf(d.add_scale, pre.a[i].w, v.w);
+      } else if (d.gate) {
+        v.x = pre.a[i].x > 0.f ? v.x * d.gate_scale : 0.f, v.y = pre.a[i].y > 0.f ? v.y * d.gate_scale : 0.f;
+        v.z = pre.a[i].z > 0.f ? v.z * d.gate_scale : 0.f, v.w = pre.a[i].w > 0.f ? v.w * d.gate_scale : 0.f;
+      }
+      if (d.epi >= 1) {
+        uint32_t ka = 0, kb = 0xFu;
+        if (d.mask_a) {
+          const uint8_t* mp = d.mask_a + (int64_t)z * d.mask_batch + (int64_t)m * d.N + n;
+          ka = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
+        } else {
+          ka = keep_bits4(d, z, m, n, d.layer_a);
+        }
+        if (d.epi == 2) {
+          if (d.mask_b) {
+            const uint8_t* mp = d.mask_b + (int64_t)z * d.mask_batch + (int64_t)m * d.N + n;
+            kb = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
+          } else {
+            kb = keep_bits4(d, z, m, n, d.layer_b);
+          }
+        }
+        auto act = [&](float x, uint32_t bit) {
+          x = (ka & bit) ? x * d.keep_inv : 0.f;
+          x = fmaxf(x, 0.f);
+          if (d.epi == 2) x = (kb & bit) ? x * d.keep_inv : 0.f;
+          return x;
+        };
+        v.x = act(v.x, 1u), v.y = act(v.y, 2u), v.z = act(v.z, 4u), v.w = act(v.w, 8u);
+      }
+      *reinterpret_cast<float4*>(d.C + (int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n) = v;
+      if (d.ck_hi) {
+        const int64_t o = (int64_t)z * d.ck_batch + (int64_t)m * d.ck_ld + n;
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                            h3 = __float2bfloat16_rn(v.w);
+        __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a), pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(d.ck_hi + o) = pk;
+        if (d.ck_lo) {
+          a = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
+          b = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+          pk.x = *reinterpret_cast<uint32_t*>(&a), pk.y = *reinterpret_cast<uint32_t*>(&b);
+          *reinterpret_cast<uint2*>(d.ck_lo + o) = pk;
+        }
+      }
+    }
+    if (want_t) blk[slot] = v;
+  }
+  __syncwarp();
+  // (3) transposed bf16 copies: back to thread = row; for every column the warp's 32 rows are 64 contiguous bytes
+  if (want_t) {
+    const int m = row0 + lane;
+    const int n0 = nt * p.BN + chunk * 16;
+    const int sw = (lane >> 1) & 3;
+    if (m < d.M) {
+      const int64_t o = (int64_t)z * d.ct_batch + (int64_t)n0 * d.ct_ld + m;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        if (n0 + 4 * qq >= d.N) break;
+        const float4 v = blk[lane * 4 + (qq ^ sw)];
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(e[j]);
+          d.ct_hi[o + (int64_t)(4 * qq + j) * d.ct_ld] = h;
+          if (d.ct_lo) d.ct_lo[o + (int64_t)(4 * qq + j) * d.ct_ld] = __float2bfloat16_rn(e[j] - __bfloat162float(h));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// One tile: prefetch, wait for the accumulator, chunks.  `part` (0..EW/4-1) selects the warp's 16-column chunks.
+__device__ __forceinline__ void bg_epilogue_tile2(const BgParams& p, uint32_t tacc, int z, int mt, int nt, int part, int lane,
+                                                  float4* blk, uint32_t bar, uint32_t parity) {
+  constexpr int PARTS = EW / 4;
+  const int n_chunks = (p.BN / 16 - part + PARTS - 1) / PARTS;  // chunks part, part + PARTS, ...
+  EpiPre pre0, pre1;
+  if (n_chunks > 0) bg_epi2_prefetch(p, z, mt, nt, part, lane, pre0);
+  if (n_chunks > 1) bg_epi2_prefetch(p, z, mt, nt, part + PARTS, lane, pre1);
+  mbar_wait(bar, parity);
+  tcgen05_fence_after();
+  if (p.debug_epi == 1) return;
+  for (int k = 0; k < n_chunks; k += 2) {
+    const int c0 = part + k * PARTS;
+    if (nt * p.BN + c0 * 16 < p.d.N) bg_epi2_chunk(p, tacc, z, mt, nt, c0, lane, blk, pre0);
+    if (k + 2 < n_chunks) bg_epi2_prefetch(p, z, mt, nt, c0 + 2 * PARTS, lane, pre0);
+    if (k + 1 < n_chunks) {
+      const int c1 = c0 + PARTS;
+      if (nt * p.BN + c1 * 16 < p.d.N) bg_epi2_chunk(p, tacc, z, mt, nt, c1, lane, blk, pre1);
+      if (k + 3 < n_chunks) bg_epi2_prefetch(p, z, mt, nt, c1 + 2 * PARTS, lane, pre1);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
 k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
            const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const BgParams p) {
@@ -311,10 +471,15 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
       const int z = w / tiles, rem = w % tiles, mt = rem / p.n_tiles, nt = rem % p.n_tiles;
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
-      tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      if (p.debug_epi != 1) bg_epilogue_tile(p, tacc, z, mt, nt, part, t);
+      if (p.epi2) {
+        float4* blk = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + (warp - 4) * 128;
+        bg_epilogue_tile2(p, tacc, z, mt, nt, part, lane, blk, smem_u32(&bar_tfull[buf]), use & 1u);
+      } else {
+        mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+        tcgen05_fence_after();
+        if (p.debug_epi != 1) bg_epilogue_tile(p, tacc, z, mt, nt, part, t);
+      }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[buf]));
     }
@@ -447,10 +612,15 @@ k_tc_bgemm2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       const int z = w / tiles, rem = w % tiles, mt = 2 * (rem / p.n_tiles) + rank, nt = rem % p.n_tiles;
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
-      tcgen05_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-      if (p.debug_epi != 1) bg_epilogue_tile(p, tacc, z, mt, nt, part, t);  // rows of a phantom tile fail its m < M test
+      if (p.epi2) {  // rows of a phantom tile fail the m < M tests
+        float4* blk = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + (warp - 4) * 128;
+        bg_epilogue_tile2(p, tacc, z, mt, nt, part, lane, blk, smem_u32(&bar_tfull[buf]), use & 1u);
+      } else {
+        mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
+        tcgen05_fence_after();
+        if (p.debug_epi != 1) bg_epilogue_tile(p, tacc, z, mt, nt, part, t);
+      }
       tcgen05_fence_before();
       if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
       else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
@@ -688,7 +858,15 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   }
   const uint32_t b_box = (uint32_t)(pair ? p.BN / 2 : p.BN);
   const int stage_bytes = (split3 ? 2 : 1) * (BM * BK * 2 + (int)b_box * BK * 2);
-  p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024) / stage_bytes)));
+  static int epi2_env = -1;
+  if (epi2_env < 0) {
+    const char* e = getenv("BHMC_BG_EPI2");
+    epi2_env = e ? atoi(e) : 1;
+  }
+  const int epi_bytes = EW * 2048;  // per-warp 32 x 16 fp32 blocks of the second epilogue form
+  p.epi2 = (epi2_env && p.vec && (!d.ck_hi || (d.ck_ld % 4 == 0 && d.ck_batch % 4 == 0 && (((uintptr_t)d.ck_hi | (uintptr_t)d.ck_lo) & 7u) == 0)) &&
+            (!d.bias || (d.bias_batch % 4 == 0 && ((uintptr_t)d.bias & 15u) == 0)) && !(d.addsrc && d.gate)) ? 1 : 0;
+  p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024 - (p.epi2 ? epi_bytes : 0)) / stage_bytes)));
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   BHMC_TRY(make_map3(&mA_hi, a_hi, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, (uint64_t)Kp, BM));
   BHMC_TRY(make_map3(&mB_hi, b_hi, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, b_box));
@@ -699,7 +877,7 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
     mA_lo = mA_hi;
     mB_lo = mB_hi;
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (p.epi2 ? epi_bytes : 0);
   static size_t configured = 0, configured2 = 0;
   if (!pair && smem > configured) {
     BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
