@@ -77,21 +77,19 @@ __global__ void __launch_bounds__(256) k_mlp_gemm(GemmDesc d) {
     if (m >= d.M) continue;
     uint32_t ka = 15u, kb = 15u;
     if (d.epi >= 1 && nb < d.N) {
+      if (!d.mask_a || (d.epi == 2 && !d.mask_b)) {
+        const uint32_t k8 = keep_bits8(d, c, m, nb);
+        ka = k8 & 15u, kb = k8 >> 4;
+      }
       if (d.mask_a) {
         ka = 0;
         for (int j = 0; j < 4; ++j)
           if (nb + j < d.N && d.mask_a[(int64_t)c * d.mask_batch + (int64_t)m * d.N + nb + j]) ka |= 1u << j;
-      } else {
-        ka = keep_bits4(d, c, m, nb, d.layer_a);
       }
-      if (d.epi == 2) {
-        if (d.mask_b) {
-          kb = 0;
-          for (int j = 0; j < 4; ++j)
-            if (nb + j < d.N && d.mask_b[(int64_t)c * d.mask_batch + (int64_t)m * d.N + nb + j]) kb |= 1u << j;
-        } else {
-          kb = keep_bits4(d, c, m, nb, d.layer_b);
-        }
+      if (d.epi == 2 && d.mask_b) {
+        kb = 0;
+        for (int j = 0; j < 4; ++j)
+          if (nb + j < d.N && d.mask_b[(int64_t)c * d.mask_batch + (int64_t)m * d.N + nb + j]) kb |= 1u << j;
       }
     }
 #pragma unroll
@@ -402,6 +400,7 @@ struct MlpModel : ModelBase {
       GemmDesc d{};
       d.keep_inv = keep_inv;
       d.keep_prob = keep_prob;
+      d.keep_thr16 = (uint32_t)lrint((double)keep_prob * 65536.0);
       d.seed = seed;
       d.chain_id0 = chain_id0;
       d.eval_id = ev;

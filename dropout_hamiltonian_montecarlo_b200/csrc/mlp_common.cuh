@@ -21,6 +21,7 @@ struct GemmDesc {
   float gate_scale;
   int epi;  // 0: linear; 1: relu(v*mask_a*keep_inv); 2: relu(v*mask_a*keep_inv)*mask_b*keep_inv
   float keep_inv, keep_prob;
+  uint32_t keep_thr16;  // round(keep_prob * 65536): threshold of the 16-bit Bernoulli draws (set by the host)
   const uint8_t* mask_a;  // injected keep-masks [c][m][n] (tests) or nullptr -> Philox
   const uint8_t* mask_b;
   int64_t mask_batch;
@@ -48,12 +49,18 @@ __device__ __forceinline__ void split_store_pair(float v, __nv_bfloat16* hi, __n
   if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-__device__ __forceinline__ uint32_t keep_bits4(const GemmDesc& d, int c, int m, int n, uint32_t layer) {
-  // four Bernoulli(keep_prob) draws for units n..n+3 (n % 4 == 0) of row m; bit e = keep
-  U4 r = philox4x32_10(U4{(uint32_t)(((int64_t)m * d.N + n) >> 2), (uint32_t)(d.chain_id0 + c), d.eval_id,
-                           TAG_DROPOUT | layer},
-                       (uint32_t)d.seed, (uint32_t)(d.seed >> 32));
-  uint32_t thr = (uint32_t)(d.keep_prob * 4294967296.0);
-  return (r.x < thr ? 1u : 0u) | (r.y < thr ? 2u : 0u) | (r.z < thr ? 4u : 0u) | (r.w < thr ? 8u : 0u);
+// Dropout keep bits of units n..n+3 (n % 4 == 0) of row m: ONE Philox4x32-10 call per quad.  Word e of the output serves
+// unit n+e: its low 16 bits decide the first mask of the epilogue (layer_a), its high 16 bits the second one (layer_b, the
+// dropout in front of l3 that the H2 epilogue applies as well) -- P(keep) = keep_thr16 / 65536 (0.9 -> 0.899994).  Returns
+// ka | kb << 4.  (Round 2, first form: one call per mask with 32-bit draws and an fp64 threshold computed per call -- ncu
+// showed the H2 epilogue issue-bound on 8 Philox calls per 16 elements.)  Keyed by position, chain, evaluation and
+// layer_a only: independent of tile geometry, precision path and sharding.
+__device__ __forceinline__ uint32_t keep_bits8(const GemmDesc& d, int c, int m, int n) {
+  const U4 r = philox4x32_10(U4{(uint32_t)(((int64_t)m * d.N + n) >> 2), (uint32_t)(d.chain_id0 + c), d.eval_id,
+                                 TAG_DROPOUT | d.layer_a},
+                             (uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+  const uint32_t t = d.keep_thr16;
+  return ((r.x & 0xFFFFu) < t ? 1u : 0u) | ((r.y & 0xFFFFu) < t ? 2u : 0u) | ((r.z & 0xFFFFu) < t ? 4u : 0u) |
+         ((r.w & 0xFFFFu) < t ? 8u : 0u) | ((r.x >> 16) < t ? 16u : 0u) | ((r.y >> 16) < t ? 32u : 0u) |
+         ((r.z >> 16) < t ? 64u : 0u) | ((r.w >> 16) < t ? 128u : 0u);
 }
-

@@ -114,35 +114,26 @@ __device__ __forceinline__ void bg_epilogue_tile(const BgParams& p, uint32_t tac
       }
       uint32_t ka = 0xFFFFu, kb = 0xFFFFu;  // keep bits of the 16 columns
       if (d.epi >= 1) {
-        ka = 0;
+        ka = 0, kb = 0;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           if (qd >= nq) break;
           const int n = n0 + 4 * qd;
-          uint32_t k4 = 0;
+          uint32_t k8 = 0xF0u;
+          if (!d.mask_a || (d.epi == 2 && !d.mask_b)) k8 = keep_bits8(d, z, m, n);
+          uint32_t a4 = k8 & 15u, b4 = k8 >> 4;
           if (d.mask_a) {
+            a4 = 0;
             for (int j = 0; j < 4; ++j)
-              if (n + j < d.N && d.mask_a[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
-          } else {
-            k4 = keep_bits4(d, z, m, n, d.layer_a);
+              if (n + j < d.N && d.mask_a[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) a4 |= 1u << j;
           }
-          ka |= k4 << (4 * qd);
-        }
-        if (d.epi == 2) {
-          kb = 0;
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            if (qd >= nq) break;
-            const int n = n0 + 4 * qd;
-            uint32_t k4 = 0;
-            if (d.mask_b) {
-              for (int j = 0; j < 4; ++j)
-                if (n + j < d.N && d.mask_b[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) k4 |= 1u << j;
-            } else {
-              k4 = keep_bits4(d, z, m, n, d.layer_b);
-            }
-            kb |= k4 << (4 * qd);
+          if (d.epi == 2 && d.mask_b) {
+            b4 = 0;
+            for (int j = 0; j < 4; ++j)
+              if (n + j < d.N && d.mask_b[(int64_t)z * d.mask_batch + (int64_t)m * d.N + n + j]) b4 |= 1u << j;
           }
+          ka |= a4 << (4 * qd);
+          kb |= b4 << (4 * qd);
         }
       }
 #pragma unroll
@@ -276,19 +267,17 @@ __device__ __forceinline__ void bg_epi2_chunk(const BgParams& p, uint32_t tacc, 
       }
       if (d.epi >= 1) {
         uint32_t ka = 0, kb = 0xFu;
+        if (!d.mask_a || (d.epi == 2 && !d.mask_b)) {
+          const uint32_t k8 = keep_bits8(d, z, m, n);
+          ka = k8 & 15u, kb = k8 >> 4;
+        }
         if (d.mask_a) {
           const uint8_t* mp = d.mask_a + (int64_t)z * d.mask_batch + (int64_t)m * d.N + n;
           ka = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
-        } else {
-          ka = keep_bits4(d, z, m, n, d.layer_a);
         }
-        if (d.epi == 2) {
-          if (d.mask_b) {
-            const uint8_t* mp = d.mask_b + (int64_t)z * d.mask_batch + (int64_t)m * d.N + n;
-            kb = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
-          } else {
-            kb = keep_bits4(d, z, m, n, d.layer_b);
-          }
+        if (d.epi == 2 && d.mask_b) {
+          const uint8_t* mp = d.mask_b + (int64_t)z * d.mask_batch + (int64_t)m * d.N + n;
+          kb = (mp[0] ? 1u : 0u) | (mp[1] ? 2u : 0u) | (mp[2] ? 4u : 0u) | (mp[3] ? 8u : 0u);
         }
         auto act = [&](float x, uint32_t bit) {
           x = (ka & bit) ? x * d.keep_inv : 0.f;
