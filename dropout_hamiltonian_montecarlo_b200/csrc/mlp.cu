@@ -351,6 +351,248 @@ __global__ void __launch_bounds__(1024) k_mlp_colsum(const float* __restrict__ S
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The n_out-wide head of the network in one pass over H2d (round 2).  Until now five launches read the same 16 MB:
+// Z = H2d W3^T + b3 (k_mlp_gemm_small_n), loss / dZ (k_mlp_loss), gW3 = dZ^T H2d (k_mlp_gemm_small_m), gb3
+// (k_mlp_colsum), dA2 = dZ W3 * gate (k_mlp_gemm_small_k), plus the transposed split of dA2 and the column sums of dA2
+// for gb2 -- 68 + 8 + 7 us of a 330 us evaluation (ncu launch list).  A block owns 32 rows of one chain: the rows of H2d
+// and W3 sit in shared memory, logits / softmax / dZ are computed once, and everything that depends on them leaves the
+// block: the loss, dA2 as bf16 hi/lo in BOTH orientations (the operands of the dA1 and gW2 GEMMs; dA2 itself is never
+// needed in fp32), and per-block partial sums of gW3, gb3, gb2 that k_mlp_head_reduce adds in block order (deterministic)
+// together with alpha/2 * theta.  mlp.py:28-31,57-63 (F.softmax_cross_entropy mean over the batch, Linear backward).
+template <int NO>  // classes padded to a multiple of 4, <= 16
+__global__ void __launch_bounds__(256, 2) k_mlp_head(const float* __restrict__ H2d, int64_t act, int B, int n_mid, int n_out,
+                                                  const float* __restrict__ q, int64_t ld, int64_t oW3, int64_t ob3,
+                                                  const int32_t* __restrict__ y, float gate_scale, double* __restrict__ loss,
+                                                  __nv_bfloat16* __restrict__ k_hi, __nv_bfloat16* __restrict__ k_lo, int64_t k_batch,
+                                                  int64_t k_ld, __nv_bfloat16* __restrict__ t_hi, __nv_bfloat16* __restrict__ t_lo,
+                                                  int64_t t_batch, int64_t t_ld, float* __restrict__ part, int n_rb) {
+  extern __shared__ __align__(16) float sm_head[];
+  const int pitch = n_mid + 4;              // floats; + 16 bytes: a column of 32 rows spreads over the banks
+  float* Hs = sm_head;                      // [32][pitch]
+  float* Ws = Hs + 32 * pitch;              // [NO][n_mid], rows >= n_out zero
+  float* dZs = Ws + NO * n_mid;             // [32][NO]
+  __shared__ double red[8];
+  const int c = blockIdx.y, rb = blockIdx.x, m0 = rb * 32;
+  const int rows = min(32, B - m0);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int nq = n_mid >> 2;  // quads per row
+  const float* Hg = H2d + (int64_t)c * act + (int64_t)m0 * n_mid;
+  const float* W3 = q + (int64_t)c * ld + oW3;
+  for (int i = t; i < 32 * nq; i += 256) {
+    const int r = i / nq, k4 = i - r * nq;
+    const float4 v = r < rows ? __ldg(reinterpret_cast<const float4*>(Hg + (int64_t)r * n_mid) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(Hs + r * pitch + 4 * k4) = v;
+  }
+  for (int i = t; i < NO * nq; i += 256) {
+    const int o = i / nq, k4 = i - o * nq;
+    // W3 rows start at oW3 + o*n_mid: 16-byte aligned when oW3 % 4 == 0 (checked by the host)
+    const float4 v = o < n_out ? __ldg(reinterpret_cast<const float4*>(W3 + (int64_t)o * n_mid) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(Ws + o * n_mid + 4 * k4) = v;
+  }
+  __syncthreads();
+  // ---- logits of rows 4*warp .. +3 (lanes split the contraction), softmax, loss, dZ ----
+  {
+    float acc[4][NO];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) acc[r][o] = 0.f;
+    for (int k4 = lane; k4 < nq; k4 += 32) {
+      float4 h[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) h[r] = *reinterpret_cast<const float4*>(Hs + (4 * warp + r) * pitch + 4 * k4);
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const float4 w = *reinterpret_cast<const float4*>(Ws + o * n_mid + 4 * k4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          acc[r][o] = fmaf(h[r].x, w.x, fmaf(h[r].y, w.y, fmaf(h[r].z, w.z, fmaf(h[r].w, w.w, acc[r][o]))));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int o = 0; o < NO; ++o)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[r][o] += __shfl_xor_sync(0xffffffffu, acc[r][o], s);
+    double my = 0.0;
+    if (lane < 4) {  // lane r finishes row 4*warp + r
+      const int r = 4 * warp + lane;
+      float z[NO];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        if (rr == lane) {
+#pragma unroll
+          for (int o = 0; o < NO; ++o) z[o] = acc[rr][o];
+        }
+      if (r < rows) {
+        const float* b3 = q + (int64_t)c * ld + ob3;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int o = 0; o < NO; ++o)
+          if (o < n_out) z[o] += __ldg(b3 + o), mx = fmaxf(mx, z[o]);
+        float ssum = 0.f;
+#pragma unroll
+        for (int o = 0; o < NO; ++o)
+          if (o < n_out) ssum += expf(z[o] - mx);
+        const int yy = y[m0 + r];
+        float zy = 0.f;
+#pragma unroll
+        for (int o = 0; o < NO; ++o)
+          if (o == yy) zy = z[o];
+        my = ((double)mx + (double)logf(ssum) - (double)zy) / (double)B;
+        const float inv = 1.0f / ssum, ib = 1.0f / (float)B;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) dZs[r * NO + o] = o < n_out ? (expf(z[o] - mx) * inv - (o == yy ? 1.f : 0.f)) * ib : 0.f;
+      } else {
+#pragma unroll
+        for (int o = 0; o < NO; ++o) dZs[r * NO + o] = 0.f;
+      }
+    }
+    my += __shfl_xor_sync(0xffffffffu, my, 1);
+    my += __shfl_xor_sync(0xffffffffu, my, 2);
+    if (lane == 0) red[warp] = my;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    atomicAdd(loss + c, quantize_addend<40>(tot));  // mean CE: order-independent, see internal.cuh
+  }
+  float* pW = part + ((int64_t)c * n_rb + rb) * ((int64_t)(NO + 2) * n_mid + NO);  // [NO][n_mid] gW3, [2][n_mid] gb2 (row halves), [NO] gb3
+  if (t < NO) {
+    float sacc = 0.f;
+    for (int r = 0; r < 32; ++r) sacc += dZs[r * NO + t];
+    pW[(int64_t)(NO + 2) * n_mid + t] = sacc;
+  }
+  // ---- dA2 = (dZ W3) * [H2d > 0] * gate_scale, thread = column quad: K-major bf16 copies, column sums (gb2);
+  //      gW3 partial = dZ^T H2d of the block's rows ----
+  const int half = t >> 7;  // rows half, half + 2, ... / classes half*NO/2 .. +NO/2
+  for (int k4 = t & 127; k4 < nq; k4 += 128) {
+    float4 w[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) w[o] = *reinterpret_cast<const float4*>(Ws + o * n_mid + 4 * k4);
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = half; r < rows; r += 2) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const float dz = dZs[r * NO + o];
+        v.x = fmaf(dz, w[o].x, v.x), v.y = fmaf(dz, w[o].y, v.y), v.z = fmaf(dz, w[o].z, v.z), v.w = fmaf(dz, w[o].w, v.w);
+      }
+      const float4 h = *reinterpret_cast<const float4*>(Hs + r * pitch + 4 * k4);
+      v.x = h.x > 0.f ? v.x * gate_scale : 0.f, v.y = h.y > 0.f ? v.y * gate_scale : 0.f;
+      v.z = h.z > 0.f ? v.z * gate_scale : 0.f, v.w = h.w > 0.f ? v.w * gate_scale : 0.f;
+      cs.x += v.x, cs.y += v.y, cs.z += v.z, cs.w += v.w;
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                          h3 = __float2bfloat16_rn(v.w);
+      const int64_t o = (int64_t)c * k_batch + (int64_t)(m0 + r) * k_ld + 4 * k4;
+      __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a), pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(k_hi + o) = pk;
+      if (k_lo) {
+        a = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
+        b = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+        pk.x = *reinterpret_cast<uint32_t*>(&a), pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(k_lo + o) = pk;
+      }
+    }
+    *reinterpret_cast<float4*>(pW + (int64_t)(NO + half) * n_mid + 4 * k4) = cs;  // gb2: one slot per row half
+    float4 gacc[NO / 2];
+#pragma unroll
+    for (int j = 0; j < NO / 2; ++j) gacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rows; ++r) {
+      const float4 h = *reinterpret_cast<const float4*>(Hs + r * pitch + 4 * k4);
+#pragma unroll
+      for (int j = 0; j < NO / 2; ++j) {
+        const float dz = dZs[r * NO + half * (NO / 2) + j];
+        gacc[j].x = fmaf(dz, h.x, gacc[j].x), gacc[j].y = fmaf(dz, h.y, gacc[j].y);
+        gacc[j].z = fmaf(dz, h.z, gacc[j].z), gacc[j].w = fmaf(dz, h.w, gacc[j].w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NO / 2; ++j) *reinterpret_cast<float4*>(pW + (int64_t)(half * (NO / 2) + j) * n_mid + 4 * k4) = gacc[j];
+  }
+  // ---- transposed bf16 copies of dA2 (operand of gW2 = dA2^T H1): lane = row, so the 32 rows of a column are 64
+  //      contiguous bytes; the values are recomputed (NO FMAs each) rather than staged ----
+  if (lane < rows) {
+    float dz[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) dz[o] = dZs[lane * NO + o];
+    for (int k4 = warp; k4 < nq; k4 += 8) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        const float4 w = *reinterpret_cast<const float4*>(Ws + o * n_mid + 4 * k4);
+        v.x = fmaf(dz[o], w.x, v.x), v.y = fmaf(dz[o], w.y, v.y), v.z = fmaf(dz[o], w.z, v.z), v.w = fmaf(dz[o], w.w, v.w);
+      }
+      const float4 h = *reinterpret_cast<const float4*>(Hs + lane * pitch + 4 * k4);
+      const float e[4] = {h.x > 0.f ? v.x * gate_scale : 0.f, h.y > 0.f ? v.y * gate_scale : 0.f, h.z > 0.f ? v.z * gate_scale : 0.f,
+                          h.w > 0.f ? v.w * gate_scale : 0.f};
+      const int64_t o0 = (int64_t)c * t_batch + (int64_t)(4 * k4) * t_ld + m0 + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16 hb = __float2bfloat16_rn(e[j]);
+        t_hi[o0 + (int64_t)j * t_ld] = hb;
+        if (t_lo) t_lo[o0 + (int64_t)j * t_ld] = __float2bfloat16_rn(e[j] - __bfloat162float(hb));
+      }
+    }
+  }
+}
+
+// g[W3] = sum_blocks partial + alpha/2 W3, likewise gb3 and gb2 (block order: deterministic)
+template <int NO>
+__global__ void __launch_bounds__(256) k_mlp_head_reduce(const float* __restrict__ part, int n_rb, int n_mid, int n_out,
+                                                         const float* __restrict__ q, int64_t ld, int64_t oW3, int64_t ob3,
+                                                         int64_t ob2, float half_alpha, float* __restrict__ g) {
+  const int c = blockIdx.y;
+  const int64_t stride = (int64_t)(NO + 2) * n_mid + NO;
+  const float* pc = part + (int64_t)c * n_rb * stride;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int nW = n_out * n_mid;
+  if (i < nW) {
+    float acc = 0.f;
+    for (int b = 0; b < n_rb; ++b) acc += pc[b * stride + i];  // rows o < n_out of the [NO][n_mid] block are contiguous
+    g[(int64_t)c * ld + oW3 + i] = acc + half_alpha * q[(int64_t)c * ld + oW3 + i];
+  } else if (i < nW + n_mid) {
+    const int n = i - nW;
+    float acc = 0.f;
+    for (int b = 0; b < n_rb; ++b) acc += pc[b * stride + (int64_t)NO * n_mid + n] + pc[b * stride + (int64_t)(NO + 1) * n_mid + n];
+    g[(int64_t)c * ld + ob2 + n] = acc + half_alpha * q[(int64_t)c * ld + ob2 + n];
+  } else if (i < nW + n_mid + n_out) {
+    const int o = i - nW - n_mid;
+    float acc = 0.f;
+    for (int b = 0; b < n_rb; ++b) acc += pc[b * stride + (int64_t)(NO + 2) * n_mid + o];
+    g[(int64_t)c * ld + ob3 + o] = acc + half_alpha * q[(int64_t)c * ld + ob3 + o];
+  }
+}
+
+template <int NO>
+static int launch_head(bhmc_ctx* ctx, const float* H2d, int64_t act, int B, int n_mid, int n_out, const float* q, int64_t ld,
+                       int64_t oW3, int64_t ob3, int64_t ob2, const int32_t* y, float gate_scale, float half_alpha, double* loss,
+                       __nv_bfloat16* k_hi, __nv_bfloat16* k_lo, int64_t k_batch, int64_t k_ld, __nv_bfloat16* t_hi,
+                       __nv_bfloat16* t_lo, int64_t t_batch, int64_t t_ld, float* part, int C, float* g) {
+  const int n_rb = (int)ceil_div(B, 32);
+  const size_t smem = sizeof(float) * ((size_t)32 * (n_mid + 4) + (size_t)NO * n_mid + 32 * NO);
+  static size_t configured = 0;
+  if (smem > configured) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_mlp_head<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k_mlp_head<NO><<<dim3((unsigned)n_rb, (unsigned)C), 256, smem, ctx->stream>>>(H2d, act, B, n_mid, n_out, q, ld, oW3, ob3, y, gate_scale,
+                                                                             loss, k_hi, k_lo, k_batch, k_ld, t_hi, t_lo, t_batch,
+                                                                             t_ld, part, n_rb);
+  const int n_items = n_out * n_mid + n_mid + n_out;
+  k_mlp_head_reduce<NO><<<dim3((unsigned)ceil_div(n_items, 256), (unsigned)C), 256, 0, ctx->stream>>>(part, n_rb, n_mid, n_out, q, ld, oW3,
+                                                                                                   ob3, ob2, half_alpha, g);
+  ctx->launches += 2;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
 struct MlpModel : ModelBase {
   int64_t N = 0;
   int n_in = 0, n_mid = 0, n_out = 0;
@@ -424,14 +666,28 @@ struct MlpModel : ModelBase {
     const int64_t e_k = (int64_t)B * kp_mid, e_t = (int64_t)n_mid * kp_b;  // elements per chain of a K-major / transposed copy
     __nv_bfloat16 *H1k = nullptr, *H1t = nullptr, *dA2k = nullptr, *dA2t = nullptr, *dA1t = nullptr;
     const int64_t lo_k = (int64_t)C * e_k, lo_t = (int64_t)C * e_t;  // offset of the lo copy inside a buffer
+    // the n_out-wide head in one pass over H2d (k_mlp_head; BHMC_MLP_HEAD=0: the five separate launches)
+    static int head_env = -1;
+    if (head_env < 0) {
+      const char* e = getenv("BHMC_MLP_HEAD");
+      head_env = e ? atoi(e) : 1;
+    }
+    const int NO = (int)round_up(n_out, 4), n_rb = (int)ceil_div(B, 32);
+    const size_t head_smem = sizeof(float) * ((size_t)32 * (n_mid + 4) + (size_t)NO * n_mid + 32 * NO);
+    const bool head = head_env && fuse && !logits_sink && n_out <= 16 && n_mid % 4 == 0 && oW3 % 4 == 0 && ld % 4 == 0 &&
+                      head_smem <= (size_t)200 * 1024;
+    const size_t part_floats = head ? (size_t)C * n_rb * ((size_t)(NO + 2) * n_mid + NO) : 0;
+    float* head_part = nullptr;
     if (fuse) {
       void* cb = nullptr;
-      BHMC_TRY(ctx->get_scratch(15, sizeof(__nv_bfloat16) * 2 * (size_t)(2 * lo_k + 3 * lo_t), &cb));
+      const size_t bf_bytes = sizeof(__nv_bfloat16) * 2 * (size_t)(2 * lo_k + 3 * lo_t);  // multiple of 256 (kp_* % 64 == 0)
+      BHMC_TRY(ctx->get_scratch(15, bf_bytes + sizeof(float) * part_floats, &cb));
       H1k = (__nv_bfloat16*)cb;
       dA2k = H1k + 2 * lo_k;
       H1t = dA2k + 2 * lo_k;
       dA2t = H1t + 2 * lo_t;
       dA1t = dA2t + 2 * lo_t;
+      head_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(cb) + bf_bytes);
     }
     auto out_k = [&](GemmDesc& gd, __nv_bfloat16* buf) {
       gd.ck_hi = buf, gd.ck_lo = split3 ? buf + lo_k : nullptr, gd.ck_batch = e_k, gd.ck_ld = kp_mid;
@@ -468,27 +724,42 @@ struct MlpModel : ModelBase {
       d.mask_b = masks ? masks + 2 * (size_t)C * mstride : nullptr;
       if (fuse) d.a_hi = H1k, d.a_lo = split3 ? H1k + lo_k : nullptr, d.a_kp = kp_mid;
       BHMC_TRY(run_gemm(ctx, d, C));
-      // Z = H2d W3^T + b3
-      d = base();
-      d.A = H2d, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
-      d.B = q + oW3, d.b_batch = ld, d.b_rs = 1, d.b_cs = n_mid;
-      d.C = Z, d.c_batch = (int64_t)B * n_out, d.c_rs = n_out;
-      d.M = B, d.N = n_out, d.K = n_mid;
-      d.bias = q + ob3, d.bias_batch = ld;
-      BHMC_TRY(run_gemm(ctx, d, C));
-      if (logits_sink) {
-        BHMC_CUDA_OK(cudaMemcpyAsync(logits_sink, Z, sizeof(float) * (size_t)C * B * n_out, cudaMemcpyDeviceToDevice, ctx->stream));
-        return BHMC_OK;
+      if (!(head && g)) {
+        // Z = H2d W3^T + b3
+        d = base();
+        d.A = H2d, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
+        d.B = q + oW3, d.b_batch = ld, d.b_rs = 1, d.b_cs = n_mid;
+        d.C = Z, d.c_batch = (int64_t)B * n_out, d.c_rs = n_out;
+        d.M = B, d.N = n_out, d.K = n_mid;
+        d.bias = q + ob3, d.bias_batch = ld;
+        BHMC_TRY(run_gemm(ctx, d, C));
+        if (logits_sink) {
+          BHMC_CUDA_OK(cudaMemcpyAsync(logits_sink, Z, sizeof(float) * (size_t)C * B * n_out, cudaMemcpyDeviceToDevice, ctx->stream));
+          return BHMC_OK;
+        }
+        dim3 grid((unsigned)ceil_div(B, 256), C);
+        k_mlp_loss<<<grid, 256, 0, ctx->stream>>>(Z, B, n_out, labels + row0, stat, g ? 1 : 0);
+        ctx->launches++;
       }
-      dim3 grid((unsigned)ceil_div(B, 256), C);
-      k_mlp_loss<<<grid, 256, 0, ctx->stream>>>(Z, B, n_out, labels + row0, stat, g ? 1 : 0);
-      ctx->launches++;
     }
     if (!g) return BHMC_OK;
     GroupTimer t(ctx, KG_BWD);
     const float ha = 0.5f * alpha;
-    // gW3 = dZ^T H2d + alpha/2 W3 ; gb3
     GemmDesc d = base();
+    if (head) {
+      // loss, dZ, gW3, gb3, gb2 and dA2 (bf16 hi/lo, both orientations) in one pass over H2d
+      __nv_bfloat16 *klo = split3 ? dA2k + lo_k : nullptr, *tlo = split3 ? dA2t + lo_t : nullptr;
+      const float gs = keep_inv * keep_inv;
+#define BHMC_HEAD(NOV)                                                                                                          \
+  BHMC_TRY(launch_head<NOV>(ctx, H2d, act, B, n_mid, n_out, q, ld, oW3, ob3, ob2, labels + row0, gs, ha, stat, dA2k, klo, e_k, kp_mid, \
+                            dA2t, tlo, e_t, kp_b, head_part, C, g))
+      if (NO == 4) BHMC_HEAD(4);
+      else if (NO == 8) BHMC_HEAD(8);
+      else if (NO == 12) BHMC_HEAD(12);
+      else BHMC_HEAD(16);
+#undef BHMC_HEAD
+    } else {
+    // gW3 = dZ^T H2d + alpha/2 W3 ; gb3
     d.A = Z, d.a_batch = (int64_t)B * n_out, d.a_rs = 1, d.a_cs = n_out;  // (m=o, k=b)
     d.B = H2d, d.b_batch = act, d.b_rs = n_mid, d.b_cs = 1;
     d.C = g + oW3, d.c_batch = ld, d.c_rs = n_mid;
@@ -505,6 +776,7 @@ struct MlpModel : ModelBase {
     d.gate = H2d, d.gate_batch = act, d.gate_rs = n_mid, d.gate_scale = keep_inv * keep_inv;
     if (fuse) out_k(d, dA2k);  // its transposed copy (for gW2) stays a split launch: see k_mlp_gemm_small_k
     BHMC_TRY(run_gemm(ctx, d, C));
+    }
     // gW2 = dA2^T H1 + alpha/2 W2 ; gb2
     d = base();
     d.A = dA2, d.a_batch = act, d.a_rs = 1, d.a_cs = n_mid;
@@ -513,8 +785,9 @@ struct MlpModel : ModelBase {
     d.M = n_mid, d.N = n_mid, d.K = B;
     d.addsrc = q + oW2, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
     if (fuse) d.b_hi = H1t, d.b_lo = split3 ? H1t + lo_t : nullptr, d.b_kp = kp_b;
+    if (head) d.a_hi = dA2t, d.a_lo = split3 ? dA2t + lo_t : nullptr, d.a_kp = kp_b;
     BHMC_TRY(run_gemm(ctx, d, C));
-    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g);
+    if (!head) k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g);
     // dA1 = (dA2 W2) * [H1 > 0] / keep
     d = base();
     d.A = dA2, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
@@ -537,7 +810,7 @@ struct MlpModel : ModelBase {
     if (fuse) d.a_hi = dA1t, d.a_lo = split3 ? dA1t + lo_t : nullptr, d.a_kp = kp_b;
     BHMC_TRY(run_gemm(ctx, d, C));
     k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g);
-    ctx->launches += 3;
+    ctx->launches += head ? 1 : 3;
     // padding columns of g (ld > P) are never read by the update kernels beyond P; keep them finite
     BHMC_CUDA_OK(cudaGetLastError());
     return BHMC_OK;

@@ -194,13 +194,21 @@ for name, (N, n_in, n_mid, n_out, C, row0, B) in {"cfg4": (1200, 784, 512, 10, 5
 np.savez(sys.argv[1], **out)
 ''' % (root,)
     res = []
-    for fuse in ("1", "0"):
+    for fuse, head in (("1", "0"), ("0", "0"), ("1", "1")):
         with tempfile.NamedTemporaryFile(suffix=".npz") as f:
-            r = subprocess.run([sys.executable, "-c", code, f.name], env=dict(os.environ, BHMC_MLP_FUSE=fuse), capture_output=True,
-                               text=True, timeout=600)
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=dict(os.environ, BHMC_MLP_FUSE=fuse, BHMC_MLP_HEAD=head),
+                               capture_output=True, text=True, timeout=600)
             assert r.returncode == 0, r.stderr[-3000:]
             res.append({k: v for k, v in np.load(f.name).items()})
-    a, b = res
+    a, b, h = res
+    # the one-pass head (k_mlp_head, BHMC_MLP_HEAD=1, the default) sums the logits and the gW3 / gb3 / gb2 terms in another
+    # order than the five launches it replaces: equal to fp32 round-off, 7 launches become 2
+    for name in ("cfg4", "odd"):
+        for prec in (1, 2):
+            ga, gh = a["%s_g%d" % (name, prec)].astype(np.float64), h["%s_g%d" % (name, prec)].astype(np.float64)
+            assert np.abs(gh - ga).max() <= 2e-5 * np.abs(ga).max(), (name, prec, np.abs(gh - ga).max() / np.abs(ga).max())
+            np.testing.assert_allclose(h["%s_s%d" % (name, prec)], a["%s_s%d" % (name, prec)], rtol=2e-6)
+            assert int(h["%s_l%d" % (name, prec)]) == int(a["%s_l%d" % (name, prec)]) - 5
     for name in ("cfg4", "odd"):
         for prec in (1, 2):
             # Philox dropout masks are keyed by an evaluation counter, identical in both processes
