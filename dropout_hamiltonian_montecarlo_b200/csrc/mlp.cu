@@ -31,6 +31,8 @@ static constexpr int TM = 64, TN = 64, TK = 16;
 
 // tc_bgemm.cu: the same GEMM + epilogue on the tensor cores (bf16 hi/lo split or single bf16 pass)
 int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3);
+int tc_split_rows(bhmc_ctx* ctx, const float* src, int64_t sb, int64_t rs, int64_t cs, int R, int K, int64_t Kp, int Z,
+                  __nv_bfloat16* hi, __nv_bfloat16* lo);
 
 __global__ void __launch_bounds__(256) k_mlp_gemm(GemmDesc d) {
   __shared__ float As[TK][TM + 4];
@@ -478,9 +480,14 @@ __global__ void __launch_bounds__(256, 2) k_mlp_head(const float* __restrict__ H
     for (int r = half; r < rows; r += 2) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int o = 0; o < NO; ++o) {
-        const float dz = dZs[r * NO + o];
-        v.x = fmaf(dz, w[o].x, v.x), v.y = fmaf(dz, w[o].y, v.y), v.z = fmaf(dz, w[o].z, v.z), v.w = fmaf(dz, w[o].w, v.w);
+      for (int o4 = 0; o4 < NO / 4; ++o4) {
+        const float4 dz4 = *reinterpret_cast<const float4*>(dZs + r * NO + 4 * o4);  // broadcast
+        const float dze[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = 4 * o4 + j;
+          v.x = fmaf(dze[j], w[o].x, v.x), v.y = fmaf(dze[j], w[o].y, v.y), v.z = fmaf(dze[j], w[o].z, v.z), v.w = fmaf(dze[j], w[o].w, v.w);
+        }
       }
       const float4 h = *reinterpret_cast<const float4*>(Hs + r * pitch + 4 * k4);
       v.x = h.x > 0.f ? v.x * gate_scale : 0.f, v.y = h.y > 0.f ? v.y * gate_scale : 0.f;
@@ -607,10 +614,19 @@ struct MlpModel : ModelBase {
   uint32_t eval_id = 0;
   int64_t oW1, ob1, oW2, ob2, oW3, ob3;
   float* logits_sink = nullptr;  // predict: grad() stops after the forward pass and leaves the logits here
+  // bf16 hi/lo operand copies of the current row window of X (K-major for X W1^T, transposed for dA1^T X): they do not
+  // depend on q, and a sampler evaluates the same minibatch window many times in a row (every leapfrog iteration of an
+  // sghmc.step) -- split once per window instead of once per evaluation (round 2; BHMC_MLP_XCACHE=0: per evaluation)
+  __nv_bfloat16* xw = nullptr;
+  size_t xw_bytes = 0;
+  const float* xw_src = nullptr;
+  int64_t xw_row0 = -1, xw_rows = -1;
+  int xw_split3 = -1;
 
   ~MlpModel() override {
     cudaFree(X_owned);
     cudaFree(y_owned);
+    cudaFree(xw);
   }
   int64_t default_rows() const override { return N; }
 
@@ -689,6 +705,28 @@ struct MlpModel : ModelBase {
       dA1t = dA2t + 2 * lo_t;
       head_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(cb) + bf_bytes);
     }
+    const int64_t kp_in = round_up(n_in, 64);
+    const int64_t e_xk = (int64_t)B * kp_in, e_xt = (int64_t)n_in * kp_b;  // elements of the K-major / transposed copy of the window
+    static int xcache_env = -1;
+    if (xcache_env < 0) {
+      const char* e = getenv("BHMC_MLP_XCACHE");
+      xcache_env = e ? atoi(e) : 1;
+    }
+    const bool xcache = xcache_env && fuse;
+    if (xcache) {
+      const size_t need = sizeof(__nv_bfloat16) * 2 * (size_t)(e_xk + e_xt);
+      if (need > xw_bytes) {
+        cudaFree(xw);
+        xw = nullptr, xw_bytes = 0, xw_row0 = -1;
+        BHMC_CUDA_OK(cudaMalloc(&xw, need));
+        xw_bytes = need;
+      }
+      if (xw_src != X || xw_row0 != row0 || xw_rows != nrows || xw_split3 != (int)split3) {
+        BHMC_TRY(tc_split_rows(ctx, Xb, 0, n_in, 1, B, n_in, kp_in, 1, xw, split3 ? xw + e_xk : nullptr));
+        BHMC_TRY(tc_split_rows(ctx, Xb, 0, 1, n_in, n_in, B, kp_b, 1, xw + 2 * e_xk, split3 ? xw + 2 * e_xk + e_xt : nullptr));
+        xw_src = X, xw_row0 = row0, xw_rows = nrows, xw_split3 = (int)split3;
+      }
+    }
     auto out_k = [&](GemmDesc& gd, __nv_bfloat16* buf) {
       gd.ck_hi = buf, gd.ck_lo = split3 ? buf + lo_k : nullptr, gd.ck_batch = e_k, gd.ck_ld = kp_mid;
     };
@@ -711,6 +749,7 @@ struct MlpModel : ModelBase {
       d.bias = q + ob1, d.bias_batch = ld;
       d.epi = 1, d.layer_a = 0, d.mask_a = masks ? masks : nullptr;
       if (fuse) out_k(d, H1k), out_t(d, H1t);
+      if (xcache) d.a_hi = xw, d.a_lo = split3 ? xw + e_xk : nullptr, d.a_kp = kp_in;
       BHMC_TRY(run_gemm(ctx, d, C));
       // H2d = dropout(relu(dropout(H1 W2^T + b2)))
       d = base();
@@ -808,6 +847,7 @@ struct MlpModel : ModelBase {
     d.M = n_mid, d.N = n_in, d.K = B;
     d.addsrc = q + oW1, d.add_batch = ld, d.add_rs = n_in, d.add_scale = ha;
     if (fuse) d.a_hi = dA1t, d.a_lo = split3 ? dA1t + lo_t : nullptr, d.a_kp = kp_b;
+    if (xcache) d.b_hi = xw + 2 * e_xk, d.b_lo = split3 ? xw + 2 * e_xk + e_xt : nullptr, d.b_kp = kp_b;
     BHMC_TRY(run_gemm(ctx, d, C));
     k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g);
     ctx->launches += head ? 1 : 3;
@@ -847,6 +887,7 @@ ModelBase* mlp_model_new(bhmc_ctx* ctx, int64_t n_rows, int n_in, int n_mid, int
 int mlp_model_bind(ModelBase* mb, const float* X, const int32_t* labels, int is_host) {
   auto* m = dynamic_cast<MlpModel*>(mb);
   BHMC_CHECK_ARG(m && X && labels, "not an mlp model / NULL data");
+  m->xw_row0 = -1;  // operand copies of the previous window are stale
   if (is_host) {
     size_t xb = sizeof(float) * (size_t)m->N * m->n_in, yb = sizeof(int32_t) * (size_t)m->N;
     if (!m->X_owned) BHMC_CUDA_OK(cudaMalloc(&m->X_owned, xb));

@@ -741,6 +741,17 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, u
   return BHMC_OK;
 }
 
+// K-major bf16 hi/lo copy of a strided fp32 matrix: dst[z][r][k] = split(src[z*sb + r*rs + k*cs]), k < K (rows of Kp elements)
+int tc_split_rows(bhmc_ctx* ctx, const float* src, int64_t sb, int64_t rs, int64_t cs, int R, int K, int64_t Kp, int Z,
+                  __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  GroupTimer t(ctx, KG_PREP);
+  dim3 g((unsigned)(Kp / 64), (unsigned)ceil_div(R, 32), (unsigned)Z);
+  k_split_operand<32><<<g, 256, 0, ctx->stream>>>(src, sb, rs, cs, R, K, Kp, hi, lo);
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
 // C[z] = epilogue(A[z] . B[z]) for z < batch, operands described by d (fp32, arbitrary strides).
 // scratch slots 1..2 of the context hold the bf16 operand copies.
 int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
@@ -788,7 +799,9 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
     }
     const int m_tiles = (int)ceil_div(d.M, BM);
     if (bn_env > 0 && bn_env % 16 == 0 && bn_env <= 256 && d.N >= bn_env) p.BN = bn_env;
-    if (bn_env == -1 && d.N >= 128) {
+    // default: 128 when it divides N; otherwise the model picks (cfg4: N = 784 of the W1 gradient -> 35.0 -> 32.4 us,
+    // while it loses 2-3 us on each of the N = 512 GEMMs)
+    if ((bn_env == -1 || (bn_env == 0 && d.N % 128 != 0)) && d.N >= 128) {
       double best = 1e30;
       for (int bn = 128; bn <= 256; bn += 16) {
         const int stg = (int)((225 * 1024) / ((split3 ? 2 : 1) * (BM * BK * 2 + bn * BK * 2)));

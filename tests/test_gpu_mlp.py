@@ -214,7 +214,8 @@ np.savez(sys.argv[1], **out)
             # Philox dropout masks are keyed by an evaluation counter, identical in both processes
             np.testing.assert_array_equal(a["%s_g%d" % (name, prec)], b["%s_g%d" % (name, prec)])
             np.testing.assert_array_equal(a["%s_s%d" % (name, prec)], b["%s_s%d" % (name, prec)])
-            assert int(a["%s_l%d" % (name, prec)]) == int(b["%s_l%d" % (name, prec)]) - 4, (name, prec, a["%s_l%d" % (name, prec)], b["%s_l%d" % (name, prec)])
+            # 4 split launches replaced by the producing epilogues, 2 more by the cached copies of the X window
+            assert int(a["%s_l%d" % (name, prec)]) == int(b["%s_l%d" % (name, prec)]) - 6, (name, prec, a["%s_l%d" % (name, prec)], b["%s_l%d" % (name, prec)])
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
