@@ -562,7 +562,7 @@ def bench_cfg4(ctx, X, y, rank, world, dev, prec, peak_tf, steps=20, C=16):
            "value": n / (ms * 1e-3), "unit": "grad-evals/s", "ms_per_step": ms / steps, "steps": steps,
            "step": "one sghmc.step of every chain on one minibatch", "gpu_launches_per_step": launches / steps,
            "algorithmic_flops_per_chain_eval": flops, "algorithmic_tflops": n * flops / (ms * 1e-3) / 1e12 / world,
-           "roofline": roof, "parity": "unpinned (no runnable Chainer reference): NumPy restatement cross-checked against torch.autograd"}
+           "roofline": roof, "parity": "pinned under a shim: the unmodified reference models/gpu/mlp.py runs under oracle/chainer_shim.py (Chainer's documented primitive semantics, torch.autograd); real Chainer / CuPy are not installable here"}
     s.close()
     h.close()
     return out

@@ -15,9 +15,12 @@ oracle is pinned against outputs of the *unmodified reference itself*:
     identical consumption order) wherever ``/root/reference`` exists, and
   * ``oracle/make_golden.py`` stored reference outputs under ``tests/golden/*.npz`` which
     ``tests/test_oracle_golden.py`` replays everywhere (including the GPU box).
-The MLP (``hamiltonian/models/gpu/mlp.py``) needs Chainer+CuPy and cannot run here: its
-restatement is cross-checked against ``torch.autograd`` instead and is marked
-"parity unpinned" (see DESIGN.md).
+The MLP (``hamiltonian/models/gpu/mlp.py``) needs Chainer+CuPy, which cannot be installed here.  Its restatement is
+pinned to the UNMODIFIED reference file executed under ``oracle/chainer_shim.py`` (stand-ins for chainer / cupy that
+implement Chainer's documented primitive semantics with torch.autograd): live in ``tests/test_oracle_vs_reference.py``
+and through the fixture ``tests/golden/mlp_model.npz``.  That pins everything the reference file itself decides (layer
+order, dropout placement, loss reduction, prior terms, parameter names); the primitives are the shim's, not Chainer's
+own code -- "pinned under a shim", stated as such in DESIGN.md.
 
 Random draws are never generated in here: every stochastic function takes a ``Draws``
 object that hands out standard normals / uniforms in exactly the order the reference
@@ -277,7 +280,7 @@ class MvnGaussianOracle:
 
 
 # --------------------------------------------------------------------------------------
-# dropout MLP -- hamiltonian/models/gpu/mlp.py (Chainer; restated, parity unpinned)
+# dropout MLP -- hamiltonian/models/gpu/mlp.py (Chainer; restated, pinned to the reference file under oracle/chainer_shim.py)
 # --------------------------------------------------------------------------------------
 MLP_KEYS = ("/l1/W", "/l1/b", "/l2/W", "/l2/b", "/l3/W", "/l3/b")
 MLP_DROPOUT = 0.1  # mlp.py:29-31 ratio=.1

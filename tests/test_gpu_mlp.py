@@ -1,5 +1,6 @@
 """GPU: dropout-MLP model (hamiltonian/models/gpu/mlp.py) against the NumPy restatement in the oracle
-(cross-checked against torch.autograd on CPU; Chainer itself is not installable here -> parity unpinned)."""
+(pinned to the unmodified reference file executed under oracle/chainer_shim.py -- Chainer itself is not installable here --
+and cross-checked against torch.autograd on CPU; golden fixture tests/golden/mlp_model.npz)."""
 import numpy as np
 import pytest
 import torch
