@@ -1433,7 +1433,13 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
           u.stream_lo = step;
           u.stream_hi = TAG_NOISE | (uint32_t)((pit * nsw + pv) & 0xffffff);
         }
+        // joint sweep: the launch rewrites every parameter of the rows that move -> it can fill the model's operand mirror
+        u.mir_hi = nullptr, u.mir_lo = nullptr, u.mir_ld = 0;
+        const bool whole = nsw == 1 && cfg.sweep_off[0] == 0 && cfg.sweep_len[0] >= P && !s->row_comm && !s->hook;
+        const bool mirrored = whole && mb->operand_mirror(C, ld, cfg.precision, &u.mir_hi, &u.mir_lo, &u.mir_ld);
         BHMC_TRY(launch_hmc_update(ctx, u));
+        if (mirrored) mb->mirror_written(s->q_new);
+        u.mir_hi = nullptr, u.mir_lo = nullptr;
         const bool last = it == iters - 1 && v == nsw - 1;
         const int vn = v == nsw - 1 ? 0 : v + 1;
         uint32_t hint = (kept && cheap[v]) ? GRAD_HINT_CHEAP_MOVE : 0u;

@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libbhmc.so.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <stdint.h>
@@ -147,6 +148,12 @@ struct ModelBase {
   virtual void energy_coeffs(int64_t nrows, double* a, double* b, double* cv) const = 0;
   virtual int64_t default_rows() const { return 0; }
   virtual int64_t n_features() const { return 0; }
+  // Operand mirror (round 2).  A model that reads bf16 hi/lo copies of its parameters may hand the sampler a [C, *mld]
+  // image to be filled by an update launch that rewrites EVERY parameter of the rows it moves (joint sweep); the sampler
+  // then reports the buffer it wrote with mirror_written(q), and the model may use the image for the next grad(q, ...)
+  // only -- any other call sequence makes it split the parameters itself, as before.
+  virtual bool operand_mirror(int, int64_t, int, __nv_bfloat16**, __nv_bfloat16**, int64_t*) { return false; }
+  virtual void mirror_written(const float*) {}
   // gradient at fs.q followed by the sampler's parameter update in the same launch sequence (no g materialised);
   // BHMC_ERR_UNSUPPORTED = caller falls back to grad() + the separate update kernel
   virtual int grad_fused_step(int, int64_t, int64_t, int64_t, int, double*, const FusedStep&) { return BHMC_ERR_UNSUPPORTED; }
@@ -194,6 +201,11 @@ struct UpdateArgs {
   const double* stat;  // [C]
   double* stat_new;    // [C] written where the chain was active for it_post
   const int32_t* perm; // row -> chain for the noise stream (nullptr = identity)
+  // bf16 hi/lo image of the moved positions, element for element ([C, mir_ld]; ModelBase::operand_mirror): a model whose
+  // gradient GEMMs read bf16 copies of the parameters gets them from the kernel that wrote the parameters
+  __nv_bfloat16* mir_hi;
+  __nv_bfloat16* mir_lo;
+  int64_t mir_ld;
 };
 int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a);
 

@@ -617,6 +617,12 @@ struct MlpModel : ModelBase {
   // bf16 hi/lo operand copies of the current row window of X (K-major for X W1^T, transposed for dA1^T X): they do not
   // depend on q, and a sampler evaluates the same minibatch window many times in a row (every leapfrog iteration of an
   // sghmc.step) -- split once per window instead of once per evaluation (round 2; BHMC_MLP_XCACHE=0: per evaluation)
+  // operand mirror: bf16 hi/lo image of the positions [C, mir_ld], filled by the sampler's update kernel (ModelBase::
+  // operand_mirror); W1 and W2 are read from it as strided K-major views when it describes the q being evaluated
+  __nv_bfloat16 *mir_hi = nullptr, *mir_lo = nullptr;
+  int64_t mir_ld = 0;
+  int mir_C = 0;
+  const float* mir_fresh = nullptr;  // the buffer whose image the mirror holds, valid for the next grad() only
   __nv_bfloat16* xw = nullptr;
   size_t xw_bytes = 0;
   const float* xw_src = nullptr;
@@ -627,8 +633,34 @@ struct MlpModel : ModelBase {
     cudaFree(X_owned);
     cudaFree(y_owned);
     cudaFree(xw);
+    cudaFree(mir_hi);
   }
   int64_t default_rows() const override { return N; }
+
+  bool operand_mirror(int C, int64_t ld, int prec, __nv_bfloat16** hi, __nv_bfloat16** lo, int64_t* mld) override {
+    static int env = -1;  // BHMC_MLP_MIRROR=0: the weights are split by launches of their own in every evaluation
+    if (env < 0) {
+      const char* e = getenv("BHMC_MLP_MIRROR");
+      env = e ? atoi(e) : 1;
+    }
+    // strided TMA views need 16-byte aligned rows: every weight matrix starts at a multiple of 8 elements and has rows of
+    // a multiple of 8 elements
+    if (!env || prec == BHMC_PREC_FP32 || n_in % 8 || n_mid % 8 || oW1 % 8 || oW2 % 8 || n_in < 64 || n_mid < 64) return false;
+    const int64_t want_ld = round_up(ld, 8);
+    if (C > mir_C || want_ld != mir_ld) {
+      cudaFree(mir_hi);
+      mir_hi = mir_lo = nullptr, mir_C = 0, mir_fresh = nullptr;
+      if (cudaMalloc(&mir_hi, sizeof(__nv_bfloat16) * 2 * (size_t)C * want_ld) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      mir_lo = mir_hi + (size_t)C * want_ld;
+      mir_C = C, mir_ld = want_ld;
+    }
+    *hi = mir_hi, *lo = mir_lo, *mld = mir_ld;
+    return true;
+  }
+  void mirror_written(const float* q) override { mir_fresh = q; }
 
   // NLP = loss + log_prior, log_prior = -alpha/2 sum_v |theta_v|^2/dim_v  (mlp.py:40-45,80-82)
   void energy_coeffs(int64_t, double* a, double* b, double* cv) const override {
@@ -737,6 +769,9 @@ struct MlpModel : ModelBase {
       if (use_tc && gd.M >= 64 && gd.N >= 64 && gd.K >= 64) return tc_bgemm(cx, gd, batch, split3);
       return bhmc::run_gemm(cx, gd, batch);
     };
+    // the image is valid for exactly the evaluation that follows the update launch that wrote it
+    const bool mirror = mir_fresh == q && mir_hi && C <= mir_C && use_tc && fuse;
+    mir_fresh = nullptr;
     BHMC_CUDA_OK(cudaMemsetAsync(stat, 0, sizeof(double) * C, ctx->stream));
     {
       GroupTimer t(ctx, KG_FWD);
@@ -750,6 +785,7 @@ struct MlpModel : ModelBase {
       d.epi = 1, d.layer_a = 0, d.mask_a = masks ? masks : nullptr;
       if (fuse) out_k(d, H1k), out_t(d, H1t);
       if (xcache) d.a_hi = xw, d.a_lo = split3 ? xw + e_xk : nullptr, d.a_kp = kp_in;
+      if (mirror) d.b_hi = mir_hi + oW1, d.b_lo = split3 ? mir_lo + oW1 : nullptr, d.b_kp = n_in, d.b_zs = mir_ld;
       BHMC_TRY(run_gemm(ctx, d, C));
       // H2d = dropout(relu(dropout(H1 W2^T + b2)))
       d = base();
@@ -762,6 +798,7 @@ struct MlpModel : ModelBase {
       d.mask_a = masks ? masks + (size_t)C * mstride : nullptr;
       d.mask_b = masks ? masks + 2 * (size_t)C * mstride : nullptr;
       if (fuse) d.a_hi = H1k, d.a_lo = split3 ? H1k + lo_k : nullptr, d.a_kp = kp_mid;
+      if (mirror) d.b_hi = mir_hi + oW2, d.b_lo = split3 ? mir_lo + oW2 : nullptr, d.b_kp = n_mid, d.b_zs = mir_ld;
       BHMC_TRY(run_gemm(ctx, d, C));
       if (!(head && g)) {
         // Z = H2d W3^T + b3

@@ -41,6 +41,7 @@ struct GemmDesc {
   // contiguous; tc_bgemm then skips its split of that operand
   const __nv_bfloat16 *a_hi, *a_lo, *b_hi, *b_lo;
   int64_t a_kp, b_kp;
+  int64_t a_zs, b_zs;  // 0: densely packed [c][rows][kp]; else elements between two chains of a strided view
 };
 
 __device__ __forceinline__ void split_store_pair(float v, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t o) {

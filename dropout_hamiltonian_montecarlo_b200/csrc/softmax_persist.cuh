@@ -43,6 +43,8 @@ struct PersistParams {
   int dm_rows;                    // rows per (P-Y)^T slab = n_tiles * BN
   int xt_rows;                    // rows per X^T slab (Dt_pad)
   unsigned int* bar;              // grid barrier counter (zeroed before the launch)
+  int pair;                       // clusters of two CTAs work on the same row / feature tile and adjacent chain tiles: each
+                                  // fetches half of the shared X (X^T) tile and multicasts it to both (BHMC_PERSIST_PAIR)
   int prefetch;                   // L2 prefetch of the next phase's X window (BHMC_PERSIST_PF, default on)
   long long* prof;                // optional [grid][8] cycle counters of one epilogue thread (BHMC_PROF=1): per step
                                   // phase F work, wait at barrier 1, phase B work, wait at barrier 2 (sums over the steps)
@@ -172,7 +174,7 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), p.pair ? 2 : 1);  // pair: the peer's producer writes into this slot as well
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1);
@@ -188,9 +190,11 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();  // peer barriers must be initialised before anything is multicast into them
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const int rank = p.pair ? (int)cluster_ctarank() : 0;
 
   // ring / accumulator bookkeeping of each role (lives across phases and steps)
   int stage = 0;
@@ -207,8 +211,14 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
       const uint32_t full = smem_u32(&bar_full[stage]);
       mbar_expect_tx(full, (uint32_t)stage_bytes);
       const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + na * a_bytes;
-      tma_load_2d(sa, a_hi, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
-      if (na == 2) tma_load_2d(sa + a_bytes, a_lo, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
+      if (p.pair) {  // the A tile is the same for both CTAs of the cluster: fetch 64 of its 128 rows for both
+        const uint32_t off = (uint32_t)rank * (BM / 2) * (BK * 2);
+        tma_load_2d_mc(sa + off, a_hi, full, a_k0 + k * a_dk, a_m0 + k * a_dm + rank * (BM / 2), 3);
+        if (na == 2) tma_load_2d_mc(sa + a_bytes + off, a_lo, full, a_k0 + k * a_dk, a_m0 + k * a_dm + rank * (BM / 2), 3);
+      } else {
+        tma_load_2d(sa, a_hi, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
+        if (na == 2) tma_load_2d(sa + a_bytes, a_lo, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
+      }
       tma_load_2d(sb, b_hi, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
       if (p.split3) tma_load_2d(sb + b_bytes, b_lo, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
       if (++stage == p.stages) stage = 0, phase ^= 1u;
@@ -252,7 +262,8 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
           umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
         }
       }
-      umma_commit(smem_u32(&bar_empty[stage]));
+      if (p.pair) umma_commit_mc(smem_u32(&bar_empty[stage]), 3);  // frees the slot in both CTAs
+      else umma_commit(smem_u32(&bar_empty[stage]));
       if (++stage == p.stages) stage = 0, phase ^= 1u;
     }
     umma_commit(smem_u32(&bar_tfull[buf]));
@@ -288,10 +299,11 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
           for (int w = blockIdx.x; w < items_b; w += gridDim.x)
             if (w % p.n_tiles == 0) {  // X^T window of this step's backward phase
               const int slab0 = (int)((row0 - shift) / BK), mt = w / p.n_tiles;
-              for (int k = 0; k < k_chunks_b; ++k) {
-                tma_prefetch_2d(&tmXt_hi, 0, (slab0 + k) * p.xt_rows + mt * BM);
-                if (na == 2) tma_prefetch_2d(&tmXt_lo, 0, (slab0 + k) * p.xt_rows + mt * BM);
-              }
+              for (int k = 0; k < k_chunks_b; ++k)
+                for (int h = 0; h <= p.pair; ++h) {  // pair mode: the boxes are 64 rows high
+                  tma_prefetch_2d(&tmXt_hi, 0, (slab0 + k) * p.xt_rows + mt * BM + h * (BM / 2));
+                  if (na == 2) tma_prefetch_2d(&tmXt_lo, 0, (slab0 + k) * p.xt_rows + mt * BM + h * (BM / 2));
+                }
             }
         for (int w = blockIdx.x; w < items_f; w += gridDim.x) {
           const int mt = w / p.n_tiles, nt = w % p.n_tiles;
@@ -326,10 +338,11 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
           for (int w = blockIdx.x; w < items_f; w += gridDim.x)
             if (w % p.n_tiles == 0) {  // X window of the next step's forward phase
               const int mt = w / p.n_tiles;
-              for (int k = 0; k < p.k_chunks_f; ++k) {
-                tma_prefetch_2d(&tmXa_hi, k * BK, (int)(row0 + p.batch) + mt * BM);
-                if (na == 2) tma_prefetch_2d(&tmXa_lo, k * BK, (int)(row0 + p.batch) + mt * BM);
-              }
+              for (int k = 0; k < p.k_chunks_f; ++k)
+                for (int h = 0; h <= p.pair; ++h) {
+                  tma_prefetch_2d(&tmXa_hi, k * BK, (int)(row0 + p.batch) + mt * BM + h * (BM / 2));
+                  if (na == 2) tma_prefetch_2d(&tmXa_lo, k * BK, (int)(row0 + p.batch) + mt * BM + h * (BM / 2));
+                }
             }
         for (int w = blockIdx.x; w < items_b; w += gridDim.x) {
           const int mt = w / p.n_tiles, nt = w % p.n_tiles;
@@ -363,6 +376,7 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();  // the peer's last commits still arrive on this CTA's barriers
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -381,11 +395,19 @@ static int launch_sg_persistent(bhmc_ctx* ctx, const CUtensorMap* maps, const Pe
   cfg.blockDim = dim3(NON_EPI_THREADS + 32 * 16);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;  // every CTA resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
+  int na = 1;
+  if (p.pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_sg_persistent<KP, 16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
                                   maps[7], p));
   ctx->launches++;
@@ -433,15 +455,29 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   }
   CUtensorMap maps[8];
   const uint64_t xt_rows_total = (uint64_t)(d.Npad / d.slab) * d.Dt_pad;
-  BHMC_TRY(make_map(&maps[0], d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  // CTA pairs (round 2): the phases are bound by what one SM can ingest per chunk (32 KB of X or X^T hi/lo + 20 KB of the
+  // chain-side operand for 12 MMAs of N = 80); two CTAs on adjacent chain tiles need the SAME X tile, so each fetches half
+  // of it and multicasts -- 36 KB requested per CTA and chunk instead of 52.  Needs an even number of chain tiles and CTAs.
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("BHMC_PERSIST_PAIR");
+    pair_env = e ? atoi(e) : 0;  // measured (cfg3, BHMC_PROF=1): phase F 22.1 k -> 23.0 k cycles, phase B 23.6 k -> 25.1 k, 4.15 -> 3.90 M
+                                 // grad-evals/s: the chunk time is not set by what a CTA REQUESTS (36 KB instead of 52 KB) but
+                                 // by what lands in its shared memory -- off by default, kept for A/B
+  }
+  const int items_all = std::max((int)(Mfwd / BM) * n_tiles, (int)ceil_div(d.Dt, BM) * n_tiles);
+  const int grid_all = std::min(items_all, ctx->sm_count);
+  const bool pair = pair_env && n_tiles % 2 == 0 && grid_all % 2 == 0 && grid_all >= 2;
+  const uint32_t abox = pair ? BM / 2 : BM;
+  BHMC_TRY(make_map(&maps[0], d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox));
   maps[1] = maps[0];
-  if (smode == 1) BHMC_TRY(make_map(&maps[1], d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, BM));
+  if (smode == 1) BHMC_TRY(make_map(&maps[1], d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox));
   BHMC_TRY(make_map(&maps[2], wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
   maps[3] = maps[2];
   if (split3) BHMC_TRY(make_map(&maps[3], wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
-  BHMC_TRY(make_map(&maps[4], d.Xt_hi, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, BM));
+  BHMC_TRY(make_map(&maps[4], d.Xt_hi, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, abox));
   maps[5] = maps[4];
-  if (smode == 1) BHMC_TRY(make_map(&maps[5], d.Xt_lo, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, BM));
+  if (smode == 1) BHMC_TRY(make_map(&maps[5], d.Xt_lo, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, abox));
   __nv_bfloat16* dmt_hi = (__nv_bfloat16*)dmt;
   __nv_bfloat16* dmt_lo = split3 ? (__nv_bfloat16*)((char*)dmt + dmt_bytes) : nullptr;
   BHMC_TRY(make_map(&maps[6], dmt_hi, (uint64_t)BK, (uint64_t)(dm_nslab * dm_rows), (uint64_t)BK, (uint32_t)BN));
@@ -464,6 +500,7 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   p.wt_hi = wt_hi, p.wt_lo = split3 ? wt_lo : nullptr, p.dmt_hi = dmt_hi, p.dmt_lo = dmt_lo;
   p.dm_rows = (int)dm_rows, p.xt_rows = (int)d.Dt_pad;
   p.bar = (unsigned int*)bar;
+  p.pair = pair ? 1 : 0;
   const int items = std::max((int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles);
   const int grid = std::min(items, ctx->sm_count);
   static int want_prof = -1, want_pf = -1;

@@ -695,12 +695,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 // bf16 [Z][R][Kp] (K contiguous), box [1][box_rows][64], 128B swizzle, OOB rows / k read as zero
-static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, uint64_t Z, uint64_t Kp, uint32_t box_rows) {
+static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, uint64_t Z, uint64_t Kp, uint32_t box_rows,
+                     uint64_t zs = 0) {  // zs: elements between two batch entries (0 = R * Kp, densely packed)
+  if (zs == 0) zs = R * Kp;
   // an encoded map is a pure function of these arguments and the scratch operands keep their addresses: the 20 driver
   // calls per MLP evaluation are served from a small cache (BHMC_MAP_CACHE=0 disables)
   struct Entry {
     const void* base;
-    uint64_t K, R, Z, Kp;
+    uint64_t K, R, Z, Kp, zs;
     uint32_t box;
     CUtensorMap m;
   };
@@ -712,7 +714,7 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, u
   }
   if (cache_env) {
     for (const Entry& e : cache)
-      if (e.base == base && e.K == K && e.R == R && e.Z == Z && e.Kp == Kp && e.box == box_rows) {
+      if (e.base == base && e.K == K && e.R == R && e.Z == Z && e.Kp == Kp && e.zs == zs && e.box == box_rows) {
         *m = e.m;
         return BHMC_OK;
       }
@@ -723,7 +725,7 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, u
     return BHMC_ERR_CUDA;
   }
   cuuint64_t dims[3] = {K, R, Z};
-  cuuint64_t strides[2] = {Kp * 2, R * Kp * 2};
+  cuuint64_t strides[2] = {Kp * 2, zs * 2};
   cuuint32_t box[3] = {(cuuint32_t)BK, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -736,7 +738,7 @@ static int make_map3(CUtensorMap* m, const void* base, uint64_t K, uint64_t R, u
   }
   if (cache_env) {
     if (cache.size() >= 64) cache.clear();
-    cache.push_back(Entry{base, K, R, Z, Kp, box_rows, *m});
+    cache.push_back(Entry{base, K, R, Z, Kp, zs, box_rows, *m});
   }
   return BHMC_OK;
 }
@@ -760,7 +762,10 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   const int za = a_shared ? 1 : batch, zb = b_shared ? 1 : batch;
   const size_t a_elems = (size_t)za * d.M * Kp, b_elems = (size_t)zb * d.N * Kp;
   // operands already split by their producer (GemmDesc::a_hi / b_hi) skip the split launch
-  const bool a_pre = d.a_hi != nullptr && d.a_kp == Kp && (!split3 || d.a_lo), b_pre = d.b_hi != nullptr && d.b_kp == Kp && (!split3 || d.b_lo);
+  // (x_zs != 0: the copy is a strided view -- row pitch x_kp >= K, x_zs elements between chains -- e.g. the operand mirror
+  // that the sampler's update kernel fills; K beyond the row is zero-filled by TMA, both strides are multiples of 16 bytes)
+  const bool a_pre = d.a_hi != nullptr && (d.a_kp == Kp || (d.a_zs && d.a_kp >= d.K && d.a_kp % 8 == 0 && d.a_zs % 8 == 0)) && (!split3 || d.a_lo);
+  const bool b_pre = d.b_hi != nullptr && (d.b_kp == Kp || (d.b_zs && d.b_kp >= d.K && d.b_kp % 8 == 0 && d.b_zs % 8 == 0)) && (!split3 || d.b_lo);
   void *sa = nullptr, *sb = nullptr;
   if (!a_pre) BHMC_TRY(ctx->get_scratch(1, a_elems * 2 * 2, &sa));
   if (!b_pre) BHMC_TRY(ctx->get_scratch(2, b_elems * 2 * 2, &sb));
@@ -870,11 +875,13 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
             (!d.bias || (d.bias_batch % 4 == 0 && ((uintptr_t)d.bias & 15u) == 0)) && !(d.addsrc && d.gate)) ? 1 : 0;
   p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024 - (p.epi2 ? epi_bytes : 0)) / stage_bytes)));
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
-  BHMC_TRY(make_map3(&mA_hi, a_hi, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, (uint64_t)Kp, BM));
-  BHMC_TRY(make_map3(&mB_hi, b_hi, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, b_box));
+  const uint64_t a_pitch = a_pre ? (uint64_t)d.a_kp : (uint64_t)Kp, b_pitch = b_pre ? (uint64_t)d.b_kp : (uint64_t)Kp;
+  const uint64_t a_zs = a_pre ? (uint64_t)d.a_zs : 0, b_zs = b_pre ? (uint64_t)d.b_zs : 0;
+  BHMC_TRY(make_map3(&mA_hi, a_hi, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, a_pitch, BM, a_zs));
+  BHMC_TRY(make_map3(&mB_hi, b_hi, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, b_pitch, b_box, b_zs));
   if (split3) {
-    BHMC_TRY(make_map3(&mA_lo, a_lo, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, (uint64_t)Kp, BM));
-    BHMC_TRY(make_map3(&mB_lo, b_lo, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, (uint64_t)Kp, b_box));
+    BHMC_TRY(make_map3(&mA_lo, a_lo, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, a_pitch, BM, a_zs));
+    BHMC_TRY(make_map3(&mB_lo, b_lo, (uint64_t)d.K, (uint64_t)d.N, (uint64_t)zb, b_pitch, b_box, b_zs));
   } else {
     mA_lo = mA_hi;
     mB_lo = mB_hi;

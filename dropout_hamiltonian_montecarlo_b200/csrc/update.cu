@@ -8,6 +8,7 @@
 // Chain state is [C, ld] fp32 with ld % 4 == 0, so every row is 16-byte aligned and each
 // thread moves one float4 per array.  grid = (ceil(P/4/256), C): coalesced, chain-uniform
 // control flow (activity mask, accept decision) is block-uniform.
+#include <cuda_bf16.h>
 #include "internal.cuh"
 #include "philox.cuh"
 #include "stream_ops.cuh"
@@ -135,7 +136,20 @@ __global__ void __launch_bounds__(TPB) k_hmc_update(UpdateArgs a) {
     }
   }
   st4(a.p + o, make_float4(pe[0], pe[1], pe[2], pe[3]));
-  if (hit_pre) st4(a.q + o, make_float4(qe[0], qe[1], qe[2], qe[3]));
+  if (hit_pre) {
+    st4(a.q + o, make_float4(qe[0], qe[1], qe[2], qe[3]));
+    if (a.mir_hi) {  // bf16 hi/lo image of the new position (operand mirror of the model)
+      const int64_t om = (int64_t)c * a.mir_ld + i;
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h[e] = __float2bfloat16_rn(qe[e]);
+        l[e] = __float2bfloat16_rn(qe[e] - __bfloat162float(h[e]));
+      }
+      *reinterpret_cast<uint2*>(a.mir_hi + om) = *reinterpret_cast<const uint2*>(h);
+      if (a.mir_lo) *reinterpret_cast<uint2*>(a.mir_lo + om) = *reinterpret_cast<const uint2*>(l);
+    }
+  }
 }
 
 int launch_hmc_update(bhmc_ctx* ctx, const UpdateArgs& a) {
