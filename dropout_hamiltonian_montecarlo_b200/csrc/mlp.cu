@@ -469,9 +469,29 @@ __global__ void __launch_bounds__(256, 2) k_mlp_head(const float* __restrict__ H
     for (int r = 0; r < 32; ++r) sacc += dZs[r * NO + t];
     pW[(int64_t)(NO + 2) * n_mid + t] = sacc;
   }
-  // ---- dA2 = (dZ W3) * [H2d > 0] * gate_scale, thread = column quad: K-major bf16 copies, column sums (gb2);
-  //      gW3 partial = dZ^T H2d of the block's rows ----
-  const int half = t >> 7;  // rows half, half + 2, ... / classes half*NO/2 .. +NO/2
+  // ---- gW3 partial = dZ^T H2d of the block's rows (thread = column quad x half of the classes); must read H before the
+  //      next phase overwrites it ----
+  const int half = t >> 7;  // classes half*NO/2 .. +NO/2 here; rows half, half + 2, ... below
+  for (int k4 = t & 127; k4 < nq; k4 += 128) {
+    float4 gacc[NO / 2];
+#pragma unroll
+    for (int j = 0; j < NO / 2; ++j) gacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rows; ++r) {
+      const float4 h = *reinterpret_cast<const float4*>(Hs + r * pitch + 4 * k4);
+#pragma unroll
+      for (int j = 0; j < NO / 2; ++j) {
+        const float dz = dZs[r * NO + half * (NO / 2) + j];
+        gacc[j].x = fmaf(dz, h.x, gacc[j].x), gacc[j].y = fmaf(dz, h.y, gacc[j].y);
+        gacc[j].z = fmaf(dz, h.z, gacc[j].z), gacc[j].w = fmaf(dz, h.w, gacc[j].w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NO / 2; ++j) *reinterpret_cast<float4*>(pW + (int64_t)(half * (NO / 2) + j) * n_mid + 4 * k4) = gacc[j];
+  }
+  __syncthreads();
+  // ---- dA2 = (dZ W3) * [H2d > 0] * gate_scale, thread = column quad: K-major bf16 copies (a warp stores 256 contiguous
+  //      bytes per row), column sums (gb2).  The 16 bytes of H a thread has just read are replaced by the bf16 hi | lo
+  //      quad of dA2, for the transposed copies below ----
   for (int k4 = t & 127; k4 < nq; k4 += 128) {
     float4 w[NO];
 #pragma unroll
@@ -489,7 +509,8 @@ __global__ void __launch_bounds__(256, 2) k_mlp_head(const float* __restrict__ H
           v.x = fmaf(dze[j], w[o].x, v.x), v.y = fmaf(dze[j], w[o].y, v.y), v.z = fmaf(dze[j], w[o].z, v.z), v.w = fmaf(dze[j], w[o].w, v.w);
         }
       }
-      const float4 h = *reinterpret_cast<const float4*>(Hs + r * pitch + 4 * k4);
+      float4* hslot = reinterpret_cast<float4*>(Hs + r * pitch + 4 * k4);
+      const float4 h = *hslot;
       v.x = h.x > 0.f ? v.x * gate_scale : 0.f, v.y = h.y > 0.f ? v.y * gate_scale : 0.f;
       v.z = h.z > 0.f ? v.z * gate_scale : 0.f, v.w = h.w > 0.f ? v.w * gate_scale : 0.f;
       cs.x += v.x, cs.y += v.y, cs.z += v.z, cs.w += v.w;
@@ -497,54 +518,30 @@ __global__ void __launch_bounds__(256, 2) k_mlp_head(const float* __restrict__ H
                           h3 = __float2bfloat16_rn(v.w);
       const int64_t o = (int64_t)c * k_batch + (int64_t)(m0 + r) * k_ld + 4 * k4;
       __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&a), pk.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(k_hi + o) = pk;
-      if (k_lo) {
-        a = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
-        b = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
-        pk.x = *reinterpret_cast<uint32_t*>(&a), pk.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(k_lo + o) = pk;
-      }
+      uint4 both;
+      both.x = *reinterpret_cast<uint32_t*>(&a), both.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(k_hi + o) = make_uint2(both.x, both.y);
+      a = __halves2bfloat162(__float2bfloat16_rn(v.x - __bfloat162float(h0)), __float2bfloat16_rn(v.y - __bfloat162float(h1)));
+      b = __halves2bfloat162(__float2bfloat16_rn(v.z - __bfloat162float(h2)), __float2bfloat16_rn(v.w - __bfloat162float(h3)));
+      both.z = *reinterpret_cast<uint32_t*>(&a), both.w = *reinterpret_cast<uint32_t*>(&b);
+      if (k_lo) *reinterpret_cast<uint2*>(k_lo + o) = make_uint2(both.z, both.w);
+      *reinterpret_cast<uint4*>(hslot) = both;  // hi quad | lo quad
     }
     *reinterpret_cast<float4*>(pW + (int64_t)(NO + half) * n_mid + 4 * k4) = cs;  // gb2: one slot per row half
-    float4 gacc[NO / 2];
-#pragma unroll
-    for (int j = 0; j < NO / 2; ++j) gacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < rows; ++r) {
-      const float4 h = *reinterpret_cast<const float4*>(Hs + r * pitch + 4 * k4);
-#pragma unroll
-      for (int j = 0; j < NO / 2; ++j) {
-        const float dz = dZs[r * NO + half * (NO / 2) + j];
-        gacc[j].x = fmaf(dz, h.x, gacc[j].x), gacc[j].y = fmaf(dz, h.y, gacc[j].y);
-        gacc[j].z = fmaf(dz, h.z, gacc[j].z), gacc[j].w = fmaf(dz, h.w, gacc[j].w);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NO / 2; ++j) *reinterpret_cast<float4*>(pW + (int64_t)(half * (NO / 2) + j) * n_mid + 4 * k4) = gacc[j];
   }
+  __syncthreads();
   // ---- transposed bf16 copies of dA2 (operand of gW2 = dA2^T H1): lane = row, so the 32 rows of a column are 64
-  //      contiguous bytes; the values are recomputed (NO FMAs each) rather than staged ----
+  //      contiguous bytes; the values come back from the H block (row pitch + 16 bytes: 4 wavefronts per 16-byte load) ----
   if (lane < rows) {
-    float dz[NO];
-#pragma unroll
-    for (int o = 0; o < NO; ++o) dz[o] = dZs[lane * NO + o];
     for (int k4 = warp; k4 < nq; k4 += 8) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int o = 0; o < NO; ++o) {
-        const float4 w = *reinterpret_cast<const float4*>(Ws + o * n_mid + 4 * k4);
-        v.x = fmaf(dz[o], w.x, v.x), v.y = fmaf(dz[o], w.y, v.y), v.z = fmaf(dz[o], w.z, v.z), v.w = fmaf(dz[o], w.w, v.w);
-      }
-      const float4 h = *reinterpret_cast<const float4*>(Hs + lane * pitch + 4 * k4);
-      const float e[4] = {h.x > 0.f ? v.x * gate_scale : 0.f, h.y > 0.f ? v.y * gate_scale : 0.f, h.z > 0.f ? v.z * gate_scale : 0.f,
-                          h.w > 0.f ? v.w * gate_scale : 0.f};
+      const uint4 both = *reinterpret_cast<const uint4*>(Hs + lane * pitch + 4 * k4);
       const int64_t o0 = (int64_t)c * t_batch + (int64_t)(4 * k4) * t_ld + m0 + lane;
+      const uint32_t hw[2] = {both.x, both.y}, lw[2] = {both.z, both.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat16 hb = __float2bfloat16_rn(e[j]);
-        t_hi[o0 + (int64_t)j * t_ld] = hb;
-        if (t_lo) t_lo[o0 + (int64_t)j * t_ld] = __float2bfloat16_rn(e[j] - __bfloat162float(hb));
+        const uint16_t hb = (uint16_t)(hw[j >> 1] >> (16 * (j & 1))), lb = (uint16_t)(lw[j >> 1] >> (16 * (j & 1)));
+        reinterpret_cast<uint16_t*>(t_hi)[o0 + (int64_t)j * t_ld] = hb;
+        if (t_lo) reinterpret_cast<uint16_t*>(t_lo)[o0 + (int64_t)j * t_ld] = lb;
       }
     }
   }
