@@ -717,6 +717,10 @@ struct bhmc_sampler {
     ctx->cur_units = rows;
     return model->grad_fused_stream(q, rows, ld, row0, nrows, cfg.precision, g, stat, hint, fst);
   }
+  int eval_fused_update(const float* q, int rows, int64_t row0, int64_t nrows, double* stat, const bhmc::UpdateArgs& u) {
+    ctx->cur_units = rows;
+    return model->grad_fused_update(q, rows, ld, row0, nrows, cfg.precision, stat, u);
+  }
   int eval(const float* q, int rows, int64_t row0, int64_t nrows, float* g, double* stat, uint32_t hint = 0) {
     ctx->cur_units = rows;
     BHMC_TRY(model->grad(q, rows, ld, row0, nrows, cfg.precision, g, stat, hint));
@@ -1415,6 +1419,10 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
       u.a_pre = 0.5f * eps;                        // hmc.py:51
     }
     int rows_prev = 0;  // rows that took part in the previous sub-step (superset of the current ones)
+    // joint sweep: a model may apply the update inside its gradient kernels (ModelBase::grad_fused_update); then the
+    // update launch in front of the next evaluation has already happened
+    const bool whole_sweep = nsw == 1 && cfg.sweep_off[0] == 0 && cfg.sweep_len[0] >= P && !s->row_comm && !s->hook;
+    bool upd_applied = false;
     for (int it = 0; it < iters; ++it) {
       const int rows = n_act(it);
       for (int v = 0; v < nsw; ++v) {
@@ -1435,23 +1443,42 @@ int bhmc_sampler_hmc_run(bhmc_sampler* s, bhmc_hmc_run* run) {
         }
         // joint sweep: the launch rewrites every parameter of the rows that move -> it can fill the model's operand mirror
         u.mir_hi = nullptr, u.mir_lo = nullptr, u.mir_ld = 0;
-        const bool whole = nsw == 1 && cfg.sweep_off[0] == 0 && cfg.sweep_len[0] >= P && !s->row_comm && !s->hook;
-        const bool mirrored = whole && mb->operand_mirror(C, ld, cfg.precision, &u.mir_hi, &u.mir_lo, &u.mir_ld);
-        BHMC_TRY(launch_hmc_update(ctx, u));
-        if (mirrored) mb->mirror_written(s->q_new);
-        u.mir_hi = nullptr, u.mir_lo = nullptr;
+        if (!upd_applied) {  // (else: the previous evaluation applied the closing kick of it - 1 and the drift of it)
+          const bool mirrored = whole_sweep && mb->operand_mirror(C, ld, cfg.precision, &u.mir_hi, &u.mir_lo, &u.mir_ld);
+          BHMC_TRY(launch_hmc_update(ctx, u));
+          if (mirrored) mb->mirror_written(s->q_new);
+          u.mir_hi = nullptr, u.mir_lo = nullptr;
+        }
+        upd_applied = false;
         const bool last = it == iters - 1 && v == nsw - 1;
         const int vn = v == nsw - 1 ? 0 : v + 1;
         uint32_t hint = (kept && cheap[v]) ? GRAD_HINT_CHEAP_MOVE : 0u;
         const bool keep_next = !last && cheap[vn] && (cheap[v] ? kept : true);
         if (keep_next) hint |= GRAD_HINT_KEEP;
         kept = keep_next;
-        BHMC_TRY(s->eval(s->q_new, rows, run->row0, nrows, s->g, stat, hint));
+        if (whole_sweep) {  // evaluation + closing kick of `it` + drift of `it + 1` inside the model's gradient kernels?
+          bhmc::UpdateArgs f = u;
+          f.post_off = cfg.sweep_off[0], f.post_len = cfg.sweep_len[0], f.it_post = it;
+          f.pre_off = cfg.sweep_off[0], f.pre_len = it + 1 < iters ? cfg.sweep_len[0] : 0, f.it_pre = it + 1;
+          f.C = rows;
+          if (sghmc) {
+            f.z = run->z_noise_dev ? run->z_noise_dev + ((size_t)t * run->z_noise_iters + it) * C * P : nullptr;
+            f.ld_z = P;
+            f.stream_lo = step;
+            f.stream_hi = TAG_NOISE | (uint32_t)((it * nsw) & 0xffffff);
+          }
+          if (mb->operand_mirror(C, ld, cfg.precision, &f.mir_hi, &f.mir_lo, &f.mir_ld)) {
+            const int rc = s->eval_fused_update(s->q_new, rows, run->row0, nrows, stat, f);
+            if (rc == BHMC_OK) upd_applied = true, kept = false;
+            else if (rc != BHMC_ERR_UNSUPPORTED) return rc;
+          }
+        }
+        if (!upd_applied) BHMC_TRY(s->eval(s->q_new, rows, run->row0, nrows, s->g, stat, hint));
         run->n_grad_launched += rows;
         rows_prev = rows;
       }
     }
-    if (iters > 0) {  // closing kick of the last variable
+    if (iters > 0 && !upd_applied) {  // closing kick of the last variable (unless the last evaluation applied it)
       u.post_off = cfg.sweep_off[nsw - 1];
       u.post_len = cfg.sweep_len[nsw - 1];
       u.it_post = iters - 1;

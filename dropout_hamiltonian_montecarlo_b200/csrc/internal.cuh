@@ -130,6 +130,7 @@ enum : uint32_t {
   GRAD_HINT_PREPARED = 4u,    // the previous fused evaluation already prepared this evaluation's operands from q
 };
 struct FusedStream;
+struct UpdateArgs;
 struct ModelBase {
   bhmc_ctx* ctx = nullptr;
   int64_t P = 0;
@@ -154,6 +155,11 @@ struct ModelBase {
   // only -- any other call sequence makes it split the parameters itself, as before.
   virtual bool operand_mirror(int, int64_t, int, __nv_bfloat16**, __nv_bfloat16**, int64_t*) { return false; }
   virtual void mirror_written(const float*) {}
+  // gradient at q followed by the lockstep sampler's whole-vector update (closing kick of one iteration, drift of the
+  // next), applied by the model's own kernels; BHMC_ERR_UNSUPPORTED (before anything is launched) = grad() + update launch
+  virtual int grad_fused_update(const float*, int, int64_t, int64_t, int64_t, int, double*, const UpdateArgs&) {
+    return BHMC_ERR_UNSUPPORTED;
+  }
   // gradient at fs.q followed by the sampler's parameter update in the same launch sequence (no g materialised);
   // BHMC_ERR_UNSUPPORTED = caller falls back to grad() + the separate update kernel
   virtual int grad_fused_step(int, int64_t, int64_t, int64_t, int, double*, const FusedStep&) { return BHMC_ERR_UNSUPPORTED; }

@@ -324,9 +324,13 @@ __global__ void __launch_bounds__(256) k_mlp_loss(float* __restrict__ Z, int B, 
 // block = 32 columns x 32 row groups of one chain (a thread per column walking all B rows left 64 blocks on the GPU and
 // took 40 us: one DRAM latency per row); each thread sums every 32nd row with four independent accumulators, the
 // groups are combined in a fixed order through shared memory (deterministic)
+struct UpdOpt {  // optional sampler update applied where a gradient value is produced (GemmDesc::upd, mlp_common.cuh)
+  int on;
+  UpdateArgs u;
+};
 __global__ void __launch_bounds__(1024) k_mlp_colsum(const float* __restrict__ S, int B, int N, int64_t s_batch,
                                                      const float* __restrict__ q, int64_t ld, int64_t b_off,
-                                                     float half_alpha, float* __restrict__ g) {
+                                                     float half_alpha, float* __restrict__ g, const UpdOpt uo) {
   __shared__ float part[32][33];
   const int c = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -349,7 +353,9 @@ __global__ void __launch_bounds__(1024) k_mlp_colsum(const float* __restrict__ S
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc += part[i][tx];
-    g[(int64_t)c * ld + b_off + n] = acc + half_alpha * q[(int64_t)c * ld + b_off + n];
+    const float gv = acc + half_alpha * q[(int64_t)c * ld + b_off + n];
+    if (uo.on) upd_apply1(uo.u, c, b_off + n, gv);
+    else g[(int64_t)c * ld + b_off + n] = gv;
   }
 }
 
@@ -551,8 +557,10 @@ __global__ void __launch_bounds__(256, 2) k_mlp_head(const float* __restrict__ H
 template <int NO>
 __global__ void __launch_bounds__(256) k_mlp_head_reduce(const float* __restrict__ part, int n_rb, int n_mid, int n_out,
                                                          const float* __restrict__ q, int64_t ld, int64_t oW3, int64_t ob3,
-                                                         int64_t ob2, float half_alpha, float* __restrict__ g) {
+                                                         int64_t ob2, float half_alpha, float* __restrict__ g, const UpdOpt uo) {
   const int c = blockIdx.y;
+  if (uo.on && blockIdx.x == 0 && threadIdx.x == 0 && uo.u.stat_new && uo.u.post_len > 0 && uo.u.it_post < uo.u.L[c] - 1)
+    uo.u.stat_new[c] = uo.u.stat[c];  // k_hmc_update's latch of the evaluation's scalar (the head kernel has finished)
   const int64_t stride = (int64_t)(NO + 2) * n_mid + NO;
   const float* pc = part + (int64_t)c * n_rb * stride;
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -560,17 +568,23 @@ __global__ void __launch_bounds__(256) k_mlp_head_reduce(const float* __restrict
   if (i < nW) {
     float acc = 0.f;
     for (int b = 0; b < n_rb; ++b) acc += pc[b * stride + i];  // rows o < n_out of the [NO][n_mid] block are contiguous
-    g[(int64_t)c * ld + oW3 + i] = acc + half_alpha * q[(int64_t)c * ld + oW3 + i];
+    const float gv = acc + half_alpha * q[(int64_t)c * ld + oW3 + i];
+    if (uo.on) upd_apply1(uo.u, c, oW3 + i, gv);
+    else g[(int64_t)c * ld + oW3 + i] = gv;
   } else if (i < nW + n_mid) {
     const int n = i - nW;
     float acc = 0.f;
     for (int b = 0; b < n_rb; ++b) acc += pc[b * stride + (int64_t)NO * n_mid + n] + pc[b * stride + (int64_t)(NO + 1) * n_mid + n];
-    g[(int64_t)c * ld + ob2 + n] = acc + half_alpha * q[(int64_t)c * ld + ob2 + n];
+    const float gv = acc + half_alpha * q[(int64_t)c * ld + ob2 + n];
+    if (uo.on) upd_apply1(uo.u, c, ob2 + n, gv);
+    else g[(int64_t)c * ld + ob2 + n] = gv;
   } else if (i < nW + n_mid + n_out) {
     const int o = i - nW - n_mid;
     float acc = 0.f;
     for (int b = 0; b < n_rb; ++b) acc += pc[b * stride + (int64_t)(NO + 2) * n_mid + o];
-    g[(int64_t)c * ld + ob3 + o] = acc + half_alpha * q[(int64_t)c * ld + ob3 + o];
+    const float gv = acc + half_alpha * q[(int64_t)c * ld + ob3 + o];
+    if (uo.on) upd_apply1(uo.u, c, ob3 + o, gv);
+    else g[(int64_t)c * ld + ob3 + o] = gv;
   }
 }
 
@@ -578,7 +592,7 @@ template <int NO>
 static int launch_head(bhmc_ctx* ctx, const float* H2d, int64_t act, int B, int n_mid, int n_out, const float* q, int64_t ld,
                        int64_t oW3, int64_t ob3, int64_t ob2, const int32_t* y, float gate_scale, float half_alpha, double* loss,
                        __nv_bfloat16* k_hi, __nv_bfloat16* k_lo, int64_t k_batch, int64_t k_ld, __nv_bfloat16* t_hi,
-                       __nv_bfloat16* t_lo, int64_t t_batch, int64_t t_ld, float* part, int C, float* g) {
+                       __nv_bfloat16* t_lo, int64_t t_batch, int64_t t_ld, float* part, int C, float* g, const UpdOpt& uo) {
   const int n_rb = (int)ceil_div(B, 32);
   const size_t smem = sizeof(float) * ((size_t)32 * (n_mid + 4) + (size_t)NO * n_mid + 32 * NO);
   static size_t configured = 0;
@@ -591,7 +605,7 @@ static int launch_head(bhmc_ctx* ctx, const float* H2d, int64_t act, int B, int 
                                                                              t_ld, part, n_rb);
   const int n_items = n_out * n_mid + n_mid + n_out;
   k_mlp_head_reduce<NO><<<dim3((unsigned)ceil_div(n_items, 256), (unsigned)C), 256, 0, ctx->stream>>>(part, n_rb, n_mid, n_out, q, ld, oW3,
-                                                                                                   ob3, ob2, half_alpha, g);
+                                                                                                   ob3, ob2, half_alpha, g, uo);
   ctx->launches += 2;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
@@ -620,6 +634,12 @@ struct MlpModel : ModelBase {
   int64_t mir_ld = 0;
   int mir_C = 0;
   const float* mir_fresh = nullptr;  // the buffer whose image the mirror holds, valid for the next grad() only
+  // fused sampler update (grad_fused_update): the gradient-producing kernels apply it; W2^T of the NEW position is written
+  // by the W2-gradient epilogue into w2t and serves the next evaluation's dA1 GEMM (same one-shot validity as the mirror)
+  const UpdateArgs* fused_upd = nullptr;
+  __nv_bfloat16* w2t = nullptr;
+  size_t w2t_bytes = 0;
+  const float* w2t_fresh = nullptr;
   __nv_bfloat16* xw = nullptr;
   size_t xw_bytes = 0;
   const float* xw_src = nullptr;
@@ -631,6 +651,7 @@ struct MlpModel : ModelBase {
     cudaFree(y_owned);
     cudaFree(xw);
     cudaFree(mir_hi);
+    cudaFree(w2t);
   }
   int64_t default_rows() const override { return N; }
 
@@ -658,6 +679,50 @@ struct MlpModel : ModelBase {
     return true;
   }
   void mirror_written(const float* q) override { mir_fresh = q; }
+
+  // Gradient at q followed by the sampler's update u (whole parameter vector: closing kick of iteration u.it_post, then --
+  // if u.pre_len > 0 -- the drift of iteration u.it_pre), applied by the kernels that produce the gradient slices: no
+  // update launch, no gradient round trip through HBM, and the bf16 operand copies of the new weights (mirror, W2^T) come
+  // from the same epilogues.  BHMC_ERR_UNSUPPORTED before anything is launched = the caller runs grad() + update.
+  int grad_fused_update(const float* q, int C, int64_t ld, int64_t row0, int64_t nrows, int prec, double* stat,
+                        const UpdateArgs& u) override {
+    // Measured (cfg4, 16 chains): 52.7 k grad-evals/s with it against 65 k without -- the GEMM epilogues are the
+    // bottleneck of these launches (1.7 tiles per CTA, last tile exposed), and Philox / Box-Muller noise plus the p / q
+    // traffic in there cost more than the HBM-bound update launch they replace.  Off by default; parity-tested both ways.
+    static int env = -1;  // BHMC_MLP_FUSE_UPD=1: on
+    if (env < 0) {
+      const char* e = getenv("BHMC_MLP_FUSE_UPD");
+      env = e ? atoi(e) : 0;
+    }
+    const bool whole = u.post_off == 0 && u.post_len >= P && (u.pre_len == 0 || (u.pre_off == 0 && u.pre_len >= P));
+    if (!env || prec == BHMC_PREC_FP32 || !whole || u.q != q || !u.p || !u.L || !u.g || !u.mir_hi || u.mir_hi != mir_hi || logits_sink ||
+        nrows < 64 || n_mid < 64 || n_in < 64 || n_out > 16 || n_mid % 8 || n_in % 8 || oW1 % 8 || oW2 % 8 || ld % 4)
+      return BHMC_ERR_UNSUPPORTED;
+    {
+      const char* e1 = getenv("BHMC_MLP_FUSE");
+      const char* e2 = getenv("BHMC_MLP_HEAD");
+      const char* e3 = getenv("BHMC_BG_EPI2");
+      if ((e1 && !atoi(e1)) || (e2 && !atoi(e2)) || (e3 && !atoi(e3))) return BHMC_ERR_UNSUPPORTED;
+      const size_t head_smem = sizeof(float) * ((size_t)32 * (n_mid + 4) + (size_t)round_up(n_out, 4) * n_mid + 32 * round_up(n_out, 4));
+      if (head_smem > (size_t)200 * 1024) return BHMC_ERR_UNSUPPORTED;
+    }
+    const int64_t kp_mid = round_up(n_mid, 64);
+    const size_t need = sizeof(__nv_bfloat16) * 2 * (size_t)C * n_mid * kp_mid;
+    if (need > w2t_bytes) {
+      cudaFree(w2t);
+      w2t = nullptr, w2t_bytes = 0, w2t_fresh = nullptr;
+      if (cudaMalloc(&w2t, need) != cudaSuccess) {
+        cudaGetLastError();
+        return BHMC_ERR_UNSUPPORTED;
+      }
+      w2t_bytes = need;
+    }
+    fused_upd = &u;
+    const int rc = grad(q, C, ld, row0, nrows, prec, const_cast<float*>(u.g), stat, 0);
+    fused_upd = nullptr;
+    if (rc == BHMC_OK) mir_fresh = q, w2t_fresh = q;  // both images describe the position the epilogues wrote
+    return rc;
+  }
 
   // NLP = loss + log_prior, log_prior = -alpha/2 sum_v |theta_v|^2/dim_v  (mlp.py:40-45,80-82)
   void energy_coeffs(int64_t, double* a, double* b, double* cv) const override {
@@ -769,6 +834,20 @@ struct MlpModel : ModelBase {
     // the image is valid for exactly the evaluation that follows the update launch that wrote it
     const bool mirror = mir_fresh == q && mir_hi && C <= mir_C && use_tc && fuse;
     mir_fresh = nullptr;
+    const bool fu = fused_upd != nullptr;
+    const bool w2t_ok = w2t_fresh == q && w2t && use_tc && fuse && sizeof(__nv_bfloat16) * 2 * (size_t)C * n_mid * kp_mid <= w2t_bytes;
+    w2t_fresh = nullptr;
+    const int64_t e_w2t = (int64_t)n_mid * kp_mid;  // elements per chain of the W2^T copy; the lo half follows C_alloc chains
+    const int64_t w2t_lo = (int64_t)(w2t_bytes / (sizeof(__nv_bfloat16) * 2));
+    UpdOpt uo{};
+    if (fu) {
+      if (!(fuse && head)) {
+        set_error("fused sampler update requested on a path without producer-written operand copies");
+        return BHMC_ERR_STATE;
+      }
+      uo.on = 1;
+      uo.u = *fused_upd;
+    }
     BHMC_CUDA_OK(cudaMemsetAsync(stat, 0, sizeof(double) * C, ctx->stream));
     {
       GroupTimer t(ctx, KG_FWD);
@@ -825,7 +904,7 @@ struct MlpModel : ModelBase {
       const float gs = keep_inv * keep_inv;
 #define BHMC_HEAD(NOV)                                                                                                          \
   BHMC_TRY(launch_head<NOV>(ctx, H2d, act, B, n_mid, n_out, q, ld, oW3, ob3, ob2, labels + row0, gs, ha, stat, dA2k, klo, e_k, kp_mid, \
-                            dA2t, tlo, e_t, kp_b, head_part, C, g))
+                            dA2t, tlo, e_t, kp_b, head_part, C, g, uo))
       if (NO == 4) BHMC_HEAD(4);
       else if (NO == 8) BHMC_HEAD(8);
       else if (NO == 12) BHMC_HEAD(12);
@@ -839,7 +918,7 @@ struct MlpModel : ModelBase {
     d.M = n_out, d.N = n_mid, d.K = B;
     d.addsrc = q + oW3, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
     BHMC_TRY(run_gemm(ctx, d, C));
-    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_out, 32), C), 1024, 0, ctx->stream>>>(Z, B, n_out, (int64_t)B * n_out, q, ld, ob3, ha, g);
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_out, 32), C), 1024, 0, ctx->stream>>>(Z, B, n_out, (int64_t)B * n_out, q, ld, ob3, ha, g, UpdOpt{});
     // dA2 = (dZ W3) * [H2d > 0] / keep^2
     d = base();
     d.A = Z, d.a_batch = (int64_t)B * n_out, d.a_rs = n_out, d.a_cs = 1;
@@ -850,29 +929,46 @@ struct MlpModel : ModelBase {
     if (fuse) out_k(d, dA2k);  // its transposed copy (for gW2) stays a split launch: see k_mlp_gemm_small_k
     BHMC_TRY(run_gemm(ctx, d, C));
     }
-    // gW2 = dA2^T H1 + alpha/2 W2 ; gb2
-    d = base();
-    d.A = dA2, d.a_batch = act, d.a_rs = 1, d.a_cs = n_mid;
-    d.B = H1, d.b_batch = act, d.b_rs = n_mid, d.b_cs = 1;
-    d.C = g + oW2, d.c_batch = ld, d.c_rs = n_mid;
-    d.M = n_mid, d.N = n_mid, d.K = B;
-    d.addsrc = q + oW2, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
-    if (fuse) d.b_hi = H1t, d.b_lo = split3 ? H1t + lo_t : nullptr, d.b_kp = kp_b;
-    if (head) d.a_hi = dA2t, d.a_lo = split3 ? dA2t + lo_t : nullptr, d.a_kp = kp_b;
-    BHMC_TRY(run_gemm(ctx, d, C));
-    if (!head) k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g);
-    // dA1 = (dA2 W2) * [H1 > 0] / keep
-    d = base();
-    d.A = dA2, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
-    d.B = q + oW2, d.b_batch = ld, d.b_rs = n_mid, d.b_cs = 1;
-    d.C = dA1, d.c_batch = act, d.c_rs = n_mid;
-    d.M = B, d.N = n_mid, d.K = n_mid;
-    d.gate = H1, d.gate_batch = act, d.gate_rs = n_mid, d.gate_scale = keep_inv;
-    if (fuse) {
-      d.a_hi = dA2k, d.a_lo = split3 ? dA2k + lo_k : nullptr, d.a_kp = kp_mid;
-      out_t(d, dA1t);
+    auto do_gW2 = [&]() -> int {  // gW2 = dA2^T H1 + alpha/2 W2 ; gb2
+      GemmDesc d = base();
+      d.A = dA2, d.a_batch = act, d.a_rs = 1, d.a_cs = n_mid;
+      d.B = H1, d.b_batch = act, d.b_rs = n_mid, d.b_cs = 1;
+      d.C = g + oW2, d.c_batch = ld, d.c_rs = n_mid;
+      d.M = n_mid, d.N = n_mid, d.K = B;
+      d.addsrc = q + oW2, d.add_batch = ld, d.add_rs = n_mid, d.add_scale = ha;
+      if (fuse) d.b_hi = H1t, d.b_lo = split3 ? H1t + lo_t : nullptr, d.b_kp = kp_b;
+      if (head) d.a_hi = dA2t, d.a_lo = split3 ? dA2t + lo_t : nullptr, d.a_kp = kp_b;
+      if (fu) {  // the epilogue updates W2 and leaves W2^T of the new position for the next evaluation's dA1 GEMM
+        d.upd_on = 1, d.upd_off = oW2, d.upd = *fused_upd;
+        d.ct_hi = w2t, d.ct_lo = split3 ? w2t + w2t_lo : nullptr, d.ct_batch = e_w2t, d.ct_ld = kp_mid;
+      }
+      BHMC_TRY(run_gemm(ctx, d, C));
+      if (!head) k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g, UpdOpt{});
+      return BHMC_OK;
+    };
+    auto do_dA1 = [&]() -> int {  // dA1 = (dA2 W2) * [H1 > 0] / keep
+      GemmDesc d = base();
+      d.A = dA2, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
+      d.B = q + oW2, d.b_batch = ld, d.b_rs = n_mid, d.b_cs = 1;
+      d.C = dA1, d.c_batch = act, d.c_rs = n_mid;
+      d.M = B, d.N = n_mid, d.K = n_mid;
+      d.gate = H1, d.gate_batch = act, d.gate_rs = n_mid, d.gate_scale = keep_inv;
+      if (fuse) {
+        d.a_hi = dA2k, d.a_lo = split3 ? dA2k + lo_k : nullptr, d.a_kp = kp_mid;
+        out_t(d, dA1t);
+      }
+      if (w2t_ok) d.b_hi = w2t, d.b_lo = split3 ? w2t + w2t_lo : nullptr, d.b_kp = kp_mid;  // written by the previous fused evaluation
+      BHMC_TRY(run_gemm(ctx, d, C));
+      return BHMC_OK;
+    };
+    // fused update: the W2-gradient epilogue overwrites W2 and its transposed copy, which the dA1 GEMM reads -> dA1 first
+    if (fu) {
+      BHMC_TRY(do_dA1());
+      BHMC_TRY(do_gW2());
+    } else {
+      BHMC_TRY(do_gW2());
+      BHMC_TRY(do_dA1());
     }
-    BHMC_TRY(run_gemm(ctx, d, C));
     // gW1 = dA1^T X + alpha/2 W1 ; gb1
     d = base();
     d.A = dA1, d.a_batch = act, d.a_rs = 1, d.a_cs = n_mid;
@@ -882,8 +978,9 @@ struct MlpModel : ModelBase {
     d.addsrc = q + oW1, d.add_batch = ld, d.add_rs = n_in, d.add_scale = ha;
     if (fuse) d.a_hi = dA1t, d.a_lo = split3 ? dA1t + lo_t : nullptr, d.a_kp = kp_b;
     if (xcache) d.b_hi = xw + 2 * e_xk, d.b_lo = split3 ? xw + 2 * e_xk + e_xt : nullptr, d.b_kp = kp_b;
+    if (fu) d.upd_on = 1, d.upd_off = oW1, d.upd = *fused_upd;
     BHMC_TRY(run_gemm(ctx, d, C));
-    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g);
+    k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA1, B, n_mid, act, q, ld, ob1, ha, g, uo);
     ctx->launches += head ? 1 : 3;
     // padding columns of g (ld > P) are never read by the update kernels beyond P; keep them finite
     BHMC_CUDA_OK(cudaGetLastError());

@@ -227,6 +227,7 @@ __device__ __forceinline__ void bg_epi2_prefetch(const BgParams& p, int z, int m
   }
 }
 
+template <bool UPD>
 __device__ __forceinline__ void bg_epi2_chunk(const BgParams& p, uint32_t tacc, int z, int mt, int nt, int chunk, int lane,
                                               float4* blk, const EpiPre& pre) {
   const GemmDesc& d = p.d;
@@ -287,7 +288,16 @@ __device__ __forceinline__ void bg_epi2_chunk(const BgParams& p, uint32_t tacc, 
         };
         v.x = act(v.x, 1u), v.y = act(v.y, 2u), v.z = act(v.z, 4u), v.w = act(v.w, 8u);
       }
-      *reinterpret_cast<float4*>(d.C + (int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n) = v;
+      if (UPD && d.upd_on) {
+        // v is the gradient slice (acc + alpha/2 q): apply the sampler's update instead of storing it; from here on v is
+        // the NEW position (the transposed operand copy below is taken from it)
+        const float ge[4] = {v.x, v.y, v.z, v.w};
+        float qe[4] = {pre.a[i].x, pre.a[i].y, pre.a[i].z, pre.a[i].w};
+        upd_apply4(d.upd, z, d.upd_off + (int64_t)m * d.add_rs + n, ge, qe);
+        v = make_float4(qe[0], qe[1], qe[2], qe[3]);
+      } else {
+        *reinterpret_cast<float4*>(d.C + (int64_t)z * d.c_batch + (int64_t)m * d.c_rs + n) = v;
+      }
       if (d.ck_hi) {
         const int64_t o = (int64_t)z * d.ck_batch + (int64_t)m * d.ck_ld + n;
         const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
@@ -312,7 +322,9 @@ __device__ __forceinline__ void bg_epi2_chunk(const BgParams& p, uint32_t tacc, 
     const int m = row0 + lane;
     const int n0 = nt * p.BN + chunk * 16;
     const int sw = (lane >> 1) & 3;
-    if (m < d.M) {
+    // fused update: a chain that does not take part in the drift keeps its position -- and its copy
+    const bool moved = !UPD || !d.upd_on || (d.upd.pre_len > 0 && d.upd.it_pre < d.upd.L[z] - 1);
+    if (m < d.M && moved) {
       const int64_t o = (int64_t)z * d.ct_batch + (int64_t)n0 * d.ct_ld + m;
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq) {
@@ -332,6 +344,7 @@ __device__ __forceinline__ void bg_epi2_chunk(const BgParams& p, uint32_t tacc, 
 }
 
 // One tile: prefetch, wait for the accumulator, chunks.  `part` (0..EW/4-1) selects the warp's 16-column chunks.
+template <bool UPD>
 __device__ __forceinline__ void bg_epilogue_tile2(const BgParams& p, uint32_t tacc, int z, int mt, int nt, int part, int lane,
                                                   float4* blk, uint32_t bar, uint32_t parity) {
   constexpr int PARTS = EW / 4;
@@ -344,16 +357,17 @@ __device__ __forceinline__ void bg_epilogue_tile2(const BgParams& p, uint32_t ta
   if (p.debug_epi == 1) return;
   for (int k = 0; k < n_chunks; k += 2) {
     const int c0 = part + k * PARTS;
-    if (nt * p.BN + c0 * 16 < p.d.N) bg_epi2_chunk(p, tacc, z, mt, nt, c0, lane, blk, pre0);
+    if (nt * p.BN + c0 * 16 < p.d.N) bg_epi2_chunk<UPD>(p, tacc, z, mt, nt, c0, lane, blk, pre0);
     if (k + 2 < n_chunks) bg_epi2_prefetch(p, z, mt, nt, c0 + 2 * PARTS, lane, pre0);
     if (k + 1 < n_chunks) {
       const int c1 = c0 + PARTS;
-      if (nt * p.BN + c1 * 16 < p.d.N) bg_epi2_chunk(p, tacc, z, mt, nt, c1, lane, blk, pre1);
+      if (nt * p.BN + c1 * 16 < p.d.N) bg_epi2_chunk<UPD>(p, tacc, z, mt, nt, c1, lane, blk, pre1);
       if (k + 3 < n_chunks) bg_epi2_prefetch(p, z, mt, nt, c1 + 2 * PARTS, lane, pre1);
     }
   }
 }
 
+template <bool UPD>
 __global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
 k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
            const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const BgParams p) {
@@ -463,7 +477,7 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
       if (p.epi2) {
         float4* blk = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + (warp - 4) * 128;
-        bg_epilogue_tile2(p, tacc, z, mt, nt, part, lane, blk, smem_u32(&bar_tfull[buf]), use & 1u);
+        bg_epilogue_tile2<UPD>(p, tacc, z, mt, nt, part, lane, blk, smem_u32(&bar_tfull[buf]), use & 1u);
       } else {
         mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
         tcgen05_fence_after();
@@ -488,6 +502,7 @@ k_tc_bgemm(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ C
 // N tile up to 256 wide: every CTA stages its own A tile and only HALF of the B tile (32 KB + BN/2 rows), the leader's
 // elected thread issues tcgen05.mma.cta_group::2.  At BN = 256 that is 64 KB per CTA for 12 MMAs of 128 cycles: the
 // main loop is bound by the tensor pipe again.  Barrier protocol as in k_tc_fwd2 (softmax_tc.cu).
+template <bool UPD>
 __global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
 k_tc_bgemm2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const BgParams p) {
@@ -604,7 +619,7 @@ k_tc_bgemm2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
       const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
       if (p.epi2) {  // rows of a phantom tile fail the m < M tests
         float4* blk = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + (warp - 4) * 128;
-        bg_epilogue_tile2(p, tacc, z, mt, nt, part, lane, blk, smem_u32(&bar_tfull[buf]), use & 1u);
+        bg_epilogue_tile2<UPD>(p, tacc, z, mt, nt, part, lane, blk, smem_u32(&bar_tfull[buf]), use & 1u);
       } else {
         mbar_wait(smem_u32(&bar_tfull[buf]), use & 1u);
         tcgen05_fence_after();
@@ -873,6 +888,10 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   const int epi_bytes = EW * 2048;  // per-warp 32 x 16 fp32 blocks of the second epilogue form
   p.epi2 = (epi2_env && p.vec && (!d.ck_hi || (d.ck_ld % 4 == 0 && d.ck_batch % 4 == 0 && (((uintptr_t)d.ck_hi | (uintptr_t)d.ck_lo) & 7u) == 0)) &&
             (!d.bias || (d.bias_batch % 4 == 0 && ((uintptr_t)d.bias & 15u) == 0)) && !(d.addsrc && d.gate)) ? 1 : 0;
+  if (d.upd_on && (!p.epi2 || !d.addsrc || d.gate || d.bias || d.epi != 0 || d.ck_hi)) {
+    set_error("fused sampler update needs the second epilogue form of k_tc_bgemm on a plain gradient GEMM");
+    return BHMC_ERR_STATE;
+  }
   p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024 - (p.epi2 ? epi_bytes : 0)) / stage_bytes)));
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   const uint64_t a_pitch = a_pre ? (uint64_t)d.a_kp : (uint64_t)Kp, b_pitch = b_pre ? (uint64_t)d.b_kp : (uint64_t)Kp;
@@ -889,11 +908,13 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (p.epi2 ? epi_bytes : 0);
   static size_t configured = 0, configured2 = 0;
   if (!pair && smem > configured) {
-    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   if (pair && smem > configured2) {
-    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured2 = smem;
   }
   const int work = batch * (pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
@@ -926,8 +947,11 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (pair) BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bgemm2, mA_hi, mA_lo, mB_hi, mB_lo, p));
-  else BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bgemm, mA_hi, mA_lo, mB_hi, mB_lo, p));
+  // the instantiation with the fused sampler update carries Philox / Box-Muller code in its epilogue: only where asked for
+  if (pair) BHMC_CUDA_OK(d.upd_on ? cudaLaunchKernelEx(&cfg, k_tc_bgemm2<true>, mA_hi, mA_lo, mB_hi, mB_lo, p)
+                                  : cudaLaunchKernelEx(&cfg, k_tc_bgemm2<false>, mA_hi, mA_lo, mB_hi, mB_lo, p));
+  else BHMC_CUDA_OK(d.upd_on ? cudaLaunchKernelEx(&cfg, k_tc_bgemm<true>, mA_hi, mA_lo, mB_hi, mB_lo, p)
+                             : cudaLaunchKernelEx(&cfg, k_tc_bgemm<false>, mA_hi, mA_lo, mB_hi, mB_lo, p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;

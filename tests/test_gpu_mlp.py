@@ -246,3 +246,108 @@ def test_mlp_model_golden_through_cuda(case, prec):
             assert bad.mean() <= 5e-3 and np.abs(gk - ref).max() <= 1e-3 * np.abs(ref).max(), (k, bad.mean())
     close(m.log_likelihood(par, X_train=X, y_train=y), g["loss"], 1e-5)
     close(m.negative_log_posterior(par, X_train=X, y_train=y), g["nlp"], 1e-5)
+
+
+class _FlatMlpOracle:
+    """The oracle's MLP seen as ONE variable 'theta' (KEYS order, the layout of the parameter vector on the device): the
+    joint sweep -- one gradient per leapfrog iteration, every parameter moved together -- is Gauss-Seidel over that
+    single variable (oracle sghmc_step / hmc_step unchanged)."""
+
+    def __init__(self, inner, shapes):
+        self.inner, self.shapes = inner, shapes
+
+    def unflat(self, par):
+        th, out, pos = np.asarray(par["theta"]), {}, 0
+        for k, sh in zip(KEYS, self.shapes):
+            n = int(np.prod(sh))
+            out[k] = th[pos:pos + n].reshape(sh)
+            pos += n
+        return out
+
+    def grad(self, par, **d):
+        g = self.inner.grad(self.unflat(par), **d)
+        return {"theta": np.concatenate([np.asarray(g[k]).ravel() for k in KEYS])}
+
+    def log_likelihood(self, par, **d):
+        return self.inner.log_likelihood(self.unflat(par), **d)
+
+    def negative_log_posterior(self, par, **d):
+        return self.inner.negative_log_posterior(self.unflat(par), **d)
+
+
+def test_sghmc_joint_sweep_on_mlp_vs_oracle():
+    """BASELINE config 4 runs the 'joint' sweep (one gradient per leapfrog iteration).  Shape with every GEMM dimension
+    >= 64: the tcgen05 path with the update applied by the gradient epilogues (ModelBase::grad_fused_update), the operand
+    mirror and the W2^T copy of csrc/mlp.cu all take part; injected noise and dropout masks; fp64 oracle."""
+    rs = np.random.RandomState(8)
+    B, n_in, n_mid, n_out, alpha = 80, 64, 64, 10, 0.1
+    par, X, y = make(rs, B, n_in, n_mid, n_out, scale=0.1)
+    masks = (rs.rand(3, 1, B, n_mid) > 0.1).astype(np.uint8)
+    eps, path = 1e-2, 3.5e-2
+    model = mlp({"alpha": alpha}, n_in, n_mid, n_out, precision="bf16x3")
+    model.bind(X, y)
+    model.set_masks(masks)
+    s = sghmc(model, par, path_length=path, step_size=eps, verbose=False, sign="descent", sweep="joint")
+    shapes = [par[k].shape for k in KEYS]
+    P = sum(int(np.prod(sh)) for sh in shapes)
+    L = O.path_length_steps(0.62, path, eps)
+    z = rs.normal(size=P * L)
+    with replay_uniforms([0.62, 0.5]):
+        q, p, a = s.step(par, None, TapeRng(z), X_train=X, y_train=y)
+    flat = _FlatMlpOracle(O.MlpOracle({"alpha": alpha}, lambda b, n: [masks[l, 0].astype(np.float64) for l in range(3)]), shapes)
+    th0 = {"theta": np.concatenate([np.asarray(par[k], dtype=np.float64).ravel() for k in KEYS])}
+    r = O.sghmc_step(flat, th0, ["theta"], eps, path, O.TapeDraws([z[i * P:(i + 1) * P] for i in range(L)], [0.62, 0.5]),
+                     sign="descent", X_train=X, y_train=y)
+    assert r["L"] == L and L >= 4
+    rq, rp = flat.unflat(r["q"]), flat.unflat(r["p"])
+    close(a, r["accept_prob"], 1e-3, 1e-6)
+    for k in KEYS:
+        close(q[k], rq[k], 1e-4, 2e-5, k)
+        close(p[k], rp[k], 1e-4, 2e-5, k)
+
+
+def test_mlp_update_applied_by_the_gradient_epilogues_matches_update_launches():
+    """csrc/mlp.cu grad_fused_update (default) against BHMC_MLP_FUSE_UPD=0 (gradient to HBM + k_hmc_update launches):
+    same Philox noise and masks, several chains, three sghmc steps on different row windows -- positions and momenta equal to
+    fp32 round-off, the same number of gradient evaluations, fewer launches."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from dropout_hamiltonian_montecarlo_b200.runtime import MlpHandle, SamplerHandle, default_context
+ctx = default_context()
+rs = np.random.RandomState(4)
+N, n_in, n_mid, n_out, C, B = 600, 128, 192, 7, 5, 200
+X = torch.as_tensor(rs.rand(N, n_in).astype(np.float32)).cuda(); y = torch.as_tensor(rs.randint(0, n_out, N).astype(np.int32)).cuda()
+out = {}
+for kind, name in ((2, "sghmc"), (0, "hmc")):
+    h = MlpHandle(ctx, N, n_in, n_mid, n_out, 0.01, 0.1, seed=3, chain_id0=2); h.bind(X, y)
+    s = SamplerHandle(ctx, h, kind, C, seed=11, precision=1, sweep=[(0, h.P)], shared_path=(kind == 2), sghmc_descent=True)
+    s.set_q(np.random.RandomState(5).normal(0, .05, (C, h.P)).astype(np.float32))
+    l0 = ctx.launches; ng = 0
+    for j in range(3):
+        o = s.hmc_run(1, 2e-3, 1.2e-2, row0=j * B, nrows=B, step0=j, keep_samples=False, schedule="lockstep")
+        ng += o["n_grad_evals"]
+    ctx.sync()
+    out[name + "_q"] = s.get(0); out[name + "_p"] = s.get(1); out[name + "_ng"] = ng; out[name + "_l"] = ctx.launches - l0
+    s.close(); h.close()
+np.savez(sys.argv[1], **out)
+''' % (root,)
+    res = []
+    for fu in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".npz") as f:
+            r = subprocess.run([sys.executable, "-c", code, f.name], env=dict(os.environ, BHMC_MLP_FUSE_UPD=fu), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-3000:]
+            res.append({k: v for k, v in np.load(f.name).items()})
+    a, b = res
+    for name in ("sghmc", "hmc"):
+        assert int(a[name + "_ng"]) == int(b[name + "_ng"]) and int(a[name + "_ng"]) > 3 * 5
+        assert int(a[name + "_l"]) < int(b[name + "_l"]), (name, a[name + "_l"], b[name + "_l"])
+        for w in ("_q", "_p"):
+            x, yv = a[name + w].astype(np.float64), b[name + w].astype(np.float64)
+            assert np.abs(x - yv).max() <= 2e-5 * np.abs(yv).max(), (name, w, np.abs(x - yv).max() / np.abs(yv).max())
