@@ -43,6 +43,8 @@ struct PersistParams {
   int dm_rows;                    // rows per (P-Y)^T slab = n_tiles * BN
   int xt_rows;                    // rows per X^T slab (Dt_pad)
   unsigned int* bar;              // grid barrier counter (zeroed before the launch)
+  int half_f;                     // forward items are HALF row tiles (64 rows of the window): twice the items, 36 KB instead of
+                                  // 52 KB per chunk and item; the MMA stays M = 128, the upper accumulator half is ignored
   int pair;                       // clusters of two CTAs work on the same row / feature tile and adjacent chain tiles: each
                                   // fetches half of the shared X (X^T) tile and multicasts it to both (BHMC_PERSIST_PAIR)
   int prefetch;                   // L2 prefetch of the next phase's X window (BHMC_PERSIST_PF, default on)
@@ -196,21 +198,32 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const int rank = p.pair ? (int)cluster_ctarank() : 0;
 
-  // ring / accumulator bookkeeping of each role (lives across phases and steps)
-  int stage = 0;
-  uint32_t phase = 0;
-  int it = 0;
+  // ring / accumulator bookkeeping (lives across phases and steps); every role has its own variables.
+  // What bounds a phase (in-kernel counters, BHMC_PROF=1): the MMA warp of phase F spends 15.6 k cycles per item and waits
+  // only 4.3 k of them for operands -- 11.3 k cycles for 156 MMAs = 72 cycles per MMA where the tensor core needs 40
+  // (M = 128, N = 80, K = 16).  Both operands come from shared memory: 4 KB of A + 2.5 KB of B per MMA at 128 B/clk is 52
+  // cycles, and the TMA writes of the next chunks (52 KB = 406 cycles per chunk) share the port.  Narrow-N bf16x3 items
+  // are bound by the shared-memory port, not by HBM, L2, the request path (pair multicast: no gain) or the bytes per
+  // chunk (half tiles: no gain).
+  int p_stage = 0;      // producer (warp 0, lane 0)
+  uint32_t p_phase = 0;
+  int m_stage = 0;      // MMA issuer (warp 1, warp-uniform)
+  uint32_t m_phase = 0;
+  int m_it = 0;
+  int it = 0;           // epilogue warps
   unsigned int n_bar = 0;
 
   // one work item of either phase, seen from the three roles
   auto produce = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* b_hi, const CUtensorMap* b_lo,
-                     int n_chunks, int a_k0, int a_dk, int a_m0, int a_dm, int b_k0, int b_dk, int b_n0, int b_dn) {
-    // chunk k: A box at (a_k0 + k*a_dk, a_m0 + k*a_dm), B box at (b_k0 + k*b_dk, b_n0 + k*b_dn)
+                     int n_chunks, int a_k0, int a_dk, int a_m0, int a_dm, int b_k0, int b_dk, int b_n0, int b_dn,
+                     int a_box_bytes) {
+    // chunk k: A box at (a_k0 + k*a_dk, a_m0 + k*a_dm), B box at (b_k0 + k*b_dk, b_n0 + k*b_dn); a_box_bytes < a_bytes: the
+    // map's box is a half tile (rows 64..127 of the slot keep whatever they held -- their accumulator rows are ignored)
     for (int k = 0; k < n_chunks; ++k) {
-      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-      const uint32_t full = smem_u32(&bar_full[stage]);
-      mbar_expect_tx(full, (uint32_t)stage_bytes);
-      const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + na * a_bytes;
+      mbar_wait(smem_u32(&bar_empty[p_stage]), p_phase ^ 1u);
+      const uint32_t full = smem_u32(&bar_full[p_stage]);
+      mbar_expect_tx(full, (uint32_t)(na * a_box_bytes + nb * b_bytes));
+      const uint32_t sa = smem_base + p_stage * stage_bytes, sb = sa + na * a_bytes;
       if (p.pair) {  // the A tile is the same for both CTAs of the cluster: fetch 64 of its 128 rows for both
         const uint32_t off = (uint32_t)rank * (BM / 2) * (BK * 2);
         tma_load_2d_mc(sa + off, a_hi, full, a_k0 + k * a_dk, a_m0 + k * a_dm + rank * (BM / 2), 3);
@@ -221,19 +234,24 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
       }
       tma_load_2d(sb, b_hi, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
       if (p.split3) tma_load_2d(sb + b_bytes, b_lo, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
-      if (++stage == p.stages) stage = 0, phase ^= 1u;
+      if (++p_stage == p.stages) p_stage = 0, p_phase ^= 1u;
     }
   };
+  long long mma_wait[2] = {0, 0}, mma_all[2] = {0, 0};  // BHMC_PROF: cycles the MMA warp waits for operands / spends per phase
+  int which_phase = 0;
   auto issue = [&](int n_chunks) {  // whole warp, warp-uniform; the elected lane issues
-    const int buf = it & 1;
-    const uint32_t use = (uint32_t)(it >> 1);
+    const int buf = m_it & 1;
+    const uint32_t use = (uint32_t)(m_it >> 1);
+    const long long t_in = p.prof ? clock64() : 0;
     mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);
     tcgen05_fence_after();
     const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
     for (int k = 0; k < n_chunks; ++k) {
-      mbar_wait(smem_u32(&bar_full[stage]), phase);
+      const long long t_w = p.prof ? clock64() : 0;
+      mbar_wait(smem_u32(&bar_full[m_stage]), m_phase);
+      if (p.prof) mma_wait[which_phase] += clock64() - t_w;
       tcgen05_fence_after();
-      const uint32_t sa = smem_base + stage * stage_bytes;
+      const uint32_t sa = smem_base + m_stage * stage_bytes;
       const uint32_t first = k > 0 ? 1u : 0u;
       if (p.split3 == 1) {
         const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
@@ -262,12 +280,13 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
           umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
         }
       }
-      if (p.pair) umma_commit_mc(smem_u32(&bar_empty[stage]), 3);  // frees the slot in both CTAs
-      else umma_commit(smem_u32(&bar_empty[stage]));
-      if (++stage == p.stages) stage = 0, phase ^= 1u;
+      if (p.pair) umma_commit_mc(smem_u32(&bar_empty[m_stage]), 3);  // frees the slot in both CTAs
+      else umma_commit(smem_u32(&bar_empty[m_stage]));
+      if (++m_stage == p.stages) m_stage = 0, m_phase ^= 1u;
     }
     umma_commit(smem_u32(&bar_tfull[buf]));
-    ++it;
+    if (p.prof) mma_all[which_phase] += clock64() - t_in;
+    ++m_it;
   };
 
   const int ew = warp & 3, part = (warp - 4) >> 2, t = ew * 32 + lane;
@@ -275,7 +294,8 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   float* epi_S = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes) +
                  (warp >= 4 ? (warp - 4) * 32 * KP : 0);
   const int m_tiles_f = (int)((p.batch + BM - 1) / BM);
-  const int items_f = m_tiles_f * p.n_tiles, items_b = p.m_tiles_b * p.n_tiles;
+  const int f_rows = p.half_f ? BM / 2 : BM;  // window rows of a forward item
+  const int items_f = (p.half_f ? 2 : 1) * m_tiles_f * p.n_tiles, items_b = p.m_tiles_b * p.n_tiles;
   // forward-epilogue parameters that do not change from step to step
   TcParams pf{};
   pf.K = p.K, pf.C = p.C, pf.cpt = p.cpt, pf.D = p.D, pf.ld = p.ld, pf.q = p.q, pf.nrows = p.batch;
@@ -306,11 +326,13 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
                 }
             }
         for (int w = blockIdx.x; w < items_f; w += gridDim.x) {
-          const int mt = w / p.n_tiles, nt = w % p.n_tiles;
-          produce(&tmXa_hi, &tmXa_lo, &tmWt_hi, &tmWt_lo, p.k_chunks_f, 0, BK, (int)row0 + mt * BM, 0, 0, BK, nt * p.BN, 0);
+          const int mt = w / p.n_tiles, nt = w % p.n_tiles;  // half_f: mt counts half tiles
+          produce(&tmXa_hi, &tmXa_lo, &tmWt_hi, &tmWt_lo, p.k_chunks_f, 0, BK, (int)row0 + mt * f_rows, 0, 0, BK, nt * p.BN, 0,
+                  p.half_f ? a_bytes / 2 : a_bytes);
         }
       }
     } else if (warp == 1) {
+      which_phase = 0;
       for (int w = blockIdx.x; w < items_f; w += gridDim.x) issue(p.k_chunks_f);
     } else if (warp >= 4) {
       pf.labels = p.labels + row0;
@@ -322,7 +344,8 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
         mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
-        fwd_epilogue_tile<KP, EW, true>(pf, tacc, mt, nt, part, lane, t);
+        if (p.half_f) fwd_epilogue_tile<KP, EW, true>(pf, tacc, mt >> 1, nt, part, lane, t, (mt & 1) * (BM / 2), BM / 2);
+        else fwd_epilogue_tile<KP, EW, true>(pf, tacc, mt, nt, part, lane, t);
         tcgen05_fence_before();
         mbar_arrive(smem_u32(&bar_tempty[buf]));
       }
@@ -340,17 +363,18 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
               const int mt = w / p.n_tiles;
               for (int k = 0; k < p.k_chunks_f; ++k)
                 for (int h = 0; h <= p.pair; ++h) {
-                  tma_prefetch_2d(&tmXa_hi, k * BK, (int)(row0 + p.batch) + mt * BM + h * (BM / 2));
-                  if (na == 2) tma_prefetch_2d(&tmXa_lo, k * BK, (int)(row0 + p.batch) + mt * BM + h * (BM / 2));
+                  tma_prefetch_2d(&tmXa_hi, k * BK, (int)(row0 + p.batch) + mt * f_rows + h * (BM / 2));
+                  if (na == 2) tma_prefetch_2d(&tmXa_lo, k * BK, (int)(row0 + p.batch) + mt * f_rows + h * (BM / 2));
                 }
             }
         for (int w = blockIdx.x; w < items_b; w += gridDim.x) {
           const int mt = w / p.n_tiles, nt = w % p.n_tiles;
           produce(&tmXt_hi, &tmXt_lo, &tmDm_hi, &tmDm_lo, k_chunks_b, 0, 0, slab0 * p.xt_rows + mt * BM, p.xt_rows, 0, 0,
-                  nt * p.BN, p.dm_rows);
+                  nt * p.BN, p.dm_rows, a_bytes);
         }
       }
     } else if (warp == 1) {
+      which_phase = 1;
       for (int w = blockIdx.x; w < items_b; w += gridDim.x) issue(k_chunks_b);
     } else if (warp >= 4) {
       const float eps = p.eps[step];
@@ -373,6 +397,10 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   if (timer) {
     long long* o = p.prof + (size_t)blockIdx.x * 8;
     o[0] = tF, o[1] = tW1, o[2] = tB, o[3] = tW2, o[4] = p.n_steps;
+  }
+  if (p.prof && warp == 1 && lane == 0) {  // MMA warp: operand waits / total per phase, packed (wait << 32 | total), in k-cycles... plain sums
+    long long* o = p.prof + (size_t)blockIdx.x * 8;
+    o[5] = mma_wait[0], o[6] = mma_all[0], o[7] = mma_wait[1];
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -468,10 +496,20 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   const int items_all = std::max((int)(Mfwd / BM) * n_tiles, (int)ceil_div(d.Dt, BM) * n_tiles);
   const int grid_all = std::min(items_all, ctx->sm_count);
   const bool pair = pair_env && n_tiles % 2 == 0 && grid_all % 2 == 0 && grid_all >= 2;
+  // half row tiles in the forward phase (default): at cfg3 the phase has 64 items for 148 SMs and each is bound by what
+  // one SM ingests per chunk (32 KB of X hi/lo + 20 KB of W^T); half tiles make 128 items of 16 + 20 KB
+  static int half_env = -1;
+  if (half_env < 0) {
+    const char* e = getenv("BHMC_PERSIST_HALF");
+    half_env = e ? atoi(e) : 0;  // measured: 128 items of 36 KB per chunk take as long as 64 items of 52 KB (phase F 20.1 k vs
+                                 // 19.5-22 k cycles; 4.17 vs 4.14-4.22 M grad-evals/s) -- see the note on the MMA warp below
+  }
+  const bool half_f = half_env && !pair && 2 * (int)(Mfwd / BM) * n_tiles <= ctx->sm_count;
   const uint32_t abox = pair ? BM / 2 : BM;
-  BHMC_TRY(make_map(&maps[0], d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox));
+  const uint32_t abox_f = (pair || half_f) ? BM / 2 : BM;
+  BHMC_TRY(make_map(&maps[0], d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox_f));
   maps[1] = maps[0];
-  if (smode == 1) BHMC_TRY(make_map(&maps[1], d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox));
+  if (smode == 1) BHMC_TRY(make_map(&maps[1], d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox_f));
   BHMC_TRY(make_map(&maps[2], wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
   maps[3] = maps[2];
   if (split3) BHMC_TRY(make_map(&maps[3], wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
@@ -501,7 +539,8 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   p.dm_rows = (int)dm_rows, p.xt_rows = (int)d.Dt_pad;
   p.bar = (unsigned int*)bar;
   p.pair = pair ? 1 : 0;
-  const int items = std::max((int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles);
+  p.half_f = half_f ? 1 : 0;
+  const int items = std::max((half_f ? 2 : 1) * (int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles);
   const int grid = std::min(items, ctx->sm_count);
   static int want_prof = -1, want_pf = -1;
   if (want_prof < 0) want_prof = getenv("BHMC_PROF") ? 1 : 0;
@@ -532,6 +571,15 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
     BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     double s[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0}, mn[4] = {1e30, 1e30, 1e30, 1e30};
     int n = 0;
+    {  // MMA warp of the CTAs that own a forward item: operand wait and total per step in phase F, operand wait in phase B
+      double w0 = 0, a0 = 0, w1 = 0;
+      int m = 0;
+      for (int b = 0; b < grid && b < 148; ++b)
+        if (hp[b * 8 + 6] > 0) w0 += (double)hp[b * 8 + 5], a0 += (double)hp[b * 8 + 6], w1 += (double)hp[b * 8 + 7], ++m;
+      if (m)
+        fprintf(stderr, "[bhmc prof persist] MMA warp (%d CTAs with forward items), cycles per step: phase F operand wait %.0f of %.0f, phase B operand wait %.0f\n",
+                m, w0 / m / n_steps, a0 / m / n_steps, w1 / m / n_steps);
+    }
     for (int b = 0; b < grid && b < 148; ++b) {
       if (hp[b * 8 + 4] <= 0) continue;
       ++n;

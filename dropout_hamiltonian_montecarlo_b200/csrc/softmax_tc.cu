@@ -130,11 +130,14 @@ __device__ __forceinline__ float lg2_approx(float x) {
 // sum, P - Y split to bf16 hi/lo and stored transposed, z_y - logsumexp warp-reduced into one fp64 red.
 template <int KP, int EW, bool EXACT, bool FROM_Z = false>
 __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t tacc, int mt, int nt, int part, int lane,
-                                                  int t) {
+                                                  int t, int row_shift = 0, int live = BM) {
+  // (row_shift, live): the accumulator holds only `live` rows, those of window rows mt*BM + row_shift + (0..live-1) -- the
+  // half tiles of the persistent minibatch kernel (live = 64: the warps of TMEM lanes 64..127 only do the zero fill)
   constexpr int PARTS = EW / 4;
   const float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-  const int64_t r = (int64_t)mt * BM + t;  // row inside the window
-  const bool valid = r < p.nrows;
+  const int64_t r = (int64_t)mt * BM + row_shift + t;  // row inside the window
+  const bool alive = t < live;                          // warp-uniform (live is a multiple of 32)
+  const bool valid = alive && r < p.nrows;
   const int y = valid ? p.labels[r] : -1;
   const int K = EXACT ? KP : p.K;  // EXACT: no padded classes, every class loop is branch-free
   // DmT position of this thread's row (chain-independent part): slab, column inside the slab
@@ -145,8 +148,9 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
     const int c = nt * p.cpt + cc;
     if (c >= p.C) break;  // warp-uniform
     const float* bias = p.q + (int64_t)c * p.ld + (int64_t)p.D * K;
-    float ll;
-    if constexpr (KP >= 24 && !FROM_Z) {
+    float ll = 0.f;
+    if (!alive) {
+    } else if constexpr (KP >= 24 && !FROM_Z) {
       // Wide class counts (KP = 24 / 40 / 64; cfg5 has K = 38): holding a whole row of logits (+ exps) per thread does
       // not fit the 96-register budget of the 640-thread CTA and spilled (ptxas: 80-156 B at KP = 40, ~900 B at
       // KP = 64).  Tensor memory is cheap to re-read, so the row is walked three times in 8-column pieces instead:
@@ -290,8 +294,9 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
       // zero what the backward chunks read but no row writes: the alignment prefix (columns before the window) and
       // the columns between the last tile row and the end of the last BK-chunk
       int zc = -1;
-      if (mt == 0 && t < p.dm_shift) zc = t;  // dm_shift, dm_tail < 64: threads 0..63 / 64..127 of the tile
-      else if (mt == p.m_tiles - 1 && t >= 64 && t - 64 < p.dm_tail) zc = p.dm_shift + p.m_tiles * BM + (t - 64);
+      if (mt == 0 && row_shift == 0 && t < p.dm_shift) zc = t;  // dm_shift, dm_tail < 64: threads 0..63 / 64..127 of the tile
+      else if (mt == p.m_tiles - 1 && (live == BM || row_shift != 0) && t >= 64 && t - 64 < p.dm_tail)
+        zc = p.dm_shift + p.m_tiles * BM + (t - 64);
       if (zc >= 0) {
         const int zs = zc / p.dm_slab;
         const int64_t zo = (zs * p.dm_slab_rows + (int64_t)c * KP) * p.dm_ld + (zc - zs * p.dm_slab);
