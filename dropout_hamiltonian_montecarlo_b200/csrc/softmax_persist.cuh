@@ -43,6 +43,8 @@ struct PersistParams {
   int dm_rows;                    // rows per (P-Y)^T slab = n_tiles * BN
   int xt_rows;                    // rows per X^T slab (Dt_pad)
   unsigned int* bar;              // grid barrier counter (zeroed before the launch)
+  unsigned int* flags;            // [2][n_tiles] monotonic item counters per chain tile (forward / backward), zeroed before the
+                                  // launch; nullptr = grid-wide barriers between the phases (BHMC_PERSIST_FLAGS=0)
   int half_f;                     // forward items are HALF row tiles (64 rows of the window): twice the items, 36 KB instead of
                                   // 52 KB per chunk and item; the MMA stays M = 128, the upper accumulator half is ignored
   int pair;                       // clusters of two CTAs work on the same row / feature tile and adjacent chain tiles: each
@@ -76,6 +78,34 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   }
   __syncthreads();
   fence_proxy_async_all();
+}
+
+// Per-chain-tile dependencies instead of grid-wide barriers (round 2).  Chain tiles never exchange data: the backward items
+// of chain tile nt need the (P-Y)^T rows of ITS forward items only, and the next step's forward items of nt need the W^T
+// rows / bias of ITS backward items only.  Every finished item bumps a counter of its chain tile; the TMA producer of a
+// dependent item waits for the count of the step.  Same fences as the grid barrier (generic stores -> TMA reads).
+__device__ __forceinline__ void flag_wait(const unsigned int* f, unsigned int target) {  // one thread
+  const long long t0 = clock64();
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v >= target) break;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("bhmc: chain-tile flag timed out (block %d, %u of %u)\n", blockIdx.x, v, target);
+      __trap();
+    }
+  }
+  fence_proxy_async_all();
+}
+// all 32 * EW epilogue threads of the CTA call it after the item's last store
+template <int EW>
+__device__ __forceinline__ void flag_signal(unsigned int* f) {
+  fence_proxy_async_all();
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+  if (threadIdx.x == NON_EPI_THREADS) {
+    __threadfence();
+    atomicAdd(f, 1u);
+  }
 }
 
 // Update epilogue of one backward tile.  Tensor memory hands a thread one gradient ROW (feature d; d == D is the bias
@@ -327,6 +357,7 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
             }
         for (int w = blockIdx.x; w < items_f; w += gridDim.x) {
           const int mt = w / p.n_tiles, nt = w % p.n_tiles;  // half_f: mt counts half tiles
+          if (p.flags && step > 0) flag_wait(p.flags + p.n_tiles + nt, (unsigned int)(p.m_tiles_b * step));  // W^T / bias of step - 1
           produce(&tmXa_hi, &tmXa_lo, &tmWt_hi, &tmWt_lo, p.k_chunks_f, 0, BK, (int)row0 + mt * f_rows, 0, 0, BK, nt * p.BN, 0,
                   p.half_f ? a_bytes / 2 : a_bytes);
         }
@@ -348,10 +379,11 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
         else fwd_epilogue_tile<KP, EW, true>(pf, tacc, mt, nt, part, lane, t);
         tcgen05_fence_before();
         mbar_arrive(smem_u32(&bar_tempty[buf]));
+        if (p.flags) flag_signal<EW>(p.flags + nt);
       }
     }
     if (timer) { const long long t = clock64(); tF += t - t_prev; t_prev = t; }
-    grid_barrier(p.bar, ++n_bar * gridDim.x);
+    if (!p.flags) grid_barrier(p.bar, ++n_bar * gridDim.x);
     if (timer) { const long long t = clock64(); tW1 += t - t_prev; t_prev = t; }
     // ---------------- phase B: G = X_window^T (P - Y), update, next W^T operand ----------------
     if (warp == 0) {
@@ -369,6 +401,7 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
             }
         for (int w = blockIdx.x; w < items_b; w += gridDim.x) {
           const int mt = w / p.n_tiles, nt = w % p.n_tiles;
+          if (p.flags) flag_wait(p.flags + nt, (unsigned int)((items_f / p.n_tiles) * (step + 1)));  // (P-Y)^T of this step
           produce(&tmXt_hi, &tmXt_lo, &tmDm_hi, &tmDm_lo, k_chunks_b, 0, 0, slab0 * p.xt_rows + mt * BM, p.xt_rows, 0, 0,
                   nt * p.BN, p.dm_rows, a_bytes);
         }
@@ -388,10 +421,11 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
         else sg_update_tile<KP, EW, BHMC_KIND_SGD>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S);
         tcgen05_fence_before();
         mbar_arrive(smem_u32(&bar_tempty[buf]));
+        if (p.flags) flag_signal<EW>(p.flags + p.n_tiles + nt);
       }
     }
     if (timer) { const long long t = clock64(); tB += t - t_prev; t_prev = t; }
-    grid_barrier(p.bar, ++n_bar * gridDim.x);
+    if (!p.flags) grid_barrier(p.bar, ++n_bar * gridDim.x);
     if (timer) { const long long t = clock64(); tW2 += t - t_prev; t_prev = t; }
   }
   if (timer) {
@@ -471,8 +505,9 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   const size_t wt_bytes = (size_t)ncols * d.Dp * 2, dmt_bytes = (size_t)(dm_nslab * dm_rows * BK) * 2;
   BHMC_TRY(ctx->get_scratch(1, wt_bytes * 2, &wt));
   BHMC_TRY(ctx->get_scratch(2, dmt_bytes * 2, &dmt));
-  BHMC_TRY(ctx->get_scratch(13, 256, &bar));
-  BHMC_CUDA_OK(cudaMemsetAsync(bar, 0, 256, ctx->stream));
+  const size_t bar_bytes = 256 + sizeof(unsigned int) * 2 * (size_t)n_tiles;  // grid-barrier counter | chain-tile item counters
+  BHMC_TRY(ctx->get_scratch(13, bar_bytes, &bar));
+  BHMC_CUDA_OK(cudaMemsetAsync(bar, 0, bar_bytes, ctx->stream));
   __nv_bfloat16* wt_hi = (__nv_bfloat16*)wt;
   __nv_bfloat16* wt_lo = (__nv_bfloat16*)((char*)wt + wt_bytes);
   {  // operand copy of the start point (later steps write it from the update epilogue)
@@ -540,6 +575,12 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   p.bar = (unsigned int*)bar;
   p.pair = pair ? 1 : 0;
   p.half_f = half_f ? 1 : 0;
+  static int flags_env = -1;
+  if (flags_env < 0) {
+    const char* e = getenv("BHMC_PERSIST_FLAGS");
+    flags_env = e ? atoi(e) : 1;
+  }
+  p.flags = flags_env ? reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(bar) + 256) : nullptr;
   const int items = std::max((half_f ? 2 : 1) * (int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles);
   const int grid = std::min(items, ctx->sm_count);
   static int want_prof = -1, want_pf = -1;
