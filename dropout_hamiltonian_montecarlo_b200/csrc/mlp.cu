@@ -31,6 +31,7 @@ static constexpr int TM = 64, TN = 64, TK = 16;
 
 // tc_bgemm.cu: the same GEMM + epilogue on the tensor cores (bf16 hi/lo split or single bf16 pass)
 int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3);
+int tc_bgemm_two(bhmc_ctx* ctx, const GemmDesc& d0, const GemmDesc& d1, int batch, bool split3);
 int tc_split_rows(bhmc_ctx* ctx, const float* src, int64_t sb, int64_t rs, int64_t cs, int R, int K, int64_t Kp, int Z,
                   __nv_bfloat16* hi, __nv_bfloat16* lo);
 
@@ -929,8 +930,8 @@ struct MlpModel : ModelBase {
     if (fuse) out_k(d, dA2k);  // its transposed copy (for gW2) stays a split launch: see k_mlp_gemm_small_k
     BHMC_TRY(run_gemm(ctx, d, C));
     }
-    auto do_gW2 = [&]() -> int {  // gW2 = dA2^T H1 + alpha/2 W2 ; gb2
-      GemmDesc d = base();
+    auto make_gW2 = [&](GemmDesc& d) {  // gW2 = dA2^T H1 + alpha/2 W2 ; gb2
+      d = base();
       d.A = dA2, d.a_batch = act, d.a_rs = 1, d.a_cs = n_mid;
       d.B = H1, d.b_batch = act, d.b_rs = n_mid, d.b_cs = 1;
       d.C = g + oW2, d.c_batch = ld, d.c_rs = n_mid;
@@ -942,12 +943,16 @@ struct MlpModel : ModelBase {
         d.upd_on = 1, d.upd_off = oW2, d.upd = *fused_upd;
         d.ct_hi = w2t, d.ct_lo = split3 ? w2t + w2t_lo : nullptr, d.ct_batch = e_w2t, d.ct_ld = kp_mid;
       }
+    };
+    auto do_gW2 = [&]() -> int {
+      GemmDesc d;
+      make_gW2(d);
       BHMC_TRY(run_gemm(ctx, d, C));
       if (!head) k_mlp_colsum<<<dim3((unsigned)ceil_div(n_mid, 32), C), 1024, 0, ctx->stream>>>(dA2, B, n_mid, act, q, ld, ob2, ha, g, UpdOpt{});
       return BHMC_OK;
     };
-    auto do_dA1 = [&]() -> int {  // dA1 = (dA2 W2) * [H1 > 0] / keep
-      GemmDesc d = base();
+    auto make_dA1 = [&](GemmDesc& d) {  // dA1 = (dA2 W2) * [H1 > 0] / keep
+      d = base();
       d.A = dA2, d.a_batch = act, d.a_rs = n_mid, d.a_cs = 1;
       d.B = q + oW2, d.b_batch = ld, d.b_rs = n_mid, d.b_cs = 1;
       d.C = dA1, d.c_batch = act, d.c_rs = n_mid;
@@ -958,6 +963,10 @@ struct MlpModel : ModelBase {
         out_t(d, dA1t);
       }
       if (w2t_ok) d.b_hi = w2t, d.b_lo = split3 ? w2t + w2t_lo : nullptr, d.b_kp = kp_mid;  // written by the previous fused evaluation
+    };
+    auto do_dA1 = [&]() -> int {
+      GemmDesc d;
+      make_dA1(d);
       BHMC_TRY(run_gemm(ctx, d, C));
       return BHMC_OK;
     };
@@ -965,6 +974,12 @@ struct MlpModel : ModelBase {
     if (fu) {
       BHMC_TRY(do_dA1());
       BHMC_TRY(do_gW2());
+    } else if (use_tc && head && n_mid >= 64 && B >= 64) {
+      // both on the tensor cores and independent of each other: one grouped launch (tc_bgemm_two; BHMC_BG_GROUP=0: two)
+      GemmDesc d0, d1;
+      make_gW2(d0);
+      make_dA1(d1);
+      BHMC_TRY(tc_bgemm_two(ctx, d0, d1, C, split3));
     } else {
       BHMC_TRY(do_gW2());
       BHMC_TRY(do_dA1());

@@ -638,6 +638,142 @@ k_tc_bgemm2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Two independent batched GEMMs in ONE launch (round 2).  At cfg4 a GEMM is 256 tiles for 148 CTAs: 1.7 tiles per CTA, so
+// its launch ramp, pipeline fill and the exposed epilogue of the last tile are paid per GEMM.  gW2 = dA2^T H1 and
+// dA1 = dA2 W2 * gate depend on the same inputs and not on each other: as one work list of 512 tiles a CTA runs 3-4 tiles
+// back to back (every epilogue but the last under the next main loop) and one ramp is gone.  Same tile code as k_tc_bgemm;
+// the two problems must agree on BN, pipeline depth, split mode and epilogue form (the host checks).
+struct BgGroup {
+  CUtensorMap m[2][4];  // A_hi, A_lo, B_hi, B_lo of each problem
+  BgParams p[2];
+  int work0;            // work items of problem 0 (they come first in the list)
+  int work;             // all work items
+};
+
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1) k_tc_bgemm_grp(const __grid_constant__ BgGroup g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = g.p[0].BN, stages = g.p[0].stages, split3 = g.p[0].split3;
+  const int a_bytes = BM * BK * 2, b_bytes = BN * BK * 2;
+  const int nmat = split3 ? 2 : 1;
+  const int stage_bytes = nmat * (a_bytes + b_bytes);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_launch_dependents();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < g.work; w += gridDim.x) {
+        const int pi = w >= g.work0 ? 1 : 0;
+        const BgParams& p = g.p[pi];
+        const int wl = w - (pi ? g.work0 : 0), tiles = p.m_tiles * p.n_tiles;
+        const int z = wl / tiles, rem = wl % tiles, mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+        const int za = p.a_shared ? 0 : z, zb = p.b_shared ? 0 : z;
+        for (int k = 0; k < p.k_chunks; ++k) {
+          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          mbar_expect_tx(full, (uint32_t)stage_bytes);
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + nmat * a_bytes;
+          tma_load_3d(sa, &g.m[pi][0], full, k * BK, mt * BM, za);
+          if (split3) tma_load_3d(sa + a_bytes, &g.m[pi][1], full, k * BK, mt * BM, za);
+          tma_load_3d(sb, &g.m[pi][2], full, k * BK, nt * BN, zb);
+          if (split3) tma_load_3d(sb + b_bytes, &g.m[pi][3], full, k * BK, nt * BN, zb);
+          if (++stage == stages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < g.work; w += gridDim.x, ++it) {
+      const int k_chunks = g.p[w >= g.work0 ? 1 : 0].k_chunks;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+      for (int k = 0; k < k_chunks; ++k) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        const uint32_t first = k > 0 ? 1u : 0u;
+        if (split3) {
+          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+          const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+        } else {
+          const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+          }
+        }
+        umma_commit(smem_u32(&bar_empty[stage]));
+        if (++stage == stages) stage = 0, phase ^= 1u;
+      }
+      umma_commit(smem_u32(&bar_tfull[buf]));
+    }
+  } else if (warp >= 4) {
+    const int ew = warp & 3, part = (warp - 4) >> 2;
+    float4* blk = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)) + stages * stage_bytes) + (warp - 4) * 128;
+    int it = 0;
+    for (int w = blockIdx.x; w < g.work; w += gridDim.x, ++it) {
+      const int pi = w >= g.work0 ? 1 : 0;
+      const BgParams& p = g.p[pi];
+      const int wl = w - (pi ? g.work0 : 0), tiles = p.m_tiles * p.n_tiles;
+      const int z = wl / tiles, rem = wl % tiles, mt = rem / p.n_tiles, nt = rem % p.n_tiles;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+      bg_epilogue_tile2<false>(p, tacc, z, mt, nt, part, lane, blk, smem_u32(&bar_tfull[buf]), use & 1u);
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(&bar_tempty[buf]));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 // dst_{hi,lo}[z][r][k] (k < Kp contiguous, Kp % 64 == 0) = split(src[z*sb + r*rs + k*cs]) for k < K, 0 for K <= k < Kp.
 // One 32 (rows) x 64 (k) tile per block through shared memory, so both cs == 1 (row-major source) and rs == 1
 // (transposed source) read coalesced; every thread writes a bf16 pair (128 B per warp and row).
@@ -769,9 +905,18 @@ int tc_split_rows(bhmc_ctx* ctx, const float* src, int64_t sb, int64_t rs, int64
   return BHMC_OK;
 }
 
-// C[z] = epilogue(A[z] . B[z]) for z < batch, operands described by d (fp32, arbitrary strides).
-// scratch slots 1..2 of the context hold the bf16 operand copies.
-int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
+// Preparation of one batched GEMM; scratch slots 1..2 of the context hold the bf16 operand copies that are not handed in.
+struct BgLaunch {  // one prepared batched GEMM: operand copies made, tensor maps encoded, kernel parameters filled
+  CUtensorMap m[4];
+  BgParams p;
+  size_t smem;
+  int work, grid;
+  bool pair, upd;
+  bool used_a, used_b;  // the A / B operand copy lives in scratch slot 1 / 2 of the context (valid until the next prepare)
+};
+static int bg_launch(bhmc_ctx* ctx, const BgLaunch& L);
+
+static int bg_prepare(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3, BgLaunch* L) {
   const int64_t Kp = round_up(d.K, 64);
   const bool a_shared = d.a_batch == 0, b_shared = d.b_batch == 0;
   const int za = a_shared ? 1 : batch, zb = b_shared ? 1 : batch;
@@ -893,7 +1038,7 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
     return BHMC_ERR_STATE;
   }
   p.stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024 - (p.epi2 ? epi_bytes : 0)) / stage_bytes)));
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  CUtensorMap &mA_hi = L->m[0], &mA_lo = L->m[1], &mB_hi = L->m[2], &mB_lo = L->m[3];
   const uint64_t a_pitch = a_pre ? (uint64_t)d.a_kp : (uint64_t)Kp, b_pitch = b_pre ? (uint64_t)d.b_kp : (uint64_t)Kp;
   const uint64_t a_zs = a_pre ? (uint64_t)d.a_zs : 0, b_zs = b_pre ? (uint64_t)d.b_zs : 0;
   BHMC_TRY(make_map3(&mA_hi, a_hi, (uint64_t)d.K, (uint64_t)d.M, (uint64_t)za, a_pitch, BM, a_zs));
@@ -905,7 +1050,30 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
     mA_lo = mA_hi;
     mB_lo = mB_hi;
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (p.epi2 ? epi_bytes : 0);
+  L->smem = (size_t)p.stages * stage_bytes + 1024 + (p.epi2 ? epi_bytes : 0);
+  L->work = batch * (pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  L->grid = pair ? 2 * std::min(L->work, ctx->sm_count / 2) : std::min(L->work, ctx->sm_count);
+  L->pair = pair;
+  L->upd = d.upd_on != 0;
+  L->used_a = !a_pre, L->used_b = !b_pre;
+  L->p = p;
+  return BHMC_OK;
+}
+
+static bool pdl_mlp_enabled() {
+  // programmatic dependent launch of the batched GEMM: its prologue runs under the split kernel in front of it
+  // (MLP parity tests green with it; cfg4 43.8 k -> 45.4 k grad-evals/s in one A/B pair).  BHMC_PDL_MLP=0: plain launch.
+  static int pdl_env = -1;
+  if (pdl_env < 0) {
+    const char* e = getenv("BHMC_PDL_MLP");
+    pdl_env = e ? atoi(e) : 1;
+  }
+  return pdl_env != 0;
+}
+
+static int bg_launch(bhmc_ctx* ctx, const BgLaunch& L) {
+  const bool pair = L.pair;
+  const size_t smem = L.smem;
   static size_t configured = 0, configured2 = 0;
   if (!pair && smem > configured) {
     BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -917,17 +1085,8 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
     BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured2 = smem;
   }
-  const int work = batch * (pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
-  const int grid = pair ? 2 * std::min(work, ctx->sm_count / 2) : std::min(work, ctx->sm_count);
-  // programmatic dependent launch of the batched GEMM: its prologue runs under the split kernel in front of it
-  // (MLP parity tests green with it; cfg4 43.8 k -> 45.4 k grad-evals/s in one A/B pair).  BHMC_PDL_MLP=0: plain launch.
-  static int pdl_env = -1;
-  if (pdl_env < 0) {
-    const char* e = getenv("BHMC_PDL_MLP");
-    pdl_env = e ? atoi(e) : 1;
-  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
+  cfg.gridDim = dim3((unsigned)L.grid);
   cfg.blockDim = dim3(NON_EPI_THREADS + 32 * EW);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
@@ -940,7 +1099,7 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_env) {
+  if (pdl_mlp_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -948,10 +1107,77 @@ int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
   cfg.attrs = attr;
   cfg.numAttrs = na;
   // the instantiation with the fused sampler update carries Philox / Box-Muller code in its epilogue: only where asked for
-  if (pair) BHMC_CUDA_OK(d.upd_on ? cudaLaunchKernelEx(&cfg, k_tc_bgemm2<true>, mA_hi, mA_lo, mB_hi, mB_lo, p)
-                                  : cudaLaunchKernelEx(&cfg, k_tc_bgemm2<false>, mA_hi, mA_lo, mB_hi, mB_lo, p));
-  else BHMC_CUDA_OK(d.upd_on ? cudaLaunchKernelEx(&cfg, k_tc_bgemm<true>, mA_hi, mA_lo, mB_hi, mB_lo, p)
-                             : cudaLaunchKernelEx(&cfg, k_tc_bgemm<false>, mA_hi, mA_lo, mB_hi, mB_lo, p));
+  if (pair) BHMC_CUDA_OK(L.upd ? cudaLaunchKernelEx(&cfg, k_tc_bgemm2<true>, L.m[0], L.m[1], L.m[2], L.m[3], L.p)
+                               : cudaLaunchKernelEx(&cfg, k_tc_bgemm2<false>, L.m[0], L.m[1], L.m[2], L.m[3], L.p));
+  else BHMC_CUDA_OK(L.upd ? cudaLaunchKernelEx(&cfg, k_tc_bgemm<true>, L.m[0], L.m[1], L.m[2], L.m[3], L.p)
+                          : cudaLaunchKernelEx(&cfg, k_tc_bgemm<false>, L.m[0], L.m[1], L.m[2], L.m[3], L.p));
+  ctx->launches++;
+  BHMC_CUDA_OK(cudaGetLastError());
+  return BHMC_OK;
+}
+
+// C[z] = epilogue(A[z] . B[z]) for z < batch, operands described by d (fp32, arbitrary strides).
+int tc_bgemm(bhmc_ctx* ctx, const GemmDesc& d, int batch, bool split3) {
+  BgLaunch L;
+  BHMC_TRY(bg_prepare(ctx, d, batch, split3, &L));
+  return bg_launch(ctx, L);
+}
+
+// Two GEMMs that do not depend on each other: one grouped launch when their tile geometry agrees (k_tc_bgemm_grp), else two.
+int tc_bgemm_two(bhmc_ctx* ctx, const GemmDesc& d0, const GemmDesc& d1, int batch, bool split3) {
+  // Measured at cfg4 (16 chains): the grouped launch takes 45.4 us where the two launches take 22.2 + 24.5 us, and the step
+  // gets 2.4 % SLOWER (62.8 vs 64.4 k grad-evals/s): with 3-4 tiles per CTA the epilogues do run under the next main loop,
+  // but they contend with it (global loads / stores and the shared-memory port) instead of hiding behind it.  Off by default.
+  static int grp_env = -1;  // BHMC_BG_GROUP=1: one grouped launch
+  if (grp_env < 0) {
+    const char* e = getenv("BHMC_BG_GROUP");
+    grp_env = e ? atoi(e) : 0;
+  }
+  BgLaunch L0, L1;
+  BHMC_TRY(bg_prepare(ctx, d0, batch, split3, &L0));
+  {
+    // the second preparation must not overwrite an operand copy of the first in the shared scratch slots
+    const bool a1_scratch = !(d1.a_hi && (!split3 || d1.a_lo)), b1_scratch = !(d1.b_hi && (!split3 || d1.b_lo));
+    if (!grp_env || (L0.used_a && a1_scratch) || (L0.used_b && b1_scratch)) {
+      BHMC_TRY(bg_launch(ctx, L0));
+      return tc_bgemm(ctx, d1, batch, split3);
+    }
+  }
+  BHMC_TRY(bg_prepare(ctx, d1, batch, split3, &L1));
+  if ((L0.used_a && L1.used_a) || (L0.used_b && L1.used_b)) {
+    set_error("grouped GEMM launch: both problems claimed the same operand scratch slot");
+    return BHMC_ERR_STATE;
+  }
+  const bool ok = grp_env && !L0.pair && !L1.pair && !L0.upd && !L1.upd && L0.p.epi2 && L1.p.epi2 && L0.p.BN == L1.p.BN &&
+                  L0.p.stages == L1.p.stages && L0.p.split3 == L1.p.split3 && L0.smem == L1.smem;
+  if (!ok) {
+    BHMC_TRY(bg_launch(ctx, L0));
+    return bg_launch(ctx, L1);
+  }
+  static BgGroup g;  // 3 KB: filled per call, passed by value to the launch
+  for (int i = 0; i < 4; ++i) g.m[0][i] = L0.m[i], g.m[1][i] = L1.m[i];
+  g.p[0] = L0.p, g.p[1] = L1.p;
+  g.work0 = L0.work, g.work = L0.work + L1.work;
+  static size_t configured = 0;
+  if (L0.smem > configured) {
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_tc_bgemm_grp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.smem));
+    configured = L0.smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)std::min(g.work, ctx->sm_count));
+  cfg.blockDim = dim3(NON_EPI_THREADS + 32 * EW);
+  cfg.dynamicSmemBytes = L0.smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_mlp_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_bgemm_grp, g));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
