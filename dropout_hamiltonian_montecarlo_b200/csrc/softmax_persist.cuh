@@ -368,6 +368,7 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
     } else if (warp >= 4) {
       pf.labels = p.labels + row0;
       pf.dm_shift = shift;
+      pf.pack_dm = 0;  // (row-pair stores of (P-Y)^T: BHMC_FWD_PACK in the per-launch path, measured neutral)
       pf.dm_tail = (BK - shift) % BK;
       for (int w = blockIdx.x; w < items_f; w += gridDim.x, ++it) {
         const int mt = w / p.n_tiles, nt = w % p.n_tiles;

@@ -97,6 +97,7 @@ struct TcParams {
   // evaluation after a sub-step that moved only the bias rebuilds softmax / (P-Y)^T / log-lik from it (k_softmax_from_z)
   float* zt;
   int zt_slab_rows;
+  int pack_dm;                    // forward epilogue: 4-byte (row pair) stores of (P-Y)^T (dm_shift even, dm_ld even; BHMC_FWD_PACK)
   int dm_shift;                   // DmT column of window row 0 (row0 % BK: backward chunks start on absolute multiples of BK)
   __nv_bfloat16* dmt_hi;
   __nv_bfloat16* dmt_lo;          // nullptr in single-pass mode
@@ -275,6 +276,34 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
       ll = valid ? ((zy - m) - LN2 * lg2_approx(ssum)) : 0.f;  // z_y - logsumexp(z)
       if (p.write_dm) {
         const int64_t o = dm_off + (int64_t)c * KP * p.dm_ld;
+        if (!FROM_Z && KP % 2 == 0 && p.pack_dm) {
+          // Rows r and r + 1 (lanes l, l ^ 1; r even) are neighbours in the transposed layout: one 4-byte store per class and
+          // copy instead of two 2-byte stores.  A lane pair exchanges (hi | lo << 16) words -- the even lane stores the even
+          // classes, the odd lane the odd ones -- so the store instructions of the epilogue halve (they share the
+          // L1 / shared-memory port with the operand traffic of the main loop).  Needs an even dm_shift (host).
+          const bool odd = lane & 1;
+          const int64_t oe = o - (odd ? 1 : 0);  // the even row's column
+#pragma unroll
+          for (int k0 = 0; k0 < KP; k0 += 2) {
+            uint32_t pk[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int k = k0 + j;
+              const float d = valid ? fmaf(z[k], inv, (k == y) ? -1.f : 0.f) : 0.f;  // P - Y
+              const __nv_bfloat16 h = __float2bfloat16_rn(d);
+              const __nv_bfloat16 l = __float2bfloat16_rn(d - __bfloat162float(h));
+              pk[j] = (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+            }
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? pk[0] : pk[1], 1);  // the partner's word of MY class
+            const uint32_t mine = odd ? pk[1] : pk[0];
+            const uint32_t E = odd ? recv : mine, O = odd ? mine : recv;                 // even row, odd row
+            const int ks = k0 + (odd ? 1 : 0);
+            if (EXACT || ks < K) {
+              *reinterpret_cast<uint32_t*>(p.dmt_hi + oe + (int64_t)ks * p.dm_ld) = __byte_perm(E, O, 0x5410);
+              if (p.split3) *reinterpret_cast<uint32_t*>(p.dmt_lo + oe + (int64_t)ks * p.dm_ld) = __byte_perm(E, O, 0x7632);
+            }
+          }
+        } else {
         __nv_bfloat16* dh = p.dmt_hi + o;
         __nv_bfloat16* dl = p.dmt_lo + o;  // only dereferenced in split mode
 #pragma unroll
@@ -287,6 +316,7 @@ __device__ __forceinline__ void fwd_epilogue_tile(const TcParams& p, uint32_t ta
           }
           dh += p.dm_ld;
           dl += p.dm_ld;
+        }
         }
       }
     }
@@ -1921,6 +1951,16 @@ int tc_softmax_grad(bhmc_ctx* ctx, const SoftmaxData& d, const float* q, int C, 
   p.dm_slab_rows = (int)dm_rows;
   p.dm_tail = dm_tail;
   p.dm_shift = shift;
+  {
+    // measured neutral at cfg2 (forward launches 12.4 ms of a 8-step run either way, 188.2 / 187.9 k vs 188.2 / 190.4 k
+    // grad-evals/s; all 115 GPU tests pass with it): off by default
+    static int pack_env = -1;  // BHMC_FWD_PACK=1: 4-byte row-pair stores
+    if (pack_env < 0) {
+      const char* e = getenv("BHMC_FWD_PACK");
+      pack_env = e ? atoi(e) : 0;
+    }
+    p.pack_dm = (pack_env && shift % 2 == 0 && dm_ld % 2 == 0 && dm_slab % 2 == 0) ? 1 : 0;
+  }
   p.dmt_hi = dmt_hi;
   p.dmt_lo = dmt_lo;
   p.loglik = loglik;
