@@ -45,6 +45,7 @@ struct PersistParams {
   unsigned int* bar;              // grid barrier counter (zeroed before the launch)
   unsigned int* flags;            // [2][n_tiles] monotonic item counters per chain tile (forward / backward), zeroed before the
                                   // launch; nullptr = grid-wide barriers between the phases (BHMC_PERSIST_FLAGS=0)
+  int two_cta;                    // k_sg_persistent2: cta_group::2 items (needs the chain-tile flags)
   int half_f;                     // forward items are HALF row tiles (64 rows of the window): twice the items, 36 KB instead of
                                   // 52 KB per chunk and item; the MMA stays M = 128, the upper accumulator half is ignored
   int pair;                       // clusters of two CTAs work on the same row / feature tile and adjacent chain tiles: each
@@ -446,11 +447,213 @@ k_sg_persistent(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same epoch loop with cta_group::2 items (round 2, BHMC_PERSIST_2CTA).  The phases of k_sg_persistent are bound by
+// the shared-memory port (72 cycles per M = 128, N = 80 MMA: 4 KB of A + 2.5 KB of B read per MMA, plus the TMA writes of
+// the next chunks).  Here a cluster of two CTAs owns TWO adjacent row tiles (phase F) / feature tiles (phase B) of one
+// chain tile: the leader's elected thread issues tcgen05.mma.cta_group::2 (M = 256), every CTA stages its own A tile and
+// only HALF of the chain-side operand (40 of 80 rows) -- 5.25 KB read per MMA and CTA, 42 KB staged per chunk instead
+// of 52 KB.  An odd tile count gets a phantom tile (phase B: rows 896.. of X^T -- the next slab's rows or TMA zero fill --
+// whose gradient rows lie beyond the parameters and are skipped by the update).  Barrier protocol as in k_tc_fwd2;
+// dependencies between the phases through the chain-tile flags only (every CTA, phantom ones included, counts).
+template <int KP, int EW>
+__global__ void __launch_bounds__(NON_EPI_THREADS + 32 * EW, 1)
+k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_constant__ CUtensorMap tmXa_lo,
+                 const __grid_constant__ CUtensorMap tmWt_hi, const __grid_constant__ CUtensorMap tmWt_lo,
+                 const __grid_constant__ CUtensorMap tmXt_hi, const __grid_constant__ CUtensorMap tmXt_lo,
+                 const __grid_constant__ CUtensorMap tmDm_hi, const __grid_constant__ CUtensorMap tmDm_lo, const PersistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const bool leader = rank == 0;
+  const int a_bytes = BM * BK * 2, bh_bytes = (p.BN / 2) * BK * 2;  // this CTA's half of the chain-side operand
+  const int na = p.split3 == 1 ? 2 : 1, nb = p.split3 ? 2 : 1;
+  const int stage_bytes = na * a_bytes + nb * bh_bytes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 2 * 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // both CTAs' warp 2 take part in the pair-wide allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+  int p_stage = 0;  // producer
+  uint32_t p_phase = 0;
+  int m_stage = 0;  // MMA issuer (leader)
+  uint32_t m_phase = 0;
+  int m_it = 0;
+  int it = 0;       // epilogue warps
+
+  auto produce = [&](const CUtensorMap* a_hi, const CUtensorMap* a_lo, const CUtensorMap* b_hi, const CUtensorMap* b_lo,
+                     int n_chunks, int a_k0, int a_dk, int a_m0, int a_dm, int b_k0, int b_dk, int b_n0, int b_dn) {
+    for (int k = 0; k < n_chunks; ++k) {
+      mbar_wait(smem_u32(&bar_empty[p_stage]), p_phase ^ 1u);
+      const uint32_t full = smem_u32(&bar_full[p_stage]);  // same offset in the leader CTA
+      if (leader) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
+      const uint32_t sa = smem_base + p_stage * stage_bytes, sb = sa + na * a_bytes;
+      tma_load_2d_2sm(sa, a_hi, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
+      if (na == 2) tma_load_2d_2sm(sa + a_bytes, a_lo, full, a_k0 + k * a_dk, a_m0 + k * a_dm);
+      tma_load_2d_2sm(sb, b_hi, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
+      if (p.split3) tma_load_2d_2sm(sb + bh_bytes, b_lo, full, b_k0 + k * b_dk, b_n0 + k * b_dn);
+      if (++p_stage == p.stages) p_stage = 0, p_phase ^= 1u;
+    }
+  };
+  auto issue = [&](int n_chunks) {  // leader's warp 1, warp-uniform; the elected lane issues
+    const int buf = m_it & 1;
+    const uint32_t use = (uint32_t)(m_it >> 1);
+    mbar_wait(smem_u32(&bar_tempty[buf]), (use & 1u) ^ 1u);  // both CTAs' epilogues have drained this accumulator
+    tcgen05_fence_after();
+    const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TMEM_BUF_COLS);
+    for (int k = 0; k < n_chunks; ++k) {
+      mbar_wait(smem_u32(&bar_full[m_stage]), m_phase);
+      tcgen05_fence_after();
+      const uint32_t sa = smem_base + m_stage * stage_bytes;
+      const uint32_t first = k > 0 ? 1u : 0u;
+      if (p.split3 == 1) {
+        const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + a_bytes);
+        const uint64_t b_hi = make_smem_desc(sa + 2 * a_bytes), b_lo = make_smem_desc(sa + 2 * a_bytes + bh_bytes);
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+          umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+          umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_bf16_2sm(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+        }
+      } else if (p.split3 == 2) {  // X exact in bf16: no lo copy of the X operand
+        const uint64_t a_hi = make_smem_desc(sa);
+        const uint64_t b_hi = make_smem_desc(sa + a_bytes), b_lo = make_smem_desc(sa + a_bytes + bh_bytes);
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+          umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+          umma_bf16_2sm(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+        }
+      } else {
+        const uint64_t a_hi = make_smem_desc(sa), b_hi = make_smem_desc(sa + a_bytes);
+#pragma unroll
+        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+          umma_bf16_2sm(tmem_d, a_hi + adv, b_hi + adv, idesc, ks > 0 ? 1u : first);
+        }
+      }
+      umma_commit_2sm(smem_u32(&bar_empty[m_stage]), 3);  // frees the stage in both CTAs
+      if (++m_stage == p.stages) m_stage = 0, m_phase ^= 1u;
+    }
+    umma_commit_2sm(smem_u32(&bar_tfull[buf]), 3);  // accumulator halves complete in both CTAs
+    ++m_it;
+  };
+
+  const int ew = warp & 3, part = (warp - 4) >> 2, t = ew * 32 + lane;
+  float* epi_S = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes) +
+                 (warp >= 4 ? (warp - 4) * 32 * KP : 0);
+  const int m_tiles_f = (int)((p.batch + BM - 1) / BM);
+  const int pairs_f = (m_tiles_f + 1) / 2, pairs_b = (p.m_tiles_b + 1) / 2;
+  const int items_f = pairs_f * p.n_tiles, items_b = pairs_b * p.n_tiles;  // pair items
+  const int wi0 = blockIdx.x / 2, wi_step = gridDim.x / 2;
+  TcParams pf{};
+  pf.K = p.K, pf.C = p.C, pf.cpt = p.cpt, pf.D = p.D, pf.ld = p.ld, pf.q = p.q, pf.nrows = p.batch;
+  pf.dm_slab = BK, pf.dm_slab_rows = p.dm_rows, pf.dm_ld = BK, pf.dmt_hi = p.dmt_hi, pf.dmt_lo = p.dmt_lo;
+  pf.split3 = p.split3, pf.write_dm = 1, pf.m_tiles = m_tiles_f, pf.skip_loglik = 1;
+
+  for (int step = 0; step < p.n_steps; ++step) {
+    const int64_t row0 = p.row_first + (int64_t)step * p.batch;
+    const int shift = (int)(row0 % BK);
+    const int k_chunks_b = (int)((p.batch + shift + BK - 1) / BK);
+    // ---------------- phase F ----------------
+    if (warp == 0) {
+      if (lane == 0)
+        for (int w = wi0; w < items_f; w += wi_step) {
+          const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+          if (step > 0) flag_wait(p.flags + p.n_tiles + nt, (unsigned int)(2 * pairs_b * step));  // W^T / bias of step - 1
+          produce(&tmXa_hi, &tmXa_lo, &tmWt_hi, &tmWt_lo, p.k_chunks_f, 0, BK, (int)row0 + mt * BM, 0, 0, BK,
+                  nt * p.BN + rank * (p.BN / 2), 0);
+        }
+    } else if (warp == 1) {
+      if (leader)
+        for (int w = wi0; w < items_f; w += wi_step) issue(p.k_chunks_f);
+    } else if (warp >= 4) {
+      pf.labels = p.labels + row0;
+      pf.dm_shift = shift;
+      pf.dm_tail = (BK - shift) % BK;
+      for (int w = wi0; w < items_f; w += wi_step, ++it) {
+        const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+        if (mt < m_tiles_f) fwd_epilogue_tile<KP, EW, true>(pf, tacc, mt, nt, part, lane, t);
+        tcgen05_fence_before();
+        if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
+        else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
+        flag_signal<EW>(p.flags + nt);
+      }
+    }
+    // ---------------- phase B ----------------
+    if (warp == 0) {
+      if (lane == 0) {
+        const int slab0 = (int)((row0 - shift) / BK);
+        for (int w = wi0; w < items_b; w += wi_step) {
+          const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+          flag_wait(p.flags + nt, (unsigned int)(2 * pairs_f * (step + 1)));  // (P-Y)^T of this step
+          produce(&tmXt_hi, &tmXt_lo, &tmDm_hi, &tmDm_lo, k_chunks_b, 0, 0, slab0 * p.xt_rows + mt * BM, p.xt_rows, 0, 0,
+                  nt * p.BN + rank * (p.BN / 2), p.dm_rows);
+        }
+      }
+    } else if (warp == 1) {
+      if (leader)
+        for (int w = wi0; w < items_b; w += wi_step) issue(k_chunks_b);
+    } else if (warp >= 4) {
+      const float eps = p.eps[step];
+      for (int w = wi0; w < items_b; w += wi_step, ++it) {
+        const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
+        if (mt < p.m_tiles_b) {  // (a phantom tile has no gradient rows)
+          if (p.kind == BHMC_KIND_SGLD) sg_update_tile<KP, EW, BHMC_KIND_SGLD>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S);
+          else sg_update_tile<KP, EW, BHMC_KIND_SGD>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S);
+        }
+        tcgen05_fence_before();
+        if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
+        else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
+        flag_signal<EW>(p.flags + p.n_tiles + nt);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 template <int KP>
 static int launch_sg_persistent(bhmc_ctx* ctx, const CUtensorMap* maps, const PersistParams& p, int grid, size_t smem) {
   static size_t configured = 0;
   if (smem > configured) {
     BHMC_CUDA_OK(cudaFuncSetAttribute(k_sg_persistent<KP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BHMC_CUDA_OK(cudaFuncSetAttribute(k_sg_persistent2<KP, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   cudaLaunchConfig_t cfg{};
@@ -462,7 +665,7 @@ static int launch_sg_persistent(bhmc_ctx* ctx, const CUtensorMap* maps, const Pe
   attr[0].id = cudaLaunchAttributeCooperative;  // every CTA resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   int na = 1;
-  if (p.pair) {
+  if (p.pair || p.two_cta) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;
     attr[na].val.clusterDim.y = 1;
@@ -471,8 +674,12 @@ static int launch_sg_persistent(bhmc_ctx* ctx, const CUtensorMap* maps, const Pe
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_sg_persistent<KP, 16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
-                                  maps[7], p));
+  if (p.two_cta)
+    BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_sg_persistent2<KP, 16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
+                                    maps[7], p));
+  else
+    BHMC_CUDA_OK(cudaLaunchKernelEx(&cfg, k_sg_persistent<KP, 16>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
+                                    maps[7], p));
   ctx->launches++;
   BHMC_CUDA_OK(cudaGetLastError());
   return BHMC_OK;
@@ -496,7 +703,15 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   if (Mfwd / BM * n_tiles > 4 * ctx->sm_count) return BHMC_ERR_UNSUPPORTED;  // big windows: the throughput kernels win
   const int smode = split3 ? (d.x_exact ? 2 : 1) : 0;
   const int nmat = split3 ? 2 : 1, na = smode == 1 ? 2 : 1;
-  const int stage_bytes = na * BM * BK * 2 + nmat * BN * BK * 2;
+  // cta_group::2 items (k_sg_persistent2): every CTA stages half of the chain-side operand
+  static int two_env = -1;
+  if (two_env < 0) {
+    const char* e = getenv("BHMC_PERSIST_2CTA");
+    two_env = e ? atoi(e) : 1;  // measured at cfg3: 28.5-28.7 -> 25.1-25.9 us per step (4.47 -> 4.94-5.09 M grad-evals/s)
+  }
+  const int pairs_max = std::max(((int)(Mfwd / BM) + 1) / 2, ((int)ceil_div(d.Dt, BM) + 1) / 2);
+  const bool two_cta = two_env && (BN / 2) % 8 == 0 && 2 * pairs_max * n_tiles <= (ctx->sm_count & ~1);
+  const int stage_bytes = na * BM * BK * 2 + nmat * (two_cta ? BN / 2 : BN) * BK * 2;
   const size_t epi_bytes = (size_t)16 * 32 * KP * sizeof(float);  // update epilogue: one 32 x KP block per epilogue warp
   const int stages = std::max(2, std::min(MAX_STAGES, (int)((225 * 1024 - epi_bytes) / stage_bytes)));
   const size_t smem = (size_t)stages * stage_bytes + 1024 + epi_bytes;
@@ -531,7 +746,7 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
   }
   const int items_all = std::max((int)(Mfwd / BM) * n_tiles, (int)ceil_div(d.Dt, BM) * n_tiles);
   const int grid_all = std::min(items_all, ctx->sm_count);
-  const bool pair = pair_env && n_tiles % 2 == 0 && grid_all % 2 == 0 && grid_all >= 2;
+  const bool pair = !two_cta && pair_env && n_tiles % 2 == 0 && grid_all % 2 == 0 && grid_all >= 2;
   // half row tiles in the forward phase (default): at cfg3 the phase has 64 items for 148 SMs and each is bound by what
   // one SM ingests per chunk (32 KB of X hi/lo + 20 KB of W^T); half tiles make 128 items of 16 + 20 KB
   static int half_env = -1;
@@ -540,23 +755,24 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
     half_env = e ? atoi(e) : 0;  // measured: 128 items of 36 KB per chunk take as long as 64 items of 52 KB (phase F 20.1 k vs
                                  // 19.5-22 k cycles; 4.17 vs 4.14-4.22 M grad-evals/s) -- see the note on the MMA warp below
   }
-  const bool half_f = half_env && !pair && 2 * (int)(Mfwd / BM) * n_tiles <= ctx->sm_count;
+  const bool half_f = half_env && !pair && !two_cta && 2 * (int)(Mfwd / BM) * n_tiles <= ctx->sm_count;
   const uint32_t abox = pair ? BM / 2 : BM;
   const uint32_t abox_f = (pair || half_f) ? BM / 2 : BM;
   BHMC_TRY(make_map(&maps[0], d.Xa_hi, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox_f));
   maps[1] = maps[0];
   if (smode == 1) BHMC_TRY(make_map(&maps[1], d.Xa_lo, (uint64_t)d.Dp, (uint64_t)d.N, (uint64_t)d.Dp, abox_f));
-  BHMC_TRY(make_map(&maps[2], wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+  const uint32_t bbox = (uint32_t)(two_cta ? BN / 2 : BN);
+  BHMC_TRY(make_map(&maps[2], wt_hi, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, bbox));
   maps[3] = maps[2];
-  if (split3) BHMC_TRY(make_map(&maps[3], wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, (uint32_t)BN));
+  if (split3) BHMC_TRY(make_map(&maps[3], wt_lo, (uint64_t)d.Dp, (uint64_t)ncols, (uint64_t)d.Dp, bbox));
   BHMC_TRY(make_map(&maps[4], d.Xt_hi, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, abox));
   maps[5] = maps[4];
   if (smode == 1) BHMC_TRY(make_map(&maps[5], d.Xt_lo, (uint64_t)d.slab, xt_rows_total, (uint64_t)d.slab_ld, abox));
   __nv_bfloat16* dmt_hi = (__nv_bfloat16*)dmt;
   __nv_bfloat16* dmt_lo = split3 ? (__nv_bfloat16*)((char*)dmt + dmt_bytes) : nullptr;
-  BHMC_TRY(make_map(&maps[6], dmt_hi, (uint64_t)BK, (uint64_t)(dm_nslab * dm_rows), (uint64_t)BK, (uint32_t)BN));
+  BHMC_TRY(make_map(&maps[6], dmt_hi, (uint64_t)BK, (uint64_t)(dm_nslab * dm_rows), (uint64_t)BK, bbox));
   maps[7] = maps[6];
-  if (split3) BHMC_TRY(make_map(&maps[7], dmt_lo, (uint64_t)BK, (uint64_t)(dm_nslab * dm_rows), (uint64_t)BK, (uint32_t)BN));
+  if (split3) BHMC_TRY(make_map(&maps[7], dmt_lo, (uint64_t)BK, (uint64_t)(dm_nslab * dm_rows), (uint64_t)BK, bbox));
   PersistParams p{};
   p.D = D, p.K = K, p.C = C, p.cpt = cpt, p.BN = BN, p.n_tiles = n_tiles;
   p.k_chunks_f = (int)ceil_div(D, BK);
@@ -581,9 +797,10 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
     const char* e = getenv("BHMC_PERSIST_FLAGS");
     flags_env = e ? atoi(e) : 1;
   }
-  p.flags = flags_env ? reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(bar) + 256) : nullptr;
+  p.flags = (flags_env || two_cta) ? reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(bar) + 256) : nullptr;
+  p.two_cta = two_cta ? 1 : 0;
   const int items = std::max((half_f ? 2 : 1) * (int)(Mfwd / BM) * n_tiles, p.m_tiles_b * n_tiles);
-  const int grid = std::min(items, ctx->sm_count);
+  const int grid = two_cta ? 2 * pairs_max * n_tiles : std::min(items, ctx->sm_count);
   static int want_prof = -1, want_pf = -1;
   if (want_prof < 0) want_prof = getenv("BHMC_PROF") ? 1 : 0;
   if (want_pf < 0) {
