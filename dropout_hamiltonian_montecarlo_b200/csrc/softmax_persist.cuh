@@ -117,9 +117,55 @@ __device__ __forceinline__ void flag_signal(unsigned int* f) {
 // gradient rows go through a per-warp shared-memory block and the update runs in the memory order: one float4 per lane
 // and instruction (coalesced q / p traffic, one Philox block per float4 -- the keys of k_sgld, element for element);
 // the new weights go back through the same block for the K-major bf16 operand copy, which IS row-ordered.
+// The noise (SGLD) / momentum (SGD) operand of the update does not depend on the gradient: it is produced while the
+// epilogue warps would otherwise wait for the accumulator (Philox + Box-Muller were ~4 k of the ~10 k cycles of a
+// backward item's epilogue, on the critical path of every step).  Slot [ci][fi]: chain part + ci*PARTS of the tile,
+// float4 index 32*fi + lane of the warp's block -- the loops of sg_update_tile.
+template <int KP>
+struct SgPre {
+  static constexpr int NF = (32 * KP / 4 + 31) / 32;
+  float4 z[2][NF];  // at most two chains per warp (cpt <= 8 with EW = 16)
+};
 template <int KP, int EW, int KIND>
+__device__ __forceinline__ void sg_update_pre(const PersistParams& p, int mt, int nt, int part, int ew, int lane, int step,
+                                              SgPre<KP>& pre) {
+  constexpr int PARTS = EW / 4;
+  constexpr int NV = 32 * KP / 4;
+  const int64_t P = (int64_t)(p.D + 1) * KP;
+  const int64_t i0w = (int64_t)(mt * BM + ew * 32) * KP;
+  const uint64_t gstep = p.step0 + (uint64_t)step;
+  const uint32_t slo = (uint32_t)gstep, shi = TAG_NOISE | (uint32_t)((gstep >> 32) & 0xffffff);
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int cc = part + ci * PARTS, c = nt * p.cpt + cc;
+#pragma unroll
+    for (int fi = 0; fi < SgPre<KP>::NF; ++fi) {
+      const int f = 32 * fi + lane;
+      const int64_t gi = i0w + 4 * f;
+      float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cc < p.cpt && c < p.C && f < NV && gi < P) {
+        if (KIND == BHMC_KIND_SGLD) {
+          if (p.z) {
+            const float* zr = p.z + (int64_t)step * p.z_step_stride + (int64_t)c * p.ld_z + gi;
+            z4.x = __ldcs(zr);
+            z4.y = gi + 1 < P ? __ldcs(zr + 1) : 0.f;
+            z4.z = gi + 2 < P ? __ldcs(zr + 2) : 0.f;
+            z4.w = gi + 3 < P ? __ldcs(zr + 3) : 0.f;
+          } else {
+            z4 = philox_normal4(p.seed, p.chain_id0 + c, (uint32_t)(gi >> 2), slo, shi);
+          }
+        } else {
+          z4 = __ldcg(reinterpret_cast<const float4*>(p.p + (int64_t)c * p.ld + gi));  // heavy-ball momentum (this thread wrote it)
+        }
+      }
+      pre.z[ci][fi] = z4;
+    }
+  }
+}
+
+template <int KP, int EW, int KIND, bool PRE = false>
 __device__ __forceinline__ void sg_update_tile(const PersistParams& p, uint32_t tacc, int mt, int nt, int part, int ew, int lane,
-                                               int step, float eps, float* S) {
+                                               int step, float eps, float* S, const SgPre<KP>* pre = nullptr) {
   constexpr int PARTS = EW / 4;
   constexpr int NV = 32 * KP / 4;  // float4s of a warp's block
   const int d = mt * BM + ew * 32 + lane;
@@ -127,7 +173,10 @@ __device__ __forceinline__ void sg_update_tile(const PersistParams& p, uint32_t 
   const int64_t i0w = (int64_t)(mt * BM + ew * 32) * KP;  // first parameter of the warp's block (multiple of 32)
   const uint64_t gstep = p.step0 + (uint64_t)step;
   const uint32_t slo = (uint32_t)gstep, shi = TAG_NOISE | (uint32_t)((gstep >> 32) & 0xffffff);
-  for (int cc = part; cc < p.cpt; cc += PARTS) {
+#pragma unroll 2
+  for (int ci = 0; ci < (PRE ? 2 : 64); ++ci) {
+    const int cc = part + ci * PARTS;
+    if (cc >= p.cpt) break;
     const int c = nt * p.cpt + cc;
     if (c >= p.C) break;  // warp-uniform
     uint32_t raw[KP];
@@ -146,7 +195,9 @@ __device__ __forceinline__ void sg_update_tile(const PersistParams& p, uint32_t 
         const float4 q4 = __ldcg(reinterpret_cast<const float4*>(qc + gi));  // L2: another SM wrote it one step ago
         const float4 g4 = *reinterpret_cast<const float4*>(S + 4 * f);
         float4 z4;
-        if (KIND == BHMC_KIND_SGLD) {
+        if (PRE) {
+          z4 = pre->z[ci < 2 ? ci : 0][f0 / 32];
+        } else if (KIND == BHMC_KIND_SGLD) {
           if (p.z) {
             const float* zr = p.z + (int64_t)step * p.z_step_stride + (int64_t)c * p.ld_z + gi;
             z4.x = __ldcs(zr);
@@ -626,12 +677,19 @@ k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_const
       for (int w = wi0; w < items_b; w += wi_step, ++it) {
         const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
         const int buf = it & 1;
+        SgPre<KP> pre;  // noise / momentum of the update, produced while the accumulator is still being computed
+        if (mt < p.m_tiles_b) {
+          if (p.kind == BHMC_KIND_SGLD) sg_update_pre<KP, EW, BHMC_KIND_SGLD>(p, mt, nt, part, ew, lane, step, pre);
+          else sg_update_pre<KP, EW, BHMC_KIND_SGD>(p, mt, nt, part, ew, lane, step, pre);
+        }
         mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
         if (mt < p.m_tiles_b) {  // (a phantom tile has no gradient rows)
-          if (p.kind == BHMC_KIND_SGLD) sg_update_tile<KP, EW, BHMC_KIND_SGLD>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S);
-          else sg_update_tile<KP, EW, BHMC_KIND_SGD>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S);
+          if (p.kind == BHMC_KIND_SGLD)
+            sg_update_tile<KP, EW, BHMC_KIND_SGLD, true>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S, &pre);
+          else
+            sg_update_tile<KP, EW, BHMC_KIND_SGD, true>(p, tacc, mt, nt, part, ew, lane, step, eps, epi_S, &pre);
         }
         tcgen05_fence_before();
         if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
