@@ -108,6 +108,9 @@ __device__ __forceinline__ void flag_signal(unsigned int* f) {
     atomicAdd(f, 1u);
   }
 }
+// (A per-warp form -- every epilogue warp fences and bumps the counter itself, no CTA-wide barrier in front of the release --
+// was measured: the signals cost the same 5.2 k cycles per step and the step got slower and erratic, 26-52 us against
+// 24.5: sixteen times the atomics on the line the consumers poll.)
 
 // Update epilogue of one backward tile.  Tensor memory hands a thread one gradient ROW (feature d; d == D is the bias
 // row) with the KP classes of a chain, while a chain's parameters are stored row-major (i = d*K + k): a warp's 32 rows
@@ -625,6 +628,16 @@ k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_const
   pf.dm_slab = BK, pf.dm_slab_rows = p.dm_rows, pf.dm_ld = BK, pf.dmt_hi = p.dmt_hi, pf.dmt_lo = p.dmt_lo;
   pf.split3 = p.split3, pf.write_dm = 1, pf.m_tiles = m_tiles_f, pf.skip_loglik = 1;
 
+  // BHMC_PROF=1: cycles of the first epilogue thread per segment (sums over the steps) and of the producer's flag waits
+  const bool timer = p.prof && threadIdx.x == NON_EPI_THREADS;
+  long long tp[7] = {0, 0, 0, 0, 0, 0, 0}, t_prev = timer ? clock64() : 0, t_flag = 0;
+  auto lap = [&](int i) {
+    if (timer) {
+      const long long t = clock64();
+      tp[i] += t - t_prev;
+      t_prev = t;
+    }
+  };
   for (int step = 0; step < p.n_steps; ++step) {
     const int64_t row0 = p.row_first + (int64_t)step * p.batch;
     const int shift = (int)(row0 % BK);
@@ -634,7 +647,9 @@ k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_const
       if (lane == 0)
         for (int w = wi0; w < items_f; w += wi_step) {
           const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+          const long long tf0 = p.prof ? clock64() : 0;
           if (step > 0) flag_wait(p.flags + p.n_tiles + nt, (unsigned int)(2 * pairs_b * step));  // W^T / bias of step - 1
+          if (p.prof) t_flag += clock64() - tf0;
           produce(&tmXa_hi, &tmXa_lo, &tmWt_hi, &tmWt_lo, p.k_chunks_f, 0, BK, (int)row0 + mt * BM, 0, 0, BK,
                   nt * p.BN + rank * (p.BN / 2), 0);
         }
@@ -648,14 +663,18 @@ k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_const
       for (int w = wi0; w < items_f; w += wi_step, ++it) {
         const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
         const int buf = it & 1;
+        lap(6);
         mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
+        lap(0);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
         if (mt < m_tiles_f) fwd_epilogue_tile<KP, EW, true>(pf, tacc, mt, nt, part, lane, t);
         tcgen05_fence_before();
         if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
         else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
+        lap(1);
         flag_signal<EW>(p.flags + nt);
+        lap(2);
       }
     }
     // ---------------- phase B ----------------
@@ -664,7 +683,9 @@ k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_const
         const int slab0 = (int)((row0 - shift) / BK);
         for (int w = wi0; w < items_b; w += wi_step) {
           const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
+          const long long tf0 = p.prof ? clock64() : 0;
           flag_wait(p.flags + nt, (unsigned int)(2 * pairs_f * (step + 1)));  // (P-Y)^T of this step
+          if (p.prof) t_flag += clock64() - tf0;
           produce(&tmXt_hi, &tmXt_lo, &tmDm_hi, &tmDm_lo, k_chunks_b, 0, 0, slab0 * p.xt_rows + mt * BM, p.xt_rows, 0, 0,
                   nt * p.BN + rank * (p.BN / 2), p.dm_rows);
         }
@@ -678,11 +699,14 @@ k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_const
         const int mt = 2 * (w / p.n_tiles) + rank, nt = w % p.n_tiles;
         const int buf = it & 1;
         SgPre<KP> pre;  // noise / momentum of the update, produced while the accumulator is still being computed
+        lap(6);
         if (mt < p.m_tiles_b) {
           if (p.kind == BHMC_KIND_SGLD) sg_update_pre<KP, EW, BHMC_KIND_SGLD>(p, mt, nt, part, ew, lane, step, pre);
           else sg_update_pre<KP, EW, BHMC_KIND_SGD>(p, mt, nt, part, ew, lane, step, pre);
         }
+        lap(3);
         mbar_wait(smem_u32(&bar_tfull[buf]), (uint32_t)(it >> 1) & 1u);
+        lap(4);
         tcgen05_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TMEM_BUF_COLS);
         if (mt < p.m_tiles_b) {  // (a phantom tile has no gradient rows)
@@ -694,10 +718,17 @@ k_sg_persistent2(const __grid_constant__ CUtensorMap tmXa_hi, const __grid_const
         tcgen05_fence_before();
         if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
         else mbar_arrive_remote(smem_u32(&bar_tempty[buf]), 0);
+        lap(5);
         flag_signal<EW>(p.flags + p.n_tiles + nt);
+        lap(2);
       }
     }
   }
+  if (timer) {  // [0] wait F accumulator, [1] F epilogue, [2] flag signals, [3] noise, [4] wait B accumulator, [5] update epilogue, [6] rest
+    long long* o = p.prof + (size_t)blockIdx.x * 8;
+    for (int i = 0; i < 7; ++i) o[i] = tp[i];
+  }
+  if (p.prof && warp == 0 && lane == 0) p.prof[(size_t)blockIdx.x * 8 + 7] = t_flag;
   tcgen05_fence_before();
   cluster_sync_all();
   if (warp == 2) {
@@ -882,7 +913,26 @@ int tc_softmax_sg_persistent(bhmc_ctx* ctx, const SoftmaxData& d, int C, int64_t
       case 16: rc = launch_sg_persistent<16>(ctx, maps, p, grid, smem); break;
     }
   }
-  if (want_prof && rc == BHMC_OK) {
+  if (want_prof && rc == BHMC_OK && two_cta) {
+    std::vector<long long> hp(8 * 148);
+    BHMC_CUDA_OK(cudaMemcpyAsync(hp.data(), prof_dev, sizeof(long long) * 8 * 148, cudaMemcpyDeviceToHost, ctx->stream));
+    BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    double sF[8] = {0}, sA[8] = {0};
+    int nF = 0, nA = 0;
+    const int f_ctas = 2 * (((int)(Mfwd / BM) + 1) / 2) * n_tiles;  // CTAs that own a forward item
+    for (int b = 0; b < grid && b < 148; ++b) {
+      for (int j = 0; j < 8; ++j) (b < f_ctas ? sF[j] : sA[j]) += (double)hp[b * 8 + j] / n_steps;
+      (b < f_ctas ? nF : nA)++;
+    }
+    const char* names[8] = {"wait F acc", "F epilogue", "flag signals", "noise", "wait B acc", "update epilogue", "rest", "producer flag waits"};
+    for (int g2 = 0; g2 < 2; ++g2) {
+      const int n = g2 ? nA : nF;
+      if (!n) continue;
+      fprintf(stderr, "[bhmc prof persist2] %d CTAs %s, cycles per step:", n, g2 ? "with a backward item only" : "with forward + backward items");
+      for (int j = 0; j < 8; ++j) fprintf(stderr, " %s %.0f;", names[j], (g2 ? sA[j] : sF[j]) / n);
+      fprintf(stderr, "\n");
+    }
+  } else if (want_prof && rc == BHMC_OK) {
     std::vector<long long> hp(8 * 148);
     BHMC_CUDA_OK(cudaMemcpyAsync(hp.data(), prof_dev, sizeof(long long) * 8 * 148, cudaMemcpyDeviceToHost, ctx->stream));
     BHMC_CUDA_OK(cudaStreamSynchronize(ctx->stream));
