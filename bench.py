@@ -466,7 +466,7 @@ def _group_roofline(ctx, run_once, flops_per_launch, peak_tf, names=("fwd", "bwd
         # backward GEMMs and the updates of all its steps -- it is timed under the forward group and there is no
         # separate backward launch; its algorithmic work is both GEMMs of every step of the launch
         flops = persistent_flops / t[0][1]
-        label = "k_sg_persistent (forward + backward GEMM + update of every step of an epoch in one launch)"
+        label = "k_sg_persistent2 (cta_group::2 forward + backward GEMM + update of every step of an epoch in one cooperative launch; k_sg_persistent where the shape has no pair form)"
     achieved = flops / avg / 1e12 if avg > 0 else 0.0
     return {"bound": "tensor", "kernel_group": label, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved / peak_tf, "avg_launch_ms": avg * 1e3, "algorithmic_flops_per_launch": flops,
