@@ -486,12 +486,12 @@ def bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf, epochs=5):
     # ---- SGLD: one library call runs whole epochs
     s = SamplerHandle(ctx, h, KIND["sgld"], C, seed=1, chain_id0=rank * C, precision=PREC[prec])
     s.set_q(np.zeros((C, h.P), np.float32))
-    s.sg_run(0, 1, B, 1e-5, n_rows=N)  # warm-up epoch (burn-in: constant step size)
+    s.sg_run(1, 1, B, 1e-5, n_rows=N)  # warm-up: one burn-in and one sampling epoch (sample store and per-epoch NLP touched once)
     l0 = ctx.launches
-    ms, o = _timed(world, lambda: s.sg_run(epochs, 0, B, 1e-5, n_rows=N, step0=nb))
+    ms, o = _timed(world, lambda: s.sg_run(epochs, 0, B, 1e-5, n_rows=N, step0=2 * nb))
     launches = ctx.launches - l0
     ms, n = _agg_time_count(dev, world, ms, o["n_grad_evals"])
-    roof = _group_roofline(ctx, lambda: s.sg_run(1, 0, B, 1e-5, n_rows=N, step0=nb * (epochs + 1)),
+    roof = _group_roofline(ctx, lambda: s.sg_run(1, 0, B, 1e-5, n_rows=N, step0=nb * (epochs + 2)),
                            {0: flops_gemm, 1: flops_gemm}, peak_tf, persistent_flops=2.0 * flops_gemm * nb)
     out["sgld"] = {"value": n / (ms * 1e-3), "ms_per_step": ms / (epochs * nb), "steps": epochs * nb,
                    "step": "one minibatch update of every chain (gradient + Philox noise + update)",
