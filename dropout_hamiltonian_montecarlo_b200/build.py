@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
         src, obj = job
         r = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
         with open(obj[:-2] + ".ptxas.log", "w") as f:
-            f.write(r.stderr)
+            # tracked next to the sources (registers / spills per kernel); compile times would change with every build
+            f.write("".join(l for l in r.stderr.splitlines(True) if "Compile time" not in l))
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr[-4000:]))
         if verbose:

@@ -755,9 +755,20 @@ static int launch_sg_persistent(bhmc_ctx* ctx, const CUtensorMap* maps, const Pe
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeCooperative;  // every CTA resident: the grid barrier cannot deadlock
-  attr[0].val.cooperative = 1;
-  int na = 1;
+  // BHMC_PERSIST_NOCOOP=1 (profiling only): ncu 2025.x fails the cooperative + cluster launch of k_sg_persistent2 with
+  // LaunchFailed before the kernel runs (grid and block reported as 0); without the attribute the launch profiles.  The grid
+  // is at most one CTA per SM, so on an otherwise idle device (ncu serialises kernels) every CTA is still resident.
+  static int nocoop = -1;
+  if (nocoop < 0) {
+    const char* e = getenv("BHMC_PERSIST_NOCOOP");
+    nocoop = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  int na = 0;
+  if (!nocoop) {
+    attr[na].id = cudaLaunchAttributeCooperative;  // every CTA resident: the grid barrier / flag waits cannot deadlock
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
   if (p.pair || p.two_cta) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;

@@ -7,6 +7,8 @@
 #   tools/gpu_session.sh ref                          reference arm
 #   tools/gpu_session.sh launches <tag> -- <cmd>      ncu launch list (gpu__time_duration.sum) of a command
 #   tools/gpu_session.sh ncu <tag> <kernel regex> <skip> <count> -- <cmd>   ncu --set full capture of matching kernels
+#   tools/gpu_session.sh ncuhw <tag> <kernel regex> <skip> <count> -- <cmd>  same with the hardware-counter sections only
+#                                                     (no SASS patching: what a cooperative persistent kernel survives)
 #   tools/gpu_session.sh ab <VAR> <v1,v2,..> -- <cmd> run a command once per value of an environment switch
 #   tools/gpu_session.sh sanitize <tool> -- <cmd>     compute-sanitizer (memcheck | racecheck | synccheck | initcheck)
 set -u
@@ -53,6 +55,13 @@ case $sub in
     tag=$1; regex=$2; skip=$3; count=$4; shift 4; [ "$1" = "--" ] && shift
     timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$regex" -s $skip -c $count -f -o $O/ncu_$tag "$@" > $O/ncu_$tag.log 2>&1
     echo "ncu full rc=$?"; tail -3 $O/ncu_$tag.log ;;
+  ncuhw)
+    tag=$1; regex=$2; skip=$3; count=$4; shift 4; [ "$1" = "--" ] && shift
+    timeout 600 ncu --section LaunchStats --section Occupancy --section SpeedOfLight --section MemoryWorkloadAnalysis \
+      --section ComputeWorkloadAnalysis --section SchedulerStats --section WarpStateStats \
+      --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum \
+      --clock-control none -k "regex:$regex" -s $skip -c $count -f -o $O/ncu_$tag "$@" > $O/ncu_$tag.log 2>&1
+    echo "ncu hw rc=$?"; tail -3 $O/ncu_$tag.log ;;
   ab)
     var=$1; vals=$2; shift 2; [ "$1" = "--" ] && shift
     for v in ${vals//,/ }; do echo "== $var=$v"; env $var=$v "$@" 2>&1 | tail -${BHMC_AB_TAIL:-2}; done ;;
