@@ -22,7 +22,7 @@ backward GEMM), Metropolis test, sample store.
            against the measured sustained bf16 peak.
 `cpu_baseline`: the NumPy oracle port of the reference path (fp64, BLAS threads = host cores) on a
            bounded sample of the same workload, same box; plus ESS/s of the CPU arm with the same
-           estimator on the small-N variant SURVEY 8(d) names.
+           estimator on the small-N variant SURVEY 8(d) names.  Rank 0 at N = 1 only.
 
 The other BASELINE configs ride on the same JSON line as secondary blocks (driver-visible, each with its
 own value / ms_per_step / roofline):
@@ -893,7 +893,8 @@ def run_ours(args, wl):
         traffic, traffic_src = ncu_traffic(dom, prec, wl, u_dom / max(1, n_dom))
         x_exact, x_scale = h.operand_info()
         mma_mult = (2.0 if x_exact else 3.0) if prec == "bf16x3" else 1.0
-        cpu = None if args.no_cpu_baseline else cpu_reference_rate(wl)
+        # the CPU leg runs at N = 1 only (rank 0 alone owns the host cores there; at N > 1 the other ranks would wait for it)
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_reference_rate(wl)
         if cpu is not None and not args.no_ess:
             cpu["ess"] = cpu_ess_small()
         line = {
