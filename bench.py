@@ -473,7 +473,7 @@ def _group_roofline(ctx, run_once, flops_per_launch, peak_tf, names=("fwd", "bwd
             "groups": groups, "timing": "one extra pass, every kernel group bracketed by CUDA events on the launching stream"}
 
 
-def bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf, epochs=5):
+def bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf, epochs=20, warm=4):
     """BASELINE configs[2]: SGLD and SGHMC softmax on sequential minibatches of 500, 128 chains per GPU (1024 chains
     over 8 GPUs; chains shard with no collective -> weak scaling).  sgld.py:31-46 / sghmc.py:19-39 + sgmcmc.py:40-86."""
     from dropout_hamiltonian_montecarlo_b200._lib import KIND, PREC
@@ -486,12 +486,14 @@ def bench_cfg3(ctx, h, X, y, rank, world, dev, prec, peak_tf, epochs=5):
     # ---- SGLD: one library call runs whole epochs
     s = SamplerHandle(ctx, h, KIND["sgld"], C, seed=1, chain_id0=rank * C, precision=PREC[prec])
     s.set_q(np.zeros((C, h.P), np.float32))
-    s.sg_run(1, 1, B, 1e-5, n_rows=N)  # warm-up: one burn-in and one sampling epoch (sample store and per-epoch NLP touched once)
+    # warm-up: one burn-in and `warm` sampling epochs (sample store and per-epoch NLP touched; a 3 ms epoch is too short to
+    # settle the clocks after the host-side gap between the blocks: single 5-epoch timings spread 24-32 us per step)
+    s.sg_run(warm, 1, B, 1e-5, n_rows=N)
     l0 = ctx.launches
-    ms, o = _timed(world, lambda: s.sg_run(epochs, 0, B, 1e-5, n_rows=N, step0=2 * nb))
+    ms, o = _timed(world, lambda: s.sg_run(epochs, 0, B, 1e-5, n_rows=N, step0=(warm + 1) * nb))
     launches = ctx.launches - l0
     ms, n = _agg_time_count(dev, world, ms, o["n_grad_evals"])
-    roof = _group_roofline(ctx, lambda: s.sg_run(1, 0, B, 1e-5, n_rows=N, step0=nb * (epochs + 2)),
+    roof = _group_roofline(ctx, lambda: s.sg_run(1, 0, B, 1e-5, n_rows=N, step0=nb * (epochs + warm + 1)),
                            {0: flops_gemm, 1: flops_gemm}, peak_tf, persistent_flops=2.0 * flops_gemm * nb)
     out["sgld"] = {"value": n / (ms * 1e-3), "ms_per_step": ms / (epochs * nb), "steps": epochs * nb,
                    "step": "one minibatch update of every chain (gradient + Philox noise + update)",
