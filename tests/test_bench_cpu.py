@@ -57,3 +57,14 @@ def test_committed_traffic_file_is_readable():
     t = json.load(open(p))
     for k, e in t.items():
         assert {"chains_per_launch", "dram_bytes", "source"} <= set(e), k
+
+
+def test_reference_arm_under_torchrun_only_rank0_works():
+    """Contract of the reference arm at N > 1: rank 0 alone runs and prints, the other ranks exit 0 without work."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
