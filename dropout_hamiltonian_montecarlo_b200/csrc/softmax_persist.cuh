@@ -755,7 +755,7 @@ static int launch_sg_persistent(bhmc_ctx* ctx, const CUtensorMap* maps, const Pe
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[2];
-  // BHMC_PERSIST_NOCOOP=1 (profiling only): ncu 2025.x fails the cooperative + cluster launch of k_sg_persistent2 with
+  // BHMC_PERSIST_NOCOOP=1 (profiling only): ncu 2025.2.1 fails the cooperative + cluster launch of k_sg_persistent2 with
   // LaunchFailed before the kernel runs (grid and block reported as 0); without the attribute the launch profiles.  The grid
   // is at most one CTA per SM, so on an otherwise idle device (ncu serialises kernels) every CTA is still resident.
   static int nocoop = -1;
